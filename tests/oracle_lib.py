@@ -1,0 +1,226 @@
+"""ctypes bindings for the CPU oracle (oracle/liboracle.so) and, when it was built, the real
+reference behind its flat C wrapper (oracle/_ref/libhohref.so).
+
+TEST INFRASTRUCTURE: imported only from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libhohref.so")
+
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+sz = C.c_size_t
+
+
+def build_oracle(force=False):
+    """Compile oracle/ (and oracle/_ref when /root/reference is present)."""
+    src = [os.path.join(ORACLE_DIR, f) for f in ("hoh_oracle.c", "hoh_oracle.h")]
+    stale = (not os.path.exists(ORACLE_SO)) or any(
+        os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in src)
+    if force or stale:
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+    ref_src = os.path.join(ORACLE_DIR, "ref_wrap.cpp")
+    if os.path.exists("/root/reference/choh.cpp"):
+        if force or not os.path.exists(REF_SO) or os.path.getmtime(ref_src) > os.path.getmtime(REF_SO):
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        L.orc_write_varint.restype = sz
+        L.orc_write_varint.argtypes = [u8p, sz, sz]
+        L.orc_normalize_freqs.restype = C.c_int
+        L.orc_normalize_freqs.argtypes = [u32p, u32p, sz, C.c_uint32]
+        L.orc_encode_entropy.restype = sz
+        L.orc_encode_entropy.argtypes = [u16p, sz, sz, u8p, C.c_uint32, C.POINTER(C.c_int)]
+        L.orc_decode_entropy.restype = sz
+        L.orc_decode_entropy.argtypes = [u8p, sz, C.POINTER(sz), u16p, sz, C.c_uint, C.POINTER(C.c_int)]
+        L.orc_rans_encode_static.restype = sz
+        L.orc_rans_encode_static.argtypes = [u16p, sz, u32p, u32p, sz, C.c_uint32, u8p]
+        L.orc_rans_decode_static.restype = None
+        L.orc_rans_decode_static.argtypes = [u8p, sz, sz, u32p, u32p, sz, C.c_uint32, u16p]
+        L.orc_subtract_green.restype = None
+        L.orc_subtract_green.argtypes = [u8p, sz, u16p, u16p, u16p]
+        L.orc_channel_picker.restype = None
+        L.orc_channel_picker.argtypes = [u8p, sz, C.c_int, C.c_int, u16p]
+        L.orc_add_green.restype = None
+        L.orc_add_green.argtypes = [u16p, u16p, u16p, sz, u8p]
+        L.orc_predict_fastpath.restype = sz
+        L.orc_predict_fastpath.argtypes = [u16p, C.c_int, C.c_int, C.c_int, u16p]
+        L.orc_predict_section.restype = sz
+        L.orc_predict_section.argtypes = [u16p, C.c_int, C.c_int, C.c_int, sz, sz, C.c_int, C.c_int,
+                                          C.c_uint16, u16p]
+        L.orc_predict_all.restype = None
+        L.orc_predict_all.argtypes = [u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u16p, u16p]
+        L.orc_unpredict_all.restype = None
+        L.orc_unpredict_all.argtypes = [u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u16p,
+                                        C.c_void_p, u16p]
+        L.orc_unpredict_fastpath.restype = None
+        L.orc_unpredict_fastpath.argtypes = [u16p, C.c_int, C.c_int, C.c_int, C.c_void_p, u16p]
+        L.orc_layer_encode.restype = sz
+        L.orc_layer_encode.argtypes = [u16p, sz, C.c_int, C.c_int, C.c_int, sz, u8p, u8p,
+                                       C.POINTER(C.c_int)]
+        L.orc_predictor_search.restype = sz
+        L.orc_predictor_search.argtypes = [u16p, sz, C.c_int, C.c_int, C.c_int, sz, u16p, u8p, C.c_void_p]
+        L.orc_synth_rgb.restype = None
+        L.orc_synth_rgb.argtypes = [u8p, C.c_int, C.c_int, C.c_uint64]
+        L.orc_synth_symbols.restype = None
+        L.orc_synth_symbols.argtypes = [u8p, sz, C.c_uint64]
+        for name in ("orc_midpoint", "orc_median", "orc_average3", "orc_paeth"):
+            f = getattr(L, name)
+            f.restype = C.c_uint16
+            f.argtypes = [C.c_uint16] * (2 if name == "orc_midpoint" else 3)
+        _oracle = L
+    return _oracle
+
+
+def have_ref():
+    build_oracle()
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        build_oracle()
+        L = C.CDLL(REF_SO)
+        L.ref_encode_entropy.restype = sz
+        L.ref_encode_entropy.argtypes = [u16p, sz, sz, u8p, C.c_uint32]
+        L.ref_decode_entropy.restype = sz
+        L.ref_decode_entropy.argtypes = [u8p, sz, C.POINTER(sz), u16p, sz]
+        L.ref_normalize_freqs.restype = None
+        L.ref_normalize_freqs.argtypes = [u32p, u32p, sz, C.c_uint32]
+        L.ref_subtract_green.restype = None
+        L.ref_subtract_green.argtypes = [u8p, sz, u16p, u16p, u16p]
+        L.ref_channel_picker.restype = None
+        L.ref_channel_picker.argtypes = [u8p, sz, C.c_int, C.c_int, u16p]
+        L.ref_predict_fastpath.restype = sz
+        L.ref_predict_fastpath.argtypes = [u16p, sz, C.c_int, C.c_int, C.c_int, u16p]
+        L.ref_predict_section.restype = sz
+        L.ref_predict_section.argtypes = [u16p, sz, C.c_int, C.c_int, C.c_int, sz, sz, C.c_int, C.c_int,
+                                          C.c_uint16, u16p]
+        L.ref_predict_all.restype = None
+        L.ref_predict_all.argtypes = [u16p, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u16p, u16p]
+        L.ref_unpredict_all.restype = None
+        L.ref_unpredict_all.argtypes = [u16p, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u16p,
+                                        u16p, u16p]
+        L.ref_layer_encode.restype = sz
+        L.ref_layer_encode.argtypes = [u16p, sz, C.c_int, C.c_int, C.c_int, sz, u8p, u8p]
+        L.ref_decode_layer.restype = None
+        L.ref_decode_layer.argtypes = [u8p, sz, sz, sz, sz, C.c_uint8, u16p, u8p]
+        L.ref_encode_tile.restype = sz
+        L.ref_encode_tile.argtypes = [u8p, sz, u8p, C.c_int, C.c_int, sz]
+        L.ref_find_lz_rgb.restype = sz
+        L.ref_find_lz_rgb.argtypes = [u8p, sz, C.c_int, C.c_int, u8p, u8p, C.c_int, C.c_int]
+        L.ref_count_colours.restype = C.c_int
+        L.ref_count_colours.argtypes = [u8p, sz]
+        L.ref_choh_main.restype = C.c_int
+        L.ref_choh_main.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        L.ref_rans_encode_static.restype = sz
+        L.ref_rans_encode_static.argtypes = [u16p, sz, u32p, u32p, sz, C.c_uint32, u8p]
+        L.ref_rans_decode_static.restype = None
+        L.ref_rans_decode_static.argtypes = [u8p, sz, sz, u32p, u32p, sz, C.c_uint32, u16p]
+        _ref = L
+    return _ref
+
+
+# ---------------------------------------------------------------------------------------------
+# numpy-level helpers (oracle side)
+# ---------------------------------------------------------------------------------------------
+
+def out_capacity(n, range_):
+    return 2048 + 4 * range_ + 4 * n
+
+
+def orc_encode_entropy(symbols, range_, prob_bits):
+    symbols = np.ascontiguousarray(symbols, dtype=np.uint16)
+    out = np.zeros(out_capacity(len(symbols), range_), np.uint8)
+    st = C.c_int(0)
+    n = oracle().orc_encode_entropy(symbols, len(symbols), range_, out, prob_bits, C.byref(st))
+    return out[:n].copy(), st.value
+
+
+def ref_encode_entropy(symbols, range_, prob_bits):
+    symbols = np.ascontiguousarray(symbols, dtype=np.uint16)
+    out = np.zeros(out_capacity(len(symbols), range_), np.uint8)
+    n = ref().ref_encode_entropy(symbols, len(symbols), range_, out, prob_bits)
+    return out[:n].copy()
+
+
+def orc_decode_entropy(stream, pos=0, flags=7, cap=1 << 22):
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    padded = np.concatenate([stream, np.zeros(16, np.uint8)])
+    out = np.zeros(cap, np.uint16)
+    bp = sz(pos)
+    st = C.c_int(0)
+    n = oracle().orc_decode_entropy(padded, len(stream), C.byref(bp), out, cap, flags, C.byref(st))
+    return out[:n].copy(), bp.value, st.value
+
+
+def ref_decode_entropy(stream, pos=0, cap=1 << 22):
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    padded = np.concatenate([stream, np.zeros(16, np.uint8)])
+    out = np.zeros(cap, np.uint16)
+    bp = sz(pos)
+    n = ref().ref_decode_entropy(padded, len(stream), C.byref(bp), out, cap)
+    return out[:n].copy(), bp.value
+
+
+def peek_stream(stream, pos=0):
+    """(range, n, entropy_mode, prob_bits(5-bit), table_mode) of the stream header at `pos`."""
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    r, n = sz(0), sz(0)
+    em, pb, tm = C.c_int(0), C.c_int(0), C.c_int(0)
+    f = oracle().orc_peek_stream
+    f.restype = None
+    f.argtypes = [u8p, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                  C.POINTER(C.c_int)]
+    f(stream, pos, C.byref(r), C.byref(n), C.byref(em), C.byref(pb), C.byref(tm))
+    return r.value, n.value, em.value, pb.value, tm.value
+
+
+def synth_rgb(w, h, seed):
+    a = np.zeros(w * h * 3, np.uint8)
+    oracle().orc_synth_rgb(a, w, h, seed)
+    return a
+
+
+def synth_symbols(n, seed):
+    a = np.zeros(n, np.uint8)
+    oracle().orc_synth_symbols(a, n, seed)
+    return a
+
+
+def orc_layer_encode(plane, w, h, depth, mode, nuke=None):
+    plane = np.ascontiguousarray(plane, dtype=np.uint16)
+    if nuke is None:
+        nuke = np.zeros(plane.size, np.uint8)
+    out = np.zeros(plane.size * 4 + 4096, np.uint8)
+    trace = (C.c_int * 4)()
+    n = oracle().orc_layer_encode(plane, plane.size, w, h, depth, mode, nuke, out, trace)
+    return out[:n].copy(), list(trace)
+
+
+def ref_layer_encode(plane, w, h, depth, mode, nuke=None):
+    plane = np.ascontiguousarray(plane, dtype=np.uint16)
+    if nuke is None:
+        nuke = np.zeros(plane.size, np.uint8)
+    out = np.zeros(plane.size * 4 + 4096, np.uint8)
+    n = ref().ref_layer_encode(plane, plane.size, w, h, depth, mode, nuke, out)
+    return out[:n].copy()
