@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""bench.py — hoh-ANS hot path on B200: raw RGB MB/s, encode + decode, cruncher mode 0.
+
+Workload (BASELINE.json configs[1]): a batch of 4096 synthetic 512x512 RGB images per GPU at -s0.
+One "step" = encode the whole batch (RGB -> channel payloads + offset table) and decode it back
+(payloads -> RGB).  `value` counts every raw byte once per direction:
+    value = 2 * raw_bytes_all_ranks / (t_encode + t_decode)      [MB/s, 1 MB = 1e6 B]
+with inputs already resident in HBM; `e2e` is the same metric through the host-buffer C-ABI calls
+(hoh_encode_images_s0_host / hoh_decode_images_s0_host) with H2D/D2H inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+N > 1: launched by torchrun, one rank per GPU, images sharded by index, no data-path collective.
+"""
+import argparse
+import ctypes as C
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+W = H = 512
+MODE = 0
+
+
+def _load(name, path):
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs (tools/synth_gen.c)
+# ------------------------------------------------------------------------------------------------
+def synth_lib():
+    so = os.path.join(ROOT, "tools", "libsynth.so")
+    src = os.path.join(ROOT, "tools", "synth_gen.c")
+    if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", so, src])
+    L = C.CDLL(so)
+    L.synth_rgb_batch.restype = None
+    L.synth_rgb_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_size_t]
+    return L
+
+
+def fill_images(dst, first_seed, count, w, h, threads):
+    """dst: uint8 array of count*w*h*3; image i uses seed first_seed + i."""
+    L = synth_lib()
+    per = w * h * 3
+    base = dst.ctypes.data
+    chunk = max(1, (count + threads - 1) // threads)
+    jobs = []
+    for lo in range(0, count, chunk):
+        n = min(chunk, count - lo)
+        t = threading.Thread(target=L.synth_rgb_batch, args=(base + lo * per, w, h, first_seed + lo, n))
+        t.start()
+        jobs.append(t)
+    for t in jobs:
+        t.join()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = f"/tmp/hoh_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own hot path (oracle/_ref, else the oracle port) on host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    first_seed, count, w, h = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    use_ref = ol.have_ref()
+    R = ol.ref() if use_ref else None
+    O = ol.oracle()
+    rgb = np.zeros(count * w * h * 3, np.uint8)
+    synth_lib().synth_rgb_batch(rgb.ctypes.data, w, h, first_seed, count)
+    gpu_mod = _load("hohgpu", os.path.join(ROOT, "hoh-ans_b200", "host", "hohgpu.py"))
+    lib = gpu_mod.load_library()  # hoh_tile_geometry_for is pure host arithmetic (choh.cpp:454-460)
+    g = gpu_mod.TileGeometry()
+    lib.hoh_tile_geometry_for(w, h, C.byref(g))
+    t_enc = t_dec = 0.0
+    nuke = np.zeros(g.tile_w * g.tile_h, np.uint8)
+    mask = np.array([0x0010], np.uint16)
+    no_backref = np.zeros(g.tile_w * g.tile_h, np.uint16)
+    for i in range(count):
+        img = rgb[i * w * h * 3:(i + 1) * w * h * 3].reshape(h, w, 3)
+        for t in range(g.tiles_per_image):
+            x0, y0 = (t % g.x_tiles) * g.tile_w, (t // g.x_tiles) * g.tile_h
+            t0 = time.perf_counter()
+            tile = np.ascontiguousarray(img[y0:y0 + g.tile_h, x0:x0 + g.tile_w])  # choh.cpp:478-484
+            th, tw = tile.shape[:2]
+            px = tw * th
+            tile = tile.ravel()
+            planes = [np.empty(px, np.uint16) for _ in range(3)]
+            if use_ref:
+                R.ref_subtract_green(tile, tile.size, *planes)
+            else:
+                O.orc_subtract_green(tile, tile.size, *planes)
+            chans = []
+            for p, d in zip(planes, (8, 9, 9)):
+                out = np.empty(px * 4 + 4096, np.uint8)
+                if use_ref:
+                    n = R.ref_layer_encode(p, px, tw, th, d, MODE, nuke[:px], out)
+                else:
+                    n = O.orc_layer_encode(p, px, tw, th, d, MODE, nuke[:px], out, None)
+                chans.append(out[:n + 16])
+            t1 = time.perf_counter()
+            dec = []
+            for ch, d in zip(chans, (8, 9, 9)):
+                sym = np.empty(px + 8, np.uint16)
+                bp = C.c_size_t(5)  # after the channel header 10 00 00 00 10
+                pl = np.empty(px, np.uint16)
+                if use_ref:
+                    R.ref_decode_entropy(ch, len(ch), C.byref(bp), sym, px)
+                    R.ref_unpredict_all(sym, px, tw, th, d, 1, 1, mask, no_backref[:px], pl)
+                else:
+                    st = C.c_int(0)
+                    O.orc_decode_entropy(ch, len(ch), C.byref(bp), sym, px, 7, C.byref(st))
+                    O.orc_unpredict_fastpath(sym, tw, th, d, None, pl)
+                dec.append(pl)
+            back = np.empty(px * 3, np.uint8)
+            O.orc_add_green(dec[0], dec[1], dec[2], px, back)  # the reference has no inverse (D4)
+            t2 = time.perf_counter()
+            t_enc += t1 - t0
+            t_dec += t2 - t1
+    return t_enc, t_dec, count * w * h * 3, use_ref
+
+
+def cpu_hot_path(sample_images, w, h, cores, seed0=1):
+    """Times the reference CPU hot path (encode + decode, LZ excluded: NUKE == 0) on `cores`
+    processes over `sample_images` images.  Returns dict(value MB/s, t_enc, t_dec, kind)."""
+    import multiprocessing as mp
+    per = [sample_images // cores + (1 if i < sample_images % cores else 0) for i in range(cores)]
+    jobs, seed = [], seed0
+    for n in per:
+        if n:
+            jobs.append((seed, n, w, h))
+            seed += n
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    raw = sum(r[2] for r in res)
+    slowest = max(r[0] + r[1] for r in res)
+    return {"value": 2 * raw / slowest / 1e6, "encode_mbs": raw / max(r[0] for r in res) / 1e6,
+            "decode_mbs": raw / max(r[1] for r in res) / 1e6, "kind": "reference" if res[0][3] else "port",
+            "cores": len(jobs), "wall_s": wall, "busy_s": slowest, "images": sample_images}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--images", type=int, default=4096, help="images per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = 4 per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = args.steps, max(args.warmup, 0)
+    config = {"workload": f"{args.images} synthetic {W}x{H} RGB images per GPU, cruncher mode -s0 "
+                          f"(BASELINE.json configs[1]), subtract-green + MED fastpath + rANS prob_bits 15, "
+                          f"encode then decode", "images_per_gpu": args.images, "width": W, "height": H,
+              "mode": MODE, "cold_cache": "inputs (3.2 GB per GPU) are larger than the 126 MB L2",
+              "sharding": f"images by index across {world} GPU(s), no collective in the data path"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or max(cores * 2, 16)
+        vals = []
+        for it in range(warmup + steps):
+            r = cpu_hot_path(sample, W, H, cores, seed0=1)
+            if it >= warmup:
+                vals.append(r)
+        busy = sum(v["busy_s"] for v in vals)
+        raw = sum(v["images"] for v in vals) * W * H * 3
+        value = 2 * raw / busy / 1e6
+        line = {"impl": "reference", "metric": "raw RGB MB/s, encode+decode, hot path", "value": value, "unit": "MB/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * busy / max(steps, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/u64 integer",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "MB/s", "cores": vals[0]["cores"], "kind": vals[0]["kind"],
+                                 "sample": f"{sample} images of {W}x{H} per step (of {args.images}), one process per "
+                                           f"core, reference hot path only (subtract_green + layer_encode x3, "
+                                           f"decode_entropy + unpredict_all x3; host LZ excluded on both arms)"},
+                "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "encode_mbs": float(np.mean([v["encode_mbs"] for v in vals])),
+                "decode_mbs": float(np.mean([v["decode_mbs"] for v in vals]))}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mod = _load("hohgpu", os.path.join(ROOT, "hoh-ans_b200", "host", "hohgpu.py"))
+    g = mod.HohGpu(local_rank)
+    lib, ctx = g.lib, g.ctx
+    geom = g.tile_geometry(W, H)
+    n_img = args.images
+    raw = n_img * W * H * 3
+    n_streams = n_img * geom.streams_per_image
+    host_threads = max(1, (os.cpu_count() or 8) // max(world, 1))
+
+    # inputs: distinct image per global index (seed = 1 + index), pinned host memory
+    rgb_host = g.host_alloc(raw)
+    fill_images(rgb_host, 1 + rank * n_img, n_img, W, H, host_threads)
+    out_bytes = int(lib.hoh_encode_images_out_bytes(C.byref(geom), n_img))
+    packed_cap = raw + raw // 4 + 4096 * n_streams
+    d_rgb, d_back = g.alloc(raw), g.alloc(raw)
+    d_out, d_packed = g.alloc(out_bytes), g.alloc(packed_cap)
+    d_res, d_off, d_st = g.alloc(n_streams * 24), g.alloc((n_streams + 1) * 8), g.alloc(n_streams * 4)
+    g._ck(lib.hoh_h2d(ctx, d_rgb.ptr, rgb_host.ctypes.data, raw), "h2d")
+    g.sync()
+
+    def encode_dev():
+        g._ck(lib.hoh_encode_images_s0(ctx, d_rgb.ptr, n_img, W, H, None, d_out.ptr, out_bytes, d_res.ptr,
+                                       d_packed.ptr, packed_cap, d_off.ptr), "hoh_encode_images_s0")
+
+    def decode_dev():
+        g._ck(lib.hoh_decode_images_s0(ctx, d_packed.ptr, packed_cap, d_off.ptr, n_img, W, H, None, d_back.ptr,
+                                       d_st.ptr), "hoh_decode_images_s0")
+
+    def barrier():
+        g.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up + correctness of what is being timed
+    for _ in range(max(warmup, 1)):
+        encode_dev()
+        decode_dev()
+    g.sync()
+    off = d_off.download(np.uint64, n_streams + 1)
+    comp_bytes = int(off[-1])
+    st = d_st.download(np.int32, n_streams)
+    res = d_res.download(mod.RESULT_DT, n_streams)
+    back = d_back.download(np.uint8, raw)
+    verified = bool((st == 0).all() and (res["status"] == 0).all() and np.array_equal(back, rgb_host))
+    del back
+
+    # timed region: device resident
+    clocks = ClockSampler(local_rank)
+    launches0 = g.launch_count()
+    barrier()
+    clocks.start()
+    t_enc = t_dec = 0.0
+    g.timer_start(0)
+    for k in range(steps):
+        g.timer_start(2)
+        encode_dev()
+        g.timer_stop(2)
+        g.timer_start(3)
+        decode_dev()
+        g.timer_stop(3)
+        t_enc += g.timer_ms(2)
+        t_dec += g.timer_ms(3)
+    g.timer_stop(0)
+    total_ms = g.timer_ms(0)
+    barrier()
+    clk = clocks.stop()
+    launches = g.launch_count() - launches0
+
+    # per-kernel profile of one step (separate pass, CUDA events after every launch)
+    g.profile_begin()
+    encode_dev()
+    decode_dev()
+    prof = g.profile_end()
+
+    # e2e: host buffers through the C-ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        packed_host = g.host_alloc(packed_cap)
+        off_host = g.host_alloc((n_streams + 1) * 8, np.uint64)
+        back_host = g.host_alloc(raw)
+
+        def e2e_step():
+            g._ck(lib.hoh_encode_images_s0_host(ctx, rgb_host.ctypes.data, n_img, W, H, packed_host.ctypes.data,
+                                                packed_cap, off_host.ctypes.data, None), "encode_host")
+            total = int(off_host[n_streams])
+            g._ck(lib.hoh_decode_images_s0_host(ctx, packed_host.ctypes.data, total, off_host.ctypes.data, n_img, W,
+                                                H, back_host.ctypes.data, None), "decode_host")
+            return total
+
+        e2e_step()
+        e2e_ok = bool(np.array_equal(back_host, rgb_host))
+        barrier()
+        g.timer_start(1)
+        t0 = time.perf_counter()
+        e_steps = max(1, min(steps, 3))
+        for _ in range(e_steps):
+            total = e2e_step()
+        g.timer_stop(1)
+        e2e_ms = g.timer_ms(1)
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        e2e_ms = max(e2e_ms, wall_ms)
+        e2e = {"ms": e2e_ms / e_steps, "ok": e2e_ok,
+               "h2d": raw + total + (n_streams + 1) * 8, "d2h": total + (n_streams + 1) * 8 + raw}
+
+    # max over ranks
+    def rmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def rsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    total_ms = rmax(total_ms)
+    t_enc, t_dec = rmax(t_enc), rmax(t_dec)
+    job_raw = rsum(float(raw))
+    job_comp = rsum(float(comp_bytes))
+    all_verified = rsum(1.0 if verified else 0.0) == world
+    if e2e:
+        e2e["ms"] = rmax(e2e["ms"])
+        e2e_all_ok = rsum(1.0 if e2e["ok"] else 0.0) == world
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        value = 2 * job_raw * steps / (total_ms / 1e3) / 1e6
+        # dominant kernel by device time in the profiled step
+        top = max(prof.items(), key=lambda kv: kv[1][0])
+        top_name, (top_ms, top_cnt) = top
+        step_ms_prof = sum(v[0] for v in prof.values())
+        per_launch_ms = top_ms / top_cnt
+        # algorithmic bytes of one launch: encode-side kernels move 3*W*H in + C out
+        # per image, decode-side kernels C in + 3*W*H out; a launch covers the rank's whole batch
+        alg_bytes = raw + comp_bytes
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tj.get(top_name.split("<")[0])
+            if ent and ent.get("images"):
+                traffic = ent["dram_bytes_per_launch"] * n_img / ent["images"]
+        except Exception:
+            pass
+        achieved = alg_bytes / (per_launch_ms / 1e3) / 1e9
+        line = {
+            "metric": "raw RGB MB/s, encode+decode (BASELINE.json: raw RGB MB/s encode & decode, % of HBM peak)",
+            "value": value, "unit": "MB/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/u16 pixels, u32 freqs, u64 rANS state (integer)", "data": "synthetic",
+            "config": config, "verified_bit_exact_roundtrip": all_verified,
+            "encode_mbs": job_raw * steps / (t_enc / 1e3) / 1e6, "decode_mbs": job_raw * steps / (t_dec / 1e3) / 1e6,
+            "compressed_ratio": job_comp / job_raw,
+            "hbm_frac_whole_step": ((job_raw + job_comp) * 2 * steps / world / (total_ms / 1e3) / 1e9) / hbm_peak,
+            "gpu_launches": launches, "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
+                         "share_of_step": top_ms / step_ms_prof},
+            "kernels_ms": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+        }
+        if e2e:
+            line["e2e"] = {"value": 2 * job_raw / (e2e["ms"] / 1e3) / 1e6, "unit": "MB/s",
+                           "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                           "ms_per_step": e2e["ms"], "verified": e2e_all_ok}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = args.cpu_sample or max(cores * 4, 32)
+            cb = cpu_hot_path(sample, W, H, cores, seed0=1)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": "MB/s", "cores": cb["cores"], "kind": cb["kind"],
+                                    "encode_mbs": cb["encode_mbs"], "decode_mbs": cb["decode_mbs"],
+                                    "sample": f"{sample} of the {n_img} images, one process per core, hot path only "
+                                              f"(host LZ excluded on both arms), busy time of the slowest worker"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    g.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

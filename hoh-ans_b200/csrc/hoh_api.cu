@@ -1,0 +1,1043 @@
+// hoh_api.cu — C-ABI of libhohgpu.so (declared in include/hohgpu.h): context, scratch memory,
+// kernel launches for the batched entry points and the compat shims with the reference's value
+// semantics.  No CPU implementation of any stage lives here: every entry point launches kernels
+// from hoh_kernels.cuh and fails with HOH_E_CUDA when there is no device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "hoh_kernels.cuh"
+
+using namespace hohk;
+
+namespace {
+
+enum Slot {
+    S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
+    S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
+    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_COUNT
+};
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct hoh_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    char err[512] = {0};
+    Buf scratch[S_COUNT];
+    cudaEvent_t ev[16][2] = {};
+    void* flush = nullptr;
+    size_t flush_bytes = 0;
+    std::map<uint64_t, double*> e_tabs;  // plane size -> device table of -log2(f/size)
+    bool smem_opt_in = false;
+    // per-kernel profiling (hoh_profile_*)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;       // event 0 = begin, event i = after launch i
+    std::vector<const char*> prof_names;        // name of launch i (index i-1)
+    std::vector<cudaEvent_t> prof_pool;
+    std::vector<std::string> prof_keys;
+    std::vector<double> prof_ms;
+    std::vector<uint64_t> prof_launches;
+};
+
+namespace {
+
+const uint16_t kStockMasks[14] = {  // layer_encode.hpp:159-175
+    0x0001, 0x0002, 0x0020, 0x0010, 0xffbf, 0x0003, 0xfffd, 0xfffb, 0xfff7, 0xffef, 0xffdf, 0xff7f, 0xfdff, 0xffff};
+
+int fail_cuda(hoh_ctx* c, cudaError_t e, const char* what) {
+    if (c) snprintf(c->err, sizeof c->err, "%s: %s", what, cudaGetErrorString(e));
+    return HOH_E_CUDA;
+}
+
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);   \
+    } while (0)
+
+int prof_mark(hoh_ctx* ctx, const char* name);
+
+#define LAUNCHED(name)                                             \
+    do {                                                           \
+        ctx->launches++;                                           \
+        cudaError_t e_ = cudaGetLastError();                       \
+        if (e_ != cudaSuccess) return fail_cuda(ctx, e_, name);    \
+        if (ctx->profiling) {                                      \
+            int p_ = prof_mark(ctx, name);                         \
+            if (p_ != HOH_OK) return p_;                           \
+        }                                                          \
+    } while (0)
+
+#define TRY(expr)                   \
+    do {                            \
+        int s_ = (expr);            \
+        if (s_ != HOH_OK) return s_; \
+    } while (0)
+
+int prof_mark(hoh_ctx* ctx, const char* name) {
+    cudaEvent_t ev;
+    if (!ctx->prof_pool.empty()) {
+        ev = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+    } else {
+        CK(cudaEventCreate(&ev));
+    }
+    CK(cudaEventRecord(ev, ctx->stream));
+    ctx->prof_events.push_back(ev);
+    if (name) ctx->prof_names.push_back(name);
+    return HOH_OK;
+}
+
+int scratch(hoh_ctx* ctx, Slot slot, size_t bytes, void** out) {
+    Buf& b = ctx->scratch[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(b.p));
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        CK(cudaMalloc(&b.p, want));
+        b.cap = want;
+    }
+    *out = b.p;
+    return HOH_OK;
+}
+
+template <typename T>
+int scratch_t(hoh_ctx* ctx, Slot slot, size_t count, T** out) {
+    void* p = nullptr;
+    TRY(scratch(ctx, slot, count * sizeof(T), &p));
+    *out = reinterpret_cast<T*>(p);
+    return HOH_OK;
+}
+
+inline unsigned blocks_for(uint64_t items, unsigned per_block) { return (unsigned)((items + per_block - 1) / per_block); }
+inline unsigned grid_cap(uint64_t items, unsigned per_block, unsigned cap = 148u * 32u) {
+    uint64_t b = (items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    return (unsigned)(b > cap ? cap : b);
+}
+
+int ensure_smem_opt_in(hoh_ctx* ctx) {
+    if (ctx->smem_opt_in) return HOH_OK;
+    const int big = 200 * 1024;
+    CK(cudaFuncSetAttribute(k_rans_encode<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_decode<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_decode<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_tile_unpredict_s0, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_unpredict_fastpath_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    ctx->smem_opt_in = true;
+    return HOH_OK;
+}
+
+// Shared tail of the encode pipeline once the raw histograms are in `freqs`.
+int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, const uint16_t* d_symbols,
+                      uint8_t* d_out, hoh_stream_result* d_results, const uint32_t* freqs,
+                      uint32_t max_range, uint32_t max_prob_bits) {
+    uint32_t* cum;
+    uint8_t* heads;
+    EncMeta* meta;
+    TRY(scratch_t(ctx, S_CUM, n * kCumRow, &cum));
+    TRY(scratch_t(ctx, S_HEADS, n * HOH_HEAD_CAP, &heads));
+    TRY(scratch_t(ctx, S_ENCMETA, n, &meta));
+    TRY(ensure_smem_opt_in(ctx));
+    k_build_tables<<<blocks_for(n, kTableWarps), kTableWarps * 32, 0, ctx->stream>>>(d_streams, (uint32_t)n, freqs,
+                                                                                    cum, heads, meta);
+    LAUNCHED("k_build_tables");
+    const uint32_t rows = max_range + 1;
+    {
+        const size_t smem = (size_t)rows * 32 * sizeof(uint16_t) + 32 * kSymStride * sizeof(uint16_t);
+        k_rans_encode<uint16_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, cum,
+                                                                             d_out, meta, rows, 1u);
+        LAUNCHED("k_rans_encode<u16>");
+    }
+    if (max_prob_bits > 16) {
+        const size_t smem = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kSymStride * sizeof(uint16_t);
+        k_rans_encode<uint32_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, cum,
+                                                                             d_out, meta, rows, 0u);
+        LAUNCHED("k_rans_encode<u32>");
+    }
+    k_finish_streams<<<blocks_for(n, 4), 128, 0, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, heads, meta, d_out,
+                                                                d_results);
+    LAUNCHED("k_finish_streams");
+    return HOH_OK;
+}
+
+int decode_common(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n, const uint8_t* d_in, size_t in_bytes,
+                  uint16_t* d_symbols, hoh_dec_result* d_results) {
+    uint32_t* cum;
+    DecMeta* meta;
+    TRY(scratch_t(ctx, S_CUM, n * kCumRow, &cum));
+    TRY(scratch_t(ctx, S_DECMETA, n, &meta));
+    TRY(ensure_smem_opt_in(ctx));
+    k_parse_streams<<<blocks_for(n, kTableWarps), kTableWarps * 32, 0, ctx->stream>>>(d_streams, (uint32_t)n, d_in,
+                                                                                     in_bytes, cum, meta, d_results);
+    LAUNCHED("k_parse_streams");
+    k_unpack_stored<<<(unsigned)n, 256, 0, ctx->stream>>>(d_streams, d_in, in_bytes, meta, d_symbols);
+    LAUNCHED("k_unpack_stored");
+    const uint32_t rows = HOH_MAX_RANGE + 1;
+    {
+        const size_t smem = (size_t)rows * 32 * sizeof(uint16_t) + 32 * kSymStride * sizeof(uint16_t);
+        k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_in, in_bytes,
+                                                                             cum, meta, d_symbols, rows, 1u);
+        LAUNCHED("k_rans_decode<u16>");
+    }
+    {
+        const size_t smem = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kSymStride * sizeof(uint16_t);
+        k_rans_decode<uint32_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_in, in_bytes,
+                                                                             cum, meta, d_symbols, rows, 0u);
+        LAUNCHED("k_rans_decode<u32>");
+    }
+    return HOH_OK;
+}
+
+TileGeom to_geom(const hoh_tile_geometry& g) {
+    TileGeom t;
+    t.width = g.width;
+    t.height = g.height;
+    t.x_tiles = g.x_tiles;
+    t.y_tiles = g.y_tiles;
+    t.tile_w = g.tile_w;
+    t.tile_h = g.tile_h;
+    t.tiles_per_image = g.tiles_per_image;
+    t.plane_stride = (g.tile_w * g.tile_h + 7u) & ~7u;
+    return t;
+}
+
+// -log2(f / size) for f = 0..size+1 computed with the host libm (the reference's std::log2,
+// layer_encode.hpp:143) so that the doubles the search compares are the reference's doubles.  This is
+// a constant table that depends only on the plane size, not on any image data.
+int cost_table_for(hoh_ctx* ctx, uint64_t size, double** out, uint32_t* len) {
+    *len = (uint32_t)(size + 2);
+    auto it = ctx->e_tabs.find(size);
+    if (it != ctx->e_tabs.end()) {
+        *out = it->second;
+        return HOH_OK;
+    }
+    std::vector<double> tab(size + 2);
+    for (uint64_t f = 0; f < size + 2; f++) tab[f] = -std::log2((double)f / (double)size);
+    double* d = nullptr;
+    CK(cudaMalloc(&d, tab.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->e_tabs[size] = d;
+    *out = d;
+    return HOH_OK;
+}
+
+}  // namespace
+
+namespace {
+__global__ void k_merge_status(const hoh_dec_result* __restrict__ res, uint64_t n, int32_t* __restrict__ status) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n && status[i] == HOH_S_OK) status[i] = res[i].status;
+}
+__global__ void k_normalize_only(uint32_t* __restrict__ freqs, uint32_t* __restrict__ cum, uint32_t range,
+                                 uint32_t target, int32_t* __restrict__ status) {
+    __shared__ uint32_t s_f[kFreqRow], s_sc[kFreqRow], s_cum[kFreqRow + 8];
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t i = lane; i < range; i += 32) s_f[i] = freqs[i];
+    __syncwarp();
+    int st = warp_normalize(s_f, s_sc, s_cum, range, target);
+    if (st == HOH_S_OK) {
+        for (uint32_t i = lane; i < range; i += 32) freqs[i] = s_f[i];
+        for (uint32_t i = lane; i <= range; i += 32) cum[i] = s_cum[i];
+    }
+    if (lane == 0) *status = st;
+}
+}  // namespace
+
+namespace {
+template <typename T>
+int stage_in(hoh_ctx* ctx, Slot slot, const T* host, size_t count, T** dev) {
+    TRY(scratch_t(ctx, slot, count ? count : 1, dev));
+    if (count) CK(cudaMemcpyAsync(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return HOH_OK;
+}
+template <typename T>
+int stage_out(hoh_ctx* ctx, T* host, const T* dev, size_t count) {
+    if (count) CK(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HOH_OK;
+}
+}  // namespace
+
+// =================================================================================================
+// context
+// =================================================================================================
+extern "C" {
+
+int hoh_ctx_create(int device, void* cuda_stream, hoh_ctx** out) {
+    if (!out) return HOH_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return HOH_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return HOH_E_CUDA;
+    hoh_ctx* ctx = new hoh_ctx();
+    ctx->device = device;
+    if (cuda_stream) {
+        ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return HOH_E_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    *out = ctx;
+    return HOH_OK;
+}
+
+void hoh_ctx_destroy(hoh_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->scratch)
+        if (b.p) cudaFree(b.p);
+    for (auto& kv : ctx->e_tabs) cudaFree(kv.second);
+    if (ctx->flush) cudaFree(ctx->flush);
+    for (auto& pair : ctx->ev)
+        for (auto& ev : pair)
+            if (ev) cudaEventDestroy(ev);
+    for (auto ev : ctx->prof_events) cudaEventDestroy(ev);
+    for (auto ev : ctx->prof_pool) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int hoh_sync(hoh_ctx* ctx) {
+    if (!ctx) return HOH_E_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HOH_OK;
+}
+
+const char* hoh_strerror(int status) {
+    switch (status) {
+        case HOH_OK: return "ok";
+        case HOH_E_CUDA: return "CUDA runtime error (no device, or a call failed)";
+        case HOH_E_ARG: return "bad argument";
+        case HOH_E_UNSUPPORTED: return "outside the supported domain of the hot path";
+        case HOH_E_CAPACITY: return "output buffer too small";
+        case HOH_E_STREAM: return "a stream failed (see per-stream status)";
+        default: return "unknown status";
+    }
+}
+
+const char* hoh_last_cuda_error(hoh_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+uint64_t hoh_launch_count(hoh_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hoh_dev_alloc(hoh_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return HOH_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(dptr, bytes ? bytes : 16));
+    return HOH_OK;
+}
+int hoh_dev_free(hoh_ctx* ctx, void* dptr) {
+    if (!ctx) return HOH_E_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(dptr));
+    return HOH_OK;
+}
+int hoh_dev_memset(hoh_ctx* ctx, void* dptr, int value, size_t bytes) {
+    if (!ctx) return HOH_E_ARG;
+    CK(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
+    return HOH_OK;
+}
+int hoh_host_alloc(hoh_ctx* ctx, size_t bytes, void** hptr) {
+    if (!ctx || !hptr) return HOH_E_ARG;
+    CK(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return HOH_OK;
+}
+int hoh_host_free(hoh_ctx* ctx, void* hptr) {
+    if (!ctx) return HOH_E_ARG;
+    CK(cudaFreeHost(hptr));
+    return HOH_OK;
+}
+int hoh_h2d(hoh_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (!ctx) return HOH_E_ARG;
+    CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return HOH_OK;
+}
+int hoh_d2h(hoh_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (!ctx) return HOH_E_ARG;
+    CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return HOH_OK;
+}
+int hoh_timer_start(hoh_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16) return HOH_E_ARG;
+    for (int k = 0; k < 2; k++)
+        if (!ctx->ev[slot][k]) CK(cudaEventCreate(&ctx->ev[slot][k]));
+    CK(cudaEventRecord(ctx->ev[slot][0], ctx->stream));
+    return HOH_OK;
+}
+int hoh_timer_stop(hoh_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16 || !ctx->ev[slot][1]) return HOH_E_ARG;
+    CK(cudaEventRecord(ctx->ev[slot][1], ctx->stream));
+    return HOH_OK;
+}
+int hoh_timer_elapsed_ms(hoh_ctx* ctx, int slot, float* ms) {
+    if (!ctx || slot < 0 || slot >= 16 || !ms || !ctx->ev[slot][1]) return HOH_E_ARG;
+    CK(cudaEventSynchronize(ctx->ev[slot][1]));
+    CK(cudaEventElapsedTime(ms, ctx->ev[slot][0], ctx->ev[slot][1]));
+    return HOH_OK;
+}
+int hoh_profile_begin(hoh_ctx* ctx) {
+    if (!ctx) return HOH_E_ARG;
+    for (auto ev : ctx->prof_events) ctx->prof_pool.push_back(ev);
+    ctx->prof_events.clear();
+    ctx->prof_names.clear();
+    ctx->prof_keys.clear();
+    ctx->prof_ms.clear();
+    ctx->prof_launches.clear();
+    TRY(prof_mark(ctx, nullptr));
+    ctx->profiling = true;
+    return HOH_OK;
+}
+int hoh_profile_end(hoh_ctx* ctx) {
+    if (!ctx || !ctx->profiling) return HOH_E_ARG;
+    ctx->profiling = false;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i + 1 < ctx->prof_events.size(); i++) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+        const std::string key = ctx->prof_names[i];
+        size_t k = 0;
+        while (k < ctx->prof_keys.size() && ctx->prof_keys[k] != key) k++;
+        if (k == ctx->prof_keys.size()) {
+            ctx->prof_keys.push_back(key);
+            ctx->prof_ms.push_back(0.0);
+            ctx->prof_launches.push_back(0);
+        }
+        ctx->prof_ms[k] += ms;
+        ctx->prof_launches[k]++;
+    }
+    return HOH_OK;
+}
+int hoh_profile_count(hoh_ctx* ctx) { return ctx ? (int)ctx->prof_keys.size() : 0; }
+int hoh_profile_entry(hoh_ctx* ctx, int index, const char** name, double* total_ms, uint64_t* launches) {
+    if (!ctx || index < 0 || index >= (int)ctx->prof_keys.size()) return HOH_E_ARG;
+    if (name) *name = ctx->prof_keys[index].c_str();
+    if (total_ms) *total_ms = ctx->prof_ms[index];
+    if (launches) *launches = ctx->prof_launches[index];
+    return HOH_OK;
+}
+int hoh_flush_l2(hoh_ctx* ctx) {
+    if (!ctx) return HOH_E_ARG;
+    if (!ctx->flush) {
+        ctx->flush_bytes = 256ull << 20;  // > 126 MB L2
+        CK(cudaMalloc(&ctx->flush, ctx->flush_bytes));
+    }
+    CK(cudaMemsetAsync(ctx->flush, 0x5a, ctx->flush_bytes, ctx->stream));
+    return HOH_OK;
+}
+
+// =================================================================================================
+// batched entropy coding
+// =================================================================================================
+size_t hoh_enc_slab_bytes(size_t n, uint32_t prob_bits) {
+    // every symbol emits at most one 32-bit word and at most prob_bits bits on average, plus the
+    // two flush words, the header room in front and slack
+    size_t payload = ((n * (size_t)prob_bits + 31) / 32) * 4 + 64;
+    size_t total = payload + HOH_HEAD_CAP + 64;
+    size_t stored = n * 2 + 64;  // stored-mode rewrite: at most 9 bits per symbol
+    if (stored > total) total = stored;
+    return (total + 15) & ~(size_t)15;
+}
+
+int hoh_encode_entropy_batch(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n_streams,
+                             const uint16_t* d_symbols, uint8_t* d_out, hoh_stream_result* d_results,
+                             uint32_t max_range, uint32_t max_prob_bits, uint32_t max_n) {
+    if (!ctx || !d_streams || !d_out || !d_results) return HOH_E_ARG;
+    if (n_streams == 0) return HOH_OK;
+    if (max_range == 0 || max_range > HOH_MAX_RANGE || max_prob_bits == 0 || max_prob_bits > HOH_MAX_PROB_BITS)
+        return HOH_E_UNSUPPORTED;
+    (void)max_n;
+    uint32_t* freqs;
+    TRY(scratch_t(ctx, S_FREQS, n_streams * kFreqRow, &freqs));
+    k_histogram<<<(unsigned)n_streams, 256, 0, ctx->stream>>>(d_streams, d_symbols, freqs);
+    LAUNCHED("k_histogram");
+    return encode_from_freqs(ctx, d_streams, n_streams, d_symbols, d_out, d_results, freqs, max_range, max_prob_bits);
+}
+
+int hoh_decode_entropy_batch(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n_streams,
+                             const uint8_t* d_in, size_t in_bytes, uint16_t* d_symbols,
+                             hoh_dec_result* d_results, uint32_t max_n) {
+    if (!ctx || !d_streams || !d_in || !d_symbols || !d_results) return HOH_E_ARG;
+    if (n_streams == 0) return HOH_OK;
+    (void)max_n;
+    return decode_common(ctx, d_streams, n_streams, d_in, in_bytes, d_symbols, d_results);
+}
+
+int hoh_rans_encode_static(hoh_ctx* ctx, const uint16_t* d_symbols, size_t n, uint32_t stream_len,
+                           const uint32_t* d_cum, uint32_t range, uint32_t prob_bits, uint8_t* d_out,
+                           uint32_t slab_bytes, uint32_t* d_payload_bytes) {
+    if (!ctx || !d_symbols || !d_cum || !d_out || !d_payload_bytes) return HOH_E_ARG;
+    if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > 31) return HOH_E_UNSUPPORTED;
+    if (stream_len == 0 || stream_len % 8 || slab_bytes % 16) return HOH_E_ARG;
+    if (n == 0) return HOH_OK;
+    const uint64_t streams = (n + stream_len - 1) / stream_len;
+    k_rans_encode_static<<<blocks_for(streams, kStaticWarps * 32), kStaticWarps * 32, 0, ctx->stream>>>(
+        d_symbols, n, stream_len, d_cum, range, prob_bits, d_out, slab_bytes, d_payload_bytes);
+    LAUNCHED("k_rans_encode_static");
+    return HOH_OK;
+}
+
+int hoh_rans_decode_static(hoh_ctx* ctx, const uint8_t* d_in, uint32_t slab_bytes,
+                           const uint32_t* d_payload_bytes, size_t n, uint32_t stream_len,
+                           const uint32_t* d_cum, uint32_t range, uint32_t prob_bits, uint16_t* d_symbols) {
+    if (!ctx || !d_symbols || !d_cum || !d_in || !d_payload_bytes) return HOH_E_ARG;
+    if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > 31) return HOH_E_UNSUPPORTED;
+    if (stream_len == 0 || stream_len % 8 || slab_bytes % 16) return HOH_E_ARG;
+    if (n == 0) return HOH_OK;
+    const uint64_t streams = (n + stream_len - 1) / stream_len;
+    k_rans_decode_static<<<blocks_for(streams, kStaticWarps * 32), kStaticWarps * 32, 0, ctx->stream>>>(
+        d_in, slab_bytes, d_payload_bytes, n, stream_len, d_cum, range, prob_bits, d_symbols);
+    LAUNCHED("k_rans_decode_static");
+    return HOH_OK;
+}
+
+// =================================================================================================
+// batched tile codec, mode 0
+// =================================================================================================
+int hoh_tile_geometry_for(uint32_t width, uint32_t height, hoh_tile_geometry* out) {
+    if (!out || width == 0 || height == 0) return HOH_E_ARG;
+    hoh_tile_geometry g;
+    g.width = width;
+    g.height = height;
+    if ((width >= 512 || height >= 512) && width >= 256 && height >= 256) {  // choh.cpp:454
+        g.x_tiles = width / 256;
+        g.y_tiles = height / 256;
+    } else {
+        g.x_tiles = g.y_tiles = 1;
+    }
+    g.tile_w = (width + g.x_tiles - 1) / g.x_tiles;   // choh.cpp:459
+    g.tile_h = (height + g.y_tiles - 1) / g.y_tiles;  // choh.cpp:460
+    g.tiles_per_image = g.x_tiles * g.y_tiles;
+    g.streams_per_image = 3 * g.tiles_per_image;
+    *out = g;
+    return HOH_OK;
+}
+
+size_t hoh_encode_images_out_bytes(const hoh_tile_geometry* g, size_t n_images) {
+    if (!g) return 0;
+    return hoh_enc_slab_bytes((size_t)g->tile_w * g->tile_h, 15) * g->streams_per_image * n_images;
+}
+
+int hoh_encode_images_s0(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
+                         const uint8_t* d_nuke, uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
+                         uint8_t* d_packed, size_t packed_cap, uint64_t* d_packed_off) {
+    if (!ctx || !d_rgb || !d_out || !d_results) return HOH_E_ARG;
+    if (d_nuke) return HOH_E_UNSUPPORTED;  // LZ-covered pixel compaction: not in this round
+    if (n_images == 0) return HOH_OK;
+    hoh_tile_geometry hg;
+    TRY(hoh_tile_geometry_for(width, height, &hg));
+    if ((uint64_t)hg.tile_w * hg.tile_h >= (1u << 21)) return HOH_E_UNSUPPORTED;  // varint.hpp:39-45
+    const TileGeom g = to_geom(hg);
+    const uint64_t n_tiles = (uint64_t)n_images * g.tiles_per_image, n_streams = n_tiles * 3;
+    const uint32_t slab = (uint32_t)hoh_enc_slab_bytes((size_t)g.tile_w * g.tile_h, 15);
+    if (out_bytes < n_streams * slab) return HOH_E_CAPACITY;
+    uint16_t* resid;
+    uint32_t* freqs;
+    hoh_enc_stream* streams;
+    TRY(scratch_t(ctx, S_RESID, n_streams * g.plane_stride, &resid));
+    TRY(scratch_t(ctx, S_FREQS, n_streams * kFreqRow, &freqs));
+    TRY(scratch_t(ctx, S_STREAMS, n_streams, &streams));
+    k_tile_residuals_s0<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(d_rgb, g, resid, freqs);
+    LAUNCHED("k_tile_residuals_s0");
+    k_make_tile_streams<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(g, n_tiles, slab, streams);
+    LAUNCHED("k_make_tile_streams");
+    TRY(encode_from_freqs(ctx, streams, n_streams, resid, d_out, d_results, freqs, 512, 15));
+    if (d_packed) {
+        if (!d_packed_off) return HOH_E_ARG;
+        k_scan_sizes<<<1, 1024, 0, ctx->stream>>>(d_results, (uint32_t)n_streams, d_packed_off);
+        LAUNCHED("k_scan_sizes");
+        k_gather_streams<<<(unsigned)n_streams, 256, 0, ctx->stream>>>(d_results, d_out, d_packed_off, d_packed,
+                                                                       packed_cap);
+        LAUNCHED("k_gather_streams");
+    }
+    return HOH_OK;
+}
+
+
+int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes, const uint64_t* d_packed_off,
+                         size_t n_images, uint32_t width, uint32_t height, const uint16_t* d_backref,
+                         uint8_t* d_rgb, int32_t* d_status) {
+    if (!ctx || !d_packed || !d_packed_off || !d_rgb || !d_status) return HOH_E_ARG;
+    if (d_backref) return HOH_E_UNSUPPORTED;  // LZ back-reference copies: not in this round
+    if (n_images == 0) return HOH_OK;
+    hoh_tile_geometry hg;
+    TRY(hoh_tile_geometry_for(width, height, &hg));
+    const TileGeom g = to_geom(hg);
+    const uint64_t n_tiles = (uint64_t)n_images * g.tiles_per_image, n_streams = n_tiles * 3;
+    uint16_t* resid;
+    hoh_dec_stream* streams;
+    hoh_dec_result* results;
+    TRY(scratch_t(ctx, S_RESID, n_streams * g.plane_stride, &resid));
+    TRY(scratch_t(ctx, S_DSTREAMS, n_streams, &streams));
+    TRY(scratch_t(ctx, S_DRESULTS, n_streams, &results));
+    if ((size_t)g.tile_w * 4 * 4 > 200 * 1024) return HOH_E_UNSUPPORTED;
+    k_make_tile_dec_streams<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(g, n_tiles, d_packed, packed_bytes,
+                                                                                 d_packed_off, streams, d_status);
+    LAUNCHED("k_make_tile_dec_streams");
+    TRY(decode_common(ctx, streams, n_streams, d_packed, packed_bytes, resid, results));
+    k_merge_status<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(results, n_streams, d_status);
+    LAUNCHED("k_merge_status");
+    k_tile_unpredict_s0<<<blocks_for(n_tiles, 4), 128, (size_t)g.tile_w * 4 * 4, ctx->stream>>>(resid, g, n_tiles, d_rgb);
+    LAUNCHED("k_tile_unpredict_s0");
+    return HOH_OK;
+}
+
+int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_images, uint32_t width,
+                              uint32_t height, uint8_t* packed_host, size_t packed_cap, uint64_t* off_host,
+                              hoh_stream_result* results_host) {
+    if (!ctx || !rgb_host || !packed_host || !off_host) return HOH_E_ARG;
+    if (n_images == 0) return HOH_OK;
+    hoh_tile_geometry hg;
+    TRY(hoh_tile_geometry_for(width, height, &hg));
+    const size_t raw = (size_t)n_images * width * height * 3;
+    const size_t n_streams = n_images * hg.streams_per_image;
+    const size_t out_bytes = hoh_encode_images_out_bytes(&hg, n_images);
+    const size_t dev_packed_cap = raw + raw / 4 + 4096 * n_streams;
+    uint8_t *d_rgb, *d_out, *d_packed;
+    hoh_stream_result* d_res;
+    uint64_t* d_off;
+    TRY(scratch_t(ctx, S_IO_A, raw, &d_rgb));
+    TRY(scratch_t(ctx, S_IO_B, out_bytes, &d_out));
+    TRY(scratch_t(ctx, S_IO_C, dev_packed_cap, &d_packed));
+    TRY(scratch_t(ctx, S_RESULTS, n_streams, &d_res));
+    TRY(scratch_t(ctx, S_IO_D, n_streams + 1, &d_off));
+    CK(cudaMemcpyAsync(d_rgb, rgb_host, raw, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(hoh_encode_images_s0(ctx, d_rgb, n_images, width, height, nullptr, d_out, out_bytes, d_res, d_packed,
+                             dev_packed_cap, d_off));
+    CK(cudaMemcpyAsync(off_host, d_off, (n_streams + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (results_host)
+        CK(cudaMemcpyAsync(results_host, d_res, n_streams * sizeof(hoh_stream_result), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t total = off_host[n_streams];
+    if (total > packed_cap || total > dev_packed_cap) return HOH_E_CAPACITY;
+    CK(cudaMemcpyAsync(packed_host, d_packed, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HOH_OK;
+}
+
+int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t packed_bytes,
+                              const uint64_t* off_host, size_t n_images, uint32_t width, uint32_t height,
+                              uint8_t* rgb_host, int32_t* status_host) {
+    if (!ctx || !rgb_host || !packed_host || !off_host) return HOH_E_ARG;
+    if (n_images == 0) return HOH_OK;
+    hoh_tile_geometry hg;
+    TRY(hoh_tile_geometry_for(width, height, &hg));
+    const size_t raw = (size_t)n_images * width * height * 3;
+    const size_t n_streams = n_images * hg.streams_per_image;
+    const size_t padded = (packed_bytes + 31) & ~(size_t)15;
+    uint8_t *d_rgb, *d_packed;
+    uint64_t* d_off;
+    int32_t* d_st;
+    TRY(scratch_t(ctx, S_IO_A, raw, &d_rgb));
+    TRY(scratch_t(ctx, S_IO_C, padded, &d_packed));
+    TRY(scratch_t(ctx, S_IO_D, n_streams + 1, &d_off));
+    TRY(scratch_t(ctx, S_IO_E, n_streams, &d_st));
+    CK(cudaMemsetAsync(d_packed + (packed_bytes & ~(size_t)15), 0, padded - (packed_bytes & ~(size_t)15), ctx->stream));
+    CK(cudaMemcpyAsync(d_packed, packed_host, packed_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_off, off_host, (n_streams + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(hoh_decode_images_s0(ctx, d_packed, padded, d_off, n_images, width, height, nullptr, d_rgb, d_st));
+    CK(cudaMemcpyAsync(rgb_host, d_rgb, raw, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status_host)
+        CK(cudaMemcpyAsync(status_host, d_st, n_streams * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HOH_OK;
+}
+
+// =================================================================================================
+// batched plane kernels
+// =================================================================================================
+int hoh_subtract_green_dev(hoh_ctx* ctx, const uint8_t* d_rgb, size_t pixels, uint16_t* d_g, uint16_t* d_rg,
+                           uint16_t* d_bg) {
+    if (!ctx || !d_rgb || !d_g || !d_rg || !d_bg) return HOH_E_ARG;
+    if (!pixels) return HOH_OK;
+    k_subtract_green<<<grid_cap(pixels, 256), 256, 0, ctx->stream>>>(d_rgb, pixels, d_g, d_rg, d_bg);
+    LAUNCHED("k_subtract_green");
+    return HOH_OK;
+}
+
+int hoh_add_green_dev(hoh_ctx* ctx, const uint16_t* d_g, const uint16_t* d_rg, const uint16_t* d_bg, size_t pixels,
+                      uint8_t* d_rgb) {
+    if (!ctx || !d_rgb || !d_g || !d_rg || !d_bg) return HOH_E_ARG;
+    if (!pixels) return HOH_OK;
+    k_add_green<<<grid_cap(pixels, 256), 256, 0, ctx->stream>>>(d_g, d_rg, d_bg, pixels, d_rgb);
+    LAUNCHED("k_add_green");
+    return HOH_OK;
+}
+
+int hoh_predict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
+                             uint16_t* d_resid) {
+    if (!ctx || !d_planes || !d_resid || w <= 0 || h <= 0 || depth < 1 || depth > 9) return HOH_E_ARG;
+    if (!n_planes) return HOH_OK;
+    k_predict_fastpath<<<grid_cap((uint64_t)n_planes * w * h, 256), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h,
+                                                                                          depth, d_resid);
+    LAUNCHED("k_predict_fastpath");
+    return HOH_OK;
+}
+
+int hoh_unpredict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_planes, int w, int h, int depth,
+                               const uint16_t* d_backref, uint16_t* d_planes) {
+    if (!ctx || !d_planes || !d_resid || w <= 0 || h <= 0 || depth < 1 || depth > 9) return HOH_E_ARG;
+    if (!n_planes) return HOH_OK;
+    TRY(ensure_smem_opt_in(ctx));
+    if (d_backref || (size_t)w * 2 * 4 > 200 * 1024) {
+        k_unpredict_fastpath_serial<<<blocks_for(n_planes, 64), 64, 0, ctx->stream>>>(d_resid, n_planes, w, h, depth,
+                                                                                      d_backref, d_planes);
+        LAUNCHED("k_unpredict_fastpath_serial");
+    } else {
+        k_unpredict_fastpath_wave<<<blocks_for(n_planes, 4), 128, (size_t)w * 2 * 4, ctx->stream>>>(
+            d_resid, n_planes, w, h, depth, d_planes);
+        LAUNCHED("k_unpredict_fastpath_wave");
+    }
+    return HOH_OK;
+}
+
+int hoh_predict_all_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
+                        int x_tiles, int y_tiles, const uint16_t* d_tile_maps, uint16_t* d_resid) {
+    if (!ctx || !d_planes || !d_resid || !d_tile_maps || w <= 0 || h <= 0 || depth < 1 || depth > 9 || x_tiles <= 0 ||
+        y_tiles <= 0)
+        return HOH_E_ARG;
+    if (!n_planes) return HOH_OK;
+    uint16_t* top;
+    uint8_t* bp;
+    TRY(scratch_t(ctx, S_TOP, n_planes * (size_t)w, &top));
+    TRY(scratch_t(ctx, S_BP, n_planes * (size_t)w, &bp));
+    k_raster_walk<false><<<blocks_for(n_planes, 64), 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, x_tiles,
+                                                                          y_tiles, d_tile_maps, nullptr, d_resid, top, bp);
+    LAUNCHED("k_raster_walk<predict>");
+    return HOH_OK;
+}
+
+int hoh_unpredict_all_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_planes, int w, int h, int depth,
+                          int x_tiles, int y_tiles, const uint16_t* d_tile_maps, const uint16_t* d_backref,
+                          uint16_t* d_planes) {
+    if (!ctx || !d_planes || !d_resid || !d_tile_maps || w <= 0 || h <= 0 || depth < 1 || depth > 9 || x_tiles <= 0 ||
+        y_tiles <= 0)
+        return HOH_E_ARG;
+    if (!n_planes) return HOH_OK;
+    uint16_t* top;
+    uint8_t* bp;
+    TRY(scratch_t(ctx, S_TOP, n_planes * (size_t)w, &top));
+    TRY(scratch_t(ctx, S_BP, n_planes * (size_t)w, &bp));
+    k_raster_walk<true><<<blocks_for(n_planes, 64), 64, 0, ctx->stream>>>(d_resid, n_planes, w, h, depth, x_tiles,
+                                                                         y_tiles, d_tile_maps, d_backref, d_planes, top, bp);
+    LAUNCHED("k_raster_walk<unpredict>");
+    return HOH_OK;
+}
+
+int hoh_predict_section_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
+                            int x_tiles, int y_tiles, const uint16_t* d_masks, int n_masks, uint16_t* d_resid,
+                            uint32_t cell_cap, uint32_t* d_counts) {
+    if (!ctx || !d_planes || !d_resid || !d_masks || !d_counts || w <= 0 || h <= 0 || depth < 1 || depth > 9 ||
+        x_tiles <= 0 || y_tiles <= 0 || n_masks <= 0)
+        return HOH_E_ARG;
+    if (!n_planes) return HOH_OK;
+    const uint64_t jobs = (uint64_t)n_planes * x_tiles * y_tiles * n_masks;
+    const int tw = (w + x_tiles - 1) / x_tiles;
+    uint16_t* wtop = nullptr;
+    uint8_t* wbp = nullptr;
+    if (tw > kMaxCellW) {
+        TRY(scratch_t(ctx, S_WIDE_TOP, jobs * tw, &wtop));
+        TRY(scratch_t(ctx, S_WIDE_BP, jobs * tw, &wbp));
+    }
+    k_section<false><<<blocks_for(jobs, 64), 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, x_tiles, y_tiles,
+                                                                  d_masks, n_masks, d_resid, cell_cap, d_counts, nullptr,
+                                                                  nullptr, wtop, wbp);
+    LAUNCHED("k_section<resid>");
+    return HOH_OK;
+}
+
+int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
+                             int mode, uint16_t* d_tile_maps, uint8_t* d_index_lists, uint16_t* d_resid) {
+    if (!ctx || !d_planes || !d_resid || !d_tile_maps || !d_index_lists || w <= 0 || h <= 0 || depth < 1 ||
+        depth > 9 || mode < 1)
+        return HOH_E_ARG;
+    if (!n_planes) return HOH_OK;
+    const int grid = 40;  // layer_encode.hpp:124
+    const int xt = (w + grid - 1) / grid, yt = (h + grid - 1) / grid;
+    const int cells = xt * yt;
+    const int n_masks = mode * 5 < 14 ? mode * 5 : 14;  // layer_encode.hpp:178
+    const int c = 1 << depth;
+    const uint64_t per = (uint64_t)w * h;
+    const uint64_t jobs = (uint64_t)n_planes * cells * n_masks;
+    uint32_t* hist;
+    double *cost, *sums, *e_tab;
+    uint16_t* masks;
+    uint16_t* top;
+    uint8_t* bp;
+    uint32_t e_len;
+    TRY(scratch_t(ctx, S_HIST, n_planes * (size_t)c, &hist));
+    TRY(scratch_t(ctx, S_COST, n_planes * (size_t)c, &cost));
+    TRY(scratch_t(ctx, S_SUMS, jobs, &sums));
+    TRY(scratch_t(ctx, S_MASKS, 16, &masks));
+    TRY(scratch_t(ctx, S_TOP, n_planes * (size_t)w, &top));
+    TRY(scratch_t(ctx, S_BP, n_planes * (size_t)w, &bp));
+    TRY(cost_table_for(ctx, per, &e_tab, &e_len));
+    CK(cudaMemcpyAsync(masks, kStockMasks, sizeof kStockMasks, cudaMemcpyHostToDevice, ctx->stream));
+    k_predict_fastpath<<<grid_cap(n_planes * per, 256), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, d_resid);
+    LAUNCHED("k_predict_fastpath");
+    const int passes = mode > 2 ? 2 : 1;  // layer_encode.hpp:215
+    for (int pass = 0; pass < passes; pass++) {
+        k_plane_histogram<<<(unsigned)n_planes, 256, 0, ctx->stream>>>(d_resid, (uint32_t)per, depth, hist);
+        LAUNCHED("k_plane_histogram");
+        k_cost_from_hist<<<blocks_for(n_planes * (uint64_t)c, 256), 256, 0, ctx->stream>>>(hist, n_planes * (uint64_t)c,
+                                                                                          e_tab, e_len, cost);
+        LAUNCHED("k_cost_from_hist");
+        k_section<true><<<blocks_for(jobs, 64), 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks,
+                                                                     n_masks, nullptr, 0, nullptr, cost, sums, nullptr,
+                                                                     nullptr);
+        LAUNCHED("k_section<cost>");
+        k_pick_masks<<<blocks_for(n_planes * (uint64_t)cells, 256), 256, 0, ctx->stream>>>(
+            sums, n_planes * (uint64_t)cells, n_masks, masks, d_tile_maps, d_index_lists);
+        LAUNCHED("k_pick_masks");
+        k_raster_walk<false><<<blocks_for(n_planes, 64), 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt,
+                                                                              d_tile_maps, nullptr, d_resid, top, bp);
+        LAUNCHED("k_raster_walk<predict>");
+    }
+    return HOH_OK;
+}
+
+// =================================================================================================
+// compat shims (host pointers)
+// =================================================================================================
+
+int hoh_encode_entropy(hoh_ctx* ctx, const uint16_t* symbols, size_t n, size_t range, uint8_t* out, size_t out_cap,
+                       uint32_t prob_bits, size_t* out_size, int* stream_status) {
+    if (!ctx || (!symbols && n) || !out || !out_size) return HOH_E_ARG;
+    if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > HOH_MAX_PROB_BITS || n > 0xfffffff0ull)
+        return HOH_E_UNSUPPORTED;
+    uint16_t* d_sym;
+    TRY(stage_in(ctx, S_IO_A, symbols, n, &d_sym));
+    hoh_enc_stream st;
+    memset(&st, 0, sizeof st);
+    st.n = (uint32_t)n;
+    st.range = (uint32_t)range;
+    st.prob_bits = prob_bits;
+    st.out_cap = (uint32_t)hoh_enc_slab_bytes(n, prob_bits);
+    hoh_enc_stream* d_st;
+    TRY(stage_in(ctx, S_IO_B, &st, 1, &d_st));
+    uint8_t* d_out;
+    hoh_stream_result* d_res;
+    TRY(scratch_t(ctx, S_IO_C, st.out_cap, &d_out));
+    TRY(scratch_t(ctx, S_RESULTS, 1, &d_res));
+    TRY(hoh_encode_entropy_batch(ctx, d_st, 1, d_sym, d_out, d_res, (uint32_t)range, prob_bits, (uint32_t)n));
+    hoh_stream_result res;
+    TRY(stage_out(ctx, &res, d_res, 1));
+    if (stream_status) *stream_status = res.status;
+    *out_size = 0;
+    if (res.status != HOH_S_OK) return HOH_E_STREAM;
+    if (res.size > out_cap) return HOH_E_CAPACITY;
+    TRY(stage_out(ctx, out, d_out + res.start, res.size));
+    *out_size = res.size;
+    return HOH_OK;
+}
+
+int hoh_encode_entropy_8bit(hoh_ctx* ctx, const uint8_t* symbols, size_t n, size_t range, uint8_t* out,
+                            size_t out_cap, uint32_t prob_bits, size_t* out_size, int* stream_status) {
+    // entropy_encoding.hpp:283-303 widens to u16 and calls the 16-bit form
+    std::vector<uint16_t> wide(n);
+    for (size_t i = 0; i < n; i++) wide[i] = symbols[i];
+    return hoh_encode_entropy(ctx, wide.data(), n, range, out, out_cap, prob_bits, out_size, stream_status);
+}
+
+int hoh_decode_entropy(hoh_ctx* ctx, const uint8_t* in, size_t in_size, size_t* byte_pointer, uint16_t* symbols,
+                       size_t symbols_cap, size_t* symbol_size, unsigned flags, int* stream_status) {
+    if (!ctx || !in || !byte_pointer || !symbol_size || (!symbols && symbols_cap)) return HOH_E_ARG;
+    uint8_t* d_in;
+    const size_t padded = (in_size + 31) & ~(size_t)15;
+    TRY(scratch_t(ctx, S_IO_A, padded, &d_in));
+    CK(cudaMemsetAsync(d_in + (in_size & ~(size_t)15), 0, padded - (in_size & ~(size_t)15), ctx->stream));
+    CK(cudaMemcpyAsync(d_in, in, in_size, cudaMemcpyHostToDevice, ctx->stream));
+    hoh_dec_stream st;
+    memset(&st, 0, sizeof st);
+    st.in_off = *byte_pointer;
+    st.sym_cap = (uint32_t)(symbols_cap > 0xfffffff0ull ? 0xfffffff0ull : symbols_cap);
+    st.flags = flags;
+    hoh_dec_stream* d_st;
+    TRY(stage_in(ctx, S_IO_B, &st, 1, &d_st));
+    uint16_t* d_sym;
+    hoh_dec_result* d_res;
+    TRY(scratch_t(ctx, S_IO_C, symbols_cap + 64, &d_sym));
+    TRY(scratch_t(ctx, S_DRESULTS, 1, &d_res));
+    TRY(hoh_decode_entropy_batch(ctx, d_st, 1, d_in, padded, d_sym, d_res, (uint32_t)st.sym_cap));
+    hoh_dec_result res;
+    TRY(stage_out(ctx, &res, d_res, 1));
+    if (stream_status) *stream_status = res.status;
+    *symbol_size = res.n;
+    *byte_pointer = res.end_off;
+    size_t take = res.n < symbols_cap ? res.n : symbols_cap;
+    if (res.status != HOH_S_OK && res.status != HOH_S_OVERFLOW) return HOH_E_STREAM;
+    TRY(stage_out(ctx, symbols, d_sym, take));
+    return res.status == HOH_S_OK ? HOH_OK : HOH_E_CAPACITY;
+}
+
+int hoh_normalize_freqs(hoh_ctx* ctx, uint32_t* freqs, uint32_t* cum_freqs, size_t size, uint32_t target_total,
+                        int* stream_status) {
+    if (!ctx || !freqs || !cum_freqs || size == 0) return HOH_E_ARG;
+    if (size > HOH_MAX_RANGE) return HOH_E_UNSUPPORTED;
+    uint32_t *d_f, *d_c;
+    int32_t* d_s;
+    TRY(stage_in(ctx, S_IO_A, freqs, size, &d_f));
+    TRY(scratch_t(ctx, S_IO_B, size + 1, &d_c));
+    TRY(scratch_t(ctx, S_IO_C, 1, &d_s));
+    k_normalize_only<<<1, 32, 0, ctx->stream>>>(d_f, d_c, (uint32_t)size, target_total, d_s);
+    LAUNCHED("k_normalize_only");
+    int32_t st;
+    TRY(stage_out(ctx, &st, d_s, 1));
+    if (stream_status) *stream_status = st;
+    if (st != HOH_S_OK) return HOH_E_STREAM;
+    TRY(stage_out(ctx, freqs, d_f, size));
+    TRY(stage_out(ctx, cum_freqs, d_c, size + 1));
+    return HOH_OK;
+}
+
+int hoh_subtract_green(hoh_ctx* ctx, const uint8_t* rgb, size_t size, uint16_t* green, uint16_t* red_g,
+                       uint16_t* blue_g) {
+    if (!ctx || !rgb || !green || !red_g || !blue_g) return HOH_E_ARG;
+    const size_t px = size / 3;
+    uint8_t* d_rgb;
+    uint16_t* d_pl;
+    TRY(stage_in(ctx, S_IO_A, rgb, px * 3, &d_rgb));
+    TRY(scratch_t(ctx, S_IO_B, px * 3, &d_pl));
+    TRY(hoh_subtract_green_dev(ctx, d_rgb, px, d_pl, d_pl + px, d_pl + 2 * px));
+    TRY(stage_out(ctx, green, d_pl, px));
+    TRY(stage_out(ctx, red_g, d_pl + px, px));
+    TRY(stage_out(ctx, blue_g, d_pl + 2 * px, px));
+    return HOH_OK;
+}
+
+int hoh_add_green(hoh_ctx* ctx, const uint16_t* green, const uint16_t* red_g, const uint16_t* blue_g, size_t pixels,
+                  uint8_t* rgb) {
+    if (!ctx || !rgb || !green || !red_g || !blue_g) return HOH_E_ARG;
+    uint16_t* d_pl;
+    uint8_t* d_rgb;
+    TRY(scratch_t(ctx, S_IO_B, pixels * 3, &d_pl));
+    TRY(scratch_t(ctx, S_IO_A, pixels * 3, &d_rgb));
+    CK(cudaMemcpyAsync(d_pl, green, pixels * 2, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_pl + pixels, red_g, pixels * 2, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_pl + 2 * pixels, blue_g, pixels * 2, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(hoh_add_green_dev(ctx, d_pl, d_pl + pixels, d_pl + 2 * pixels, pixels, d_rgb));
+    TRY(stage_out(ctx, rgb, d_rgb, pixels * 3));
+    return HOH_OK;
+}
+
+int hoh_channelpredict_fastpath(hoh_ctx* ctx, const uint16_t* data, int w, int h, int depth, uint16_t* out) {
+    if (!ctx || !data || !out || w <= 0 || h <= 0) return HOH_E_ARG;
+    const size_t px = (size_t)w * h;
+    uint16_t *d_in, *d_out;
+    TRY(stage_in(ctx, S_IO_A, data, px, &d_in));
+    TRY(scratch_t(ctx, S_IO_B, px, &d_out));
+    TRY(hoh_predict_fastpath_dev(ctx, d_in, 1, w, h, depth, d_out));
+    return stage_out(ctx, out, d_out, px);
+}
+
+int hoh_channelpredict_section(hoh_ctx* ctx, const uint16_t* data, int w, int h, int depth, int x_tiles, int y_tiles,
+                               int x, int y, uint16_t predictor, uint16_t* out, size_t out_cap, size_t* out_count) {
+    if (!ctx || !data || !out || !out_count || w <= 0 || h <= 0 || x_tiles <= 0 || y_tiles <= 0 || x < 0 || y < 0 ||
+        x >= x_tiles || y >= y_tiles)
+        return HOH_E_ARG;
+    const size_t px = (size_t)w * h;
+    const int tw = (w + x_tiles - 1) / x_tiles, th = (h + y_tiles - 1) / y_tiles;
+    const uint32_t cell_cap = (uint32_t)tw * th;
+    const size_t cells = (size_t)x_tiles * y_tiles;
+    uint16_t *d_in, *d_mask, *d_res;
+    uint32_t* d_cnt;
+    TRY(stage_in(ctx, S_IO_A, data, px, &d_in));
+    TRY(stage_in(ctx, S_IO_B, &predictor, 1, &d_mask));
+    TRY(scratch_t(ctx, S_IO_C, cells * cell_cap, &d_res));
+    TRY(scratch_t(ctx, S_IO_D, cells, &d_cnt));
+    TRY(hoh_predict_section_dev(ctx, d_in, 1, w, h, depth, x_tiles, y_tiles, d_mask, 1, d_res, cell_cap, d_cnt));
+    const size_t cell = (size_t)y * x_tiles + x;
+    uint32_t cnt;
+    TRY(stage_out(ctx, &cnt, d_cnt + cell, 1));
+    *out_count = cnt;
+    if (cnt > out_cap) return HOH_E_CAPACITY;
+    return stage_out(ctx, out, d_res + cell * cell_cap, cnt);
+}
+
+int hoh_channelpredict_all(hoh_ctx* ctx, const uint16_t* data, int w, int h, int depth, int x_tiles, int y_tiles,
+                           const uint16_t* tile_map, uint16_t* out) {
+    if (!ctx || !data || !out || !tile_map || w <= 0 || h <= 0 || x_tiles <= 0 || y_tiles <= 0) return HOH_E_ARG;
+    const size_t px = (size_t)w * h;
+    uint16_t *d_in, *d_map, *d_out;
+    TRY(stage_in(ctx, S_IO_A, data, px, &d_in));
+    TRY(stage_in(ctx, S_IO_B, tile_map, (size_t)x_tiles * y_tiles, &d_map));
+    TRY(scratch_t(ctx, S_IO_C, px, &d_out));
+    TRY(hoh_predict_all_dev(ctx, d_in, 1, w, h, depth, x_tiles, y_tiles, d_map, d_out));
+    return stage_out(ctx, out, d_out, px);
+}
+
+int hoh_unpredict_all(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, int w, int h, int depth, int x_tiles,
+                      int y_tiles, const uint16_t* tile_map, const uint16_t* backref, uint16_t* out) {
+    if (!ctx || !resid || !out || !tile_map || w <= 0 || h <= 0 || x_tiles <= 0 || y_tiles <= 0) return HOH_E_ARG;
+    const size_t px = (size_t)w * h;
+    if (n_resid > px) n_resid = px;
+    uint16_t *d_in, *d_map, *d_out, *d_br = nullptr;
+    TRY(scratch_t(ctx, S_IO_A, px, &d_in));
+    CK(cudaMemsetAsync(d_in, 0, px * 2, ctx->stream));
+    CK(cudaMemcpyAsync(d_in, resid, n_resid * 2, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(stage_in(ctx, S_IO_B, tile_map, (size_t)x_tiles * y_tiles, &d_map));
+    TRY(scratch_t(ctx, S_IO_C, px, &d_out));
+    if (backref) TRY(stage_in(ctx, S_IO_D, backref, px, &d_br));
+    TRY(hoh_unpredict_all_dev(ctx, d_in, 1, w, h, depth, x_tiles, y_tiles, d_map, d_br, d_out));
+    return stage_out(ctx, out, d_out, px);
+}
+
+int hoh_unpredict_fastpath(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, int w, int h, int depth,
+                           const uint16_t* backref, uint16_t* out) {
+    if (!ctx || !resid || !out || w <= 0 || h <= 0) return HOH_E_ARG;
+    const size_t px = (size_t)w * h;
+    if (n_resid > px) n_resid = px;
+    uint16_t *d_in, *d_out, *d_br = nullptr;
+    TRY(scratch_t(ctx, S_IO_A, px, &d_in));
+    CK(cudaMemsetAsync(d_in, 0, px * 2, ctx->stream));
+    CK(cudaMemcpyAsync(d_in, resid, n_resid * 2, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(scratch_t(ctx, S_IO_C, px, &d_out));
+    if (backref) TRY(stage_in(ctx, S_IO_D, backref, px, &d_br));
+    TRY(hoh_unpredict_fastpath_dev(ctx, d_in, 1, w, h, depth, d_br, d_out));
+    return stage_out(ctx, out, d_out, px);
+}
+
+int hoh_predictor_search(hoh_ctx* ctx, const uint16_t* plane, int w, int h, int depth, int mode, uint16_t* tile_map,
+                         uint8_t* index_list, uint16_t* final_resid) {
+    if (!ctx || !plane || !tile_map || !index_list || w <= 0 || h <= 0) return HOH_E_ARG;
+    const size_t px = (size_t)w * h;
+    const size_t cells = (size_t)((w + 39) / 40) * ((h + 39) / 40);
+    uint16_t *d_in, *d_map, *d_res;
+    uint8_t* d_idx;
+    TRY(stage_in(ctx, S_IO_A, plane, px, &d_in));
+    TRY(scratch_t(ctx, S_IO_B, cells, &d_map));
+    TRY(scratch_t(ctx, S_IO_C, px, &d_res));
+    TRY(scratch_t(ctx, S_IO_D, cells, &d_idx));
+    TRY(hoh_predictor_search_dev(ctx, d_in, 1, w, h, depth, mode, d_map, d_idx, d_res));
+    TRY(stage_out(ctx, tile_map, d_map, cells));
+    TRY(stage_out(ctx, index_list, d_idx, cells));
+    if (final_resid) TRY(stage_out(ctx, final_resid, d_res, px));
+    return HOH_OK;
+}
+
+}  // extern "C"

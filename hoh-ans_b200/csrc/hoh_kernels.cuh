@@ -1,0 +1,1500 @@
+// hoh_kernels.cuh — sm_100a kernels of the hoh-ANS hot path (included once, by hoh_api.cu).
+//
+// Parallelisation: the format gives every entropy stream ONE Rans64 state, so
+// a stream is a serial chain and throughput comes from running one stream per warp lane over many
+// independent streams (channel x tile x image).  Per-stream frequency tables live in shared memory
+// laid out [symbol][lane] so that 32 lanes indexing 32 different tables never collide on a bank;
+// symbols are moved between HBM and the lanes through a padded shared-memory transpose so that
+// every global access is a coalesced row; renormalisation words go straight to / from each lane's
+// own slab (L2 merges the sectors).  Prediction kernels are per-pixel data parallel on the encode
+// side and an anti-diagonal wavefront (one row per lane, skewed by one column) on the decode side.
+//
+// Reference functions restated (file:line into the reference tree) are named at each kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hohgpu.h"
+#include "hoh_format.cuh"
+
+namespace hohk {
+
+constexpr int kFreqRow = 512;   // u32 per stream in the histogram / frequency scratch
+constexpr int kCumRow = 520;    // u32 per stream in the cumulative-table scratch (range+1 used)
+constexpr int kChunk = 64;      // symbols per lane between two shared-memory refills
+constexpr int kSymStride = 66;  // u16 per staged row (64 + 2 pad -> 33 words: conflict-free transpose)
+constexpr uint64_t kRansL = 1ull << 31;  // rans64.hpp:59
+
+// Per-stream scratch the encode pipeline threads through its kernels.
+struct EncMeta {
+    uint64_t payload_start;  // byte offset of the first payload word in the output buffer
+    uint32_t payload_bytes;
+    uint32_t head_len;     // varints + metadata + table
+    uint32_t stored_size;  // entropy_encoding.hpp:45
+    int32_t status;
+    uint32_t table_u16;  // 1 if prob_bits <= 16 (cum table fits 16-bit lanes)
+    uint32_t pad;
+};
+
+// Per-stream scratch of the decode pipeline.
+struct DecMeta {
+    uint64_t payload_off;  // byte offset of the rANS payload (or of the stored symbols)
+    uint32_t n;
+    uint32_t range;
+    uint32_t prob_bits;
+    uint32_t kind;  // 0 nothing to do, 1 stored, 2 rANS
+    uint32_t maxbits;
+    int32_t status;
+};
+
+// Bounds-clamped byte view of the input buffer: malformed streams read zeros, never fault.
+struct ByteView {
+    const uint8_t* base;
+    uint64_t size;
+    __host__ __device__ __forceinline__ uint8_t operator[](uint64_t i) const { return i < size ? base[i] : (uint8_t)0; }
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if ((int)lane_id() >= d) v += o;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
+// =================================================================================================
+// Symbol histogram — entropy_encoding.hpp:32-39.  One CTA per stream, shared-memory atomics.
+// =================================================================================================
+__global__ void __launch_bounds__(256) k_histogram(const hoh_enc_stream* __restrict__ streams,
+                                                   const uint16_t* __restrict__ symbols,
+                                                   uint32_t* __restrict__ freqs) {
+    __shared__ uint32_t hist[kFreqRow];
+    const hoh_enc_stream st = streams[blockIdx.x];
+    for (int i = threadIdx.x; i < kFreqRow; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint16_t* src = symbols + st.sym_off;
+    for (uint32_t i = threadIdx.x; i < st.n; i += blockDim.x) {
+        uint32_t s = src[i];
+        if (s < st.range) atomicAdd(&hist[s], 1u);
+    }
+    __syncthreads();
+    uint32_t* dst = freqs + (size_t)blockIdx.x * kFreqRow;
+    for (int i = threadIdx.x; i < kFreqRow; i += blockDim.x) dst[i] = hist[i];
+}
+
+// =================================================================================================
+// Table build — stattools.hpp:6-70 (calc_cum_freqs, normalize_freqs) + entropy_encoding.hpp:43-203
+// (header, clamp search, table serialisation).  One warp per stream.
+// =================================================================================================
+// Exclusive prefix sum of v[0..count) into out[0..count], each lane owning a contiguous run.
+__device__ __forceinline__ void warp_cumsum(const uint32_t* v, uint32_t* out, uint32_t count) {
+    const uint32_t lane = lane_id();
+    const uint32_t per = (count + 31u) / 32u;
+    const uint32_t lo = min(lane * per, count), hi = min(lo + per, count);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += v[i];
+    uint32_t run = warp_incl_scan(sum) - sum;
+    for (uint32_t i = lo; i < hi; i++) {
+        out[i] = run;
+        run += v[i];
+    }
+    __syncwarp();
+    // total = last exclusive + last value; computed by lane 0 to keep it simple and race free
+    if (lane == 0) out[count] = count ? out[count - 1] + v[count - 1] : 0u;
+    __syncwarp();
+}
+
+// Rescales raw counts `f` (range entries, in shared memory) to sum to 2^prob_bits with every used
+// symbol kept non-zero — stattools.hpp:13-70.  `sc` is a second shared array.  On return f holds the
+// normalised frequencies and cum[0..range] their prefix sums.  Returns HOH_S_*.
+__device__ int warp_normalize(uint32_t* f, uint32_t* sc, uint32_t* cum, uint32_t range, uint32_t target) {
+    const uint32_t lane = lane_id();
+    if (target < range) return HOH_S_RANGE_GT_TOTAL;  // stattools.hpp:14
+    warp_cumsum(f, cum, range);
+    const uint32_t total = cum[range];
+    __syncwarp();
+    // stattools.hpp:20-24: cum[i] = target * cum[i] / total, then scaled freq = difference
+    for (uint32_t i = lane; i < range; i += 32) {
+        uint32_t a = (uint32_t)(((uint64_t)target * cum[i]) / total);
+        uint32_t b = (uint32_t)(((uint64_t)target * cum[i + 1]) / total);
+        sc[i] = b - a;
+    }
+    __syncwarp();
+    // stattools.hpp:28-57: every used symbol that rounded to zero takes one count from the
+    // lowest-index symbol of smallest frequency > 1, in ascending thief order.
+    int status = HOH_S_OK;
+    for (uint32_t base = 0; base < range; base += 32) {
+        uint32_t i = base + lane;
+        bool thief = i < range && f[i] != 0 && sc[i] == 0;
+        uint32_t pending = __ballot_sync(0xffffffffu, thief);
+        while (pending) {
+            uint32_t who = base + (uint32_t)__ffs((int)pending) - 1u;
+            pending &= pending - 1u;
+            uint32_t key = 0xffffffffu;
+            for (uint32_t j = lane; j < range; j += 32) {
+                uint32_t v = sc[j];
+                if (v > 1u) key = min(key, (v << 10) | j);
+            }
+            key = warp_min(key);
+            if (key == 0xffffffffu) {
+                status = HOH_S_NO_DONOR;  // stattools.hpp:42
+                pending = 0;
+                base = range;
+                break;
+            }
+            if (lane == 0) {
+                sc[key & 1023u]--;
+                sc[who] = 1;
+            }
+            __syncwarp();
+        }
+    }
+    if (status != HOH_S_OK) return status;
+    for (uint32_t i = lane; i < range; i += 32) f[i] = sc[i];
+    __syncwarp();
+    warp_cumsum(f, cum, range);
+    return HOH_S_OK;
+}
+
+constexpr int kTableWarps = 4;
+
+__global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
+    const hoh_enc_stream* __restrict__ streams, uint32_t n_streams, const uint32_t* __restrict__ freqs,
+    uint32_t* __restrict__ cumtab, uint8_t* __restrict__ heads, EncMeta* __restrict__ meta) {
+    __shared__ uint32_t s_f[kTableWarps][kFreqRow];
+    __shared__ uint32_t s_sc[kTableWarps][kFreqRow];
+    __shared__ uint32_t s_cum[kTableWarps][kFreqRow + 8];
+    __shared__ __align__(16) uint8_t s_head[kTableWarps][HOH_HEAD_CAP];
+    const uint32_t w = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t s = blockIdx.x * kTableWarps + w;
+    if (s >= n_streams) return;
+    const hoh_enc_stream st = streams[s];
+    EncMeta m;
+    m.payload_start = 0;
+    m.payload_bytes = 0;
+    m.head_len = 0;
+    m.stored_size = 0;
+    m.status = HOH_S_OK;
+    m.table_u16 = st.prob_bits <= 16 ? 1u : 0u;
+    m.pad = 0;
+    uint8_t* head = heads + (size_t)s * HOH_HEAD_CAP;
+    if (st.n == 0) {  // entropy_encoding.hpp:19-23: two varints and nothing else (D2)
+        if (lane == 0) {
+            uint32_t at = hohfmt::put_varint(s_head[w], 0, st.range - 1);
+            at = hohfmt::put_varint(s_head[w], at, 0);
+            for (uint32_t k = 0; k < at; k++) head[k] = s_head[w][k];
+            m.head_len = at;
+            meta[s] = m;
+        }
+        return;
+    }
+    uint32_t* f = s_f[w];
+    uint32_t* sc = s_sc[w];
+    uint32_t* cum = s_cum[w];
+    const uint32_t* src = freqs + (size_t)s * kFreqRow;
+    for (uint32_t i = lane; i < st.range; i += 32) f[i] = src[i];
+    __syncwarp();
+    int status = warp_normalize(f, sc, cum, st.range, 1u << st.prob_bits);
+    if (status != HOH_S_OK) {
+        if (lane == 0) {
+            m.status = status;
+            meta[s] = m;
+        }
+        return;
+    }
+    uint32_t* ct = cumtab + (size_t)s * kCumRow;
+    for (uint32_t i = lane; i <= st.range; i += 32) ct[i] = cum[i];
+    if (lane == 0) m.head_len = hohfmt::build_head(f, st.range, st.n, st.prob_bits, s_head[w], &m.stored_size);
+    m.head_len = __shfl_sync(0xffffffffu, m.head_len, 0);
+    __syncwarp();
+    const uint32_t words = (m.head_len + 3u) / 4u;
+    for (uint32_t k = lane; k < words; k += 32)
+        reinterpret_cast<uint32_t*>(head)[k] = reinterpret_cast<const uint32_t*>(s_head[w])[k];
+    if (lane == 0) meta[s] = m;
+}
+
+// =================================================================================================
+// Rans64 core — rans64.hpp.  One state per lane.
+// =================================================================================================
+// rans64.hpp:262-278 (Rans64EncPutSymbol) == rans64.hpp:77-94 (Rans64EncPut) for every reachable
+// state: x' = ((x / f) << bits) + x % f + start after the optional 32-bit renormalisation.
+// The reference multiplies by a precomputed 64-bit reciprocal per symbol (24 B/symbol: 12 KB per
+// stream, far beyond 32 per-lane tables in shared memory); here the quotient is estimated with one
+// FP64 multiply by 1/f and corrected with exact integer arithmetic, so the result is exact whatever
+// the estimate's rounding was.
+__device__ __forceinline__ uint64_t rans_put(uint64_t x, uint32_t start, uint32_t freq, uint32_t bits,
+                                             uint32_t*& wp, const uint32_t* wp_floor, bool& overflow) {
+    const uint64_t x_max = (uint64_t)freq << (63u - bits);  // ((L >> bits) << 32) * freq
+    if (x >= x_max) {
+        if (wp > wp_floor) *--wp = (uint32_t)x; else overflow = true;
+        x >>= 32;
+    }
+    const double inv = __drcp_rn((double)freq);
+    uint64_t q = __double2ull_rz(__ull2double_rz(x) * inv);
+    int64_t r = (int64_t)(x - q * (uint64_t)freq);
+    while (r < 0) {
+        q--;
+        r += freq;
+    }
+    while (r >= (int64_t)freq) {
+        q++;
+        r -= freq;
+    }
+    return (q << bits) + (uint64_t)r + start;
+}
+
+// Table accessors.  PerLane: tab[(symbol * 32 + lane)] — 32 independent tables, bank == lane.
+template <typename CumT>
+struct PerLaneTable {
+    const CumT* tab;
+    uint32_t lane;
+    __device__ __forceinline__ uint32_t cum(uint32_t s) const { return tab[s * 32u + lane]; }
+};
+// Shared: one table for every lane (static-table sweep).
+template <typename CumT>
+struct SharedTable {
+    const CumT* tab;
+    __device__ __forceinline__ uint32_t cum(uint32_t s) const { return tab[s]; }
+};
+
+template <typename CumT>
+__device__ __forceinline__ uint32_t freq_from(uint32_t c0, uint32_t c1, uint32_t bits);
+template <>
+__device__ __forceinline__ uint32_t freq_from<uint32_t>(uint32_t c0, uint32_t c1, uint32_t) {
+    return c1 - c0;
+}
+template <>
+__device__ __forceinline__ uint32_t freq_from<uint16_t>(uint32_t c0, uint32_t c1, uint32_t bits) {
+    // 16-bit lanes hold cum mod 65536: only cum[range] == 65536 (prob_bits 16) wraps, and then a
+    // zero difference can only mean the one symbol that owns everything.
+    uint32_t f = (c1 - c0) & 0xffffu;
+    return (f == 0u && bits == 16u) ? 65536u : f;
+}
+
+// Cooperative load of one 64-symbol chunk for the 32 streams of a warp into the padded transpose.
+// Row r of `stage` receives symbols [64*chunk, 64*chunk+64) of stream r (zero beyond its n).
+__device__ __forceinline__ void stage_load_chunk(uint16_t* stage, const uint16_t* __restrict__ symbols,
+                                                 const uint64_t* s_off, const uint32_t* s_n, uint32_t chunk) {
+    const uint32_t lane = lane_id(), half = lane >> 4, q = lane & 15u;
+    uint32_t* stage32 = reinterpret_cast<uint32_t*>(stage);
+#pragma unroll 4
+    for (uint32_t jj = 0; jj < 16; jj++) {
+        const uint32_t r = 2u * jj + half;
+        const uint32_t first = chunk * kChunk + 4u * q;
+        const uint32_t n = s_n[r];
+        uint2 v = make_uint2(0u, 0u);
+        if (first + 3u < n) {
+            v = *reinterpret_cast<const uint2*>(symbols + s_off[r] + first);
+        } else if (first < n) {
+            const uint16_t* p = symbols + s_off[r] + first;
+            uint32_t a = p[0];
+            uint32_t b = first + 1u < n ? p[1] : 0u;
+            uint32_t c = first + 2u < n ? p[2] : 0u;
+            v = make_uint2(a | (b << 16), c);
+        }
+        stage32[r * (kSymStride / 2) + 2u * q] = v.x;
+        stage32[r * (kSymStride / 2) + 2u * q + 1u] = v.y;
+    }
+}
+
+// Inverse: rows of `stage` -> global symbol arrays (decode side).
+__device__ __forceinline__ void stage_store_chunk(const uint16_t* stage, uint16_t* __restrict__ symbols,
+                                                  const uint64_t* s_off, const uint32_t* s_n, uint32_t chunk) {
+    const uint32_t lane = lane_id(), half = lane >> 4, q = lane & 15u;
+    const uint32_t* stage32 = reinterpret_cast<const uint32_t*>(stage);
+#pragma unroll 4
+    for (uint32_t jj = 0; jj < 16; jj++) {
+        const uint32_t r = 2u * jj + half;
+        const uint32_t first = chunk * kChunk + 4u * q;
+        const uint32_t n = s_n[r];
+        const uint32_t a = stage32[r * (kSymStride / 2) + 2u * q];
+        const uint32_t b = stage32[r * (kSymStride / 2) + 2u * q + 1u];
+        if (first + 3u < n) {
+            *reinterpret_cast<uint2*>(symbols + s_off[r] + first) = make_uint2(a, b);
+        } else if (first < n) {
+            uint16_t* p = symbols + s_off[r] + first;
+            p[0] = (uint16_t)a;
+            if (first + 1u < n) p[1] = (uint16_t)(a >> 16);
+            if (first + 2u < n) p[2] = (uint16_t)b;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// rANS encode, per-stream tables — entropy_encoding.hpp:206-238.  One warp per CTA, one stream per
+// lane.  Dynamic shared memory: (rows * 32) CumT + 32 * kSymStride u16.
+// -------------------------------------------------------------------------------------------------
+template <typename CumT>
+__global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __restrict__ streams,
+                                                    uint32_t n_streams, const uint16_t* __restrict__ symbols,
+                                                    const uint32_t* __restrict__ cumtab, uint8_t* __restrict__ out,
+                                                    EncMeta* __restrict__ meta, uint32_t rows, uint32_t want_u16) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    CumT* tab = reinterpret_cast<CumT*>(smem_raw);
+    uint16_t* stage = reinterpret_cast<uint16_t*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));
+    __shared__ uint64_t s_off[32];
+    __shared__ uint32_t s_n[32];
+
+    const uint32_t lane = lane_id();
+    const uint32_t s = blockIdx.x * 32u + lane;
+    const bool exists = s < n_streams;
+    hoh_enc_stream st;
+    EncMeta m;
+    if (exists) {
+        st = streams[s];
+        m = meta[s];
+    } else {
+        st.n = 0;
+        st.range = 1;
+        st.prob_bits = 1;
+        st.sym_off = 0;
+        st.out_off = 0;
+        st.out_cap = 0;
+        m.status = HOH_S_OK;
+        m.table_u16 = want_u16;
+    }
+    // a stream takes part if it has symbols, its table was built, and it belongs to this launch's
+    // table width (16-bit lanes for prob_bits <= 16, 32-bit otherwise)
+    const bool live = exists && st.n > 0 && m.status == HOH_S_OK && m.table_u16 == want_u16;
+    s_off[lane] = st.sym_off;
+    s_n[lane] = live ? st.n : 0u;
+    if (__ballot_sync(0xffffffffu, live) == 0u) return;
+
+    // tables: stream j's row i -> tab[i*32 + j]
+    for (uint32_t j = 0; j < 32; j++) {
+        const uint32_t sj = blockIdx.x * 32u + j;
+        const bool lj = __shfl_sync(0xffffffffu, (int)live, j) != 0;
+        const uint32_t rj = __shfl_sync(0xffffffffu, st.range, j);
+        if (!lj) continue;
+        const uint32_t* src = cumtab + (size_t)sj * kCumRow;
+        for (uint32_t i = lane; i <= rj; i += 32) tab[i * 32u + j] = (CumT)src[i];
+    }
+    __syncwarp();
+
+    const PerLaneTable<CumT> T{tab, lane};
+    const uint32_t bits = st.prob_bits;
+    uint32_t* wp = reinterpret_cast<uint32_t*>(out + st.out_off + st.out_cap);
+    const uint32_t* wp_floor = reinterpret_cast<const uint32_t*>(out + st.out_off) + (HOH_HEAD_CAP + 32) / 4;
+    bool overflow = false;
+    uint64_t x = kRansL;  // rans64.hpp:65
+
+    uint32_t n_max = s_n[lane];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
+    const uint32_t my_n = live ? st.n : 0u;
+    const uint16_t* my_row = stage + lane * kSymStride;
+
+    for (int chunk = (int)((n_max + kChunk - 1) / kChunk) - 1; chunk >= 0; chunk--) {
+        __syncwarp();
+        stage_load_chunk(stage, symbols, s_off, s_n, (uint32_t)chunk);
+        __syncwarp();
+        const uint32_t base = (uint32_t)chunk * kChunk;
+#pragma unroll 4
+        for (int k = kChunk - 1; k >= 0; k--) {  // entropy_encoding.hpp:222-225, last symbol first
+            if (base + (uint32_t)k < my_n) {
+                const uint32_t sym = my_row[k];
+                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+                x = rans_put(x, c0, freq_from<CumT>(c0, c1, bits), bits, wp, wp_floor, overflow);
+            }
+        }
+    }
+    if (live) {
+        // rans64.hpp:96-103 flush: low word at the lower address
+        if (wp - 2 >= wp_floor) {
+            wp -= 2;
+            wp[0] = (uint32_t)x;
+            wp[1] = (uint32_t)(x >> 32);
+        } else {
+            overflow = true;
+        }
+        m.payload_start = (uint64_t)(reinterpret_cast<uint8_t*>(wp) - out);
+        m.payload_bytes = (uint32_t)(st.out_off + st.out_cap - m.payload_start);
+        if (overflow) m.status = HOH_S_OVERFLOW;
+        meta[s] = m;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Finish — entropy_encoding.hpp:232-267: length varint in front of the payload, or the stored-mode
+// rewrite when that is smaller.  One warp per stream.  The header is written immediately in front
+// of the payload (which already sits at the END of the stream's slab), so the payload never moves.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_finish_streams(const hoh_enc_stream* __restrict__ streams,
+                                                        uint32_t n_streams, const uint16_t* __restrict__ symbols,
+                                                        const uint8_t* __restrict__ heads,
+                                                        const EncMeta* __restrict__ meta, uint8_t* __restrict__ out,
+                                                        hoh_stream_result* __restrict__ results) {
+    const uint32_t s = blockIdx.x * 4u + (threadIdx.x >> 5), lane = lane_id();
+    if (s >= n_streams) return;
+    const hoh_enc_stream st = streams[s];
+    const EncMeta m = meta[s];
+    const uint8_t* head = heads + (size_t)s * HOH_HEAD_CAP;
+    hoh_stream_result res;
+    res.status = m.status;
+    res.payload_bytes = 0;
+    res.stored = 0;
+    res.start = st.out_off;
+    res.size = 0;
+    if (m.status != HOH_S_OK) {
+        if (lane == 0) results[s] = res;
+        return;
+    }
+    if (st.n == 0) {
+        uint8_t* dst = out + st.out_off;
+        if (lane == 0) {
+            for (uint32_t k = 0; k < st.prefix_len; k++) dst[k] = st.prefix[k];
+            for (uint32_t k = 0; k < m.head_len; k++) dst[st.prefix_len + k] = head[k];
+            res.size = st.prefix_len + m.head_len;
+            results[s] = res;
+        }
+        return;
+    }
+    const uint32_t vlen = hohfmt::varint_len(m.payload_bytes);
+    const uint32_t coded = m.head_len + vlen + m.payload_bytes;  // what encode_entropy returns
+    if (m.stored_size < coded) {  // entropy_encoding.hpp:244-267
+        uint8_t* dst = out + st.out_off;
+        const uint32_t maxbits = hohfmt::bit_length(st.range - 1);
+        uint32_t at = st.prefix_len;
+        if (lane == 0) {
+            for (uint32_t k = 0; k < st.prefix_len; k++) dst[k] = st.prefix[k];
+            uint32_t a = hohfmt::put_varint(dst, at, st.range - 1);
+            a = hohfmt::put_varint(dst, a, st.n);
+            dst[a] = 0;
+        }
+        at += hohfmt::varint_len(st.range - 1) + hohfmt::varint_len(st.n) + 1u;
+        const uint32_t body = (uint32_t)(((uint64_t)maxbits * st.n + 7) / 8);
+        const uint16_t* sym = symbols + st.sym_off;
+        for (uint32_t b = lane; b < body; b += 32) {  // MSB-first packing, symbol i at bit i*maxbits
+            uint32_t byte = 0;
+            for (uint32_t k = 0; k < 8; k++) {
+                const uint64_t bit = (uint64_t)b * 8u + k;
+                const uint64_t i = bit / maxbits;
+                uint32_t v = 0;
+                if (i < st.n) v = (sym[i] >> (maxbits - 1u - (uint32_t)(bit % maxbits))) & 1u;
+                byte = (byte << 1) | v;
+            }
+            dst[at + b] = (uint8_t)byte;
+        }
+        res.size = st.prefix_len + m.stored_size;
+        res.stored = 1;
+        if (lane == 0) results[s] = res;
+        return;
+    }
+    const uint32_t front = st.prefix_len + m.head_len + vlen;
+    uint8_t* dst = out + m.payload_start - front;
+    for (uint32_t k = lane; k < st.prefix_len; k += 32) dst[k] = st.prefix[k];
+    for (uint32_t k = lane; k < m.head_len; k += 32) dst[st.prefix_len + k] = head[k];
+    if (lane == 0) {
+        hohfmt::put_varint(dst, st.prefix_len + m.head_len, m.payload_bytes);
+        res.start = m.payload_start - front;
+        res.size = front + m.payload_bytes;
+        res.payload_bytes = m.payload_bytes;
+        results[s] = res;
+    }
+}
+
+// =================================================================================================
+// Decode: header + table parse — entropy_decoding.hpp:143-253.  One warp per stream.
+// =================================================================================================
+__global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
+    const hoh_dec_stream* __restrict__ streams, uint32_t n_streams, const uint8_t* __restrict__ in,
+    uint64_t in_bytes, uint32_t* __restrict__ cumtab, DecMeta* __restrict__ meta,
+    hoh_dec_result* __restrict__ results) {
+    __shared__ uint32_t s_f[kTableWarps][kFreqRow];
+    __shared__ uint32_t s_cum[kTableWarps][kFreqRow + 8];
+    const uint32_t w = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t s = blockIdx.x * kTableWarps + w;
+    if (s >= n_streams) return;
+    const hoh_dec_stream st = streams[s];
+    const ByteView bytes{in, in_bytes};
+    uint32_t* f = s_f[w];
+    uint32_t* cum = s_cum[w];
+
+    // lane 0 walks the bit-serial parts; the fields are then broadcast
+    hohfmt::StreamHead h;
+    uint64_t after_table = 0;
+    int status = HOH_S_OK;
+    if (lane == 0) {
+        h = hohfmt::parse_head(bytes, st.in_off, st.flags);
+        after_table = h.body;
+        if (!h.empty && h.rans) {
+            if (h.range > HOH_MAX_RANGE) {
+                status = HOH_S_BAD_TABLE;
+            } else if (h.table_mode == 1 || h.table_mode == 2) {
+                after_table = hohfmt::parse_table(bytes, h, f);
+            } else if (h.table_mode == 3) {
+                status = HOH_S_BAD_TABLE;
+            }
+        }
+    }
+    h.range = __shfl_sync(0xffffffffu, h.range, 0);
+    h.n = __shfl_sync(0xffffffffu, h.n, 0);
+    h.maxbits = __shfl_sync(0xffffffffu, h.maxbits, 0);
+    h.rans = __shfl_sync(0xffffffffu, h.rans, 0);
+    h.prob_bits = __shfl_sync(0xffffffffu, h.prob_bits, 0);
+    h.table_mode = __shfl_sync(0xffffffffu, h.table_mode, 0);
+    h.empty = __shfl_sync(0xffffffffu, h.empty, 0);
+    h.body = __shfl_sync(0xffffffffu, h.body, 0);
+    after_table = __shfl_sync(0xffffffffu, after_table, 0);
+    status = __shfl_sync(0xffffffffu, status, 0);
+    __syncwarp();
+
+    DecMeta m;
+    m.payload_off = h.body;
+    m.n = h.n;
+    m.range = h.range;
+    m.prob_bits = h.prob_bits;
+    m.kind = 0;
+    m.maxbits = h.maxbits;
+    m.status = status;
+    hoh_dec_result res;
+    res.end_off = h.body;
+    res.n = h.n;
+    res.status = status;
+    res.range = h.range;
+    res.prob_bits = h.prob_bits;
+    res.stored = 0;
+    res.table_mode = h.table_mode;
+
+    if (h.empty) {
+        // nothing
+    } else if (!h.rans) {  // entropy_decoding.hpp:278-290
+        m.kind = 1;
+        res.stored = 1;
+        res.end_off = h.body + ((uint64_t)h.maxbits * h.n + 7) / 8;
+    } else if (status == HOH_S_OK) {
+        const uint32_t target = h.prob_bits < 32 ? (1u << h.prob_bits) : 0u;
+        if (h.table_mode == 0) {  // entropy_decoding.hpp:174-179: flat counts through normalize_freqs
+            if (target < h.range) {
+                status = HOH_S_RANGE_GT_TOTAL;
+            } else {
+                for (uint32_t i = lane; i < h.range; i += 32) {
+                    uint32_t a = (uint32_t)(((uint64_t)target * i) / h.range);
+                    uint32_t b = (uint32_t)(((uint64_t)target * (i + 1)) / h.range);
+                    f[i] = b - a;
+                }
+            }
+        }
+        __syncwarp();
+        if (status == HOH_S_OK) {
+            warp_cumsum(f, cum, h.range);  // stattools.hpp:6-11
+            uint32_t* ct = cumtab + (size_t)s * kCumRow;
+            for (uint32_t i = lane; i <= h.range; i += 32) ct[i] = cum[i];
+            uint64_t at = after_table;
+            const uint32_t payload = hohfmt::get_varint(bytes, &at);  // entropy_decoding.hpp:256
+            m.payload_off = at;
+            m.kind = 2;
+            res.end_off = (st.flags & HOH_FIX_ADVANCE) ? at + payload : at;  // D8
+        }
+        m.status = status;
+        res.status = status;
+    }
+    if (m.n > st.sym_cap) {
+        m.status = m.status == HOH_S_OK ? HOH_S_OVERFLOW : m.status;
+        res.status = m.status;
+    }
+    if (lane == 0) {
+        meta[s] = m;
+        results[s] = res;
+    }
+}
+
+// Stored-mode symbols — entropy_decoding.hpp:278-290.  One CTA per stream, exits unless stored.
+__global__ void __launch_bounds__(256) k_unpack_stored(const hoh_dec_stream* __restrict__ streams,
+                                                       const uint8_t* __restrict__ in, uint64_t in_bytes,
+                                                       const DecMeta* __restrict__ meta,
+                                                       uint16_t* __restrict__ symbols) {
+    const DecMeta m = meta[blockIdx.x];
+    if (m.kind != 1) return;
+    const hoh_dec_stream st = streams[blockIdx.x];
+    const ByteView bytes{in, in_bytes};
+    const uint32_t n = min(m.n, st.sym_cap);
+    uint16_t* dst = symbols + st.sym_off;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint64_t bit = (uint64_t)i * m.maxbits;
+        uint32_t v = 0;
+        for (uint32_t k = 0; k < m.maxbits; k++, bit++)
+            v = (v << 1) | ((bytes[m.payload_off + (bit >> 3)] >> (7u - (uint32_t)(bit & 7u))) & 1u);
+        dst[i] = (uint16_t)v;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// rANS decode, per-stream tables — entropy_decoding.hpp:254-276 with rans64.hpp:107-142.
+// cum2sym (2^prob_bits entries, :262-267) is replaced by a search over the cumulative table, which
+// returns the same symbol by construction.
+// -------------------------------------------------------------------------------------------------
+struct WordReader {  // unaligned little-endian u32 stream from aligned loads
+    const uint32_t* base;  // aligned word that holds the next payload byte
+    const uint32_t* last;  // last readable aligned word of the input buffer
+    uint32_t shift;        // 8 * misalignment
+    uint32_t cur, nxt;
+    __device__ __forceinline__ void open(const uint8_t* in, uint64_t in_bytes, uint64_t off) {
+        const uint64_t addr = reinterpret_cast<uint64_t>(in) + off;
+        base = reinterpret_cast<const uint32_t*>(addr & ~3ull);
+        shift = (uint32_t)(addr & 3ull) * 8u;
+        const uint64_t end = (reinterpret_cast<uint64_t>(in) + in_bytes) & ~3ull;
+        last = reinterpret_cast<const uint32_t*>(end) - 1;
+        cur = *(base < last ? base : last);
+        nxt = *(base + 1 < last ? base + 1 : last);
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(cur, nxt, shift); }
+    __device__ __forceinline__ void advance() {
+        base++;
+        cur = nxt;
+        nxt = *(base + 1 < last ? base + 1 : last);
+    }
+};
+
+template <typename CumT, typename Table>
+__device__ __forceinline__ uint32_t rans_find(const Table& T, uint32_t slot, uint32_t range, uint32_t steps) {
+    // largest s in [0, range) with cum[s] <= slot
+    uint32_t lo = 0, hi = range;
+    for (uint32_t it = 0; it < steps; it++) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t c = T.cum(mid);
+        const bool go_up = (hi - lo > 1u) && c <= slot;
+        const bool go_dn = (hi - lo > 1u) && c > slot;
+        lo = go_up ? mid : lo;
+        hi = go_dn ? mid : hi;
+    }
+    return lo;
+}
+
+template <typename CumT>
+__global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __restrict__ streams,
+                                                    uint32_t n_streams, const uint8_t* __restrict__ in,
+                                                    uint64_t in_bytes, const uint32_t* __restrict__ cumtab,
+                                                    const DecMeta* __restrict__ meta,
+                                                    uint16_t* __restrict__ symbols, uint32_t rows,
+                                                    uint32_t want_u16) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    CumT* tab = reinterpret_cast<CumT*>(smem_raw);
+    uint16_t* stage = reinterpret_cast<uint16_t*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));
+    __shared__ uint64_t s_off[32];
+    __shared__ uint32_t s_n[32];
+
+    const uint32_t lane = lane_id();
+    const uint32_t s = blockIdx.x * 32u + lane;
+    const bool exists = s < n_streams;
+    hoh_dec_stream st;
+    DecMeta m;
+    st.sym_off = 0;
+    st.sym_cap = 0;
+    m.kind = 0;
+    m.n = 0;
+    m.range = 1;
+    m.prob_bits = 1;
+    m.payload_off = 0;
+    m.status = HOH_S_OK;
+    if (exists) {
+        st = streams[s];
+        m = meta[s];
+    }
+    const bool is_u16 = m.prob_bits <= 16u;
+    const bool live = exists && m.kind == 2u && m.n > 0u && (is_u16 ? 1u : 0u) == want_u16 && m.range + 1u <= rows;
+    const uint32_t my_n = live ? min(m.n, st.sym_cap) : 0u;
+    s_off[lane] = st.sym_off;
+    s_n[lane] = my_n;
+    if (__ballot_sync(0xffffffffu, live) == 0u) return;
+
+    for (uint32_t j = 0; j < 32; j++) {
+        const uint32_t sj = blockIdx.x * 32u + j;
+        const bool lj = __shfl_sync(0xffffffffu, (int)live, j) != 0;
+        const uint32_t rj = __shfl_sync(0xffffffffu, m.range, j);
+        if (!lj) continue;
+        const uint32_t* src = cumtab + (size_t)sj * kCumRow;
+        for (uint32_t i = lane; i <= rj; i += 32) tab[i * 32u + j] = (CumT)src[i];
+    }
+    __syncwarp();
+
+    const PerLaneTable<CumT> T{tab, lane};
+    const uint32_t bits = m.prob_bits;
+    const uint32_t mask = (bits < 32u ? (1u << bits) : 0u) - 1u;
+    uint32_t range_max = live ? m.range : 1u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) range_max = max(range_max, __shfl_xor_sync(0xffffffffu, range_max, d));
+    const uint32_t steps = 32u - __clz(max(range_max, 2u) - 1u);  // ceil(log2(range_max))
+    uint32_t n_max = my_n;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
+
+    WordReader rd;
+    uint64_t x = 0;
+    if (live) {  // rans64.hpp:107-116: state = first two payload words, low word first
+        rd.open(in, in_bytes, m.payload_off);
+        uint32_t lo = rd.peek();
+        rd.advance();
+        uint32_t hi = rd.peek();
+        rd.advance();
+        x = (uint64_t)lo | ((uint64_t)hi << 32);
+    }
+    uint16_t* my_row = stage + lane * kSymStride;
+    const uint32_t chunks = (n_max + kChunk - 1) / kChunk;
+    for (uint32_t chunk = 0; chunk < chunks; chunk++) {
+        const uint32_t base = chunk * kChunk;
+        __syncwarp();
+#pragma unroll 2
+        for (uint32_t k = 0; k < (uint32_t)kChunk; k++) {
+            if (base + k < my_n) {
+                const uint32_t slot = (uint32_t)x & mask;                               // rans64.hpp:118-121
+                const uint32_t sym = rans_find<CumT>(T, slot, m.range, steps);         // cum2sym[slot]
+                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+                const uint32_t f = freq_from<CumT>(c0, c1, bits);
+                x = (uint64_t)f * (x >> bits) + slot - c0;                              // rans64.hpp:126-134
+                if (x < kRansL) {                                                       // rans64.hpp:137-141
+                    x = (x << 32) | rd.peek();
+                    rd.advance();
+                }
+                my_row[k] = (uint16_t)sym;
+            }
+        }
+        __syncwarp();
+        stage_store_chunk(stage, symbols, s_off, s_n, chunk);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Static-table sweep (config 4): rans64.hpp loops with one table shared by every stream.
+// Streams are implicit: stream i = symbols [i*stream_len, ...).  4 warps per CTA share the table.
+// -------------------------------------------------------------------------------------------------
+constexpr int kStaticWarps = 4;
+
+__global__ void __launch_bounds__(kStaticWarps * 32) k_rans_encode_static(
+    const uint16_t* __restrict__ symbols, uint64_t n_total, uint32_t stream_len,
+    const uint32_t* __restrict__ cum_g, uint32_t range, uint32_t bits, uint8_t* __restrict__ out,
+    uint32_t slab_bytes, uint32_t* __restrict__ payload_bytes) {
+    __shared__ uint32_t s_cum[HOH_MAX_RANGE + 8];
+    __shared__ __align__(16) uint16_t s_stage[kStaticWarps][32 * kSymStride];
+    __shared__ uint64_t s_off[kStaticWarps][32];
+    __shared__ uint32_t s_n[kStaticWarps][32];
+    for (uint32_t i = threadIdx.x; i <= range; i += blockDim.x) s_cum[i] = cum_g[i];
+    const uint32_t w = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t n_streams = (n_total + stream_len - 1) / stream_len;
+    const uint64_t s = ((uint64_t)blockIdx.x * kStaticWarps + w) * 32u + lane;
+    const bool live = s < n_streams;
+    const uint64_t first = s * stream_len;
+    const uint32_t my_n = live ? (uint32_t)min((uint64_t)stream_len, n_total - first) : 0u;
+    s_off[w][lane] = live ? first : 0ull;
+    s_n[w][lane] = my_n;
+    __syncthreads();
+    if (__ballot_sync(0xffffffffu, live) == 0u) return;
+    const SharedTable<uint32_t> T{s_cum};
+    uint16_t* stage = s_stage[w];
+    uint8_t* slab = out + s * slab_bytes;
+    uint32_t* wp = reinterpret_cast<uint32_t*>(slab + slab_bytes);
+    const uint32_t* wp_floor = reinterpret_cast<const uint32_t*>(slab);
+    if (!live) wp = const_cast<uint32_t*>(wp_floor = nullptr);
+    bool overflow = false;
+    uint64_t x = kRansL;
+    uint32_t n_max = my_n;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
+    const uint16_t* my_row = stage + lane * kSymStride;
+    for (int chunk = (int)((n_max + kChunk - 1) / kChunk) - 1; chunk >= 0; chunk--) {
+        __syncwarp();
+        stage_load_chunk(stage, symbols, s_off[w], s_n[w], (uint32_t)chunk);
+        __syncwarp();
+        const uint32_t base = (uint32_t)chunk * kChunk;
+#pragma unroll 4
+        for (int k = kChunk - 1; k >= 0; k--) {
+            if (base + (uint32_t)k < my_n) {
+                const uint32_t sym = my_row[k];
+                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+                x = rans_put(x, c0, c1 - c0, bits, wp, wp_floor, overflow);
+            }
+        }
+    }
+    if (live) {
+        if (wp - 2 >= wp_floor) {
+            wp -= 2;
+            wp[0] = (uint32_t)x;
+            wp[1] = (uint32_t)(x >> 32);
+        } else {
+            overflow = true;
+        }
+        payload_bytes[s] = overflow ? 0xffffffffu : (uint32_t)(slab + slab_bytes - reinterpret_cast<uint8_t*>(wp));
+    }
+}
+
+__global__ void __launch_bounds__(kStaticWarps * 32) k_rans_decode_static(
+    const uint8_t* __restrict__ in, uint32_t slab_bytes, const uint32_t* __restrict__ payload_bytes,
+    uint64_t n_total, uint32_t stream_len, const uint32_t* __restrict__ cum_g, uint32_t range,
+    uint32_t bits, uint16_t* __restrict__ symbols) {
+    __shared__ uint32_t s_cum[HOH_MAX_RANGE + 8];
+    __shared__ __align__(16) uint16_t s_stage[kStaticWarps][32 * kSymStride];
+    __shared__ uint64_t s_off[kStaticWarps][32];
+    __shared__ uint32_t s_n[kStaticWarps][32];
+    for (uint32_t i = threadIdx.x; i <= range; i += blockDim.x) s_cum[i] = cum_g[i];
+    const uint32_t w = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t n_streams = (n_total + stream_len - 1) / stream_len;
+    const uint64_t s = ((uint64_t)blockIdx.x * kStaticWarps + w) * 32u + lane;
+    const bool exists = s < n_streams;
+    const uint64_t first = s * stream_len;
+    const uint32_t pb = exists ? payload_bytes[s] : 0u;
+    const bool live = exists && pb >= 8u && pb <= slab_bytes;
+    const uint32_t my_n = live ? (uint32_t)min((uint64_t)stream_len, n_total - first) : 0u;
+    s_off[w][lane] = live ? first : 0ull;
+    s_n[w][lane] = my_n;
+    __syncthreads();
+    if (__ballot_sync(0xffffffffu, live) == 0u) return;
+    const SharedTable<uint32_t> T{s_cum};
+    const uint32_t mask = (1u << bits) - 1u;
+    const uint32_t steps = 32u - __clz(max(range, 2u) - 1u);
+    uint32_t n_max = my_n;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
+    WordReader rd;
+    uint64_t x = 0;
+    if (live) {
+        const uint64_t total_bytes = n_streams * (uint64_t)slab_bytes;
+        rd.open(in, total_bytes, (s + 1) * (uint64_t)slab_bytes - pb);
+        uint32_t lo = rd.peek();
+        rd.advance();
+        uint32_t hi = rd.peek();
+        rd.advance();
+        x = (uint64_t)lo | ((uint64_t)hi << 32);
+    }
+    uint16_t* stage = s_stage[w];
+    uint16_t* my_row = stage + lane * kSymStride;
+    const uint32_t chunks = (n_max + kChunk - 1) / kChunk;
+    for (uint32_t chunk = 0; chunk < chunks; chunk++) {
+        const uint32_t base = chunk * kChunk;
+        __syncwarp();
+#pragma unroll 2
+        for (uint32_t k = 0; k < (uint32_t)kChunk; k++) {
+            if (base + k < my_n) {
+                const uint32_t slot = (uint32_t)x & mask;
+                const uint32_t sym = rans_find<uint32_t>(T, slot, range, steps);
+                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+                x = (uint64_t)(c1 - c0) * (x >> bits) + slot - c0;
+                if (x < kRansL) {
+                    x = (x << 32) | rd.peek();
+                    rd.advance();
+                }
+                my_row[k] = (uint16_t)sym;
+            }
+        }
+        __syncwarp();
+        stage_store_chunk(stage, symbols, s_off[w], s_n[w], chunk);
+    }
+}
+
+// =================================================================================================
+// Offsets and gather — "stream-offset prefix sums with warp shuffles" + the final gather.
+// =================================================================================================
+// Exclusive scan of results[i].size into off[0..n]; one CTA of 1024 threads, serial over tiles of 1024.
+__global__ void __launch_bounds__(1024) k_scan_sizes(const hoh_stream_result* __restrict__ results,
+                                                     uint32_t n, uint64_t* __restrict__ off) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = (i < n && results[i].status == HOH_S_OK) ? results[i].size : 0ull;
+        uint64_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            uint64_t t = warp_tot[lane];
+            uint64_t ti = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t o = __shfl_up_sync(0xffffffffu, ti, d);
+                if ((int)lane >= d) ti += o;
+            }
+            warp_tot[lane] = ti - t;  // exclusive over warps
+        }
+        __syncthreads();
+        const uint64_t c = carry;
+        if (i < n) off[i] = c + warp_tot[w] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + warp_tot[w] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n] = carry;
+}
+
+// Copies every stream's bytes to its packed position.  One CTA per stream; destination-aligned
+// 32-bit stores fed by two aligned source loads and a funnel shift.
+__global__ void __launch_bounds__(256) k_gather_streams(const hoh_stream_result* __restrict__ results,
+                                                        const uint8_t* __restrict__ src,
+                                                        const uint64_t* __restrict__ off, uint8_t* __restrict__ dst,
+                                                        uint64_t dst_cap) {
+    const hoh_stream_result r = results[blockIdx.x];
+    if (r.status != HOH_S_OK || r.size == 0) return;
+    const uint64_t d0 = off[blockIdx.x];
+    if (d0 + r.size > dst_cap) return;
+    const uint8_t* s = src + r.start;
+    uint8_t* d = dst + d0;
+    // head: bytes until d is 4-aligned
+    const uint32_t lead = min((uint32_t)((4u - (uint32_t)(reinterpret_cast<uint64_t>(d) & 3u)) & 3u), r.size);
+    if (threadIdx.x < lead) d[threadIdx.x] = s[threadIdx.x];
+    const uint32_t words = (r.size - lead) / 4u;
+    const uint8_t* sb = s + lead;
+    const uint64_t sa = reinterpret_cast<uint64_t>(sb);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~3ull);
+    const uint32_t sh = (uint32_t)(sa & 3ull) * 8u;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(d + lead);
+    if (sh == 0) {
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dw[i] = sw[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dw[i] = __funnelshift_r(sw[i], sw[i + 1], sh);
+    }
+    const uint32_t done = lead + words * 4u;
+    if (threadIdx.x < r.size - done) d[done + threadIdx.x] = s[done + threadIdx.x];
+}
+
+// =================================================================================================
+// Predictor primitives — predictor_operations.hpp (u16 forms, C int promotion semantics)
+// =================================================================================================
+__device__ __forceinline__ int p_mid(int a, int b) { return a + (b - a) / 2; }  // :8-10, truncating
+__device__ __forceinline__ int p_med(int a, int b, int c) {                     // :37-60
+    const int lo = min(a, b), hi = max(a, b);
+    return c < lo ? lo : (c > hi ? hi : c);
+}
+__device__ __forceinline__ int p_avg3(int a, int b, int c) { return (a + b + c) / 3; }  // :66-68
+__device__ __forceinline__ int p_paeth(int A, int B, int C) {                            // :89-106
+    const int p = A + B - C;
+    const int da = abs(A - p), db = abs(B - p), dc = abs(C - p);
+    if (da < db) return da < dc ? A : C;
+    return db < dc ? B : C;
+}
+// median(T, L, (u16)(T + L - TL)): the gradient wraps to u16 before the median
+__device__ __forceinline__ int p_med_grad(int T, int L, int TL) { return p_med(T, L, (T + L - TL) & 0xffff); }
+
+// =================================================================================================
+// Colour transform — channel.hpp:73-79 and its algebraic inverse
+// =================================================================================================
+__global__ void k_subtract_green(const uint8_t* __restrict__ rgb, uint64_t pixels, uint16_t* __restrict__ g,
+                                 uint16_t* __restrict__ rg, uint16_t* __restrict__ bg) {
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < pixels; p += (uint64_t)gridDim.x * blockDim.x) {
+        const int r = rgb[3 * p], gg = rgb[3 * p + 1], b = rgb[3 * p + 2];
+        g[p] = (uint16_t)gg;
+        rg[p] = (uint16_t)(r - gg + 256);
+        bg[p] = (uint16_t)(b - gg + 256);
+    }
+}
+
+__global__ void k_add_green(const uint16_t* __restrict__ g, const uint16_t* __restrict__ rg,
+                            const uint16_t* __restrict__ bg, uint64_t pixels, uint8_t* __restrict__ rgb) {
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < pixels; p += (uint64_t)gridDim.x * blockDim.x) {
+        const int gg = g[p];
+        rgb[3 * p] = (uint8_t)((rg[p] + gg - 256) & 255);
+        rgb[3 * p + 1] = (uint8_t)gg;
+        rgb[3 * p + 2] = (uint8_t)((bg[p] + gg - 256) & 255);
+    }
+}
+
+// =================================================================================================
+// channelpredict_fastpath — prediction.hpp:6-44.  Per-pixel data parallel on planes.
+// =================================================================================================
+__global__ void k_predict_fastpath(const uint16_t* __restrict__ planes, uint64_t n_planes, int w, int h,
+                                   int depth, uint16_t* __restrict__ resid) {
+    const int c = 1 << depth, half = c >> 1;
+    const uint64_t per = (uint64_t)w * h, total = per * n_planes;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t at = i % per;
+        const int x = (int)(at % w), y = (int)(at / w);
+        const uint16_t* p = planes + i;
+        const int L = x ? p[-1] : half;
+        const int T = y ? p[-w] : half;
+        const int TL = (x && y) ? p[-w - 1] : half;
+        resid[i] = (uint16_t)(((int)p[0] - p_med_grad(T, L, TL) + half + c) % c);
+    }
+}
+
+// Raster-serial inverse of the above for one plane per thread (used when back-references are
+// present: unprediction.hpp:63-65 makes a pixel depend on an arbitrary earlier one).
+__global__ void k_unpredict_fastpath_serial(const uint16_t* __restrict__ resid, uint64_t n_planes, int w, int h,
+                                            int depth, const uint16_t* __restrict__ backref,
+                                            uint16_t* __restrict__ planes) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_planes) return;
+    const int c = 1 << depth, half = c >> 1;
+    const uint64_t per = (uint64_t)w * h;
+    const uint16_t* r = resid + p * per;
+    const uint16_t* br = backref ? backref + p * per : nullptr;
+    uint16_t* o = planes + p * per;
+    uint64_t k = 0;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint64_t at = (uint64_t)y * w + x;
+            if (br && br[at]) {
+                o[at] = o[at - br[at]];
+                continue;
+            }
+            const int L = x ? o[at - 1] : half;
+            const int T = y ? o[at - w] : half;
+            const int TL = (x && y) ? o[at - w - 1] : half;
+            o[at] = (uint16_t)(((int)r[k++] + p_med_grad(T, L, TL) - half) & (c - 1));
+        }
+}
+
+// Wavefront inverse of channelpredict_fastpath on planes: one warp per plane, lane = row inside a
+// 32-row band, lane r works on column t - r at step t, T comes from lane r-1 by shuffle.
+__global__ void __launch_bounds__(128) k_unpredict_fastpath_wave(const uint16_t* __restrict__ resid,
+                                                                 uint64_t n_planes, int w, int h, int depth,
+                                                                 uint16_t* __restrict__ planes) {
+    extern __shared__ uint16_t s_rows[];  // 4 warps * w: last row of the previous band
+    const uint32_t wid = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t p = (uint64_t)blockIdx.x * 4u + wid;
+    if (p >= n_planes) return;
+    const int c = 1 << depth, half = c >> 1;
+    const uint64_t per = (uint64_t)w * h;
+    const uint16_t* r = resid + p * per;
+    uint16_t* o = planes + p * per;
+    uint16_t* carry = s_rows + (size_t)wid * w;
+    for (int band = 0; band * 32 < h; band++) {
+        const int y = band * 32 + (int)lane;
+        const bool row_ok = y < h;
+        int left = half, top_left = half, mine = half;
+        for (int t = 0; t < w + 31; t++) {
+            const int x = t - (int)lane;
+            int top = __shfl_up_sync(0xffffffffu, mine, 1);
+            if (lane == 0) top = (band && x >= 0 && x < w) ? carry[x] : half;
+            if (y == 0) top = half;
+            if (row_ok && x >= 0 && x < w) {
+                if (x == 0) {
+                    left = half;
+                    top_left = half;
+                }
+                if (y == 0) top_left = half;
+                const int v = ((int)r[(uint64_t)y * w + x] + p_med_grad(top, left, top_left) - half) & (c - 1);
+                o[(uint64_t)y * w + x] = (uint16_t)v;
+                mine = v;
+                left = v;
+                top_left = top;
+                if (lane == 31) carry[x] = (uint16_t)v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
+// channelpredict_all / unpredict_all — prediction.hpp:153-229, unprediction.hpp:6-91.
+// One plane per thread, raster order (the chain is serial: SURVEY H4); row state in global scratch.
+// =================================================================================================
+struct Cand {
+    int v[16];
+};
+// The 16 candidate predictions (prediction.hpp:190-207).  section_order selects
+// channelpredict_section's paeth(L, T, TL) argument order (prediction.hpp:126).
+__device__ __forceinline__ void candidates(int L, int T, int TL, int TR, bool section_order, Cand& k) {
+    k.v[0] = L;
+    k.v[1] = T;
+    k.v[2] = TL;
+    k.v[3] = TR;
+    k.v[4] = p_med_grad(T, L, TL);
+    k.v[5] = p_mid(L, T);
+    k.v[6] = p_mid(L, TL);
+    k.v[7] = p_mid(TL, T);
+    k.v[8] = p_mid(T, TR);
+    k.v[9] = section_order ? p_paeth(L, T, TL) : p_paeth(L, TL, T);
+    k.v[10] = p_avg3(L, L, TL);
+    k.v[11] = p_avg3(L, TL, TL);
+    k.v[12] = p_avg3(TL, TL, T);
+    k.v[13] = p_avg3(TL, T, T);
+    k.v[14] = p_avg3(T, T, TR);
+    k.v[15] = p_avg3(T, TR, TR);
+}
+__device__ __forceinline__ int cand_at(const Cand& k, int j) {
+    int r = k.v[0];
+#pragma unroll
+    for (int i = 1; i < 16; i++) r = (j == i) ? k.v[i] : r;
+    return r;
+}
+// prediction.hpp:138-146: lowest index wins ties, stays 0 when nothing beats 2*c
+__device__ __forceinline__ int pick_best(int v, const Cand& k, uint32_t mask, int c) {
+    int best = 0, best_err = c * 2;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int err = abs(v - k.v[j]);
+        const bool take = err < best_err && ((mask >> j) & 1u);
+        best_err = take ? err : best_err;
+        best = take ? j : best;
+    }
+    return best;
+}
+
+// state per plane in global scratch: top[w] u16 followed by bp[w] u8
+template <bool INVERSE>
+__global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__ in, uint64_t n_planes, int w,
+                                                    int h, int depth, int x_tiles, int y_tiles,
+                                                    const uint16_t* __restrict__ tile_maps,
+                                                    const uint16_t* __restrict__ backref,
+                                                    uint16_t* __restrict__ out, uint16_t* __restrict__ top_s,
+                                                    uint8_t* __restrict__ bp_s) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_planes) return;
+    const int c = 1 << depth, half = c >> 1;
+    const int tw = (w + x_tiles - 1) / x_tiles, th = (h + y_tiles - 1) / y_tiles;
+    const uint64_t per = (uint64_t)w * h;
+    const uint16_t* src = in + p * per;
+    const uint16_t* br = (INVERSE && backref) ? backref + p * per : nullptr;
+    uint16_t* dst = out + p * per;
+    const uint16_t* tmap = tile_maps + p * (uint64_t)x_tiles * y_tiles;
+    uint16_t* top = top_s + p * (uint64_t)w;
+    uint8_t* bp = bp_s + p * (uint64_t)w;
+    for (int i = 0; i < w; i++) {
+        top[i] = (uint16_t)half;
+        bp[i] = 4;
+    }
+    uint64_t next_resid = 0;
+    for (int y = 0; y < h; y++) {
+        int left = half, left_top = half;
+        int bp_left = bp[w - 1];  // bp[(x-1) mod w] for x == 0: last column, still the previous row's
+        const bool last_row = y + 1 >= h;
+        const uint16_t* mrow = tmap + (size_t)((y + 1) / th) * x_tiles;
+        int first_of_row = 0;
+        for (int x = 0; x < w; x++) {
+            const uint64_t at = (uint64_t)y * w + x;
+            // TR of the last column = top[0], which already holds this row's first pixel
+            const int tr = (x + 1 < w) ? top[x + 1] : (w > 1 ? first_of_row : top[0]);
+            const int t = top[x];
+            Cand k;
+            candidates(left, t, left_top, tr, false, k);
+            const int bpx = bp[x];
+            const int pred = p_mid(cand_at(k, bpx), cand_at(k, bp_left));
+            int v;
+            if (!INVERSE) {
+                v = src[at];
+                dst[at] = (uint16_t)((v - pred + half + c) % c);  // prediction.hpp:208
+            } else if (br && br[at]) {
+                v = dst[at - br[at]];  // unprediction.hpp:63-65
+                dst[at] = (uint16_t)v;
+            } else {
+                const uint32_t tval = (uint32_t)((int)src[next_resid++] - c - half + pred) & 0xffffu;  // :67
+                v = (int)(tval % (uint32_t)c);
+                dst[at] = (uint16_t)v;
+            }
+            if (x == 0) first_of_row = v;
+            left_top = t;
+            top[x] = (uint16_t)v;
+            left = v;
+            const int nb = last_row ? 0 : pick_best(v, k, mrow[x / tw], c);  // prediction.hpp:213-225
+            bp[x] = (uint8_t)nb;
+            bp_left = nb;
+        }
+    }
+}
+
+// =================================================================================================
+// channelpredict_section — prediction.hpp:46-151.  One thread per (plane, cell, mask).
+// Writes the cell's residuals in cell-raster order.  COST mode instead accumulates
+// sum(cost[resid]) in double precision in raster order (layer_encode.hpp:192-195).
+// =================================================================================================
+constexpr int kMaxCellW = 64;  // the predictor grid is 40 px (layer_encode.hpp:124): cells are <= 40 wide
+
+template <bool COST>
+__global__ void __launch_bounds__(64) k_section(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
+                                                int h, int depth, int x_tiles, int y_tiles,
+                                                const uint16_t* __restrict__ masks, int n_masks,
+                                                uint16_t* __restrict__ resid, uint32_t cell_cap,
+                                                uint32_t* __restrict__ counts, const double* __restrict__ cost,
+                                                double* __restrict__ sums, uint16_t* __restrict__ wide_top,
+                                                uint8_t* __restrict__ wide_bp) {
+    const int cells = x_tiles * y_tiles;
+    const uint64_t job = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t jobs = n_planes * (uint64_t)cells * n_masks;
+    if (job >= jobs) return;
+    const int mi = (int)(job % n_masks);
+    const int cell = (int)((job / n_masks) % cells);
+    const uint64_t p = job / ((uint64_t)n_masks * cells);
+    const uint32_t mask = masks[mi];
+    const int c = 1 << depth, half = c >> 1;
+    const int tw = (w + x_tiles - 1) / x_tiles, th = (h + y_tiles - 1) / y_tiles;
+    const int cx = cell % x_tiles, cy = cell / x_tiles;
+    const int x0 = cx * tw, y0 = cy * th;
+    const uint64_t per = (uint64_t)w * h;
+    const uint16_t* data = planes + p * per;
+    const double* ctab = COST ? cost + p * (uint64_t)c : nullptr;
+    uint16_t* dst = COST ? nullptr : resid + job * cell_cap;
+
+    uint16_t top_local[kMaxCellW];
+    uint8_t bp_local[kMaxCellW];
+    // cells of the 40-px predictor grid fit the local arrays; arbitrary callers (tw > 64) use scratch
+    uint16_t* top = tw <= kMaxCellW ? top_local : wide_top + job * (uint64_t)tw;
+    uint8_t* bp = tw <= kMaxCellW ? bp_local : wide_bp + job * (uint64_t)tw;
+    // prediction.hpp:76-94 — tw entries of the row above are read even when the cell is clipped at
+    // the right edge (the read then runs into the next image row); reads are clamped to the plane.
+    for (int i = 0; i < tw; i++) {
+        bp[i] = 4;
+        if (cy) {
+            const int64_t idx = (int64_t)y0 * w + x0 + i - w;
+            top[i] = (idx >= 0 && (uint64_t)idx < per) ? data[idx] : (uint16_t)0;
+        } else {
+            top[i] = (uint16_t)half;
+        }
+    }
+    uint32_t k = 0;
+    double sum = 0.0;
+    for (int ym = 0; ym < th && y0 + ym < h; ym++) {
+        int left, left_top;
+        if (cx) {  // prediction.hpp:97-105
+            left = data[(uint64_t)(y0 + ym) * w + x0 - 1];
+            left_top = (ym || cy) ? data[(uint64_t)(y0 + ym - 1) * w + x0 - 1] : half;
+        } else {
+            left = left_top = half;
+        }
+        for (int xm = 0; xm < tw && x0 + xm < w; xm++) {
+            const int v = data[(uint64_t)(y0 + ym) * w + x0 + xm];
+            Cand kk;
+            candidates(left, top[xm], left_top, top[(xm + 1) % tw], true, kk);  // :115 TR wraps inside the cell
+            const int pred = p_mid(cand_at(kk, bp[xm]), cand_at(kk, bp[(xm + tw - 1) % tw]));  // :134
+            const int r = (v - pred + half + c) % c;
+            if (COST) sum += ctab[r]; else if (k < cell_cap) dst[k] = (uint16_t)r;
+            k++;
+            left_top = top[xm];
+            top[xm] = (uint16_t)v;
+            left = v;
+            bp[xm] = (uint8_t)pick_best(v, kk, mask, c);
+        }
+    }
+    if (COST) sums[job] = sum; else counts[job] = k;
+}
+
+// layer_encode.hpp:133-144 / :217-225: +1-smoothed histogram of a residual plane.  One CTA per plane.
+__global__ void __launch_bounds__(256) k_plane_histogram(const uint16_t* __restrict__ resid, uint32_t per,
+                                                         int depth, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_h[kFreqRow];
+    const int c = 1 << depth;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) s_h[i] = 1;  // the +1 smoothing
+    __syncthreads();
+    const uint16_t* r = resid + (uint64_t)blockIdx.x * per;
+    for (uint32_t i = threadIdx.x; i < per; i += blockDim.x) atomicAdd(&s_h[r[i] & (c - 1)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) hist[(uint64_t)blockIdx.x * c + i] = s_h[i];
+}
+
+// cost[v] = -log2(f / size) looked up in a host-built table E[f] (glibc log2 is the
+// reference; the table is indexed by the exact integer count so no device log2 is involved).
+__global__ void k_cost_from_hist(const uint32_t* __restrict__ hist, uint64_t entries, const double* __restrict__ e_tab,
+                                 uint32_t e_len, double* __restrict__ cost) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= entries) return;
+    const uint32_t f = hist[i];
+    cost[i] = e_tab[f < e_len ? f : e_len - 1];
+}
+
+// layer_encode.hpp:196-200: strict-< argmin over masks in order; 99999999999 is the starting best.
+__global__ void k_pick_masks(const double* __restrict__ sums, uint64_t n_cells_total, int n_masks,
+                             const uint16_t* __restrict__ masks, uint16_t* __restrict__ tile_maps,
+                             uint8_t* __restrict__ index_lists) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_cells_total) return;
+    double best = 99999999999.0;
+    int arg = 0;
+    uint16_t m = tile_maps[i];
+    bool any = false;
+    for (int k = 0; k < n_masks; k++) {
+        const double s = sums[i * n_masks + k];
+        if (s < best) {
+            best = s;
+            arg = k;
+            m = masks[k];
+            any = true;
+        }
+    }
+    if (any) {
+        tile_maps[i] = m;
+        index_lists[i] = (uint8_t)arg;
+    }
+}
+
+// =================================================================================================
+// Tile front end, cruncher mode 0 — choh.cpp:464-484 (tile gather) + channel.hpp:73 (subtract green)
+// + prediction.hpp:6-44 (fastpath residuals) + entropy_encoding.hpp:32-39 (histograms), fused: one
+// pass over the RGB bytes.  One CTA per tile.
+// =================================================================================================
+struct TileGeom {
+    uint32_t width, height, x_tiles, y_tiles, tile_w, tile_h, tiles_per_image;
+    uint32_t plane_stride;  // u16 elements reserved per channel plane (tile_w*tile_h rounded up to 8)
+};
+
+__device__ __forceinline__ void tile_rect(const TileGeom& g, uint32_t tile, uint32_t& x0, uint32_t& y0,
+                                          uint32_t& tw, uint32_t& th) {
+    x0 = (tile % g.x_tiles) * g.tile_w;
+    y0 = (tile / g.x_tiles) * g.tile_h;
+    tw = min(g.tile_w, g.width - x0);   // choh.cpp:466-474
+    th = min(g.tile_h, g.height - y0);
+}
+
+__global__ void __launch_bounds__(256) k_tile_residuals_s0(const uint8_t* __restrict__ rgb, TileGeom g,
+                                                           uint16_t* __restrict__ resid,
+                                                           uint32_t* __restrict__ freqs) {
+    __shared__ uint32_t s_h[3][kFreqRow];
+    for (int i = threadIdx.x; i < 3 * kFreqRow; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t t = blockIdx.x;  // global tile index = image * tiles_per_image + tile
+    const uint64_t image = t / g.tiles_per_image;
+    const uint32_t tile = (uint32_t)(t % g.tiles_per_image);
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, tile, x0, y0, tw, th);
+    const uint8_t* img = rgb + image * (uint64_t)g.width * g.height * 3u;
+    uint16_t* out_g = resid + (t * 3u + 0u) * g.plane_stride;
+    uint16_t* out_rg = resid + (t * 3u + 1u) * g.plane_stride;
+    uint16_t* out_bg = resid + (t * 3u + 2u) * g.plane_stride;
+    const uint32_t px = tw * th;
+    for (uint32_t i = threadIdx.x; i < px; i += blockDim.x) {
+        const uint32_t x = i % tw, y = i / tw;
+        const uint8_t* p = img + ((uint64_t)(y0 + y) * g.width + x0 + x) * 3u;
+        const int64_t up = -(int64_t)g.width * 3;
+        const int r = p[0], gg = p[1], b = p[2];
+        int Lg = 128, Lr = 256, Lb = 256, Tg = 128, Tr = 256, Tb = 256, TLg = 128, TLr = 256, TLb = 256;
+        if (x) {
+            const int lr = p[-3], lg = p[-2], lb = p[-1];
+            Lg = lg;
+            Lr = lr - lg + 256;
+            Lb = lb - lg + 256;
+        }
+        if (y) {
+            const int tr = p[up], tg = p[up + 1], tb = p[up + 2];
+            Tg = tg;
+            Tr = tr - tg + 256;
+            Tb = tb - tg + 256;
+            if (x) {
+                const int ar = p[up - 3], ag = p[up - 2], ab = p[up - 1];
+                TLg = ag;
+                TLr = ar - ag + 256;
+                TLb = ab - ag + 256;
+            }
+        }
+        const int vg = gg, vr = r - gg + 256, vb = b - gg + 256;
+        const int rg_ = (vg - p_med_grad(Tg, Lg, TLg) + 128 + 256) & 255;   // % 256
+        const int rr_ = (vr - p_med_grad(Tr, Lr, TLr) + 256 + 512) & 511;   // % 512
+        const int rb_ = (vb - p_med_grad(Tb, Lb, TLb) + 256 + 512) & 511;
+        out_g[i] = (uint16_t)rg_;
+        out_rg[i] = (uint16_t)rr_;
+        out_bg[i] = (uint16_t)rb_;
+        atomicAdd(&s_h[0][rg_], 1u);
+        atomicAdd(&s_h[1][rr_], 1u);
+        atomicAdd(&s_h[2][rb_], 1u);
+    }
+    __syncthreads();
+    for (int ch = 0; ch < 3; ch++) {
+        uint32_t* dst = freqs + (t * 3u + ch) * kFreqRow;
+        for (int i = threadIdx.x; i < kFreqRow; i += blockDim.x) dst[i] = s_h[ch][i];
+    }
+}
+
+// Descriptors for the 3 streams of every tile (layer_encode.hpp:57, 59, 321-324: channel header
+// 10 | 00 00 | 00 10, prob_bits 15, range 1 << depth).
+__global__ void k_make_tile_streams(TileGeom g, uint64_t n_tiles, uint32_t slab_bytes,
+                                    hoh_enc_stream* __restrict__ streams) {
+    const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= n_tiles * 3u) return;
+    const uint64_t t = s / 3u;
+    const uint32_t ch = (uint32_t)(s % 3u);
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
+    hoh_enc_stream st;
+    st.sym_off = s * g.plane_stride;
+    st.n = tw * th;
+    st.range = ch == 0 ? 256u : 512u;
+    st.prob_bits = 15;
+    st.prefix_len = 5;
+    st.prefix[0] = 0x10;
+    st.prefix[1] = 0;
+    st.prefix[2] = 0;
+    st.prefix[3] = 0x00;
+    st.prefix[4] = 0x10;
+    st.prefix[5] = st.prefix[6] = st.prefix[7] = 0;
+    st.out_off = s * (uint64_t)slab_bytes;
+    st.out_cap = slab_bytes;
+    st.reserved = 0;
+    streams[s] = st;
+}
+
+// Decode side descriptors: stream s starts at packed_off[s]; checks the 5-byte mode-0 channel header.
+__global__ void k_make_tile_dec_streams(TileGeom g, uint64_t n_tiles, const uint8_t* __restrict__ packed,
+                                        uint64_t packed_bytes, const uint64_t* __restrict__ packed_off,
+                                        hoh_dec_stream* __restrict__ streams, int32_t* __restrict__ status) {
+    const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= n_tiles * 3u) return;
+    const uint64_t off = packed_off[s];
+    const ByteView b{packed, packed_bytes};
+    const bool ok = b[off] == 0x10 && b[off + 1] == 0 && b[off + 2] == 0 && b[off + 3] == 0 && b[off + 4] == 0x10;
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, (uint32_t)((s / 3u) % g.tiles_per_image), x0, y0, tw, th);
+    hoh_dec_stream st;
+    st.in_off = off + 5u;
+    st.sym_off = s * g.plane_stride;
+    st.sym_cap = ok ? tw * th : 0u;
+    st.flags = HOH_FIX_ALL;
+    streams[s] = st;
+    status[s] = ok ? HOH_S_OK : HOH_S_BAD_LAYER;
+}
+
+// Tile back end, mode 0: wavefront inverse of the MED predictor on the three planes of a tile, the
+// inverse colour transform and the scatter into the interleaved image (dhoh.cpp:72-84, 268-276).
+// One warp per tile; lane = row inside a 32-row band.
+__global__ void __launch_bounds__(128) k_tile_unpredict_s0(const uint16_t* __restrict__ resid, TileGeom g,
+                                                           uint64_t n_tiles, uint8_t* __restrict__ rgb) {
+    extern __shared__ uint32_t s_carry[];  // 4 warps * tile_w packed (g | rg << 8 | bg << 17)
+    const uint32_t wid = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t t = (uint64_t)blockIdx.x * 4u + wid;
+    if (t >= n_tiles) return;
+    const uint64_t image = t / g.tiles_per_image;
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
+    uint8_t* img = rgb + image * (uint64_t)g.width * g.height * 3u;
+    const uint16_t* in_g = resid + (t * 3u + 0u) * g.plane_stride;
+    const uint16_t* in_rg = resid + (t * 3u + 1u) * g.plane_stride;
+    const uint16_t* in_bg = resid + (t * 3u + 2u) * g.plane_stride;
+    uint32_t* carry = s_carry + (size_t)wid * g.tile_w;
+    for (uint32_t band = 0; band * 32u < th; band++) {
+        const uint32_t y = band * 32u + lane;
+        const bool row_ok = y < th;
+        int Lg = 128, Lr = 256, Lb = 256, TLg = 128, TLr = 256, TLb = 256;
+        uint32_t mine = 128u | (256u << 8) | (256u << 17);
+        for (uint32_t step = 0; step < tw + 31u; step++) {
+            const int x = (int)step - (int)lane;
+            uint32_t top = __shfl_up_sync(0xffffffffu, mine, 1);
+            if (lane == 0) top = (band && x >= 0 && x < (int)tw) ? carry[x] : (128u | (256u << 8) | (256u << 17));
+            if (y == 0) top = 128u | (256u << 8) | (256u << 17);
+            if (row_ok && x >= 0 && x < (int)tw) {
+                const int Tg = top & 255u, Tr = (top >> 8) & 511u, Tb = (top >> 17) & 511u;
+                if (x == 0) {
+                    Lg = 128; Lr = 256; Lb = 256;
+                    TLg = 128; TLr = 256; TLb = 256;
+                }
+                if (y == 0) {
+                    TLg = 128; TLr = 256; TLb = 256;
+                }
+                const uint32_t i = y * tw + (uint32_t)x;
+                const int vg = ((int)in_g[i] + p_med_grad(Tg, Lg, TLg) - 128) & 255;
+                const int vr = ((int)in_rg[i] + p_med_grad(Tr, Lr, TLr) - 256) & 511;
+                const int vb = ((int)in_bg[i] + p_med_grad(Tb, Lb, TLb) - 256) & 511;
+                uint8_t* p = img + ((uint64_t)(y0 + y) * g.width + x0 + (uint32_t)x) * 3u;
+                p[0] = (uint8_t)((vr + vg - 256) & 255);
+                p[1] = (uint8_t)vg;
+                p[2] = (uint8_t)((vb + vg - 256) & 255);
+                mine = (uint32_t)vg | ((uint32_t)vr << 8) | ((uint32_t)vb << 17);
+                Lg = vg; Lr = vr; Lb = vb;
+                TLg = Tg; TLr = Tr; TLb = Tb;
+                if (lane == 31) carry[x] = mine;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace hohk

@@ -1,0 +1,304 @@
+/* hohgpu.h — C-ABI of libhohgpu.so: the B200 (sm_100a) implementation of the hoh-ANS hot path.
+ *
+ * What this replaces.  hoh-ANS (hohMiyazawa/hoh-ANS) has no plugin / FFI interface: its hot path is a
+ * set of free C++ functions defined in headers which the container code (choh.cpp, dhoh.cpp,
+ * layer_encode.hpp, layer_decode.hpp, lz.hpp, un_lz.hpp) calls directly.  Every entry point below
+ * names the reference function it stands in for (file:line into the reference tree).  Two tiers:
+ *
+ *   (i)  compat shims  — one call = one reference call, HOST pointers in and out, the reference's
+ *        value semantics (same bytes, same symbols, same planes).  They exist so that the
+ *        reference's own host code can be relinked against the GPU and so that
+ *        parity tests read like the reference's tests.  Each call is a batch of one: H2D copy,
+ *        kernels, D2H copy.
+ *   (ii) batched entry points — DEVICE pointers, many independent streams / tiles / images per
+ *        call; this is where the throughput is.  No host work other than launching kernels.
+ *
+ * Conventions: plain C, plain pointers and sizes, no exceptions, no stdout, every function returns
+ * an int status (HOH_OK == 0) unless stated otherwise; the library owns its scratch device memory
+ * (grown on demand, cached in the context), the caller owns every buffer it passes in and states
+ * its capacity.  A context is bound to one CUDA device and one stream; calls on one context must
+ * not overlap in time, different contexts are independent (one per GPU / per host thread).
+ * There is NO CPU fallback: without a CUDA device hoh_ctx_create fails with HOH_E_CUDA.
+ */
+#ifndef HOHGPU_H
+#define HOHGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* status codes                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+#define HOH_OK 0
+#define HOH_E_CUDA 1          /* a CUDA runtime call failed (hoh_last_cuda_error has the text)   */
+#define HOH_E_ARG 2           /* bad argument (null pointer, zero size, misaligned offset)       */
+#define HOH_E_UNSUPPORTED 3   /* outside the hot path's domain (range > 512, prob_bits > 19 ...) */
+#define HOH_E_CAPACITY 4      /* caller's output buffer too small                                */
+#define HOH_E_STREAM 5        /* at least one stream failed; see the per-stream status array      */
+
+/* per-stream status (hoh_stream_result.status) */
+#define HOH_S_OK 0
+#define HOH_S_RANGE_GT_TOTAL 1 /* stattools.hpp:14  assert(target_total >= size) would fire        */
+#define HOH_S_NO_DONOR 2       /* stattools.hpp:42  assert(best_steal != -1) would fire            */
+#define HOH_S_BAD_TABLE 3      /* decode: table storage mode 3                                     */
+#define HOH_S_OVERFLOW 4       /* output slab / symbol capacity too small                          */
+#define HOH_S_BAD_LAYER 5      /* tile decode: channel header is not the mode-0 form 10 00 00 00 10 */
+
+/* decode flags: 0 reproduces entropy_decoding.hpp byte for byte including its defects; the FIX
+ * bits turn individual defects off. */
+#define HOH_FIX_PROB_BITS5 1u /* D9: prob_bits is a 5-bit field (mask 0x7C), reference masks 4 bits */
+#define HOH_FIX_ADVANCE 2u    /* D8: leave *byte_pointer after the rANS payload, not at its start   */
+#define HOH_FIX_EMPTY 4u      /* D2: a zero-symbol stream has no metadata byte                      */
+#define HOH_FIX_ALL 7u
+
+#define HOH_MAX_RANGE 512     /* largest alphabet on the hot path (depth-9 sub-green planes)        */
+#define HOH_MAX_PROB_BITS 19  /* layer_encode.hpp:359-392 tries up to 19                            */
+#define HOH_HEAD_CAP 1536     /* bytes reserved in front of a payload for varints + metadata + table */
+
+typedef struct hoh_ctx hoh_ctx;
+
+/* ------------------------------------------------------------------------------------------ */
+/* context, memory and timing helpers                                                         */
+/* ------------------------------------------------------------------------------------------ */
+/* cuda_stream: a cudaStream_t to launch on (e.g. torch.cuda.current_stream().cuda_stream), or NULL
+ * to let the context create its own non-blocking stream. */
+int hoh_ctx_create(int device, void* cuda_stream, hoh_ctx** out);
+void hoh_ctx_destroy(hoh_ctx* ctx);
+int hoh_sync(hoh_ctx* ctx);
+const char* hoh_strerror(int status);
+const char* hoh_last_cuda_error(hoh_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches claim). */
+uint64_t hoh_launch_count(hoh_ctx* ctx);
+
+int hoh_dev_alloc(hoh_ctx* ctx, size_t bytes, void** dptr);
+int hoh_dev_free(hoh_ctx* ctx, void* dptr);
+int hoh_dev_memset(hoh_ctx* ctx, void* dptr, int value, size_t bytes);
+int hoh_host_alloc(hoh_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int hoh_host_free(hoh_ctx* ctx, void* hptr);
+int hoh_h2d(hoh_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on the ctx stream */
+int hoh_d2h(hoh_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on the ctx stream */
+/* CUDA-event timer on the context's stream: start/stop record events, elapsed synchronises. */
+int hoh_timer_start(hoh_ctx* ctx, int slot); /* slot 0..15 */
+int hoh_timer_stop(hoh_ctx* ctx, int slot);
+int hoh_timer_elapsed_ms(hoh_ctx* ctx, int slot, float* ms);
+/* Writes a scratch buffer larger than L2 so that the next timed launch starts cold. */
+int hoh_flush_l2(hoh_ctx* ctx);
+/* Per-kernel device timing: between begin and end every kernel launch is followed by a CUDA event on
+ * the context's stream; end synchronises and sums the intervals per kernel name.  For profiling
+ * passes only (the events add a little launch overhead). */
+int hoh_profile_begin(hoh_ctx* ctx);
+int hoh_profile_end(hoh_ctx* ctx);
+int hoh_profile_count(hoh_ctx* ctx);
+int hoh_profile_entry(hoh_ctx* ctx, int index, const char** name, double* total_ms, uint64_t* launches);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (ii) batched entropy coding — entropy_encoding.hpp:8 / entropy_decoding.hpp:134 over N streams */
+/* ------------------------------------------------------------------------------------------ */
+/* One stream to encode.  Arrays of these live in DEVICE memory. */
+typedef struct hoh_enc_stream {
+    uint64_t sym_off;    /* element offset of the first symbol in the u16 symbol buffer; multiple of 8 */
+    uint32_t n;          /* symbols in this stream (< 2^21: varint.hpp:39-45)                           */
+    uint32_t range;      /* alphabet size, 1..HOH_MAX_RANGE                                             */
+    uint32_t prob_bits;  /* 1..HOH_MAX_PROB_BITS, 2^prob_bits >= range                                  */
+    uint32_t prefix_len; /* literal bytes emitted in front of the stream (channel header), 0..8         */
+    uint8_t prefix[8];
+    uint64_t out_off;    /* byte offset of this stream's slab in the output buffer; multiple of 16      */
+    uint32_t out_cap;    /* slab bytes, multiple of 16; see hoh_enc_slab_bytes                          */
+    uint32_t reserved;
+} hoh_enc_stream;
+
+typedef struct hoh_stream_result {
+    uint64_t start;  /* byte offset in the output buffer where prefix+stream begin           */
+    uint32_t size;   /* prefix_len + bytes encode_entropy would have returned                */
+    int32_t status;  /* HOH_S_*                                                              */
+    uint32_t payload_bytes; /* rANS payload length (0 in stored mode / empty stream)         */
+    uint32_t stored;        /* 1 if the stored-mode fallback won (entropy_encoding.hpp:244)  */
+} hoh_stream_result;
+
+/* Slab size that can never overflow for a stream of n symbols at prob_bits. */
+size_t hoh_enc_slab_bytes(size_t n, uint32_t prob_bits);
+
+/* encode_entropy for every stream: histogram -> normalize_freqs -> header + table -> rANS -> length
+ * varint -> stored-mode fallback.  d_streams, d_symbols, d_out, d_results are device pointers.
+ * max_range / max_prob_bits / max_n are upper bounds over the batch (they size shared memory and
+ * loop trip counts; the host does not read the descriptors). */
+int hoh_encode_entropy_batch(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n_streams,
+                             const uint16_t* d_symbols, uint8_t* d_out, hoh_stream_result* d_results,
+                             uint32_t max_range, uint32_t max_prob_bits, uint32_t max_n);
+
+/* One stream to decode. */
+typedef struct hoh_dec_stream {
+    uint64_t in_off;   /* byte offset of the stream header (varint(range-1)) in the input buffer */
+    uint64_t sym_off;  /* element offset for the decoded u16 symbols; multiple of 8              */
+    uint32_t sym_cap;  /* symbols that may be written                                            */
+    uint32_t flags;    /* HOH_FIX_*                                                              */
+} hoh_dec_stream;
+
+typedef struct hoh_dec_result {
+    uint64_t end_off;  /* *byte_pointer after the call (reference semantics, see HOH_FIX_ADVANCE) */
+    uint32_t n;        /* symbols decoded                                                         */
+    int32_t status;
+    uint32_t range;
+    uint32_t prob_bits;
+    uint32_t stored;
+    uint32_t table_mode;
+} hoh_dec_result;
+
+/* decode_entropy for every stream.  in_bytes = size of d_in (reads are clamped to it). */
+int hoh_decode_entropy_batch(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n_streams,
+                             const uint8_t* d_in, size_t in_bytes, uint16_t* d_symbols,
+                             hoh_dec_result* d_results, uint32_t max_n);
+
+/* rans64.hpp:262 / :107-142 loops with ONE caller-supplied table shared by all streams (config 4:
+ * static-table symbol-stream sweep).  Stream i covers symbols [i*stream_len, min(n, (i+1)*stream_len));
+ * its payload is written at d_out + i*slab_bytes, END-aligned inside the slab; d_payload_bytes[i]
+ * receives its length.  stream_len multiple of 8, slab_bytes multiple of 16. */
+int hoh_rans_encode_static(hoh_ctx* ctx, const uint16_t* d_symbols, size_t n, uint32_t stream_len,
+                           const uint32_t* d_cum /* range+1 */, uint32_t range, uint32_t prob_bits,
+                           uint8_t* d_out, uint32_t slab_bytes, uint32_t* d_payload_bytes);
+int hoh_rans_decode_static(hoh_ctx* ctx, const uint8_t* d_in, uint32_t slab_bytes,
+                           const uint32_t* d_payload_bytes, size_t n, uint32_t stream_len,
+                           const uint32_t* d_cum, uint32_t range, uint32_t prob_bits,
+                           uint16_t* d_symbols);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (ii) batched tile codec, cruncher mode 0 — choh.cpp:454-506 tiling, channel.hpp:73,            */
+/*      layer_encode.hpp:11 (mode 0 branch), and their inverses                                   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct hoh_tile_geometry {
+    uint32_t width, height;     /* image                                             */
+    uint32_t x_tiles, y_tiles;  /* choh.cpp:455-456 (1,1 when the image is not tiled) */
+    uint32_t tile_w, tile_h;    /* choh.cpp:459-460 nominal tile size                */
+    uint32_t tiles_per_image;
+    uint32_t streams_per_image; /* 3 * tiles_per_image (G, R-G, B-G)                 */
+} hoh_tile_geometry;
+
+/* choh.cpp:454-460: the 256-pixel image tiling rule. */
+int hoh_tile_geometry_for(uint32_t width, uint32_t height, hoh_tile_geometry* out);
+
+/* Bytes of device output needed by hoh_encode_images_s0 for n_images (slabs, worst case). */
+size_t hoh_encode_images_out_bytes(const hoh_tile_geometry* g, size_t n_images);
+
+/* Encode n_images interleaved RGB8 images (d_rgb: n_images * height * width * 3 bytes) at cruncher
+ * mode 0 with the subtract-green colour mode (choh.cpp:219-255) and no LZ matches (NUKE == 0; pass
+ * d_nuke = NULL) or a caller-computed LEMPEL_NUKE map (d_nuke: one byte per pixel in TILE-major
+ * order, i.e. for each image, for each tile, tile_w*tile_h bytes in raster order).
+ * For stream s = (image * tiles_per_image + tile) * 3 + channel, d_results[s] gives the byte range in
+ * d_out holding exactly what layer_encode() writes for that channel ("10 00 00 00 10" + stream).
+ * If d_packed != NULL the channel payloads are also gathered back to back in stream order into
+ * d_packed (capacity packed_cap bytes) and d_packed_off[s] (n_streams+1 entries, u64) receives their
+ * offsets — the "final gather" the host container writer consumes. */
+int hoh_encode_images_s0(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width,
+                         uint32_t height, const uint8_t* d_nuke, uint8_t* d_out, size_t out_bytes,
+                         hoh_stream_result* d_results, uint8_t* d_packed, size_t packed_cap,
+                         uint64_t* d_packed_off);
+
+/* Inverse: channel payloads (as produced above: d_packed + d_packed_off, n_images*streams_per_image
+ * of them, each starting with the 5-byte mode-0 channel header) -> interleaved RGB8 images.
+ * The un-prediction is the exact inverse of channelpredict_fastpath (pure MED) and the
+ * colour inverse is the algebraic inverse of channel.hpp:73-79; d_backref = NULL or the
+ * LEMPEL_BACKREF map (u16 per pixel, tile-major) for unprediction.hpp:63-65 copies. */
+int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes,
+                         const uint64_t* d_packed_off, size_t n_images, uint32_t width,
+                         uint32_t height, const uint16_t* d_backref, uint8_t* d_rgb,
+                         int32_t* d_status /* n_images*streams_per_image */);
+
+/* Host-buffer forms of the two calls above — what a host container writer / reader calls: the RGB
+ * (or packed) bytes are copied to the device, coded, and the result copied back, all on the context's
+ * stream; device staging lives in the context and is reused across calls.  Pass pinned buffers
+ * (hoh_host_alloc) for full copy bandwidth.  encode: packed_host/packed_cap receive the channel
+ * payloads back to back, off_host (n_streams+1 u64) their offsets, results_host (n_streams, may be
+ * NULL) the per-stream results.  decode: status_host (n_streams, may be NULL). */
+int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_images, uint32_t width,
+                              uint32_t height, uint8_t* packed_host, size_t packed_cap, uint64_t* off_host,
+                              hoh_stream_result* results_host);
+int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t packed_bytes,
+                              const uint64_t* off_host, size_t n_images, uint32_t width, uint32_t height,
+                              uint8_t* rgb_host, int32_t* status_host);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (ii) batched plane kernels (device pointers; planes are u16, raster order, back to back)     */
+/* ------------------------------------------------------------------------------------------ */
+/* channel.hpp:73 subtract_green over `pixels` interleaved RGB8 pixels. */
+int hoh_subtract_green_dev(hoh_ctx* ctx, const uint8_t* d_rgb, size_t pixels, uint16_t* d_g,
+                           uint16_t* d_rg, uint16_t* d_bg);
+/* algebraic inverse */
+int hoh_add_green_dev(hoh_ctx* ctx, const uint16_t* d_g, const uint16_t* d_rg, const uint16_t* d_bg,
+                      size_t pixels, uint8_t* d_rgb);
+/* prediction.hpp:6 channelpredict_fastpath on n_planes planes of w*h. */
+int hoh_predict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h,
+                             int depth, uint16_t* d_resid);
+/* exact inverse of the above (with optional back-reference copies, n_planes*w*h u16 or NULL);
+ * residuals are dense per plane (w*h of them when d_backref == NULL). */
+int hoh_unpredict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_planes, int w, int h,
+                               int depth, const uint16_t* d_backref, uint16_t* d_planes);
+/* prediction.hpp:153 channelpredict_all: per plane its own tile_map (x_tiles*y_tiles u16 masks). */
+int hoh_predict_all_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h,
+                        int depth, int x_tiles, int y_tiles, const uint16_t* d_tile_maps,
+                        uint16_t* d_resid);
+/* unprediction.hpp:6 unpredict_all.  Residuals of plane p start at d_resid + p*w*h. */
+int hoh_unpredict_all_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_planes, int w, int h,
+                          int depth, int x_tiles, int y_tiles, const uint16_t* d_tile_maps,
+                          const uint16_t* d_backref, uint16_t* d_planes);
+/* prediction.hpp:46 channelpredict_section for every (plane, grid cell, mask): writes the cell's
+ * residuals (cell-raster order) to d_resid + ((p*cells + cell)*n_masks + m)*cell_cap and the count to
+ * d_counts (same index without cell_cap); cell_cap >= tile_w*tile_h of the predictor grid. */
+int hoh_predict_section_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h,
+                            int depth, int x_tiles, int y_tiles, const uint16_t* d_masks, int n_masks,
+                            uint16_t* d_resid, uint32_t cell_cap, uint32_t* d_counts);
+/* layer_encode.hpp:126-272: the predictor search (histogram -> -log2 cost table -> per cell argmin
+ * over the first min(14, 5*mode) stock masks, costs summed in raster order in double precision,
+ * strict <; refinement pass when mode > 2) followed by channelpredict_all.  Outputs per plane:
+ * tile_map (cells u16), index_list (cells u8, index into the 14 stock masks) and the final residual
+ * plane.  The grid is ceil(w/40) x ceil(h/40) (layer_encode.hpp:124,150-151). */
+int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h,
+                             int depth, int mode, uint16_t* d_tile_maps, uint8_t* d_index_lists,
+                             uint16_t* d_resid);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (i) compat shims — host pointers, one reference call each                                    */
+/* ------------------------------------------------------------------------------------------ */
+/* entropy_encoding.hpp:8  size_t encode_entropy(symbols, n, range, out, prob_bits, diagnostics).
+ * Returns the byte count through *out_size; out_cap is the capacity the reference never checked. */
+int hoh_encode_entropy(hoh_ctx* ctx, const uint16_t* symbols, size_t n, size_t range, uint8_t* out,
+                       size_t out_cap, uint32_t prob_bits, size_t* out_size, int* stream_status);
+/* entropy_encoding.hpp:283 (8-bit symbols overload) */
+int hoh_encode_entropy_8bit(hoh_ctx* ctx, const uint8_t* symbols, size_t n, size_t range, uint8_t* out,
+                            size_t out_cap, uint32_t prob_bits, size_t* out_size, int* stream_status);
+/* entropy_decoding.hpp:134  uint16_t* decode_entropy(in, in_size, &byte_pointer, &symbol_size, diag).
+ * The caller supplies the symbol buffer instead of receiving a new[] array. */
+int hoh_decode_entropy(hoh_ctx* ctx, const uint8_t* in, size_t in_size, size_t* byte_pointer,
+                       uint16_t* symbols, size_t symbols_cap, size_t* symbol_size, unsigned flags,
+                       int* stream_status);
+/* stattools.hpp:13 normalize_freqs (in place; cum_freqs has size+1 entries). */
+int hoh_normalize_freqs(hoh_ctx* ctx, uint32_t* freqs, uint32_t* cum_freqs, size_t size,
+                        uint32_t target_total, int* stream_status);
+/* channel.hpp:73 / :63 */
+int hoh_subtract_green(hoh_ctx* ctx, const uint8_t* rgb, size_t size, uint16_t* green, uint16_t* red_g,
+                       uint16_t* blue_g);
+int hoh_add_green(hoh_ctx* ctx, const uint16_t* green, const uint16_t* red_g, const uint16_t* blue_g,
+                  size_t pixels, uint8_t* rgb);
+/* prediction.hpp:6, :46, :153; unprediction.hpp:6 (+ the pure-MED inverse) */
+int hoh_channelpredict_fastpath(hoh_ctx* ctx, const uint16_t* data, int w, int h, int depth, uint16_t* out);
+int hoh_channelpredict_section(hoh_ctx* ctx, const uint16_t* data, int w, int h, int depth, int x_tiles,
+                               int y_tiles, int x, int y, uint16_t predictor, uint16_t* out,
+                               size_t out_cap, size_t* out_count);
+int hoh_channelpredict_all(hoh_ctx* ctx, const uint16_t* data, int w, int h, int depth, int x_tiles,
+                           int y_tiles, const uint16_t* tile_map, uint16_t* out);
+int hoh_unpredict_all(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, int w, int h, int depth,
+                      int x_tiles, int y_tiles, const uint16_t* tile_map, const uint16_t* backref,
+                      uint16_t* out);
+int hoh_unpredict_fastpath(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, int w, int h, int depth,
+                           const uint16_t* backref, uint16_t* out);
+/* layer_encode.hpp:126-272 for one plane */
+int hoh_predictor_search(hoh_ctx* ctx, const uint16_t* plane, int w, int h, int depth, int mode,
+                         uint16_t* tile_map, uint8_t* index_list, uint16_t* final_resid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOHGPU_H */
