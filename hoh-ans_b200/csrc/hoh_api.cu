@@ -169,7 +169,7 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
                                                                              d_out, meta, rows, 1u);
         LAUNCHED("k_rans_encode<u16>");
     }
-    if (max_prob_bits > 16) {
+    if (max_prob_bits > 15) {
         const size_t smem = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kSymStride * sizeof(uint16_t);
         k_rans_encode<uint32_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, cum,
                                                                              d_out, meta, rows, 0u);
@@ -195,13 +195,13 @@ int decode_common(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n, const
     LAUNCHED("k_unpack_stored");
     const uint32_t rows = HOH_MAX_RANGE + 1;
     {
-        const size_t smem = (size_t)rows * 32 * sizeof(uint16_t) + 32 * kSymStride * sizeof(uint16_t);
+        const size_t smem = (size_t)rows * 32 * sizeof(uint16_t) + kLutSize * 32 * 2 + 32 * kSymStride * sizeof(uint16_t);
         k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_in, in_bytes,
                                                                              cum, meta, d_symbols, rows, 1u);
         LAUNCHED("k_rans_decode<u16>");
     }
     {
-        const size_t smem = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kSymStride * sizeof(uint16_t);
+        const size_t smem = (size_t)rows * 32 * sizeof(uint32_t) + kLutSize * 32 * 2 + 32 * kSymStride * sizeof(uint16_t);
         k_rans_decode<uint32_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_in, in_bytes,
                                                                              cum, meta, d_symbols, rows, 0u);
         LAUNCHED("k_rans_decode<u32>");
@@ -491,7 +491,7 @@ int hoh_rans_encode_static(hoh_ctx* ctx, const uint16_t* d_symbols, size_t n, ui
                            const uint32_t* d_cum, uint32_t range, uint32_t prob_bits, uint8_t* d_out,
                            uint32_t slab_bytes, uint32_t* d_payload_bytes) {
     if (!ctx || !d_symbols || !d_cum || !d_out || !d_payload_bytes) return HOH_E_ARG;
-    if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > 31) return HOH_E_UNSUPPORTED;
+    if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > HOH_MAX_PROB_BITS) return HOH_E_UNSUPPORTED;
     if (stream_len == 0 || stream_len % 8 || slab_bytes % 16) return HOH_E_ARG;
     if (n == 0) return HOH_OK;
     const uint64_t streams = (n + stream_len - 1) / stream_len;
@@ -505,7 +505,7 @@ int hoh_rans_decode_static(hoh_ctx* ctx, const uint8_t* d_in, uint32_t slab_byte
                            const uint32_t* d_payload_bytes, size_t n, uint32_t stream_len,
                            const uint32_t* d_cum, uint32_t range, uint32_t prob_bits, uint16_t* d_symbols) {
     if (!ctx || !d_symbols || !d_cum || !d_in || !d_payload_bytes) return HOH_E_ARG;
-    if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > 31) return HOH_E_UNSUPPORTED;
+    if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > HOH_MAX_PROB_BITS) return HOH_E_UNSUPPORTED;
     if (stream_len == 0 || stream_len % 8 || slab_bytes % 16) return HOH_E_ARG;
     if (n == 0) return HOH_OK;
     const uint64_t streams = (n + stream_len - 1) / stream_len;

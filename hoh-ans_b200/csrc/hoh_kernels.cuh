@@ -32,7 +32,7 @@ struct EncMeta {
     uint32_t head_len;     // varints + metadata + table
     uint32_t stored_size;  // entropy_encoding.hpp:45
     int32_t status;
-    uint32_t table_u16;  // 1 if prob_bits <= 16 (cum table fits 16-bit lanes)
+    uint32_t table_u16;  // 1 if prob_bits <= 15 (every cumulative count fits a 16-bit lane)
     uint32_t pad;
 };
 
@@ -45,6 +45,8 @@ struct DecMeta {
     uint32_t kind;  // 0 nothing to do, 1 stored, 2 rANS
     uint32_t maxbits;
     int32_t status;
+    uint32_t wide;  // 1 if some cumulative count needs more than 16 bits (32-bit table lanes)
+    uint32_t pad;
 };
 
 // Bounds-clamped byte view of the input buffer: malformed streams read zeros, never fault.
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
     m.head_len = 0;
     m.stored_size = 0;
     m.status = HOH_S_OK;
-    m.table_u16 = st.prob_bits <= 16 ? 1u : 0u;
+    m.table_u16 = st.prob_bits <= 15 ? 1u : 0u;
     m.pad = 0;
     uint8_t* head = heads + (size_t)s * HOH_HEAD_CAP;
     if (st.n == 0) {  // entropy_encoding.hpp:19-23: two varints and nothing else (D2)
@@ -227,29 +229,72 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
 // =================================================================================================
 // rans64.hpp:262-278 (Rans64EncPutSymbol) == rans64.hpp:77-94 (Rans64EncPut) for every reachable
 // state: x' = ((x / f) << bits) + x % f + start after the optional 32-bit renormalisation.
-// The reference multiplies by a precomputed 64-bit reciprocal per symbol (24 B/symbol: 12 KB per
-// stream, far beyond 32 per-lane tables in shared memory); here the quotient is estimated with one
-// FP64 multiply by 1/f and corrected with exact integer arithmetic, so the result is exact whatever
-// the estimate's rounding was.
+// The reference multiplies by a precomputed 64-bit reciprocal per symbol (24 B/symbol = 12 KB per
+// stream — 32 per-lane tables of that size do not fit in shared memory).  Here the only per-symbol
+// state in shared memory is the 16-bit cumulative count; the quotient comes from a 32-bit reciprocal
+// built on the fly (one MUFU.RCP, biased low) refined in three exact integer rounds, so the result is
+// the true floor(x / f) for every f <= 2^19 and x < f * 2^(63-bits).
+
+// Normalised reciprocal: with L = bit length of f, returns m <= 2^(31+L) / f (biased low by at most
+// 2^-20 relative, saturating at 2^32 - 1 when f is a power of two) and sh = L - 1, so that
+// floor(x / f) ~ ((x * m) >> 32) >> sh.
+__device__ __forceinline__ uint32_t recip_under(uint32_t f, uint32_t& sh) {
+    const uint32_t L = 32u - (uint32_t)__clz((int)f);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_rn(f)));        // f <= 2^19: exact in fp32
+    r = __int_as_float(__float_as_int(r) + (int)((31u + L) << 23)) * 0.99999952316284f;  // * 2^(31+L) * (1 - 2^-21)
+    sh = L - 1u;
+    return __float2uint_rz(r);  // saturates
+}
+
+// q = floor(x / f), r = x mod f for f <= 2^19, x < f * 2^(63 - bits).  Every partial quotient
+// under-estimates (m is biased low) so the remainders stay non-negative; brute-forced on the CPU over
+// 10^8 (x, f, bits in 1..19) cases with the reciprocal perturbed by +-1 ulp: R1 < 2^43, R2 < 2^23 and at
+// most one final correction.
+__device__ __forceinline__ void divmod_u64(uint64_t x, uint32_t f, uint32_t m, uint32_t sh, uint64_t& q,
+                                           uint32_t& r) {
+    const uint32_t a = (uint32_t)(x >> 32), b = (uint32_t)x;
+    const uint64_t q0 = ((uint64_t)a * m + __umulhi(b, m)) >> sh;  // floor(x * m / 2^(32+sh))
+    const uint64_t r1 = x - q0 * f;
+    const uint64_t q1 = ((uint64_t)(uint32_t)(r1 >> 32) * m + __umulhi((uint32_t)r1, m)) >> sh;
+    const uint32_t r2 = (uint32_t)r1 - (uint32_t)q1 * f;  // true value < 2^23: exact mod 2^32
+    const uint32_t q2 = __umulhi(r2, m) >> sh;
+    uint32_t rr = r2 - q2 * f;
+    uint32_t fix = q2;
+    if (rr >= f) {
+        rr -= f;
+        fix++;
+    }
+    if (rr >= f) {  // bound: r < 3f; never observed to need the second correction
+        rr -= f;
+        fix++;
+    }
+    q = q0 + q1 + fix;
+    r = rr;
+}
+
+// One encoder step.  `words` is the stream's slab viewed as u32, `widx` the index of the lowest word
+// written so far (words are emitted downwards).  The caller has checked the slab capacity up front
+// (at most (n * bits + 32) / 32 + 3 words are ever written), so there is no per-symbol bounds test.
+// A step with freq == 2^bits, start == 0 is an exact no-op (x / 2^bits, x mod 2^bits recombine to x and
+// the renormalisation test x >= 2^63 never fires): lanes whose stream is shorter use it as padding.
 __device__ __forceinline__ uint64_t rans_put(uint64_t x, uint32_t start, uint32_t freq, uint32_t bits,
-                                             uint32_t*& wp, const uint32_t* wp_floor, bool& overflow) {
-    const uint64_t x_max = (uint64_t)freq << (63u - bits);  // ((L >> bits) << 32) * freq
-    if (x >= x_max) {
-        if (wp > wp_floor) *--wp = (uint32_t)x; else overflow = true;
-        x >>= 32;
-    }
-    const double inv = __drcp_rn((double)freq);
-    uint64_t q = __double2ull_rz(__ull2double_rz(x) * inv);
-    int64_t r = (int64_t)(x - q * (uint64_t)freq);
-    while (r < 0) {
-        q--;
-        r += freq;
-    }
-    while (r >= (int64_t)freq) {
-        q++;
-        r -= freq;
-    }
-    return (q << bits) + (uint64_t)r + start;
+                                             uint32_t* __restrict__ words, uint32_t& widx) {
+    uint32_t sh;
+    const uint32_t m = recip_under(freq, sh);
+    // x >= ((L >> bits) << 32) * freq  <=>  (x >> (63 - bits)) >= freq, and 63 - bits >= 32
+    const bool emit = ((uint32_t)(x >> 32) >> (31u - bits)) >= freq;
+    if (emit) words[--widx] = (uint32_t)x;
+    x = emit ? (x >> 32) : x;
+    uint64_t q;
+    uint32_t r;
+    divmod_u64(x, freq, m, sh, q, r);
+    return (q << bits) + (uint64_t)(r + start);
+}
+
+// Words a stream of n symbols can emit at most, flush included, plus slack.
+__device__ __host__ __forceinline__ uint64_t rans_words_bound(uint64_t n, uint32_t bits) {
+    return (n * bits + 32u) / 32u + 4u;
 }
 
 // Table accessors.  PerLane: tab[(symbol * 32 + lane)] — 32 independent tables, bank == lane.
@@ -265,20 +310,6 @@ struct SharedTable {
     const CumT* tab;
     __device__ __forceinline__ uint32_t cum(uint32_t s) const { return tab[s]; }
 };
-
-template <typename CumT>
-__device__ __forceinline__ uint32_t freq_from(uint32_t c0, uint32_t c1, uint32_t bits);
-template <>
-__device__ __forceinline__ uint32_t freq_from<uint32_t>(uint32_t c0, uint32_t c1, uint32_t) {
-    return c1 - c0;
-}
-template <>
-__device__ __forceinline__ uint32_t freq_from<uint16_t>(uint32_t c0, uint32_t c1, uint32_t bits) {
-    // 16-bit lanes hold cum mod 65536: only cum[range] == 65536 (prob_bits 16) wraps, and then a
-    // zero difference can only mean the one symbol that owns everything.
-    uint32_t f = (c1 - c0) & 0xffffu;
-    return (f == 0u && bits == 16u) ? 65536u : f;
-}
 
 // Cooperative load of one 64-symbol chunk for the 32 streams of a warp into the padded transpose.
 // Row r of `stage` receives symbols [64*chunk, 64*chunk+64) of stream r (zero beyond its n).
@@ -364,7 +395,12 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
     }
     // a stream takes part if it has symbols, its table was built, and it belongs to this launch's
     // table width (16-bit lanes for prob_bits <= 16, 32-bit otherwise)
-    const bool live = exists && st.n > 0 && m.status == HOH_S_OK && m.table_u16 == want_u16;
+    bool live = exists && st.n > 0 && m.status == HOH_S_OK && m.table_u16 == want_u16;
+    if (live && (uint64_t)st.out_cap < rans_words_bound(st.n, st.prob_bits) * 4u + HOH_HEAD_CAP + 32u) {
+        m.status = HOH_S_OVERFLOW;  // slab too small for the worst case: refuse rather than test per symbol
+        meta[s] = m;
+        live = false;
+    }
     s_off[lane] = st.sym_off;
     s_n[lane] = live ? st.n : 0u;
     if (__ballot_sync(0xffffffffu, live) == 0u) return;
@@ -382,9 +418,9 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
 
     const PerLaneTable<CumT> T{tab, lane};
     const uint32_t bits = st.prob_bits;
-    uint32_t* wp = reinterpret_cast<uint32_t*>(out + st.out_off + st.out_cap);
-    const uint32_t* wp_floor = reinterpret_cast<const uint32_t*>(out + st.out_off) + (HOH_HEAD_CAP + 32) / 4;
-    bool overflow = false;
+    uint32_t* words = reinterpret_cast<uint32_t*>(out + st.out_off);
+    const uint32_t cap_words = st.out_cap / 4u;
+    uint32_t widx = cap_words;
     uint64_t x = kRansL;  // rans64.hpp:65
 
     uint32_t n_max = s_n[lane];
@@ -392,33 +428,31 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
     for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
     const uint32_t my_n = live ? st.n : 0u;
     const uint16_t* my_row = stage + lane * kSymStride;
+    const uint32_t full = 1u << bits;
+    const uint32_t sym_max = st.range - 1u;  // out-of-alphabet input must not index past the lane's table
 
     for (int chunk = (int)((n_max + kChunk - 1) / kChunk) - 1; chunk >= 0; chunk--) {
         __syncwarp();
         stage_load_chunk(stage, symbols, s_off, s_n, (uint32_t)chunk);
         __syncwarp();
         const uint32_t base = (uint32_t)chunk * kChunk;
-#pragma unroll 4
+#pragma unroll 8
         for (int k = kChunk - 1; k >= 0; k--) {  // entropy_encoding.hpp:222-225, last symbol first
-            if (base + (uint32_t)k < my_n) {
-                const uint32_t sym = my_row[k];
-                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
-                x = rans_put(x, c0, freq_from<CumT>(c0, c1, bits), bits, wp, wp_floor, overflow);
-            }
+            const bool on = base + (uint32_t)k < my_n;
+            const uint32_t sym = on ? min((uint32_t)my_row[k], sym_max) : 0u;
+            uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+            c0 = on ? c0 : 0u;      // padding step: freq = 2^bits, start = 0 leaves x untouched
+            c1 = on ? c1 : full;
+            x = rans_put(x, c0, c1 - c0, bits, words, widx);
         }
     }
     if (live) {
         // rans64.hpp:96-103 flush: low word at the lower address
-        if (wp - 2 >= wp_floor) {
-            wp -= 2;
-            wp[0] = (uint32_t)x;
-            wp[1] = (uint32_t)(x >> 32);
-        } else {
-            overflow = true;
-        }
-        m.payload_start = (uint64_t)(reinterpret_cast<uint8_t*>(wp) - out);
-        m.payload_bytes = (uint32_t)(st.out_off + st.out_cap - m.payload_start);
-        if (overflow) m.status = HOH_S_OVERFLOW;
+        widx -= 2;
+        words[widx] = (uint32_t)x;
+        words[widx + 1] = (uint32_t)(x >> 32);
+        m.payload_start = st.out_off + (uint64_t)widx * 4u;
+        m.payload_bytes = (cap_words - widx) * 4u;
         meta[s] = m;
     }
 }
@@ -556,6 +590,8 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
     m.kind = 0;
     m.maxbits = h.maxbits;
     m.status = status;
+    m.wide = 0;
+    m.pad = 0;
     hoh_dec_result res;
     res.end_off = h.body;
     res.n = h.n;
@@ -589,6 +625,7 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
             warp_cumsum(f, cum, h.range);  // stattools.hpp:6-11
             uint32_t* ct = cumtab + (size_t)s * kCumRow;
             for (uint32_t i = lane; i <= h.range; i += 32) ct[i] = cum[i];
+            m.wide = (h.prob_bits > 15u || cum[h.range] > 65535u) ? 1u : 0u;
             uint64_t at = after_table;
             const uint32_t payload = hohfmt::get_varint(bytes, &at);  // entropy_decoding.hpp:256
             m.payload_off = at;
@@ -634,8 +671,9 @@ __global__ void __launch_bounds__(256) k_unpack_stored(const hoh_dec_stream* __r
 // returns the same symbol by construction.
 // -------------------------------------------------------------------------------------------------
 struct WordReader {  // unaligned little-endian u32 stream from aligned loads
-    const uint32_t* base;  // aligned word that holds the next payload byte
-    const uint32_t* last;  // last readable aligned word of the input buffer
+    const uint32_t* base;  // aligned word holding the first payload byte
+    uint32_t idx;          // index (from base) of the aligned word holding the next payload byte
+    uint32_t last;         // highest index that may be read (inside the input buffer)
     uint32_t shift;        // 8 * misalignment
     uint32_t cur, nxt;
     __device__ __forceinline__ void open(const uint8_t* in, uint64_t in_bytes, uint64_t off) {
@@ -643,31 +681,52 @@ struct WordReader {  // unaligned little-endian u32 stream from aligned loads (S
         base = reinterpret_cast<const uint32_t*>(addr & ~3ull);
         shift = (uint32_t)(addr & 3ull) * 8u;
         const uint64_t end = (reinterpret_cast<uint64_t>(in) + in_bytes) & ~3ull;
-        last = reinterpret_cast<const uint32_t*>(end) - 1;
-        cur = *(base < last ? base : last);
-        nxt = *(base + 1 < last ? base + 1 : last);
+        const uint64_t words_left = end > (addr & ~3ull) ? (end - (addr & ~3ull)) / 4u : 1u;
+        last = (uint32_t)min(words_left - 1u, (uint64_t)0xfffffff0u);
+        idx = 0;
+        cur = base[0];
+        nxt = base[min(1u, last)];
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(cur, nxt, shift); }
-    __device__ __forceinline__ void advance() {
-        base++;
-        cur = nxt;
-        nxt = *(base + 1 < last ? base + 1 : last);
+    __device__ __forceinline__ void advance_if(bool take) {
+        if (take) {
+            idx++;
+            cur = nxt;
+            nxt = base[min(idx + 1u, last)];
+        }
     }
 };
 
-template <typename CumT, typename Table>
-__device__ __forceinline__ uint32_t rans_find(const Table& T, uint32_t slot, uint32_t range, uint32_t steps) {
-    // largest s in [0, range) with cum[s] <= slot
-    uint32_t lo = 0, hi = range;
-    for (uint32_t it = 0; it < steps; it++) {
-        const uint32_t mid = (lo + hi) >> 1;
-        const uint32_t c = T.cum(mid);
-        const bool go_up = (hi - lo > 1u) && c <= slot;
-        const bool go_dn = (hi - lo > 1u) && c > slot;
-        lo = go_up ? mid : lo;
-        hi = go_dn ? mid : hi;
+// Symbol lookup, the equivalent of cum2sym[slot] (entropy_decoding.hpp:262-267): a 64-entry
+// first-symbol table indexed by the top bits of the slot, then a short forward scan over the
+// cumulative counts.  lut[j] = largest s with cum[s] <= (j << lut_shift); the scan ends on the
+// largest s with cum[s] <= slot, exactly the symbol the reference's table holds.
+constexpr int kLutSize = 64;
+
+template <typename Table, typename LutT>
+__device__ __forceinline__ void lut_build(const Table& T, LutT* lut, uint32_t lut_stride, uint32_t lut_shift,
+                                          uint32_t range) {
+    uint32_t s = 0;
+    for (uint32_t j = 0; j < (uint32_t)kLutSize; j++) {
+        const uint32_t target = j << lut_shift;
+        while (s + 1u < range && T.cum(s + 1u) <= target) s++;
+        lut[j * lut_stride] = (LutT)s;
     }
-    return lo;
+}
+
+template <typename Table, typename LutT>
+__device__ __forceinline__ uint32_t rans_lookup(const Table& T, const LutT* lut, uint32_t lut_stride,
+                                                uint32_t lut_shift, uint32_t slot, uint32_t range, uint32_t& c0,
+                                                uint32_t& c1) {
+    uint32_t s = lut[(slot >> lut_shift) * lut_stride];
+    c0 = T.cum(s);
+    c1 = T.cum(s + 1u);
+    while (c1 <= slot && s + 1u < range) {
+        s++;
+        c0 = c1;
+        c1 = T.cum(s + 1u);
+    }
+    return s;
 }
 
 template <typename CumT>
@@ -679,7 +738,8 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
                                                     uint32_t want_u16) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CumT* tab = reinterpret_cast<CumT*>(smem_raw);
-    uint16_t* stage = reinterpret_cast<uint16_t*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));
+    uint16_t* lut = reinterpret_cast<uint16_t*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));
+    uint16_t* stage = lut + kLutSize * 32;
     __shared__ uint64_t s_off[32];
     __shared__ uint32_t s_n[32];
 
@@ -700,7 +760,7 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
         st = streams[s];
         m = meta[s];
     }
-    const bool is_u16 = m.prob_bits <= 16u;
+    const bool is_u16 = m.wide == 0u;
     const bool live = exists && m.kind == 2u && m.n > 0u && (is_u16 ? 1u : 0u) == want_u16 && m.range + 1u <= rows;
     const uint32_t my_n = live ? min(m.n, st.sym_cap) : 0u;
     s_off[lane] = st.sym_off;
@@ -720,43 +780,43 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
     const PerLaneTable<CumT> T{tab, lane};
     const uint32_t bits = m.prob_bits;
     const uint32_t mask = (bits < 32u ? (1u << bits) : 0u) - 1u;
-    uint32_t range_max = live ? m.range : 1u;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) range_max = max(range_max, __shfl_xor_sync(0xffffffffu, range_max, d));
-    const uint32_t steps = 32u - __clz(max(range_max, 2u) - 1u);  // ceil(log2(range_max))
+    const uint32_t lut_shift = bits > 6u ? bits - 6u : 0u;
+    if (live) lut_build(T, lut + lane, 32u, lut_shift, m.range);
+    __syncwarp();
     uint32_t n_max = my_n;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
 
     WordReader rd;
     uint64_t x = 0;
-    if (live) {  // rans64.hpp:107-116: state = first two payload words, low word first
-        rd.open(in, in_bytes, m.payload_off);
-        uint32_t lo = rd.peek();
-        rd.advance();
-        uint32_t hi = rd.peek();
-        rd.advance();
-        x = (uint64_t)lo | ((uint64_t)hi << 32);
+    rd.open(in, in_bytes, live ? m.payload_off : 0ull);
+    {  // rans64.hpp:107-116: state = first two payload words, low word first
+        const uint32_t lo = rd.peek();
+        rd.advance_if(true);
+        const uint32_t hi = rd.peek();
+        rd.advance_if(true);
+        x = live ? ((uint64_t)lo | ((uint64_t)hi << 32)) : kRansL;
     }
+    const uint32_t full = 1u << bits;
     uint16_t* my_row = stage + lane * kSymStride;
     const uint32_t chunks = (n_max + kChunk - 1) / kChunk;
     for (uint32_t chunk = 0; chunk < chunks; chunk++) {
         const uint32_t base = chunk * kChunk;
         __syncwarp();
-#pragma unroll 2
+#pragma unroll 4
         for (uint32_t k = 0; k < (uint32_t)kChunk; k++) {
-            if (base + k < my_n) {
-                const uint32_t slot = (uint32_t)x & mask;                               // rans64.hpp:118-121
-                const uint32_t sym = rans_find<CumT>(T, slot, m.range, steps);         // cum2sym[slot]
-                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
-                const uint32_t f = freq_from<CumT>(c0, c1, bits);
-                x = (uint64_t)f * (x >> bits) + slot - c0;                              // rans64.hpp:126-134
-                if (x < kRansL) {                                                       // rans64.hpp:137-141
-                    x = (x << 32) | rd.peek();
-                    rd.advance();
-                }
-                my_row[k] = (uint16_t)sym;
-            }
+            // past the end of a shorter stream the step runs with freq = 2^bits, start = 0: x is unchanged
+            const bool on = base + k < my_n;
+            const uint32_t slot = (uint32_t)x & mask;                                   // rans64.hpp:118-121
+            uint32_t c0, c1;
+            const uint32_t sym = rans_lookup(T, lut + lane, 32u, lut_shift, slot, m.range, c0, c1);
+            const uint32_t f = on ? c1 - c0 : full;
+            const uint32_t back = on ? slot - c0 : slot;
+            x = (uint64_t)f * (x >> bits) + back;                                       // rans64.hpp:126-134
+            const bool refill = x < kRansL;                                             // rans64.hpp:137-141
+            x = refill ? ((x << 32) | rd.peek()) : x;
+            rd.advance_if(refill);
+            my_row[k] = (uint16_t)sym;
         }
         __syncwarp();
         stage_store_chunk(stage, symbols, s_off, s_n, chunk);
@@ -790,39 +850,41 @@ __global__ void __launch_bounds__(kStaticWarps * 32) k_rans_encode_static(
     if (__ballot_sync(0xffffffffu, live) == 0u) return;
     const SharedTable<uint32_t> T{s_cum};
     uint16_t* stage = s_stage[w];
-    uint8_t* slab = out + s * slab_bytes;
-    uint32_t* wp = reinterpret_cast<uint32_t*>(slab + slab_bytes);
-    const uint32_t* wp_floor = reinterpret_cast<const uint32_t*>(slab);
-    if (!live) wp = const_cast<uint32_t*>(wp_floor = nullptr);
-    bool overflow = false;
+    const bool fits = (uint64_t)slab_bytes >= rans_words_bound(my_n, bits) * 4u;
+    uint32_t* words = reinterpret_cast<uint32_t*>(out + (live ? s : 0) * slab_bytes);
+    const uint32_t cap_words = slab_bytes / 4u;
+    uint32_t widx = cap_words;
     uint64_t x = kRansL;
-    uint32_t n_max = my_n;
+    const uint32_t run_n = (live && fits) ? my_n : 0u;
+    uint32_t n_max = run_n;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
     const uint16_t* my_row = stage + lane * kSymStride;
+    const uint32_t full = 1u << bits;
     for (int chunk = (int)((n_max + kChunk - 1) / kChunk) - 1; chunk >= 0; chunk--) {
         __syncwarp();
         stage_load_chunk(stage, symbols, s_off[w], s_n[w], (uint32_t)chunk);
         __syncwarp();
         const uint32_t base = (uint32_t)chunk * kChunk;
-#pragma unroll 4
+#pragma unroll 8
         for (int k = kChunk - 1; k >= 0; k--) {
-            if (base + (uint32_t)k < my_n) {
-                const uint32_t sym = my_row[k];
-                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
-                x = rans_put(x, c0, c1 - c0, bits, wp, wp_floor, overflow);
-            }
+            const bool on = base + (uint32_t)k < run_n;
+            const uint32_t sym = on ? min((uint32_t)my_row[k], range - 1u) : 0u;
+            uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+            c0 = on ? c0 : 0u;
+            c1 = on ? c1 : full;
+            x = rans_put(x, c0, c1 - c0, bits, words, widx);
         }
     }
     if (live) {
-        if (wp - 2 >= wp_floor) {
-            wp -= 2;
-            wp[0] = (uint32_t)x;
-            wp[1] = (uint32_t)(x >> 32);
+        if (fits) {
+            widx -= 2;
+            words[widx] = (uint32_t)x;
+            words[widx + 1] = (uint32_t)(x >> 32);
+            payload_bytes[s] = (cap_words - widx) * 4u;
         } else {
-            overflow = true;
+            payload_bytes[s] = 0xffffffffu;
         }
-        payload_bytes[s] = overflow ? 0xffffffffu : (uint32_t)(slab + slab_bytes - reinterpret_cast<uint8_t*>(wp));
     }
 }
 
@@ -849,40 +911,44 @@ __global__ void __launch_bounds__(kStaticWarps * 32) k_rans_decode_static(
     if (__ballot_sync(0xffffffffu, live) == 0u) return;
     const SharedTable<uint32_t> T{s_cum};
     const uint32_t mask = (1u << bits) - 1u;
-    const uint32_t steps = 32u - __clz(max(range, 2u) - 1u);
+    const uint32_t lut_shift = bits > 6u ? bits - 6u : 0u;
+    __shared__ uint16_t s_lut[kLutSize];
+    if (threadIdx.x == 0) lut_build(T, s_lut, 1u, lut_shift, range);
+    __syncthreads();
     uint32_t n_max = my_n;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
     WordReader rd;
     uint64_t x = 0;
-    if (live) {
+    {
         const uint64_t total_bytes = n_streams * (uint64_t)slab_bytes;
-        rd.open(in, total_bytes, (s + 1) * (uint64_t)slab_bytes - pb);
-        uint32_t lo = rd.peek();
-        rd.advance();
-        uint32_t hi = rd.peek();
-        rd.advance();
-        x = (uint64_t)lo | ((uint64_t)hi << 32);
+        rd.open(in, total_bytes, live ? (s + 1) * (uint64_t)slab_bytes - pb : 0ull);
+        const uint32_t lo = rd.peek();
+        rd.advance_if(true);
+        const uint32_t hi = rd.peek();
+        rd.advance_if(true);
+        x = live ? ((uint64_t)lo | ((uint64_t)hi << 32)) : kRansL;
     }
+    const uint32_t full = 1u << bits;
     uint16_t* stage = s_stage[w];
     uint16_t* my_row = stage + lane * kSymStride;
     const uint32_t chunks = (n_max + kChunk - 1) / kChunk;
     for (uint32_t chunk = 0; chunk < chunks; chunk++) {
         const uint32_t base = chunk * kChunk;
         __syncwarp();
-#pragma unroll 2
+#pragma unroll 4
         for (uint32_t k = 0; k < (uint32_t)kChunk; k++) {
-            if (base + k < my_n) {
-                const uint32_t slot = (uint32_t)x & mask;
-                const uint32_t sym = rans_find<uint32_t>(T, slot, range, steps);
-                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
-                x = (uint64_t)(c1 - c0) * (x >> bits) + slot - c0;
-                if (x < kRansL) {
-                    x = (x << 32) | rd.peek();
-                    rd.advance();
-                }
-                my_row[k] = (uint16_t)sym;
-            }
+            const bool on = base + k < my_n;
+            const uint32_t slot = (uint32_t)x & mask;
+            uint32_t c0, c1;
+            const uint32_t sym = rans_lookup(T, s_lut, 1u, lut_shift, slot, range, c0, c1);
+            const uint32_t f = on ? c1 - c0 : full;
+            const uint32_t back = on ? slot - c0 : slot;
+            x = (uint64_t)f * (x >> bits) + back;
+            const bool refill = x < kRansL;
+            x = refill ? ((x << 32) | rd.peek()) : x;
+            rd.advance_if(refill);
+            my_row[k] = (uint16_t)sym;
         }
         __syncwarp();
         stage_store_chunk(stage, symbols, s_off[w], s_n[w], chunk);

@@ -106,7 +106,7 @@ def test_decode_entropy_vs_oracle_and_roundtrip():
     g = gpu_lib.gpu()
     rng = np.random.default_rng(3)
     blobs, offs, caps, exp = [], [], [], []
-    pos = 0
+    pos = lossless = 0
     for it in range(400):
         rangev = int(rng.choice([2, 3, 14, 256, 257, 512]))
         pb = int(rng.integers(9, 20))
@@ -118,12 +118,18 @@ def test_decode_entropy_vs_oracle_and_roundtrip():
         if st != 0:
             continue
         lead = int(rng.integers(0, 7))  # arbitrary byte alignment of the stream
+        # expected = what the oracle's decoder reads: table mode 1 is lossy when a frequency needs
+        # more than maxbits bits, and then the decoded symbols are not the input
+        want, _, wst = ol.orc_decode_entropy(enc, 0, flags=7, cap=n)
+        assert wst == 0
+        lossless += int(np.array_equal(want, s))
         blobs.append(np.zeros(lead, np.uint8))
         blobs.append(enc)
         offs.append(pos + lead)
         caps.append(n)
-        exp.append((s, pos + lead + len(enc)))
+        exp.append((want, pos + lead + len(enc)))
         pos += lead + len(enc)
+    assert lossless > 250
     blob = np.concatenate(blobs)
     got = g.decode_entropy_batch(blob, offs, caps, flags=7)
     for i, ((sym, end, st), (s, e)) in enumerate(zip(got, exp)):
