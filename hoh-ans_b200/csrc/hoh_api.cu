@@ -138,20 +138,23 @@ inline unsigned grid_cap(uint64_t items, unsigned per_block, unsigned cap = 148u
 int ensure_smem_opt_in(hoh_ctx* ctx) {
     if (ctx->smem_opt_in) return HOH_OK;
     const int big = 200 * 1024;
-    CK(cudaFuncSetAttribute(k_rans_encode<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CK(cudaFuncSetAttribute(k_rans_encode<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_decode<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_decode<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CK(cudaFuncSetAttribute(k_rans_decode<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CK(cudaFuncSetAttribute(k_tile_unpredict_s0, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_tile_unpredict_s0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_tile_unpredict_s0<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_unpredict_fastpath_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     ctx->smem_opt_in = true;
     return HOH_OK;
 }
 
 // Shared tail of the encode pipeline once the raw histograms are in `freqs`.
+// min_prob_bits: a lower bound the CALLER guarantees for every stream's prob_bits (0 = unknown).
 int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, const uint16_t* d_symbols,
                       uint8_t* d_out, hoh_stream_result* d_results, const uint32_t* freqs,
-                      uint32_t max_range, uint32_t max_prob_bits) {
+                      uint32_t max_range, uint32_t max_prob_bits, uint32_t min_prob_bits) {
     uint32_t* cum;
     uint8_t* heads;
     EncMeta* meta;
@@ -162,18 +165,26 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
     k_build_tables<<<blocks_for(n, kTableWarps), kTableWarps * 32, 0, ctx->stream>>>(d_streams, (uint32_t)n, freqs,
                                                                                     cum, heads, meta);
     LAUNCHED("k_build_tables");
-    const uint32_t rows = max_range + 1;
-    {
-        const size_t smem = (size_t)rows * 32 * sizeof(uint16_t) + 32 * kSymStride * sizeof(uint16_t);
-        k_rans_encode<uint16_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, cum,
-                                                                             d_out, meta, rows, 1u);
+    // one launch per (table width, window-size class); every warp takes part in exactly one of them
+    const uint32_t classes[5] = {0, 64, 128, 256, HOH_MAX_RANGE + 1};
+    for (int c = 0; c < 4; c++) {
+        if (classes[c] >= max_range + 1) break;
+        const uint32_t rows = classes[c + 1];
+        const size_t stage = 2 * 32 * kSymStride * sizeof(uint16_t);
+        const size_t smem16 = (size_t)rows * 32 * sizeof(uint16_t) + stage, smem32 = (size_t)rows * 32 * sizeof(uint32_t) + stage;
+        if (min_prob_bits >= 14) {
+            k_rans_encode<uint16_t, false><<<blocks_for(n, 32), 32, smem16, ctx->stream>>>(
+                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+        } else {
+            k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, ctx->stream>>>(
+                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+        }
         LAUNCHED("k_rans_encode<u16>");
-    }
-    if (max_prob_bits > 15) {
-        const size_t smem = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kSymStride * sizeof(uint16_t);
-        k_rans_encode<uint32_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, cum,
-                                                                             d_out, meta, rows, 0u);
-        LAUNCHED("k_rans_encode<u32>");
+        if (max_prob_bits > 15) {  // 32-bit table lanes; prob_bits >= 16 there, so never LOW_BITS
+            k_rans_encode<uint32_t, false><<<blocks_for(n, 32), 32, smem32, ctx->stream>>>(
+                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);
+            LAUNCHED("k_rans_encode<u32>");
+        }
     }
     k_finish_streams<<<blocks_for(n, 4), 128, 0, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, heads, meta, d_out,
                                                                 d_results);
@@ -193,18 +204,20 @@ int decode_common(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n, const
     LAUNCHED("k_parse_streams");
     k_unpack_stored<<<(unsigned)n, 256, 0, ctx->stream>>>(d_streams, d_in, in_bytes, meta, d_symbols);
     LAUNCHED("k_unpack_stored");
-    const uint32_t rows = HOH_MAX_RANGE + 1;
-    {
-        const size_t smem = (size_t)rows * 32 * sizeof(uint16_t) + kLutSize * 32 * 2 + 32 * kSymStride * sizeof(uint16_t);
-        k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_in, in_bytes,
-                                                                             cum, meta, d_symbols, rows, 1u);
-        LAUNCHED("k_rans_decode<u16>");
-    }
-    {
-        const size_t smem = (size_t)rows * 32 * sizeof(uint32_t) + kLutSize * 32 * 2 + 32 * kSymStride * sizeof(uint16_t);
-        k_rans_decode<uint32_t><<<blocks_for(n, 32), 32, smem, ctx->stream>>>(d_streams, (uint32_t)n, d_in, in_bytes,
-                                                                             cum, meta, d_symbols, rows, 0u);
-        LAUNCHED("k_rans_decode<u32>");
+    // one launch per table-size class; every warp takes part in exactly one of them
+    const uint32_t classes[5] = {0, 64, 128, 256, HOH_MAX_RANGE + 3};
+    for (int c = 0; c < 4; c++) {
+        const uint32_t rows = classes[c + 1];
+        const size_t fixed = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kRingWords * sizeof(uint32_t) +
+                             32 * kSymStride * sizeof(uint16_t);
+        if (rows <= 256) {
+            k_rans_decode<uint8_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 1, ctx->stream>>>(
+                d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, classes[c], rows);
+        } else {
+            k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 2, ctx->stream>>>(
+                d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, classes[c], rows);
+        }
+        LAUNCHED("k_rans_decode");
     }
     return HOH_OK;
 }
@@ -475,7 +488,7 @@ int hoh_encode_entropy_batch(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size
     TRY(scratch_t(ctx, S_FREQS, n_streams * kFreqRow, &freqs));
     k_histogram<<<(unsigned)n_streams, 256, 0, ctx->stream>>>(d_streams, d_symbols, freqs);
     LAUNCHED("k_histogram");
-    return encode_from_freqs(ctx, d_streams, n_streams, d_symbols, d_out, d_results, freqs, max_range, max_prob_bits);
+    return encode_from_freqs(ctx, d_streams, n_streams, d_symbols, d_out, d_results, freqs, max_range, max_prob_bits, 0);
 }
 
 int hoh_decode_entropy_batch(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n_streams,
@@ -509,7 +522,7 @@ int hoh_rans_decode_static(hoh_ctx* ctx, const uint8_t* d_in, uint32_t slab_byte
     if (stream_len == 0 || stream_len % 8 || slab_bytes % 16) return HOH_E_ARG;
     if (n == 0) return HOH_OK;
     const uint64_t streams = (n + stream_len - 1) / stream_len;
-    k_rans_decode_static<<<blocks_for(streams, kStaticWarps * 32), kStaticWarps * 32, 0, ctx->stream>>>(
+    k_rans_decode_static<<<blocks_for(streams, kStaticDecWarps * 32), kStaticDecWarps * 32, 0, ctx->stream>>>(
         d_in, slab_bytes, d_payload_bytes, n, stream_len, d_cum, range, prob_bits, d_symbols);
     LAUNCHED("k_rans_decode_static");
     return HOH_OK;
@@ -561,11 +574,15 @@ int hoh_encode_images_s0(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, ui
     TRY(scratch_t(ctx, S_RESID, n_streams * g.plane_stride, &resid));
     TRY(scratch_t(ctx, S_FREQS, n_streams * kFreqRow, &freqs));
     TRY(scratch_t(ctx, S_STREAMS, n_streams, &streams));
-    k_tile_residuals_s0<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(d_rgb, g, resid, freqs);
+    if (g.width % 4 == 0 && g.tile_w % 4 == 0 && g.tile_w <= 1024) {
+        k_tile_residuals_s0<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(d_rgb, g, resid, freqs);
+    } else {
+        k_tile_residuals_s0_generic<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(d_rgb, g, resid, freqs);
+    }
     LAUNCHED("k_tile_residuals_s0");
     k_make_tile_streams<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(g, n_tiles, slab, streams);
     LAUNCHED("k_make_tile_streams");
-    TRY(encode_from_freqs(ctx, streams, n_streams, resid, d_out, d_results, freqs, 512, 15));
+    TRY(encode_from_freqs(ctx, streams, n_streams, resid, d_out, d_results, freqs, 512, 15, 15));
     if (d_packed) {
         if (!d_packed_off) return HOH_E_ARG;
         k_scan_sizes<<<1, 1024, 0, ctx->stream>>>(d_results, (uint32_t)n_streams, d_packed_off);
@@ -594,14 +611,19 @@ int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_by
     TRY(scratch_t(ctx, S_RESID, n_streams * g.plane_stride, &resid));
     TRY(scratch_t(ctx, S_DSTREAMS, n_streams, &streams));
     TRY(scratch_t(ctx, S_DRESULTS, n_streams, &results));
-    if ((size_t)g.tile_w * 4 * 4 > 200 * 1024) return HOH_E_UNSUPPORTED;
+    const size_t unp_smem = (size_t)kUnpWarps * (2 * 32 * kRingStride + g.tile_w) * sizeof(uint32_t);
+    if (unp_smem > 200 * 1024) return HOH_E_UNSUPPORTED;
     k_make_tile_dec_streams<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(g, n_tiles, d_packed, packed_bytes,
                                                                                  d_packed_off, streams, d_status);
     LAUNCHED("k_make_tile_dec_streams");
     TRY(decode_common(ctx, streams, n_streams, d_packed, packed_bytes, resid, results));
     k_merge_status<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(results, n_streams, d_status);
     LAUNCHED("k_merge_status");
-    k_tile_unpredict_s0<<<blocks_for(n_tiles, 4), 128, (size_t)g.tile_w * 4 * 4, ctx->stream>>>(resid, g, n_tiles, d_rgb);
+    if (g.width % 4 == 0 && g.tile_w % 4 == 0) {
+        k_tile_unpredict_s0<true><<<blocks_for(n_tiles, kUnpWarps), kUnpWarps * 32, unp_smem, ctx->stream>>>(resid, g, n_tiles, d_rgb);
+    } else {
+        k_tile_unpredict_s0<false><<<blocks_for(n_tiles, kUnpWarps), kUnpWarps * 32, unp_smem, ctx->stream>>>(resid, g, n_tiles, d_rgb);
+    }
     LAUNCHED("k_tile_unpredict_s0");
     return HOH_OK;
 }

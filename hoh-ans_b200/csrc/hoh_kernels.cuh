@@ -22,6 +22,8 @@ namespace hohk {
 constexpr int kFreqRow = 512;   // u32 per stream in the histogram / frequency scratch
 constexpr int kCumRow = 520;    // u32 per stream in the cumulative-table scratch (range+1 used)
 constexpr int kChunk = 64;      // symbols per lane between two shared-memory refills
+static_assert(true, "");
+constexpr int kGroup = 8;       // encoder: symbols whose lookups + reciprocals are hoisted ahead of the serial part
 constexpr int kSymStride = 66;  // u16 per staged row (64 + 2 pad -> 33 words: conflict-free transpose)
 constexpr uint64_t kRansL = 1ull << 31;  // rans64.hpp:59
 
@@ -33,6 +35,8 @@ struct EncMeta {
     uint32_t stored_size;  // entropy_encoding.hpp:45
     int32_t status;
     uint32_t table_u16;  // 1 if prob_bits <= 15 (every cumulative count fits a 16-bit lane)
+    uint32_t win_lo;     // lowest symbol with a non-zero frequency
+    uint32_t win_rows;   // (highest - lowest + 1) + 1: rows of cum[] the encoder needs for this stream
     uint32_t pad;
 };
 
@@ -45,7 +49,7 @@ struct DecMeta {
     uint32_t kind;  // 0 nothing to do, 1 stored, 2 rANS
     uint32_t maxbits;
     int32_t status;
-    uint32_t wide;  // 1 if some cumulative count needs more than 16 bits (32-bit table lanes)
+    uint32_t used;  // symbols with non-zero frequency = rows of the dense decode table (+1 sentinel)
     uint32_t pad;
 };
 
@@ -187,6 +191,8 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
     m.stored_size = 0;
     m.status = HOH_S_OK;
     m.table_u16 = st.prob_bits <= 15 ? 1u : 0u;
+    m.win_lo = 0;
+    m.win_rows = 0;
     m.pad = 0;
     uint8_t* head = heads + (size_t)s * HOH_HEAD_CAP;
     if (st.n == 0) {  // entropy_encoding.hpp:19-23: two varints and nothing else (D2)
@@ -215,6 +221,19 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
     }
     uint32_t* ct = cumtab + (size_t)s * kCumRow;
     for (uint32_t i = lane; i <= st.range; i += 32) ct[i] = cum[i];
+    {  // window of symbols that actually occur: the encoder stages only cum[win_lo .. win_lo + win_rows)
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        for (uint32_t i = lane; i < st.range; i += 32)
+            if (f[i] != 0u) {
+                lo = min(lo, i);
+                hi = max(hi, i);
+            }
+        lo = warp_min(lo);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+        m.win_lo = lo;
+        m.win_rows = hi - lo + 2u;
+    }
     if (lane == 0) m.head_len = hohfmt::build_head(f, st.range, st.n, st.prob_bits, s_head[w], &m.stored_size);
     m.head_len = __shfl_sync(0xffffffffu, m.head_len, 0);
     __syncwarp();
@@ -231,46 +250,24 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
 // state: x' = ((x / f) << bits) + x % f + start after the optional 32-bit renormalisation.
 // The reference multiplies by a precomputed 64-bit reciprocal per symbol (24 B/symbol = 12 KB per
 // stream — 32 per-lane tables of that size do not fit in shared memory).  Here the only per-symbol
-// state in shared memory is the 16-bit cumulative count; the quotient comes from a 32-bit reciprocal
-// built on the fly (one MUFU.RCP, biased low) refined in three exact integer rounds, so the result is
-// the true floor(x / f) for every f <= 2^19 and x < f * 2^(63-bits).
+// state in shared memory is the cumulative count.  A stream is one serial chain of steps, so what
+// bounds the kernel is the LENGTH OF THE DEPENDENT CHAIN per symbol, not the instruction count:
+// the reciprocal 1/f is computed in fp64 off the chain (it does not depend on x: MUFU.RCP64H + two
+// Newton steps, biased low), and the chain itself is  u64 -> f64, one DMUL, f64 -> u64, one IMAD for the
+// remainder, one correction.  The estimate never exceeds the true quotient (operand truncated, the
+// reciprocal biased by 2^-50, checked on the CPU over 2*10^8 cases) and is at most 1 short for
+// prob_bits >= 14 (3 for 12..13), so the corrections below make the result exact for every input.
 
-// Normalised reciprocal: with L = bit length of f, returns m <= 2^(31+L) / f (biased low by at most
-// 2^-20 relative, saturating at 2^32 - 1 when f is a power of two) and sh = L - 1, so that
-// floor(x / f) ~ ((x * m) >> 32) >> sh.
-__device__ __forceinline__ uint32_t recip_under(uint32_t f, uint32_t& sh) {
-    const uint32_t L = 32u - (uint32_t)__clz((int)f);
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_rn(f)));        // f <= 2^19: exact in fp32
-    r = __int_as_float(__float_as_int(r) + (int)((31u + L) << 23)) * 0.99999952316284f;  // * 2^(31+L) * (1 - 2^-21)
-    sh = L - 1u;
-    return __float2uint_rz(r);  // saturates
-}
-
-// q = floor(x / f), r = x mod f for f <= 2^19, x < f * 2^(63 - bits).  Every partial quotient
-// under-estimates (m is biased low) so the remainders stay non-negative; brute-forced on the CPU over
-// 10^8 (x, f, bits in 1..19) cases with the reciprocal perturbed by +-1 ulp: R1 < 2^43, R2 < 2^23 and at
-// most one final correction.
-__device__ __forceinline__ void divmod_u64(uint64_t x, uint32_t f, uint32_t m, uint32_t sh, uint64_t& q,
-                                           uint32_t& r) {
-    const uint32_t a = (uint32_t)(x >> 32), b = (uint32_t)x;
-    const uint64_t q0 = ((uint64_t)a * m + __umulhi(b, m)) >> sh;  // floor(x * m / 2^(32+sh))
-    const uint64_t r1 = x - q0 * f;
-    const uint64_t q1 = ((uint64_t)(uint32_t)(r1 >> 32) * m + __umulhi((uint32_t)r1, m)) >> sh;
-    const uint32_t r2 = (uint32_t)r1 - (uint32_t)q1 * f;  // true value < 2^23: exact mod 2^32
-    const uint32_t q2 = __umulhi(r2, m) >> sh;
-    uint32_t rr = r2 - q2 * f;
-    uint32_t fix = q2;
-    if (rr >= f) {
-        rr -= f;
-        fix++;
-    }
-    if (rr >= f) {  // bound: r < 3f; never observed to need the second correction
-        rr -= f;
-        fix++;
-    }
-    q = q0 + q1 + fix;
-    r = rr;
+// 1/f biased low: inv <= (1/f)(1 - 2^-51), relative error < 2^-49.
+__device__ __forceinline__ double recip_low(uint32_t f) {
+    const double fd = (double)f;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(fd));  // 20-bit seed
+    double e = fma(-fd, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-fd, r, 1.0);
+    r = fma(r, e, r);
+    return r * 0.99999999999999911182;  // 1 - 2^-50
 }
 
 // One encoder step.  `words` is the stream's slab viewed as u32, `widx` the index of the lowest word
@@ -278,18 +275,31 @@ __device__ __forceinline__ void divmod_u64(uint64_t x, uint32_t f, uint32_t m, u
 // (at most (n * bits + 32) / 32 + 3 words are ever written), so there is no per-symbol bounds test.
 // A step with freq == 2^bits, start == 0 is an exact no-op (x / 2^bits, x mod 2^bits recombine to x and
 // the renormalisation test x >= 2^63 never fires): lanes whose stream is shorter use it as padding.
-__device__ __forceinline__ uint64_t rans_put(uint64_t x, uint32_t start, uint32_t freq, uint32_t bits,
+// LOW_BITS: prob_bits below 14 may occur (the quotient estimate can then be short by more than one).
+// `inv` = recip_low(freq) is passed in: it does not depend on the state, so callers compute it for a
+// group of symbols ahead of the serial part (those computations overlap each other) and the serial
+// part is only the short dependent chain.
+template <bool LOW_BITS>
+__device__ __forceinline__ uint64_t rans_put(uint64_t x, uint32_t start, uint32_t freq, double inv, uint32_t bits,
                                              uint32_t* __restrict__ words, uint32_t& widx) {
-    uint32_t sh;
-    const uint32_t m = recip_under(freq, sh);
     // x >= ((L >> bits) << 32) * freq  <=>  (x >> (63 - bits)) >= freq, and 63 - bits >= 32
     const bool emit = ((uint32_t)(x >> 32) >> (31u - bits)) >= freq;
     if (emit) words[--widx] = (uint32_t)x;
     x = emit ? (x >> 32) : x;
-    uint64_t q;
-    uint32_t r;
-    divmod_u64(x, freq, m, sh, q, r);
-    return (q << bits) + (uint64_t)(r + start);
+    uint64_t q = __double2ull_rz(__ull2double_rz(x) * inv);  // q <= floor(x / freq), short by <= 1 (bits >= 14)
+    uint32_t r = (uint32_t)x - (uint32_t)q * freq;           // true remainder < 2^32: exact mod 2^32
+    if (r >= freq) {
+        r -= freq;
+        q++;
+    }
+    if (LOW_BITS) {
+        while (r >= freq) {
+            r -= freq;
+            q++;
+        }
+    }
+    // r + start < 2^bits, so the sum cannot carry into the shifted quotient
+    return (q << bits) | (uint64_t)(r + start);
 }
 
 // Words a stream of n symbols can emit at most, flush included, plus slack.
@@ -311,29 +321,32 @@ struct SharedTable {
     __device__ __forceinline__ uint32_t cum(uint32_t s) const { return tab[s]; }
 };
 
-// Cooperative load of one 64-symbol chunk for the 32 streams of a warp into the padded transpose.
-// Row r of `stage` receives symbols [64*chunk, 64*chunk+64) of stream r (zero beyond its n).
+// Cooperative, asynchronous load of one 64-symbol chunk for the 32 streams of a warp into the padded
+// transpose: row r of `stage` receives symbols [64*chunk, 64*chunk+64) of stream r, zero-filled beyond
+// its n.  cp.async (LDGSTS) writes shared memory directly, so the copy of the next chunk overlaps the
+// coding of the current one; complete it with stage_wait().
+__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void* gptr, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void stage_wait() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+}
 __device__ __forceinline__ void stage_load_chunk(uint16_t* stage, const uint16_t* __restrict__ symbols,
                                                  const uint64_t* s_off, const uint32_t* s_n, uint32_t chunk) {
     const uint32_t lane = lane_id(), half = lane >> 4, q = lane & 15u;
-    uint32_t* stage32 = reinterpret_cast<uint32_t*>(stage);
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
 #pragma unroll 4
     for (uint32_t jj = 0; jj < 16; jj++) {
         const uint32_t r = 2u * jj + half;
         const uint32_t first = chunk * kChunk + 4u * q;
         const uint32_t n = s_n[r];
-        uint2 v = make_uint2(0u, 0u);
-        if (first + 3u < n) {
-            v = *reinterpret_cast<const uint2*>(symbols + s_off[r] + first);
-        } else if (first < n) {
-            const uint16_t* p = symbols + s_off[r] + first;
-            uint32_t a = p[0];
-            uint32_t b = first + 1u < n ? p[1] : 0u;
-            uint32_t c = first + 2u < n ? p[2] : 0u;
-            v = make_uint2(a | (b << 16), c);
-        }
-        stage32[r * (kSymStride / 2) + 2u * q] = v.x;
-        stage32[r * (kSymStride / 2) + 2u * q + 1u] = v.y;
+        const uint32_t left = n > first ? min(n - first, 4u) : 0u;  // symbols of this quad that exist
+        // never form an address past the stream: clamp the source to its start when nothing is read
+        const uint16_t* src = symbols + s_off[r] + (left ? first : 0u);
+        const uint32_t dst = stage_addr + (r * (kSymStride / 2) + 2u * q) * 4u;
+        cp_async4(dst, src, min(left, 2u) * 2u);
+        cp_async4(dst + 4u, src + (left > 2u ? 2 : 0), left > 2u ? (left - 2u) * 2u : 0u);
     }
 }
 
@@ -364,14 +377,19 @@ __device__ __forceinline__ void stage_store_chunk(const uint16_t* stage, uint16_
 // rANS encode, per-stream tables — entropy_encoding.hpp:206-238.  One warp per CTA, one stream per
 // lane.  Dynamic shared memory: (rows * 32) CumT + 32 * kSymStride u16.
 // -------------------------------------------------------------------------------------------------
-template <typename CumT>
+// One warp per CTA, one stream per lane.  Each lane's table holds only the window of symbols that occur
+// in its stream (cum[win_lo .. win_lo + win_rows)); `rows_lo < need <= rows` selects the warps of this
+// launch's table-size class (need = widest window among the warp's streams), one launch per class.
+// Dynamic shared memory: rows * 32 CumT + 2 * 32 * kSymStride u16 (double-buffered symbol staging).
+template <typename CumT, bool LOW_BITS>
 __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __restrict__ streams,
                                                     uint32_t n_streams, const uint16_t* __restrict__ symbols,
                                                     const uint32_t* __restrict__ cumtab, uint8_t* __restrict__ out,
-                                                    EncMeta* __restrict__ meta, uint32_t rows, uint32_t want_u16) {
+                                                    EncMeta* __restrict__ meta, uint32_t rows_lo, uint32_t rows,
+                                                    uint32_t want_u16) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CumT* tab = reinterpret_cast<CumT*>(smem_raw);
-    uint16_t* stage = reinterpret_cast<uint16_t*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));
+    uint16_t* stage0 = reinterpret_cast<uint16_t*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));
     __shared__ uint64_t s_off[32];
     __shared__ uint32_t s_n[32];
 
@@ -392,10 +410,16 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
         st.out_cap = 0;
         m.status = HOH_S_OK;
         m.table_u16 = want_u16;
+        m.win_lo = 0;
+        m.win_rows = 0;
     }
     // a stream takes part if it has symbols, its table was built, and it belongs to this launch's
-    // table width (16-bit lanes for prob_bits <= 16, 32-bit otherwise)
+    // table width (16-bit lanes for prob_bits <= 15, 32-bit otherwise)
     bool live = exists && st.n > 0 && m.status == HOH_S_OK && m.table_u16 == want_u16;
+    uint32_t need = live ? m.win_rows : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) need = max(need, __shfl_xor_sync(0xffffffffu, need, d));
+    if (need <= rows_lo || need > rows) return;  // another class's launch (or nothing to do)
     if (live && (uint64_t)st.out_cap < rans_words_bound(st.n, st.prob_bits) * 4u + HOH_HEAD_CAP + 32u) {
         m.status = HOH_S_OVERFLOW;  // slab too small for the worst case: refuse rather than test per symbol
         meta[s] = m;
@@ -403,18 +427,18 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
     }
     s_off[lane] = st.sym_off;
     s_n[lane] = live ? st.n : 0u;
-    if (__ballot_sync(0xffffffffu, live) == 0u) return;
+    __syncwarp();
 
-    // tables: stream j's row i -> tab[i*32 + j]
+    // tables: row i of stream j's window -> tab[i*32 + j]
     for (uint32_t j = 0; j < 32; j++) {
         const uint32_t sj = blockIdx.x * 32u + j;
         const bool lj = __shfl_sync(0xffffffffu, (int)live, j) != 0;
-        const uint32_t rj = __shfl_sync(0xffffffffu, st.range, j);
+        const uint32_t wj = __shfl_sync(0xffffffffu, m.win_rows, j);
+        const uint32_t oj = __shfl_sync(0xffffffffu, m.win_lo, j);
         if (!lj) continue;
-        const uint32_t* src = cumtab + (size_t)sj * kCumRow;
-        for (uint32_t i = lane; i <= rj; i += 32) tab[i * 32u + j] = (CumT)src[i];
+        const uint32_t* src = cumtab + (size_t)sj * kCumRow + oj;
+        for (uint32_t i = lane; i < wj; i += 32) tab[i * 32u + j] = (CumT)src[i];
     }
-    __syncwarp();
 
     const PerLaneTable<CumT> T{tab, lane};
     const uint32_t bits = st.prob_bits;
@@ -427,23 +451,59 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
     const uint32_t my_n = live ? st.n : 0u;
-    const uint16_t* my_row = stage + lane * kSymStride;
     const uint32_t full = 1u << bits;
-    const uint32_t sym_max = st.range - 1u;  // out-of-alphabet input must not index past the lane's table
+    const uint32_t win_lo = m.win_lo;
+    const uint32_t sym_max = live ? m.win_rows - 2u : 0u;  // index of the last window row that is a symbol
 
-    for (int chunk = (int)((n_max + kChunk - 1) / kChunk) - 1; chunk >= 0; chunk--) {
-        __syncwarp();
-        stage_load_chunk(stage, symbols, s_off, s_n, (uint32_t)chunk);
-        __syncwarp();
-        const uint32_t base = (uint32_t)chunk * kChunk;
-#pragma unroll 8
-        for (int k = kChunk - 1; k >= 0; k--) {  // entropy_encoding.hpp:222-225, last symbol first
-            const bool on = base + (uint32_t)k < my_n;
-            const uint32_t sym = on ? min((uint32_t)my_row[k], sym_max) : 0u;
-            uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
-            c0 = on ? c0 : 0u;      // padding step: freq = 2^bits, start = 0 leaves x untouched
-            c1 = on ? c1 : full;
-            x = rans_put(x, c0, c1 - c0, bits, words, widx);
+    // entropy_encoding.hpp:222-225, last symbol first, as a software pipeline over groups of kGroup
+    // symbols: while the serial state updates of group g run, the table lookups and reciprocals of group
+    // g-1 (independent of the state) are computed, so they are ready long before the chain needs them
+    // and their instructions fill the chain's dependency stalls.  Groups are numbered across chunks:
+    // group g covers symbols [kGroup*g, kGroup*g + kGroup).
+    const int n_chunks = (int)((n_max + kChunk - 1) / kChunk);
+    constexpr int kGroupsPerChunk = kChunk / kGroup;
+    auto prepare = [&](int g, uint32_t(&g_start)[kGroup], uint32_t(&g_freq)[kGroup], double(&g_inv)[kGroup]) {
+        const int chunk = g / kGroupsPerChunk, k0 = (g % kGroupsPerChunk) * kGroup;
+        const uint16_t* row = stage0 + (chunk & 1) * 32 * kSymStride + lane * kSymStride + k0;
+        const uint32_t base = (uint32_t)g * kGroup;
+#pragma unroll
+        for (int j = 0; j < kGroup; j++) {
+            const bool on = base + (uint32_t)j < my_n;
+            // window-relative index; out-of-alphabet input must not index past the lane's table
+            const uint32_t sym = on ? min((uint32_t)row[j] - win_lo, sym_max) : 0u;
+            const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+            g_start[j] = on ? c0 : 0u;  // padding step: freq = 2^bits, start = 0 leaves x untouched
+            g_freq[j] = on ? c1 - c0 : full;
+            g_inv[j] = recip_low(g_freq[j]);
+        }
+    };
+    auto run = [&](const uint32_t(&g_start)[kGroup], const uint32_t(&g_freq)[kGroup], const double(&g_inv)[kGroup]) {
+#pragma unroll
+        for (int j = kGroup - 1; j >= 0; j--)
+            x = rans_put<LOW_BITS>(x, g_start[j], g_freq[j], g_inv[j], bits, words, widx);
+    };
+    if (n_chunks > 0) {
+        uint32_t a_start[kGroup], a_freq[kGroup], b_start[kGroup], b_freq[kGroup];
+        double a_inv[kGroup], b_inv[kGroup];
+        stage_load_chunk(stage0 + ((n_chunks - 1) & 1) * 32 * kSymStride, symbols, s_off, s_n, (uint32_t)(n_chunks - 1));
+        stage_wait();
+        if (n_chunks > 1)
+            stage_load_chunk(stage0 + ((n_chunks - 2) & 1) * 32 * kSymStride, symbols, s_off, s_n, (uint32_t)(n_chunks - 2));
+        const int n_groups = n_chunks * kGroupsPerChunk;  // even
+        prepare(n_groups - 1, a_start, a_freq, a_inv);
+        for (int g = n_groups - 1; g >= 1; g -= 2) {
+            prepare(g - 1, b_start, b_freq, b_inv);  // g odd: g-1 is in the same chunk
+            run(a_start, a_freq, a_inv);
+            if (g - 1 >= 1) {
+                if (((g - 1) % kGroupsPerChunk) == 0) {  // group g-2 is the last of the previous chunk
+                    const int chunk = (g - 1) / kGroupsPerChunk;
+                    stage_wait();  // chunk-1 has landed; this chunk's buffer is free (its last group is in b_*)
+                    if (chunk >= 2)
+                        stage_load_chunk(stage0 + (chunk & 1) * 32 * kSymStride, symbols, s_off, s_n, (uint32_t)(chunk - 2));
+                }
+                prepare(g - 2, a_start, a_freq, a_inv);
+            }
+            run(b_start, b_freq, b_inv);
         }
     }
     if (live) {
@@ -590,7 +650,7 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
     m.kind = 0;
     m.maxbits = h.maxbits;
     m.status = status;
-    m.wide = 0;
+    m.used = 0;
     m.pad = 0;
     hoh_dec_result res;
     res.end_off = h.body;
@@ -623,13 +683,33 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
         __syncwarp();
         if (status == HOH_S_OK) {
             warp_cumsum(f, cum, h.range);  // stattools.hpp:6-11
+            // Dense decode table: one packed entry (cum | symbol << 20) per symbol that has a non-zero
+            // frequency, in symbol order.  Dropping the empty symbols changes nothing for a valid table
+            // (a slot never falls on one) and keeps the lookup's neighbourhood search short.  Physical
+            // rows: [0] = leading sentinel (cum 0), [1 .. used] = entries, [used+1], [used+2] = the total.
             uint32_t* ct = cumtab + (size_t)s * kCumRow;
-            for (uint32_t i = lane; i <= h.range; i += 32) ct[i] = cum[i];
-            m.wide = (h.prob_bits > 15u || cum[h.range] > 65535u) ? 1u : 0u;
+            {
+                const uint32_t per = (h.range + 31u) / 32u;
+                const uint32_t lo = min(lane * per, h.range), hi = min(lo + per, h.range);
+                uint32_t cnt = 0;
+                for (uint32_t i = lo; i < hi; i++) cnt += f[i] != 0u;
+                const uint32_t incl = warp_incl_scan(cnt);
+                uint32_t d = incl - cnt;
+                for (uint32_t i = lo; i < hi; i++)
+                    if (f[i] != 0u) ct[1u + d++] = cum[i] | (i << 20);
+                m.used = __shfl_sync(0xffffffffu, incl, 31);
+                if (lane == 0) {
+                    ct[0] = 0u;
+                    ct[m.used + 1u] = cum[h.range];
+                    ct[m.used + 2u] = cum[h.range];
+                }
+            }
+            if (m.used == 0u || cum[h.range] >= (1u << 20) || h.prob_bits > HOH_MAX_PROB_BITS || h.prob_bits == 0u)
+                status = HOH_S_BAD_TABLE;
             uint64_t at = after_table;
             const uint32_t payload = hohfmt::get_varint(bytes, &at);  // entropy_decoding.hpp:256
             m.payload_off = at;
-            m.kind = 2;
+            m.kind = status == HOH_S_OK ? 2u : 0u;
             res.end_off = (st.flags & HOH_FIX_ADVANCE) ? at + payload : at;  // D8
         }
         m.status = status;
@@ -667,79 +747,176 @@ __global__ void __launch_bounds__(256) k_unpack_stored(const hoh_dec_stream* __r
 
 // -------------------------------------------------------------------------------------------------
 // rANS decode, per-stream tables — entropy_decoding.hpp:254-276 with rans64.hpp:107-142.
-// cum2sym (2^prob_bits entries, :262-267) is replaced by a search over the cumulative table, which
-// returns the same symbol by construction.
 // -------------------------------------------------------------------------------------------------
-struct WordReader {  // unaligned little-endian u32 stream from aligned loads
-    const uint32_t* base;  // aligned word holding the first payload byte
-    uint32_t idx;          // index (from base) of the aligned word holding the next payload byte
-    uint32_t last;         // highest index that may be read (inside the input buffer)
-    uint32_t shift;        // 8 * misalignment
-    uint32_t cur, nxt;
-    __device__ __forceinline__ void open(const uint8_t* in, uint64_t in_bytes, uint64_t off) {
-        const uint64_t addr = reinterpret_cast<uint64_t>(in) + off;
-        base = reinterpret_cast<const uint32_t*>(addr & ~3ull);
-        shift = (uint32_t)(addr & 3ull) * 8u;
-        const uint64_t end = (reinterpret_cast<uint64_t>(in) + in_bytes) & ~3ull;
-        const uint64_t words_left = end > (addr & ~3ull) ? (end - (addr & ~3ull)) / 4u : 1u;
-        last = (uint32_t)min(words_left - 1u, (uint64_t)0xfffffff0u);
-        idx = 0;
-        cur = base[0];
-        nxt = base[min(1u, last)];
+// Payload words.  Every lane reads its own stream, at its own data-dependent pace, starting at an
+// arbitrary byte offset.  Words are staged in a per-lane ring in shared memory filled by
+// cp.async in aligned 16-byte blocks: nothing in the decode loop ever names a register with a load in
+// flight (a register look-ahead queue stalls on exactly that), and the ring is topped up at uniform
+// points (every kTopUp symbols) far enough ahead that a whole period of consumption is always resident:
+// a symbol consumes at most one word and a top-up requests words up to position + kAhead, so whatever
+// is read during one period was requested by the previous top-up at the latest, whose copies are
+// complete (cp.async.wait_group 1) before the period starts.
+constexpr int kRingWords = 32;  // per lane, power of two (>= kAhead + 3 + 4: requests never overwrite unread words)
+constexpr int kTopUp = 8;       // symbols between two top-ups (<= 8 words consumed)
+constexpr int kAhead = 20;      // words requested ahead of the read position (>= 2 * kTopUp + 2)
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct WordRing {
+    const uint32_t* base16;  // 16-byte aligned word pointer at or below the first payload byte
+    uint32_t* ring;          // this lane's kRingWords words of shared memory
+    uint32_t ring_addr;      // the same, as a shared-window address
+    uint32_t pos;            // aligned-word index (from base16) holding the next payload byte
+    uint32_t end;            // aligned-word index up to which blocks have been requested (multiple of 4)
+    uint32_t limit;          // first aligned-word index that must not be read (multiple of 4, inside the buffer)
+    uint32_t shift;          // 8 * byte misalignment of the payload
+    uint32_t next;           // the next payload word, already assembled
+
+    __device__ __forceinline__ void request(uint32_t want) {  // blocks up to word index `want`
+        while (end < want) {
+            if (end < limit) cp_async16(ring_addr + (end & (kRingWords - 1)) * 4u, base16 + end);
+            end += 4u;
+        }
     }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(cur, nxt, shift); }
-    __device__ __forceinline__ void advance_if(bool take) {
+    __device__ __forceinline__ uint32_t assemble() const {
+        const uint32_t lo = ring[pos & (kRingWords - 1)], hi = ring[(pos + 1u) & (kRingWords - 1)];
+        return __funnelshift_r(lo, hi, shift);
+    }
+    // in / in_bytes: the whole input buffer (16-byte aligned base; reads stay inside it)
+    __device__ __forceinline__ void open(const uint8_t* in, uint64_t in_bytes, uint64_t off, uint32_t* lane_ring) {
+        ring = lane_ring;
+        ring_addr = (uint32_t)__cvta_generic_to_shared(lane_ring);
+        const uint64_t buf_end = (reinterpret_cast<uint64_t>(in) + in_bytes) & ~15ull;
+        uint64_t addr = reinterpret_cast<uint64_t>(in) + off;
+        if (addr + 16u > buf_end) addr = buf_end - 16u;  // a malformed offset must not leave the buffer
+        base16 = reinterpret_cast<const uint32_t*>(addr & ~15ull);
+        pos = (uint32_t)((addr & 15ull) >> 2);
+        shift = (uint32_t)(addr & 3ull) * 8u;
+        const uint64_t words_left = (buf_end - (addr & ~15ull)) / 4u;
+        limit = (uint32_t)min(words_left, (uint64_t)0xfffffff0u);
+        end = 0;
+        request(pos + kAhead);
+        cp_async_commit();
+        cp_async_wait_group<0>();
+        next = assemble();
+    }
+    // uniform point, every kTopUp symbols: request ahead, and make everything but that request resident
+    __device__ __forceinline__ void top_up() {
+        request(pos + kAhead);
+        cp_async_commit();
+        cp_async_wait_group<1>();
+    }
+    __device__ __forceinline__ void take_if(bool take) {
         if (take) {
-            idx++;
-            cur = nxt;
-            nxt = base[min(idx + 1u, last)];
+            pos++;
+            next = assemble();
         }
     }
 };
 
-// Symbol lookup, the equivalent of cum2sym[slot] (entropy_decoding.hpp:262-267): a 64-entry
-// first-symbol table indexed by the top bits of the slot, then a short forward scan over the
-// cumulative counts.  lut[j] = largest s with cum[s] <= (j << lut_shift); the scan ends on the
-// largest s with cum[s] <= slot, exactly the symbol the reference's table holds.
-constexpr int kLutSize = 64;
+// Symbol lookup, the equivalent of cum2sym[slot] (entropy_decoding.hpp:262-267), over the dense table
+// (physical rows: see k_parse_streams).  A 128-entry table indexed by the top 7 bits of the slot holds
+// the row whose interval contains the MIDDLE of that 1/128th of the range, so the wanted row is that
+// one or a direct neighbour unless several symbols share the bucket; the four rows around it are
+// fetched together (independent loads: one shared-memory round trip on the dependent chain) and the
+// answer is selected without a branch; only a slot further away takes the scan loops.  The result is
+// the largest row with cum <= slot, i.e. the symbol the reference's 2^prob_bits-entry table holds.
+constexpr int kLutSize = 128;
+constexpr uint32_t kCumMask = (1u << 20) - 1u;
+
+// Dense table accessors: PerLane = 32 independent tables interleaved [row][lane]; Shared = one table.
+struct PerLaneDense {
+    const uint32_t* tab;
+    uint32_t lane;
+    __device__ __forceinline__ uint32_t at(uint32_t p) const { return tab[p * 32u + lane]; }
+};
+struct SharedDense {
+    const uint32_t* tab;
+    __device__ __forceinline__ uint32_t at(uint32_t p) const { return tab[p]; }
+};
 
 template <typename Table, typename LutT>
 __device__ __forceinline__ void lut_build(const Table& T, LutT* lut, uint32_t lut_stride, uint32_t lut_shift,
-                                          uint32_t range) {
-    uint32_t s = 0;
+                                          uint32_t used) {
+    uint32_t p = 1;
+    const uint32_t half = lut_shift ? (1u << (lut_shift - 1u)) : 0u;
     for (uint32_t j = 0; j < (uint32_t)kLutSize; j++) {
-        const uint32_t target = j << lut_shift;
-        while (s + 1u < range && T.cum(s + 1u) <= target) s++;
-        lut[j * lut_stride] = (LutT)s;
+        const uint32_t target = (j << lut_shift) + half;
+        while (p < used && (T.at(p + 1u) & kCumMask) <= target) p++;
+        lut[j * lut_stride] = (LutT)p;
     }
 }
 
+// Returns the symbol; c0 / c1 = cumulative count of the symbol / of the next used symbol.
 template <typename Table, typename LutT>
 __device__ __forceinline__ uint32_t rans_lookup(const Table& T, const LutT* lut, uint32_t lut_stride,
-                                                uint32_t lut_shift, uint32_t slot, uint32_t range, uint32_t& c0,
+                                                uint32_t lut_shift, uint32_t slot, uint32_t used, uint32_t& c0,
                                                 uint32_t& c1) {
-    uint32_t s = lut[(slot >> lut_shift) * lut_stride];
-    c0 = T.cum(s);
-    c1 = T.cum(s + 1u);
-    while (c1 <= slot && s + 1u < range) {
-        s++;
-        c0 = c1;
-        c1 = T.cum(s + 1u);
+    uint32_t p = lut[(slot >> lut_shift) * lut_stride];
+    const uint32_t em = T.at(p - 1u), e0 = T.at(p), e1 = T.at(p + 1u), e2 = T.at(p + 2u);
+    const bool down = slot < (e0 & kCumMask);
+    const bool up = slot >= (e1 & kCumMask) && p < used;
+    uint32_t e = down ? em : (up ? e1 : e0);
+    uint32_t hi = down ? e0 : (up ? e2 : e1);
+    p += up ? 1u : 0u;
+    p -= down ? 1u : 0u;
+    while (slot < (e & kCumMask)) {  // further down (rare)
+        p--;
+        hi = e;
+        e = T.at(p);
     }
-    return s;
+    while (slot >= (hi & kCumMask) && p < used) {  // further up (rare)
+        p++;
+        e = hi;
+        hi = T.at(p + 1u);
+    }
+    c0 = e & kCumMask;
+    c1 = hi & kCumMask;
+    return e >> 20;
 }
 
-template <typename CumT>
+// One decode step (rans64.hpp:118-142).  `on` false = padding step past the end of a shorter stream:
+// freq = 2^bits, start = 0 leaves x unchanged and never refills.
+template <typename Table, typename LutT>
+__device__ __forceinline__ uint32_t rans_get(uint64_t& x, WordRing& rd, const Table& T, const LutT* lut,
+                                             uint32_t lut_stride, uint32_t lut_shift, uint32_t used, uint32_t bits,
+                                             uint32_t mask, uint32_t full, bool on) {
+    const uint32_t slot = (uint32_t)x & mask;  // rans64.hpp:118-121
+    uint32_t c0, c1;
+    const uint32_t sym = rans_lookup(T, lut, lut_stride, lut_shift, slot, used, c0, c1);
+    const uint32_t f = on ? c1 - c0 : full;
+    const uint32_t back = on ? slot - c0 : slot;
+    x = (uint64_t)f * (x >> bits) + back;      // rans64.hpp:126-134
+    const bool refill = x < kRansL;            // rans64.hpp:137-141
+    x = refill ? ((x << 32) | rd.next) : x;
+    rd.take_if(refill);
+    return sym;
+}
+
+// One warp per CTA, one stream per lane.  `rows_lo < need <= rows` selects the warps of this launch's
+// table-size class (need = rows of the largest dense table among the warp's streams): the host
+// launches one grid per class with the matching shared-memory size and every warp runs in exactly one.
+// LutT = u8 when rows <= 256.  Dynamic shared memory: rows * 32 u32 (tables) + 32 * kRingWords u32 (word
+// rings) + 128 * 32 LutT + 32 * kSymStride u16 (symbol staging).
+template <typename LutT>
 __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __restrict__ streams,
                                                     uint32_t n_streams, const uint8_t* __restrict__ in,
                                                     uint64_t in_bytes, const uint32_t* __restrict__ cumtab,
                                                     const DecMeta* __restrict__ meta,
-                                                    uint16_t* __restrict__ symbols, uint32_t rows,
-                                                    uint32_t want_u16) {
+                                                    uint16_t* __restrict__ symbols, uint32_t rows_lo,
+                                                    uint32_t rows) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    CumT* tab = reinterpret_cast<CumT*>(smem_raw);
-    uint16_t* lut = reinterpret_cast<uint16_t*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));
-    uint16_t* stage = lut + kLutSize * 32;
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* rings = tab + (size_t)rows * 32u;
+    uint16_t* stage = reinterpret_cast<uint16_t*>(rings + 32 * kRingWords);
+    LutT* lut = reinterpret_cast<LutT*>(stage + 32 * kSymStride);
     __shared__ uint64_t s_off[32];
     __shared__ uint32_t s_n[32];
 
@@ -756,67 +933,71 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
     m.prob_bits = 1;
     m.payload_off = 0;
     m.status = HOH_S_OK;
+    m.used = 0;
     if (exists) {
         st = streams[s];
         m = meta[s];
     }
-    const bool is_u16 = m.wide == 0u;
-    const bool live = exists && m.kind == 2u && m.n > 0u && (is_u16 ? 1u : 0u) == want_u16 && m.range + 1u <= rows;
+    const bool live = exists && m.kind == 2u && m.n > 0u;
+    uint32_t need = live ? m.used + 3u : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) need = max(need, __shfl_xor_sync(0xffffffffu, need, d));
+    if (need <= rows_lo || need > rows) return;  // another class's launch (or nothing to do)
     const uint32_t my_n = live ? min(m.n, st.sym_cap) : 0u;
     s_off[lane] = st.sym_off;
     s_n[lane] = my_n;
-    if (__ballot_sync(0xffffffffu, live) == 0u) return;
 
     for (uint32_t j = 0; j < 32; j++) {
         const uint32_t sj = blockIdx.x * 32u + j;
         const bool lj = __shfl_sync(0xffffffffu, (int)live, j) != 0;
-        const uint32_t rj = __shfl_sync(0xffffffffu, m.range, j);
+        const uint32_t uj = __shfl_sync(0xffffffffu, m.used, j);
         if (!lj) continue;
         const uint32_t* src = cumtab + (size_t)sj * kCumRow;
-        for (uint32_t i = lane; i <= rj; i += 32) tab[i * 32u + j] = (CumT)src[i];
+        for (uint32_t i = lane; i < uj + 3u; i += 32) tab[i * 32u + j] = src[i];
     }
     __syncwarp();
 
-    const PerLaneTable<CumT> T{tab, lane};
+    const PerLaneDense T{tab, lane};
     const uint32_t bits = m.prob_bits;
-    const uint32_t mask = (bits < 32u ? (1u << bits) : 0u) - 1u;
-    const uint32_t lut_shift = bits > 6u ? bits - 6u : 0u;
-    if (live) lut_build(T, lut + lane, 32u, lut_shift, m.range);
+    const uint32_t mask = (1u << bits) - 1u;
+    const uint32_t full = 1u << bits;
+    const uint32_t lut_shift = bits > 7u ? bits - 7u : 0u;
+    if (live) {
+        lut_build(T, lut + lane, 32u, lut_shift, m.used);
+    } else {  // idle lane of a working warp: a one-entry table so that its (discarded) lookups stay in bounds
+        tab[lane] = 0u;
+        tab[32u + lane] = 0u;
+        tab[64u + lane] = full;
+        tab[96u + lane] = full;
+        for (uint32_t j = 0; j < (uint32_t)kLutSize; j++) lut[j * 32u + lane] = (LutT)1;
+    }
+    const uint32_t my_used = live ? m.used : 1u;
     __syncwarp();
     uint32_t n_max = my_n;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
 
-    WordReader rd;
-    uint64_t x = 0;
-    rd.open(in, in_bytes, live ? m.payload_off : 0ull);
+    WordRing rd;
+    rd.open(in, in_bytes, live ? m.payload_off : 0ull, rings + lane * kRingWords);
+    uint64_t x;
     {  // rans64.hpp:107-116: state = first two payload words, low word first
-        const uint32_t lo = rd.peek();
-        rd.advance_if(true);
-        const uint32_t hi = rd.peek();
-        rd.advance_if(true);
+        const uint32_t lo = rd.next;
+        rd.take_if(true);
+        const uint32_t hi = rd.next;
+        rd.take_if(true);
         x = live ? ((uint64_t)lo | ((uint64_t)hi << 32)) : kRansL;
     }
-    const uint32_t full = 1u << bits;
     uint16_t* my_row = stage + lane * kSymStride;
     const uint32_t chunks = (n_max + kChunk - 1) / kChunk;
     for (uint32_t chunk = 0; chunk < chunks; chunk++) {
         const uint32_t base = chunk * kChunk;
         __syncwarp();
+        for (uint32_t k0 = 0; k0 < (uint32_t)kChunk; k0 += kTopUp) {
+            rd.top_up();
 #pragma unroll 4
-        for (uint32_t k = 0; k < (uint32_t)kChunk; k++) {
-            // past the end of a shorter stream the step runs with freq = 2^bits, start = 0: x is unchanged
-            const bool on = base + k < my_n;
-            const uint32_t slot = (uint32_t)x & mask;                                   // rans64.hpp:118-121
-            uint32_t c0, c1;
-            const uint32_t sym = rans_lookup(T, lut + lane, 32u, lut_shift, slot, m.range, c0, c1);
-            const uint32_t f = on ? c1 - c0 : full;
-            const uint32_t back = on ? slot - c0 : slot;
-            x = (uint64_t)f * (x >> bits) + back;                                       // rans64.hpp:126-134
-            const bool refill = x < kRansL;                                             // rans64.hpp:137-141
-            x = refill ? ((x << 32) | rd.peek()) : x;
-            rd.advance_if(refill);
-            my_row[k] = (uint16_t)sym;
+            for (uint32_t k = k0; k < k0 + kTopUp; k++)
+                my_row[k] = (uint16_t)rans_get(x, rd, T, lut + lane, 32u, lut_shift, my_used, bits, mask, full,
+                                               base + k < my_n);
         }
         __syncwarp();
         stage_store_chunk(stage, symbols, s_off, s_n, chunk);
@@ -864,16 +1045,24 @@ __global__ void __launch_bounds__(kStaticWarps * 32) k_rans_encode_static(
     for (int chunk = (int)((n_max + kChunk - 1) / kChunk) - 1; chunk >= 0; chunk--) {
         __syncwarp();
         stage_load_chunk(stage, symbols, s_off[w], s_n[w], (uint32_t)chunk);
-        __syncwarp();
+        stage_wait();
         const uint32_t base = (uint32_t)chunk * kChunk;
-#pragma unroll 8
-        for (int k = kChunk - 1; k >= 0; k--) {
-            const bool on = base + (uint32_t)k < run_n;
-            const uint32_t sym = on ? min((uint32_t)my_row[k], range - 1u) : 0u;
-            uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
-            c0 = on ? c0 : 0u;
-            c1 = on ? c1 : full;
-            x = rans_put(x, c0, c1 - c0, bits, words, widx);
+        for (int k0 = kChunk - kGroup; k0 >= 0; k0 -= kGroup) {
+            uint32_t g_start[kGroup], g_freq[kGroup];
+            double g_inv[kGroup];
+#pragma unroll
+            for (int j = 0; j < kGroup; j++) {
+                const int k = k0 + j;
+                const bool on = base + (uint32_t)k < run_n;
+                const uint32_t sym = on ? min((uint32_t)my_row[k], range - 1u) : 0u;
+                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+                g_start[j] = on ? c0 : 0u;
+                g_freq[j] = on ? c1 - c0 : full;
+                g_inv[j] = recip_low(g_freq[j]);
+            }
+#pragma unroll
+            for (int j = kGroup - 1; j >= 0; j--)
+                x = rans_put<true>(x, g_start[j], g_freq[j], g_inv[j], bits, words, widx);
         }
     }
     if (live) {
@@ -888,18 +1077,37 @@ __global__ void __launch_bounds__(kStaticWarps * 32) k_rans_encode_static(
     }
 }
 
-__global__ void __launch_bounds__(kStaticWarps * 32) k_rans_decode_static(
+constexpr int kStaticDecWarps = 2;
+
+__global__ void __launch_bounds__(kStaticDecWarps * 32) k_rans_decode_static(
     const uint8_t* __restrict__ in, uint32_t slab_bytes, const uint32_t* __restrict__ payload_bytes,
     uint64_t n_total, uint32_t stream_len, const uint32_t* __restrict__ cum_g, uint32_t range,
     uint32_t bits, uint16_t* __restrict__ symbols) {
+    __shared__ uint32_t s_dense[HOH_MAX_RANGE + 8];
+    __shared__ uint32_t s_used;
+    __shared__ __align__(16) uint16_t s_stage[kStaticDecWarps][32 * kSymStride];
+    __shared__ __align__(16) uint32_t s_rings[kStaticDecWarps][32 * kRingWords];
+    __shared__ uint64_t s_off[kStaticDecWarps][32];
+    __shared__ uint32_t s_n[kStaticDecWarps][32];
     __shared__ uint32_t s_cum[HOH_MAX_RANGE + 8];
-    __shared__ __align__(16) uint16_t s_stage[kStaticWarps][32 * kSymStride];
-    __shared__ uint64_t s_off[kStaticWarps][32];
-    __shared__ uint32_t s_n[kStaticWarps][32];
+    __shared__ uint16_t s_lut[kLutSize];
     for (uint32_t i = threadIdx.x; i <= range; i += blockDim.x) s_cum[i] = cum_g[i];
+    __syncthreads();
+    const uint32_t lut_shift = bits > 7u ? bits - 7u : 0u;
+    const SharedDense T{s_dense};
+    if (threadIdx.x == 0) {  // dense table, physical layout as in k_parse_streams
+        uint32_t d = 0;
+        s_dense[0] = 0u;
+        for (uint32_t i = 0; i < range; i++)
+            if (s_cum[i + 1] != s_cum[i]) s_dense[1u + d++] = s_cum[i] | (i << 20);
+        s_dense[d + 1] = s_cum[range];
+        s_dense[d + 2] = s_cum[range];
+        s_used = d;
+        if (d) lut_build(T, s_lut, 1u, lut_shift, d);
+    }
     const uint32_t w = threadIdx.x >> 5, lane = lane_id();
     const uint64_t n_streams = (n_total + stream_len - 1) / stream_len;
-    const uint64_t s = ((uint64_t)blockIdx.x * kStaticWarps + w) * 32u + lane;
+    const uint64_t s = ((uint64_t)blockIdx.x * kStaticDecWarps + w) * 32u + lane;
     const bool exists = s < n_streams;
     const uint64_t first = s * stream_len;
     const uint32_t pb = exists ? payload_bytes[s] : 0u;
@@ -908,47 +1116,35 @@ __global__ void __launch_bounds__(kStaticWarps * 32) k_rans_decode_static(
     s_off[w][lane] = live ? first : 0ull;
     s_n[w][lane] = my_n;
     __syncthreads();
-    if (__ballot_sync(0xffffffffu, live) == 0u) return;
-    const SharedTable<uint32_t> T{s_cum};
+    const uint32_t used = s_used;
+    if (used == 0u || __ballot_sync(0xffffffffu, live) == 0u) return;
     const uint32_t mask = (1u << bits) - 1u;
-    const uint32_t lut_shift = bits > 6u ? bits - 6u : 0u;
-    __shared__ uint16_t s_lut[kLutSize];
-    if (threadIdx.x == 0) lut_build(T, s_lut, 1u, lut_shift, range);
-    __syncthreads();
+    const uint32_t full = 1u << bits;
     uint32_t n_max = my_n;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
-    WordReader rd;
-    uint64_t x = 0;
+    WordRing rd;
+    const uint64_t total_bytes = n_streams * (uint64_t)slab_bytes;
+    rd.open(in, total_bytes, live ? (s + 1) * (uint64_t)slab_bytes - pb : 0ull, s_rings[w] + lane * kRingWords);
+    uint64_t x;
     {
-        const uint64_t total_bytes = n_streams * (uint64_t)slab_bytes;
-        rd.open(in, total_bytes, live ? (s + 1) * (uint64_t)slab_bytes - pb : 0ull);
-        const uint32_t lo = rd.peek();
-        rd.advance_if(true);
-        const uint32_t hi = rd.peek();
-        rd.advance_if(true);
+        const uint32_t lo = rd.next;
+        rd.take_if(true);
+        const uint32_t hi = rd.next;
+        rd.take_if(true);
         x = live ? ((uint64_t)lo | ((uint64_t)hi << 32)) : kRansL;
     }
-    const uint32_t full = 1u << bits;
     uint16_t* stage = s_stage[w];
     uint16_t* my_row = stage + lane * kSymStride;
     const uint32_t chunks = (n_max + kChunk - 1) / kChunk;
     for (uint32_t chunk = 0; chunk < chunks; chunk++) {
         const uint32_t base = chunk * kChunk;
         __syncwarp();
+        for (uint32_t k0 = 0; k0 < (uint32_t)kChunk; k0 += kTopUp) {
+            rd.top_up();
 #pragma unroll 4
-        for (uint32_t k = 0; k < (uint32_t)kChunk; k++) {
-            const bool on = base + k < my_n;
-            const uint32_t slot = (uint32_t)x & mask;
-            uint32_t c0, c1;
-            const uint32_t sym = rans_lookup(T, s_lut, 1u, lut_shift, slot, range, c0, c1);
-            const uint32_t f = on ? c1 - c0 : full;
-            const uint32_t back = on ? slot - c0 : slot;
-            x = (uint64_t)f * (x >> bits) + back;
-            const bool refill = x < kRansL;
-            x = refill ? ((x << 32) | rd.peek()) : x;
-            rd.advance_if(refill);
-            my_row[k] = (uint16_t)sym;
+            for (uint32_t k = k0; k < k0 + kTopUp; k++)
+                my_row[k] = (uint16_t)rans_get(x, rd, T, s_lut, 1u, lut_shift, used, bits, mask, full, base + k < my_n);
         }
         __syncwarp();
         stage_store_chunk(stage, symbols, s_off[w], s_n[w], chunk);
@@ -1403,7 +1599,7 @@ __device__ __forceinline__ void tile_rect(const TileGeom& g, uint32_t tile, uint
     th = min(g.tile_h, g.height - y0);
 }
 
-__global__ void __launch_bounds__(256) k_tile_residuals_s0(const uint8_t* __restrict__ rgb, TileGeom g,
+__global__ void __launch_bounds__(256) k_tile_residuals_s0_generic(const uint8_t* __restrict__ rgb, TileGeom g,
                                                            uint16_t* __restrict__ resid,
                                                            uint32_t* __restrict__ freqs) {
     __shared__ uint32_t s_h[3][kFreqRow];
@@ -1453,6 +1649,91 @@ __global__ void __launch_bounds__(256) k_tile_residuals_s0(const uint8_t* __rest
         atomicAdd(&s_h[0][rg_], 1u);
         atomicAdd(&s_h[1][rr_], 1u);
         atomicAdd(&s_h[2][rb_], 1u);
+    }
+    __syncthreads();
+    for (int ch = 0; ch < 3; ch++) {
+        uint32_t* dst = freqs + (t * 3u + ch) * kFreqRow;
+        for (int i = threadIdx.x; i < kFreqRow; i += blockDim.x) dst[i] = s_h[ch][i];
+    }
+}
+
+// Same stage for the common geometry (image width and tile width multiples of 4): every thread takes
+// four horizontally adjacent pixels = 12 bytes = three aligned words per row (plus the word holding the
+// left neighbour), so global traffic is 32-bit loads and 8-byte stores and the row/column bookkeeping
+// is incremental (no per-pixel division).
+struct Px3 {
+    int g, r, b;  // G, R-G+256, B-G+256 (channel.hpp:75-77)
+};
+__device__ __forceinline__ Px3 planes_of(uint32_t p) {  // p = 0x00BBGGRR
+    const int g = (p >> 8) & 255;
+    Px3 o;
+    o.g = g;
+    o.r = (int)(p & 255u) - g + 256;
+    o.b = (int)((p >> 16) & 255u) - g + 256;
+    return o;
+}
+
+__global__ void __launch_bounds__(256) k_tile_residuals_s0(const uint8_t* __restrict__ rgb, TileGeom g,
+                                                           uint16_t* __restrict__ resid,
+                                                           uint32_t* __restrict__ freqs) {
+    __shared__ uint32_t s_h[3][kFreqRow];
+    for (int i = threadIdx.x; i < 3 * kFreqRow; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t t = blockIdx.x;  // global tile index = image * tiles_per_image + tile
+    const uint64_t image = t / g.tiles_per_image;
+    const uint32_t tile = (uint32_t)(t % g.tiles_per_image);
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, tile, x0, y0, tw, th);
+    const uint8_t* img = rgb + image * (uint64_t)g.width * g.height * 3u;
+    uint16_t* out_g = resid + (t * 3u + 0u) * g.plane_stride;
+    uint16_t* out_rg = resid + (t * 3u + 1u) * g.plane_stride;
+    uint16_t* out_bg = resid + (t * 3u + 2u) * g.plane_stride;
+    const uint32_t quads = tw / 4u;  // tw % 4 == 0 on this path
+    const uint32_t dy = 256u / quads, dq = 256u % quads;
+    uint32_t y = threadIdx.x / quads, q = threadIdx.x % quads;
+    const Px3 mid{128, 256, 256};
+    const uint32_t row_words = g.width * 3u / 4u;
+    for (; y < th; y += dy, q += dq) {
+        if (q >= quads) {
+            q -= quads;
+            y++;
+            if (y >= th) break;
+        }
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(img + ((uint64_t)(y0 + y) * g.width + x0 + 4u * q) * 3u);
+        const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+        Px3 cur[5], top[5];
+        cur[0] = q ? planes_of(row[-1] >> 8) : mid;  // column 0: L = c/2
+        cur[1] = planes_of(w0 & 0xffffffu);
+        cur[2] = planes_of((w0 >> 24) | ((w1 & 0xffffu) << 8));
+        cur[3] = planes_of((w1 >> 16) | ((w2 & 0xffu) << 16));
+        cur[4] = planes_of(w2 >> 8);
+        if (y) {
+            const uint32_t* up = row - row_words;
+            const uint32_t u0 = up[0], u1 = up[1], u2 = up[2];
+            top[0] = q ? planes_of(up[-1] >> 8) : mid;  // column 0: TL = c/2
+            top[1] = planes_of(u0 & 0xffffffu);
+            top[2] = planes_of((u0 >> 24) | ((u1 & 0xffffu) << 8));
+            top[3] = planes_of((u1 >> 16) | ((u2 & 0xffu) << 16));
+            top[4] = planes_of(u2 >> 8);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; i++) top[i] = mid;  // row 0: T = TL = c/2
+        }
+        uint32_t rg_[4], rr_[4], rb_[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const Px3 v = cur[i + 1], L = cur[i], T = top[i + 1], TL = top[i];
+            rg_[i] = (uint32_t)((v.g - p_med_grad(T.g, L.g, TL.g) + 128 + 256) & 255);
+            rr_[i] = (uint32_t)((v.r - p_med_grad(T.r, L.r, TL.r) + 256 + 512) & 511);
+            rb_[i] = (uint32_t)((v.b - p_med_grad(T.b, L.b, TL.b) + 256 + 512) & 511);
+            atomicAdd(&s_h[0][rg_[i]], 1u);
+            atomicAdd(&s_h[1][rr_[i]], 1u);
+            atomicAdd(&s_h[2][rb_[i]], 1u);
+        }
+        const uint32_t at = y * tw + 4u * q;
+        *reinterpret_cast<uint2*>(out_g + at) = make_uint2(rg_[0] | (rg_[1] << 16), rg_[2] | (rg_[3] << 16));
+        *reinterpret_cast<uint2*>(out_rg + at) = make_uint2(rr_[0] | (rr_[1] << 16), rr_[2] | (rr_[3] << 16));
+        *reinterpret_cast<uint2*>(out_bg + at) = make_uint2(rb_[0] | (rb_[1] << 16), rb_[2] | (rb_[3] << 16));
     }
     __syncthreads();
     for (int ch = 0; ch < 3; ch++) {
@@ -1511,13 +1792,102 @@ __global__ void k_make_tile_dec_streams(TileGeom g, uint64_t n_tiles, const uint
 
 // Tile back end, mode 0: wavefront inverse of the MED predictor on the three planes of a tile, the
 // inverse colour transform and the scatter into the interleaved image (dhoh.cpp:72-84, 268-276).
-// One warp per tile; lane = row inside a 32-row band.
-__global__ void __launch_bounds__(128) k_tile_unpredict_s0(const uint16_t* __restrict__ resid, TileGeom g,
-                                                           uint64_t n_tiles, uint8_t* __restrict__ rgb) {
-    extern __shared__ uint32_t s_carry[];  // 4 warps * tile_w packed (g | rg << 8 | bg << 17)
+// One warp per tile; lane = row inside a 32-row band; lane r works on column t - r at step t and gets
+// its top neighbour from lane r-1 by shuffle (anti-diagonal wavefront).  Residuals and pixels move
+// through two shared-memory rings (32 rows x 64 columns, row stride 66 words so that both the
+// row-wise transfers and the diagonal accesses are bank-conflict free): every 32 steps the warp loads
+// the next 32-column block of all 32 rows with coalesced reads and writes back the block that was
+// completed two boundaries ago with coalesced stores.
+constexpr int kRingStride = 66;                      // words per ring row (64 columns + 2 pad)
+constexpr int kUnpWarps = 4;
+constexpr uint32_t kMidPacked = 128u | (256u << 8) | (256u << 17);  // border value c/2 of G, R-G, B-G
+
+template <bool ALIGNED>
+__device__ __forceinline__ void unp_load_block(uint32_t* ring, const uint16_t* __restrict__ in_g,
+                                               const uint16_t* __restrict__ in_rg,
+                                               const uint16_t* __restrict__ in_bg, uint32_t y_base, uint32_t th,
+                                               uint32_t tw, uint32_t block) {
+    const uint32_t lane = lane_id();
+    const uint32_t half = (block & 1u) * 32u;
+    if (ALIGNED) {  // tw % 4 == 0: 4 columns per lane, 4 rows per instruction
+        const uint32_t c = 32u * block + 4u * (lane & 7u);
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) {
+            const uint32_t r = 4u * i + (lane >> 3);
+            const uint32_t y = y_base + r;
+            if (y < th && c < tw) {
+                const uint32_t at = y * tw + c;
+                const uint2 g = *reinterpret_cast<const uint2*>(in_g + at);
+                const uint2 a = *reinterpret_cast<const uint2*>(in_rg + at);
+                const uint2 b = *reinterpret_cast<const uint2*>(in_bg + at);
+                uint32_t* dst = ring + r * kRingStride + half + 4u * (lane & 7u);
+                dst[0] = (g.x & 0xffffu) | ((a.x & 0xffffu) << 8) | ((b.x & 0xffffu) << 17);
+                dst[1] = (g.x >> 16) | ((a.x >> 16) << 8) | ((b.x >> 16) << 17);
+                dst[2] = (g.y & 0xffffu) | ((a.y & 0xffffu) << 8) | ((b.y & 0xffffu) << 17);
+                dst[3] = (g.y >> 16) | ((a.y >> 16) << 8) | ((b.y >> 16) << 17);
+            }
+        }
+    } else {
+        const uint32_t c = 32u * block + lane;
+        for (uint32_t r = 0; r < 32; r++) {
+            const uint32_t y = y_base + r;
+            if (y < th && c < tw) {
+                const uint32_t at = y * tw + c;
+                ring[r * kRingStride + half + lane] =
+                    (uint32_t)in_g[at] | ((uint32_t)in_rg[at] << 8) | ((uint32_t)in_bg[at] << 17);
+            }
+        }
+    }
+}
+
+// ring values are 0x00BBGGRR
+template <bool ALIGNED>
+__device__ __forceinline__ void unp_store_block(const uint32_t* ring, uint8_t* __restrict__ img, uint32_t width,
+                                                uint32_t x0, uint32_t y0, uint32_t y_base, uint32_t th, uint32_t tw,
+                                                uint32_t block) {
+    const uint32_t lane = lane_id();
+    const uint32_t half = (block & 1u) * 32u;
+    if (ALIGNED) {  // width % 4 == 0 and tile_w % 4 == 0: 4 pixels = 3 aligned words per lane
+        const uint32_t c = 32u * block + 4u * (lane & 7u);
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) {
+            const uint32_t r = 4u * i + (lane >> 3);
+            const uint32_t y = y_base + r;
+            if (y < th && c < tw) {
+                const uint32_t* src = ring + r * kRingStride + half + 4u * (lane & 7u);
+                const uint32_t A = src[0], B = src[1], C = src[2], D = src[3];
+                uint32_t* dst = reinterpret_cast<uint32_t*>(img + ((uint64_t)(y0 + y) * width + x0 + c) * 3u);
+                dst[0] = A | (B << 24);
+                dst[1] = (B >> 8) | (C << 16);
+                dst[2] = (C >> 16) | (D << 8);
+            }
+        }
+    } else {
+        const uint32_t c = 32u * block + lane;
+        for (uint32_t r = 0; r < 32; r++) {
+            const uint32_t y = y_base + r;
+            if (y < th && c < tw) {
+                const uint32_t v = ring[r * kRingStride + half + lane];
+                uint8_t* dst = img + ((uint64_t)(y0 + y) * width + x0 + c) * 3u;
+                dst[0] = (uint8_t)v;
+                dst[1] = (uint8_t)(v >> 8);
+                dst[2] = (uint8_t)(v >> 16);
+            }
+        }
+    }
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(kUnpWarps * 32) k_tile_unpredict_s0(const uint16_t* __restrict__ resid, TileGeom g,
+                                                                      uint64_t n_tiles, uint8_t* __restrict__ rgb) {
+    extern __shared__ uint32_t s_unp[];  // per warp: in ring, out ring, carry row (tile_w words)
     const uint32_t wid = threadIdx.x >> 5, lane = lane_id();
-    const uint64_t t = (uint64_t)blockIdx.x * 4u + wid;
+    const uint64_t t = (uint64_t)blockIdx.x * kUnpWarps + wid;
     if (t >= n_tiles) return;
+    const uint32_t per_warp = 2u * 32u * kRingStride + g.tile_w;
+    uint32_t* ring_in = s_unp + (size_t)wid * per_warp;
+    uint32_t* ring_out = ring_in + 32 * kRingStride;
+    uint32_t* carry = ring_out + 32 * kRingStride;
     const uint64_t image = t / g.tiles_per_image;
     uint32_t x0, y0, tw, th;
     tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
@@ -1525,38 +1895,49 @@ __global__ void __launch_bounds__(128) k_tile_unpredict_s0(const uint16_t* __res
     const uint16_t* in_g = resid + (t * 3u + 0u) * g.plane_stride;
     const uint16_t* in_rg = resid + (t * 3u + 1u) * g.plane_stride;
     const uint16_t* in_bg = resid + (t * 3u + 2u) * g.plane_stride;
-    uint32_t* carry = s_carry + (size_t)wid * g.tile_w;
+    const uint32_t n_blocks = (tw + 31u) / 32u;
+    const uint32_t* my_in = ring_in + lane * kRingStride;
+    uint32_t* my_out = ring_out + lane * kRingStride;
+
     for (uint32_t band = 0; band * 32u < th; band++) {
-        const uint32_t y = band * 32u + lane;
+        const uint32_t y_base = band * 32u;
+        const uint32_t y = y_base + lane;
         const bool row_ok = y < th;
         int Lg = 128, Lr = 256, Lb = 256, TLg = 128, TLr = 256, TLb = 256;
-        uint32_t mine = 128u | (256u << 8) | (256u << 17);
-        for (uint32_t step = 0; step < tw + 31u; step++) {
-            const int x = (int)step - (int)lane;
-            uint32_t top = __shfl_up_sync(0xffffffffu, mine, 1);
-            if (lane == 0) top = (band && x >= 0 && x < (int)tw) ? carry[x] : (128u | (256u << 8) | (256u << 17));
-            if (y == 0) top = 128u | (256u << 8) | (256u << 17);
-            if (row_ok && x >= 0 && x < (int)tw) {
-                const int Tg = top & 255u, Tr = (top >> 8) & 511u, Tb = (top >> 17) & 511u;
-                if (x == 0) {
-                    Lg = 128; Lr = 256; Lb = 256;
-                    TLg = 128; TLr = 256; TLb = 256;
+        uint32_t mine = kMidPacked;
+        for (uint32_t blk = 0; blk < n_blocks + 2u; blk++) {
+            __syncwarp();
+            if (blk >= 2u) unp_store_block<ALIGNED>(ring_out, img, g.width, x0, y0, y_base, th, tw, blk - 2u);
+            if (blk < n_blocks) unp_load_block<ALIGNED>(ring_in, in_g, in_rg, in_bg, y_base, th, tw, blk);
+            __syncwarp();
+#pragma unroll 4
+            for (uint32_t k = 0; k < 32u; k++) {
+                const uint32_t step = blk * 32u + k;
+                const int x = (int)step - (int)lane;
+                uint32_t top = __shfl_up_sync(0xffffffffu, mine, 1);
+                const bool in_row = x >= 0 && x < (int)tw;
+                if (lane == 0) top = (band != 0u && in_row) ? carry[x] : kMidPacked;
+                if (y == 0u) top = kMidPacked;
+                if (row_ok && in_row) {
+                    const uint32_t v = my_in[x & 63];
+                    const int Tg = top & 255u, Tr = (top >> 8) & 511u, Tb = (top >> 17) & 511u;
+                    if (x == 0) {  // column 0: L = TL = c/2
+                        Lg = 128; Lr = 256; Lb = 256;
+                        TLg = 128; TLr = 256; TLb = 256;
+                    }
+                    if (y == 0u) {  // row 0: T = TL = c/2
+                        TLg = 128; TLr = 256; TLb = 256;
+                    }
+                    const int vg = ((int)(v & 255u) + p_med_grad(Tg, Lg, TLg) - 128) & 255;
+                    const int vr = ((int)((v >> 8) & 511u) + p_med_grad(Tr, Lr, TLr) - 256) & 511;
+                    const int vb = ((int)((v >> 17) & 511u) + p_med_grad(Tb, Lb, TLb) - 256) & 511;
+                    my_out[x & 63] = (uint32_t)((vr + vg - 256) & 255) | ((uint32_t)vg << 8) |
+                                     ((uint32_t)((vb + vg - 256) & 255) << 16);
+                    mine = (uint32_t)vg | ((uint32_t)vr << 8) | ((uint32_t)vb << 17);
+                    Lg = vg; Lr = vr; Lb = vb;
+                    TLg = Tg; TLr = Tr; TLb = Tb;
+                    if (lane == 31u) carry[x] = mine;
                 }
-                if (y == 0) {
-                    TLg = 128; TLr = 256; TLb = 256;
-                }
-                const uint32_t i = y * tw + (uint32_t)x;
-                const int vg = ((int)in_g[i] + p_med_grad(Tg, Lg, TLg) - 128) & 255;
-                const int vr = ((int)in_rg[i] + p_med_grad(Tr, Lr, TLr) - 256) & 511;
-                const int vb = ((int)in_bg[i] + p_med_grad(Tb, Lb, TLb) - 256) & 511;
-                uint8_t* p = img + ((uint64_t)(y0 + y) * g.width + x0 + (uint32_t)x) * 3u;
-                p[0] = (uint8_t)((vr + vg - 256) & 255);
-                p[1] = (uint8_t)vg;
-                p[2] = (uint8_t)((vb + vg - 256) & 255);
-                mine = (uint32_t)vg | ((uint32_t)vr << 8) | ((uint32_t)vb << 17);
-                Lg = vg; Lr = vr; Lb = vb;
-                TLg = Tg; TLr = Tr; TLb = Tb;
-                if (lane == 31) carry[x] = mine;
             }
         }
         __syncwarp();

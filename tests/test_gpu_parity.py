@@ -122,7 +122,11 @@ def test_decode_entropy_vs_oracle_and_roundtrip():
         # more than maxbits bits, and then the decoded symbols are not the input
         want, _, wst = ol.orc_decode_entropy(enc, 0, flags=7, cap=n)
         assert wst == 0
-        lossless += int(np.array_equal(want, s))
+        ok = np.array_equal(want, s)
+        lossless += int(ok)
+        if not ok:
+            want = None  # garbage table: the state collapses and the decoder runs off the payload, so what
+                         # it reads (oracle and reference alike) is whatever follows in memory
         blobs.append(np.zeros(lead, np.uint8))
         blobs.append(enc)
         offs.append(pos + lead)
@@ -133,8 +137,12 @@ def test_decode_entropy_vs_oracle_and_roundtrip():
     blob = np.concatenate(blobs)
     got = g.decode_entropy_batch(blob, offs, caps, flags=7)
     for i, ((sym, end, st), (s, e)) in enumerate(zip(got, exp)):
+        if s is None:  # garbage table (lossy mode 1): decoded without faulting, or refused as a bad table
+            assert st in (0, 3), i
+            continue
         assert st == 0 and end == e and np.array_equal(sym, s), i
     # single-call shim, reference semantics: byte_pointer stops at the payload (D8), 4-bit prob_bits (D9)
+    checked_ref = 0
     for it in range(40):
         rangev, pb, n = int(rng.choice([14, 256, 512])), int(rng.integers(9, 16)), int(rng.choice([5, 1000, 20000]))
         s = _symbols(rng, 1 + it % 3, n, rangev)
@@ -143,8 +151,12 @@ def test_decode_entropy_vs_oracle_and_roundtrip():
         if st:
             continue
         a, bpa, sta = ol.orc_decode_entropy(enc, 0, flags=0, cap=n)
+        if not np.array_equal(a, s):
+            continue  # lossy table (D6): what the decoder reads past the payload is undefined
         b, bpb, stb = g.decode_entropy(enc, 0, flags=0, cap=n)
         assert sta == stb == 0 and bpa == bpb and np.array_equal(a, b)
+        checked_ref += 1
+    assert checked_ref > 15
 
 
 def test_decode_entropy_golden_and_empty():
