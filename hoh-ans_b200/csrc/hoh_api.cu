@@ -209,7 +209,7 @@ int decode_common(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n, const
     for (int c = 0; c < 4; c++) {
         const uint32_t rows = classes[c + 1];
         const size_t fixed = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kRingWords * sizeof(uint32_t) +
-                             32 * kSymStride * sizeof(uint16_t);
+                             32 * kDecStride * sizeof(uint16_t);
         if (rows <= 256) {
             k_rans_decode<uint8_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 1, ctx->stream>>>(
                 d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, classes[c], rows);

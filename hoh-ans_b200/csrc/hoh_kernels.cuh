@@ -26,6 +26,10 @@ static_assert(true, "");
 constexpr int kGroup = 8;       // encoder: symbols whose lookups + reciprocals are hoisted ahead of the serial part
 constexpr int kSymStride = 66;  // u16 per staged row (64 + 2 pad -> 33 words: conflict-free transpose)
 constexpr uint64_t kRansL = 1ull << 31;  // rans64.hpp:59
+constexpr int kDecChunk = 32;   // decoder: symbols per lane between two coalesced flushes
+constexpr int kDecStride = 34;  // u16 per staged row (32 + 2 pad -> 17 words: conflict-free transpose)
+constexpr uint32_t kSymBits = 9;  // dense decode table entry = cum << 9 | symbol (symbols < 512)
+constexpr uint32_t kSymMask = (1u << kSymBits) - 1u;
 
 // Per-stream scratch the encode pipeline threads through its kernels.
 struct EncMeta {
@@ -350,18 +354,19 @@ __device__ __forceinline__ void stage_load_chunk(uint16_t* stage, const uint16_t
     }
 }
 
-// Inverse: rows of `stage` -> global symbol arrays (decode side).
+// Decode side: rows of `stage` (32 symbols per stream, row stride kDecStride) -> global symbol arrays.
+// Eight lanes cover one row with 8-byte stores, four rows per instruction.
 __device__ __forceinline__ void stage_store_chunk(const uint16_t* stage, uint16_t* __restrict__ symbols,
                                                   const uint64_t* s_off, const uint32_t* s_n, uint32_t chunk) {
-    const uint32_t lane = lane_id(), half = lane >> 4, q = lane & 15u;
+    const uint32_t lane = lane_id(), sub = lane >> 3, q = lane & 7u;
     const uint32_t* stage32 = reinterpret_cast<const uint32_t*>(stage);
-#pragma unroll 4
-    for (uint32_t jj = 0; jj < 16; jj++) {
-        const uint32_t r = 2u * jj + half;
-        const uint32_t first = chunk * kChunk + 4u * q;
+#pragma unroll
+    for (uint32_t jj = 0; jj < 8; jj++) {
+        const uint32_t r = 4u * jj + sub;
+        const uint32_t first = chunk * kDecChunk + 4u * q;
         const uint32_t n = s_n[r];
-        const uint32_t a = stage32[r * (kSymStride / 2) + 2u * q];
-        const uint32_t b = stage32[r * (kSymStride / 2) + 2u * q + 1u];
+        const uint32_t a = stage32[r * (kDecStride / 2) + 2u * q];
+        const uint32_t b = stage32[r * (kDecStride / 2) + 2u * q + 1u];
         if (first + 3u < n) {
             *reinterpret_cast<uint2*>(symbols + s_off[r] + first) = make_uint2(a, b);
         } else if (first < n) {
@@ -373,10 +378,6 @@ __device__ __forceinline__ void stage_store_chunk(const uint16_t* stage, uint16_
     }
 }
 
-// -------------------------------------------------------------------------------------------------
-// rANS encode, per-stream tables — entropy_encoding.hpp:206-238.  One warp per CTA, one stream per
-// lane.  Dynamic shared memory: (rows * 32) CumT + 32 * kSymStride u16.
-// -------------------------------------------------------------------------------------------------
 // One warp per CTA, one stream per lane.  Each lane's table holds only the window of symbols that occur
 // in its stream (cum[win_lo .. win_lo + win_rows)); `rows_lo < need <= rows` selects the warps of this
 // launch's table-size class (need = widest window among the warp's streams), one launch per class.
@@ -683,10 +684,11 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
         __syncwarp();
         if (status == HOH_S_OK) {
             warp_cumsum(f, cum, h.range);  // stattools.hpp:6-11
-            // Dense decode table: one packed entry (cum | symbol << 20) per symbol that has a non-zero
-            // frequency, in symbol order.  Dropping the empty symbols changes nothing for a valid table
+            // Dense decode table: one packed entry (cum << 9 | symbol) per symbol that has a non-zero
+            // frequency, in symbol order (so the packed words are strictly increasing).  Dropping the empty symbols changes nothing for a valid table
             // (a slot never falls on one) and keeps the lookup's neighbourhood search short.  Physical
-            // rows: [0] = leading sentinel (cum 0), [1 .. used] = entries, [used+1], [used+2] = the total.
+            // rows: [0] = leading sentinel (0), [1 .. used] = entries, [used+1] = the total, [used+2] = all ones
+            // (a row no slot can reach: the lookup needs no bounds tests).
             uint32_t* ct = cumtab + (size_t)s * kCumRow;
             {
                 const uint32_t per = (h.range + 31u) / 32u;
@@ -696,15 +698,15 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
                 const uint32_t incl = warp_incl_scan(cnt);
                 uint32_t d = incl - cnt;
                 for (uint32_t i = lo; i < hi; i++)
-                    if (f[i] != 0u) ct[1u + d++] = cum[i] | (i << 20);
+                    if (f[i] != 0u) ct[1u + d++] = (cum[i] << kSymBits) | i;
                 m.used = __shfl_sync(0xffffffffu, incl, 31);
                 if (lane == 0) {
                     ct[0] = 0u;
-                    ct[m.used + 1u] = cum[h.range];
-                    ct[m.used + 2u] = cum[h.range];
+                    ct[m.used + 1u] = cum[h.range] << kSymBits;
+                    ct[m.used + 2u] = 0xffffffffu;
                 }
             }
-            if (m.used == 0u || cum[h.range] >= (1u << 20) || h.prob_bits > HOH_MAX_PROB_BITS || h.prob_bits == 0u)
+            if (m.used == 0u || cum[h.range] >= (1u << 22) || h.prob_bits > HOH_MAX_PROB_BITS || h.prob_bits == 0u)
                 status = HOH_S_BAD_TABLE;
             uint64_t at = after_table;
             const uint32_t payload = hohfmt::get_varint(bytes, &at);  // entropy_decoding.hpp:256
@@ -829,7 +831,6 @@ struct WordRing {
 // answer is selected without a branch; only a slot further away takes the scan loops.  The result is
 // the largest row with cum <= slot, i.e. the symbol the reference's 2^prob_bits-entry table holds.
 constexpr int kLutSize = 128;
-constexpr uint32_t kCumMask = (1u << 20) - 1u;
 
 // Dense table accessors: PerLane = 32 independent tables interleaved [row][lane]; Shared = one table.
 struct PerLaneDense {
@@ -849,52 +850,52 @@ __device__ __forceinline__ void lut_build(const Table& T, LutT* lut, uint32_t lu
     const uint32_t half = lut_shift ? (1u << (lut_shift - 1u)) : 0u;
     for (uint32_t j = 0; j < (uint32_t)kLutSize; j++) {
         const uint32_t target = (j << lut_shift) + half;
-        while (p < used && (T.at(p + 1u) & kCumMask) <= target) p++;
+        while (p < used && (T.at(p + 1u) >> kSymBits) <= target) p++;
         lut[j * lut_stride] = (LutT)p;
     }
 }
 
 // Returns the symbol; c0 / c1 = cumulative count of the symbol / of the next used symbol.
+// With key = (slot + 1) << 9, "cum(row) <= slot" is simply "row < key" on the packed words.
 template <typename Table, typename LutT>
 __device__ __forceinline__ uint32_t rans_lookup(const Table& T, const LutT* lut, uint32_t lut_stride,
-                                                uint32_t lut_shift, uint32_t slot, uint32_t used, uint32_t& c0,
-                                                uint32_t& c1) {
+                                                uint32_t lut_shift, uint32_t slot, uint32_t& c0, uint32_t& c1) {
     uint32_t p = lut[(slot >> lut_shift) * lut_stride];
+    const uint32_t key = (slot + 1u) << kSymBits;
     const uint32_t em = T.at(p - 1u), e0 = T.at(p), e1 = T.at(p + 1u), e2 = T.at(p + 2u);
-    const bool down = slot < (e0 & kCumMask);
-    const bool up = slot >= (e1 & kCumMask) && p < used;
+    const bool down = e0 >= key;  // the row holding the bucket's middle starts after the slot
+    const bool up = e1 < key;     // ... or ends before it
     uint32_t e = down ? em : (up ? e1 : e0);
     uint32_t hi = down ? e0 : (up ? e2 : e1);
-    p += up ? 1u : 0u;
-    p -= down ? 1u : 0u;
-    while (slot < (e & kCumMask)) {  // further down (rare)
-        p--;
-        hi = e;
-        e = T.at(p);
+    if (e >= key || hi < key) {  // more than one row away (several symbols inside 1/128th of the range)
+        p = down ? p - 1u : (up ? p + 1u : p);
+        while (e >= key) {
+            p--;
+            hi = e;
+            e = T.at(p);
+        }
+        while (hi < key) {
+            p++;
+            e = hi;
+            hi = T.at(p + 1u);
+        }
     }
-    while (slot >= (hi & kCumMask) && p < used) {  // further up (rare)
-        p++;
-        e = hi;
-        hi = T.at(p + 1u);
-    }
-    c0 = e & kCumMask;
-    c1 = hi & kCumMask;
-    return e >> 20;
+    c0 = e >> kSymBits;
+    c1 = hi >> kSymBits;
+    return e & kSymMask;
 }
 
-// One decode step (rans64.hpp:118-142).  `on` false = padding step past the end of a shorter stream:
-// freq = 2^bits, start = 0 leaves x unchanged and never refills.
+// One decode step (rans64.hpp:118-142).  There is no "past the end of this stream" case: a lane whose
+// stream is shorter than its neighbours' keeps decoding (its table lookups and word reads stay in
+// bounds whatever the state is) and the surplus symbols are simply not stored.
 template <typename Table, typename LutT>
 __device__ __forceinline__ uint32_t rans_get(uint64_t& x, WordRing& rd, const Table& T, const LutT* lut,
-                                             uint32_t lut_stride, uint32_t lut_shift, uint32_t used, uint32_t bits,
-                                             uint32_t mask, uint32_t full, bool on) {
+                                             uint32_t lut_stride, uint32_t lut_shift, uint32_t bits, uint32_t mask) {
     const uint32_t slot = (uint32_t)x & mask;  // rans64.hpp:118-121
     uint32_t c0, c1;
-    const uint32_t sym = rans_lookup(T, lut, lut_stride, lut_shift, slot, used, c0, c1);
-    const uint32_t f = on ? c1 - c0 : full;
-    const uint32_t back = on ? slot - c0 : slot;
-    x = (uint64_t)f * (x >> bits) + back;      // rans64.hpp:126-134
-    const bool refill = x < kRansL;            // rans64.hpp:137-141
+    const uint32_t sym = rans_lookup(T, lut, lut_stride, lut_shift, slot, c0, c1);
+    x = (uint64_t)(c1 - c0) * (x >> bits) + (slot - c0);  // rans64.hpp:126-134
+    const bool refill = x < kRansL;                       // rans64.hpp:137-141
     x = refill ? ((x << 32) | rd.next) : x;
     rd.take_if(refill);
     return sym;
@@ -904,7 +905,7 @@ __device__ __forceinline__ uint32_t rans_get(uint64_t& x, WordRing& rd, const Ta
 // table-size class (need = rows of the largest dense table among the warp's streams): the host
 // launches one grid per class with the matching shared-memory size and every warp runs in exactly one.
 // LutT = u8 when rows <= 256.  Dynamic shared memory: rows * 32 u32 (tables) + 32 * kRingWords u32 (word
-// rings) + 128 * 32 LutT + 32 * kSymStride u16 (symbol staging).
+// rings) + 32 * kDecStride u16 (symbol staging) + 128 * 32 LutT.
 template <typename LutT>
 __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __restrict__ streams,
                                                     uint32_t n_streams, const uint8_t* __restrict__ in,
@@ -916,7 +917,7 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* rings = tab + (size_t)rows * 32u;
     uint16_t* stage = reinterpret_cast<uint16_t*>(rings + 32 * kRingWords);
-    LutT* lut = reinterpret_cast<LutT*>(stage + 32 * kSymStride);
+    LutT* lut = reinterpret_cast<LutT*>(stage + 32 * kDecStride);
     __shared__ uint64_t s_off[32];
     __shared__ uint32_t s_n[32];
 
@@ -967,11 +968,10 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
     } else {  // idle lane of a working warp: a one-entry table so that its (discarded) lookups stay in bounds
         tab[lane] = 0u;
         tab[32u + lane] = 0u;
-        tab[64u + lane] = full;
-        tab[96u + lane] = full;
+        tab[64u + lane] = full << kSymBits;
+        tab[96u + lane] = 0xffffffffu;
         for (uint32_t j = 0; j < (uint32_t)kLutSize; j++) lut[j * 32u + lane] = (LutT)1;
     }
-    const uint32_t my_used = live ? m.used : 1u;
     __syncwarp();
     uint32_t n_max = my_n;
 #pragma unroll
@@ -987,17 +987,15 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
         rd.take_if(true);
         x = live ? ((uint64_t)lo | ((uint64_t)hi << 32)) : kRansL;
     }
-    uint16_t* my_row = stage + lane * kSymStride;
-    const uint32_t chunks = (n_max + kChunk - 1) / kChunk;
+    uint16_t* my_row = stage + lane * kDecStride;
+    const uint32_t chunks = (n_max + kDecChunk - 1) / kDecChunk;
     for (uint32_t chunk = 0; chunk < chunks; chunk++) {
-        const uint32_t base = chunk * kChunk;
         __syncwarp();
-        for (uint32_t k0 = 0; k0 < (uint32_t)kChunk; k0 += kTopUp) {
+        for (uint32_t k0 = 0; k0 < (uint32_t)kDecChunk; k0 += kTopUp) {
             rd.top_up();
-#pragma unroll 4
+#pragma unroll
             for (uint32_t k = k0; k < k0 + kTopUp; k++)
-                my_row[k] = (uint16_t)rans_get(x, rd, T, lut + lane, 32u, lut_shift, my_used, bits, mask, full,
-                                               base + k < my_n);
+                my_row[k] = (uint16_t)rans_get(x, rd, T, lut + lane, 32u, lut_shift, bits, mask);
         }
         __syncwarp();
         stage_store_chunk(stage, symbols, s_off, s_n, chunk);
@@ -1085,7 +1083,7 @@ __global__ void __launch_bounds__(kStaticDecWarps * 32) k_rans_decode_static(
     uint32_t bits, uint16_t* __restrict__ symbols) {
     __shared__ uint32_t s_dense[HOH_MAX_RANGE + 8];
     __shared__ uint32_t s_used;
-    __shared__ __align__(16) uint16_t s_stage[kStaticDecWarps][32 * kSymStride];
+    __shared__ __align__(16) uint16_t s_stage[kStaticDecWarps][32 * kDecStride];
     __shared__ __align__(16) uint32_t s_rings[kStaticDecWarps][32 * kRingWords];
     __shared__ uint64_t s_off[kStaticDecWarps][32];
     __shared__ uint32_t s_n[kStaticDecWarps][32];
@@ -1099,9 +1097,9 @@ __global__ void __launch_bounds__(kStaticDecWarps * 32) k_rans_decode_static(
         uint32_t d = 0;
         s_dense[0] = 0u;
         for (uint32_t i = 0; i < range; i++)
-            if (s_cum[i + 1] != s_cum[i]) s_dense[1u + d++] = s_cum[i] | (i << 20);
-        s_dense[d + 1] = s_cum[range];
-        s_dense[d + 2] = s_cum[range];
+            if (s_cum[i + 1] != s_cum[i]) s_dense[1u + d++] = (s_cum[i] << kSymBits) | i;
+        s_dense[d + 1] = s_cum[range] << kSymBits;
+        s_dense[d + 2] = 0xffffffffu;
         s_used = d;
         if (d) lut_build(T, s_lut, 1u, lut_shift, d);
     }
@@ -1119,7 +1117,6 @@ __global__ void __launch_bounds__(kStaticDecWarps * 32) k_rans_decode_static(
     const uint32_t used = s_used;
     if (used == 0u || __ballot_sync(0xffffffffu, live) == 0u) return;
     const uint32_t mask = (1u << bits) - 1u;
-    const uint32_t full = 1u << bits;
     uint32_t n_max = my_n;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
@@ -1135,16 +1132,15 @@ __global__ void __launch_bounds__(kStaticDecWarps * 32) k_rans_decode_static(
         x = live ? ((uint64_t)lo | ((uint64_t)hi << 32)) : kRansL;
     }
     uint16_t* stage = s_stage[w];
-    uint16_t* my_row = stage + lane * kSymStride;
-    const uint32_t chunks = (n_max + kChunk - 1) / kChunk;
+    uint16_t* my_row = stage + lane * kDecStride;
+    const uint32_t chunks = (n_max + kDecChunk - 1) / kDecChunk;
     for (uint32_t chunk = 0; chunk < chunks; chunk++) {
-        const uint32_t base = chunk * kChunk;
         __syncwarp();
-        for (uint32_t k0 = 0; k0 < (uint32_t)kChunk; k0 += kTopUp) {
+        for (uint32_t k0 = 0; k0 < (uint32_t)kDecChunk; k0 += kTopUp) {
             rd.top_up();
-#pragma unroll 4
+#pragma unroll
             for (uint32_t k = k0; k < k0 + kTopUp; k++)
-                my_row[k] = (uint16_t)rans_get(x, rd, T, s_lut, 1u, lut_shift, used, bits, mask, full, base + k < my_n);
+                my_row[k] = (uint16_t)rans_get(x, rd, T, s_lut, 1u, lut_shift, bits, mask);
         }
         __syncwarp();
         stage_store_chunk(stage, symbols, s_off[w], s_n[w], chunk);
