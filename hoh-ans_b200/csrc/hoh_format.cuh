@@ -178,12 +178,13 @@ HOH_HD uint32_t clamp_width_of(const ClampSet& c, uint32_t prob_bits, uint32_t s
     return w > prob_bits ? prob_bits : w;
 }
 
-// Builds everything encode_entropy writes before the payload-length varint:
-//   varint(range-1) varint(n) metadata table
-// from the NORMALISED frequencies.  Returns the number of bytes written to `head`; *stored_size gets
+// First part of what encode_entropy writes before the payload-length varint:
+//   varint(range-1) varint(n) metadata
+// plus the decisions the table needs: the clamp set and the table mode (1 = every frequency on maxbits
+// bits, 2 = clamp pairs + variable-width frequencies).  Returns the bytes written; *stored_size gets
 // entropy_encoding.hpp:45's size of the stored-mode alternative.
-HOH_HD uint32_t build_head(const uint32_t* freqs, uint32_t range, uint32_t n, uint32_t prob_bits,
-                           uint8_t* head, uint32_t* stored_size) {
+HOH_HD uint32_t plan_head(const uint32_t* freqs, uint32_t range, uint32_t n, uint32_t prob_bits, uint8_t* head,
+                          uint32_t* stored_size, ClampSet* cs, uint32_t* table_mode) {
     uint32_t at = 0;
     at = put_varint(head, at, range - 1);
     at = put_varint(head, at, n);
@@ -191,27 +192,37 @@ HOH_HD uint32_t build_head(const uint32_t* freqs, uint32_t range, uint32_t n, ui
     *stored_size = at + 1 + (uint32_t)(((uint64_t)maxbits * n + 7) / 8);
 
     uint64_t raw_table_bytes = ((uint64_t)prob_bits * range + 7) / 8;  // :47
-    ClampSet cs;
-    cs.count = (prob_bits - 1) / 4 + 2;  // :51
-    for (int k = 0; k < 16; k++) cs.lo[k] = cs.hi[k] = 0;
+    cs->count = (prob_bits - 1) / 4 + 2;                               // :51
+    for (int k = 0; k < 16; k++) cs->lo[k] = cs->hi[k] = 0;
     // :48-49 — 2*(maxbits-1) is int, the clamp count uint32_t: 32-bit unsigned product (range 1 wraps)
-    uint64_t clamped_bits = (uint64_t)((uint32_t)(2 * ((int)maxbits - 1)) * cs.count) + 2ull * prob_bits;
+    uint64_t clamped_bits = (uint64_t)((uint32_t)(2 * ((int)maxbits - 1)) * cs->count) + 2ull * prob_bits;
     uint32_t w_up, w_down;
-    uint32_t stop_up = clamp_walk(freqs, range, false, prob_bits, cs.count, cs.lo, &clamped_bits, &w_up,
+    uint32_t stop_up = clamp_walk(freqs, range, false, prob_bits, cs->count, cs->lo, &clamped_bits, &w_up,
                                   (uint16_t)(range - 1));
-    uint32_t stop_down = clamp_walk(freqs, range, true, prob_bits, cs.count, cs.hi, &clamped_bits, &w_down, 0);
+    uint32_t stop_down = clamp_walk(freqs, range, true, prob_bits, cs->count, cs->hi, &clamped_bits, &w_down, 0);
     // :121 — size_t arithmetic, wraps when the scans crossed
     clamped_bits += (uint64_t)w_down * ((uint64_t)stop_down - (uint64_t)stop_up - 1ull);
     uint64_t clamped_bytes = (clamped_bits + 7) / 8;
+    *table_mode = raw_table_bytes < clamped_bytes ? 1u : 2u;  // :135 / :148
+    head[at++] = (uint8_t)((1u << 7) + (prob_bits << 2) + *table_mode);
+    return at;
+}
 
+// Everything before the payload-length varint (plan_head + the table), bit-serially with the
+// reference's packer: exact for every input including the over-wide fields of D6.  The kernels use it
+// as is for those rare tables and a warp-parallel packer (same bytes when no field is over-wide) for
+// the rest.
+HOH_HD uint32_t build_head(const uint32_t* freqs, uint32_t range, uint32_t n, uint32_t prob_bits,
+                           uint8_t* head, uint32_t* stored_size) {
+    ClampSet cs;
+    uint32_t mode;
+    uint32_t at = plan_head(freqs, range, n, prob_bits, head, stored_size, &cs, &mode);
+    uint32_t maxbits = bit_length(range - 1);
     BitSink sink;
-    if (raw_table_bytes < clamped_bytes) {  // table mode 1, :135-147 (each freq on maxbits bits: D6)
-        head[at++] = (uint8_t)((1u << 7) + (prob_bits << 2) + 1u);
-        sink.open(head, at);
+    sink.open(head, at);
+    if (mode == 1) {  // table mode 1, :135-147 (each freq on maxbits bits: D6)
         for (uint32_t s = 0; s < range; s++) sink.put(freqs[s], maxbits);
     } else {  // table mode 2, :148-200
-        head[at++] = (uint8_t)((1u << 7) + (prob_bits << 2) + 2u);
-        sink.open(head, at);
         for (uint32_t j = 0; j < cs.count; j++) {
             sink.put(cs.lo[j], maxbits);
             sink.put(cs.hi[j], maxbits);

@@ -175,6 +175,107 @@ __device__ int warp_normalize(uint32_t* f, uint32_t* sc, uint32_t* cum, uint32_t
     return HOH_S_OK;
 }
 
+// Warp-parallel form of hohfmt::build_head.  Lane 0 makes the (short, data-dependent) decisions —
+// varints, clamp search, table mode — then every lane packs its contiguous run of frequencies: field
+// widths are computed per symbol, their bit offsets come from a prefix sum (warp shuffles), and each
+// field is OR-ed MSB-first into a zeroed big-endian word buffer with shared-memory atomics.  OR equals
+// the reference packer's ADD as long as no field is wider than its width; a table with such a field
+// (D6: table mode 1 with a frequency >= 2^maxbits, or one symbol owning all of 2^prob_bits) is detected
+// with a ballot and handed to the bit-serial builder, which reproduces the reference's carries.
+// `buf` = HOH_HEAD_CAP bytes of shared memory; on return it holds the head bytes in memory order.
+__device__ __forceinline__ void bits_or(uint32_t* words, uint32_t bit, uint32_t value, uint32_t width) {
+    if (width == 0u) return;
+    const uint64_t win = (uint64_t)value << (64u - (bit & 31u) - width);  // width <= 19: fits
+    const uint32_t k = bit >> 5;
+    atomicOr(&words[k], (uint32_t)(win >> 32));
+    if ((uint32_t)win) atomicOr(&words[k + 1u], (uint32_t)win);
+}
+
+__device__ uint32_t warp_build_head(const uint32_t* f, uint32_t range, uint32_t n, uint32_t prob_bits,
+                                    uint8_t* buf, uint32_t* scratch /* >= 40 words */, uint32_t* stored_size) {
+    const uint32_t lane = lane_id();
+    uint32_t* words = reinterpret_cast<uint32_t*>(buf);
+    const uint32_t maxbits = hohfmt::bit_length(range - 1);
+    // scratch: [0] = bytes of varints+metadata, [1] = mode, [2] = stored size, [3] = clamp count, [4..] = lo/hi
+    if (lane == 0) {
+        hohfmt::ClampSet cs;
+        uint32_t mode, st;
+        uint8_t tmp[8];
+        const uint32_t at = hohfmt::plan_head(f, range, n, prob_bits, tmp, &st, &cs, &mode);
+        scratch[0] = at;
+        scratch[1] = mode;
+        scratch[2] = st;
+        scratch[3] = cs.count;
+        for (uint32_t j = 0; j < 16; j++) scratch[4 + j] = (uint32_t)cs.lo[j] | ((uint32_t)cs.hi[j] << 16);
+        for (uint32_t k = 0; k < 8; k++) scratch[20 + k] = tmp[k];
+    }
+    for (uint32_t k = lane; k < HOH_HEAD_CAP / 4; k += 32) words[k] = 0u;
+    __syncwarp();
+    const uint32_t at = scratch[0], mode = scratch[1], count = scratch[3];
+    *stored_size = scratch[2];
+    // field widths of this lane's run of symbols, and whether every value fits
+    const uint32_t per = (range + 31u) / 32u;
+    const uint32_t lo = min(lane * per, range), hi = min(lo + per, range);
+    uint32_t my_bits = 0;
+    bool fits = true;
+    for (uint32_t i = lo; i < hi; i++) {
+        uint32_t w;
+        if (mode == 1u) {
+            w = maxbits;
+        } else {  // hohfmt::clamp_width_of
+            w = 0;
+            for (uint32_t j = 0; j < count; j++) {
+                const uint32_t c = scratch[4 + j];
+                if ((c & 0xffffu) <= i && (c >> 16) >= i) w = j == 0 ? 1u : 4u * j;
+            }
+            w = min(w, prob_bits);
+        }
+        fits = fits && (w >= 32u || f[i] < (1u << w));
+        my_bits += w;
+    }
+    if (!__all_sync(0xffffffffu, fits)) {  // over-wide field somewhere: exact bit-serial path
+        uint32_t len = 0;
+        if (lane == 0) len = hohfmt::build_head(f, range, n, prob_bits, buf, stored_size);
+        len = __shfl_sync(0xffffffffu, len, 0);
+        *stored_size = __shfl_sync(0xffffffffu, *stored_size, 0);
+        __syncwarp();
+        return len;
+    }
+    const uint32_t pair_bits = mode == 2u ? 2u * count * maxbits : 0u;
+    uint32_t bit = warp_incl_scan(my_bits) - my_bits + 8u * at + pair_bits;
+    const uint32_t total_bits = __shfl_sync(0xffffffffu, bit + my_bits, 31);
+    if (lane == 0) {
+        for (uint32_t k = 0; k < at; k++) bits_or(words, 8u * k, scratch[20 + k], 8u);
+        if (mode == 2u)
+            for (uint32_t j = 0; j < count; j++) {
+                const uint32_t c = scratch[4 + j];
+                bits_or(words, 8u * at + 2u * j * maxbits, c & 0xffffu, maxbits);
+                bits_or(words, 8u * at + (2u * j + 1u) * maxbits, c >> 16, maxbits);
+            }
+    }
+    for (uint32_t i = lo; i < hi; i++) {
+        uint32_t w;
+        if (mode == 1u) {
+            w = maxbits;
+        } else {
+            w = 0;
+            for (uint32_t j = 0; j < count; j++) {
+                const uint32_t c = scratch[4 + j];
+                if ((c & 0xffffu) <= i && (c >> 16) >= i) w = j == 0 ? 1u : 4u * j;
+            }
+            w = min(w, prob_bits);
+        }
+        bits_or(words, bit, f[i], w);
+        bit += w;
+    }
+    __syncwarp();
+    // big-endian bit order -> bytes in memory order
+    const uint32_t len = (total_bits + 7u) / 8u;
+    for (uint32_t k = lane; k < (len + 3u) / 4u; k += 32) words[k] = __byte_perm(words[k], 0u, 0x0123);
+    __syncwarp();
+    return len;
+}
+
 constexpr int kTableWarps = 4;
 
 __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
@@ -238,8 +339,7 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
         m.win_lo = lo;
         m.win_rows = hi - lo + 2u;
     }
-    if (lane == 0) m.head_len = hohfmt::build_head(f, st.range, st.n, st.prob_bits, s_head[w], &m.stored_size);
-    m.head_len = __shfl_sync(0xffffffffu, m.head_len, 0);
+    m.head_len = warp_build_head(f, st.range, st.n, st.prob_bits, s_head[w], sc, &m.stored_size);
     __syncwarp();
     const uint32_t words = (m.head_len + 3u) / 4u;
     for (uint32_t k = lane; k < words; k += 32)
@@ -614,18 +714,31 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
     uint32_t* f = s_f[w];
     uint32_t* cum = s_cum[w];
 
-    // lane 0 walks the bit-serial parts; the fields are then broadcast
+    // lane 0 reads the header (varints, metadata byte) and, for table mode 2, the clamp pairs; the
+    // frequency fields themselves are read by all lanes below
     hohfmt::StreamHead h;
     uint64_t after_table = 0;
     int status = HOH_S_OK;
+    uint32_t* clamps = s_cum[w];  // [0] = count, [1..] = lo | hi << 16 (the cumulative counts come later)
+    uint64_t field_bit = 0;       // absolute bit position (from byte 0 of the buffer) of the first frequency
     if (lane == 0) {
         h = hohfmt::parse_head(bytes, st.in_off, st.flags);
         after_table = h.body;
+        field_bit = h.body * 8u;
         if (!h.empty && h.rans) {
             if (h.range > HOH_MAX_RANGE) {
                 status = HOH_S_BAD_TABLE;
-            } else if (h.table_mode == 1 || h.table_mode == 2) {
-                after_table = hohfmt::parse_table(bytes, h, f);
+            } else if (h.table_mode == 2) {  // entropy_decoding.hpp:196-213: clamp pairs on maxbits bits each
+                hohfmt::BitSource<ByteView> bits{bytes, h.body, 0, 0};
+                uint32_t count = (uint32_t)(((int)h.prob_bits - 1) / 4 + 2);  // :197, int arithmetic
+                if (count > 16u) count = 16u;
+                clamps[0] = count;
+                for (uint32_t j = 0; j < count; j++) {
+                    const uint32_t lo = bits.get(h.maxbits) & 0xffffu;
+                    const uint32_t hi = bits.get(h.maxbits) & 0xffffu;
+                    clamps[1 + j] = lo | (hi << 16);
+                }
+                field_bit += 2ull * count * h.maxbits;
             } else if (h.table_mode == 3) {
                 status = HOH_S_BAD_TABLE;
             }
@@ -640,8 +753,40 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
     h.empty = __shfl_sync(0xffffffffu, h.empty, 0);
     h.body = __shfl_sync(0xffffffffu, h.body, 0);
     after_table = __shfl_sync(0xffffffffu, after_table, 0);
+    field_bit = __shfl_sync(0xffffffffu, field_bit, 0);
     status = __shfl_sync(0xffffffffu, status, 0);
     __syncwarp();
+
+    // table modes 1 and 2 (entropy_decoding.hpp:180-244): every lane reads the fields of its contiguous
+    // run of symbols; widths per symbol, then bit offsets by prefix sum, then the reference's bit reader
+    // positioned at the run's first bit
+    if (!h.empty && h.rans && status == HOH_S_OK && (h.table_mode == 1u || h.table_mode == 2u)) {
+        const uint32_t count = h.table_mode == 2u ? clamps[0] : 0u;
+        const uint32_t per = (h.range + 31u) / 32u;
+        const uint32_t lo = min(lane * per, h.range), hi = min(lo + per, h.range);
+        auto width_of = [&](uint32_t i) -> uint32_t {
+            if (h.table_mode == 1u) return h.maxbits;
+            uint32_t wd = 0;  // hohfmt::clamp_width_of
+            for (uint32_t j = 0; j < count; j++) {
+                const uint32_t c = clamps[1 + j];
+                if ((c & 0xffffu) <= i && (c >> 16) >= i) wd = j == 0 ? 1u : 4u * j;
+            }
+            return min(wd, h.prob_bits);
+        };
+        uint32_t my_bits = 0;
+        for (uint32_t i = lo; i < hi; i++) my_bits += width_of(i);
+        const uint32_t incl = warp_incl_scan(my_bits);
+        const uint64_t my_bit = field_bit + (incl - my_bits);
+        const uint64_t end_bit = field_bit + __shfl_sync(0xffffffffu, incl, 31);
+        hohfmt::BitSource<ByteView> bits{bytes, my_bit >> 3, 0, 0};
+        if (my_bit & 7u) {  // start inside a byte: its low bits are the first ones of this run
+            bits.have = 8u - (uint32_t)(my_bit & 7u);
+            bits.held = bytes[bits.at++] & ((1u << bits.have) - 1u);
+        }
+        for (uint32_t i = lo; i < hi; i++) f[i] = bits.get(width_of(i));
+        after_table = (end_bit + 7u) >> 3;
+        __syncwarp();
+    }
 
     DecMeta m;
     m.payload_off = h.body;
