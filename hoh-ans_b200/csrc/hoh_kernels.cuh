@@ -1941,83 +1941,106 @@ __global__ void k_make_tile_dec_streams(TileGeom g, uint64_t n_tiles, const uint
 // completed two boundaries ago with coalesced stores.
 constexpr int kRingStride = 66;                      // words per ring row (64 columns + 2 pad)
 constexpr int kUnpWarps = 4;
+constexpr int kUnpBlock = 16;                        // columns per transfer block; the rings hold 4 blocks
 constexpr uint32_t kMidPacked = 128u | (256u << 8) | (256u << 17);  // border value c/2 of G, R-G, B-G
 
+// Residual block (32 rows x 16 columns, three planes) -> registers: four rows per instruction, four
+// columns (8 bytes per plane) per lane; the loads are issued one block ahead of their use.
+struct UnpPrefetch {
+    uint2 g[4], a[4], b[4];
+};
 template <bool ALIGNED>
-__device__ __forceinline__ void unp_load_block(uint32_t* ring, const uint16_t* __restrict__ in_g,
-                                               const uint16_t* __restrict__ in_rg,
-                                               const uint16_t* __restrict__ in_bg, uint32_t y_base, uint32_t th,
-                                               uint32_t tw, uint32_t block) {
+__device__ __forceinline__ void unp_fetch_block(UnpPrefetch& pf, const uint16_t* __restrict__ in_g,
+                                                const uint16_t* __restrict__ in_rg,
+                                                const uint16_t* __restrict__ in_bg, uint32_t y_base, uint32_t th,
+                                                uint32_t tw, uint32_t block) {
     const uint32_t lane = lane_id();
-    const uint32_t half = (block & 1u) * 32u;
-    if (ALIGNED) {  // tw % 4 == 0: 4 columns per lane, 4 rows per instruction
-        const uint32_t c = 32u * block + 4u * (lane & 7u);
+    const uint32_t c = kUnpBlock * block + 4u * (lane & 3u);
 #pragma unroll
-        for (uint32_t i = 0; i < 8; i++) {
-            const uint32_t r = 4u * i + (lane >> 3);
-            const uint32_t y = y_base + r;
-            if (y < th && c < tw) {
-                const uint32_t at = y * tw + c;
-                const uint2 g = *reinterpret_cast<const uint2*>(in_g + at);
-                const uint2 a = *reinterpret_cast<const uint2*>(in_rg + at);
-                const uint2 b = *reinterpret_cast<const uint2*>(in_bg + at);
-                uint32_t* dst = ring + r * kRingStride + half + 4u * (lane & 7u);
-                dst[0] = (g.x & 0xffffu) | ((a.x & 0xffffu) << 8) | ((b.x & 0xffffu) << 17);
-                dst[1] = (g.x >> 16) | ((a.x >> 16) << 8) | ((b.x >> 16) << 17);
-                dst[2] = (g.y & 0xffffu) | ((a.y & 0xffffu) << 8) | ((b.y & 0xffffu) << 17);
-                dst[3] = (g.y >> 16) | ((a.y >> 16) << 8) | ((b.y >> 16) << 17);
-            }
-        }
-    } else {
-        const uint32_t c = 32u * block + lane;
-        for (uint32_t r = 0; r < 32; r++) {
-            const uint32_t y = y_base + r;
-            if (y < th && c < tw) {
-                const uint32_t at = y * tw + c;
-                ring[r * kRingStride + half + lane] =
-                    (uint32_t)in_g[at] | ((uint32_t)in_rg[at] << 8) | ((uint32_t)in_bg[at] << 17);
+    for (uint32_t i = 0; i < 4; i++) {
+        const uint32_t y = y_base + 8u * i + (lane >> 2);
+        pf.g[i] = pf.a[i] = pf.b[i] = make_uint2(0u, 0u);
+        if (y < th && c < tw) {
+            const uint32_t at = y * tw + c;
+            if (ALIGNED) {  // tw % 4 == 0
+                pf.g[i] = *reinterpret_cast<const uint2*>(in_g + at);
+                pf.a[i] = *reinterpret_cast<const uint2*>(in_rg + at);
+                pf.b[i] = *reinterpret_cast<const uint2*>(in_bg + at);
+            } else {
+                uint32_t v[3][4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++) {
+                    const bool ok = c + k < tw;
+                    v[0][k] = ok ? in_g[at + k] : 0u;
+                    v[1][k] = ok ? in_rg[at + k] : 0u;
+                    v[2][k] = ok ? in_bg[at + k] : 0u;
+                }
+                pf.g[i] = make_uint2(v[0][0] | (v[0][1] << 16), v[0][2] | (v[0][3] << 16));
+                pf.a[i] = make_uint2(v[1][0] | (v[1][1] << 16), v[1][2] | (v[1][3] << 16));
+                pf.b[i] = make_uint2(v[2][0] | (v[2][1] << 16), v[2][2] | (v[2][3] << 16));
             }
         }
     }
 }
+// registers -> ring slot of `block`, packed g | rg << 8 | bg << 17
+__device__ __forceinline__ void unp_commit_block(const UnpPrefetch& pf, uint32_t* ring, uint32_t block) {
+    const uint32_t lane = lane_id();
+    const uint32_t col = (block & 3u) * kUnpBlock + 4u * (lane & 3u);
+#pragma unroll
+    for (uint32_t i = 0; i < 4; i++) {
+        uint32_t* dst = ring + (8u * i + (lane >> 2)) * kRingStride + col;
+        const uint2 g = pf.g[i], a = pf.a[i], b = pf.b[i];
+        dst[0] = (g.x & 0xffffu) | ((a.x & 0xffffu) << 8) | ((b.x & 0xffffu) << 17);
+        dst[1] = (g.x >> 16) | ((a.x >> 16) << 8) | ((b.x >> 16) << 17);
+        dst[2] = (g.y & 0xffffu) | ((a.y & 0xffffu) << 8) | ((b.y & 0xffffu) << 17);
+        dst[3] = (g.y >> 16) | ((a.y >> 16) << 8) | ((b.y >> 16) << 17);
+    }
+}
 
-// ring values are 0x00BBGGRR
+// ring values are 0x00BBGGRR; block = 32 rows x 16 columns = 48 bytes per row
 template <bool ALIGNED>
 __device__ __forceinline__ void unp_store_block(const uint32_t* ring, uint8_t* __restrict__ img, uint32_t width,
                                                 uint32_t x0, uint32_t y0, uint32_t y_base, uint32_t th, uint32_t tw,
                                                 uint32_t block) {
     const uint32_t lane = lane_id();
-    const uint32_t half = (block & 1u) * 32u;
-    if (ALIGNED) {  // width % 4 == 0 and tile_w % 4 == 0: 4 pixels = 3 aligned words per lane
-        const uint32_t c = 32u * block + 4u * (lane & 7u);
+    const uint32_t col = (block & 3u) * kUnpBlock + 4u * (lane & 3u);
+    const uint32_t c = kUnpBlock * block + 4u * (lane & 3u);
 #pragma unroll
-        for (uint32_t i = 0; i < 8; i++) {
-            const uint32_t r = 4u * i + (lane >> 3);
-            const uint32_t y = y_base + r;
-            if (y < th && c < tw) {
-                const uint32_t* src = ring + r * kRingStride + half + 4u * (lane & 7u);
-                const uint32_t A = src[0], B = src[1], C = src[2], D = src[3];
-                uint32_t* dst = reinterpret_cast<uint32_t*>(img + ((uint64_t)(y0 + y) * width + x0 + c) * 3u);
+    for (uint32_t i = 0; i < 4; i++) {
+        const uint32_t r = 8u * i + (lane >> 2);
+        const uint32_t y = y_base + r;
+        if (y < th && c < tw) {
+            const uint32_t* src = ring + r * kRingStride + col;
+            const uint32_t A = src[0], B = src[1], C = src[2], D = src[3];
+            uint8_t* dst8 = img + ((uint64_t)(y0 + y) * width + x0 + c) * 3u;
+            if (ALIGNED) {  // width % 4 == 0 and tile_w % 4 == 0: 4 pixels = 3 aligned words
+                uint32_t* dst = reinterpret_cast<uint32_t*>(dst8);
                 dst[0] = A | (B << 24);
                 dst[1] = (B >> 8) | (C << 16);
                 dst[2] = (C >> 16) | (D << 8);
-            }
-        }
-    } else {
-        const uint32_t c = 32u * block + lane;
-        for (uint32_t r = 0; r < 32; r++) {
-            const uint32_t y = y_base + r;
-            if (y < th && c < tw) {
-                const uint32_t v = ring[r * kRingStride + half + lane];
-                uint8_t* dst = img + ((uint64_t)(y0 + y) * width + x0 + c) * 3u;
-                dst[0] = (uint8_t)v;
-                dst[1] = (uint8_t)(v >> 8);
-                dst[2] = (uint8_t)(v >> 16);
+            } else {
+                const uint32_t px[4] = {A, B, C, D};
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++)
+                    if (c + k < tw) {
+                        dst8[3 * k] = (uint8_t)px[k];
+                        dst8[3 * k + 1] = (uint8_t)(px[k] >> 8);
+                        dst8[3 * k + 2] = (uint8_t)(px[k] >> 16);
+                    }
             }
         }
     }
 }
 
+// Tile back end, mode 0: wavefront inverse of the MED predictor on the three planes of a tile, the
+// inverse colour transform and the scatter into the interleaved image (dhoh.cpp:72-84, 268-276).
+// One warp per tile; lane = row inside a 32-row band; lane r works on column t - r at step t and gets
+// its top neighbour from lane r-1 by shuffle (anti-diagonal wavefront).  Residuals and pixels move
+// through two shared-memory rings (32 rows x 64 columns = 4 blocks of 16, row stride 66 words so that
+// both the row-wise transfers and the diagonal accesses are bank-conflict free).  Every 16 steps: the
+// block completed three boundaries ago is written back with coalesced stores, the residual block
+// fetched (into registers) one boundary ago is committed to the ring, and the fetch of the next one is
+// issued, so global-memory latency overlaps a whole block of computation.
 template <bool ALIGNED>
 __global__ void __launch_bounds__(kUnpWarps * 32) k_tile_unpredict_s0(const uint16_t* __restrict__ resid, TileGeom g,
                                                                       uint64_t n_tiles, uint8_t* __restrict__ rgb) {
@@ -2036,7 +2059,7 @@ __global__ void __launch_bounds__(kUnpWarps * 32) k_tile_unpredict_s0(const uint
     const uint16_t* in_g = resid + (t * 3u + 0u) * g.plane_stride;
     const uint16_t* in_rg = resid + (t * 3u + 1u) * g.plane_stride;
     const uint16_t* in_bg = resid + (t * 3u + 2u) * g.plane_stride;
-    const uint32_t n_blocks = (tw + 31u) / 32u;
+    const uint32_t n_blocks = (tw + kUnpBlock - 1u) / kUnpBlock;
     const uint32_t* my_in = ring_in + lane * kRingStride;
     uint32_t* my_out = ring_out + lane * kRingStride;
 
@@ -2044,31 +2067,28 @@ __global__ void __launch_bounds__(kUnpWarps * 32) k_tile_unpredict_s0(const uint
         const uint32_t y_base = band * 32u;
         const uint32_t y = y_base + lane;
         const bool row_ok = y < th;
+        // column 0: L = TL = c/2; they are first used at x == 0 and only change from then on
         int Lg = 128, Lr = 256, Lb = 256, TLg = 128, TLr = 256, TLb = 256;
         uint32_t mine = kMidPacked;
-        for (uint32_t blk = 0; blk < n_blocks + 2u; blk++) {
+        UnpPrefetch pf;
+        unp_fetch_block<ALIGNED>(pf, in_g, in_rg, in_bg, y_base, th, tw, 0u);
+        for (uint32_t blk = 0; blk < n_blocks + 3u; blk++) {
             __syncwarp();
-            if (blk >= 2u) unp_store_block<ALIGNED>(ring_out, img, g.width, x0, y0, y_base, th, tw, blk - 2u);
-            if (blk < n_blocks) unp_load_block<ALIGNED>(ring_in, in_g, in_rg, in_bg, y_base, th, tw, blk);
+            if (blk >= 3u) unp_store_block<ALIGNED>(ring_out, img, g.width, x0, y0, y_base, th, tw, blk - 3u);
+            if (blk < n_blocks) unp_commit_block(pf, ring_in, blk);
+            if (blk + 1u < n_blocks) unp_fetch_block<ALIGNED>(pf, in_g, in_rg, in_bg, y_base, th, tw, blk + 1u);
             __syncwarp();
 #pragma unroll 4
-            for (uint32_t k = 0; k < 32u; k++) {
-                const uint32_t step = blk * 32u + k;
+            for (uint32_t k = 0; k < (uint32_t)kUnpBlock; k++) {
+                const uint32_t step = blk * kUnpBlock + k;
                 const int x = (int)step - (int)lane;
                 uint32_t top = __shfl_up_sync(0xffffffffu, mine, 1);
                 const bool in_row = x >= 0 && x < (int)tw;
+                // lane 0's top row is the previous band's last row; row 0 of the tile has T = TL = c/2
                 if (lane == 0) top = (band != 0u && in_row) ? carry[x] : kMidPacked;
-                if (y == 0u) top = kMidPacked;
                 if (row_ok && in_row) {
                     const uint32_t v = my_in[x & 63];
                     const int Tg = top & 255u, Tr = (top >> 8) & 511u, Tb = (top >> 17) & 511u;
-                    if (x == 0) {  // column 0: L = TL = c/2
-                        Lg = 128; Lr = 256; Lb = 256;
-                        TLg = 128; TLr = 256; TLb = 256;
-                    }
-                    if (y == 0u) {  // row 0: T = TL = c/2
-                        TLg = 128; TLr = 256; TLb = 256;
-                    }
                     const int vg = ((int)(v & 255u) + p_med_grad(Tg, Lg, TLg) - 128) & 255;
                     const int vr = ((int)((v >> 8) & 511u) + p_med_grad(Tr, Lr, TLr) - 256) & 511;
                     const int vb = ((int)((v >> 17) & 511u) + p_med_grad(Tb, Lb, TLb) - 256) & 511;
