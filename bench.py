@@ -267,6 +267,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     mod = _load("hohgpu", os.path.join(ROOT, "hoh-ans_b200", "host", "hohgpu.py"))
+    shard = _load("hoh_shard", os.path.join(ROOT, "hoh-ans_b200", "host", "shard.py"))
     g = mod.HohGpu(local_rank)
     lib, ctx = g.lib, g.ctx
     geom = g.tile_geometry(W, H)
@@ -277,7 +278,7 @@ def main():
 
     # inputs: distinct image per global index (seed = 1 + index), pinned host memory
     rgb_host = g.host_alloc(raw)
-    fill_images(rgb_host, 1 + rank * n_img, n_img, W, H, host_threads)
+    fill_images(rgb_host, shard.weak_first_seed(n_img, rank), n_img, W, H, host_threads)
     out_bytes = int(lib.hoh_encode_images_out_bytes(C.byref(geom), n_img))
     packed_cap = raw + raw // 4 + 4096 * n_streams
     d_rgb, d_back = g.alloc(raw), g.alloc(raw)
@@ -372,20 +373,12 @@ def main():
         e2e = {"ms": e2e_ms / e_steps, "ok": e2e_ok,
                "h2d": raw + total + (n_streams + 1) * 8, "d2h": total + (n_streams + 1) * 8 + raw}
 
-    # max over ranks
+    # max over ranks of the device time, sum over ranks of the bytes (hoh-ans_b200/host/shard.py)
     def rmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.reduce_max(x, world, device="cuda")
 
     def rsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return shard.reduce_sum(x, world, device="cuda")
 
     total_ms = rmax(total_ms)
     t_enc, t_dec = rmax(t_enc), rmax(t_dec)

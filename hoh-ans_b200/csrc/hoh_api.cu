@@ -179,11 +179,15 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
             k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, ctx->stream>>>(
                 d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
         }
-        LAUNCHED("k_rans_encode<u16>");
+        static const char* const names16[4] = {"k_rans_encode<u16>[rows<=64]", "k_rans_encode<u16>[rows<=128]",
+                                               "k_rans_encode<u16>[rows<=256]", "k_rans_encode<u16>[rows<=513]"};
+        static const char* const names32[4] = {"k_rans_encode<u32>[rows<=64]", "k_rans_encode<u32>[rows<=128]",
+                                               "k_rans_encode<u32>[rows<=256]", "k_rans_encode<u32>[rows<=513]"};
+        LAUNCHED(names16[c]);
         if (max_prob_bits > 15) {  // 32-bit table lanes; prob_bits >= 16 there, so never LOW_BITS
             k_rans_encode<uint32_t, false><<<blocks_for(n, 32), 32, smem32, ctx->stream>>>(
                 d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);
-            LAUNCHED("k_rans_encode<u32>");
+            LAUNCHED(names32[c]);
         }
     }
     k_finish_streams<<<blocks_for(n, 4), 128, 0, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, heads, meta, d_out,
@@ -217,7 +221,9 @@ int decode_common(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n, const
             k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 2, ctx->stream>>>(
                 d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, classes[c], rows);
         }
-        LAUNCHED("k_rans_decode");
+        static const char* const names[4] = {"k_rans_decode[rows<=64]", "k_rans_decode[rows<=128]",
+                                             "k_rans_decode[rows<=256]", "k_rans_decode[rows<=515]"};
+        LAUNCHED(names[c]);
     }
     return HOH_OK;
 }
