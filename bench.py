@@ -349,16 +349,23 @@ def main():
         off_host = g.host_alloc((n_streams + 1) * 8, np.uint64)
         back_host = g.host_alloc(raw)
 
+        e2e_split = [0.0, 0.0]
+
         def e2e_step():
+            ta = time.perf_counter()
             g._ck(lib.hoh_encode_images_s0_host(ctx, rgb_host.ctypes.data, n_img, W, H, packed_host.ctypes.data,
                                                 packed_cap, off_host.ctypes.data, None), "encode_host")
+            tb = time.perf_counter()
             total = int(off_host[n_streams])
             g._ck(lib.hoh_decode_images_s0_host(ctx, packed_host.ctypes.data, total, off_host.ctypes.data, n_img, W,
                                                 H, back_host.ctypes.data, None), "decode_host")
+            e2e_split[0] += tb - ta
+            e2e_split[1] += time.perf_counter() - tb
             return total
 
         e2e_step()
         e2e_ok = bool(np.array_equal(back_host, rgb_host))
+        e2e_split[0] = e2e_split[1] = 0.0
         barrier()
         g.timer_start(1)
         t0 = time.perf_counter()
@@ -370,7 +377,8 @@ def main():
         wall_ms = 1e3 * (time.perf_counter() - t0)
         barrier()
         e2e_ms = max(e2e_ms, wall_ms)
-        e2e = {"ms": e2e_ms / e_steps, "ok": e2e_ok,
+        e2e = {"ms": e2e_ms / e_steps, "ok": e2e_ok, "enc_ms": 1e3 * e2e_split[0] / e_steps,
+               "dec_ms": 1e3 * e2e_split[1] / e_steps,
                "h2d": raw + total + (n_streams + 1) * 8, "d2h": total + (n_streams + 1) * 8 + raw}
 
     # max over ranks of the device time, sum over ranks of the bytes (hoh-ans_b200/host/shard.py)
@@ -409,7 +417,7 @@ def main():
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            ent = tj.get(top_name.split("<")[0])
+            ent = tj.get(top_name.split("<")[0].split("[")[0])
             if ent and ent.get("images"):
                 traffic = ent["dram_bytes_per_launch"] * n_img / ent["images"]
         except Exception:
@@ -434,7 +442,8 @@ def main():
         if e2e:
             line["e2e"] = {"value": 2 * job_raw / (e2e["ms"] / 1e3) / 1e6, "unit": "MB/s",
                            "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
-                           "ms_per_step": e2e["ms"], "verified": e2e_all_ok}
+                           "ms_per_step": e2e["ms"], "encode_ms": e2e["enc_ms"], "decode_ms": e2e["dec_ms"],
+                           "verified": e2e_all_ok}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = args.cpu_sample or max(cores * 4, 32)

@@ -43,6 +43,13 @@ struct hoh_ctx {
     size_t flush_bytes = 0;
     std::map<uint64_t, double*> e_tabs;  // plane size -> device table of -log2(f/size)
     bool smem_opt_in = false;
+    // host-buffer pipeline (hoh_*_images_s0_host): copy streams, events, pinned offset staging
+    bool pipe_ready = false;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[4] = {}, ev_comp[4] = {}, ev_d2h[4] = {}, ev_off[4] = {}, ev_start = nullptr;
+    uint64_t* h_off[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t h_off_cap[4] = {0, 0, 0, 0};
+    hoh_ctx* child[4] = {nullptr, nullptr, nullptr, nullptr};  // one per chunk in flight (own stream + scratch)
     // per-kernel profiling (hoh_profile_*)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;       // event 0 = begin, event i = after launch i
@@ -339,6 +346,18 @@ void hoh_ctx_destroy(hoh_ctx* ctx) {
             if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->prof_events) cudaEventDestroy(ev);
     for (auto ev : ctx->prof_pool) cudaEventDestroy(ev);
+    for (int k = 0; k < 4; k++)
+        if (ctx->child[k]) hoh_ctx_destroy(ctx->child[k]);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (int k = 0; k < 4; k++) {
+        if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
+        if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
+        if (ctx->ev_d2h[k]) cudaEventDestroy(ctx->ev_d2h[k]);
+        if (ctx->ev_off[k]) cudaEventDestroy(ctx->ev_off[k]);
+        if (ctx->h_off[k]) cudaFreeHost(ctx->h_off[k]);
+    }
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -634,6 +653,68 @@ int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_by
     return HOH_OK;
 }
 
+// Host-buffer tile codec: the batch is cut into chunks that flow through a three-stage pipeline —
+// H2D copy (own stream), kernels, D2H copy (own stream) — so PCIe traffic in both directions overlaps
+// the kernels and each other.  The entropy kernels are bound by the serial chain of a stream, not by
+// how many streams run (one chunk alone takes almost as long as the whole batch), so the chunks'
+// kernels must themselves run CONCURRENTLY: each of the kPipeDepth chunks in flight has its own child
+// context (own stream, own scratch memory) and the GPU co-schedules their kernels.  The only host waits
+// are on the small per-chunk offset table (its total decides how many bytes to fetch).
+namespace {
+constexpr int kPipeDepth = 4;
+
+int pipe_init(hoh_ctx* ctx) {
+    if (ctx->pipe_ready) return HOH_OK;
+    CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < kPipeDepth; k++) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_off[k], cudaEventDisableTiming));
+        if (hoh_ctx_create(ctx->device, nullptr, &ctx->child[k]) != HOH_OK) return HOH_E_CUDA;
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+    ctx->pipe_ready = true;
+    return HOH_OK;
+}
+int pinned_off(hoh_ctx* ctx, int k, size_t entries, uint64_t** out) {
+    if (ctx->h_off_cap[k] < entries) {
+        if (ctx->h_off[k]) CK(cudaFreeHost(ctx->h_off[k]));
+        ctx->h_off[k] = nullptr;
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_off[k]), entries * sizeof(uint64_t), cudaHostAllocDefault));
+        ctx->h_off_cap[k] = entries;
+    }
+    *out = ctx->h_off[k];
+    return HOH_OK;
+}
+size_t chunk_images_for(size_t n_images, size_t raw_per_image) {
+    // about 8 chunks, but not below ~64 MB of pixels per chunk (small batches are not worth pipelining)
+    size_t per = (n_images + 7) / 8;
+    const size_t min_per = (64u << 20) / (raw_per_image ? raw_per_image : 1) + 1;
+    if (per < min_per) per = min_per;
+    if (per > n_images) per = n_images;
+    return per;
+}
+// everything queued on the parent's stream so far happens before the pipeline, and the pipeline's
+// completion is visible on the parent's stream afterwards
+int pipe_enter(hoh_ctx* ctx) {
+    CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_start, 0));
+    for (int k = 0; k < kPipeDepth; k++) CK(cudaStreamWaitEvent(ctx->child[k]->stream, ctx->ev_start, 0));
+    return HOH_OK;
+}
+int pipe_leave(hoh_ctx* ctx, uint64_t* launches_before) {
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    for (int k = 0; k < kPipeDepth; k++) {
+        CK(cudaStreamSynchronize(ctx->child[k]->stream));
+        ctx->launches += ctx->child[k]->launches - launches_before[k];
+    }
+    return HOH_OK;
+}
+}  // namespace
+
 int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_images, uint32_t width,
                               uint32_t height, uint8_t* packed_host, size_t packed_cap, uint64_t* off_host,
                               hoh_stream_result* results_host) {
@@ -641,31 +722,75 @@ int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_im
     if (n_images == 0) return HOH_OK;
     hoh_tile_geometry hg;
     TRY(hoh_tile_geometry_for(width, height, &hg));
-    const size_t raw = (size_t)n_images * width * height * 3;
-    const size_t n_streams = n_images * hg.streams_per_image;
-    const size_t out_bytes = hoh_encode_images_out_bytes(&hg, n_images);
-    const size_t dev_packed_cap = raw + raw / 4 + 4096 * n_streams;
-    uint8_t *d_rgb, *d_out, *d_packed;
-    hoh_stream_result* d_res;
-    uint64_t* d_off;
-    TRY(scratch_t(ctx, S_IO_A, raw, &d_rgb));
-    TRY(scratch_t(ctx, S_IO_B, out_bytes, &d_out));
-    TRY(scratch_t(ctx, S_IO_C, dev_packed_cap, &d_packed));
-    TRY(scratch_t(ctx, S_RESULTS, n_streams, &d_res));
-    TRY(scratch_t(ctx, S_IO_D, n_streams + 1, &d_off));
-    CK(cudaMemcpyAsync(d_rgb, rgb_host, raw, cudaMemcpyHostToDevice, ctx->stream));
-    TRY(hoh_encode_images_s0(ctx, d_rgb, n_images, width, height, nullptr, d_out, out_bytes, d_res, d_packed,
-                             dev_packed_cap, d_off));
-    CK(cudaMemcpyAsync(off_host, d_off, (n_streams + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (results_host)
-        CK(cudaMemcpyAsync(results_host, d_res, n_streams * sizeof(hoh_stream_result), cudaMemcpyDeviceToHost,
-                           ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const uint64_t total = off_host[n_streams];
-    if (total > packed_cap || total > dev_packed_cap) return HOH_E_CAPACITY;
-    CK(cudaMemcpyAsync(packed_host, d_packed, total, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return HOH_OK;
+    TRY(pipe_init(ctx));
+    const size_t raw1 = (size_t)width * height * 3;
+    const size_t per = chunk_images_for(n_images, raw1);
+    const size_t n_chunks = (n_images + per - 1) / per;
+    const size_t spi = hg.streams_per_image;
+    const size_t chunk_streams = per * spi;
+    const size_t out_bytes = hoh_encode_images_out_bytes(&hg, per);
+    const size_t dev_packed_cap = per * raw1 + per * raw1 / 4 + 4096 * chunk_streams;
+    const int depth = (int)(n_chunks < (size_t)kPipeDepth ? n_chunks : kPipeDepth);
+    uint8_t *d_rgb[kPipeDepth], *d_packed[kPipeDepth], *d_out[kPipeDepth];
+    hoh_stream_result* d_res[kPipeDepth];
+    uint64_t *d_off[kPipeDepth], *h_off[kPipeDepth];
+    uint64_t launches_before[kPipeDepth];
+    for (int k = 0; k < kPipeDepth; k++) launches_before[k] = ctx->child[k]->launches;
+    for (int k = 0; k < depth; k++) {  // staging lives in the child contexts
+        hoh_ctx* ch = ctx->child[k];
+        TRY(scratch_t(ch, S_IO_A, per * raw1, &d_rgb[k]));
+        TRY(scratch_t(ch, S_IO_B, out_bytes, &d_out[k]));
+        TRY(scratch_t(ch, S_IO_C, dev_packed_cap, &d_packed[k]));
+        TRY(scratch_t(ch, S_IO_D, chunk_streams + 1, &d_off[k]));
+        TRY(scratch_t(ch, S_RESULTS, chunk_streams, &d_res[k]));
+        TRY(pinned_off(ctx, k, chunk_streams + 1, &h_off[k]));
+    }
+    TRY(pipe_enter(ctx));
+    uint64_t base = 0;
+    off_host[0] = 0;
+    // chunk c: (1) H2D + kernels are queued `depth - 1` chunks ahead of (2) the fetch of its payloads
+    for (size_t c = 0; c < n_chunks + (size_t)depth - 1 + 1; c++) {
+        if (c < n_chunks) {
+            const int b = (int)(c % depth);
+            hoh_ctx* ch = ctx->child[b];
+            const size_t first = c * per;
+            const size_t n_c = first + per <= n_images ? per : n_images - first;
+            if (c >= (size_t)depth) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[b], 0));  // d_rgb[b] free again
+            CK(cudaMemcpyAsync(d_rgb[b], rgb_host + first * raw1, n_c * raw1, cudaMemcpyHostToDevice, ctx->s_h2d));
+            CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+            CK(cudaStreamWaitEvent(ch->stream, ctx->ev_h2d[b], 0));
+            if (c >= (size_t)depth) CK(cudaStreamWaitEvent(ch->stream, ctx->ev_d2h[b], 0));  // d_packed[b] fetched
+            TRY(hoh_encode_images_s0(ch, d_rgb[b], n_c, width, height, nullptr, d_out[b], out_bytes, d_res[b], d_packed[b],
+                                     dev_packed_cap, d_off[b]));
+            CK(cudaEventRecord(ctx->ev_comp[b], ch->stream));
+            // its offset table follows on the child's own stream (tiny; must not queue behind big fetches)
+            CK(cudaMemcpyAsync(h_off[b], d_off[b], (n_c * spi + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ch->stream));
+            CK(cudaEventRecord(ctx->ev_off[b], ch->stream));
+        }
+        if (c + 1 >= (size_t)depth && c + 1 - depth < n_chunks) {  // fetch chunk p = c - (depth - 1)
+            const size_t pc = c + 1 - depth;
+            const int p = (int)(pc % depth);
+            const size_t pfirst = pc * per;
+            const size_t n_p = pfirst + per <= n_images ? per : n_images - pfirst;
+            CK(cudaEventSynchronize(ctx->ev_off[p]));
+            const uint64_t total = h_off[p][n_p * spi];
+            if (base + total > packed_cap || total > dev_packed_cap) {
+                uint64_t dummy[kPipeDepth];
+                for (int k = 0; k < kPipeDepth; k++) dummy[k] = ctx->child[k]->launches;
+                pipe_leave(ctx, dummy);
+                return HOH_E_CAPACITY;
+            }
+            CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[p], 0));
+            CK(cudaMemcpyAsync(packed_host + base, d_packed[p], total, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (results_host)
+                CK(cudaMemcpyAsync(results_host + pfirst * spi, d_res[p], n_p * spi * sizeof(hoh_stream_result),
+                                   cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(cudaEventRecord(ctx->ev_d2h[p], ctx->s_d2h));
+            for (size_t i = 1; i <= n_p * spi; i++) off_host[pfirst * spi + i] = base + h_off[p][i];
+            base += total;
+        }
+    }
+    return pipe_leave(ctx, launches_before);
 }
 
 int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t packed_bytes,
@@ -675,25 +800,60 @@ int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t p
     if (n_images == 0) return HOH_OK;
     hoh_tile_geometry hg;
     TRY(hoh_tile_geometry_for(width, height, &hg));
-    const size_t raw = (size_t)n_images * width * height * 3;
-    const size_t n_streams = n_images * hg.streams_per_image;
-    const size_t padded = (packed_bytes + 31) & ~(size_t)15;
-    uint8_t *d_rgb, *d_packed;
-    uint64_t* d_off;
-    int32_t* d_st;
-    TRY(scratch_t(ctx, S_IO_A, raw, &d_rgb));
-    TRY(scratch_t(ctx, S_IO_C, padded, &d_packed));
-    TRY(scratch_t(ctx, S_IO_D, n_streams + 1, &d_off));
-    TRY(scratch_t(ctx, S_IO_E, n_streams, &d_st));
-    CK(cudaMemsetAsync(d_packed + (packed_bytes & ~(size_t)15), 0, padded - (packed_bytes & ~(size_t)15), ctx->stream));
-    CK(cudaMemcpyAsync(d_packed, packed_host, packed_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_off, off_host, (n_streams + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    TRY(hoh_decode_images_s0(ctx, d_packed, padded, d_off, n_images, width, height, nullptr, d_rgb, d_st));
-    CK(cudaMemcpyAsync(rgb_host, d_rgb, raw, cudaMemcpyDeviceToHost, ctx->stream));
-    if (status_host)
-        CK(cudaMemcpyAsync(status_host, d_st, n_streams * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return HOH_OK;
+    TRY(pipe_init(ctx));
+    const size_t raw1 = (size_t)width * height * 3;
+    const size_t per = chunk_images_for(n_images, raw1);
+    const size_t n_chunks = (n_images + per - 1) / per;
+    const size_t spi = hg.streams_per_image;
+    const size_t chunk_streams = per * spi;
+    size_t max_packed = 0;  // largest packed chunk
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t s0 = c * per * spi, s1 = (c + 1) * per < n_images ? (c + 1) * per * spi : n_images * spi;
+        if (off_host[s1] < off_host[s0] || off_host[s1] > packed_bytes) return HOH_E_ARG;
+        if (off_host[s1] - off_host[s0] > max_packed) max_packed = off_host[s1] - off_host[s0];
+    }
+    const size_t padded_cap = (max_packed + 47) & ~(size_t)15;
+    const int depth = (int)(n_chunks < (size_t)kPipeDepth ? n_chunks : kPipeDepth);
+    uint8_t *d_rgb[kPipeDepth], *d_packed[kPipeDepth];
+    uint64_t *d_off[kPipeDepth], *h_off[kPipeDepth];
+    int32_t* d_st[kPipeDepth];
+    uint64_t launches_before[kPipeDepth];
+    for (int k = 0; k < kPipeDepth; k++) launches_before[k] = ctx->child[k]->launches;
+    for (int k = 0; k < depth; k++) {
+        hoh_ctx* ch = ctx->child[k];
+        TRY(scratch_t(ch, S_IO_A, per * raw1, &d_rgb[k]));
+        TRY(scratch_t(ch, S_IO_C, padded_cap, &d_packed[k]));
+        TRY(scratch_t(ch, S_IO_D, chunk_streams + 1, &d_off[k]));
+        TRY(scratch_t(ch, S_IO_E, chunk_streams, &d_st[k]));
+        TRY(pinned_off(ctx, k, chunk_streams + 1, &h_off[k]));
+    }
+    TRY(pipe_enter(ctx));
+    for (size_t c = 0; c < n_chunks; c++) {
+        const int b = (int)(c % depth);
+        hoh_ctx* ch = ctx->child[b];
+        const size_t first = c * per;
+        const size_t n_c = first + per <= n_images ? per : n_images - first;
+        const size_t s0 = first * spi, ns = n_c * spi;
+        const uint64_t lo = off_host[s0], bytes = off_host[s0 + ns] - lo;
+        const size_t padded = (bytes + 31) & ~(size_t)15;
+        if (c >= (size_t)depth) CK(cudaEventSynchronize(ctx->ev_h2d[b]));  // h_off[b] was read by chunk c-depth's copy
+        for (size_t i = 0; i <= ns; i++) h_off[b][i] = off_host[s0 + i] - lo;
+        if (c >= (size_t)depth) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[b], 0));  // d_packed[b] / d_off[b] free
+        CK(cudaMemsetAsync(d_packed[b] + (bytes & ~(size_t)15), 0, padded - (bytes & ~(size_t)15), ctx->s_h2d));
+        CK(cudaMemcpyAsync(d_packed[b], packed_host + lo, bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaMemcpyAsync(d_off[b], h_off[b], (ns + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+        CK(cudaStreamWaitEvent(ch->stream, ctx->ev_h2d[b], 0));
+        if (c >= (size_t)depth) CK(cudaStreamWaitEvent(ch->stream, ctx->ev_d2h[b], 0));  // d_rgb[b] fetched
+        TRY(hoh_decode_images_s0(ch, d_packed[b], padded, d_off[b], n_c, width, height, nullptr, d_rgb[b], d_st[b]));
+        CK(cudaEventRecord(ctx->ev_comp[b], ch->stream));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[b], 0));
+        CK(cudaMemcpyAsync(rgb_host + first * raw1, d_rgb[b], n_c * raw1, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (status_host)
+            CK(cudaMemcpyAsync(status_host + s0, d_st[b], ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+    }
+    return pipe_leave(ctx, launches_before);
 }
 
 // =================================================================================================

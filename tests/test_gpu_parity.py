@@ -398,3 +398,38 @@ def test_decode_images_s0_noisy_and_flat_images():
     # reference's own decoder fails on it too), so image 1 is only checked on the encode side
     assert np.array_equal(back[:W * H * 3], imgs[0])
     assert np.array_equal(back[2 * W * H * 3:], imgs[2])
+
+
+def test_host_buffer_pipeline_matches_device_path():
+    """hoh_encode_images_s0_host / hoh_decode_images_s0_host (chunked H2D / kernels / D2H pipeline, 3 chunks
+    here) return exactly what the one-shot device-resident calls return."""
+    import ctypes as C
+    g = gpu_lib.gpu()
+    mod = gpu_lib.hohgpu()
+    W = H = 512
+    n = 200  # 157 MB of pixels: above the pipeline's 64 MB minimum chunk, so several chunks
+    rgb = g.host_alloc(n * W * H * 3)
+    for i in range(n):
+        rgb[i * W * H * 3:(i + 1) * W * H * 3] = ol.synth_rgb(W, H, 1 + (i % 7))
+    geom = g.tile_geometry(W, H)
+    ns = n * geom.streams_per_image
+    cap = rgb.size * 2
+    packed = g.host_alloc(cap)
+    off = g.host_alloc((ns + 1) * 8, np.uint64)
+    res = np.zeros(ns, mod.RESULT_DT)
+    g._ck(g.lib.hoh_encode_images_s0_host(g.ctx, rgb.ctypes.data, n, W, H, packed.ctypes.data, cap, off.ctypes.data,
+                                          res.ctypes.data), "encode_host")
+    assert (res["status"] == 0).all()
+    ref_packed, ref_off, _ = g.encode_images_s0(rgb[:7 * W * H * 3], 7, W, H)
+    per_img = geom.streams_per_image
+    assert np.array_equal(np.diff(off.astype(np.int64))[:7 * per_img], np.diff(ref_off.astype(np.int64)))
+    assert packed[:int(ref_off[-1])].tobytes() == ref_packed.tobytes()
+    # images repeat with period 7, so every image's payload sizes must repeat too
+    sizes = np.diff(off.astype(np.int64)).reshape(n, per_img)
+    assert all(np.array_equal(sizes[i], sizes[i % 7]) for i in range(n))
+    back = g.host_alloc(rgb.size)
+    st = np.zeros(ns, np.int32)
+    g._ck(g.lib.hoh_decode_images_s0_host(g.ctx, packed.ctypes.data, int(off[ns]), off.ctypes.data, n, W, H,
+                                          back.ctypes.data, st.ctypes.data), "decode_host")
+    assert (st == 0).all()
+    assert np.array_equal(back, rgb)
