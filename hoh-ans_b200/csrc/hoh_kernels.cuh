@@ -920,21 +920,18 @@ struct WordRing {
     const uint32_t* base16;  // 16-byte aligned word pointer at or below the first payload byte
     uint32_t* ring;          // this lane's kRingWords words of shared memory
     uint32_t ring_addr;      // the same, as a shared-window address
-    uint32_t pos;            // aligned-word index (from base16) holding the next payload byte
+    uint32_t pos;            // aligned-word index (from base16) holding the first byte of `next`
     uint32_t end;            // aligned-word index up to which blocks have been requested (multiple of 4)
     uint32_t limit;          // first aligned-word index that must not be read (multiple of 4, inside the buffer)
     uint32_t shift;          // 8 * byte misalignment of the payload
-    uint32_t next;           // the next payload word, already assembled
+    uint32_t next;           // the next payload word, assembled
+    uint32_t wa, wb;         // ring[pos + 1], ring[pos + 2]: the aligned words the word after `next` is cut from
 
     __device__ __forceinline__ void request(uint32_t want) {  // blocks up to word index `want`
         while (end < want) {
             if (end < limit) cp_async16(ring_addr + (end & (kRingWords - 1)) * 4u, base16 + end);
             end += 4u;
         }
-    }
-    __device__ __forceinline__ uint32_t assemble() const {
-        const uint32_t lo = ring[pos & (kRingWords - 1)], hi = ring[(pos + 1u) & (kRingWords - 1)];
-        return __funnelshift_r(lo, hi, shift);
     }
     // in / in_bytes: the whole input buffer (16-byte aligned base; reads stay inside it)
     __device__ __forceinline__ void open(const uint8_t* in, uint64_t in_bytes, uint64_t off, uint32_t* lane_ring) {
@@ -952,7 +949,9 @@ struct WordRing {
         request(pos + kAhead);
         cp_async_commit();
         cp_async_wait_group<0>();
-        next = assemble();
+        next = __funnelshift_r(ring[pos & (kRingWords - 1)], ring[(pos + 1u) & (kRingWords - 1)], shift);
+        wa = ring[(pos + 1u) & (kRingWords - 1)];
+        wb = ring[(pos + 2u) & (kRingWords - 1)];
     }
     // uniform point, every kTopUp symbols: request ahead, and make everything but that request resident
     __device__ __forceinline__ void top_up() {
@@ -960,11 +959,15 @@ struct WordRing {
         cp_async_commit();
         cp_async_wait_group<1>();
     }
+    // Consume `next` if `take`.  Branch-free: the following word is cut from two registers that were
+    // loaded when the previous word was taken (at least one whole step ago), and the only memory access
+    // is one predicated shared-memory load whose result is not looked at before the next take.
     __device__ __forceinline__ void take_if(bool take) {
-        if (take) {
-            pos++;
-            next = assemble();
-        }
+        const uint32_t following = __funnelshift_r(wa, wb, shift);
+        next = take ? following : next;
+        pos += take ? 1u : 0u;
+        wa = take ? wb : wa;
+        if (take) wb = ring[(pos + 2u) & (kRingWords - 1)];
     }
 };
 
@@ -1012,7 +1015,9 @@ __device__ __forceinline__ uint32_t rans_lookup(const Table& T, const LutT* lut,
     const bool up = e1 < key;     // ... or ends before it
     uint32_t e = down ? em : (up ? e1 : e0);
     uint32_t hi = down ? e0 : (up ? e2 : e1);
-    if (e >= key || hi < key) {  // more than one row away (several symbols inside 1/128th of the range)
+    // more than one row away (several symbols inside 1/128th of the range): rare; the vote makes the
+    // branch uniform so that the common path carries no divergence bookkeeping
+    if (__any_sync(0xffffffffu, e >= key || hi < key)) {
         p = down ? p - 1u : (up ? p + 1u : p);
         while (e >= key) {
             p--;
