@@ -433,3 +433,87 @@ def test_host_buffer_pipeline_matches_device_path():
                                           back.ctypes.data, st.ctypes.data), "decode_host")
     assert (st == 0).all()
     assert np.array_equal(back, rgb)
+
+
+def test_predictor_search_batched_planes_vs_oracle():
+    """hoh_predictor_search_dev over several planes at once (the BASELINE config 3 / 5 shape: every
+    channel of every tile is one plane) equals the per-plane oracle."""
+    g = gpu_lib.gpu()
+    O = ol.oracle()
+    rng = np.random.default_rng(31)
+    w, h, depth, mode, n_planes = 128, 96, 9, 2, 6
+    planes = np.concatenate([_smooth_plane(rng, w, h, depth) for _ in range(n_planes)])
+    cells = ((w + 39) // 40) * ((h + 39) // 40)
+    d_pl = g.alloc(planes.nbytes).upload(planes)
+    d_map, d_idx, d_res = g.alloc(n_planes * cells * 2), g.alloc(n_planes * cells), g.alloc(planes.nbytes)
+    g._ck(g.lib.hoh_predictor_search_dev(g.ctx, d_pl.ptr, n_planes, w, h, depth, mode, d_map.ptr, d_idx.ptr,
+                                         d_res.ptr), "search_dev")
+    maps = d_map.download(np.uint16, n_planes * cells).reshape(n_planes, cells)
+    idxs = d_idx.download(np.uint8, n_planes * cells).reshape(n_planes, cells)
+    res = d_res.download(np.uint16, planes.size).reshape(n_planes, w * h)
+    for p in range(n_planes):
+        tm, idx, r = np.zeros(cells, np.uint16), np.zeros(cells, np.uint8), np.zeros(w * h, np.uint16)
+        O.orc_predictor_search(np.ascontiguousarray(planes[p * w * h:(p + 1) * w * h]), w * h, w, h, depth, mode,
+                               tm, idx, r.ctypes.data)
+        assert np.array_equal(maps[p], tm) and np.array_equal(idxs[p], idx) and np.array_equal(res[p], r), p
+    # and the batched inverse: unpredict_all over all planes returns the planes
+    d_back = g.alloc(planes.nbytes)
+    g._ck(g.lib.hoh_unpredict_all_dev(g.ctx, d_res.ptr, n_planes, w, h, depth, (w + 39) // 40, (h + 39) // 40,
+                                      d_map.ptr, None, d_back.ptr), "unpredict_all_dev")
+    assert np.array_equal(d_back.download(np.uint16, planes.size), planes)
+    for b in (d_pl, d_map, d_idx, d_res, d_back):
+        b.free()
+
+
+def test_round_trip_4k_images_and_larger_batch():
+    """Size-independent property at BASELINE shapes: 3840x2160 (15x8 tiles of 256x270, choh.cpp:455-460) and
+    a 256-image batch of 512x512 round-trip exactly; payload sizes of identical images are identical."""
+    g = gpu_lib.gpu()
+    W, H = 3840, 2160
+    rgb = np.concatenate([ol.synth_rgb(W, H, 1), ol.synth_rgb(W, H, 2)])
+    packed, off, res = g.encode_images_s0(rgb, 2, W, H)
+    assert (res["status"] == 0).all() and len(off) == 2 * 360 + 1
+    assert hashlib.md5(rgb[:W * H * 3].tobytes()).hexdigest() == "2517cea8921e09ee393f541b4a3a4f51"  # SURVEY 8(c)
+    back, st = g.decode_images_s0(packed, off, 2, W, H)
+    assert (st == 0).all() and np.array_equal(back, rgb)
+    # one tile against the oracle
+    tile = np.ascontiguousarray(rgb[:W * H * 3].reshape(H, W, 3)[270:540, 256:512]).ravel()
+    s = (1 * 15 + 1) * 3
+    for k, want in enumerate(_oracle_channels(tile, 256, 270)):
+        assert packed[int(off[s + k]):int(off[s + k + 1])].tobytes() == want.tobytes()
+    n = 256
+    base = [ol.synth_rgb(512, 512, 1 + i) for i in range(4)]
+    rgb = np.concatenate([base[i % 4] for i in range(n)])
+    packed, off, res = g.encode_images_s0(rgb, n, 512, 512)
+    sizes = np.diff(off.astype(np.int64)).reshape(n, 12)
+    assert all(np.array_equal(sizes[i], sizes[i % 4]) for i in range(n))
+    back, st = g.decode_images_s0(packed, off, n, 512, 512)
+    assert (st == 0).all() and np.array_equal(back, rgb)
+
+
+def test_rans_static_sweep_64mb_round_trip():
+    """Config 4 at a larger size: 64 Mi geometric symbols in 65 536-symbol streams, one static table;
+    decode(encode(x)) == x and the payload total matches the entropy within 1 %."""
+    g = gpu_lib.gpu()
+    n, stream_len, pb = 1 << 26, 65536, 12
+    sym8 = np.tile(ol.synth_symbols(1 << 22, 11), 16)
+    f = np.bincount(sym8[:1 << 22], minlength=256).astype(np.uint32)
+    cum = np.zeros(257, np.uint32)
+    assert ol.oracle().orc_normalize_freqs(f, cum, 256, 1 << pb) == 0
+    sym = sym8.astype(np.uint16)
+    n_streams = n // stream_len
+    slab = (stream_len * pb // 8 + 64 + 15) & ~15
+    d_sym, d_cum = g.alloc(sym.nbytes).upload(sym), g.alloc(cum.nbytes).upload(cum)
+    d_out, d_len, d_dec = g.alloc(n_streams * slab), g.alloc(n_streams * 4), g.alloc(sym.nbytes)
+    g._ck(g.lib.hoh_rans_encode_static(g.ctx, d_sym.ptr, n, stream_len, d_cum.ptr, 256, pb, d_out.ptr, slab,
+                                       d_len.ptr), "enc")
+    g._ck(g.lib.hoh_rans_decode_static(g.ctx, d_out.ptr, slab, d_len.ptr, n, stream_len, d_cum.ptr, 256, pb,
+                                       d_dec.ptr), "dec")
+    assert np.array_equal(d_dec.download(np.uint16, n), sym)
+    lens = d_len.download(np.uint32, n_streams)
+    p = f[f > 0] / float(1 << pb)
+    counts = np.bincount(sym8[:1 << 22], minlength=256)[f > 0]
+    ideal_bits = float(-(counts * np.log2(p)).sum()) * 16
+    assert abs(lens.sum() * 8.0 / ideal_bits - 1.0) < 0.01
+    for b in (d_sym, d_cum, d_out, d_len, d_dec):
+        b.free()
