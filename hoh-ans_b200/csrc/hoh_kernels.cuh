@@ -1386,6 +1386,22 @@ __device__ __forceinline__ int p_paeth(int A, int B, int C) {                   
 }
 // median(T, L, (u16)(T + L - TL)): the gradient wraps to u16 before the median
 __device__ __forceinline__ int p_med_grad(int T, int L, int TL) { return p_med(T, L, (T + L - TL) & 0xffff); }
+// The same on two u16 lanes of one register (sm_100a has native 16x2 integer add / min / max:
+// VIADD.16x2, VIMNMX.U16x2, VIADDMNMX.U16x2).  The lanes wrap modulo 2^16 exactly like the reference's
+// uint16_t gradient, and the comparisons are unsigned, so this IS predictor_operations.hpp:37-60 on
+// (T, L, (u16)(T + L - TL)) for two channels at once.
+__device__ __forceinline__ uint32_t p_med_grad2(uint32_t T, uint32_t L, uint32_t TL) {
+    const uint32_t lo = __vminu2(T, L), hi = __vmaxu2(T, L);
+    const uint32_t grad = __vsub2(__vadd2(T, L), TL);
+    return __vmaxu2(lo, __vminu2(hi, grad));
+}
+constexpr uint32_t kHalfRB = 256u | (256u << 16);   // c/2 of the two 9-bit planes (R-G, B-G), one per lane
+constexpr uint32_t kMaskRB = 511u | (511u << 16);
+// pixel 0x00BBGGRR -> g and (R-G+256 | B-G+256 << 16)   (channel.hpp:75-77)
+__device__ __forceinline__ void planes2_of(uint32_t p, uint32_t& g, uint32_t& rb) {
+    g = (p >> 8) & 255u;
+    rb = __vadd2(__vsub2(p & 0x00ff00ffu, g * 0x00010001u), kHalfRB);
+}
 
 // =================================================================================================
 // Colour transform — channel.hpp:73-79 and its algebraic inverse
@@ -1806,19 +1822,8 @@ __global__ void __launch_bounds__(256) k_tile_residuals_s0_generic(const uint8_t
 // Same stage for the common geometry (image width and tile width multiples of 4): every thread takes
 // four horizontally adjacent pixels = 12 bytes = three aligned words per row (plus the word holding the
 // left neighbour), so global traffic is 32-bit loads and 8-byte stores and the row/column bookkeeping
-// is incremental (no per-pixel division).
-struct Px3 {
-    int g, r, b;  // G, R-G+256, B-G+256 (channel.hpp:75-77)
-};
-__device__ __forceinline__ Px3 planes_of(uint32_t p) {  // p = 0x00BBGGRR
-    const int g = (p >> 8) & 255;
-    Px3 o;
-    o.g = g;
-    o.r = (int)(p & 255u) - g + 256;
-    o.b = (int)((p >> 16) & 255u) - g + 256;
-    return o;
-}
-
+// is incremental (no per-pixel division).  The two 9-bit planes (R-G, B-G) travel as two 16-bit lanes
+// of one register through the packed median.
 __global__ void __launch_bounds__(256) k_tile_residuals_s0(const uint8_t* __restrict__ rgb, TileGeom g,
                                                            uint16_t* __restrict__ resid,
                                                            uint32_t* __restrict__ freqs) {
@@ -1837,7 +1842,6 @@ __global__ void __launch_bounds__(256) k_tile_residuals_s0(const uint8_t* __rest
     const uint32_t quads = tw / 4u;  // tw % 4 == 0 on this path
     const uint32_t dy = 256u / quads, dq = 256u % quads;
     uint32_t y = threadIdx.x / quads, q = threadIdx.x % quads;
-    const Px3 mid{128, 256, 256};
     const uint32_t row_words = g.width * 3u / 4u;
     for (; y < th; y += dy, q += dq) {
         if (q >= quads) {
@@ -1847,39 +1851,53 @@ __global__ void __launch_bounds__(256) k_tile_residuals_s0(const uint8_t* __rest
         }
         const uint32_t* row = reinterpret_cast<const uint32_t*>(img + ((uint64_t)(y0 + y) * g.width + x0 + 4u * q) * 3u);
         const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
-        Px3 cur[5], top[5];
-        cur[0] = q ? planes_of(row[-1] >> 8) : mid;  // column 0: L = c/2
-        cur[1] = planes_of(w0 & 0xffffffu);
-        cur[2] = planes_of((w0 >> 24) | ((w1 & 0xffffu) << 8));
-        cur[3] = planes_of((w1 >> 16) | ((w2 & 0xffu) << 16));
-        cur[4] = planes_of(w2 >> 8);
+        // five pixels of this row (left neighbour + the quad) and of the row above, as g and (rg | bg << 16)
+        uint32_t cg[5], cr[5], tg[5], tr[5];
+        planes2_of(w0 & 0xffffffu, cg[1], cr[1]);
+        planes2_of((w0 >> 24) | ((w1 & 0xffffu) << 8), cg[2], cr[2]);
+        planes2_of((w1 >> 16) | ((w2 & 0xffu) << 16), cg[3], cr[3]);
+        planes2_of(w2 >> 8, cg[4], cr[4]);
+        if (q) {
+            planes2_of(row[-1] >> 8, cg[0], cr[0]);
+        } else {  // column 0: L = c/2
+            cg[0] = 128u;
+            cr[0] = kHalfRB;
+        }
         if (y) {
             const uint32_t* up = row - row_words;
             const uint32_t u0 = up[0], u1 = up[1], u2 = up[2];
-            top[0] = q ? planes_of(up[-1] >> 8) : mid;  // column 0: TL = c/2
-            top[1] = planes_of(u0 & 0xffffffu);
-            top[2] = planes_of((u0 >> 24) | ((u1 & 0xffffu) << 8));
-            top[3] = planes_of((u1 >> 16) | ((u2 & 0xffu) << 16));
-            top[4] = planes_of(u2 >> 8);
+            planes2_of(u0 & 0xffffffu, tg[1], tr[1]);
+            planes2_of((u0 >> 24) | ((u1 & 0xffffu) << 8), tg[2], tr[2]);
+            planes2_of((u1 >> 16) | ((u2 & 0xffu) << 16), tg[3], tr[3]);
+            planes2_of(u2 >> 8, tg[4], tr[4]);
+            if (q) {
+                planes2_of(up[-1] >> 8, tg[0], tr[0]);
+            } else {  // column 0: TL = c/2
+                tg[0] = 128u;
+                tr[0] = kHalfRB;
+            }
         } else {
 #pragma unroll
-            for (int i = 0; i < 5; i++) top[i] = mid;  // row 0: T = TL = c/2
+            for (int i = 0; i < 5; i++) {  // row 0: T = TL = c/2
+                tg[i] = 128u;
+                tr[i] = kHalfRB;
+            }
         }
-        uint32_t rg_[4], rr_[4], rb_[4];
+        uint32_t rg_[4], rr_[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const Px3 v = cur[i + 1], L = cur[i], T = top[i + 1], TL = top[i];
-            rg_[i] = (uint32_t)((v.g - p_med_grad(T.g, L.g, TL.g) + 128 + 256) & 255);
-            rr_[i] = (uint32_t)((v.r - p_med_grad(T.r, L.r, TL.r) + 256 + 512) & 511);
-            rb_[i] = (uint32_t)((v.b - p_med_grad(T.b, L.b, TL.b) + 256 + 512) & 511);
+        for (int i = 0; i < 4; i++) {  // prediction.hpp:35-41: (v - median + c/2 + c) % c
+            rg_[i] = (cg[i + 1] - p_med_grad2(tg[i + 1], cg[i], tg[i]) + 128u + 256u) & 255u;
+            rr_[i] = __vadd2(__vsub2(cr[i + 1], p_med_grad2(tr[i + 1], cr[i], tr[i])), kHalfRB) & kMaskRB;
             atomicAdd(&s_h[0][rg_[i]], 1u);
-            atomicAdd(&s_h[1][rr_[i]], 1u);
-            atomicAdd(&s_h[2][rb_[i]], 1u);
+            atomicAdd(&s_h[1][rr_[i] & 0xffffu], 1u);
+            atomicAdd(&s_h[2][rr_[i] >> 16], 1u);
         }
         const uint32_t at = y * tw + 4u * q;
         *reinterpret_cast<uint2*>(out_g + at) = make_uint2(rg_[0] | (rg_[1] << 16), rg_[2] | (rg_[3] << 16));
-        *reinterpret_cast<uint2*>(out_rg + at) = make_uint2(rr_[0] | (rr_[1] << 16), rr_[2] | (rr_[3] << 16));
-        *reinterpret_cast<uint2*>(out_bg + at) = make_uint2(rb_[0] | (rb_[1] << 16), rb_[2] | (rb_[3] << 16));
+        *reinterpret_cast<uint2*>(out_rg + at) =
+            make_uint2(__byte_perm(rr_[0], rr_[1], 0x5410), __byte_perm(rr_[2], rr_[3], 0x5410));
+        *reinterpret_cast<uint2*>(out_bg + at) =
+            make_uint2(__byte_perm(rr_[0], rr_[1], 0x7632), __byte_perm(rr_[2], rr_[3], 0x7632));
     }
     __syncthreads();
     for (int ch = 0; ch < 3; ch++) {
@@ -2047,16 +2065,18 @@ __device__ __forceinline__ void unp_store_block(const uint32_t* ring, uint8_t* _
 // fetched (into registers) one boundary ago is committed to the ring, and the fetch of the next one is
 // issued, so global-memory latency overlaps a whole block of computation.
 template <bool ALIGNED>
-__global__ void __launch_bounds__(kUnpWarps * 32) k_tile_unpredict_s0(const uint16_t* __restrict__ resid, TileGeom g,
+__global__ void __launch_bounds__(kUnpWarps * 32, 3) k_tile_unpredict_s0(const uint16_t* __restrict__ resid, TileGeom g,
                                                                       uint64_t n_tiles, uint8_t* __restrict__ rgb) {
     extern __shared__ uint32_t s_unp[];  // per warp: in ring, out ring, carry row (tile_w words)
     const uint32_t wid = threadIdx.x >> 5, lane = lane_id();
     const uint64_t t = (uint64_t)blockIdx.x * kUnpWarps + wid;
     if (t >= n_tiles) return;
-    const uint32_t per_warp = 2u * 32u * kRingStride + g.tile_w;
+    const uint32_t carry_words = g.tile_w + (g.tile_w + 1u) / 2u;  // (rg | bg << 16) as u32 + g as u16
+    const uint32_t per_warp = 2u * 32u * kRingStride + carry_words;
     uint32_t* ring_in = s_unp + (size_t)wid * per_warp;
     uint32_t* ring_out = ring_in + 32 * kRingStride;
-    uint32_t* carry = ring_out + 32 * kRingStride;
+    uint32_t* carry_rb = ring_out + 32 * kRingStride;  // last row of the previous band
+    uint16_t* carry_g = reinterpret_cast<uint16_t*>(carry_rb + g.tile_w);
     const uint64_t image = t / g.tiles_per_image;
     uint32_t x0, y0, tw, th;
     tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
@@ -2073,8 +2093,8 @@ __global__ void __launch_bounds__(kUnpWarps * 32) k_tile_unpredict_s0(const uint
         const uint32_t y = y_base + lane;
         const bool row_ok = y < th;
         // column 0: L = TL = c/2; they are first used at x == 0 and only change from then on
-        int Lg = 128, Lr = 256, Lb = 256, TLg = 128, TLr = 256, TLb = 256;
-        uint32_t mine = kMidPacked;
+        uint32_t Lg = 128u, TLg = 128u, Lrb = kHalfRB, TLrb = kHalfRB;
+        uint32_t mine_g = 128u, mine_rb = kHalfRB;
         UnpPrefetch pf;
         unp_fetch_block<ALIGNED>(pf, in_g, in_rg, in_bg, y_base, th, tw, 0u);
         for (uint32_t blk = 0; blk < n_blocks + 3u; blk++) {
@@ -2087,22 +2107,34 @@ __global__ void __launch_bounds__(kUnpWarps * 32) k_tile_unpredict_s0(const uint
             for (uint32_t k = 0; k < (uint32_t)kUnpBlock; k++) {
                 const uint32_t step = blk * kUnpBlock + k;
                 const int x = (int)step - (int)lane;
-                uint32_t top = __shfl_up_sync(0xffffffffu, mine, 1);
+                uint32_t Tg = __shfl_up_sync(0xffffffffu, mine_g, 1);
+                uint32_t Trb = __shfl_up_sync(0xffffffffu, mine_rb, 1);
                 const bool in_row = x >= 0 && x < (int)tw;
                 // lane 0's top row is the previous band's last row; row 0 of the tile has T = TL = c/2
-                if (lane == 0) top = (band != 0u && in_row) ? carry[x] : kMidPacked;
+                if (lane == 0) {
+                    const bool have = band != 0u && in_row;
+                    Tg = have ? carry_g[x] : 128u;
+                    Trb = have ? carry_rb[x] : kHalfRB;
+                }
                 if (row_ok && in_row) {
-                    const uint32_t v = my_in[x & 63];
-                    const int Tg = top & 255u, Tr = (top >> 8) & 511u, Tb = (top >> 17) & 511u;
-                    const int vg = ((int)(v & 255u) + p_med_grad(Tg, Lg, TLg) - 128) & 255;
-                    const int vr = ((int)((v >> 8) & 511u) + p_med_grad(Tr, Lr, TLr) - 256) & 511;
-                    const int vb = ((int)((v >> 17) & 511u) + p_med_grad(Tb, Lb, TLb) - 256) & 511;
-                    my_out[x & 63] = (uint32_t)((vr + vg - 256) & 255) | ((uint32_t)vg << 8) |
-                                     ((uint32_t)((vb + vg - 256) & 255) << 16);
-                    mine = (uint32_t)vg | ((uint32_t)vr << 8) | ((uint32_t)vb << 17);
-                    Lg = vg; Lr = vr; Lb = vb;
-                    TLg = Tg; TLr = Tr; TLb = Tb;
-                    if (lane == 31u) carry[x] = mine;
+                    const uint32_t v = my_in[x & 63];  // residuals g | rg << 8 | bg << 17
+                    const uint32_t rg2 = ((v >> 8) & 511u) | ((v >> 17) << 16);
+                    // unprediction of the pure-MED fastpath: (resid + median - c/2) mod c, planes G and (R-G, B-G)
+                    const uint32_t vg = ((v & 255u) + p_med_grad2(Tg, Lg, TLg) - 128u) & 255u;
+                    const uint32_t vrb = __vsub2(__vadd2(rg2, p_med_grad2(Trb, Lrb, TLrb)), kHalfRB) & kMaskRB;
+                    // inverse colour transform: R = rg + g - 256, B = bg + g - 256 (mod 256)
+                    const uint32_t rb8 = __vsub2(__vadd2(vrb, vg * 0x00010001u), kHalfRB) & 0x00ff00ffu;
+                    my_out[x & 63] = rb8 | (vg << 8);  // 0x00BBGGRR
+                    mine_g = vg;
+                    mine_rb = vrb;
+                    Lg = vg;
+                    Lrb = vrb;
+                    TLg = Tg;
+                    TLrb = Trb;
+                    if (lane == 31u) {
+                        carry_g[x] = (uint16_t)vg;
+                        carry_rb[x] = vrb;
+                    }
                 }
             }
         }
