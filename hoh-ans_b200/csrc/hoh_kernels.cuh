@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/hohgpu.h"
 #include "hoh_format.cuh"
 
@@ -2088,13 +2090,52 @@ __global__ void __launch_bounds__(kUnpWarps * 32, 3) k_tile_unpredict_s0(const u
     const uint32_t* my_in = ring_in + lane * kRingStride;
     uint32_t* my_out = ring_out + lane * kRingStride;
 
+    // row 0 of the tile has T = TL = c/2: the carry row starts as the border value
+    for (uint32_t i = lane; i < tw; i += 32) {
+        carry_g[i] = 128;
+        carry_rb[i] = kHalfRB;
+    }
+    __syncwarp();
     for (uint32_t band = 0; band * 32u < th; band++) {
         const uint32_t y_base = band * 32u;
-        const uint32_t y = y_base + lane;
-        const bool row_ok = y < th;
+        const bool row_ok = y_base + lane < th;
         // column 0: L = TL = c/2; they are first used at x == 0 and only change from then on
         uint32_t Lg = 128u, TLg = 128u, Lrb = kHalfRB, TLrb = kHalfRB;
         uint32_t mine_g = 128u, mine_rb = kHalfRB;
+        // One wavefront step.  FULL = every lane is inside its row (the steady state: 14 of 19 blocks of a
+        // 256-wide tile), so there is nothing to predicate; rows past the bottom of the tile compute
+        // harmless garbage there (their ring rows are never written back).
+        auto step_fn = [&](uint32_t step, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int x = (int)step - (int)lane;
+            const uint32_t tg_up = __shfl_up_sync(0xffffffffu, mine_g, 1);
+            const uint32_t trb_up = __shfl_up_sync(0xffffffffu, mine_rb, 1);
+            const bool in_row = FULL || (x >= 0 && x < (int)tw);
+            const uint32_t xc = in_row ? (uint32_t)x : 0u;
+            // lane 0's top row is the previous band's last row (carry), the others get it from the lane above
+            const uint32_t Tg = lane == 0 ? (uint32_t)carry_g[xc] : tg_up;
+            const uint32_t Trb = lane == 0 ? carry_rb[xc] : trb_up;
+            if (FULL || (row_ok && in_row)) {
+                const uint32_t v = my_in[xc & 63];  // residuals g | rg << 8 | bg << 17
+                const uint32_t rg2 = ((v >> 8) & 511u) | ((v >> 17) << 16);
+                // unprediction of the pure-MED fastpath: (resid + median - c/2) mod c, planes G and (R-G, B-G)
+                const uint32_t vg = ((v & 255u) + p_med_grad2(Tg, Lg, TLg) - 128u) & 255u;
+                const uint32_t vrb = __vsub2(__vadd2(rg2, p_med_grad2(Trb, Lrb, TLrb)), kHalfRB) & kMaskRB;
+                // inverse colour transform: R = rg + g - 256, B = bg + g - 256 (mod 256)
+                const uint32_t rb8 = __vsub2(__vadd2(vrb, vg * 0x00010001u), kHalfRB) & 0x00ff00ffu;
+                my_out[xc & 63] = rb8 | (vg << 8);  // 0x00BBGGRR
+                mine_g = vg;
+                mine_rb = vrb;
+                Lg = vg;
+                Lrb = vrb;
+                TLg = Tg;
+                TLrb = Trb;
+                if (lane == 31u) {
+                    carry_g[xc] = (uint16_t)vg;
+                    carry_rb[xc] = vrb;
+                }
+            }
+        };
         UnpPrefetch pf;
         unp_fetch_block<ALIGNED>(pf, in_g, in_rg, in_bg, y_base, th, tw, 0u);
         for (uint32_t blk = 0; blk < n_blocks + 3u; blk++) {
@@ -2103,39 +2144,13 @@ __global__ void __launch_bounds__(kUnpWarps * 32, 3) k_tile_unpredict_s0(const u
             if (blk < n_blocks) unp_commit_block(pf, ring_in, blk);
             if (blk + 1u < n_blocks) unp_fetch_block<ALIGNED>(pf, in_g, in_rg, in_bg, y_base, th, tw, blk + 1u);
             __syncwarp();
+            const uint32_t s0 = blk * kUnpBlock;
+            if (s0 >= 31u && s0 + kUnpBlock <= tw) {
 #pragma unroll 4
-            for (uint32_t k = 0; k < (uint32_t)kUnpBlock; k++) {
-                const uint32_t step = blk * kUnpBlock + k;
-                const int x = (int)step - (int)lane;
-                uint32_t Tg = __shfl_up_sync(0xffffffffu, mine_g, 1);
-                uint32_t Trb = __shfl_up_sync(0xffffffffu, mine_rb, 1);
-                const bool in_row = x >= 0 && x < (int)tw;
-                // lane 0's top row is the previous band's last row; row 0 of the tile has T = TL = c/2
-                if (lane == 0) {
-                    const bool have = band != 0u && in_row;
-                    Tg = have ? carry_g[x] : 128u;
-                    Trb = have ? carry_rb[x] : kHalfRB;
-                }
-                if (row_ok && in_row) {
-                    const uint32_t v = my_in[x & 63];  // residuals g | rg << 8 | bg << 17
-                    const uint32_t rg2 = ((v >> 8) & 511u) | ((v >> 17) << 16);
-                    // unprediction of the pure-MED fastpath: (resid + median - c/2) mod c, planes G and (R-G, B-G)
-                    const uint32_t vg = ((v & 255u) + p_med_grad2(Tg, Lg, TLg) - 128u) & 255u;
-                    const uint32_t vrb = __vsub2(__vadd2(rg2, p_med_grad2(Trb, Lrb, TLrb)), kHalfRB) & kMaskRB;
-                    // inverse colour transform: R = rg + g - 256, B = bg + g - 256 (mod 256)
-                    const uint32_t rb8 = __vsub2(__vadd2(vrb, vg * 0x00010001u), kHalfRB) & 0x00ff00ffu;
-                    my_out[x & 63] = rb8 | (vg << 8);  // 0x00BBGGRR
-                    mine_g = vg;
-                    mine_rb = vrb;
-                    Lg = vg;
-                    Lrb = vrb;
-                    TLg = Tg;
-                    TLrb = Trb;
-                    if (lane == 31u) {
-                        carry_g[x] = (uint16_t)vg;
-                        carry_rb[x] = vrb;
-                    }
-                }
+                for (uint32_t k = 0; k < (uint32_t)kUnpBlock; k++) step_fn(s0 + k, std::true_type{});
+            } else {
+#pragma unroll 4
+                for (uint32_t k = 0; k < (uint32_t)kUnpBlock; k++) step_fn(s0 + k, std::false_type{});
             }
         }
         __syncwarp();
