@@ -72,27 +72,81 @@ def fill_images(dst, first_seed, count, w, h, threads):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region.  NVML is polled from a thread every ~2 ms (the
+    timed region of a default run is ~150 ms, shorter than one nvidia-smi start-up); when NVML cannot be
+    loaded an `nvidia-smi -lms` child started at construction is used and only the lines it printed between
+    start() and stop() are counted."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
+        import threading
         self.idx = gpu_index
+        self.sm, self.reason_bits, self.mx = [], 0, None
+        self.recording = False
+        self.alive = True
+        self.nvml = None
         self.proc = None
-        self.path = f"/tmp/hoh_clocks_{os.getpid()}.csv"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = gpu_index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nvml = None
+            self.path = f"/tmp/hoh_clocks_{os.getpid()}.csv"
+            try:
+                self.out = open(self.path, "w")
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                              "--format=csv,noheader,nounits", "-lms", "20"],
+                                             stdout=self.out, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        while self.alive:
+            if self.recording:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                    try:
+                        self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.out = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=self.out, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        if self.proc:
+            self.out.flush()
+            self.pos0 = os.path.getsize(self.path)
+        self.recording = True
 
     def stop(self):
+        self.recording = False
+        self.alive = False
+        if self.nvml:
+            self.thread.join(timeout=2)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["no samples"]}
+            reasons = sorted(k for k, bit in self.BITS.items() if self.reason_bits & bit)
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        pos1 = os.path.getsize(self.path)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -101,7 +155,10 @@ class ClockSampler:
         self.out.close()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
+        with open(self.path) as fh:
+            fh.seek(self.pos0)
+            text = fh.read(max(0, pos1 - self.pos0))
+        for line in text.splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -120,7 +177,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -302,6 +359,7 @@ def main():
         torch.cuda.synchronize()
 
     # warm-up + correctness of what is being timed
+    clocks = ClockSampler(local_rank)
     for _ in range(max(warmup, 1)):
         encode_dev()
         decode_dev()
@@ -315,7 +373,6 @@ def main():
     del back
 
     # timed region: device resident
-    clocks = ClockSampler(local_rank)
     launches0 = g.launch_count()
     barrier()
     clocks.start()

@@ -21,7 +21,7 @@ namespace {
 enum Slot {
     S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
     S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
-    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_COUNT
+    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_COUNT
 };
 
 struct Buf {
@@ -882,7 +882,7 @@ int hoh_predict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pl
     if (!ctx || !d_planes || !d_resid || w <= 0 || h <= 0 || depth < 1 || depth > 9) return HOH_E_ARG;
     if (!n_planes) return HOH_OK;
     k_predict_fastpath<<<grid_cap((uint64_t)n_planes * w * h, 256), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h,
-                                                                                          depth, d_resid);
+                                                                                          depth, d_resid, (uint64_t)w * h);
     LAUNCHED("k_predict_fastpath");
     return HOH_OK;
 }
@@ -915,7 +915,7 @@ int hoh_predict_all_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes,
     TRY(scratch_t(ctx, S_TOP, n_planes * (size_t)w, &top));
     TRY(scratch_t(ctx, S_BP, n_planes * (size_t)w, &bp));
     k_raster_walk<false><<<blocks_for(n_planes, 64), 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, x_tiles,
-                                                                          y_tiles, d_tile_maps, nullptr, d_resid, top, bp);
+                                                                          y_tiles, d_tile_maps, nullptr, d_resid, top, bp, (uint64_t)w * h);
     LAUNCHED("k_raster_walk<predict>");
     return HOH_OK;
 }
@@ -932,7 +932,7 @@ int hoh_unpredict_all_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_planes
     TRY(scratch_t(ctx, S_TOP, n_planes * (size_t)w, &top));
     TRY(scratch_t(ctx, S_BP, n_planes * (size_t)w, &bp));
     k_raster_walk<true><<<blocks_for(n_planes, 64), 64, 0, ctx->stream>>>(d_resid, n_planes, w, h, depth, x_tiles,
-                                                                         y_tiles, d_tile_maps, d_backref, d_planes, top, bp);
+                                                                         y_tiles, d_tile_maps, d_backref, d_planes, top, bp, (uint64_t)w * h);
     LAUNCHED("k_raster_walk<unpredict>");
     return HOH_OK;
 }
@@ -959,8 +959,12 @@ int hoh_predict_section_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pla
     return HOH_OK;
 }
 
-int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
-                             int mode, uint16_t* d_tile_maps, uint8_t* d_index_lists, uint16_t* d_resid) {
+} // extern "C" (reopened below)
+namespace {
+// resid_stride: u16 elements between consecutive residual planes (>= w*h)
+int predictor_search_impl(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
+                          int mode, uint16_t* d_tile_maps, uint8_t* d_index_lists, uint16_t* d_resid,
+                          uint64_t resid_stride) {
     if (!ctx || !d_planes || !d_resid || !d_tile_maps || !d_index_lists || w <= 0 || h <= 0 || depth < 1 ||
         depth > 9 || mode < 1)
         return HOH_E_ARG;
@@ -986,11 +990,12 @@ int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pl
     TRY(scratch_t(ctx, S_BP, n_planes * (size_t)w, &bp));
     TRY(cost_table_for(ctx, per, &e_tab, &e_len));
     CK(cudaMemcpyAsync(masks, kStockMasks, sizeof kStockMasks, cudaMemcpyHostToDevice, ctx->stream));
-    k_predict_fastpath<<<grid_cap(n_planes * per, 256), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, d_resid);
+    k_predict_fastpath<<<grid_cap(n_planes * per, 256), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, d_resid,
+                                                                                resid_stride);
     LAUNCHED("k_predict_fastpath");
     const int passes = mode > 2 ? 2 : 1;  // layer_encode.hpp:215
     for (int pass = 0; pass < passes; pass++) {
-        k_plane_histogram<<<(unsigned)n_planes, 256, 0, ctx->stream>>>(d_resid, (uint32_t)per, depth, hist);
+        k_plane_histogram<<<(unsigned)n_planes, 256, 0, ctx->stream>>>(d_resid, (uint32_t)per, depth, hist, resid_stride);
         LAUNCHED("k_plane_histogram");
         k_cost_from_hist<<<blocks_for(n_planes * (uint64_t)c, 256), 256, 0, ctx->stream>>>(hist, n_planes * (uint64_t)c,
                                                                                           e_tab, e_len, cost);
@@ -1003,8 +1008,113 @@ int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pl
             sums, n_planes * (uint64_t)cells, n_masks, masks, d_tile_maps, d_index_lists);
         LAUNCHED("k_pick_masks");
         k_raster_walk<false><<<blocks_for(n_planes, 64), 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt,
-                                                                              d_tile_maps, nullptr, d_resid, top, bp);
+                                                                              d_tile_maps, nullptr, d_resid, top, bp, resid_stride);
         LAUNCHED("k_raster_walk<predict>");
+    }
+    return HOH_OK;
+}
+}  // namespace
+extern "C" {
+
+int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
+                             int mode, uint16_t* d_tile_maps, uint8_t* d_index_lists, uint16_t* d_resid) {
+    return predictor_search_impl(ctx, d_planes, n_planes, w, h, depth, mode, d_tile_maps, d_index_lists, d_resid,
+                                 (uint64_t)w * h);
+}
+
+// -------------------------------------------------------------------------------------------------
+// layer_encode.hpp:11 for many planes
+// -------------------------------------------------------------------------------------------------
+static LayerGeom layer_geom(int w, int h, int depth, int mode) {
+    LayerGeom lg;
+    lg.per = (uint32_t)w * h;
+    lg.per_pad = (lg.per + 7u) & ~7u;
+    lg.xt = (w + 39) / 40;
+    lg.yt = (h + 39) / 40;
+    lg.cells = (mode >= 1 && (lg.xt > 1 || lg.yt > 1)) ? lg.xt * lg.yt : 0u;  // layer_encode.hpp:126-132
+    lg.cells_pad = (lg.cells + 7u) & ~7u;
+    lg.depth = depth;
+    lg.mode = mode;
+    lg.slab = (uint32_t)hoh_enc_slab_bytes(lg.per > lg.cells ? lg.per : lg.cells, HOH_MAX_PROB_BITS);
+    lg.out_cap = (lg.slab + kLayerHdrCap + 2048u + 15u) & ~15u;
+    return lg;
+}
+
+size_t hoh_layer_encode_out_bytes(size_t n_planes, int w, int h, int depth, int mode) {
+    const LayerGeom lg = layer_geom(w, h, depth, mode);
+    return n_planes * ((size_t)kLayerSlots * lg.slab + lg.out_cap);
+}
+
+int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
+                           int mode, uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
+                           uint8_t* d_packed, size_t packed_cap, uint64_t* d_packed_off) {
+    if (!ctx || !d_planes || !d_out || !d_results || w <= 0 || h <= 0 || depth < 1 || depth > 9 || mode < 0 || mode > 4)
+        return HOH_E_ARG;
+    if (n_planes == 0) return HOH_OK;
+    if ((uint64_t)w * h >= (1u << 21)) return HOH_E_UNSUPPORTED;  // varint.hpp:39-45
+    const LayerGeom lg = layer_geom(w, h, depth, mode);
+    if (lg.xt > 256 || lg.yt > 256) return HOH_E_UNSUPPORTED;    // grid size bytes (layer_encode.hpp:276-277)
+    if (out_bytes < hoh_layer_encode_out_bytes(n_planes, w, h, depth, mode)) return HOH_E_CAPACITY;
+    const size_t n = n_planes;
+    uint16_t *syms, *maps;
+    uint8_t *idx, *hdr;
+    uint32_t *n_used, *hdr_len, *kept, *best;
+    int32_t* status;
+    hoh_enc_stream* streams;
+    hoh_stream_result *rr, *res;
+    TRY(scratch_t(ctx, S_RESID, 2 * n * lg.per_pad + n * lg.cells_pad, &syms));
+    TRY(scratch_t(ctx, S_L_MAPS, n * (lg.cells ? lg.cells : 1), &maps));
+    TRY(scratch_t(ctx, S_L_IDX, n * (lg.cells ? lg.cells : 1), &idx));
+    TRY(scratch_t(ctx, S_L_HDR, n * kLayerHdrCap, &hdr));
+    TRY(scratch_t(ctx, S_L_U32, 4 * n, &n_used));
+    hdr_len = n_used + n;
+    kept = hdr_len + n;
+    best = kept + n;
+    TRY(scratch_t(ctx, S_L_STATUS, n, &status));
+    TRY(scratch_t(ctx, S_STREAMS, 3 * n, &streams));
+    TRY(scratch_t(ctx, S_L_RR, 3 * n, &rr));
+    TRY(scratch_t(ctx, S_L_RES, (size_t)kLayerSlots * n, &res));
+    CK(cudaMemsetAsync(res, 0, (size_t)kLayerSlots * n * sizeof(hoh_stream_result), ctx->stream));
+    uint16_t* resid0 = syms;
+    uint16_t* resid1 = syms + n * lg.per_pad;
+    const uint32_t range = 1u << depth;
+    auto run_round = [&](int round, size_t count, uint32_t max_range, uint32_t max_pb) -> int {
+        k_layer_streams<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, n_used, res, streams);
+        LAUNCHED("k_layer_streams");
+        TRY(hoh_encode_entropy_batch(ctx, streams, count, syms, d_out, rr, max_range, max_pb, lg.per));
+        k_layer_scatter<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(n, round, rr, res);
+        LAUNCHED("k_layer_scatter");
+        return HOH_OK;
+    };
+    // layer_encode.hpp:63-120: fastpath residuals, prob_bits 15
+    k_predict_fastpath<<<grid_cap(n * (uint64_t)lg.per, 256), 256, 0, ctx->stream>>>(d_planes, n, w, h, depth, resid0,
+                                                                                  lg.per_pad);
+    LAUNCHED("k_predict_fastpath");
+    TRY(run_round(0, n, range, 15));
+    if (mode >= 1) {
+        if (lg.cells)  // :126-272
+            TRY(predictor_search_impl(ctx, d_planes, n, w, h, depth, mode, maps, idx, resid1, lg.per_pad));
+        k_layer_headers<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(lg, n, idx, syms, n_used, hdr, hdr_len);
+        LAUNCHED("k_layer_headers");
+        if (lg.cells) TRY(run_round(1, n, 14, 8));  // :308-317
+        TRY(run_round(2, 2 * n, range, 16));         // :334-353
+        TRY(run_round(3, 3 * n, range, 19));         // :355-392
+    } else {
+        k_layer_headers<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(lg, n, idx, syms, n_used, hdr, hdr_len);
+        LAUNCHED("k_layer_headers");
+    }
+    k_layer_decide<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(lg, n, res, kept, best, status);
+    LAUNCHED("k_layer_decide");
+    const uint64_t out_base = (uint64_t)n * kLayerSlots * lg.slab;
+    k_layer_assemble<<<(unsigned)n, 256, 0, ctx->stream>>>(lg, hdr, hdr_len, res, kept, best, status, d_out, d_out, out_base,
+                                                           d_results);
+    LAUNCHED("k_layer_assemble");
+    if (d_packed) {
+        if (!d_packed_off) return HOH_E_ARG;
+        k_scan_sizes<<<1, 1024, 0, ctx->stream>>>(d_results, (uint32_t)n, d_packed_off);
+        LAUNCHED("k_scan_sizes");
+        k_gather_streams<<<(unsigned)n, 256, 0, ctx->stream>>>(d_results, d_out, d_packed_off, d_packed, packed_cap);
+        LAUNCHED("k_gather_streams");
     }
     return HOH_OK;
 }

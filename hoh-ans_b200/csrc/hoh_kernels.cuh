@@ -1431,8 +1431,9 @@ __global__ void k_add_green(const uint16_t* __restrict__ g, const uint16_t* __re
 // =================================================================================================
 // channelpredict_fastpath — prediction.hpp:6-44.  Per-pixel data parallel on planes.
 // =================================================================================================
+// out_stride: u16 elements between consecutive residual planes (>= w*h)
 __global__ void k_predict_fastpath(const uint16_t* __restrict__ planes, uint64_t n_planes, int w, int h,
-                                   int depth, uint16_t* __restrict__ resid) {
+                                   int depth, uint16_t* __restrict__ resid, uint64_t out_stride) {
     const int c = 1 << depth, half = c >> 1;
     const uint64_t per = (uint64_t)w * h, total = per * n_planes;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1442,7 +1443,7 @@ __global__ void k_predict_fastpath(const uint16_t* __restrict__ planes, uint64_t
         const int L = x ? p[-1] : half;
         const int T = y ? p[-w] : half;
         const int TL = (x && y) ? p[-w - 1] : half;
-        resid[i] = (uint16_t)(((int)p[0] - p_med_grad(T, L, TL) + half + c) % c);
+        resid[(i / per) * out_stride + at] = (uint16_t)(((int)p[0] - p_med_grad(T, L, TL) + half + c) % c);
     }
 }
 
@@ -1567,7 +1568,7 @@ __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__
                                                     const uint16_t* __restrict__ tile_maps,
                                                     const uint16_t* __restrict__ backref,
                                                     uint16_t* __restrict__ out, uint16_t* __restrict__ top_s,
-                                                    uint8_t* __restrict__ bp_s) {
+                                                    uint8_t* __restrict__ bp_s, uint64_t out_stride) {
     const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (p >= n_planes) return;
     const int c = 1 << depth, half = c >> 1;
@@ -1575,7 +1576,7 @@ __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__
     const uint64_t per = (uint64_t)w * h;
     const uint16_t* src = in + p * per;
     const uint16_t* br = (INVERSE && backref) ? backref + p * per : nullptr;
-    uint16_t* dst = out + p * per;
+    uint16_t* dst = out + p * out_stride;
     const uint16_t* tmap = tile_maps + p * (uint64_t)x_tiles * y_tiles;
     uint16_t* top = top_s + p * (uint64_t)w;
     uint8_t* bp = bp_s + p * (uint64_t)w;
@@ -1699,12 +1700,12 @@ __global__ void __launch_bounds__(64) k_section(const uint16_t* __restrict__ pla
 
 // layer_encode.hpp:133-144 / :217-225: +1-smoothed histogram of a residual plane.  One CTA per plane.
 __global__ void __launch_bounds__(256) k_plane_histogram(const uint16_t* __restrict__ resid, uint32_t per,
-                                                         int depth, uint32_t* __restrict__ hist) {
+                                                         int depth, uint32_t* __restrict__ hist, uint64_t stride) {
     __shared__ uint32_t s_h[kFreqRow];
     const int c = 1 << depth;
     for (int i = threadIdx.x; i < c; i += blockDim.x) s_h[i] = 1;  // the +1 smoothing
     __syncthreads();
-    const uint16_t* r = resid + (uint64_t)blockIdx.x * per;
+    const uint16_t* r = resid + (uint64_t)blockIdx.x * stride;
     for (uint32_t i = threadIdx.x; i < per; i += blockDim.x) atomicAdd(&s_h[r[i] & (c - 1)], 1u);
     __syncthreads();
     for (int i = threadIdx.x; i < c; i += blockDim.x) hist[(uint64_t)blockIdx.x * c + i] = s_h[i];
@@ -2155,6 +2156,192 @@ __global__ void __launch_bounds__(kUnpWarps * 32, 3) k_tile_unpredict_s0(const u
         }
         __syncwarp();
     }
+}
+
+// =================================================================================================
+// layer_encode.hpp:11-412 for many planes — the decision sequence of the channel codec replayed on
+// the device around the batched kernels above.  These small kernels are the glue: descriptors for each
+// round of entropy coding, the predictor-map header, the "which buffer wins" logic (including the
+// stale-buffer behaviour D7) and the final assembly of every channel payload.
+// =================================================================================================
+constexpr int kLayerSlots = 7;   // per plane: A (fastpath, 15 bits), B (predictor-index map), C (16), D (15), E, F, G
+constexpr int kLayerHdrCap = 48;  // 0x10 + x_tiles-1 + y_tiles-1 + count + 14 masks * 2
+
+struct LayerGeom {
+    uint32_t per;         // w * h
+    uint32_t per_pad;     // rounded up to 8 symbols
+    uint32_t cells;       // predictor grid cells (0 when the plane is a single cell or mode == 0)
+    uint32_t cells_pad;
+    uint32_t xt, yt;
+    uint32_t depth, mode;
+    uint32_t slab;        // bytes of one candidate slab
+    uint32_t out_cap;     // bytes of one assembled channel payload
+};
+
+// Round descriptors.  round 0: A = fastpath residuals at 15 bits.  round 1: B = predictor-index map at 8
+// bits (range = number of masks used).  round 2: C, D = final residuals at 16 and 15 bits.  round 3: E, F, G
+// = 17, 18, 19 bits if C beat D (layer_encode.hpp:359-374) else 14, 13, 12 (:376-392).
+__global__ void k_layer_streams(LayerGeom lg, uint64_t n_planes, int round, const uint32_t* __restrict__ n_used,
+                                const hoh_stream_result* __restrict__ results, hoh_enc_stream* __restrict__ streams) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint32_t per_round = round == 0 ? 1u : (round == 1 ? 1u : (round == 2 ? 2u : 3u));
+    if (i >= n_planes * per_round) return;
+    const uint64_t p = i / per_round;
+    const uint32_t k = (uint32_t)(i % per_round);
+    const uint64_t resid0 = p * lg.per_pad, resid1 = (n_planes + p) * (uint64_t)lg.per_pad;
+    const uint64_t idx_sym = 2u * n_planes * (uint64_t)lg.per_pad + p * lg.cells_pad;
+    const bool searched = lg.cells != 0u;
+    hoh_enc_stream st;
+    st.prefix_len = 0;
+    for (int b = 0; b < 8; b++) st.prefix[b] = 0;
+    st.reserved = 0;
+    st.range = 1u << lg.depth;
+    st.n = lg.per;
+    uint32_t slot;
+    if (round == 0) {
+        slot = 0;
+        st.sym_off = resid0;
+        st.prob_bits = 15;
+    } else if (round == 1) {
+        slot = 1;
+        st.sym_off = idx_sym;
+        st.n = lg.cells;
+        st.range = n_used[p];
+        st.prob_bits = 8;
+    } else if (round == 2) {
+        slot = 2 + k;
+        st.sym_off = searched ? resid1 : resid0;
+        st.prob_bits = k == 0 ? 16u : 15u;
+    } else {
+        slot = 4 + k;
+        st.sym_off = searched ? resid1 : resid0;
+        const hoh_stream_result c = results[p * kLayerSlots + 2], d = results[p * kLayerSlots + 3];
+        const bool up = c.size < d.size;  // layer_encode.hpp:357
+        st.prob_bits = up ? 17u + k : 14u - k;
+    }
+    st.out_off = (p * kLayerSlots + slot) * (uint64_t)lg.slab;
+    st.out_cap = lg.slab;
+    streams[round == 2 ? p * 2 + k : (round == 3 ? p * 3 + k : p)] = st;
+}
+
+// After the predictor search: channel header bytes + the predictor-index symbols (layer_encode.hpp:276-306).
+__global__ void k_layer_headers(LayerGeom lg, uint64_t n_planes, const uint8_t* __restrict__ index_lists,
+                                uint16_t* __restrict__ symbols, uint32_t* __restrict__ n_used,
+                                uint8_t* __restrict__ hdr, uint32_t* __restrict__ hdr_len) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_planes) return;
+    uint8_t* h = hdr + p * kLayerHdrCap;
+    uint32_t at = 0;
+    h[at++] = 0x10;  // layer_encode.hpp:57: prediction on, no compaction
+    if (lg.cells == 0u) {  // :320-325 single predictor 0x0010
+        h[at++] = 0;
+        h[at++] = 0;
+        h[at++] = 0x00;
+        h[at++] = 0x10;
+        n_used[p] = 1;
+        hdr_len[p] = at;
+        return;
+    }
+    const uint16_t masks[14] = {0x0001, 0x0002, 0x0020, 0x0010, 0xffbf, 0x0003, 0xfffd,
+                                0xfffb, 0xfff7, 0xffef, 0xffdf, 0xff7f, 0xfdff, 0xffff};
+    const uint8_t* idx = index_lists + p * lg.cells;
+    uint32_t used = 0;
+    for (uint32_t c = 0; c < lg.cells; c++) used |= 1u << idx[c];
+    uint8_t remap[14];
+    uint32_t count = 0;
+    h[at++] = (uint8_t)(lg.xt - 1);
+    h[at++] = (uint8_t)(lg.yt - 1);
+    const uint32_t count_at = at++;
+    for (uint32_t m = 0; m < 14; m++)
+        if (used & (1u << m)) {  // :292-304 masks actually used, in stock order
+            h[at++] = (uint8_t)(masks[m] >> 8);
+            h[at++] = (uint8_t)(masks[m] & 0xff);
+            remap[m] = (uint8_t)count++;
+        }
+    h[count_at] = (uint8_t)count;
+    uint16_t* sym = symbols + 2u * n_planes * (uint64_t)lg.per_pad + p * lg.cells_pad;
+    for (uint32_t c = 0; c < lg.cells; c++) sym[c] = remap[idx[c]];
+    n_used[p] = count;
+    hdr_len[p] = at;
+}
+
+// layer_encode.hpp:108-120, 326-398: which candidate's bytes are emitted and how many of them.
+__global__ void k_layer_decide(LayerGeom lg, uint64_t n_planes, const hoh_stream_result* __restrict__ results,
+                               uint32_t* __restrict__ kept_slot, uint32_t* __restrict__ best_size,
+                               int32_t* __restrict__ status) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_planes) return;
+    const hoh_stream_result* r = results + p * kLayerSlots;
+    const uint64_t bits = (uint64_t)lg.depth * lg.per;
+    uint32_t best = (uint32_t)((bits + bits % 8 + 1024) / 8);  // :22
+    uint32_t kept = 0xffffffffu;  // nothing kept: the reference would emit an uninitialised buffer
+    int32_t st = r[0].status;
+    if (r[0].size < best) {  // :115-120
+        best = r[0].size;
+        kept = 0;
+    }
+    if (lg.mode) {
+        if (lg.cells) st = st ? st : r[1].status;
+        for (int k = 2; k < kLayerSlots; k++) st = st ? st : r[k].status;
+        const bool up = r[2].size < r[3].size;
+        const uint32_t first = up ? r[2].size : r[3].size;
+        if (first < best) best = first;  // size updated, buffers NOT swapped (D7): kept stays
+        for (int k = 0; k < 3; k++)
+            if (r[4 + k].size < best) {
+                best = r[4 + k].size;
+                kept = 4 + k;
+            }
+    }
+    kept_slot[p] = kept;
+    best_size[p] = best;
+    status[p] = st;
+}
+
+// Channel payload = header bytes | predictor-index stream | best_size bytes of the kept candidate.
+// One CTA per plane.
+__global__ void __launch_bounds__(256) k_layer_assemble(LayerGeom lg, const uint8_t* __restrict__ hdr,
+                                                        const uint32_t* __restrict__ hdr_len,
+                                                        const hoh_stream_result* __restrict__ results,
+                                                        const uint32_t* __restrict__ kept_slot,
+                                                        const uint32_t* __restrict__ best_size,
+                                                        const int32_t* __restrict__ status,
+                                                        const uint8_t* __restrict__ cand, uint8_t* __restrict__ out,
+                                                        uint64_t out_base, hoh_stream_result* __restrict__ final_results) {
+    const uint64_t p = blockIdx.x;
+    uint8_t* dst = out + out_base + p * (uint64_t)lg.out_cap;
+    const hoh_stream_result* r = results + p * kLayerSlots;
+    uint32_t at = hdr_len[p];
+    for (uint32_t i = threadIdx.x; i < at; i += blockDim.x) dst[i] = hdr[p * kLayerHdrCap + i];
+    if (lg.cells) {  // :308-317 the predictor-index stream follows the masks
+        const uint8_t* src = cand + r[1].start;
+        for (uint32_t i = threadIdx.x; i < r[1].size; i += blockDim.x) dst[at + i] = src[i];
+        at += r[1].size;
+    }
+    const uint32_t kept = kept_slot[p], best = best_size[p];
+    const uint32_t have = kept == 0xffffffffu ? 0u : r[kept].size;
+    const uint8_t* src = kept == 0xffffffffu ? cand : cand + r[kept].start;
+    for (uint32_t i = threadIdx.x; i < best; i += blockDim.x) dst[at + i] = i < have ? src[i] : (uint8_t)0;
+    if (threadIdx.x == 0) {
+        hoh_stream_result fr;
+        fr.start = out_base + p * (uint64_t)lg.out_cap;
+        fr.size = at + best;
+        fr.status = status[p];
+        fr.payload_bytes = best;
+        fr.stored = kept;
+        final_results[p] = fr;
+    }
+}
+
+// round-local result order -> results[plane * kLayerSlots + slot]
+__global__ void k_layer_scatter(uint64_t n_planes, int round, const hoh_stream_result* __restrict__ rr,
+                                hoh_stream_result* __restrict__ results) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint32_t per_round = round == 2 ? 2u : (round == 3 ? 3u : 1u);
+    if (i >= n_planes * per_round) return;
+    const uint64_t p = i / per_round;
+    const uint32_t k = (uint32_t)(i % per_round);
+    const uint32_t slot = round == 0 ? 0u : (round == 1 ? 1u : (round == 2 ? 2u + k : 4u + k));
+    results[p * kLayerSlots + slot] = rr[i];
 }
 
 }  // namespace hohk

@@ -111,6 +111,8 @@ SIGNATURES = {
     "hoh_unpredict_all_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "hoh_predict_section_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _int, _vp, _int, _vp, _u32, _vp]),
     "hoh_predictor_search_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "hoh_layer_encode_out_bytes": (_sz, [_sz, _int, _int, _int, _int]),
+    "hoh_layer_encode_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _sz, _vp, _vp, _sz, _vp]),
     "hoh_encode_entropy": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _u32, C.POINTER(_sz), C.POINTER(_int)]),
     "hoh_encode_entropy_8bit": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _u32, C.POINTER(_sz), C.POINTER(_int)]),
     "hoh_decode_entropy": (_int, [_vp, _vp, _sz, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz), C.c_uint,
@@ -464,6 +466,30 @@ class HohGpu:
             for b in (d_rgb, d_out, d_res, d_packed, d_off):
                 b.free()
         return packed, off, res
+
+    def layer_encode_batch(self, planes, n_planes, w, h, depth, mode):
+        """layer_encode.hpp:11 for n_planes planes of the same shape -> list of (payload bytes, status, kept slot)."""
+        planes = np.ascontiguousarray(planes, dtype=np.uint16).ravel()
+        assert planes.size == n_planes * w * h
+        out_bytes = int(self.lib.hoh_layer_encode_out_bytes(n_planes, w, h, depth, mode))
+        d_pl = self.alloc(planes.nbytes).upload(planes)
+        d_out = self.alloc(out_bytes)
+        d_res = self.alloc(n_planes * RESULT_DT.itemsize)
+        packed_cap = planes.nbytes * 2 + 4096 * n_planes
+        d_packed = self.alloc(packed_cap)
+        d_off = self.alloc((n_planes + 1) * 8)
+        try:
+            self._ck(self.lib.hoh_layer_encode_batch(self.ctx, d_pl.ptr, n_planes, w, h, depth, mode, d_out.ptr,
+                                                     out_bytes, d_res.ptr, d_packed.ptr, packed_cap, d_off.ptr),
+                     "hoh_layer_encode_batch")
+            off = d_off.download(np.uint64, n_planes + 1)
+            res = d_res.download(RESULT_DT, n_planes)
+            packed = d_packed.download(np.uint8, int(off[-1]))
+        finally:
+            for b in (d_pl, d_out, d_res, d_packed, d_off):
+                b.free()
+        return [(packed[int(off[i]):int(off[i + 1])].tobytes(), int(res[i]["status"]), int(res[i]["stored"]))
+                for i in range(n_planes)]
 
     def decode_images_s0(self, packed, offsets, n_images, width, height):
         """Host-buffer convenience over hoh_decode_images_s0 -> (rgb, per-stream status)."""

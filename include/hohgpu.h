@@ -259,6 +259,18 @@ int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pl
                              int depth, int mode, uint16_t* d_tile_maps, uint8_t* d_index_lists,
                              uint16_t* d_resid);
 
+/* layer_encode.hpp:11 for n_planes planes of the same geometry (w x h, depth, cruncher mode 0..4, all
+ * NUKE == 0): the reference's decision sequence — which candidates are entropy-coded, in which order,
+ * which buffer is finally emitted, including the stale-buffer behaviour of SURVEY D7 — replayed with the
+ * batched kernels (fastpath residuals, predictor search, up to seven entropy-coding passes per plane).
+ * d_results[p] (start, size) locates plane p's channel payload in d_out (capacity out_bytes >=
+ * hoh_layer_encode_out_bytes); .stored holds the index of the candidate whose bytes were kept.
+ * If d_packed != NULL the payloads are also gathered back to back (d_packed_off: n_planes+1 offsets). */
+size_t hoh_layer_encode_out_bytes(size_t n_planes, int w, int h, int depth, int mode);
+int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
+                           int mode, uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
+                           uint8_t* d_packed, size_t packed_cap, uint64_t* d_packed_off);
+
 /* ------------------------------------------------------------------------------------------ */
 /* (i) compat shims — host pointers, one reference call each                                    */
 /* ------------------------------------------------------------------------------------------ */

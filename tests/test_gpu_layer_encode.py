@@ -106,3 +106,46 @@ def test_layer_encode_random_vs_oracle():
         want, _ = ol.orc_layer_encode(plane, w, h, depth, mode)
         got = gpu_layer_encode(g, plane, w, h, depth, mode)
         assert got == want.tobytes(), (it, w, h, depth, mode)
+
+
+def _smooth_planes(rng, n, w, h, depth):
+    yy, xx = np.mgrid[0:h, 0:w]
+    c = 1 << depth
+    out = []
+    for i in range(n):
+        f = 7.0 + 3.0 * (i % 5)
+        noise = rng.normal(0, 0.5 + (i % 4) * 2.0, (h, w))
+        out.append(np.clip(np.rint((np.sin(xx / f) + np.cos(yy / (f / 2))) * c / 5 + c / 2 + noise), 0, c - 1)
+                   .astype(np.uint16).ravel())
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("w,h,depth,mode,n", [(96, 64, 8, 1, 5), (100, 90, 9, 2, 4), (128, 128, 8, 3, 3),
+                                              (64, 100, 9, 4, 3), (33, 27, 8, 2, 6), (81, 41, 8, 0, 4),
+                                              (41, 43, 9, 1, 3)])
+def test_layer_encode_batch_vs_oracle(w, h, depth, mode, n):
+    """hoh_layer_encode_batch: the whole of layer_encode.hpp:11-412 on the device for n planes at once,
+    byte-identical to the oracle's layer_encode plane by plane (odd plane sizes exercise the padded
+    symbol layout; 33x27 is a single predictor cell, 81x41 a 3x2 grid)."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(1000 * mode + w)
+    planes = _smooth_planes(rng, n, w, h, depth)
+    got = g.layer_encode_batch(planes, n, w, h, depth, mode)
+    for i in range(n):
+        want, _ = ol.orc_layer_encode(planes[i * w * h:(i + 1) * w * h], w, h, depth, mode)
+        payload, st, kept = got[i]
+        assert st == 0
+        assert payload == want.tobytes(), (i, w, h, depth, mode, kept, len(payload), len(want))
+
+
+def test_layer_encode_batch_golden():
+    """The reference's own layer_encode outputs (golden vectors, modes 0-4) through the batched call."""
+    g = gpu_lib.gpu()
+    z = np.load(os.path.join(G, "layer_tile.npz"))
+    for name in _cases(z, "__plane"):
+        w, h, depth, mode = (int(v) for v in z[name + "__par"])
+        plane = z[name + "__plane"]
+        got = g.layer_encode_batch(np.concatenate([plane, plane]), 2, w, h, depth, mode)
+        want = z[name + "__out"].tobytes()
+        for payload, st, kept in got:
+            assert st == 0 and payload == want, (name, w, h, depth, mode, kept)
