@@ -833,6 +833,112 @@ size_t orc_layer_encode(const uint16_t* plane, size_t size, int w, int h, int de
 }
 
 /* ======================================================================== */
+/* lz.hpp — LZ match finder over RGB pixels                                 */
+/* ======================================================================== */
+
+/* Number of consecutive pixels, at most 259, for which pixel (at + k) equals pixel (at - back + k); the run
+ * also stops at the end of the image (lz.hpp:37-46 and :55-64 — the two loops differ only in how the end
+ * bound is written, and for size % 3 == 0 the bounds coincide). */
+static int lz_run(const uint8_t* rgb, size_t size, size_t at, size_t back_bytes) {
+    int k = 0;
+    while (k < 259) {
+        size_t a = at + (size_t)k * 3;
+        if (a + 2 >= size) break;
+        const uint8_t* p = rgb + a;
+        const uint8_t* q = p - back_bytes;
+        if (p[0] != q[0] || p[1] != q[1] || p[2] != q[2]) break;
+        k++;
+    }
+    return k;
+}
+
+size_t orc_find_lz_rgb(const uint8_t* rgb, size_t size, int width, int distance, int bonus, uint8_t* lz_out,
+                       uint8_t* nuke, uint8_t* const side_out[4], size_t side_n_out[4]) {
+    const size_t cap = size / 9 + 1;
+    uint8_t* side[4];
+    size_t cnt[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; k++) side[k] = (uint8_t*)malloc(cap);
+    const long near_limit = 1L << distance; /* :20 */
+    const int wide = distance > 8;
+    int gap = 0; /* pixels since the last match, wraps at 255 (:77-83) */
+    for (size_t at = 0; at < size; at += 3) {
+        int best_len = 0;
+        long best_back = -1;
+        /* :34-52 every distance 1..2^distance; the first (smallest) distance with the longest run wins */
+        for (long back = 1; back <= near_limit && (long)(int)at - back * 3 >= 0; back++) {
+            int len = lz_run(rgb, size, at, (size_t)back * 3);
+            if (len > best_len) {
+                best_len = len;
+                best_back = back;
+                if (len == 259) break;
+            }
+        }
+        /* :53-74 whole rows up: multiples of the width up to 65536 */
+        if (best_len < 259 && wide)
+            for (long back = width; back <= 65536 && (long)(int)at - back * 3 >= 0; back += width) {
+                int len = lz_run(rgb, size, at, (size_t)back * 3);
+                if (len > best_len) {
+                    best_len = len;
+                    best_back = back;
+                    if (len == 259) break; /* nothing can be longer; the reference's odd restart (:70) finds nothing new */
+                }
+            }
+        if (best_len < 4 + bonus) { /* :75-83 */
+            if (++gap == 255) {
+                gap = 0;
+                side[0][cnt[0]++] = 255;
+            }
+            continue;
+        }
+        side[0][cnt[0]++] = (uint8_t)gap; /* :85-91 */
+        if (wide) side[3][cnt[3]++] = (uint8_t)(best_back / 256);
+        side[2][cnt[2]++] = (uint8_t)(best_back % 256);
+        side[1][cnt[1]++] = (uint8_t)(best_len - 4);
+        gap = 0;
+        for (int k = 0; k < best_len; k++) nuke[at / 3 + (size_t)k] = 1; /* :92-94 */
+        at += (size_t)(best_len - 1) * 3;                                 /* :95 */
+    }
+    /* :100-142: tag byte, then each side stream through encode_entropy (8-bit overload, range 256, 10 bits) */
+    size_t o = 0;
+    lz_out[o++] = 0x03;
+    uint16_t* wide_sym = (uint16_t*)malloc(cap * sizeof(uint16_t));
+    for (int k = 0; k < (wide ? 4 : 3); k++) {
+        for (size_t i = 0; i < cnt[k]; i++) wide_sym[i] = side[k][i];
+        o += orc_encode_entropy(wide_sym, cnt[k], 256, lz_out + o, 10, NULL);
+    }
+    free(wide_sym);
+    for (int k = 0; k < 4; k++) {
+        if (side_out && side_out[k]) memcpy(side_out[k], side[k], cnt[k]);
+        if (side_n_out) side_n_out[k] = cnt[k];
+        free(side[k]);
+    }
+    return o;
+}
+
+/* choh.cpp:17-50 */
+int orc_count_colours(const uint8_t* rgb, size_t size) {
+    uint8_t pal[257][3];
+    int n = 0;
+    for (size_t i = 0; i + 2 < size; i += 3) {
+        int j = 0;
+        while (j < n && (pal[j][0] != rgb[i] || pal[j][1] != rgb[i + 1] || pal[j][2] != rgb[i + 2])) j++;
+        if (j < n) continue;
+        memcpy(pal[n], rgb + i, 3);
+        if (++n == 257) return -1;
+    }
+    return n;
+}
+
+/* choh.cpp:123-154 */
+void orc_lz_params(const uint8_t* rgb, size_t size, size_t mode, int* distance, int* bonus) {
+    static const int dist_of_mode[5] = {6, 10, 11, 12, 14};
+    *distance = mode <= 4 ? dist_of_mode[mode] : 6;
+    int colours = orc_count_colours(rgb, size);
+    *bonus = 0;
+    if (colours != -1) *bonus = colours <= 4 ? 32 : colours <= 8 ? 20 : colours <= 16 ? 10 : colours <= 32 ? 2 : 0;
+}
+
+/* ======================================================================== */
 /* synthetic inputs                                          */
 /* ======================================================================== */
 

@@ -96,6 +96,18 @@ size_t orc_predictor_search(const uint16_t* plane, size_t size, int w, int h, in
                             uint16_t* tile_map, uint8_t* index_list, uint16_t* final_resid);
 extern const uint16_t orc_stock_masks[14];                                   /* layer_encode.hpp:159-175 */
 
+/* ---- lz.hpp: the LZ match finder ------------------- */
+/* lz.hpp:6-145.  rgb: size bytes (size = 3 * pixels).  nuke: pixels bytes, OR-ed with 1 where a match covers
+ * the pixel (caller zeroes it, choh.cpp:118-121).  lz_out receives 0x03 + the 3 (distance <= 8) or 4 entropy
+ * coded side streams; the return value is its length.  side / side_n (optional, may be NULL): the raw side
+ * streams in the order since_last, length-4, back%256, back/256, each with capacity size/9 + 1. */
+size_t orc_find_lz_rgb(const uint8_t* rgb, size_t size, int width, int distance, int break_even_bonus,
+                       uint8_t* lz_out, uint8_t* nuke, uint8_t* const side[4], size_t side_n[4]);
+/* choh.cpp:17-50: number of distinct colours, -1 if more than 256 */
+int orc_count_colours(const uint8_t* rgb, size_t size);
+/* choh.cpp:123-154: seek distance and break-even bonus encode_tile derives from the cruncher mode / colours */
+void orc_lz_params(const uint8_t* rgb, size_t size, size_t mode, int* distance, int* bonus);
+
 /* ---- synthetic inputs ----------------------------------- */
 void orc_synth_rgb(uint8_t* rgb, int w, int h, uint64_t seed);
 void orc_synth_symbols(uint8_t* sym, size_t n, uint64_t seed);   /* geometric(p=0.08), clipped to 255 */

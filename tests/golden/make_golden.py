@@ -147,8 +147,27 @@ def layer_and_tile_cases():
     print("layer_tile.npz", k, "layer cases;", files)
 
 
+def lz_cases():
+    """find_lz_rgb (lz.hpp:6) on images with matches: LZ bytes + nuke map from the real reference."""
+    rng = np.random.default_rng(2024)
+    out = {}
+    k = 0
+    for kind in ("flat", "pattern", "rows", "few", "photo"):
+        for (w, h, distance, bonus) in [(64, 48, 6, 0), (61, 37, 10, 2), (96, 64, 12, 0), (80, 50, 14, 10)]:
+            img = ol.lz_test_image(rng, w, h, kind)
+            lz, nuke = ol.ref_find_lz_rgb(img, w, h, distance, bonus)
+            out[f"z{k}__rgb"] = img.ravel()
+            out[f"z{k}__par"] = np.array([w, h, distance, bonus], np.int64)
+            out[f"z{k}__lz"] = lz
+            out[f"z{k}__nuke"] = np.packbits(nuke)
+            k += 1
+    np.savez_compressed(os.path.join(HERE, "lz.npz"), **out)
+    print("lz.npz", k, "cases")
+
+
 if __name__ == "__main__":
     assert ol.have_ref(), "needs /root/reference (development container)"
     entropy_cases()
     predict_cases()
     layer_and_tile_cases()
+    lz_cases()

@@ -78,6 +78,13 @@ def oracle():
                                        C.POINTER(C.c_int)]
         L.orc_predictor_search.restype = sz
         L.orc_predictor_search.argtypes = [u16p, sz, C.c_int, C.c_int, C.c_int, sz, u16p, u8p, C.c_void_p]
+        L.orc_find_lz_rgb.restype = sz
+        L.orc_find_lz_rgb.argtypes = [u8p, sz, C.c_int, C.c_int, C.c_int, u8p, u8p, C.POINTER(C.c_void_p),
+                                      C.POINTER(sz)]
+        L.orc_count_colours.restype = C.c_int
+        L.orc_count_colours.argtypes = [u8p, sz]
+        L.orc_lz_params.restype = None
+        L.orc_lz_params.argtypes = [u8p, sz, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_synth_rgb.restype = None
         L.orc_synth_rgb.argtypes = [u8p, C.c_int, C.c_int, C.c_uint64]
         L.orc_synth_symbols.restype = None
@@ -205,6 +212,61 @@ def synth_symbols(n, seed):
     a = np.zeros(n, np.uint8)
     oracle().orc_synth_symbols(a, n, seed)
     return a
+
+
+def orc_find_lz_rgb(rgb, width, distance, bonus):
+    """lz.hpp:6 -> (lz bytes, nuke map, [since_last, length-4, back%256, back/256] raw side streams)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
+    size = rgb.size
+    cap = size // 9 + 1
+    out = np.zeros(4 * (cap * 2 + 2048), np.uint8)
+    nuke = np.zeros(size // 3, np.uint8)
+    side = [np.zeros(cap, np.uint8) for _ in range(4)]
+    ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in side])
+    cnt = (sz * 4)()
+    n = oracle().orc_find_lz_rgb(rgb, size, width, distance, bonus, out, nuke, ptrs, cnt)
+    return out[:n].copy(), nuke, [side[k][:cnt[k]].copy() for k in range(4)]
+
+
+def ref_find_lz_rgb(rgb, width, height, distance, bonus):
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
+    size = rgb.size
+    out = np.zeros(4 * ((size // 9 + 1) * 2 + 2048), np.uint8)
+    nuke = np.zeros(size // 3, np.uint8)
+    n = ref().ref_find_lz_rgb(rgb, size, width, height, out, nuke, distance, bonus)
+    return out[:n].copy(), nuke
+
+
+def orc_lz_params(rgb, mode):
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
+    d, b = C.c_int(), C.c_int()
+    oracle().orc_lz_params(rgb, rgb.size, mode, C.byref(d), C.byref(b))
+    return d.value, b.value
+
+
+def lz_test_image(rng, w, h, kind):
+    """Images that actually contain LZ matches (the §8(d) generator has none)."""
+    if kind == "flat":          # large uniform areas with a few marks
+        img = np.full((h, w, 3), 200, np.uint8)
+        for _ in range(12):
+            y, x = int(rng.integers(0, h)), int(rng.integers(0, w))
+            img[y:y + int(rng.integers(1, 9)), x:x + int(rng.integers(1, 30))] = rng.integers(0, 256, 3)
+    elif kind == "pattern":     # periodic texture: many equally long candidates at different distances
+        tile = rng.integers(0, 256, (int(rng.integers(2, 7)), int(rng.integers(3, 23)), 3)).astype(np.uint8)
+        img = np.tile(tile, (h // tile.shape[0] + 1, w // tile.shape[1] + 1, 1))[:h, :w].copy()
+        noise = rng.random((h, w)) < 0.01
+        img[noise] = rng.integers(0, 256, (int(noise.sum()), 3))
+    elif kind == "rows":        # rows repeated further up: only the width-multiple distances find them
+        base = rng.integers(0, 256, (4, w, 3)).astype(np.uint8)
+        img = base[rng.integers(0, 4, h)].copy()
+        noise = rng.random((h, w)) < 0.02
+        img[noise] = rng.integers(0, 256, (int(noise.sum()), 3))
+    elif kind == "few":         # a handful of colours: break-even bonus territory
+        pal = rng.integers(0, 256, (int(rng.integers(2, 20)), 3)).astype(np.uint8)
+        img = pal[(rng.integers(0, len(pal), (h, w)) * (rng.random((h, w)) < 0.3)).astype(np.int64)]
+    else:                       # smooth synthetic photo: (almost) no matches
+        img = synth_rgb(w, h, int(rng.integers(1, 1 << 30))).reshape(h, w, 3)
+    return np.ascontiguousarray(img, dtype=np.uint8)
 
 
 def orc_layer_encode(plane, w, h, depth, mode, nuke=None):

@@ -89,3 +89,15 @@ def test_example_tile_known_answer():
     assert z["tile_example_s0"].tobytes().hex() == "00007f03817f00817f00817f0010000000108" "17f0400008182" "81"
     assert len(z["tile_example_s1"]) == 29
     assert hashlib.md5(z["file_512x512_s0"].tobytes()).hexdigest() == "78c14f89f3787559f0652b9ab31f3fa6"
+
+
+def test_find_lz_rgb_golden():
+    """lz.hpp:6 — LZ bytes and nuke maps recorded from the real reference (tests/golden/lz.npz)."""
+    z = np.load(os.path.join(G, "lz.npz"))
+    names = sorted({k[:-5] for k in z.files if k.endswith("__rgb")})
+    assert len(names) == 20
+    for name in names:
+        w, h, distance, bonus = (int(v) for v in z[name + "__par"])
+        lz, nuke, _ = ol.orc_find_lz_rgb(z[name + "__rgb"], w, distance, bonus)
+        assert np.array_equal(lz, z[name + "__lz"]), name
+        assert np.array_equal(nuke, np.unpackbits(z[name + "__nuke"])[: w * h]), name

@@ -222,3 +222,38 @@ def test_static_table_rans():
     O.orc_rans_decode_static(oa[:na].copy(), na, sym.size, freqs, cum, 256, 12, da)
     R.ref_rans_decode_static(ob[:nb].copy(), nb, sym.size, freqs, cum, 256, 12, db)
     assert (da == sym).all() and (db == sym).all()
+
+
+
+def test_find_lz_rgb_pinned_against_reference():
+    """lz.hpp:6 — oracle restatement vs the compiled reference: LZ bytes and nuke map, every seek distance
+    encode_tile uses (6, 10, 11, 12, 14) and every break-even bonus, on images that contain matches."""
+    rng = np.random.default_rng(77)
+    total_matches = 0
+    for it in range(40):
+        kind = ["flat", "pattern", "rows", "few", "photo"][it % 5]
+        w, h = int(rng.integers(5, 70)), int(rng.integers(4, 50))
+        img = ol.lz_test_image(rng, w, h, kind)
+        for distance in (6, 10, 11, 12, 14):
+            bonus = [0, 2, 10, 20, 32][int(rng.integers(0, 5))]
+            want, want_nuke = ol.ref_find_lz_rgb(img, w, h, distance, bonus)
+            got, got_nuke, side = ol.orc_find_lz_rgb(img, w, distance, bonus)
+            assert np.array_equal(got, want), (it, kind, w, h, distance, bonus)
+            assert np.array_equal(got_nuke, want_nuke), (it, kind, w, h, distance, bonus)
+            total_matches += len(side[1])
+    assert total_matches > 1000
+
+
+
+def test_lz_params_pinned_against_reference():
+    rng = np.random.default_rng(5)
+    for it in range(30):
+        ncol = [1, 3, 4, 5, 8, 9, 16, 17, 32, 33, 255, 256, 257, 400][it % 14]
+        pal = np.unique(rng.integers(0, 256, (ncol * 3, 3)).astype(np.uint8), axis=0)[:ncol]
+        while len(pal) < ncol:
+            pal = np.unique(np.concatenate([pal, rng.integers(0, 256, (ncol, 3)).astype(np.uint8)]), axis=0)[:ncol]
+        idx = np.concatenate([np.arange(ncol), rng.integers(0, ncol, 500)])
+        rng.shuffle(idx)
+        img = pal[idx].ravel()
+        want = ol.ref().ref_count_colours(img, img.size)
+        assert ol.oracle().orc_count_colours(img, img.size) == want == (ncol if ncol <= 256 else -1)
