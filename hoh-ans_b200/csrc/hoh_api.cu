@@ -21,7 +21,7 @@ namespace {
 enum Slot {
     S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
     S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
-    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_COUNT
+    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_COUNT
 };
 
 struct Buf {
@@ -1119,6 +1119,67 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     return HOH_OK;
 }
 
+// -------------------------------------------------------------------------------------------------
+// lz.hpp:6 for many tiles
+// -------------------------------------------------------------------------------------------------
+static uint32_t lz_side_stride(size_t npx) { return (uint32_t)((npx / 3 + 1 + 7) & ~(size_t)7); }  // lz.hpp:23-26: size/9 entries
+
+size_t hoh_find_lz_stride(int w, int h) {
+    if (w <= 0 || h <= 0) return 0;
+    const size_t npx = (size_t)w * h;
+    // each side stream: 8 bytes of varints/metadata, a table of at most ~520 bytes, 10 bits per symbol
+    return (1 + 4 * hoh_enc_slab_bytes(lz_side_stride(npx), 10) + 15) & ~(size_t)15;
+}
+
+int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, int w, int h, int distance,
+                          const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
+                          uint32_t* d_lz_size, int32_t* d_status) {
+    if (!ctx || !d_rgb || !d_nuke || !d_lz || !d_lz_size || w <= 0 || h <= 0 || distance < 0 || distance > 16)
+        return HOH_E_ARG;
+    if (n_tiles == 0) return HOH_OK;
+    const size_t npx = (size_t)w * h;
+    if (npx >= (1u << 21) * 3ull) return HOH_E_UNSUPPORTED;  // side streams must stay below 2^21 symbols (varint.hpp:39-45)
+    if (lz_stride < hoh_find_lz_stride(w, h) || lz_stride > 0xffffffffull) return HOH_E_CAPACITY;
+    const uint32_t stride = lz_side_stride(npx);
+    const uint32_t slab = (uint32_t)hoh_enc_slab_bytes(stride, 10);
+    const uint32_t wide = distance > 8;
+    uint32_t *px, *state, *counts;
+    uint16_t* side;
+    uint8_t* slabs;
+    int32_t* bonus = nullptr;
+    hoh_enc_stream* streams;
+    hoh_stream_result* res;
+    TRY(scratch_t(ctx, S_LZ_PX, n_tiles * npx, &px));
+    TRY(scratch_t(ctx, S_LZ_STATE, n_tiles * npx, &state));
+    TRY(scratch_t(ctx, S_LZ_SIDE, n_tiles * 4 * stride, &side));
+    TRY(scratch_t(ctx, S_LZ_COUNTS, n_tiles * 4, &counts));
+    TRY(scratch_t(ctx, S_LZ_SLABS, n_tiles * 4 * slab, &slabs));
+    TRY(scratch_t(ctx, S_LZ_RES, n_tiles * 4, &res));
+    TRY(scratch_t(ctx, S_STREAMS, n_tiles * 4, &streams));
+    k_lz_pack<<<grid_cap(n_tiles * npx, 256), 256, 0, ctx->stream>>>(d_rgb, n_tiles * npx, px);
+    LAUNCHED("k_lz_pack");
+    if (!d_bonus) {
+        TRY(scratch_t(ctx, S_LZ_BONUS, n_tiles, &bonus));
+        k_lz_bonus<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(px, (uint32_t)npx, bonus);
+        LAUNCHED("k_lz_bonus");
+        d_bonus = bonus;
+    }
+    const uint64_t segs = (npx + kLzSeg - 1) / kLzSeg;
+    k_lz_match<<<blocks_for(n_tiles * segs * 32, 128), 128, 0, ctx->stream>>>(px, (uint32_t)npx, n_tiles, (uint32_t)w,
+                                                                             1u << distance, wide, state);
+    LAUNCHED("k_lz_match");
+    k_lz_walk<<<blocks_for(n_tiles * 32, 128), 128, 0, ctx->stream>>>(state, (uint32_t)npx, n_tiles, d_bonus, 0, wide,
+                                                                     d_nuke, side, stride, counts);
+    LAUNCHED("k_lz_walk");
+    k_lz_streams<<<blocks_for(n_tiles * 4, 256), 256, 0, ctx->stream>>>(n_tiles, counts, stride, slab, streams);
+    LAUNCHED("k_lz_streams");
+    TRY(hoh_encode_entropy_batch(ctx, streams, n_tiles * 4, side, slabs, res, 256, 10, stride));
+    k_lz_assemble<<<(unsigned)n_tiles, 128, 0, ctx->stream>>>(res, slabs, wide, d_lz, (uint32_t)lz_stride, d_lz_size,
+                                                             d_status);
+    LAUNCHED("k_lz_assemble");
+    return HOH_OK;
+}
+
 // =================================================================================================
 // compat shims (host pointers)
 // =================================================================================================
@@ -1335,6 +1396,33 @@ int hoh_predictor_search(hoh_ctx* ctx, const uint16_t* plane, int w, int h, int 
     TRY(stage_out(ctx, tile_map, d_map, cells));
     TRY(stage_out(ctx, index_list, d_idx, cells));
     if (final_resid) TRY(stage_out(ctx, final_resid, d_res, px));
+    return HOH_OK;
+}
+
+int hoh_find_lz_rgb(hoh_ctx* ctx, const uint8_t* source, size_t size, int width, int height, uint8_t* lz_symbols,
+                    size_t lz_cap, uint8_t* nukemap, int distance, int break_even_bonus, size_t* lz_size) {
+    if (!ctx || !source || !lz_symbols || !nukemap || !lz_size || width <= 0 || height <= 0) return HOH_E_ARG;
+    const size_t npx = (size_t)width * height;
+    if (size != npx * 3) return HOH_E_ARG;
+    const size_t stride = hoh_find_lz_stride(width, height);
+    uint8_t *d_rgb, *d_nuke, *d_lz;
+    uint32_t* d_size;
+    int32_t* d_bonus;
+    TRY(stage_in(ctx, S_IO_A, source, size, &d_rgb));
+    TRY(scratch_t(ctx, S_IO_B, npx, &d_nuke));
+    TRY(scratch_t(ctx, S_IO_C, stride, &d_lz));
+    TRY(scratch_t(ctx, S_IO_D, 2, &d_size));
+    d_bonus = reinterpret_cast<int32_t*>(d_size + 1);
+    CK(cudaMemcpyAsync(d_bonus, &break_even_bonus, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(hoh_find_lz_rgb_batch(ctx, d_rgb, 1, width, height, distance, d_bonus, d_nuke, d_lz, stride, d_size, nullptr));
+    uint32_t n = 0;
+    TRY(stage_out(ctx, &n, d_size, 1));
+    if (n > lz_cap) return HOH_E_CAPACITY;
+    TRY(stage_out(ctx, lz_symbols, d_lz, n));
+    std::vector<uint8_t> nk(npx);
+    TRY(stage_out(ctx, nk.data(), d_nuke, npx));
+    for (size_t i = 0; i < npx; i++) nukemap[i] |= nk[i];
+    *lz_size = n;
     return HOH_OK;
 }
 

@@ -2344,4 +2344,250 @@ __global__ void k_layer_scatter(uint64_t n_planes, int round, const hoh_stream_r
     results[p * kLayerSlots + slot] = rr[i];
 }
 
+// =================================================================================================
+// lz.hpp:6-145 — the LZ match finder, for many tiles.
+//
+// The reference walks the pixels greedily and, at every pixel it lands on, tries every distance and extends
+// each candidate pixel by pixel.  Here the two halves are separated:
+//   k_lz_match  computes (longest run, first distance reaching it) for EVERY pixel, all pixels in parallel —
+//               exactly what the reference would compute if it landed there;
+//   k_lz_walk   replays the greedy walk over those answers (a warp per tile, 32 pixels per step) and emits
+//               the four side streams and the NUKE map.
+// Run lengths are not found by extension: for a fixed distance b the equality bits e_b[i] = (px[i] ==
+// px[i-b]) of 32 consecutive pixels are one warp ballot, and the run starting at pixel i is the number of
+// consecutive ones from bit i on, continued into the following ballot words.  Walking a segment backwards
+// the continuation is ONE warp-uniform number (the run length at the start of the next word), so a
+// (distance, 32 pixels) pair costs one load, one compare, one ballot and — only if some pixel matched — a
+// shift / count-trailing-ones per lane, whatever the image content is (flat images do not blow up).
+// =================================================================================================
+constexpr int kLzSeg = 1024;      // pixels per warp: 32 words of 32 pixels, one (run, distance) register each
+constexpr int kLzMaxRun = 259;    // lz.hpp:42
+constexpr int kLzAhead = 9;       // 32-pixel words of look-ahead that a capped run can reach into
+constexpr uint32_t kLzBackBits = 17;  // distances go up to 65536 (lz.hpp:54)
+
+__global__ void k_lz_pack(const uint8_t* __restrict__ rgb, uint64_t n_px, uint32_t* __restrict__ px) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_px; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t* p = rgb + i * 3u;
+        px[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    }
+}
+
+// trailing ones of w (32 when w is all ones)
+__device__ __forceinline__ uint32_t lz_ones(uint32_t w) { return w == 0xffffffffu ? 32u : (uint32_t)(__ffs((int)~w) - 1); }
+
+// One distance for one 1024-pixel segment.  CHECK = the segment touches the tile's ends (or the distance
+// reaches before the tile's first pixel), so every access is bounds-tested.
+template <bool CHECK>
+__device__ __forceinline__ void lz_one_distance(const uint32_t* __restrict__ P, uint32_t npx, uint32_t s0,
+                                                uint32_t lane, uint32_t b, const uint32_t (&mine)[32],
+                                                uint32_t (&best)[32]) {
+    // run length at the first pixel after the segment: forward over the look-ahead words until one breaks
+    uint32_t carry = 0;
+    for (uint32_t k = 32; k < 32u + kLzAhead; k++) {
+        const uint32_t i = s0 + 32u * k + lane;
+        bool e;
+        if (CHECK) e = i < npx && i >= b && P[i] == P[i - b];
+        else e = P[i] == P[i - b];
+        const uint32_t w = __ballot_sync(0xffffffffu, e);
+        carry += lz_ones(w);
+        if (w != 0xffffffffu) break;
+    }
+    const uint32_t* q = P + s0 + lane - b;  // only dereferenced where s0 + 32k + lane >= b
+#pragma unroll
+    for (int k = 31; k >= 0; k--) {
+        bool e;
+        if (CHECK) {
+            const uint32_t i = s0 + 32u * k + lane;
+            e = i < npx && i >= b && mine[k] == q[32 * k];
+        } else {
+            e = mine[k] == q[32 * k];
+        }
+        const uint32_t w = __ballot_sync(0xffffffffu, e);
+        if (w) {  // warp-uniform
+            const uint32_t t = w >> lane;
+            const uint32_t ones = lz_ones(t);  // bits above 31 - lane are zero: ones <= 32 - lane
+            uint32_t len = ones == 32u - lane ? ones + carry : ones;
+            len = min(len, (uint32_t)kLzMaxRun);
+            if (len > (best[k] >> kLzBackBits)) best[k] = (len << kLzBackBits) | b;  // strict: first distance wins
+            carry = w == 0xffffffffu ? carry + 32u : lz_ones(w);
+        } else {
+            carry = 0;
+        }
+    }
+}
+
+// state[tile * npx + i] = longest << 17 | distance  (0 when nothing matches at all)
+__global__ void __launch_bounds__(128) k_lz_match(const uint32_t* __restrict__ px, uint32_t npx, uint64_t n_tiles,
+                                                  uint32_t width, uint32_t near_limit, uint32_t wide,
+                                                  uint32_t* __restrict__ state) {
+    const uint32_t lane = lane_id();
+    const uint32_t segs = (npx + kLzSeg - 1) / kLzSeg;
+    const uint64_t wid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (wid >= n_tiles * segs) return;
+    const uint64_t tile = wid / segs;
+    const uint32_t s0 = (uint32_t)(wid % segs) * kLzSeg;
+    const uint32_t* P = px + tile * npx;
+    uint32_t mine[32], best[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const uint32_t i = s0 + 32u * k + lane;
+        mine[k] = i < npx ? P[i] : 0xffffffffu;
+        best[k] = 0;
+    }
+    const uint32_t last = min(s0 + kLzSeg, npx) - 1u;  // highest pixel of the segment: larger distances reach nothing
+    const bool inside = s0 + kLzSeg + 32u * kLzAhead <= npx;
+    // lz.hpp:34-52: every distance 1 .. 2^distance
+    const uint32_t near_end = min(near_limit, last);
+    for (uint32_t b = 1; b <= near_end; b++) {
+        if (inside && b <= s0) lz_one_distance<false>(P, npx, s0, lane, b, mine, best);
+        else lz_one_distance<true>(P, npx, s0, lane, b, mine, best);
+    }
+    // lz.hpp:53-74: whole rows up, multiples of the width up to 65536
+    if (wide)
+        for (uint32_t b = width; b <= 65536u && b <= last; b += width) {
+            if (inside && b <= s0) lz_one_distance<false>(P, npx, s0, lane, b, mine, best);
+            else lz_one_distance<true>(P, npx, s0, lane, b, mine, best);
+        }
+    uint32_t* S = state + tile * npx;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const uint32_t i = s0 + 32u * k + lane;
+        if (i < npx) S[i] = best[k];
+    }
+}
+
+// choh.cpp:17-50 + :134-154: distinct colours of a tile (more than 256 = "many") -> break-even bonus.
+// One CTA per tile, open-addressing hash set in shared memory.
+__global__ void __launch_bounds__(256) k_lz_bonus(const uint32_t* __restrict__ px, uint32_t npx,
+                                                  int32_t* __restrict__ bonus) {
+    __shared__ uint32_t s_set[1024];
+    __shared__ uint32_t s_count;
+    for (uint32_t i = threadIdx.x; i < 1024u; i += blockDim.x) s_set[i] = 0xffffffffu;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const uint32_t* P = px + (uint64_t)blockIdx.x * npx;
+    volatile uint32_t* seen = &s_count;
+    for (uint32_t base = 0; base < npx; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        if (i < npx && *seen <= 256u) {
+            const uint32_t v = P[i];
+            uint32_t h = (v * 2654435761u) >> 22;
+            for (;;) {
+                const uint32_t old = atomicCAS(&s_set[h], 0xffffffffu, v);
+                if (old == 0xffffffffu) {
+                    atomicAdd(&s_count, 1u);
+                    break;
+                }
+                if (old == v) break;
+                h = (h + 1u) & 1023u;
+                if (*seen > 256u) break;  // the set cannot fill up: at most 257 + 256 in-flight inserts
+            }
+        }
+        if (__syncthreads_or(*seen > 256u)) break;  // same answer in every thread
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t c = *seen;
+        bonus[blockIdx.x] = c > 256u ? 0 : (c <= 4u ? 32 : (c <= 8u ? 20 : (c <= 16u ? 10 : (c <= 32u ? 2 : 0))));
+    }
+}
+
+// The greedy walk (lz.hpp:33, 75-96) over the per-pixel answers.  One warp per tile.  side: u16 symbol
+// buffers, 4 per tile, side_stride elements apart (since_last, length - 4, distance % 256, distance / 256);
+// counts[tile * 4 + k] = symbols in each.
+__global__ void __launch_bounds__(128) k_lz_walk(const uint32_t* __restrict__ state, uint32_t npx, uint64_t n_tiles,
+                                                 const int32_t* __restrict__ bonus, int32_t fixed_bonus, uint32_t wide,
+                                                 uint8_t* __restrict__ nuke, uint16_t* __restrict__ side,
+                                                 uint32_t side_stride, uint32_t* __restrict__ counts) {
+    const uint32_t lane = lane_id();
+    const uint64_t tile = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (tile >= n_tiles) return;
+    const uint32_t* S = state + tile * npx;
+    uint8_t* N = nuke + tile * npx;
+    uint16_t* side0 = side + (tile * 4u) * side_stride;
+    uint16_t* side1 = side0 + side_stride;
+    uint16_t* side2 = side1 + side_stride;
+    uint16_t* side3 = side2 + side_stride;
+    const uint32_t threshold = 4u + (uint32_t)(bonus ? bonus[tile] : fixed_bonus);  // lz.hpp:75
+    uint32_t pos = 0, gap = 0, c0 = 0, c1 = 0;  // c1 counts matches: the other three streams grow together
+    while (pos < npx) {
+        const uint32_t i = pos + lane;
+        const uint32_t v = i < npx ? S[i] : 0u;
+        const uint32_t hits = __ballot_sync(0xffffffffu, (v >> kLzBackBits) >= threshold);
+        const uint32_t room = min(32u, npx - pos);
+        const uint32_t skipped = hits ? (uint32_t)(__ffs((int)hits) - 1) : room;  // pixels without a match
+        if (lane < skipped) N[i] = 0;
+        gap += skipped;
+        if (gap >= 255u) {  // lz.hpp:77-81 (at most once: skipped <= 32)
+            if (lane == 0) side0[c0] = 255;
+            c0++;
+            gap -= 255u;
+        }
+        pos += skipped;
+        if (!hits) continue;
+        const uint32_t m = __shfl_sync(0xffffffffu, v, (int)skipped);
+        const uint32_t len = m >> kLzBackBits, back = m & ((1u << kLzBackBits) - 1u);
+        if (lane == 0) {  // lz.hpp:85-91
+            side0[c0] = (uint16_t)gap;
+            side1[c1] = (uint16_t)(len - 4u);
+            side2[c1] = (uint16_t)(back & 255u);
+            if (wide) side3[c1] = (uint16_t)((back >> 8) & 255u);
+        }
+        c0++;
+        c1++;
+        gap = 0;
+        for (uint32_t k = lane; k < len; k += 32) N[pos + k] = 1;  // lz.hpp:92-94
+        pos += len;                                                 // :95
+    }
+    if (lane == 0) {
+        counts[tile * 4u + 0] = c0;
+        counts[tile * 4u + 1] = c1;
+        counts[tile * 4u + 2] = c1;
+        counts[tile * 4u + 3] = wide ? c1 : 0u;
+    }
+}
+
+// descriptors of the 4 side streams of every tile (lz.hpp:102-141: range 256, 10 bits)
+__global__ void k_lz_streams(uint64_t n_tiles, const uint32_t* __restrict__ counts, uint32_t side_stride,
+                             uint32_t slab, hoh_enc_stream* __restrict__ streams) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_tiles * 4u) return;
+    hoh_enc_stream st;
+    st.sym_off = i * side_stride;
+    st.n = counts[i];
+    st.range = 256;
+    st.prob_bits = 10;
+    st.prefix_len = 0;
+    for (int b = 0; b < 8; b++) st.prefix[b] = 0;
+    st.out_off = i * (uint64_t)slab;
+    st.out_cap = slab;
+    st.reserved = 0;
+    streams[i] = st;
+}
+
+// LEMPEL bytes of a tile = 0x03 | stream 0 | stream 1 | stream 2 [| stream 3]  (lz.hpp:100-142).  One CTA per tile.
+__global__ void __launch_bounds__(128) k_lz_assemble(const hoh_stream_result* __restrict__ results,
+                                                     const uint8_t* __restrict__ slabs, uint32_t wide,
+                                                     uint8_t* __restrict__ lz, uint32_t lz_stride,
+                                                     uint32_t* __restrict__ lz_size, int32_t* __restrict__ status) {
+    const uint64_t tile = blockIdx.x;
+    uint8_t* dst = lz + tile * lz_stride;
+    uint32_t at = 1;
+    int32_t st = HOH_S_OK;
+    if (threadIdx.x == 0) dst[0] = 0x03;
+    for (uint32_t k = 0; k < (wide ? 4u : 3u); k++) {
+        const hoh_stream_result r = results[tile * 4u + k];
+        st = st ? st : r.status;
+        const uint32_t size = at + r.size <= lz_stride ? r.size : 0u;
+        if (size != r.size) st = st ? st : HOH_S_OVERFLOW;
+        const uint8_t* src = slabs + r.start;
+        for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) dst[at + i] = src[i];
+        at += size;
+    }
+    if (threadIdx.x == 0) {
+        lz_size[tile] = at;
+        if (status) status[tile] = st;
+    }
+}
+
 }  // namespace hohk

@@ -111,6 +111,9 @@ SIGNATURES = {
     "hoh_unpredict_all_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "hoh_predict_section_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _int, _vp, _int, _vp, _u32, _vp]),
     "hoh_predictor_search_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "hoh_find_lz_stride": (_sz, [_int, _int]),
+    "hoh_find_lz_rgb_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "hoh_find_lz_rgb": (_int, [_vp, _vp, _sz, _int, _int, _vp, _sz, _vp, _int, _int, C.POINTER(_sz)]),
     "hoh_layer_encode_out_bytes": (_sz, [_sz, _int, _int, _int, _int]),
     "hoh_layer_encode_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _sz, _vp, _vp, _sz, _vp]),
     "hoh_encode_entropy": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _u32, C.POINTER(_sz), C.POINTER(_int)]),
@@ -466,6 +469,47 @@ class HohGpu:
             for b in (d_rgb, d_out, d_res, d_packed, d_off):
                 b.free()
         return packed, off, res
+
+    def find_lz_rgb(self, rgb, width, height, distance, bonus):
+        """lz.hpp:6 -> (lz bytes, nuke map)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
+        cap = int(self.lib.hoh_find_lz_stride(width, height))
+        out = np.zeros(cap, np.uint8)
+        nuke = np.zeros(rgb.size // 3, np.uint8)
+        n = _sz(0)
+        self._ck(self.lib.hoh_find_lz_rgb(self.ctx, _ptr(rgb), rgb.size, width, height, _ptr(out), cap, _ptr(nuke),
+                                          distance, bonus, C.byref(n)), "hoh_find_lz_rgb")
+        return out[:n.value].copy(), nuke
+
+    def find_lz_rgb_batch(self, tiles, n_tiles, width, height, distance, bonus=None):
+        """tiles: n_tiles*H*W*3 u8; bonus: per-tile int32 array or None (derived from the colour count on the
+        device) -> list of (lz bytes, nuke map, status)."""
+        tiles = np.ascontiguousarray(tiles, dtype=np.uint8).ravel()
+        npx = width * height
+        assert tiles.size == n_tiles * npx * 3
+        stride = int(self.lib.hoh_find_lz_stride(width, height))
+        d_rgb = self.alloc(tiles.nbytes).upload(tiles)
+        d_nuke = self.alloc(n_tiles * npx)
+        d_lz = self.alloc(n_tiles * stride)
+        d_size = self.alloc(n_tiles * 4)
+        d_st = self.alloc(n_tiles * 4)
+        d_bonus = None
+        if bonus is not None:
+            b = np.ascontiguousarray(bonus, dtype=np.int32)
+            d_bonus = self.alloc(b.nbytes).upload(b)
+        try:
+            self._ck(self.lib.hoh_find_lz_rgb_batch(self.ctx, d_rgb.ptr, n_tiles, width, height, distance,
+                                                    d_bonus.ptr if d_bonus else None, d_nuke.ptr, d_lz.ptr, stride,
+                                                    d_size.ptr, d_st.ptr), "hoh_find_lz_rgb_batch")
+            sizes = d_size.download(np.uint32, n_tiles)
+            st = d_st.download(np.int32, n_tiles)
+            lz = d_lz.download(np.uint8, n_tiles * stride).reshape(n_tiles, stride)
+            nuke = d_nuke.download(np.uint8, n_tiles * npx).reshape(n_tiles, npx)
+        finally:
+            for buf in (d_rgb, d_nuke, d_lz, d_size, d_st, d_bonus):
+                if buf is not None:
+                    buf.free()
+        return [(lz[i, :int(sizes[i])].copy(), nuke[i].copy(), int(st[i])) for i in range(n_tiles)]
 
     def layer_encode_batch(self, planes, n_planes, w, h, depth, mode):
         """layer_encode.hpp:11 for n_planes planes of the same shape -> list of (payload bytes, status, kept slot)."""

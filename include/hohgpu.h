@@ -259,6 +259,23 @@ int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pl
                              int depth, int mode, uint16_t* d_tile_maps, uint8_t* d_index_lists,
                              uint16_t* d_resid);
 
+/* ------------------------------------------------------------------------------------------ */
+/* (v) LZ match finder — find_lz_rgb lz.hpp:6-145 over N tiles                 */
+/* ------------------------------------------------------------------------------------------ */
+/* Bytes of one tile's LEMPEL record buffer (tag byte + up to four entropy-coded side streams). */
+size_t hoh_find_lz_stride(int w, int h);
+
+/* find_lz_rgb for n_tiles tiles of w x h pixels (tile t = RGB8 bytes [t*w*h*3, (t+1)*w*h*3): matches
+ * never cross tiles, exactly like the per-tile call at choh.cpp:156).  distance = log2 of the near seek
+ * window (choh.cpp:123-136: 6, 10, 11, 12, 14 for cruncher modes 0-4).  d_bonus: per-tile break-even
+ * bonus, or NULL to derive it on the device from the tile's colour count (count_colours choh.cpp:17-50 and
+ * the table at :138-154).  Outputs: d_nuke[n_tiles*w*h] (0/1, fully written), d_lz[n_tiles * lz_stride]
+ * with lz_stride >= hoh_find_lz_stride(w, h), d_lz_size[n_tiles] = find_lz_rgb's return value,
+ * d_status[n_tiles] (optional) = HOH_S_*. */
+int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, int w, int h, int distance,
+                          const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
+                          uint32_t* d_lz_size, int32_t* d_status);
+
 /* layer_encode.hpp:11 for n_planes planes of the same geometry (w x h, depth, cruncher mode 0..4, all
  * NUKE == 0): the reference's decision sequence — which candidates are entropy-coded, in which order,
  * which buffer is finally emitted, including the stale-buffer behaviour of SURVEY D7 — replayed with the
@@ -306,6 +323,11 @@ int hoh_unpredict_all(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, int w
                       uint16_t* out);
 int hoh_unpredict_fastpath(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, int w, int h, int depth,
                            const uint16_t* backref, uint16_t* out);
+/* lz.hpp:6 — one tile, host pointers.  lz_symbols receives *lz_size <= lz_cap bytes; nukemap (size/3
+ * bytes) is OR-ed like the reference does (the caller zeroes it, choh.cpp:118-121). */
+int hoh_find_lz_rgb(hoh_ctx* ctx, const uint8_t* source, size_t size, int width, int height, uint8_t* lz_symbols,
+                    size_t lz_cap, uint8_t* nukemap, int distance, int break_even_bonus, size_t* lz_size);
+
 /* layer_encode.hpp:126-272 for one plane */
 int hoh_predictor_search(hoh_ctx* ctx, const uint16_t* plane, int w, int h, int depth, int mode,
                          uint16_t* tile_map, uint8_t* index_list, uint16_t* final_resid);
