@@ -584,7 +584,6 @@ int hoh_encode_images_s0(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, ui
                          const uint8_t* d_nuke, uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
                          uint8_t* d_packed, size_t packed_cap, uint64_t* d_packed_off) {
     if (!ctx || !d_rgb || !d_out || !d_results) return HOH_E_ARG;
-    if (d_nuke) return HOH_E_UNSUPPORTED;  // LZ-covered pixel compaction: not in this round
     if (n_images == 0) return HOH_OK;
     hoh_tile_geometry hg;
     TRY(hoh_tile_geometry_for(width, height, &hg));
@@ -607,6 +606,13 @@ int hoh_encode_images_s0(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, ui
     LAUNCHED("k_tile_residuals_s0");
     k_make_tile_streams<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(g, n_tiles, slab, streams);
     LAUNCHED("k_make_tile_streams");
+    if (d_nuke) {  // layer_encode.hpp:93-99: only the residuals of pixels no LZ match covers are coded
+        k_compact_nuke<<<blocks_for(n_streams * 32, 128), 128, 0, ctx->stream>>>(g, n_tiles, d_nuke, g.plane_stride, resid,
+                                                                                streams);
+        LAUNCHED("k_compact_nuke");
+        k_histogram<<<(unsigned)n_streams, 256, 0, ctx->stream>>>(streams, resid, freqs);
+        LAUNCHED("k_histogram");
+    }
     TRY(encode_from_freqs(ctx, streams, n_streams, resid, d_out, d_results, freqs, 512, 15, 15));
     if (d_packed) {
         if (!d_packed_off) return HOH_E_ARG;
@@ -1131,45 +1137,45 @@ size_t hoh_find_lz_stride(int w, int h) {
     return (1 + 4 * hoh_enc_slab_bytes(lz_side_stride(npx), 10) + 15) & ~(size_t)15;
 }
 
-int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, int w, int h, int distance,
-                          const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
-                          uint32_t* d_lz_size, int32_t* d_status) {
-    if (!ctx || !d_rgb || !d_nuke || !d_lz || !d_lz_size || w <= 0 || h <= 0 || distance < 0 || distance > 16)
-        return HOH_E_ARG;
-    if (n_tiles == 0) return HOH_OK;
-    const size_t npx = (size_t)w * h;
-    if (npx >= (1u << 21) * 3ull) return HOH_E_UNSUPPORTED;  // side streams must stay below 2^21 symbols (varint.hpp:39-45)
-    if (lz_stride < hoh_find_lz_stride(w, h) || lz_stride > 0xffffffffull) return HOH_E_CAPACITY;
-    const uint32_t stride = lz_side_stride(npx);
+} // extern "C" (reopened below)
+namespace {
+// shared body of the two LZ entry points; nuke_stride = elements per tile in d_nuke
+int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles, size_t max_npx, int distance,
+                 const int32_t* d_bonus, uint8_t* d_nuke, uint32_t nuke_stride, uint8_t* d_lz, size_t lz_stride,
+                 uint32_t* d_lz_size, int32_t* d_status) {
+    if (max_npx >= (1u << 21) * 3ull) return HOH_E_UNSUPPORTED;  // side streams must stay below 2^21 symbols (varint.hpp:39-45)
+    const uint32_t stride = lz_side_stride(max_npx);
     const uint32_t slab = (uint32_t)hoh_enc_slab_bytes(stride, 10);
+    if (lz_stride < (1 + 4 * (size_t)slab + 15) / 16 * 16 || lz_stride > 0xffffffffull) return HOH_E_CAPACITY;
     const uint32_t wide = distance > 8;
+    sh.pad = 1u << distance;
+    sh.px_stride = sh.pad + (sh.stride + kLzSeg - 1) / kLzSeg * kLzSeg + 32 * kLzAhead;
     uint32_t *px, *state, *counts;
     uint16_t* side;
     uint8_t* slabs;
     int32_t* bonus = nullptr;
     hoh_enc_stream* streams;
     hoh_stream_result* res;
-    TRY(scratch_t(ctx, S_LZ_PX, n_tiles * npx, &px));
-    TRY(scratch_t(ctx, S_LZ_STATE, n_tiles * npx, &state));
+    TRY(scratch_t(ctx, S_LZ_PX, n_tiles * sh.px_stride, &px));
+    TRY(scratch_t(ctx, S_LZ_STATE, n_tiles * sh.stride, &state));
     TRY(scratch_t(ctx, S_LZ_SIDE, n_tiles * 4 * stride, &side));
     TRY(scratch_t(ctx, S_LZ_COUNTS, n_tiles * 4, &counts));
     TRY(scratch_t(ctx, S_LZ_SLABS, n_tiles * 4 * slab, &slabs));
     TRY(scratch_t(ctx, S_LZ_RES, n_tiles * 4, &res));
     TRY(scratch_t(ctx, S_STREAMS, n_tiles * 4, &streams));
-    k_lz_pack<<<grid_cap(n_tiles * npx, 256), 256, 0, ctx->stream>>>(d_rgb, n_tiles * npx, px);
+    k_lz_pack<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(d_rgb, sh, px);
     LAUNCHED("k_lz_pack");
     if (!d_bonus) {
         TRY(scratch_t(ctx, S_LZ_BONUS, n_tiles, &bonus));
-        k_lz_bonus<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(px, (uint32_t)npx, bonus);
+        k_lz_bonus<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(px, sh, bonus);
         LAUNCHED("k_lz_bonus");
         d_bonus = bonus;
     }
-    const uint64_t segs = (npx + kLzSeg - 1) / kLzSeg;
-    k_lz_match<<<blocks_for(n_tiles * segs * 32, 128), 128, 0, ctx->stream>>>(px, (uint32_t)npx, n_tiles, (uint32_t)w,
-                                                                             1u << distance, wide, state);
+    const uint64_t segs = (sh.stride + kLzSeg - 1) / kLzSeg;
+    k_lz_match<<<blocks_for(n_tiles * segs * 32, 128), 128, 0, ctx->stream>>>(px, sh, n_tiles, 1u << distance, wide, state);
     LAUNCHED("k_lz_match");
-    k_lz_walk<<<blocks_for(n_tiles * 32, 128), 128, 0, ctx->stream>>>(state, (uint32_t)npx, n_tiles, d_bonus, 0, wide,
-                                                                     d_nuke, side, stride, counts);
+    k_lz_walk<<<blocks_for(n_tiles * 32, 128), 128, 0, ctx->stream>>>(state, sh, n_tiles, d_bonus, 0, wide, d_nuke,
+                                                                     nuke_stride, side, stride, counts);
     LAUNCHED("k_lz_walk");
     k_lz_streams<<<blocks_for(n_tiles * 4, 256), 256, 0, ctx->stream>>>(n_tiles, counts, stride, slab, streams);
     LAUNCHED("k_lz_streams");
@@ -1178,6 +1184,42 @@ int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, in
                                                              d_status);
     LAUNCHED("k_lz_assemble");
     return HOH_OK;
+}
+}  // namespace
+extern "C" {
+
+int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, int w, int h, int distance,
+                          const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
+                          uint32_t* d_lz_size, int32_t* d_status) {
+    if (!ctx || !d_rgb || !d_nuke || !d_lz || !d_lz_size || w <= 0 || h <= 0 || distance < 0 || distance > 16)
+        return HOH_E_ARG;
+    if (n_tiles == 0) return HOH_OK;
+    const size_t npx = (size_t)w * h;
+    if (npx > 0xffffffffull) return HOH_E_UNSUPPORTED;
+    LzShape sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.tiled = 0;
+    sh.npx = (uint32_t)npx;
+    sh.width = (uint32_t)w;
+    sh.stride = (uint32_t)npx;
+    return find_lz_impl(ctx, d_rgb, sh, n_tiles, npx, distance, d_bonus, d_nuke, (uint32_t)npx, d_lz, lz_stride, d_lz_size,
+                        d_status);
+}
+
+int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
+                       int distance, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
+                       uint32_t* d_lz_size, int32_t* d_status) {
+    if (!ctx || !d_rgb || !d_nuke || !d_lz || !d_lz_size || distance < 0 || distance > 16) return HOH_E_ARG;
+    if (n_images == 0) return HOH_OK;
+    hoh_tile_geometry hg;
+    TRY(hoh_tile_geometry_for(width, height, &hg));
+    LzShape sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.tiled = 1;
+    sh.g = to_geom(hg);
+    sh.stride = sh.g.plane_stride;
+    return find_lz_impl(ctx, d_rgb, sh, n_images * sh.g.tiles_per_image, (size_t)hg.tile_w * hg.tile_h, distance, d_bonus,
+                        d_nuke, sh.g.plane_stride, d_lz, lz_stride, d_lz_size, d_status);
 }
 
 // =================================================================================================

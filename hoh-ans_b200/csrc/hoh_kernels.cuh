@@ -2365,22 +2365,74 @@ constexpr int kLzMaxRun = 259;    // lz.hpp:42
 constexpr int kLzAhead = 9;       // 32-pixel words of look-ahead that a capped run can reach into
 constexpr uint32_t kLzBackBits = 17;  // distances go up to 65536 (lz.hpp:54)
 
-__global__ void k_lz_pack(const uint8_t* __restrict__ rgb, uint64_t n_px, uint32_t* __restrict__ px) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_px; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint8_t* p = rgb + i * 3u;
-        px[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+// Where the tiles are.  tiled == 0: n contiguous tiles of npx pixels (row length `width`), `stride` elements
+// apart in every per-pixel array.  tiled == 1: the tiles of whole images cut as choh.cpp:454-484 cuts them
+// (edge tiles may be smaller), per-pixel arrays still `stride` elements per tile.
+struct LzShape {
+    uint32_t tiled, npx, width, stride;
+    uint32_t pad;        // never-matching words in front of every tile's packed pixels (>= 2^distance)
+    uint32_t px_stride;  // words per tile in the packed-pixel array: pad + segments * kLzSeg + 32 * kLzAhead
+    TileGeom g;
+};
+
+__device__ __forceinline__ void lz_dims(const LzShape& sh, uint64_t tile, uint32_t& npx, uint32_t& width) {
+    if (!sh.tiled) {
+        npx = sh.npx;
+        width = sh.width;
+        return;
+    }
+    uint32_t x0, y0, tw, th;
+    tile_rect(sh.g, (uint32_t)(tile % sh.g.tiles_per_image), x0, y0, tw, th);
+    npx = tw * th;
+    width = tw;
+}
+
+// px[tile * px_stride + pad + i] = R | G << 8 | B << 16 of the tile's i-th pixel, framed by words that equal
+// no pixel and no other framing word at any distance (top byte set, low bits = position), so the match kernel
+// needs no bounds tests for distances up to `pad`.  One CTA per tile.
+__global__ void __launch_bounds__(256) k_lz_pack(const uint8_t* __restrict__ rgb, LzShape sh,
+                                                 uint32_t* __restrict__ px) {
+    const uint64_t tile = blockIdx.x;
+    uint32_t* base = px + tile * sh.px_stride;
+    uint32_t* dst = base + sh.pad;
+    uint32_t npx, width;
+    lz_dims(sh, tile, npx, width);
+    for (uint32_t i = threadIdx.x; i < sh.pad; i += blockDim.x) base[i] = 0xfe000000u | i;
+    for (uint32_t i = npx + threadIdx.x; i < sh.px_stride - sh.pad; i += blockDim.x) dst[i] = 0xff000000u | (i & 0xffffffu);
+    if (!sh.tiled) {
+        const uint8_t* src = rgb + tile * (uint64_t)sh.npx * 3u;
+        for (uint32_t i = threadIdx.x; i < sh.npx; i += blockDim.x) {
+            const uint8_t* p = src + i * 3u;
+            dst[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+        }
+        return;
+    }
+    uint32_t x0, y0, tw, th;
+    tile_rect(sh.g, (uint32_t)(tile % sh.g.tiles_per_image), x0, y0, tw, th);
+    const uint8_t* img = rgb + (tile / sh.g.tiles_per_image) * (uint64_t)sh.g.width * sh.g.height * 3u;
+    for (uint32_t i = threadIdx.x; i < tw * th; i += blockDim.x) {
+        const uint32_t x = i % tw, y = i / tw;
+        const uint8_t* p = img + ((uint64_t)(y0 + y) * sh.g.width + x0 + x) * 3u;
+        dst[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
     }
 }
 
 // trailing ones of w (32 when w is all ones)
 __device__ __forceinline__ uint32_t lz_ones(uint32_t w) { return w == 0xffffffffu ? 32u : (uint32_t)(__ffs((int)~w) - 1); }
 
-// One distance for one 1024-pixel segment.  CHECK = the segment touches the tile's ends (or the distance
-// reaches before the tile's first pixel), so every access is bounds-tested.
+// A candidate is ranked by key = run << 17 | (0x1ffff - distance): the largest key is the longest run and,
+// among equally long runs, the smallest distance — which is what the reference's two ascending loops with a
+// strict '>' keep (lz.hpp:47, :65; the row distances of the second loop that are <= 2^distance repeat
+// distances of the first, the others are larger than all of them).  A max is order-independent, so the
+// distances can be visited in whatever order is cheapest.
+__device__ __forceinline__ uint32_t lz_key(uint32_t run, uint32_t b) { return (run << kLzBackBits) | (0x1ffffu - b); }
+
+// One distance for one 1024-pixel segment, exact run lengths.  CHECK = the segment touches the tile's ends
+// (or the distance reaches before the tile's first pixel), so every access is bounds-tested.
 template <bool CHECK>
 __device__ __forceinline__ void lz_one_distance(const uint32_t* __restrict__ P, uint32_t npx, uint32_t s0,
-                                                uint32_t lane, uint32_t b, const uint32_t (&mine)[32],
-                                                uint32_t (&best)[32]) {
+                                             uint32_t lane, uint32_t b, const uint32_t (&mine)[32],
+                                             uint32_t (&best)[32]) {
     // run length at the first pixel after the segment: forward over the look-ahead words until one breaks
     uint32_t carry = 0;
     for (uint32_t k = 32; k < 32u + kLzAhead; k++) {
@@ -2408,7 +2460,7 @@ __device__ __forceinline__ void lz_one_distance(const uint32_t* __restrict__ P, 
             const uint32_t ones = lz_ones(t);  // bits above 31 - lane are zero: ones <= 32 - lane
             uint32_t len = ones == 32u - lane ? ones + carry : ones;
             len = min(len, (uint32_t)kLzMaxRun);
-            if (len > (best[k] >> kLzBackBits)) best[k] = (len << kLzBackBits) | b;  // strict: first distance wins
+            if (len) best[k] = max(best[k], lz_key(len, b));
             carry = w == 0xffffffffu ? carry + 32u : lz_ones(w);
         } else {
             carry = 0;
@@ -2416,56 +2468,115 @@ __device__ __forceinline__ void lz_one_distance(const uint32_t* __restrict__ P, 
     }
 }
 
-// state[tile * npx + i] = longest << 17 | distance  (0 when nothing matches at all)
-__global__ void __launch_bounds__(128) k_lz_match(const uint32_t* __restrict__ px, uint32_t npx, uint64_t n_tiles,
-                                                  uint32_t width, uint32_t near_limit, uint32_t wide,
+// M distances r + 32 * (c0 + j), j = 0 .. M-1, for a segment all of whose partner pixels exist.  The word a
+// lane compares block k with at distance b + 32 is the word it compares block k - 1 with at distance b, so
+// 32 + M - 1 loads serve 32 * M comparisons; a distance none of whose 1024 comparisons hits (the normal case
+// on photographic content) costs one compare per 32 pixels and nothing else.
+template <int M, int R>
+__device__ __forceinline__ void lz_distance_group(const uint32_t* __restrict__ P, uint32_t npx, uint32_t s0,
+                                                  uint32_t lane, uint32_t r, uint32_t c0, bool exact_inside,
+                                                  const uint32_t (&mine)[32], uint32_t (&best)[32]) {
+    // R consecutive residues r .. r + R - 1 share one round of loads (more loads in flight per warp)
+    uint32_t v[R][32 + M - 1];
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+        const uint32_t* q = P + s0 + lane - (r + u) - 32u * c0;
+#pragma unroll
+        for (int t = 0; t < 32 + M - 1; t++) v[u][t] = q[32 * (t - (M - 1))];
+    }
+    uint32_t hit_mask = 0;
+#pragma unroll
+    for (int u = 0; u < R; u++)
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 32; k++) any |= mine[k] == v[u][k + (M - 1) - j];
+            hit_mask |= __any_sync(0xffffffffu, any) ? (1u << (u * M + j)) : 0u;
+        }
+    while (hit_mask) {  // warp-uniform, rare
+        const uint32_t bit = (uint32_t)__ffs((int)hit_mask) - 1u;
+        hit_mask &= hit_mask - 1u;
+        const uint32_t b = r + bit / M + 32u * (c0 + bit % M);
+        if (exact_inside) lz_one_distance<false>(P, npx, s0, lane, b, mine, best);
+        else lz_one_distance<true>(P, npx, s0, lane, b, mine, best);
+    }
+}
+
+// state[tile * stride + i] = longest << 17 | distance  (longest 0 when nothing matches)
+__global__ void __launch_bounds__(128) k_lz_match(const uint32_t* __restrict__ px, LzShape sh, uint64_t n_tiles,
+                                                  uint32_t near_limit, uint32_t wide,
                                                   uint32_t* __restrict__ state) {
     const uint32_t lane = lane_id();
-    const uint32_t segs = (npx + kLzSeg - 1) / kLzSeg;
+    const uint32_t segs = (sh.stride + kLzSeg - 1) / kLzSeg;
     const uint64_t wid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     if (wid >= n_tiles * segs) return;
     const uint64_t tile = wid / segs;
     const uint32_t s0 = (uint32_t)(wid % segs) * kLzSeg;
-    const uint32_t* P = px + tile * npx;
+    uint32_t npx, width;
+    lz_dims(sh, tile, npx, width);
+    if (s0 >= npx) return;
+    const uint32_t* P = px + tile * sh.px_stride + sh.pad;
     uint32_t mine[32], best[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) {
         const uint32_t i = s0 + 32u * k + lane;
-        mine[k] = i < npx ? P[i] : 0xffffffffu;
+        mine[k] = i < npx ? P[i] : 0xfd000000u;  // equals nothing in memory
         best[k] = 0;
     }
-    const uint32_t last = min(s0 + kLzSeg, npx) - 1u;  // highest pixel of the segment: larger distances reach nothing
-    const bool inside = s0 + kLzSeg + 32u * kLzAhead <= npx;
+    // The framing words make every access for a distance b <= s0 + pad an in-bounds access that cannot
+    // match, in front of the tile and behind it: no bounds tests on the near window (pad >= near_limit).
     // lz.hpp:34-52: every distance 1 .. 2^distance
-    const uint32_t near_end = min(near_limit, last);
-    for (uint32_t b = 1; b <= near_end; b++) {
-        if (inside && b <= s0) lz_one_distance<false>(P, npx, s0, lane, b, mine, best);
-        else lz_one_distance<true>(P, npx, s0, lane, b, mine, best);
-    }
-    // lz.hpp:53-74: whole rows up, multiples of the width up to 65536
-    if (wide)
-        for (uint32_t b = width; b <= 65536u && b <= last; b += width) {
-            if (inside && b <= s0) lz_one_distance<false>(P, npx, s0, lane, b, mine, best);
-            else lz_one_distance<true>(P, npx, s0, lane, b, mine, best);
+    uint32_t done = 0;  // distances 1 .. done are finished
+    {
+        constexpr int M = 8;
+        const uint32_t full = near_limit / (32u * M);
+        for (uint32_t c = 0; c < full; c++)
+            for (uint32_t r = 1; r <= 32u; r++) lz_distance_group<M, 1>(P, npx, s0, lane, r, c * M, true, mine, best);
+        done = full * 32u * M;
+        while (near_limit - done >= 64u) {  // the 2^6 window, or the tail of another one
+            for (uint32_t r = 1; r <= 32u; r += 2) lz_distance_group<2, 2>(P, npx, s0, lane, r, done / 32u, true, mine, best);
+            done += 64u;
         }
-    uint32_t* S = state + tile * npx;
+    }
+    for (uint32_t b = done + 1u; b <= near_limit; b++) lz_one_distance<false>(P, npx, s0, lane, b, mine, best);
+    // lz.hpp:53-74: whole rows up, multiples of the width up to 65536
+    if (wide) {
+        const uint32_t last = min(s0 + kLzSeg, npx) - 1u;  // highest pixel of the segment: larger distances reach nothing
+        for (uint32_t b = width; b <= 65536u && b <= last; b += width) {
+            const bool framed = b <= s0 + sh.pad;
+            if (framed) {  // quick test first: one load and one compare per 32 pixels
+                const uint32_t* q = P + s0 + lane - b;
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < 32; k++) any |= mine[k] == q[32 * k];
+                if (!__any_sync(0xffffffffu, any)) continue;
+                lz_one_distance<false>(P, npx, s0, lane, b, mine, best);
+            } else {
+                lz_one_distance<true>(P, npx, s0, lane, b, mine, best);
+            }
+        }
+    }
+    uint32_t* S = state + tile * sh.stride;
 #pragma unroll
     for (int k = 0; k < 32; k++) {
         const uint32_t i = s0 + 32u * k + lane;
-        if (i < npx) S[i] = best[k];
+        if (i < npx) S[i] = (best[k] & ~0x1ffffu) | (0x1ffffu - (best[k] & 0x1ffffu));
     }
 }
 
 // choh.cpp:17-50 + :134-154: distinct colours of a tile (more than 256 = "many") -> break-even bonus.
 // One CTA per tile, open-addressing hash set in shared memory.
-__global__ void __launch_bounds__(256) k_lz_bonus(const uint32_t* __restrict__ px, uint32_t npx,
+__global__ void __launch_bounds__(256) k_lz_bonus(const uint32_t* __restrict__ px, LzShape sh,
                                                   int32_t* __restrict__ bonus) {
+    uint32_t npx, width_unused;
+    lz_dims(sh, blockIdx.x, npx, width_unused);
     __shared__ uint32_t s_set[1024];
     __shared__ uint32_t s_count;
     for (uint32_t i = threadIdx.x; i < 1024u; i += blockDim.x) s_set[i] = 0xffffffffu;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    const uint32_t* P = px + (uint64_t)blockIdx.x * npx;
+    const uint32_t* P = px + (uint64_t)blockIdx.x * sh.px_stride + sh.pad;
     volatile uint32_t* seen = &s_count;
     for (uint32_t base = 0; base < npx; base += blockDim.x) {
         const uint32_t i = base + threadIdx.x;
@@ -2495,25 +2606,31 @@ __global__ void __launch_bounds__(256) k_lz_bonus(const uint32_t* __restrict__ p
 // The greedy walk (lz.hpp:33, 75-96) over the per-pixel answers.  One warp per tile.  side: u16 symbol
 // buffers, 4 per tile, side_stride elements apart (since_last, length - 4, distance % 256, distance / 256);
 // counts[tile * 4 + k] = symbols in each.
-__global__ void __launch_bounds__(128) k_lz_walk(const uint32_t* __restrict__ state, uint32_t npx, uint64_t n_tiles,
+__global__ void __launch_bounds__(128) k_lz_walk(const uint32_t* __restrict__ state, LzShape sh, uint64_t n_tiles,
                                                  const int32_t* __restrict__ bonus, int32_t fixed_bonus, uint32_t wide,
-                                                 uint8_t* __restrict__ nuke, uint16_t* __restrict__ side,
-                                                 uint32_t side_stride, uint32_t* __restrict__ counts) {
+                                                 uint8_t* __restrict__ nuke, uint32_t nuke_stride,
+                                                 uint16_t* __restrict__ side, uint32_t side_stride,
+                                                 uint32_t* __restrict__ counts) {
     const uint32_t lane = lane_id();
     const uint64_t tile = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     if (tile >= n_tiles) return;
-    const uint32_t* S = state + tile * npx;
-    uint8_t* N = nuke + tile * npx;
+    uint32_t npx, width_unused;
+    lz_dims(sh, tile, npx, width_unused);
+    const uint32_t* S = state + tile * sh.stride;
+    uint8_t* N = nuke + tile * nuke_stride;
     uint16_t* side0 = side + (tile * 4u) * side_stride;
     uint16_t* side1 = side0 + side_stride;
     uint16_t* side2 = side1 + side_stride;
     uint16_t* side3 = side2 + side_stride;
     const uint32_t threshold = 4u + (uint32_t)(bonus ? bonus[tile] : fixed_bonus);  // lz.hpp:75
     uint32_t pos = 0, gap = 0, c0 = 0, c1 = 0;  // c1 counts matches: the other three streams grow together
+    uint32_t v = lane < npx ? S[lane] : 0u;
     while (pos < npx) {
         const uint32_t i = pos + lane;
-        const uint32_t v = i < npx ? S[i] : 0u;
-        const uint32_t hits = __ballot_sync(0xffffffffu, (v >> kLzBackBits) >= threshold);
+        // the block after this one is requested now: when nothing matches here (the usual case) the walk
+        // continues with it and the chain of dependent loads is off the critical path
+        const uint32_t ahead = i + 32u < npx ? S[i + 32u] : 0u;
+        const uint32_t hits = __ballot_sync(0xffffffffu, i < npx && (v >> kLzBackBits) >= threshold);
         const uint32_t room = min(32u, npx - pos);
         const uint32_t skipped = hits ? (uint32_t)(__ffs((int)hits) - 1) : room;  // pixels without a match
         if (lane < skipped) N[i] = 0;
@@ -2524,7 +2641,10 @@ __global__ void __launch_bounds__(128) k_lz_walk(const uint32_t* __restrict__ st
             gap -= 255u;
         }
         pos += skipped;
-        if (!hits) continue;
+        if (!hits) {
+            v = ahead;
+            continue;
+        }
         const uint32_t m = __shfl_sync(0xffffffffu, v, (int)skipped);
         const uint32_t len = m >> kLzBackBits, back = m & ((1u << kLzBackBits) - 1u);
         if (lane == 0) {  // lz.hpp:85-91
@@ -2538,6 +2658,7 @@ __global__ void __launch_bounds__(128) k_lz_walk(const uint32_t* __restrict__ st
         gap = 0;
         for (uint32_t k = lane; k < len; k += 32) N[pos + k] = 1;  // lz.hpp:92-94
         pos += len;                                                 // :95
+        v = pos + lane < npx ? S[pos + lane] : 0u;
     }
     if (lane == 0) {
         counts[tile * 4u + 0] = c0;
@@ -2588,6 +2709,33 @@ __global__ void __launch_bounds__(128) k_lz_assemble(const hoh_stream_result* __
         lz_size[tile] = at;
         if (status) status[tile] = st;
     }
+}
+
+// layer_encode.hpp:93-99: residuals of LZ-covered pixels are dropped (stable compaction, in place).  One
+// warp per stream; the stream descriptor's symbol count becomes the number of kept residuals.
+__global__ void __launch_bounds__(128) k_compact_nuke(TileGeom g, uint64_t n_tiles, const uint8_t* __restrict__ nuke,
+                                                      uint32_t nuke_stride, uint16_t* __restrict__ resid,
+                                                      hoh_enc_stream* __restrict__ streams) {
+    const uint32_t lane = lane_id();
+    const uint64_t s = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_tiles * 3u) return;
+    const uint64_t t = s / 3u;
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
+    const uint32_t n = tw * th;
+    const uint8_t* N = nuke + t * nuke_stride;
+    uint16_t* R = resid + s * g.plane_stride;
+    uint32_t kept = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        const bool keep = i < n && N[i] == 0;
+        const uint16_t v = i < n ? R[i] : (uint16_t)0;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();  // every lane has read its element before any lane overwrites an earlier position
+        if (keep) R[kept + __popc(m & ((1u << lane) - 1u))] = v;
+        kept += __popc(m);
+    }
+    if (lane == 0) streams[s].n = kept;
 }
 
 }  // namespace hohk

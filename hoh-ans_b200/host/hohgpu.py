@@ -113,6 +113,7 @@ SIGNATURES = {
     "hoh_predictor_search_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _vp, _vp]),
     "hoh_find_lz_stride": (_sz, [_int, _int]),
     "hoh_find_lz_rgb_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "hoh_find_lz_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "hoh_find_lz_rgb": (_int, [_vp, _vp, _sz, _int, _int, _vp, _sz, _vp, _int, _int, C.POINTER(_sz)]),
     "hoh_layer_encode_out_bytes": (_sz, [_sz, _int, _int, _int, _int]),
     "hoh_layer_encode_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _sz, _vp, _vp, _sz, _vp]),
@@ -510,6 +511,39 @@ class HohGpu:
                 if buf is not None:
                     buf.free()
         return [(lz[i, :int(sizes[i])].copy(), nuke[i].copy(), int(st[i])) for i in range(n_tiles)]
+
+    def encode_tiles_s0_lz(self, rgb, n_images, width, height):
+        """Device-side pieces of encode_tile (choh.cpp:104) at mode 0 for photographic tiles: LZ records +
+        NUKE maps (hoh_find_lz_images) and the three channel payloads coded with those maps
+        (hoh_encode_images_s0) -> (list of lz bytes per tile, packed, offsets, results)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
+        g = self.tile_geometry(width, height)
+        n_tiles = n_images * g.tiles_per_image
+        n_streams = n_tiles * 3
+        nuke_stride = (g.tile_w * g.tile_h + 7) & ~7
+        lz_stride = int(self.lib.hoh_find_lz_stride(g.tile_w, g.tile_h))
+        out_bytes = int(self.lib.hoh_encode_images_out_bytes(C.byref(g), n_images))
+        packed_cap = rgb.nbytes * 2 + 4096 * n_streams
+        bufs = [self.alloc(rgb.nbytes).upload(rgb), self.alloc(n_tiles * nuke_stride), self.alloc(n_tiles * lz_stride),
+                self.alloc(n_tiles * 4), self.alloc(n_tiles * 4), self.alloc(out_bytes),
+                self.alloc(n_streams * RESULT_DT.itemsize), self.alloc(packed_cap), self.alloc((n_streams + 1) * 8)]
+        d_rgb, d_nuke, d_lz, d_size, d_st, d_out, d_res, d_packed, d_off = bufs
+        try:
+            self._ck(self.lib.hoh_find_lz_images(self.ctx, d_rgb.ptr, n_images, width, height, 6, None, d_nuke.ptr,
+                                                 d_lz.ptr, lz_stride, d_size.ptr, d_st.ptr), "hoh_find_lz_images")
+            self._ck(self.lib.hoh_encode_images_s0(self.ctx, d_rgb.ptr, n_images, width, height, d_nuke.ptr, d_out.ptr,
+                                                   out_bytes, d_res.ptr, d_packed.ptr, packed_cap, d_off.ptr),
+                     "hoh_encode_images_s0")
+            assert (d_st.download(np.int32, n_tiles) == 0).all()
+            sizes = d_size.download(np.uint32, n_tiles)
+            lz = d_lz.download(np.uint8, n_tiles * lz_stride).reshape(n_tiles, lz_stride)
+            off = d_off.download(np.uint64, n_streams + 1)
+            res = d_res.download(RESULT_DT, n_streams)
+            packed = d_packed.download(np.uint8, int(off[-1]))
+        finally:
+            for b in bufs:
+                b.free()
+        return [lz[t, :int(sizes[t])].copy() for t in range(n_tiles)], packed, off, res
 
     def layer_encode_batch(self, planes, n_planes, w, h, depth, mode):
         """layer_encode.hpp:11 for n_planes planes of the same shape -> list of (payload bytes, status, kept slot)."""

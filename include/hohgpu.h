@@ -185,8 +185,9 @@ size_t hoh_encode_images_out_bytes(const hoh_tile_geometry* g, size_t n_images);
 
 /* Encode n_images interleaved RGB8 images (d_rgb: n_images * height * width * 3 bytes) at cruncher
  * mode 0 with the subtract-green colour mode (choh.cpp:219-255) and no LZ matches (NUKE == 0; pass
- * d_nuke = NULL) or a caller-computed LEMPEL_NUKE map (d_nuke: one byte per pixel in TILE-major
- * order, i.e. for each image, for each tile, tile_w*tile_h bytes in raster order).
+ * d_nuke = NULL) or the LEMPEL_NUKE map hoh_find_lz_images writes (d_nuke: one byte per pixel, tile t's
+ * map in raster order at t * nuke_stride, nuke_stride = tile_w*tile_h rounded up to 8): the residuals of
+ * covered pixels are dropped before entropy coding (layer_encode.hpp:93-99).
  * For stream s = (image * tiles_per_image + tile) * 3 + channel, d_results[s] gives the byte range in
  * d_out holding exactly what layer_encode() writes for that channel ("10 00 00 00 10" + stream).
  * If d_packed != NULL the channel payloads are also gathered back to back in stream order into
@@ -275,6 +276,14 @@ size_t hoh_find_lz_stride(int w, int h);
 int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, int w, int h, int distance,
                           const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
                           uint32_t* d_lz_size, int32_t* d_status);
+
+/* The same for whole images: every image is cut into tiles as choh.cpp:454-484 cuts it and find_lz_rgb runs
+ * on each tile (tile index = image * tiles_per_image + tile, as everywhere in this header).  d_nuke holds
+ * n_tiles * nuke_stride bytes with nuke_stride = tile_w*tile_h rounded up to 8 (tile t's map starts at
+ * t * nuke_stride; it is the map hoh_encode_images_s0 takes); lz_stride >= hoh_find_lz_stride(tile_w, tile_h). */
+int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
+                       int distance, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
+                       uint32_t* d_lz_size, int32_t* d_status);
 
 /* layer_encode.hpp:11 for n_planes planes of the same geometry (w x h, depth, cruncher mode 0..4, all
  * NUKE == 0): the reference's decision sequence — which candidates are entropy-coded, in which order,

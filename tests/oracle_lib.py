@@ -269,6 +269,48 @@ def lz_test_image(rng, w, h, kind):
     return np.ascontiguousarray(img, dtype=np.uint8)
 
 
+def photo_with_repeats(rng, w, h, seed):
+    """A photographic image (> 256 colours, so encode_tile stays in sub-green mode) with runs repeated a short
+    distance to the left and smeared runs, so that find_lz_rgb finds matches inside its 64-pixel -s0 window."""
+    img = synth_rgb(w, h, seed).reshape(h, w, 3).copy()
+    for _ in range(max(8, w * h // 2000)):
+        n, d = int(rng.integers(4, 50)), int(rng.integers(1, 60))
+        y, x = int(rng.integers(0, h)), int(rng.integers(d, max(d + 1, w - n)))
+        n = min(n, w - x)
+        for k in range(n):                      # forward copy: overlapping runs behave like LZ copies
+            img[y, x + k] = img[y, x + k - d]
+    return img
+
+
+def orc_subtract_green(rgb):
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
+    n = rgb.size // 3
+    g, rg, bg = (np.zeros(n, np.uint16) for _ in range(3))
+    oracle().orc_subtract_green(rgb, rgb.size, g, rg, bg)
+    return g, rg, bg
+
+
+def varint_bytes(v):
+    out = np.zeros(4, np.uint8)
+    n = oracle().orc_write_varint(out, 0, v)
+    return out[:n].tobytes()
+
+
+def orc_encode_tile_subgreen(tile, mode=0):
+    """encode_tile (choh.cpp:104-382) for a tile that stays in sub-green mode (not grey, > 256 colours, RGB
+    alternative not smaller): header, LZ record, channel-order byte, size varints, three channel payloads.
+    tile: (h, w, 3) u8.  Returns (bytes, nuke map)."""
+    tile = np.ascontiguousarray(tile, dtype=np.uint8)
+    h, w = tile.shape[:2]
+    distance, bonus = orc_lz_params(tile, mode)
+    lz, nuke, _ = orc_find_lz_rgb(tile, w, distance, bonus)
+    g, rg, bg = orc_subtract_green(tile)
+    ch = [orc_layer_encode(p, w, h, d, mode, nuke)[0].tobytes() for p, d in ((g, 8), (rg, 9), (bg, 9))]
+    out = (bytes([0, 0, 128]) + lz.tobytes() + bytes([0b00100100]) + varint_bytes(len(ch[0])) +
+           varint_bytes(len(ch[1])) + b"".join(ch))
+    return out, nuke
+
+
 def orc_layer_encode(plane, w, h, depth, mode, nuke=None):
     plane = np.ascontiguousarray(plane, dtype=np.uint16)
     if nuke is None:

@@ -59,3 +59,38 @@ def test_find_lz_rgb_synthetic_photo_has_constant_record():
     for lz, nuke, st in got:
         assert st == 0 and not nuke.any()
         assert np.array_equal(lz, want)
+
+
+def _varint(v):
+    if v < 128:
+        return bytes([v])
+    if v < (1 << 14):
+        return bytes([0x80 | (v >> 7), v & 0x7f])
+    return bytes([0x80 | (v >> 14), 0x80 | ((v >> 7) & 0x7f), v & 0x7f])
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (512, 512), (200, 120), (600, 512)])
+def test_encode_tile_s0_with_lz_matches_reference_bytes(w, h):
+    """encode_tile (choh.cpp:104-382) at -s0 for photographic tiles with LZ matches: the tile bytes assembled by
+    the host rules of choh.cpp:112-116, 328-363 from the device's LZ record, NUKE-compacted channel payloads and
+    sizes equal the reference's (the oracle's tile encoder = find_lz_rgb + subtract_green + 3 x layer_encode)."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(w + h)
+    n_images = 3
+    imgs = [ol.photo_with_repeats(rng, w, h, 40 + i) for i in range(n_images)]
+    lz, packed, off, res = g.encode_tiles_s0_lz(np.concatenate([i.ravel() for i in imgs]), n_images, w, h)
+    assert (res["status"] == 0).all()
+    geo = g.tile_geometry(w, h)
+    nuked = 0
+    for i, img in enumerate(imgs):
+        for t in range(geo.tiles_per_image):
+            x0, y0 = (t % geo.x_tiles) * geo.tile_w, (t // geo.x_tiles) * geo.tile_h
+            tile = np.ascontiguousarray(img[y0:y0 + geo.tile_h, x0:x0 + geo.tile_w])
+            want, nuke = ol.orc_encode_tile_subgreen(tile, 0)
+            nuked += int(nuke.sum())
+            s = (i * geo.tiles_per_image + t) * 3
+            got_ch = [packed[int(off[s + c]):int(off[s + c + 1])].tobytes() for c in range(3)]
+            got = (bytes([0, 0, 128]) + lz[i * geo.tiles_per_image + t].tobytes() + bytes([0b00100100]) +
+                   _varint(len(got_ch[0])) + _varint(len(got_ch[1])) + b"".join(got_ch))
+            assert got == want, (i, t, len(got), len(want))
+    assert nuked > 100

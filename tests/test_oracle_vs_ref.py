@@ -257,3 +257,18 @@ def test_lz_params_pinned_against_reference():
         img = pal[idx].ravel()
         want = ol.ref().ref_count_colours(img, img.size)
         assert ol.oracle().orc_count_colours(img, img.size) == want == (ncol if ncol <= 256 else -1)
+
+
+def test_encode_tile_subgreen_with_lz_pinned_against_reference():
+    """choh.cpp:104-382 at -s0 on photographic tiles with repeats: the oracle's pieces (find_lz_rgb, NUKE-aware
+    layer_encode) assembled by encode_tile's rules give the reference's tile bytes."""
+    rng = np.random.default_rng(9)
+    nuked = 0
+    for it, (w, h) in enumerate([(64, 64), (120, 75), (256, 256)]):
+        img = ol.photo_with_repeats(rng, w, h, 100 + it)
+        got, nuke = ol.orc_encode_tile_subgreen(img, 0)
+        buf = np.zeros(img.size * 3 + 4096, np.uint8)
+        n = ol.ref().ref_encode_tile(np.ascontiguousarray(img).ravel(), img.size, buf, w, h, 0)
+        assert got == buf[:n].tobytes(), (it, w, h)
+        nuked += int(nuke.sum())
+    assert nuked > 50
