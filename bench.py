@@ -196,8 +196,9 @@ def _cpu_worker(args):
     lib = gpu_mod.load_library()  # hoh_tile_geometry_for is pure host arithmetic (choh.cpp:454-460)
     g = gpu_mod.TileGeometry()
     lib.hoh_tile_geometry_for(w, h, C.byref(g))
-    t_enc = t_dec = 0.0
+    t_enc = t_dec = t_lz = 0.0
     nuke = np.zeros(g.tile_w * g.tile_h, np.uint8)
+    lz_out = np.zeros(g.tile_w * g.tile_h * 2 + 8192, np.uint8)
     mask = np.array([0x0010], np.uint16)
     no_backref = np.zeros(g.tile_w * g.tile_h, np.uint16)
     for i in range(count):
@@ -239,9 +240,17 @@ def _cpu_worker(args):
             back = np.empty(px * 3, np.uint8)
             O.orc_add_green(dec[0], dec[1], dec[2], px, back)  # the reference has no inverse (D4)
             t2 = time.perf_counter()
+            # the LZ match finder (lz.hpp:6, seek distance 6 at -s0): timed on its own, not part of `value`
+            lz_nuke = np.zeros(px, np.uint8)
+            if use_ref:
+                R.ref_find_lz_rgb(tile, tile.size, tw, th, lz_out, lz_nuke, 6, 0)
+            else:
+                O.orc_find_lz_rgb(tile, tile.size, tw, 6, 0, lz_out, lz_nuke, None, None)
+            t3 = time.perf_counter()
             t_enc += t1 - t0
             t_dec += t2 - t1
-    return t_enc, t_dec, count * w * h * 3, use_ref
+            t_lz += t3 - t2
+    return t_enc, t_dec, count * w * h * 3, use_ref, t_lz
 
 
 def cpu_hot_path(sample_images, w, h, cores, seed0=1):
@@ -261,7 +270,8 @@ def cpu_hot_path(sample_images, w, h, cores, seed0=1):
     raw = sum(r[2] for r in res)
     slowest = max(r[0] + r[1] for r in res)
     return {"value": 2 * raw / slowest / 1e6, "encode_mbs": raw / max(r[0] for r in res) / 1e6,
-            "decode_mbs": raw / max(r[1] for r in res) / 1e6, "kind": "reference" if res[0][3] else "port",
+            "decode_mbs": raw / max(r[1] for r in res) / 1e6, "lz_mbs": raw / max(r[4] for r in res) / 1e6,
+            "kind": "reference" if res[0][3] else "port",
             "cores": len(jobs), "wall_s": wall, "busy_s": slowest, "images": sample_images}
 
 
@@ -273,6 +283,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images", type=int, default=4096, help="images per GPU")
+    ap.add_argument("--no-lz", action="store_true", help="skip the LZ match finder timing")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = 4 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -399,6 +410,32 @@ def main():
     decode_dev()
     prof = g.profile_end()
 
+    # the LZ match finder on the same resident batch (reported beside `value`, not in it)
+    lz = None
+    if not args.no_lz:
+        geo = g.tile_geometry(W, H)
+        n_tiles = n_img * geo.tiles_per_image
+        nuke_stride = (geo.tile_w * geo.tile_h + 7) & ~7
+        lz_stride = int(lib.hoh_find_lz_stride(geo.tile_w, geo.tile_h))
+        lz_bufs = [g.alloc(n_tiles * nuke_stride), g.alloc(n_tiles * lz_stride), g.alloc(n_tiles * 4), g.alloc(n_tiles * 4)]
+
+        def lz_dev():
+            g._ck(lib.hoh_find_lz_images(ctx, d_rgb.ptr, n_img, W, H, 6, None, lz_bufs[0].ptr, lz_bufs[1].ptr, lz_stride,
+                                         lz_bufs[2].ptr, lz_bufs[3].ptr), "hoh_find_lz_images")
+        lz_dev()
+        g.sync()
+        l0 = g.launch_count()
+        g.timer_start(1)
+        for _ in range(steps):
+            lz_dev()
+        g.timer_stop(1)
+        lz_ms = g.timer_ms(1) / steps
+        lz_ok = bool((lz_bufs[3].download(np.int32, n_tiles) == 0).all())
+        lz = {"ms": lz_ms, "mbs": raw / (lz_ms / 1e3) / 1e6, "launches_per_call": (g.launch_count() - l0) // steps,
+              "ok": lz_ok, "nuked_pixels": int(np.count_nonzero(lz_bufs[0].download(np.uint8, min(n_tiles, 64) * nuke_stride)))}
+        for b in lz_bufs:
+            b.free()
+
     # e2e: host buffers through the C-ABI, copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -496,6 +533,11 @@ def main():
                          "share_of_step": top_ms / step_ms_prof},
             "kernels_ms": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
         }
+        if lz:
+            line["lz_find"] = {"what": "find_lz_rgb (lz.hpp:6) for every tile of the batch on the device, seek distance 6; "
+                                       "not included in value/e2e (BASELINE keeps LZ beside the metric)",
+                               "ms_per_batch": lz["ms"], "raw_mbs_per_gpu": lz["mbs"], "gpu_launches": lz["launches_per_call"],
+                               "status_ok": lz["ok"], "nuked_pixels_first_tiles": lz["nuked_pixels"]}
         if e2e:
             line["e2e"] = {"value": 2 * job_raw / (e2e["ms"] / 1e3) / 1e6, "unit": "MB/s",
                            "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
@@ -507,6 +549,7 @@ def main():
             cb = cpu_hot_path(sample, W, H, cores, seed0=1)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "MB/s", "cores": cb["cores"], "kind": cb["kind"],
                                     "encode_mbs": cb["encode_mbs"], "decode_mbs": cb["decode_mbs"],
+                                    "lz_find_mbs": cb["lz_mbs"],
                                     "sample": f"{sample} of the {n_img} images, one process per core, hot path only "
                                               f"(host LZ excluded on both arms), busy time of the slowest worker"}
         print(json.dumps(line))

@@ -883,6 +883,14 @@ int hoh_add_green_dev(hoh_ctx* ctx, const uint16_t* d_g, const uint16_t* d_rg, c
     return HOH_OK;
 }
 
+int hoh_channel_picker_dev(hoh_ctx* ctx, const uint8_t* d_src, size_t n_px, int total, int target, uint16_t* d_out) {
+    if (!ctx || !d_src || !d_out || total <= 0 || target < 0 || target >= total) return HOH_E_ARG;
+    if (n_px == 0) return HOH_OK;
+    k_channel_picker<<<grid_cap(n_px, 256), 256, 0, ctx->stream>>>(d_src, n_px, (uint32_t)total, (uint32_t)target, d_out);
+    LAUNCHED("k_channel_picker");
+    return HOH_OK;
+}
+
 int hoh_predict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
                              uint16_t* d_resid) {
     if (!ctx || !d_planes || !d_resid || w <= 0 || h <= 0 || depth < 1 || depth > 9) return HOH_E_ARG;
@@ -1052,10 +1060,12 @@ size_t hoh_layer_encode_out_bytes(size_t n_planes, int w, int h, int depth, int 
 }
 
 int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
-                           int mode, uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
+                           int mode, const uint8_t* d_nuke, size_t nuke_stride, uint32_t planes_per_map,
+                           uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
                            uint8_t* d_packed, size_t packed_cap, uint64_t* d_packed_off) {
     if (!ctx || !d_planes || !d_out || !d_results || w <= 0 || h <= 0 || depth < 1 || depth > 9 || mode < 0 || mode > 4)
         return HOH_E_ARG;
+    if (d_nuke && (planes_per_map == 0 || nuke_stride < (size_t)w * h)) return HOH_E_ARG;
     if (n_planes == 0) return HOH_OK;
     if ((uint64_t)w * h >= (1u << 21)) return HOH_E_UNSUPPORTED;  // varint.hpp:39-45
     const LayerGeom lg = layer_geom(w, h, depth, mode);
@@ -1064,7 +1074,7 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     const size_t n = n_planes;
     uint16_t *syms, *maps;
     uint8_t *idx, *hdr;
-    uint32_t *n_used, *hdr_len, *kept, *best;
+    uint32_t *n_used, *hdr_len, *kept, *best, *kept_px = nullptr;
     int32_t* status;
     hoh_enc_stream* streams;
     hoh_stream_result *rr, *res;
@@ -1072,10 +1082,11 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     TRY(scratch_t(ctx, S_L_MAPS, n * (lg.cells ? lg.cells : 1), &maps));
     TRY(scratch_t(ctx, S_L_IDX, n * (lg.cells ? lg.cells : 1), &idx));
     TRY(scratch_t(ctx, S_L_HDR, n * kLayerHdrCap, &hdr));
-    TRY(scratch_t(ctx, S_L_U32, 4 * n, &n_used));
+    TRY(scratch_t(ctx, S_L_U32, 5 * n, &n_used));
     hdr_len = n_used + n;
     kept = hdr_len + n;
     best = kept + n;
+    if (d_nuke) kept_px = best + n;
     TRY(scratch_t(ctx, S_L_STATUS, n, &status));
     TRY(scratch_t(ctx, S_STREAMS, 3 * n, &streams));
     TRY(scratch_t(ctx, S_L_RR, 3 * n, &rr));
@@ -1085,7 +1096,7 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     uint16_t* resid1 = syms + n * lg.per_pad;
     const uint32_t range = 1u << depth;
     auto run_round = [&](int round, size_t count, uint32_t max_range, uint32_t max_pb) -> int {
-        k_layer_streams<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, n_used, res, streams);
+        k_layer_streams<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, n_used, kept_px, res, streams);
         LAUNCHED("k_layer_streams");
         TRY(hoh_encode_entropy_batch(ctx, streams, count, syms, d_out, rr, max_range, max_pb, lg.per));
         k_layer_scatter<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(n, round, rr, res);
@@ -1096,10 +1107,20 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     k_predict_fastpath<<<grid_cap(n * (uint64_t)lg.per, 256), 256, 0, ctx->stream>>>(d_planes, n, w, h, depth, resid0,
                                                                                   lg.per_pad);
     LAUNCHED("k_predict_fastpath");
+    auto compact = [&](uint16_t* resid) -> int {  // :93-99, :328-333
+        if (!d_nuke) return HOH_OK;
+        k_compact_planes<<<blocks_for(n * 32, 128), 128, 0, ctx->stream>>>(n, lg.per, lg.per_pad, d_nuke, nuke_stride,
+                                                                          planes_per_map, resid, kept_px);
+        LAUNCHED("k_compact_planes");
+        return HOH_OK;
+    };
+    TRY(compact(resid0));
     TRY(run_round(0, n, range, 15));
     if (mode >= 1) {
-        if (lg.cells)  // :126-272
+        if (lg.cells) {  // :126-272
             TRY(predictor_search_impl(ctx, d_planes, n, w, h, depth, mode, maps, idx, resid1, lg.per_pad));
+            TRY(compact(resid1));
+        }
         k_layer_headers<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(lg, n, idx, syms, n_used, hdr, hdr_len);
         LAUNCHED("k_layer_headers");
         if (lg.cells) TRY(run_round(1, n, 14, 8));  // :308-317
@@ -1466,6 +1487,16 @@ int hoh_find_lz_rgb(hoh_ctx* ctx, const uint8_t* source, size_t size, int width,
     for (size_t i = 0; i < npx; i++) nukemap[i] |= nk[i];
     *lz_size = n;
     return HOH_OK;
+}
+
+int hoh_channel_picker(hoh_ctx* ctx, const uint8_t* src, size_t size, int total, int target, uint16_t* out) {
+    if (!ctx || !src || !out || total <= 0 || size % (size_t)total) return HOH_E_ARG;
+    uint8_t* d_in;
+    uint16_t* d_out;
+    TRY(stage_in(ctx, S_IO_A, src, size, &d_in));
+    TRY(scratch_t(ctx, S_IO_B, size / total, &d_out));
+    TRY(hoh_channel_picker_dev(ctx, d_in, size / total, total, target, d_out));
+    return stage_out(ctx, out, d_out, size / total);
 }
 
 }  // extern "C"

@@ -2182,6 +2182,7 @@ struct LayerGeom {
 // bits (range = number of masks used).  round 2: C, D = final residuals at 16 and 15 bits.  round 3: E, F, G
 // = 17, 18, 19 bits if C beat D (layer_encode.hpp:359-374) else 14, 13, 12 (:376-392).
 __global__ void k_layer_streams(LayerGeom lg, uint64_t n_planes, int round, const uint32_t* __restrict__ n_used,
+                                const uint32_t* __restrict__ kept_px,
                                 const hoh_stream_result* __restrict__ results, hoh_enc_stream* __restrict__ streams) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint32_t per_round = round == 0 ? 1u : (round == 1 ? 1u : (round == 2 ? 2u : 3u));
@@ -2196,7 +2197,7 @@ __global__ void k_layer_streams(LayerGeom lg, uint64_t n_planes, int round, cons
     for (int b = 0; b < 8; b++) st.prefix[b] = 0;
     st.reserved = 0;
     st.range = 1u << lg.depth;
-    st.n = lg.per;
+    st.n = kept_px ? kept_px[p] : lg.per;  // residuals left after NUKE compaction (layer_encode.hpp:93-99, 328-333)
     uint32_t slot;
     if (round == 0) {
         slot = 0;
@@ -2736,6 +2737,37 @@ __global__ void __launch_bounds__(128) k_compact_nuke(TileGeom g, uint64_t n_til
         kept += __popc(m);
     }
     if (lane == 0) streams[s].n = kept;
+}
+
+// layer_encode.hpp:93-99 / 328-333 for plane residuals: plane p uses NUKE map p / planes_per_map.  In place,
+// one warp per plane; kept_px[p] = residuals left.
+__global__ void __launch_bounds__(128) k_compact_planes(uint64_t n_planes, uint32_t per, uint64_t plane_stride,
+                                                        const uint8_t* __restrict__ nuke, uint64_t nuke_stride,
+                                                        uint32_t planes_per_map, uint16_t* __restrict__ resid,
+                                                        uint32_t* __restrict__ kept_px) {
+    const uint32_t lane = lane_id();
+    const uint64_t p = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (p >= n_planes) return;
+    const uint8_t* N = nuke + (p / planes_per_map) * nuke_stride;
+    uint16_t* R = resid + p * plane_stride;
+    uint32_t kept = 0;
+    for (uint32_t base = 0; base < per; base += 32) {
+        const uint32_t i = base + lane;
+        const bool keep = i < per && N[i] == 0;
+        const uint16_t v = i < per ? R[i] : (uint16_t)0;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) R[kept + __popc(m & ((1u << lane) - 1u))] = v;
+        kept += __popc(m);
+    }
+    if (lane == 0) kept_px[p] = kept;
+}
+
+// channel.hpp:63-71: one channel of interleaved bytes -> u16 plane
+__global__ void k_channel_picker(const uint8_t* __restrict__ src, uint64_t n_px, uint32_t total, uint32_t target,
+                                 uint16_t* __restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_px; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = src[i * total + target];
 }
 
 }  // namespace hohk

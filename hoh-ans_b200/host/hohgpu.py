@@ -116,7 +116,10 @@ SIGNATURES = {
     "hoh_find_lz_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "hoh_find_lz_rgb": (_int, [_vp, _vp, _sz, _int, _int, _vp, _sz, _vp, _int, _int, C.POINTER(_sz)]),
     "hoh_layer_encode_out_bytes": (_sz, [_sz, _int, _int, _int, _int]),
-    "hoh_layer_encode_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "hoh_layer_encode_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _sz, _u32, _vp, _sz, _vp, _vp, _sz,
+                                      _vp]),
+    "hoh_channel_picker_dev": (_int, [_vp, _vp, _sz, _int, _int, _vp]),
+    "hoh_channel_picker": (_int, [_vp, _vp, _sz, _int, _int, _vp]),
     "hoh_encode_entropy": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _u32, C.POINTER(_sz), C.POINTER(_int)]),
     "hoh_encode_entropy_8bit": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _u32, C.POINTER(_sz), C.POINTER(_int)]),
     "hoh_decode_entropy": (_int, [_vp, _vp, _sz, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz), C.c_uint,
@@ -545,10 +548,23 @@ class HohGpu:
                 b.free()
         return [lz[t, :int(sizes[t])].copy() for t in range(n_tiles)], packed, off, res
 
-    def layer_encode_batch(self, planes, n_planes, w, h, depth, mode):
-        """layer_encode.hpp:11 for n_planes planes of the same shape -> list of (payload bytes, status, kept slot)."""
+    def channel_picker(self, src, total, target):
+        """channel.hpp:63"""
+        src = np.ascontiguousarray(src, dtype=np.uint8).ravel()
+        out = np.zeros(src.size // total, np.uint16)
+        self._ck(self.lib.hoh_channel_picker(self.ctx, _ptr(src), src.size, total, target, _ptr(out)), "hoh_channel_picker")
+        return out
+
+    def layer_encode_batch(self, planes, n_planes, w, h, depth, mode, nuke=None, planes_per_map=1):
+        """layer_encode.hpp:11 for n_planes planes of the same shape -> list of (payload bytes, status, kept slot).
+        nuke: (n_planes / planes_per_map) maps of w*h bytes, or None."""
         planes = np.ascontiguousarray(planes, dtype=np.uint16).ravel()
         assert planes.size == n_planes * w * h
+        d_nuke = None
+        if nuke is not None:
+            nuke = np.ascontiguousarray(nuke, dtype=np.uint8).ravel()
+            assert nuke.size * planes_per_map == n_planes * w * h
+            d_nuke = self.alloc(nuke.nbytes).upload(nuke)
         out_bytes = int(self.lib.hoh_layer_encode_out_bytes(n_planes, w, h, depth, mode))
         d_pl = self.alloc(planes.nbytes).upload(planes)
         d_out = self.alloc(out_bytes)
@@ -557,15 +573,17 @@ class HohGpu:
         d_packed = self.alloc(packed_cap)
         d_off = self.alloc((n_planes + 1) * 8)
         try:
-            self._ck(self.lib.hoh_layer_encode_batch(self.ctx, d_pl.ptr, n_planes, w, h, depth, mode, d_out.ptr,
+            self._ck(self.lib.hoh_layer_encode_batch(self.ctx, d_pl.ptr, n_planes, w, h, depth, mode,
+                                                     d_nuke.ptr if d_nuke else None, w * h, planes_per_map, d_out.ptr,
                                                      out_bytes, d_res.ptr, d_packed.ptr, packed_cap, d_off.ptr),
                      "hoh_layer_encode_batch")
             off = d_off.download(np.uint64, n_planes + 1)
             res = d_res.download(RESULT_DT, n_planes)
             packed = d_packed.download(np.uint8, int(off[-1]))
         finally:
-            for b in (d_pl, d_out, d_res, d_packed, d_off):
-                b.free()
+            for b in (d_pl, d_out, d_res, d_packed, d_off, d_nuke):
+                if b is not None:
+                    b.free()
         return [(packed[int(off[i]):int(off[i + 1])].tobytes(), int(res[i]["status"]), int(res[i]["stored"]))
                 for i in range(n_planes)]
 

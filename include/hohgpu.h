@@ -224,6 +224,9 @@ int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t p
 /* ------------------------------------------------------------------------------------------ */
 /* (ii) batched plane kernels (device pointers; planes are u16, raster order, back to back)     */
 /* ------------------------------------------------------------------------------------------ */
+/* channel_picker channel.hpp:63-71: channel `target` of `total`-byte interleaved pixels -> u16 plane. */
+int hoh_channel_picker_dev(hoh_ctx* ctx, const uint8_t* d_src, size_t n_px, int total, int target, uint16_t* d_out);
+
 /* channel.hpp:73 subtract_green over `pixels` interleaved RGB8 pixels. */
 int hoh_subtract_green_dev(hoh_ctx* ctx, const uint8_t* d_rgb, size_t pixels, uint16_t* d_g,
                            uint16_t* d_rg, uint16_t* d_bg);
@@ -285,17 +288,21 @@ int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint
                        int distance, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
                        uint32_t* d_lz_size, int32_t* d_status);
 
-/* layer_encode.hpp:11 for n_planes planes of the same geometry (w x h, depth, cruncher mode 0..4, all
- * NUKE == 0): the reference's decision sequence — which candidates are entropy-coded, in which order,
+/* layer_encode.hpp:11 for n_planes planes of the same geometry (w x h, depth, cruncher mode 0..4): the
+ * reference's decision sequence — which candidates are entropy-coded, in which order,
  * which buffer is finally emitted, including the stale-buffer behaviour of SURVEY D7 — replayed with the
  * batched kernels (fastpath residuals, predictor search, up to seven entropy-coding passes per plane).
  * d_results[p] (start, size) locates plane p's channel payload in d_out (capacity out_bytes >=
  * hoh_layer_encode_out_bytes); .stored holds the index of the candidate whose bytes were kept.
+ * d_nuke = NULL, or LEMPEL_NUKE maps (one byte per pixel): plane p uses the map at
+ * d_nuke + (p / planes_per_map) * nuke_stride — e.g. planes_per_map = 3 when the planes are the G, R-G, B-G
+ * planes of consecutive tiles — and the residuals of covered pixels are dropped (layer_encode.hpp:93-99, 328-333).
  * If d_packed != NULL the payloads are also gathered back to back (d_packed_off: n_planes+1 offsets). */
 size_t hoh_layer_encode_out_bytes(size_t n_planes, int w, int h, int depth, int mode);
 int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
-                           int mode, uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
-                           uint8_t* d_packed, size_t packed_cap, uint64_t* d_packed_off);
+                           int mode, const uint8_t* d_nuke, size_t nuke_stride, uint32_t planes_per_map,
+                           uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results, uint8_t* d_packed,
+                           size_t packed_cap, uint64_t* d_packed_off);
 
 /* ------------------------------------------------------------------------------------------ */
 /* (i) compat shims — host pointers, one reference call each                                    */
@@ -315,6 +322,9 @@ int hoh_decode_entropy(hoh_ctx* ctx, const uint8_t* in, size_t in_size, size_t* 
 /* stattools.hpp:13 normalize_freqs (in place; cum_freqs has size+1 entries). */
 int hoh_normalize_freqs(hoh_ctx* ctx, uint32_t* freqs, uint32_t* cum_freqs, size_t size,
                         uint32_t target_total, int* stream_status);
+/* channel.hpp:63 (host pointers; size = bytes of src) */
+int hoh_channel_picker(hoh_ctx* ctx, const uint8_t* src, size_t size, int total, int target, uint16_t* out);
+
 /* channel.hpp:73 / :63 */
 int hoh_subtract_green(hoh_ctx* ctx, const uint8_t* rgb, size_t size, uint16_t* green, uint16_t* red_g,
                        uint16_t* blue_g);

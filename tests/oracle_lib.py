@@ -296,9 +296,32 @@ def varint_bytes(v):
     return out[:n].tobytes()
 
 
+def orc_channel_picker(src, total, target):
+    src = np.ascontiguousarray(src, dtype=np.uint8).ravel()
+    out = np.zeros(src.size // total, np.uint16)
+    oracle().orc_channel_picker(src, src.size, total, target, out)
+    return out
+
+
+def assemble_tile(lz, colour_mode, chans):
+    """encode_tile's emit rules for three channels (choh.cpp:112-116, 328-363)."""
+    return (bytes([0, 0, colour_mode]) + bytes(lz) + bytes([0b00100100]) + varint_bytes(len(chans[0])) +
+            varint_bytes(len(chans[1])) + b"".join(chans))
+
+
+def pick_colour_mode(sub_green, alt_rb):
+    """choh.cpp:257-327 for a tile that is neither grey nor palettable: sub-green (128) unless the plain R, B
+    planes (only tried at cruncher mode > 2) make the three channels smaller -> (colour mode, channels)."""
+    if alt_rb is not None:
+        rgb_size = len(alt_rb[0]) + len(sub_green[0]) + len(alt_rb[1])      # :289
+        if rgb_size < sum(len(c) for c in sub_green):                       # :309 (the LZ bytes are on both sides)
+            return 2, [sub_green[0], alt_rb[0], alt_rb[1]]
+    return 128, list(sub_green)
+
+
 def orc_encode_tile_subgreen(tile, mode=0):
-    """encode_tile (choh.cpp:104-382) for a tile that stays in sub-green mode (not grey, > 256 colours, RGB
-    alternative not smaller): header, LZ record, channel-order byte, size varints, three channel payloads.
+    """encode_tile (choh.cpp:104-382) for a photographic tile (not grey, > 256 colours): header, LZ record,
+    colour mode competition, channel-order byte, size varints, three channel payloads.
     tile: (h, w, 3) u8.  Returns (bytes, nuke map)."""
     tile = np.ascontiguousarray(tile, dtype=np.uint8)
     h, w = tile.shape[:2]
@@ -306,9 +329,11 @@ def orc_encode_tile_subgreen(tile, mode=0):
     lz, nuke, _ = orc_find_lz_rgb(tile, w, distance, bonus)
     g, rg, bg = orc_subtract_green(tile)
     ch = [orc_layer_encode(p, w, h, d, mode, nuke)[0].tobytes() for p, d in ((g, 8), (rg, 9), (bg, 9))]
-    out = (bytes([0, 0, 128]) + lz.tobytes() + bytes([0b00100100]) + varint_bytes(len(ch[0])) +
-           varint_bytes(len(ch[1])) + b"".join(ch))
-    return out, nuke
+    alt = None
+    if mode > 2:                                                            # :263-290
+        alt = [orc_layer_encode(orc_channel_picker(tile, 3, c), w, h, 8, mode, nuke)[0].tobytes() for c in (0, 2)]
+    colour_mode, chans = pick_colour_mode(ch, alt)
+    return assemble_tile(lz.tobytes(), colour_mode, chans), nuke
 
 
 def orc_layer_encode(plane, w, h, depth, mode, nuke=None):

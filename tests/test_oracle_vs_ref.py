@@ -272,3 +272,22 @@ def test_encode_tile_subgreen_with_lz_pinned_against_reference():
         assert got == buf[:n].tobytes(), (it, w, h)
         nuked += int(nuke.sum())
     assert nuked > 50
+
+
+def test_encode_tile_all_modes_pinned_against_reference():
+    """encode_tile at cruncher modes 1-4 (wider LZ windows, predictor search, prob_bits search, the plain-RGB
+    alternative at modes 3-4) on photographic tiles with repeats; one tile is built so that plain RGB wins."""
+    rng = np.random.default_rng(10)
+    modes_seen, colour_modes = set(), set()
+    for it, (w, h, mode) in enumerate([(96, 80, 1), (100, 64, 2), (90, 70, 3), (64, 96, 4), (80, 80, 3)]):
+        img = ol.photo_with_repeats(rng, w, h, 200 + it)
+        if it == 4:  # decorrelate the channels: subtracting green then only adds noise
+            img[..., 0] = rng.integers(0, 256, (h, w))
+            img[..., 2] = rng.integers(0, 256, (h, w))
+        got, _ = ol.orc_encode_tile_subgreen(img, mode)
+        buf = np.zeros(img.size * 3 + 4096, np.uint8)
+        n = ol.ref().ref_encode_tile(np.ascontiguousarray(img).ravel(), img.size, buf, w, h, mode)
+        assert got == buf[:n].tobytes(), (it, w, h, mode)
+        modes_seen.add(mode)
+        colour_modes.add(got[2])
+    assert modes_seen == {1, 2, 3, 4} and colour_modes == {128, 2}
