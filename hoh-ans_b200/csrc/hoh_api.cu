@@ -4,6 +4,7 @@
 // from hoh_kernels.cuh and fails with HOH_E_CUDA when there is no device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,7 +22,7 @@ namespace {
 enum Slot {
     S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
     S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
-    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_COUNT
+    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_COUNT
 };
 
 struct Buf {
@@ -1049,14 +1050,24 @@ static LayerGeom layer_geom(int w, int h, int depth, int mode) {
     lg.cells_pad = (lg.cells + 7u) & ~7u;
     lg.depth = depth;
     lg.mode = mode;
-    lg.slab = (uint32_t)hoh_enc_slab_bytes(lg.per > lg.cells ? lg.per : lg.cells, HOH_MAX_PROB_BITS);
-    lg.out_cap = (lg.slab + kLayerHdrCap + 2048u + 15u) & ~15u;
+    // candidate slabs sized by what each is coded with: A 15 bits, B the index map at 8, C 16, D 15, E-G up to 19
+    const uint32_t bits_of[kLayerSlots] = {15, 8, 16, 15, 19, 19, 19};
+    uint32_t at = 0, widest = 0;
+    for (int k = 0; k < kLayerSlots; k++) {
+        const bool used = k == 0 || (mode >= 1 && (k != 1 || lg.cells));
+        lg.slot_cap[k] = used ? (uint32_t)hoh_enc_slab_bytes(k == 1 ? lg.cells : lg.per, bits_of[k]) : 0u;
+        lg.slot_off[k] = at;
+        at += lg.slot_cap[k];
+        if (k != 1 && lg.slot_cap[k] > widest) widest = lg.slot_cap[k];
+    }
+    lg.plane_bytes = at;
+    lg.out_cap = (kLayerHdrCap + lg.slot_cap[1] + widest + 15u) & ~15u;
     return lg;
 }
 
 size_t hoh_layer_encode_out_bytes(size_t n_planes, int w, int h, int depth, int mode) {
     const LayerGeom lg = layer_geom(w, h, depth, mode);
-    return n_planes * ((size_t)kLayerSlots * lg.slab + lg.out_cap);
+    return n_planes * ((size_t)lg.plane_bytes + lg.out_cap);
 }
 
 int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
@@ -1132,7 +1143,7 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     }
     k_layer_decide<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(lg, n, res, kept, best, status);
     LAUNCHED("k_layer_decide");
-    const uint64_t out_base = (uint64_t)n * kLayerSlots * lg.slab;
+    const uint64_t out_base = (uint64_t)n * lg.plane_bytes;
     k_layer_assemble<<<(unsigned)n, 256, 0, ctx->stream>>>(lg, hdr, hdr_len, res, kept, best, status, d_out, d_out, out_base,
                                                            d_results);
     LAUNCHED("k_layer_assemble");
@@ -1163,7 +1174,7 @@ namespace {
 // shared body of the two LZ entry points; nuke_stride = elements per tile in d_nuke
 int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles, size_t max_npx, int distance,
                  const int32_t* d_bonus, uint8_t* d_nuke, uint32_t nuke_stride, uint8_t* d_lz, size_t lz_stride,
-                 uint32_t* d_lz_size, int32_t* d_status) {
+                 uint32_t* d_lz_size, int32_t* d_status, uint32_t* d_info = nullptr) {
     if (max_npx >= (1u << 21) * 3ull) return HOH_E_UNSUPPORTED;  // side streams must stay below 2^21 symbols (varint.hpp:39-45)
     const uint32_t stride = lz_side_stride(max_npx);
     const uint32_t slab = (uint32_t)hoh_enc_slab_bytes(stride, 10);
@@ -1186,11 +1197,11 @@ int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles,
     TRY(scratch_t(ctx, S_STREAMS, n_tiles * 4, &streams));
     k_lz_pack<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(d_rgb, sh, px);
     LAUNCHED("k_lz_pack");
-    if (!d_bonus) {
+    if (!d_bonus || d_info) {
         TRY(scratch_t(ctx, S_LZ_BONUS, n_tiles, &bonus));
-        k_lz_bonus<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(px, sh, bonus);
+        k_lz_bonus<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(px, sh, bonus, d_info);
         LAUNCHED("k_lz_bonus");
-        d_bonus = bonus;
+        if (!d_bonus) d_bonus = bonus;
     }
     const uint64_t segs = (sh.stride + kLzSeg - 1) / kLzSeg;
     k_lz_match<<<blocks_for(n_tiles * segs * 32, 128), 128, 0, ctx->stream>>>(px, sh, n_tiles, 1u << distance, wide, state);
@@ -1241,6 +1252,82 @@ int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint
     sh.stride = sh.g.plane_stride;
     return find_lz_impl(ctx, d_rgb, sh, n_images * sh.g.tiles_per_image, (size_t)hg.tile_w * hg.tile_h, distance, d_bonus,
                         d_nuke, sh.g.plane_stride, d_lz, lz_stride, d_lz_size, d_status);
+}
+
+// -------------------------------------------------------------------------------------------------
+// encode_tile for the tiles of whole images, any cruncher mode
+// -------------------------------------------------------------------------------------------------
+int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
+                      int mode, uint8_t* d_packed, size_t packed_cap, uint64_t* d_tile_off,
+                      hoh_tile_result* d_tiles) {
+    if (!ctx || !d_rgb || !d_packed || !d_tile_off || !d_tiles || mode < 0 || mode > 4) return HOH_E_ARG;
+    hoh_tile_geometry hg;
+    TRY(hoh_tile_geometry_for(width, height, &hg));
+    if (width % hg.x_tiles || height % hg.y_tiles) return HOH_E_UNSUPPORTED;  // unequal tiles: not in this round
+    CK(cudaMemsetAsync(d_tile_off, 0, sizeof(uint64_t), ctx->stream));
+    if (n_images == 0) return HOH_OK;
+    const TileGeom g = to_geom(hg);
+    const int tw = (int)hg.tile_w, th = (int)hg.tile_h;
+    const size_t npx = (size_t)tw * th;
+    static const int dist_of_mode[5] = {6, 10, 11, 12, 14};  // choh.cpp:123-136
+    const int distance = dist_of_mode[mode];
+    const uint32_t per8 = mode > 2 ? 3u : 1u;
+    const size_t lz_stride = hoh_find_lz_stride(tw, th);
+    const size_t out8_tile = hoh_layer_encode_out_bytes(per8, tw, th, 8, mode);
+    const size_t out9_tile = hoh_layer_encode_out_bytes(2, tw, th, 9, mode);
+    // scratch per tile: this function's buffers + what the LZ finder and layer_encode_batch allocate themselves
+    const size_t lz_words = (1u << distance) + (npx + kLzSeg) + 32 * kLzAhead;
+    const size_t per_tile = (per8 + 2) * npx * 2 + out8_tile + out9_tile + lz_stride + g.plane_stride +
+                            lz_words * 4 + npx * 4 + 4 * (size_t)lz_side_stride(npx) * 2 +
+                            4 * hoh_enc_slab_bytes(lz_side_stride(npx), 10) + 3 * (2 * npx * 2 + 8192) + 4096;
+    size_t budget = (size_t)32 << 30;
+    if (const char* e = getenv("HOH_SCRATCH_GB")) budget = (size_t)atof(e) * ((size_t)1 << 30);
+    size_t images_per_chunk = budget / (per_tile * g.tiles_per_image);
+    if (images_per_chunk == 0) images_per_chunk = 1;
+    if (images_per_chunk > n_images) images_per_chunk = n_images;
+    const size_t chunk_tiles = images_per_chunk * g.tiles_per_image;
+    uint8_t *nuke, *lz, *out8, *out9;
+    uint32_t* u32;
+    uint16_t *p8, *p9;
+    hoh_stream_result *r8, *r9;
+    TRY(scratch_t(ctx, S_T_NUKE, chunk_tiles * g.plane_stride, &nuke));
+    TRY(scratch_t(ctx, S_T_LZ, chunk_tiles * lz_stride, &lz));
+    TRY(scratch_t(ctx, S_T_U32, chunk_tiles * 3, &u32));
+    TRY(scratch_t(ctx, S_T_P8, chunk_tiles * per8 * npx, &p8));
+    TRY(scratch_t(ctx, S_T_P9, chunk_tiles * 2 * npx, &p9));
+    TRY(scratch_t(ctx, S_T_O8, chunk_tiles * out8_tile, &out8));
+    TRY(scratch_t(ctx, S_T_O9, chunk_tiles * out9_tile, &out9));
+    TRY(scratch_t(ctx, S_T_R8, chunk_tiles * per8, &r8));
+    TRY(scratch_t(ctx, S_T_R9, chunk_tiles * 2, &r9));
+    uint32_t* lz_size = u32;
+    int32_t* lz_status = reinterpret_cast<int32_t*>(u32 + chunk_tiles);
+    uint32_t* info = u32 + 2 * chunk_tiles;
+    for (size_t img0 = 0; img0 < n_images; img0 += images_per_chunk) {
+        const size_t ni = std::min(images_per_chunk, n_images - img0);
+        const size_t nt = ni * g.tiles_per_image, first = img0 * g.tiles_per_image;
+        const uint8_t* rgb = d_rgb + img0 * (size_t)width * height * 3;
+        LzShape sh;
+        memset(&sh, 0, sizeof(sh));
+        sh.tiled = 1;
+        sh.g = g;
+        sh.stride = g.plane_stride;
+        TRY(find_lz_impl(ctx, rgb, sh, nt, npx, distance, nullptr, nuke, g.plane_stride, lz, lz_stride, lz_size, lz_status,
+                         info));
+        k_tile_planes<<<(unsigned)nt, 256, 0, ctx->stream>>>(rgb, g, 0, per8, p8, p9);
+        LAUNCHED("k_tile_planes");
+        TRY(hoh_layer_encode_batch(ctx, p8, nt * per8, tw, th, 8, mode, nuke, g.plane_stride, per8, out8, nt * out8_tile, r8,
+                                   nullptr, 0, nullptr));
+        TRY(hoh_layer_encode_batch(ctx, p9, nt * 2, tw, th, 9, mode, nuke, g.plane_stride, 2, out9, nt * out9_tile, r9,
+                                   nullptr, 0, nullptr));
+        k_tile_decide<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, first, per8, r8, r9, lz_size, lz_status, info, d_tiles);
+        LAUNCHED("k_tile_decide");
+        k_tile_scan<<<1, 1024, 0, ctx->stream>>>(d_tiles, first, (uint32_t)nt, d_tile_off);
+        LAUNCHED("k_tile_scan");
+        k_tile_emit<<<(unsigned)nt, 256, 0, ctx->stream>>>(first, per8, r8, r9, out8, out9, lz, (uint32_t)lz_stride, d_tiles,
+                                                          d_packed, packed_cap);
+        LAUNCHED("k_tile_emit");
+    }
+    return HOH_OK;
 }
 
 // =================================================================================================

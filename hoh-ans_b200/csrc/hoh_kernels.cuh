@@ -2174,7 +2174,9 @@ struct LayerGeom {
     uint32_t cells_pad;
     uint32_t xt, yt;
     uint32_t depth, mode;
-    uint32_t slab;        // bytes of one candidate slab
+    uint32_t slot_off[7]; // byte offset of each candidate's slab inside a plane's block (kLayerSlots entries)
+    uint32_t slot_cap[7]; // ... and its capacity (sized for the candidate's prob_bits; 0 = not used at this mode)
+    uint32_t plane_bytes; // candidate bytes per plane
     uint32_t out_cap;     // bytes of one assembled channel payload
 };
 
@@ -2220,8 +2222,8 @@ __global__ void k_layer_streams(LayerGeom lg, uint64_t n_planes, int round, cons
         const bool up = c.size < d.size;  // layer_encode.hpp:357
         st.prob_bits = up ? 17u + k : 14u - k;
     }
-    st.out_off = (p * kLayerSlots + slot) * (uint64_t)lg.slab;
-    st.out_cap = lg.slab;
+    st.out_off = p * (uint64_t)lg.plane_bytes + lg.slot_off[slot];
+    st.out_cap = lg.slot_cap[slot];
     streams[round == 2 ? p * 2 + k : (round == 3 ? p * 3 + k : p)] = st;
 }
 
@@ -2568,8 +2570,9 @@ __global__ void __launch_bounds__(128) k_lz_match(const uint32_t* __restrict__ p
 
 // choh.cpp:17-50 + :134-154: distinct colours of a tile (more than 256 = "many") -> break-even bonus.
 // One CTA per tile, open-addressing hash set in shared memory.
+// info (optional): bit 31 = every pixel is grey (grey_test channel.hpp:21), low bits = colours (257 = more than 256)
 __global__ void __launch_bounds__(256) k_lz_bonus(const uint32_t* __restrict__ px, LzShape sh,
-                                                  int32_t* __restrict__ bonus) {
+                                                  int32_t* __restrict__ bonus, uint32_t* __restrict__ info) {
     uint32_t npx, width_unused;
     lz_dims(sh, blockIdx.x, npx, width_unused);
     __shared__ uint32_t s_set[1024];
@@ -2601,6 +2604,15 @@ __global__ void __launch_bounds__(256) k_lz_bonus(const uint32_t* __restrict__ p
     if (threadIdx.x == 0) {
         const uint32_t c = *seen;
         bonus[blockIdx.x] = c > 256u ? 0 : (c <= 4u ? 32 : (c <= 8u ? 20 : (c <= 16u ? 10 : (c <= 32u ? 2 : 0))));
+    }
+    if (info) {
+        bool grey = true;
+        for (uint32_t i = threadIdx.x; i < npx; i += blockDim.x) {
+            const uint32_t v = P[i];
+            grey &= (v & 0xffu) == ((v >> 8) & 0xffu) && (v & 0xffu) == (v >> 16);
+        }
+        const int all_grey = __syncthreads_and(grey);
+        if (threadIdx.x == 0) info[blockIdx.x] = min(*seen, 257u) | (all_grey ? 0x80000000u : 0u);
     }
 }
 
@@ -2768,6 +2780,153 @@ __global__ void k_channel_picker(const uint8_t* __restrict__ src, uint64_t n_px,
                                  uint16_t* __restrict__ out) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_px; i += (uint64_t)gridDim.x * blockDim.x)
         out[i] = src[i * total + target];
+}
+
+// =================================================================================================
+// encode_tile (choh.cpp:104-382) for the tiles of whole images, photographic colour modes: what is left
+// around the LZ finder and the batched layer_encode — colour planes of a tile, the colour-mode comparison
+// and the emission of the tile's bytes.
+// =================================================================================================
+// planes8[(t * per8 + k) * npx]: k = 0 green, and (per8 == 3, cruncher mode > 2: choh.cpp:263-290) 1 red, 2 blue;
+// planes9[(t * 2 + k) * npx]: R - G + 256, B - G + 256 (channel.hpp:73-79).  One CTA per tile, uniform tiles.
+__global__ void __launch_bounds__(256) k_tile_planes(const uint8_t* __restrict__ rgb, TileGeom g, uint64_t first_tile,
+                                                     uint32_t per8, uint16_t* __restrict__ planes8,
+                                                     uint16_t* __restrict__ planes9) {
+    const uint64_t lt = blockIdx.x, t = first_tile + lt;
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
+    const uint32_t npx = tw * th;
+    const uint8_t* img = rgb + (t / g.tiles_per_image) * (uint64_t)g.width * g.height * 3u;
+    uint16_t* p8 = planes8 + lt * per8 * (uint64_t)npx;
+    uint16_t* p9 = planes9 + lt * 2u * (uint64_t)npx;
+    for (uint32_t i = threadIdx.x; i < npx; i += blockDim.x) {
+        const uint32_t x = i % tw, y = i / tw;
+        const uint8_t* p = img + ((uint64_t)(y0 + y) * g.width + x0 + x) * 3u;
+        const uint32_t r = p[0], gr = p[1], b = p[2];
+        p8[i] = (uint16_t)gr;
+        if (per8 == 3u) {
+            p8[npx + i] = (uint16_t)r;
+            p8[2u * npx + i] = (uint16_t)b;
+        }
+        p9[i] = (uint16_t)(r + 256u - gr);
+        p9[npx + i] = (uint16_t)(b + 256u - gr);
+    }
+}
+
+constexpr uint32_t kTileGrey = 1u, kTilePalette = 2u;  // = HOH_TILE_GREY, HOH_TILE_PALETTE
+
+// choh.cpp:295-327 (without the palette competitor) + sizes of what :328-363 emits.  One thread per tile.
+__global__ void k_tile_decide(uint64_t n_tiles, uint64_t first_tile, uint32_t per8,
+                              const hoh_stream_result* __restrict__ res8, const hoh_stream_result* __restrict__ res9,
+                              const uint32_t* __restrict__ lz_size, const int32_t* __restrict__ lz_status,
+                              const uint32_t* __restrict__ info, hoh_tile_result* __restrict__ tiles) {
+    const uint64_t lt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (lt >= n_tiles) return;
+    const hoh_stream_result g = res8[lt * per8], rg = res9[lt * 2u], bg = res9[lt * 2u + 1u];
+    hoh_tile_result tr;
+    tr.status = lz_status[lt] ? lz_status[lt] : (g.status ? g.status : (rg.status ? rg.status : bg.status));
+    tr.colour_mode = 128;
+    tr.chan_size[0] = g.size;
+    tr.chan_size[1] = rg.size;
+    tr.chan_size[2] = bg.size;
+    if (per8 == 3u) {
+        const hoh_stream_result r = res8[lt * 3u + 1u], b = res8[lt * 3u + 2u];
+        if (!tr.status) tr.status = r.status ? r.status : b.status;
+        // :289, :309: plain RGB replaces sub-green when its three channels are smaller (LZ bytes on both sides)
+        if ((uint64_t)r.size + g.size + b.size < (uint64_t)g.size + rg.size + bg.size) {
+            tr.colour_mode = 2;
+            tr.chan_size[1] = r.size;
+            tr.chan_size[2] = b.size;
+        }
+    }
+    tr.lz_size = lz_size[lt];
+    const uint32_t c = info[lt] & 0x7fffffffu;
+    tr.flags = ((info[lt] >> 31) ? kTileGrey : 0u) | (c <= 256u ? kTilePalette : 0u);
+    tr.size = 3u + tr.lz_size + 1u + hohfmt::varint_len(tr.chan_size[0]) + hohfmt::varint_len(tr.chan_size[1]) + tr.chan_size[0] +
+              tr.chan_size[1] + tr.chan_size[2];
+    tr.start = 0;
+    tiles[first_tile + lt] = tr;
+}
+
+// off[first + i + 1] = off[first] + sizes of tiles first .. first + i.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) k_tile_scan(hoh_tile_result* __restrict__ tiles, uint64_t first, uint32_t n,
+                                                    uint64_t* __restrict__ off) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = off[first];
+    __syncthreads();
+    const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = i < n ? tiles[first + i].size : 0ull;
+        uint64_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            uint64_t t = warp_tot[lane];
+            uint64_t ti = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t o = __shfl_up_sync(0xffffffffu, ti, d);
+                if ((int)lane >= d) ti += o;
+            }
+            warp_tot[lane] = ti - t;
+        }
+        __syncthreads();
+        const uint64_t c = carry;
+        if (i < n) {
+            tiles[first + i].start = c + warp_tot[w] + incl - v;
+            off[first + i + 1] = c + warp_tot[w] + incl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + warp_tot[w] + incl;
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint32_t n) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// choh.cpp:112-116, 328-363: 00 00 | colour mode | LZ record | 0x24 | varint(size 1) varint(size 2) | channels.
+__global__ void __launch_bounds__(256) k_tile_emit(uint64_t first_tile, uint32_t per8,
+                                                   const hoh_stream_result* __restrict__ res8,
+                                                   const hoh_stream_result* __restrict__ res9,
+                                                   const uint8_t* __restrict__ out8, const uint8_t* __restrict__ out9,
+                                                   const uint8_t* __restrict__ lz, uint32_t lz_stride,
+                                                   hoh_tile_result* __restrict__ tiles, uint8_t* __restrict__ packed,
+                                                   uint64_t packed_cap) {
+    const uint64_t lt = blockIdx.x;
+    hoh_tile_result& tr = tiles[first_tile + lt];
+    if (tr.start + tr.size > packed_cap) {
+        if (threadIdx.x == 0 && !tr.status) tr.status = HOH_S_OVERFLOW;
+        return;
+    }
+    uint8_t* dst = packed + tr.start;
+    const uint32_t v0 = hohfmt::varint_len(tr.chan_size[0]), v1 = hohfmt::varint_len(tr.chan_size[1]);
+    if (threadIdx.x == 0) {
+        dst[0] = 0;
+        dst[1] = 0;
+        dst[2] = (uint8_t)tr.colour_mode;
+        uint8_t* q = dst + 3u + tr.lz_size;
+        q[0] = 0x24;
+        hohfmt::put_varint(q, 1u, tr.chan_size[0]);
+        hohfmt::put_varint(q, 1u + v0, tr.chan_size[1]);
+    }
+    cta_copy(dst + 3, lz + lt * (uint64_t)lz_stride, tr.lz_size);
+    uint8_t* body = dst + 3u + tr.lz_size + 1u + v0 + v1;
+    const bool plain = tr.colour_mode == 2u;
+    const hoh_stream_result c0 = res8[lt * per8];
+    const hoh_stream_result c1 = plain ? res8[lt * 3u + 1u] : res9[lt * 2u];
+    const hoh_stream_result c2 = plain ? res8[lt * 3u + 2u] : res9[lt * 2u + 1u];
+    cta_copy(body, out8 + c0.start, c0.size);
+    cta_copy(body + c0.size, (plain ? out8 : out9) + c1.start, c1.size);
+    cta_copy(body + c0.size + c1.size, (plain ? out8 : out9) + c2.start, c2.size);
 }
 
 }  // namespace hohk

@@ -59,6 +59,8 @@ ENC_STREAM_DT = np.dtype([("sym_off", "<u8"), ("n", "<u4"), ("range", "<u4"), ("
                           ("reserved", "<u4")])
 RESULT_DT = np.dtype([("start", "<u8"), ("size", "<u4"), ("status", "<i4"), ("payload_bytes", "<u4"),
                       ("stored", "<u4")])
+TILE_DT = np.dtype([("start", np.uint64), ("size", np.uint32), ("status", np.int32), ("colour_mode", np.uint32),
+                    ("lz_size", np.uint32), ("chan_size", np.uint32, (3,)), ("flags", np.uint32)])
 DEC_STREAM_DT = np.dtype([("in_off", "<u8"), ("sym_off", "<u8"), ("sym_cap", "<u4"), ("flags", "<u4")])
 DEC_RESULT_DT = np.dtype([("end_off", "<u8"), ("n", "<u4"), ("status", "<i4"), ("range", "<u4"),
                           ("prob_bits", "<u4"), ("stored", "<u4"), ("table_mode", "<u4")])
@@ -111,6 +113,7 @@ SIGNATURES = {
     "hoh_unpredict_all_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "hoh_predict_section_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _int, _vp, _int, _vp, _u32, _vp]),
     "hoh_predictor_search_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "hoh_encode_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, _vp, _sz, _vp, _vp]),
     "hoh_find_lz_stride": (_sz, [_int, _int]),
     "hoh_find_lz_rgb_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "hoh_find_lz_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
@@ -554,6 +557,27 @@ class HohGpu:
         out = np.zeros(src.size // total, np.uint16)
         self._ck(self.lib.hoh_channel_picker(self.ctx, _ptr(src), src.size, total, target, _ptr(out)), "hoh_channel_picker")
         return out
+
+    def encode_images(self, rgb, n_images, width, height, mode):
+        """hoh_encode_images: encode_tile for every tile -> (list of tile bytes, TILE_DT records)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
+        g = self.tile_geometry(width, height)
+        n_tiles = n_images * g.tiles_per_image
+        packed_cap = rgb.nbytes * 2 + 8192 * n_tiles
+        d_rgb = self.alloc(rgb.nbytes).upload(rgb)
+        d_packed = self.alloc(packed_cap)
+        d_off = self.alloc((n_tiles + 1) * 8)
+        d_tiles = self.alloc(n_tiles * TILE_DT.itemsize)
+        try:
+            self._ck(self.lib.hoh_encode_images(self.ctx, d_rgb.ptr, n_images, width, height, mode, d_packed.ptr,
+                                                packed_cap, d_off.ptr, d_tiles.ptr), "hoh_encode_images")
+            off = d_off.download(np.uint64, n_tiles + 1)
+            rec = d_tiles.download(TILE_DT, n_tiles)
+            packed = d_packed.download(np.uint8, int(off[-1]))
+        finally:
+            for b in (d_rgb, d_packed, d_off, d_tiles):
+                b.free()
+        return [packed[int(off[t]):int(off[t + 1])].tobytes() for t in range(n_tiles)], rec
 
     def layer_encode_batch(self, planes, n_planes, w, h, depth, mode, nuke=None, planes_per_map=1):
         """layer_encode.hpp:11 for n_planes planes of the same shape -> list of (payload bytes, status, kept slot).

@@ -264,6 +264,35 @@ int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pl
                              uint16_t* d_resid);
 
 /* ------------------------------------------------------------------------------------------ */
+/* (vi) whole tiles — encode_tile choh.cpp:104-382 for every tile of N images, any cruncher mode   */
+/* ------------------------------------------------------------------------------------------ */
+#define HOH_TILE_GREY 1u    /* every pixel grey: encode_tile takes the greyscale branch (choh.cpp:180-213)      */
+#define HOH_TILE_PALETTE 2u /* <= 256 colours: encode_tile also tries the indexed mode (choh.cpp:298-307)       */
+
+typedef struct hoh_tile_result {
+    uint64_t start;        /* byte offset of the tile's bytes in d_packed                                  */
+    uint32_t size;         /* = encode_tile's return value                                                 */
+    int32_t status;        /* HOH_S_* of the first failing stage                                           */
+    uint32_t colour_mode;  /* 128 subtract-green, 2 plain RGB (choh.cpp:295-327)                           */
+    uint32_t lz_size;      /* bytes of the LZ record inside the tile                                       */
+    uint32_t chan_size[3]; /* the three channel payloads                                                   */
+    uint32_t flags;        /* HOH_TILE_*: the reference would (also) take a colour mode that stays on the host */
+} hoh_tile_result;
+
+/* encode_tile for every tile of n_images interleaved RGB8 images at cruncher mode 0..4, entirely on the
+ * device: LZ match finder with the mode's seek window (choh.cpp:123-156), subtract-green planes (and the plain
+ * R, B alternatives at mode > 2), layer_encode of every plane with the NUKE maps, the colour-mode comparison
+ * and the emission of the tile's bytes (header 00 00, colour mode, LZ record, channel-order byte, size varints,
+ * channels).  Tile t = image * tiles_per_image + tile occupies d_packed[d_tile_off[t], d_tile_off[t+1]).
+ * The host keeps only the file header and the tile offset table (choh.cpp:436-506).  Tiles the reference would
+ * code in greyscale / indexed mode are flagged (they still get their sub-green bytes).  Tilings with unequal
+ * tiles (width or height not a multiple of the tile count) return HOH_E_UNSUPPORTED.  Large batches are
+ * processed in chunks of whole images sized by an internal scratch budget. */
+int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
+                      int mode, uint8_t* d_packed, size_t packed_cap, uint64_t* d_tile_off,
+                      hoh_tile_result* d_tiles);
+
+/* ------------------------------------------------------------------------------------------ */
 /* (v) LZ match finder — find_lz_rgb lz.hpp:6-145 over N tiles                 */
 /* ------------------------------------------------------------------------------------------ */
 /* Bytes of one tile's LEMPEL record buffer (tag byte + up to four entropy-coded side streams). */
