@@ -420,7 +420,7 @@ def main():
         lz_bufs = [g.alloc(n_tiles * nuke_stride), g.alloc(n_tiles * lz_stride), g.alloc(n_tiles * 4), g.alloc(n_tiles * 4)]
 
         def lz_dev():
-            g._ck(lib.hoh_find_lz_images(ctx, d_rgb.ptr, n_img, W, H, 6, None, lz_bufs[0].ptr, lz_bufs[1].ptr, lz_stride,
+            g._ck(lib.hoh_find_lz_images(ctx, d_rgb.ptr, n_img, W, H, 6, 0, None, lz_bufs[0].ptr, lz_bufs[1].ptr, lz_stride,
                                          lz_bufs[2].ptr, lz_bufs[3].ptr), "hoh_find_lz_images")
         lz_dev()
         g.sync()

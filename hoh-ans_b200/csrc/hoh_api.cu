@@ -22,7 +22,8 @@ namespace {
 enum Slot {
     S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
     S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
-    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_COUNT
+    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_D_TILES, S_D_PLANES, S_D_LZSYM, S_D_IDXSYM, S_D_RESID, S_D_OUT, S_D_BACKREF, S_D_MAPS,
+    S_D_STREAMS, S_D_RES_A, S_D_RES_B, S_D_TOP, S_D_BP, S_D_PSTATUS, S_COUNT
 };
 
 struct Buf {
@@ -1050,6 +1051,7 @@ static LayerGeom layer_geom(int w, int h, int depth, int mode) {
     lg.cells_pad = (lg.cells + 7u) & ~7u;
     lg.depth = depth;
     lg.mode = mode;
+    lg.enc_flags = 0;
     // candidate slabs sized by what each is coded with: A 15 bits, B the index map at 8, C 16, D 15, E-G up to 19
     const uint32_t bits_of[kLayerSlots] = {15, 8, 16, 15, 19, 19, 19};
     uint32_t at = 0, widest = 0;
@@ -1071,7 +1073,7 @@ size_t hoh_layer_encode_out_bytes(size_t n_planes, int w, int h, int depth, int 
 }
 
 int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
-                           int mode, const uint8_t* d_nuke, size_t nuke_stride, uint32_t planes_per_map,
+                           int mode, unsigned flags, const uint8_t* d_nuke, size_t nuke_stride, uint32_t planes_per_map,
                            uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
                            uint8_t* d_packed, size_t packed_cap, uint64_t* d_packed_off) {
     if (!ctx || !d_planes || !d_out || !d_results || w <= 0 || h <= 0 || depth < 1 || depth > 9 || mode < 0 || mode > 4)
@@ -1079,7 +1081,8 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     if (d_nuke && (planes_per_map == 0 || nuke_stride < (size_t)w * h)) return HOH_E_ARG;
     if (n_planes == 0) return HOH_OK;
     if ((uint64_t)w * h >= (1u << 21)) return HOH_E_UNSUPPORTED;  // varint.hpp:39-45
-    const LayerGeom lg = layer_geom(w, h, depth, mode);
+    LayerGeom lg = layer_geom(w, h, depth, mode);
+    lg.enc_flags = flags & HOH_FIX_LONE;
     if (lg.xt > 256 || lg.yt > 256) return HOH_E_UNSUPPORTED;    // grid size bytes (layer_encode.hpp:276-277)
     if (out_bytes < hoh_layer_encode_out_bytes(n_planes, w, h, depth, mode)) return HOH_E_CAPACITY;
     const size_t n = n_planes;
@@ -1093,11 +1096,13 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     TRY(scratch_t(ctx, S_L_MAPS, n * (lg.cells ? lg.cells : 1), &maps));
     TRY(scratch_t(ctx, S_L_IDX, n * (lg.cells ? lg.cells : 1), &idx));
     TRY(scratch_t(ctx, S_L_HDR, n * kLayerHdrCap, &hdr));
-    TRY(scratch_t(ctx, S_L_U32, 5 * n, &n_used));
+    uint32_t* with_idx;
+    TRY(scratch_t(ctx, S_L_U32, 6 * n, &n_used));
     hdr_len = n_used + n;
     kept = hdr_len + n;
     best = kept + n;
-    if (d_nuke) kept_px = best + n;
+    with_idx = best + n;
+    if (d_nuke) kept_px = with_idx + n;
     TRY(scratch_t(ctx, S_L_STATUS, n, &status));
     TRY(scratch_t(ctx, S_STREAMS, 3 * n, &streams));
     TRY(scratch_t(ctx, S_L_RR, 3 * n, &rr));
@@ -1141,11 +1146,12 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
         k_layer_headers<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(lg, n, idx, syms, n_used, hdr, hdr_len);
         LAUNCHED("k_layer_headers");
     }
-    k_layer_decide<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(lg, n, res, kept, best, status);
+    k_layer_decide<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(lg, n, res, (flags & HOH_FIX_STALE) ? 1u : 0u, hdr, hdr_len,
+                                                                kept, best, with_idx, status);
     LAUNCHED("k_layer_decide");
     const uint64_t out_base = (uint64_t)n * lg.plane_bytes;
-    k_layer_assemble<<<(unsigned)n, 256, 0, ctx->stream>>>(lg, hdr, hdr_len, res, kept, best, status, d_out, d_out, out_base,
-                                                           d_results);
+    k_layer_assemble<<<(unsigned)n, 256, 0, ctx->stream>>>(lg, hdr, hdr_len, res, kept, best, with_idx, status, d_out, d_out,
+                                                           out_base, d_results);
     LAUNCHED("k_layer_assemble");
     if (d_packed) {
         if (!d_packed_off) return HOH_E_ARG;
@@ -1172,7 +1178,7 @@ size_t hoh_find_lz_stride(int w, int h) {
 } // extern "C" (reopened below)
 namespace {
 // shared body of the two LZ entry points; nuke_stride = elements per tile in d_nuke
-int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles, size_t max_npx, int distance,
+int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles, size_t max_npx, int distance, unsigned flags,
                  const int32_t* d_bonus, uint8_t* d_nuke, uint32_t nuke_stride, uint8_t* d_lz, size_t lz_stride,
                  uint32_t* d_lz_size, int32_t* d_status, uint32_t* d_info = nullptr) {
     if (max_npx >= (1u << 21) * 3ull) return HOH_E_UNSUPPORTED;  // side streams must stay below 2^21 symbols (varint.hpp:39-45)
@@ -1209,7 +1215,8 @@ int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles,
     k_lz_walk<<<blocks_for(n_tiles * 32, 128), 128, 0, ctx->stream>>>(state, sh, n_tiles, d_bonus, 0, wide, d_nuke,
                                                                      nuke_stride, side, stride, counts);
     LAUNCHED("k_lz_walk");
-    k_lz_streams<<<blocks_for(n_tiles * 4, 256), 256, 0, ctx->stream>>>(n_tiles, counts, stride, slab, streams);
+    k_lz_streams<<<blocks_for(n_tiles * 4, 256), 256, 0, ctx->stream>>>(n_tiles, counts, stride, slab, flags & HOH_FIX_LONE,
+                                                                        streams);
     LAUNCHED("k_lz_streams");
     TRY(hoh_encode_entropy_batch(ctx, streams, n_tiles * 4, side, slabs, res, 256, 10, stride));
     k_lz_assemble<<<(unsigned)n_tiles, 128, 0, ctx->stream>>>(res, slabs, wide, d_lz, (uint32_t)lz_stride, d_lz_size,
@@ -1221,7 +1228,7 @@ int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles,
 extern "C" {
 
 int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, int w, int h, int distance,
-                          const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
+                          unsigned flags, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
                           uint32_t* d_lz_size, int32_t* d_status) {
     if (!ctx || !d_rgb || !d_nuke || !d_lz || !d_lz_size || w <= 0 || h <= 0 || distance < 0 || distance > 16)
         return HOH_E_ARG;
@@ -1234,12 +1241,12 @@ int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, in
     sh.npx = (uint32_t)npx;
     sh.width = (uint32_t)w;
     sh.stride = (uint32_t)npx;
-    return find_lz_impl(ctx, d_rgb, sh, n_tiles, npx, distance, d_bonus, d_nuke, (uint32_t)npx, d_lz, lz_stride, d_lz_size,
+    return find_lz_impl(ctx, d_rgb, sh, n_tiles, npx, distance, flags, d_bonus, d_nuke, (uint32_t)npx, d_lz, lz_stride, d_lz_size,
                         d_status);
 }
 
 int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
-                       int distance, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
+                       int distance, unsigned flags, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
                        uint32_t* d_lz_size, int32_t* d_status) {
     if (!ctx || !d_rgb || !d_nuke || !d_lz || !d_lz_size || distance < 0 || distance > 16) return HOH_E_ARG;
     if (n_images == 0) return HOH_OK;
@@ -1250,7 +1257,7 @@ int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint
     sh.tiled = 1;
     sh.g = to_geom(hg);
     sh.stride = sh.g.plane_stride;
-    return find_lz_impl(ctx, d_rgb, sh, n_images * sh.g.tiles_per_image, (size_t)hg.tile_w * hg.tile_h, distance, d_bonus,
+    return find_lz_impl(ctx, d_rgb, sh, n_images * sh.g.tiles_per_image, (size_t)hg.tile_w * hg.tile_h, distance, flags, d_bonus,
                         d_nuke, sh.g.plane_stride, d_lz, lz_stride, d_lz_size, d_status);
 }
 
@@ -1258,7 +1265,7 @@ int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint
 // encode_tile for the tiles of whole images, any cruncher mode
 // -------------------------------------------------------------------------------------------------
 int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
-                      int mode, uint8_t* d_packed, size_t packed_cap, uint64_t* d_tile_off,
+                      int mode, unsigned flags, uint8_t* d_packed, size_t packed_cap, uint64_t* d_tile_off,
                       hoh_tile_result* d_tiles) {
     if (!ctx || !d_rgb || !d_packed || !d_tile_off || !d_tiles || mode < 0 || mode > 4) return HOH_E_ARG;
     hoh_tile_geometry hg;
@@ -1311,13 +1318,13 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
         sh.tiled = 1;
         sh.g = g;
         sh.stride = g.plane_stride;
-        TRY(find_lz_impl(ctx, rgb, sh, nt, npx, distance, nullptr, nuke, g.plane_stride, lz, lz_stride, lz_size, lz_status,
+        TRY(find_lz_impl(ctx, rgb, sh, nt, npx, distance, flags, nullptr, nuke, g.plane_stride, lz, lz_stride, lz_size, lz_status,
                          info));
         k_tile_planes<<<(unsigned)nt, 256, 0, ctx->stream>>>(rgb, g, 0, per8, p8, p9);
         LAUNCHED("k_tile_planes");
-        TRY(hoh_layer_encode_batch(ctx, p8, nt * per8, tw, th, 8, mode, nuke, g.plane_stride, per8, out8, nt * out8_tile, r8,
+        TRY(hoh_layer_encode_batch(ctx, p8, nt * per8, tw, th, 8, mode, flags, nuke, g.plane_stride, per8, out8, nt * out8_tile, r8,
                                    nullptr, 0, nullptr));
-        TRY(hoh_layer_encode_batch(ctx, p9, nt * 2, tw, th, 9, mode, nuke, g.plane_stride, 2, out9, nt * out9_tile, r9,
+        TRY(hoh_layer_encode_batch(ctx, p9, nt * 2, tw, th, 9, mode, flags, nuke, g.plane_stride, 2, out9, nt * out9_tile, r9,
                                    nullptr, 0, nullptr));
         k_tile_decide<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, first, per8, r8, r9, lz_size, lz_status, info, d_tiles);
         LAUNCHED("k_tile_decide");
@@ -1326,6 +1333,83 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
         k_tile_emit<<<(unsigned)nt, 256, 0, ctx->stream>>>(first, per8, r8, r9, out8, out9, lz, (uint32_t)lz_stride, d_tiles,
                                                           d_packed, packed_cap);
         LAUNCHED("k_tile_emit");
+    }
+    return HOH_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// tile decoder, any cruncher mode (inverse of hoh_encode_images)
+// -------------------------------------------------------------------------------------------------
+int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes, const uint64_t* d_tile_off,
+                      size_t n_images, uint32_t width, uint32_t height, uint8_t* d_rgb, int32_t* d_status) {
+    if (!ctx || !d_packed || !d_tile_off || !d_rgb || !d_status) return HOH_E_ARG;
+    if (n_images == 0) return HOH_OK;
+    hoh_tile_geometry hg;
+    TRY(hoh_tile_geometry_for(width, height, &hg));
+    if (width % hg.x_tiles || height % hg.y_tiles) return HOH_E_UNSUPPORTED;
+    const TileGeom g = to_geom(hg);
+    const int tw = (int)hg.tile_w, th = (int)hg.tile_h;
+    const uint32_t npx = (uint32_t)tw * th;
+    const uint32_t xt = (tw + 39) / 40, yt = (th + 39) / 40, cells = xt * yt, cells_pad = (cells + 7u) & ~7u;
+    if (xt > 256 || yt > 256) return HOH_E_UNSUPPORTED;
+    const uint32_t side = lz_side_stride(npx);
+    const size_t per_tile = 4 * (size_t)side * 2 + 3 * (size_t)g.plane_stride * 2 * 2 + (size_t)g.plane_stride * 2 +
+                            3 * (size_t)(kCumRow * 4 + kFreqRow * 4) + 3 * (size_t)tw * 3 + 4096;
+    size_t budget = (size_t)32 << 30;
+    if (const char* e = getenv("HOH_SCRATCH_GB")) budget = (size_t)atof(e) * ((size_t)1 << 30);
+    size_t images_per_chunk = budget / (per_tile * g.tiles_per_image);
+    if (images_per_chunk == 0) images_per_chunk = 1;
+    if (images_per_chunk > n_images) images_per_chunk = n_images;
+    const size_t ct = images_per_chunk * g.tiles_per_image;
+    DTile* tiles;
+    DPlane* planes;
+    uint16_t *lz_sym, *idx_sym, *resid, *out, *backref, *maps, *top;
+    uint8_t* bp;
+    int32_t* pstatus;
+    hoh_dec_stream* streams;
+    hoh_dec_result *res_a, *res_b;
+    TRY(scratch_t(ctx, S_D_TILES, ct, &tiles));
+    TRY(scratch_t(ctx, S_D_PLANES, ct * 3, &planes));
+    TRY(scratch_t(ctx, S_D_LZSYM, ct * 4 * side, &lz_sym));
+    TRY(scratch_t(ctx, S_D_IDXSYM, ct * 3 * cells_pad, &idx_sym));
+    TRY(scratch_t(ctx, S_D_RESID, ct * 3 * g.plane_stride, &resid));
+    TRY(scratch_t(ctx, S_D_OUT, ct * 3 * g.plane_stride, &out));
+    TRY(scratch_t(ctx, S_D_BACKREF, ct * g.plane_stride, &backref));
+    TRY(scratch_t(ctx, S_D_MAPS, ct * 3 * cells, &maps));
+    TRY(scratch_t(ctx, S_D_STREAMS, ct * 3, &streams));
+    TRY(scratch_t(ctx, S_D_RES_A, ct * 3, &res_a));
+    TRY(scratch_t(ctx, S_D_RES_B, ct * 3, &res_b));
+    TRY(scratch_t(ctx, S_D_TOP, ct * 3 * (size_t)tw, &top));
+    TRY(scratch_t(ctx, S_D_BP, ct * 3 * (size_t)tw, &bp));
+    TRY(scratch_t(ctx, S_D_PSTATUS, ct * 3, &pstatus));
+    for (size_t img0 = 0; img0 < n_images; img0 += images_per_chunk) {
+        const size_t ni = std::min(images_per_chunk, n_images - img0);
+        const size_t nt = ni * g.tiles_per_image, first = img0 * g.tiles_per_image;
+        k_dt_begin<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, d_packed, packed_bytes, d_tile_off + first, side, tiles,
+                                                                 streams);
+        LAUNCHED("k_dt_begin");
+        for (uint32_t k = 0; k < 4; k++) {  // un_lz.hpp:100-145: the side streams follow one another
+            TRY(decode_common(ctx, streams, nt, d_packed, packed_bytes, lz_sym, res_a));
+            k_dt_lz_next<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, k, d_packed, packed_bytes, res_a, side, tiles,
+                                                                       streams);
+            LAUNCHED("k_dt_lz_next");
+        }
+        k_dt_channels<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, d_packed, packed_bytes, xt, yt, cells_pad, tiles,
+                                                                    planes, streams);
+        LAUNCHED("k_dt_channels");
+        TRY(decode_common(ctx, streams, nt * 3, d_packed, packed_bytes, idx_sym, res_a));
+        k_dt_main<<<blocks_for(nt * 3, 128), 128, 0, ctx->stream>>>(nt * 3, cells, cells_pad, g.plane_stride, npx, res_a,
+                                                                    idx_sym, planes, maps, streams);
+        LAUNCHED("k_dt_main");
+        TRY(decode_common(ctx, streams, nt * 3, d_packed, packed_bytes, resid, res_b));
+        k_dt_unlz<<<blocks_for(nt * 32, 128), 128, 0, ctx->stream>>>(nt, npx, g.plane_stride, lz_sym, side, tiles, backref);
+        LAUNCHED("k_dt_unlz");
+        k_dt_unpredict<<<blocks_for(nt * 3, 64), 64, 0, ctx->stream>>>(nt * 3, tw, th, (int)xt, (int)yt, g.plane_stride,
+                                                                       planes, tiles, res_b, resid, maps, backref, out, top,
+                                                                       bp, pstatus);
+        LAUNCHED("k_dt_unpredict");
+        k_dt_store<<<(unsigned)nt, 256, 0, ctx->stream>>>(g, first, g.plane_stride, tiles, pstatus, out, d_rgb, d_status);
+        LAUNCHED("k_dt_store");
     }
     return HOH_OK;
 }
@@ -1564,7 +1648,7 @@ int hoh_find_lz_rgb(hoh_ctx* ctx, const uint8_t* source, size_t size, int width,
     TRY(scratch_t(ctx, S_IO_D, 2, &d_size));
     d_bonus = reinterpret_cast<int32_t*>(d_size + 1);
     CK(cudaMemcpyAsync(d_bonus, &break_even_bonus, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    TRY(hoh_find_lz_rgb_batch(ctx, d_rgb, 1, width, height, distance, d_bonus, d_nuke, d_lz, stride, d_size, nullptr));
+    TRY(hoh_find_lz_rgb_batch(ctx, d_rgb, 1, width, height, distance, 0, d_bonus, d_nuke, d_lz, stride, d_size, nullptr));
     uint32_t n = 0;
     TRY(stage_out(ctx, &n, d_size, 1));
     if (n > lz_cap) return HOH_E_CAPACITY;

@@ -183,8 +183,10 @@ HOH_HD uint32_t clamp_width_of(const ClampSet& c, uint32_t prob_bits, uint32_t s
 // plus the decisions the table needs: the clamp set and the table mode (1 = every frequency on maxbits
 // bits, 2 = clamp pairs + variable-width frequencies).  Returns the bytes written; *stored_size gets
 // entropy_encoding.hpp:45's size of the stored-mode alternative.
+// representable != 0 (HOH_FIX_LONE): table mode 1 is not chosen when a frequency does not fit its maxbits-wide
+// field (the reference writes it anyway and the table is lost, D6).
 HOH_HD uint32_t plan_head(const uint32_t* freqs, uint32_t range, uint32_t n, uint32_t prob_bits, uint8_t* head,
-                          uint32_t* stored_size, ClampSet* cs, uint32_t* table_mode) {
+                          uint32_t* stored_size, ClampSet* cs, uint32_t* table_mode, uint32_t representable = 0) {
     uint32_t at = 0;
     at = put_varint(head, at, range - 1);
     at = put_varint(head, at, n);
@@ -204,6 +206,9 @@ HOH_HD uint32_t plan_head(const uint32_t* freqs, uint32_t range, uint32_t n, uin
     clamped_bits += (uint64_t)w_down * ((uint64_t)stop_down - (uint64_t)stop_up - 1ull);
     uint64_t clamped_bytes = (clamped_bits + 7) / 8;
     *table_mode = raw_table_bytes < clamped_bytes ? 1u : 2u;  // :135 / :148
+    if (representable && *table_mode == 1u)
+        for (uint32_t s = 0; s < range; s++)
+            if (freqs[s] >> maxbits) *table_mode = 2u;
     head[at++] = (uint8_t)((1u << 7) + (prob_bits << 2) + *table_mode);
     return at;
 }

@@ -194,7 +194,8 @@ __device__ __forceinline__ void bits_or(uint32_t* words, uint32_t bit, uint32_t 
 }
 
 __device__ uint32_t warp_build_head(const uint32_t* f, uint32_t range, uint32_t n, uint32_t prob_bits,
-                                    uint8_t* buf, uint32_t* scratch /* >= 40 words */, uint32_t* stored_size) {
+                                    uint8_t* buf, uint32_t* scratch /* >= 40 words */, uint32_t* stored_size,
+                                    uint32_t representable = 0) {
     const uint32_t lane = lane_id();
     uint32_t* words = reinterpret_cast<uint32_t*>(buf);
     const uint32_t maxbits = hohfmt::bit_length(range - 1);
@@ -203,7 +204,7 @@ __device__ uint32_t warp_build_head(const uint32_t* f, uint32_t range, uint32_t 
         hohfmt::ClampSet cs;
         uint32_t mode, st;
         uint8_t tmp[8];
-        const uint32_t at = hohfmt::plan_head(f, range, n, prob_bits, tmp, &st, &cs, &mode);
+        const uint32_t at = hohfmt::plan_head(f, range, n, prob_bits, tmp, &st, &cs, &mode, representable);
         scratch[0] = at;
         scratch[1] = mode;
         scratch[2] = st;
@@ -326,6 +327,23 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
         }
         return;
     }
+    if ((st.reserved & HOH_FIX_LONE) && st.range > 1u) {
+        // A stream with ONE distinct symbol gives it the whole 2^prob_bits, which the table format cannot
+        // hold (the field is prob_bits wide: SURVEY D6) — no decoder can read such a stream back.  Decodable
+        // variant: one count goes to a neighbouring symbol that never occurs.
+        uint32_t lone = 0xffffffffu;
+        for (uint32_t i = lane; i < st.range; i += 32)
+            if (f[i] == (1u << st.prob_bits)) lone = i;
+        lone = warp_min(lone);
+        if (lone != 0xffffffffu) {
+            if (lane == 0) {
+                f[lone] -= 1u;
+                f[lone + 1u < st.range ? lone + 1u : lone - 1u] = 1u;
+            }
+            __syncwarp();
+            warp_cumsum(f, cum, st.range);
+        }
+    }
     uint32_t* ct = cumtab + (size_t)s * kCumRow;
     for (uint32_t i = lane; i <= st.range; i += 32) ct[i] = cum[i];
     {  // window of symbols that actually occur: the encoder stages only cum[win_lo .. win_lo + win_rows)
@@ -341,7 +359,7 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
         m.win_lo = lo;
         m.win_rows = hi - lo + 2u;
     }
-    m.head_len = warp_build_head(f, st.range, st.n, st.prob_bits, s_head[w], sc, &m.stored_size);
+    m.head_len = warp_build_head(f, st.range, st.n, st.prob_bits, s_head[w], sc, &m.stored_size, st.reserved & HOH_FIX_LONE);
     __syncwarp();
     const uint32_t words = (m.head_len + 3u) / 4u;
     for (uint32_t k = lane; k < words; k += 32)
@@ -744,6 +762,45 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
             } else if (h.table_mode == 3) {
                 status = HOH_S_BAD_TABLE;
             }
+            // HOH_FIX_CARRY.  A stream with ONE distinct symbol s writes the value 2^prob_bits into a prob_bits-wide
+            // field.  The reference's bit packer ADDS fields into its pending byte (varint.hpp:47-77), so the field
+            // itself reads 0 and the extra bit increments the bits already written in that byte (mod 2^k, k = bits
+            // of the clamp pairs that share the field's first byte; k = 0: the bit is simply lost).  A valid table
+            // never has frequency 0 for the first symbol inside its clamps, so the pattern is unambiguous: when the
+            // field reads 0 and, with the increment undone, every clamp value is the same symbol, that symbol owns
+            // the whole range.
+            if ((st.flags & HOH_FIX_CARRY) && h.table_mode == 2u && status == HOH_S_OK && h.prob_bits >= 1u &&
+                h.prob_bits <= HOH_MAX_PROB_BITS) {
+                const uint32_t count = clamps[0];
+                uint32_t v[32];
+                for (uint32_t j = 0; j < count; j++) {
+                    v[2u * j] = clamps[1 + j] & 0xffffu;
+                    v[2u * j + 1u] = clamps[1 + j] >> 16;
+                }
+                hohfmt::BitSource<ByteView> bits{bytes, h.body, 0, 0};
+                for (uint32_t j = 0; j < 2u * count; j++) bits.get(h.maxbits);
+                const uint32_t field = bits.get(h.prob_bits);
+                uint32_t rem = (2u * count * h.maxbits) & 7u;  // k
+                bool borrow = true;
+                for (int j = (int)(2u * count) - 1; j >= 0 && rem && borrow; j--) {
+                    const uint32_t t = min(rem, h.maxbits), mask = (1u << t) - 1u;
+                    uint32_t part = v[j] & mask;
+                    if (part == 0u) part = mask;
+                    else {
+                        part--;
+                        borrow = false;
+                    }
+                    v[j] = (v[j] & ~mask) | part;
+                    rem -= t;
+                }
+                bool lone = field == 0u && count > 0u;
+                for (uint32_t j = 1; j < 2u * count; j++) lone = lone && v[j] == v[0];
+                if (lone && v[0] < h.range) {
+                    clamps[0] = 0xffffffffu;  // marks the recovered table
+                    clamps[1] = v[0];
+                    field_bit = h.body * 8u + 2ull * count * h.maxbits + h.prob_bits;
+                }
+            }
         }
     }
     h.range = __shfl_sync(0xffffffffu, h.range, 0);
@@ -762,7 +819,13 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_parse_streams(
     // table modes 1 and 2 (entropy_decoding.hpp:180-244): every lane reads the fields of its contiguous
     // run of symbols; widths per symbol, then bit offsets by prefix sum, then the reference's bit reader
     // positioned at the run's first bit
-    if (!h.empty && h.rans && status == HOH_S_OK && (h.table_mode == 1u || h.table_mode == 2u)) {
+    if (!h.empty && h.rans && status == HOH_S_OK && h.table_mode == 2u && clamps[0] == 0xffffffffu) {
+        const uint32_t lone = clamps[1];  // recovered lone-symbol table (HOH_FIX_CARRY)
+        __syncwarp();
+        for (uint32_t i = lane; i < h.range; i += 32) f[i] = i == lone ? (1u << h.prob_bits) : 0u;
+        after_table = (field_bit + 7u) >> 3;
+        __syncwarp();
+    } else if (!h.empty && h.rans && status == HOH_S_OK && (h.table_mode == 1u || h.table_mode == 2u)) {
         const uint32_t count = h.table_mode == 2u ? clamps[0] : 0u;
         const uint32_t per = (h.range + 31u) / 32u;
         const uint32_t lo = min(lane * per, h.range), hi = min(lo + per, h.range);
@@ -2177,6 +2240,7 @@ struct LayerGeom {
     uint32_t slot_off[7]; // byte offset of each candidate's slab inside a plane's block (kLayerSlots entries)
     uint32_t slot_cap[7]; // ... and its capacity (sized for the candidate's prob_bits; 0 = not used at this mode)
     uint32_t plane_bytes; // candidate bytes per plane
+    uint32_t enc_flags;   // HOH_FIX_LONE or 0, handed to every entropy stream
     uint32_t out_cap;     // bytes of one assembled channel payload
 };
 
@@ -2197,7 +2261,7 @@ __global__ void k_layer_streams(LayerGeom lg, uint64_t n_planes, int round, cons
     hoh_enc_stream st;
     st.prefix_len = 0;
     for (int b = 0; b < 8; b++) st.prefix[b] = 0;
-    st.reserved = 0;
+    st.reserved = lg.enc_flags;
     st.range = 1u << lg.depth;
     st.n = kept_px ? kept_px[p] : lg.per;  // residuals left after NUKE compaction (layer_encode.hpp:93-99, 328-333)
     uint32_t slot;
@@ -2269,34 +2333,71 @@ __global__ void k_layer_headers(LayerGeom lg, uint64_t n_planes, const uint8_t* 
 }
 
 // layer_encode.hpp:108-120, 326-398: which candidate's bytes are emitted and how many of them.
+// fix == 0 reproduces the reference, including D7: when the 16- or 15-bit candidate wins the second stage only
+// the SIZE is updated, so the emitted bytes are a stale buffer cut to that size.  fix != 0 (HOH_FIX_STALE) is
+// the decodable variant: the smallest candidate's own bytes are kept, and when the plain fastpath stream (A)
+// beats every searched candidate including their predictor-map overhead the channel is written with the
+// single-predictor header A belongs to.
 __global__ void k_layer_decide(LayerGeom lg, uint64_t n_planes, const hoh_stream_result* __restrict__ results,
+                               uint32_t fix, uint8_t* __restrict__ hdr, uint32_t* __restrict__ hdr_len,
                                uint32_t* __restrict__ kept_slot, uint32_t* __restrict__ best_size,
-                               int32_t* __restrict__ status) {
+                               uint32_t* __restrict__ with_idx, int32_t* __restrict__ status) {
     const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (p >= n_planes) return;
     const hoh_stream_result* r = results + p * kLayerSlots;
     const uint64_t bits = (uint64_t)lg.depth * lg.per;
     uint32_t best = (uint32_t)((bits + bits % 8 + 1024) / 8);  // :22
     uint32_t kept = 0xffffffffu;  // nothing kept: the reference would emit an uninitialised buffer
+    uint32_t idx = lg.cells ? 1u : 0u;
     int32_t st = r[0].status;
-    if (r[0].size < best) {  // :115-120
-        best = r[0].size;
-        kept = 0;
-    }
     if (lg.mode) {
         if (lg.cells) st = st ? st : r[1].status;
         for (int k = 2; k < kLayerSlots; k++) st = st ? st : r[k].status;
-        const bool up = r[2].size < r[3].size;
-        const uint32_t first = up ? r[2].size : r[3].size;
-        if (first < best) best = first;  // size updated, buffers NOT swapped (D7): kept stays
-        for (int k = 0; k < 3; k++)
-            if (r[4 + k].size < best) {
-                best = r[4 + k].size;
-                kept = 4 + k;
+    }
+    if (fix) {
+        best = r[0].size;
+        kept = 0;
+        if (lg.mode) {
+            uint32_t sb = r[2].size, sk = 2;
+            for (uint32_t k = 3; k < (uint32_t)kLayerSlots; k++)
+                if (r[k].size < sb) {
+                    sb = r[k].size;
+                    sk = k;
+                }
+            const uint64_t searched = (uint64_t)sb + (lg.cells ? hdr_len[p] + r[1].size : 5u);
+            if (searched < (uint64_t)r[0].size + 5u) {
+                best = sb;
+                kept = sk;
+            } else if (lg.cells) {  // A under the header it was coded for: 10 | 00 00 | 00 10
+                uint8_t* h = hdr + p * kLayerHdrCap;
+                h[0] = 0x10;
+                h[1] = 0;
+                h[2] = 0;
+                h[3] = 0x00;
+                h[4] = 0x10;
+                hdr_len[p] = 5;
+                idx = 0;
             }
+        }
+    } else {
+        if (r[0].size < best) {  // :115-120
+            best = r[0].size;
+            kept = 0;
+        }
+        if (lg.mode) {
+            const bool up = r[2].size < r[3].size;
+            const uint32_t first = up ? r[2].size : r[3].size;
+            if (first < best) best = first;  // size updated, buffers NOT swapped (D7): kept stays
+            for (int k = 0; k < 3; k++)
+                if (r[4 + k].size < best) {
+                    best = r[4 + k].size;
+                    kept = 4 + k;
+                }
+        }
     }
     kept_slot[p] = kept;
     best_size[p] = best;
+    with_idx[p] = idx;
     status[p] = st;
 }
 
@@ -2307,6 +2408,7 @@ __global__ void __launch_bounds__(256) k_layer_assemble(LayerGeom lg, const uint
                                                         const hoh_stream_result* __restrict__ results,
                                                         const uint32_t* __restrict__ kept_slot,
                                                         const uint32_t* __restrict__ best_size,
+                                                        const uint32_t* __restrict__ with_idx,
                                                         const int32_t* __restrict__ status,
                                                         const uint8_t* __restrict__ cand, uint8_t* __restrict__ out,
                                                         uint64_t out_base, hoh_stream_result* __restrict__ final_results) {
@@ -2315,7 +2417,7 @@ __global__ void __launch_bounds__(256) k_layer_assemble(LayerGeom lg, const uint
     const hoh_stream_result* r = results + p * kLayerSlots;
     uint32_t at = hdr_len[p];
     for (uint32_t i = threadIdx.x; i < at; i += blockDim.x) dst[i] = hdr[p * kLayerHdrCap + i];
-    if (lg.cells) {  // :308-317 the predictor-index stream follows the masks
+    if (with_idx[p]) {  // :308-317 the predictor-index stream follows the masks
         const uint8_t* src = cand + r[1].start;
         for (uint32_t i = threadIdx.x; i < r[1].size; i += blockDim.x) dst[at + i] = src[i];
         at += r[1].size;
@@ -2683,7 +2785,7 @@ __global__ void __launch_bounds__(128) k_lz_walk(const uint32_t* __restrict__ st
 
 // descriptors of the 4 side streams of every tile (lz.hpp:102-141: range 256, 10 bits)
 __global__ void k_lz_streams(uint64_t n_tiles, const uint32_t* __restrict__ counts, uint32_t side_stride,
-                             uint32_t slab, hoh_enc_stream* __restrict__ streams) {
+                             uint32_t slab, uint32_t enc_flags, hoh_enc_stream* __restrict__ streams) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n_tiles * 4u) return;
     hoh_enc_stream st;
@@ -2695,7 +2797,7 @@ __global__ void k_lz_streams(uint64_t n_tiles, const uint32_t* __restrict__ coun
     for (int b = 0; b < 8; b++) st.prefix[b] = 0;
     st.out_off = i * (uint64_t)slab;
     st.out_cap = slab;
-    st.reserved = 0;
+    st.reserved = enc_flags;
     streams[i] = st;
 }
 
@@ -2927,6 +3029,355 @@ __global__ void __launch_bounds__(256) k_tile_emit(uint64_t first_tile, uint32_t
     cta_copy(body, out8 + c0.start, c0.size);
     cta_copy(body + c0.size, (plain ? out8 : out9) + c1.start, c1.size);
     cta_copy(body + c0.size + c1.size, (plain ? out8 : out9) + c2.start, c2.size);
+}
+
+// =================================================================================================
+// Tile decoder, any cruncher mode — the inverse of encode_tile as a WORKING decoder has to do it
+// (dhoh.cpp:22-141, un_lz.hpp:66-180, layer_decode.hpp:127-277 with SURVEY defects D2, D3, D4, D8, D9, D10,
+// D12 corrected; none of the corrections touches hot-path arithmetic).  A tile's bytes are parsed in
+// phases, because every entropy stream's end is only known once its header has been read:
+//   begin -> LZ side stream 0 .. 3 (one batched decode each) -> channels (order byte, size varints, layer
+//   headers) -> predictor-index streams -> residual streams -> LZ expansion -> un-prediction -> colour.
+// =================================================================================================
+struct DTile {
+    uint64_t cursor;      // next unread byte of the tile
+    uint64_t end;         // one past the tile's last byte
+    uint32_t colour_mode; // 128 or 2
+    int32_t status;
+    uint32_t lz_n[4];     // symbols in each LZ side stream
+    uint32_t lz_streams;  // 3 or 4
+    uint32_t uncovered;   // pixels no LZ match covers = residuals per channel
+};
+
+struct DPlane {
+    uint64_t main_off;    // where the residual stream's header starts (set after the index stream is decoded)
+    uint32_t kind;        // 0: single predictor 0x0010 = pure MED (fastpath inverse); 1: predictor grid
+    uint32_t depth;       // 8 or 9
+    uint32_t n_masks;
+    int32_t status;
+    uint16_t masks[16];
+};
+
+// tile header: 00 00 | colour mode | LZ tag
+__global__ void k_dt_begin(uint64_t n_tiles, const uint8_t* __restrict__ packed, uint64_t packed_bytes,
+                           const uint64_t* __restrict__ tile_off, uint32_t side_stride, DTile* __restrict__ tiles,
+                           hoh_dec_stream* __restrict__ streams) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const ByteView b{packed, packed_bytes};
+    const uint64_t off = tile_off[t];
+    DTile d;
+    d.end = tile_off[t + 1];
+    d.status = HOH_S_OK;
+    d.colour_mode = b[off + 2];
+    // 1x1 sub-tiles (choh.cpp:112-116), a colour mode this library emits, the LZ tag find_lz_rgb writes (lz.hpp:100)
+    if (b[off] != 0 || b[off + 1] != 0 || (d.colour_mode != 128u && d.colour_mode != 2u) || b[off + 3] != 0x03 ||
+        d.end > packed_bytes || d.end < off + 4u)
+        d.status = HOH_S_BAD_LAYER;
+    d.cursor = off + 4u;
+    for (int k = 0; k < 4; k++) d.lz_n[k] = 0;
+    d.lz_streams = 3;
+    d.uncovered = 0;
+    tiles[t] = d;
+    hoh_dec_stream st;
+    st.in_off = d.cursor;
+    st.sym_off = (t * 4u) * side_stride;
+    st.sym_cap = d.status ? 0u : side_stride;
+    st.flags = HOH_FIX_DECODER;
+    streams[t] = st;
+}
+
+// after LZ side stream k: advance, describe stream k + 1.  The fourth stream exists only for seek windows wider
+// than 2^8 (lz.hpp:132) and nothing in the bytes says so (D3): it is there iff the next byte starts an entropy
+// stream of range 256 (0x81 0x7f), which the channel-order byte that follows otherwise (0x24) never is.
+__global__ void k_dt_lz_next(uint64_t n_tiles, uint32_t k, const uint8_t* __restrict__ packed, uint64_t packed_bytes,
+                             const hoh_dec_result* __restrict__ res, uint32_t side_stride, DTile* __restrict__ tiles,
+                             hoh_dec_stream* __restrict__ streams) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    DTile& d = tiles[t];
+    const ByteView b{packed, packed_bytes};
+    const bool ran = d.status == HOH_S_OK && (k < 3u || d.lz_streams == 4u);
+    if (ran) {
+        const hoh_dec_result r = res[t];
+        if (r.status) d.status = r.status;
+        else if (r.end_off > d.end || r.range != 256u) d.status = HOH_S_BAD_LAYER;
+        else {
+            d.cursor = r.end_off;
+            d.lz_n[k] = r.n;
+        }
+    }
+    if (k == 2u && d.status == HOH_S_OK && b[d.cursor] == 0x81 && b[d.cursor + 1] == 0x7f) d.lz_streams = 4;
+    if (k >= 3u) return;
+    const bool next = d.status == HOH_S_OK && (k + 1u < 3u || d.lz_streams == 4u);
+    hoh_dec_stream st;
+    st.in_off = d.cursor;
+    st.sym_off = (t * 4u + k + 1u) * side_stride;
+    st.sym_cap = next ? side_stride : 0u;
+    st.flags = HOH_FIX_DECODER;
+    streams[t] = st;
+}
+
+// channel-order byte, two size varints, and the layer header of each of the three channels
+// (layer_decode.hpp:136-139, 208-235).  One thread per tile.  idx_streams: 3 per tile (inactive: capacity 0).
+__global__ void k_dt_channels(uint64_t n_tiles, const uint8_t* __restrict__ packed, uint64_t packed_bytes, uint32_t xt,
+                              uint32_t yt, uint32_t cells_pad, DTile* __restrict__ tiles, DPlane* __restrict__ planes,
+                              hoh_dec_stream* __restrict__ idx_streams) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    DTile& d = tiles[t];
+    const ByteView b{packed, packed_bytes};
+    uint64_t at = d.cursor;
+    uint64_t chan[4];
+    if (d.status == HOH_S_OK) {
+        if (b[at] != 0x24) d.status = HOH_S_BAD_LAYER;  // three channels, never reordered (choh.cpp:352)
+        at++;
+        uint32_t size[2];
+        for (int k = 0; k < 2; k++) {  // read_varint varint.hpp:6-27
+            const uint32_t b0 = b[at++];
+            uint32_t v = b0;
+            if (b0 & 0x80u) {
+                const uint32_t b1 = b[at++];
+                v = ((b0 & 0x7fu) << 7) + b1;
+                if (b1 & 0x80u) v = ((b0 & 0x7fu) << 14) + ((b1 & 0x7fu) << 7) + b[at++];
+            }
+            size[k] = v;
+        }
+        chan[0] = at;
+        chan[1] = chan[0] + size[0];
+        chan[2] = chan[1] + size[1];
+        chan[3] = d.end;
+        if (chan[2] > d.end) d.status = HOH_S_BAD_LAYER;
+    }
+    for (uint32_t c = 0; c < 3u; c++) {
+        DPlane pl;
+        pl.status = d.status;
+        pl.kind = 0;
+        pl.depth = (c == 0u || d.colour_mode == 2u) ? 8u : 9u;  // sub-green differences are 9-bit (choh.cpp:240, 251; D4)
+        pl.n_masks = 1;
+        pl.main_off = 0;
+        for (int m = 0; m < 16; m++) pl.masks[m] = 0x0010;
+        hoh_dec_stream st;
+        st.in_off = d.cursor;
+        st.sym_off = (t * 3u + c) * cells_pad;
+        st.sym_cap = 0;
+        st.flags = HOH_FIX_DECODER;
+        if (pl.status == HOH_S_OK) {
+            uint64_t q = chan[c];
+            if (b[q] != 0x10) pl.status = HOH_S_BAD_LAYER;  // prediction on, no compaction (layer_encode.hpp:57)
+            const uint32_t gx = (uint32_t)b[q + 1] + 1u, gy = (uint32_t)b[q + 2] + 1u;
+            q += 3;
+            if (gx == 1u && gy == 1u) {
+                const uint32_t mask = ((uint32_t)b[q] << 8) | b[q + 1];
+                q += 2;
+                if (mask != 0x0010u) pl.status = HOH_S_BAD_LAYER;  // the only single predictor the encoder emits
+                pl.main_off = q;
+            } else {
+                if (gx != xt || gy != yt) pl.status = HOH_S_BAD_LAYER;  // the grid is a function of the tile size
+                pl.kind = 1;
+                pl.n_masks = b[q++];
+                if (pl.n_masks == 0u || pl.n_masks > 14u) pl.status = HOH_S_BAD_LAYER;
+                for (uint32_t m = 0; m < pl.n_masks && m < 16u; m++, q += 2)
+                    pl.masks[m] = (uint16_t)(((uint32_t)b[q] << 8) | b[q + 1]);
+                if (pl.status == HOH_S_OK) {
+                    st.in_off = q;
+                    st.sym_cap = xt * yt;
+                }
+            }
+            if (q > chan[c + 1]) pl.status = HOH_S_BAD_LAYER;
+        }
+        planes[t * 3u + c] = pl;
+        idx_streams[t * 3u + c] = st;
+    }
+}
+
+// residual stream descriptors (after the index streams are decoded) + the planes' predictor maps
+__global__ void k_dt_main(uint64_t n_planes, uint32_t cells, uint32_t cells_pad, uint32_t plane_stride, uint32_t npx,
+                          const hoh_dec_result* __restrict__ idx_res, const uint16_t* __restrict__ idx_syms,
+                          DPlane* __restrict__ planes, uint16_t* __restrict__ maps,
+                          hoh_dec_stream* __restrict__ streams) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_planes) return;
+    DPlane& pl = planes[p];
+    if (pl.status == HOH_S_OK && pl.kind == 1u) {
+        const hoh_dec_result r = idx_res[p];
+        if (r.status) pl.status = r.status;
+        else if (r.n != cells || r.range != pl.n_masks) pl.status = HOH_S_BAD_LAYER;
+        else {
+            pl.main_off = r.end_off;
+            for (uint32_t c = 0; c < cells; c++) {
+                const uint32_t i = idx_syms[p * cells_pad + c];
+                maps[p * cells + c] = pl.masks[i < pl.n_masks ? i : 0u];  // layer_decode.hpp:231-233
+            }
+        }
+    }
+    hoh_dec_stream st;
+    st.in_off = pl.main_off;
+    st.sym_off = p * (uint64_t)plane_stride;
+    st.sym_cap = pl.status == HOH_S_OK ? npx : 0u;
+    st.flags = HOH_FIX_DECODER;
+    streams[p] = st;
+}
+
+// un_lz.hpp:150-170 as it has to work: runs of 255 accumulate, the entry after them completes the count of
+// uncovered pixels, then one match of length + 4 at the recorded distance; what follows the last match is
+// uncovered (D12).  One warp per tile: the walk is warp-uniform, the fills are cooperative.
+__global__ void __launch_bounds__(128) k_dt_unlz(uint64_t n_tiles, uint32_t npx, uint32_t plane_stride,
+                                                 const uint16_t* __restrict__ side, uint32_t side_stride,
+                                                 DTile* __restrict__ tiles, uint16_t* __restrict__ backref) {
+    const uint32_t lane = lane_id();
+    const uint64_t t = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
+    DTile& d = tiles[t];
+    uint16_t* B = backref + t * plane_stride;
+    for (uint32_t i = lane; i < npx; i += 32) B[i] = 0;
+    __syncwarp();
+    if (d.status != HOH_S_OK) return;
+    const uint16_t* s0 = side + (t * 4u) * side_stride;
+    const uint16_t* s1 = s0 + side_stride;
+    const uint16_t* s2 = s1 + side_stride;
+    const uint16_t* s3 = s2 + side_stride;
+    const bool wide = d.lz_streams == 4u;
+    uint32_t pos = 0, group = 0, covered = 0, i = 0;
+    int32_t st = HOH_S_OK;
+    const uint32_t n0 = d.lz_n[0];
+    if (d.lz_n[1] != d.lz_n[2] || (wide && d.lz_n[3] != d.lz_n[1])) st = HOH_S_BAD_LAYER;
+    while (st == HOH_S_OK && i < n0) {
+        uint32_t count = 0;
+        while (i < n0 && s0[i] == 255u) {
+            count += 255u;
+            i++;
+        }
+        if (i >= n0) break;
+        count += s0[i++];
+        pos += count;
+        if (group >= d.lz_n[1]) {
+            st = HOH_S_BAD_LAYER;
+            break;
+        }
+        const uint32_t len = (uint32_t)s1[group] + 4u;
+        const uint32_t back = (wide ? ((uint32_t)s3[group] << 8) : 0u) + s2[group];
+        group++;
+        if (pos + len > npx || back == 0u || back > pos) {
+            st = HOH_S_BAD_LAYER;
+            break;
+        }
+        for (uint32_t k = lane; k < len; k += 32) B[pos + k] = (uint16_t)back;
+        pos += len;
+        covered += len;
+    }
+    if (lane == 0) {
+        if (st) d.status = st;
+        d.uncovered = npx - covered;
+    }
+}
+
+// Un-prediction of every plane (one thread per plane, raster order, LZ copies interleaved as in
+// unprediction.hpp:63-65): kind 0 = exact inverse of channelpredict_fastpath (D10), kind 1 = unpredict_all.
+__global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, int h, int x_tiles, int y_tiles,
+                                                     uint32_t plane_stride, const DPlane* __restrict__ planes,
+                                                     const DTile* __restrict__ tiles,
+                                                     const hoh_dec_result* __restrict__ main_res,
+                                                     const uint16_t* __restrict__ resid,
+                                                     const uint16_t* __restrict__ maps,
+                                                     const uint16_t* __restrict__ backref, uint16_t* __restrict__ out,
+                                                     uint16_t* __restrict__ top_s, uint8_t* __restrict__ bp_s,
+                                                     int32_t* __restrict__ plane_status) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_planes) return;
+    const DPlane pl = planes[p];
+    const DTile& dt = tiles[p / 3u];
+    int32_t st = pl.status ? pl.status : dt.status;
+    if (!st) st = main_res[p].status;
+    if (!st && (main_res[p].n != dt.uncovered || main_res[p].range != (1u << pl.depth))) st = HOH_S_BAD_LAYER;
+    plane_status[p] = st;
+    if (st) return;
+    const int c = 1 << pl.depth, half = c >> 1;
+    const uint16_t* src = resid + p * (uint64_t)plane_stride;
+    const uint16_t* br = backref + (p / 3u) * (uint64_t)plane_stride;
+    uint16_t* dst = out + p * (uint64_t)plane_stride;
+    uint64_t next_resid = 0;
+    if (pl.kind == 0u) {
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                const uint64_t at = (uint64_t)y * w + x;
+                if (br[at]) {
+                    dst[at] = dst[at - br[at]];
+                    continue;
+                }
+                const int L = x ? dst[at - 1] : half;
+                const int T = y ? dst[at - w] : half;
+                const int TL = (x && y) ? dst[at - w - 1] : half;
+                dst[at] = (uint16_t)(((int)src[next_resid++] + p_med_grad(T, L, TL) - half) & (c - 1));
+            }
+        return;
+    }
+    const int tw = (w + x_tiles - 1) / x_tiles, th = (h + y_tiles - 1) / y_tiles;
+    const uint16_t* tmap = maps + p * (uint64_t)x_tiles * y_tiles;
+    uint16_t* top = top_s + p * (uint64_t)w;
+    uint8_t* bp = bp_s + p * (uint64_t)w;
+    for (int i = 0; i < w; i++) {
+        top[i] = (uint16_t)half;
+        bp[i] = 4;
+    }
+    for (int y = 0; y < h; y++) {  // same walk as k_raster_walk<true>
+        int left = half, left_top = half;
+        int bp_left = bp[w - 1];
+        const bool last_row = y + 1 >= h;
+        const uint16_t* mrow = tmap + (size_t)((y + 1) / th) * x_tiles;
+        int first_of_row = 0;
+        for (int x = 0; x < w; x++) {
+            const uint64_t at = (uint64_t)y * w + x;
+            const int tr = (x + 1 < w) ? top[x + 1] : (w > 1 ? first_of_row : top[0]);
+            const int t = top[x];
+            Cand k;
+            candidates(left, t, left_top, tr, false, k);
+            const int pred = p_mid(cand_at(k, bp[x]), cand_at(k, bp_left));
+            int v;
+            if (br[at]) {
+                v = dst[at - br[at]];  // unprediction.hpp:63-65
+            } else {
+                const uint32_t tval = (uint32_t)((int)src[next_resid++] - c - half + pred) & 0xffffu;  // :67
+                v = (int)(tval % (uint32_t)c);
+            }
+            dst[at] = (uint16_t)v;
+            if (x == 0) first_of_row = v;
+            left_top = t;
+            top[x] = (uint16_t)v;
+            left = v;
+            const int nb = last_row ? 0 : pick_best(v, k, mrow[x / tw], c);
+            bp[x] = (uint8_t)nb;
+            bp_left = nb;
+        }
+    }
+}
+
+// planes -> interleaved RGB in the image (inverse of channel.hpp:73-79 for colour mode 128, D4), tile status
+__global__ void __launch_bounds__(256) k_dt_store(TileGeom g, uint64_t first_tile, uint32_t plane_stride,
+                                                  const DTile* __restrict__ tiles,
+                                                  const int32_t* __restrict__ plane_status,
+                                                  const uint16_t* __restrict__ planes, uint8_t* __restrict__ rgb,
+                                                  int32_t* __restrict__ status) {
+    const uint64_t lt = blockIdx.x, t = first_tile + lt;
+    int32_t st = tiles[lt].status;
+    for (int c = 0; c < 3; c++) st = st ? st : plane_status[lt * 3u + c];
+    if (threadIdx.x == 0) status[t] = st;
+    if (st) return;
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
+    uint8_t* img = rgb + (t / g.tiles_per_image) * (uint64_t)g.width * g.height * 3u;
+    const uint16_t* a = planes + (lt * 3u) * (uint64_t)plane_stride;
+    const uint16_t* b = a + plane_stride;
+    const uint16_t* c = b + plane_stride;
+    const bool sub_green = tiles[lt].colour_mode == 128u;
+    for (uint32_t i = threadIdx.x; i < tw * th; i += blockDim.x) {
+        const uint32_t x = i % tw, y = i / tw;
+        uint8_t* o = img + ((uint64_t)(y0 + y) * g.width + x0 + x) * 3u;
+        const uint32_t gr = a[i];
+        o[1] = (uint8_t)gr;
+        o[0] = (uint8_t)(sub_green ? (b[i] + gr - 256u) & 255u : b[i]);
+        o[2] = (uint8_t)(sub_green ? (c[i] + gr - 256u) & 255u : c[i]);
+    }
 }
 
 }  // namespace hohk

@@ -113,14 +113,15 @@ SIGNATURES = {
     "hoh_unpredict_all_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "hoh_predict_section_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _int, _vp, _int, _vp, _u32, _vp]),
     "hoh_predictor_search_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _vp, _vp]),
-    "hoh_encode_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, _vp, _sz, _vp, _vp]),
+    "hoh_encode_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, C.c_uint, _vp, _sz, _vp, _vp]),
+    "hoh_decode_images": (_int, [_vp, _vp, _sz, _vp, _sz, _u32, _u32, _vp, _vp]),
     "hoh_find_lz_stride": (_sz, [_int, _int]),
-    "hoh_find_lz_rgb_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
-    "hoh_find_lz_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "hoh_find_lz_rgb_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, C.c_uint, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "hoh_find_lz_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, C.c_uint, _vp, _vp, _vp, _sz, _vp, _vp]),
     "hoh_find_lz_rgb": (_int, [_vp, _vp, _sz, _int, _int, _vp, _sz, _vp, _int, _int, C.POINTER(_sz)]),
     "hoh_layer_encode_out_bytes": (_sz, [_sz, _int, _int, _int, _int]),
-    "hoh_layer_encode_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _sz, _u32, _vp, _sz, _vp, _vp, _sz,
-                                      _vp]),
+    "hoh_layer_encode_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, C.c_uint, _vp, _sz, _u32, _vp, _sz, _vp, _vp,
+                                      _sz, _vp]),
     "hoh_channel_picker_dev": (_int, [_vp, _vp, _sz, _int, _int, _vp]),
     "hoh_channel_picker": (_int, [_vp, _vp, _sz, _int, _int, _vp]),
     "hoh_encode_entropy": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _u32, C.POINTER(_sz), C.POINTER(_int)]),
@@ -505,7 +506,7 @@ class HohGpu:
             b = np.ascontiguousarray(bonus, dtype=np.int32)
             d_bonus = self.alloc(b.nbytes).upload(b)
         try:
-            self._ck(self.lib.hoh_find_lz_rgb_batch(self.ctx, d_rgb.ptr, n_tiles, width, height, distance,
+            self._ck(self.lib.hoh_find_lz_rgb_batch(self.ctx, d_rgb.ptr, n_tiles, width, height, distance, 0,
                                                     d_bonus.ptr if d_bonus else None, d_nuke.ptr, d_lz.ptr, stride,
                                                     d_size.ptr, d_st.ptr), "hoh_find_lz_rgb_batch")
             sizes = d_size.download(np.uint32, n_tiles)
@@ -535,7 +536,7 @@ class HohGpu:
                 self.alloc(n_streams * RESULT_DT.itemsize), self.alloc(packed_cap), self.alloc((n_streams + 1) * 8)]
         d_rgb, d_nuke, d_lz, d_size, d_st, d_out, d_res, d_packed, d_off = bufs
         try:
-            self._ck(self.lib.hoh_find_lz_images(self.ctx, d_rgb.ptr, n_images, width, height, 6, None, d_nuke.ptr,
+            self._ck(self.lib.hoh_find_lz_images(self.ctx, d_rgb.ptr, n_images, width, height, 6, 0, None, d_nuke.ptr,
                                                  d_lz.ptr, lz_stride, d_size.ptr, d_st.ptr), "hoh_find_lz_images")
             self._ck(self.lib.hoh_encode_images_s0(self.ctx, d_rgb.ptr, n_images, width, height, d_nuke.ptr, d_out.ptr,
                                                    out_bytes, d_res.ptr, d_packed.ptr, packed_cap, d_off.ptr),
@@ -558,7 +559,7 @@ class HohGpu:
         self._ck(self.lib.hoh_channel_picker(self.ctx, _ptr(src), src.size, total, target, _ptr(out)), "hoh_channel_picker")
         return out
 
-    def encode_images(self, rgb, n_images, width, height, mode):
+    def encode_images(self, rgb, n_images, width, height, mode, flags=0):
         """hoh_encode_images: encode_tile for every tile -> (list of tile bytes, TILE_DT records)."""
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
         g = self.tile_geometry(width, height)
@@ -569,7 +570,7 @@ class HohGpu:
         d_off = self.alloc((n_tiles + 1) * 8)
         d_tiles = self.alloc(n_tiles * TILE_DT.itemsize)
         try:
-            self._ck(self.lib.hoh_encode_images(self.ctx, d_rgb.ptr, n_images, width, height, mode, d_packed.ptr,
+            self._ck(self.lib.hoh_encode_images(self.ctx, d_rgb.ptr, n_images, width, height, mode, flags, d_packed.ptr,
                                                 packed_cap, d_off.ptr, d_tiles.ptr), "hoh_encode_images")
             off = d_off.download(np.uint64, n_tiles + 1)
             rec = d_tiles.download(TILE_DT, n_tiles)
@@ -579,7 +580,27 @@ class HohGpu:
                 b.free()
         return [packed[int(off[t]):int(off[t + 1])].tobytes() for t in range(n_tiles)], rec
 
-    def layer_encode_batch(self, planes, n_planes, w, h, depth, mode, nuke=None, planes_per_map=1):
+    def decode_images(self, tiles, n_images, width, height):
+        """hoh_decode_images: list of tile byte strings (n_images * tiles_per_image) -> (rgb u8, status per tile)."""
+        off = np.zeros(len(tiles) + 1, np.uint64)
+        off[1:] = np.cumsum([len(t) for t in tiles])
+        blob = np.frombuffer(b"".join(tiles) + bytes(64), np.uint8)
+        d_packed = self.alloc(blob.nbytes).upload(blob)
+        d_off = self.alloc(off.nbytes).upload(off)
+        d_rgb = self.alloc(n_images * width * height * 3)
+        d_rgb.zero()
+        d_st = self.alloc(len(tiles) * 4)
+        try:
+            self._ck(self.lib.hoh_decode_images(self.ctx, d_packed.ptr, blob.nbytes, d_off.ptr, n_images, width, height,
+                                                d_rgb.ptr, d_st.ptr), "hoh_decode_images")
+            rgb = d_rgb.download(np.uint8, n_images * width * height * 3)
+            st = d_st.download(np.int32, len(tiles))
+        finally:
+            for b in (d_packed, d_off, d_rgb, d_st):
+                b.free()
+        return rgb, st
+
+    def layer_encode_batch(self, planes, n_planes, w, h, depth, mode, nuke=None, planes_per_map=1, flags=0):
         """layer_encode.hpp:11 for n_planes planes of the same shape -> list of (payload bytes, status, kept slot).
         nuke: (n_planes / planes_per_map) maps of w*h bytes, or None."""
         planes = np.ascontiguousarray(planes, dtype=np.uint16).ravel()
@@ -597,7 +618,7 @@ class HohGpu:
         d_packed = self.alloc(packed_cap)
         d_off = self.alloc((n_planes + 1) * 8)
         try:
-            self._ck(self.lib.hoh_layer_encode_batch(self.ctx, d_pl.ptr, n_planes, w, h, depth, mode,
+            self._ck(self.lib.hoh_layer_encode_batch(self.ctx, d_pl.ptr, n_planes, w, h, depth, mode, flags,
                                                      d_nuke.ptr if d_nuke else None, w * h, planes_per_map, d_out.ptr,
                                                      out_bytes, d_res.ptr, d_packed.ptr, packed_cap, d_off.ptr),
                      "hoh_layer_encode_batch")

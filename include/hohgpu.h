@@ -54,6 +54,22 @@ extern "C" {
 #define HOH_FIX_ADVANCE 2u    /* D8: leave *byte_pointer after the rANS payload, not at its start   */
 #define HOH_FIX_EMPTY 4u      /* D2: a zero-symbol stream has no metadata byte                      */
 #define HOH_FIX_ALL 7u
+/* Decoder side: recognise the table of a stream with ONE distinct symbol, whose over-wide frequency field reads 0
+ * and increments the clamp bits sharing its first byte (D6: every stock `choh -s0` file of a photograph has such
+ * a stream — the LZ stream of 255s), and give that symbol the whole range.
+ * The pattern cannot be produced by a valid table, so the flag never changes how a valid stream decodes. */
+#define HOH_FIX_CARRY 32u
+#define HOH_FIX_DECODER 39u /* HOH_FIX_ALL | HOH_FIX_CARRY: what hoh_decode_images uses */
+/* Encoder side (hoh_layer_encode_batch, hoh_encode_images): D7 — keep the winning candidate's own bytes
+ * instead of the reference's stale buffer, and give the plain fastpath stream its own single-predictor header
+ * when it beats the searched candidates.  0 = byte-for-byte reference output (not decodable where D7 strikes). */
+#define HOH_FIX_STALE 8u
+/* Encoder side: a stream with ONE distinct symbol would give it all of 2^prob_bits, which the table's
+ * prob_bits-wide field cannot hold (D6): neither the reference's decoder nor any other can read it back.
+ * With this flag one count goes to a neighbouring symbol that never occurs (a few bits per stream), and table
+ * mode 1 (maxbits-wide fields) is not chosen when a frequency does not fit its field. */
+#define HOH_FIX_LONE 16u
+#define HOH_FIX_ENCODER 24u /* HOH_FIX_STALE | HOH_FIX_LONE: what hoh_decode_images can always invert */
 
 #define HOH_MAX_RANGE 512     /* largest alphabet on the hot path (depth-9 sub-green planes)        */
 #define HOH_MAX_PROB_BITS 19  /* layer_encode.hpp:359-392 tries up to 19                            */
@@ -108,7 +124,7 @@ typedef struct hoh_enc_stream {
     uint8_t prefix[8];
     uint64_t out_off;    /* byte offset of this stream's slab in the output buffer; multiple of 16      */
     uint32_t out_cap;    /* slab bytes, multiple of 16; see hoh_enc_slab_bytes                          */
-    uint32_t reserved;
+    uint32_t reserved;   /* 0, or HOH_FIX_LONE                                                          */
 } hoh_enc_stream;
 
 typedef struct hoh_stream_result {
@@ -289,8 +305,21 @@ typedef struct hoh_tile_result {
  * tiles (width or height not a multiple of the tile count) return HOH_E_UNSUPPORTED.  Large batches are
  * processed in chunks of whole images sized by an internal scratch budget. */
 int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
-                      int mode, uint8_t* d_packed, size_t packed_cap, uint64_t* d_tile_off,
+                      int mode, unsigned flags /* 0 or HOH_FIX_ENCODER */, uint8_t* d_packed, size_t packed_cap, uint64_t* d_tile_off,
                       hoh_tile_result* d_tiles);
+
+/* The inverse: tiles as hoh_encode_images (or stock `choh`) wrote them -> interleaved RGB8 images, entirely on
+ * the device.  This is the decoder the format needs rather than the reference's (dhoh.cpp:22-141,
+ * un_lz.hpp:66-180, layer_decode.hpp:127-277 cannot parse choh's output: SURVEY D2, D3, D4, D8, D9, D10, D12 are
+ * corrected here; none of the corrections changes hot-path arithmetic): tile header, the 3 or 4 LZ side streams,
+ * channel order and sizes, per channel the layer header / predictor masks / predictor-index stream / residual
+ * stream, LZ expansion into back-references, un-prediction (pure-MED inverse for the single-predictor header,
+ * unpredict_all otherwise) with the copies of unprediction.hpp:63-65, colour inverse, tile scatter.
+ * Tile t's bytes are d_packed[d_tile_off[t], d_tile_off[t+1]).  d_status[t] != 0: the tile could not be decoded
+ * (its pixels are left untouched).  Channels the reference emitted under defect D7 (see HOH_FIX_STALE) decode
+ * to wrong pixels without any error, exactly as they would with any conforming decoder. */
+int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes, const uint64_t* d_tile_off,
+                      size_t n_images, uint32_t width, uint32_t height, uint8_t* d_rgb, int32_t* d_status);
 
 /* ------------------------------------------------------------------------------------------ */
 /* (v) LZ match finder — find_lz_rgb lz.hpp:6-145 over N tiles                 */
@@ -306,7 +335,7 @@ size_t hoh_find_lz_stride(int w, int h);
  * with lz_stride >= hoh_find_lz_stride(w, h), d_lz_size[n_tiles] = find_lz_rgb's return value,
  * d_status[n_tiles] (optional) = HOH_S_*. */
 int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, int w, int h, int distance,
-                          const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
+                          unsigned flags /* 0 or HOH_FIX_LONE */, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
                           uint32_t* d_lz_size, int32_t* d_status);
 
 /* The same for whole images: every image is cut into tiles as choh.cpp:454-484 cuts it and find_lz_rgb runs
@@ -314,7 +343,7 @@ int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, in
  * n_tiles * nuke_stride bytes with nuke_stride = tile_w*tile_h rounded up to 8 (tile t's map starts at
  * t * nuke_stride; it is the map hoh_encode_images_s0 takes); lz_stride >= hoh_find_lz_stride(tile_w, tile_h). */
 int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
-                       int distance, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
+                       int distance, unsigned flags /* 0 or HOH_FIX_LONE */, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
                        uint32_t* d_lz_size, int32_t* d_status);
 
 /* layer_encode.hpp:11 for n_planes planes of the same geometry (w x h, depth, cruncher mode 0..4): the
@@ -329,7 +358,7 @@ int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint
  * If d_packed != NULL the payloads are also gathered back to back (d_packed_off: n_planes+1 offsets). */
 size_t hoh_layer_encode_out_bytes(size_t n_planes, int w, int h, int depth, int mode);
 int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
-                           int mode, const uint8_t* d_nuke, size_t nuke_stride, uint32_t planes_per_map,
+                           int mode, unsigned flags /* 0 or HOH_FIX_STALE | HOH_FIX_LONE */, const uint8_t* d_nuke, size_t nuke_stride, uint32_t planes_per_map,
                            uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results, uint8_t* d_packed,
                            size_t packed_cap, uint64_t* d_packed_off);
 

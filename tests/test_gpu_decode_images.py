@@ -1,0 +1,117 @@
+"""hoh_decode_images: the working tile decoder (all cruncher modes, LZ back-references, both photographic colour
+modes) against hoh_encode_images — exact round trips at every mode with HOH_FIX_STALE (the decodable variant of
+SURVEY D7), at mode 0 also for the byte-exact reference output and for a stock `choh` file."""
+import os
+
+import numpy as np
+import pytest
+
+import gpu_lib
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIX_STALE = 24  # HOH_FIX_ENCODER = HOH_FIX_STALE | HOH_FIX_LONE
+
+
+def _images(rng, w, h, n, seed, mode):
+    imgs = [ol.photo_with_repeats(rng, w, h, seed + i) for i in range(n)]
+    if mode > 2 and n > 1:  # uncorrelated channels: the plain-RGB colour mode wins
+        imgs[1][..., 0] = rng.integers(0, 256, (h, w))
+        imgs[1][..., 2] = rng.integers(0, 256, (h, w))
+    return np.concatenate([i.ravel() for i in imgs])
+
+
+@pytest.mark.parametrize("w,h,mode,n", [(512, 512, 0, 3), (96, 80, 1, 4), (512, 256, 2, 2), (90, 70, 3, 4), (64, 96, 4, 3),
+                                        (768, 540, 2, 1), (33, 27, 2, 3)])
+def test_roundtrip_all_modes_with_lz(w, h, mode, n):
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(17 * mode + w)
+    rgb = _images(rng, w, h, n, 700 + mode, mode)
+    tiles, rec = g.encode_images(rgb, n, w, h, mode, FIX_STALE)
+    assert (rec["status"] == 0).all()
+    back, st = g.decode_images(tiles, n, w, h)
+    assert (st == 0).all(), st
+    assert np.array_equal(back, rgb), int(np.count_nonzero(back != rgb))
+    if mode > 2 and n > 1:
+        assert 2 in set(rec["colour_mode"])
+    # the LZ records are not empty: some pixels really are copies
+    assert sum(int(r) for r in rec["lz_size"]) > 20 * len(tiles)
+
+
+def test_reference_bytes_decode_at_mode0():
+    """Without HOH_FIX_STALE the tiles are the reference's bytes; at -s0 those are decodable (D7 needs mode >= 1)."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(2)
+    w, h, n = 512, 512, 2
+    rgb = _images(rng, w, h, n, 900, 0)
+    tiles, rec = g.encode_images(rgb, n, w, h, 0, 0)
+    back, st = g.decode_images(tiles, n, w, h)
+    assert (st == 0).all() and np.array_equal(back, rgb)
+
+
+def test_stock_choh_file_decodes():
+    """A file written by the real `choh -s0` (tests/golden): the container is parsed here on the host
+    (choh.cpp:436-506 read backwards), the tiles are decoded on the device -> the generator image."""
+    g = gpu_lib.gpu()
+    data = np.load(os.path.join(G, "layer_tile.npz"))["file_512x512_s0"].tobytes()
+    assert data[:6] == bytes([153, 72, 79, 72, 2, 8])
+    pos = 6
+
+    def varint():
+        nonlocal pos
+        b0 = data[pos]; pos += 1
+        if not b0 & 0x80:
+            return b0
+        b1 = data[pos]; pos += 1
+        if not b1 & 0x80:
+            return ((b0 & 0x7f) << 7) + b1
+        b2 = data[pos]; pos += 1
+        return ((b0 & 0x7f) << 14) + ((b1 & 0x7f) << 7) + b2
+
+    w, h = varint() + 1, varint() + 1
+    xt, yt = data[pos] + 1, data[pos + 1] + 1
+    pos += 2
+    assert (w, h, xt, yt) == (512, 512, 2, 2)
+    sizes = [varint() for _ in range(xt * yt - 1)]
+    tiles = []
+    for s in sizes:
+        tiles.append(data[pos:pos + s])
+        pos += s
+    tiles.append(data[pos:])
+    back, st = g.decode_images(tiles, 1, w, h)
+    assert (st == 0).all()
+    assert np.array_equal(back, ol.synth_rgb(512, 512, 1))
+
+
+def test_damaged_tiles_are_reported_not_decoded():
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(4)
+    w, h, n = 96, 80, 4
+    rgb = _images(rng, w, h, n, 950, 2)
+    tiles, rec = g.encode_images(rgb, n, w, h, 2, FIX_STALE)
+    bad = [bytearray(t) for t in tiles]
+    bad[0][2] = 77                      # unknown colour mode
+    bad[1][3] = 0                       # LZ tag
+    bad[2] = bad[2][: len(bad[2]) // 3]  # truncated
+    back, st = g.decode_images([bytes(b) for b in bad], n, w, h)
+    assert st[0] != 0 and st[1] != 0 and st[3] == 0
+    per = w * h * 3
+    assert np.array_equal(back[3 * per:], rgb[3 * per:])
+
+
+def test_reference_bytes_of_flat_and_matchless_images_decode():
+    """Reference-format tiles (no encoder-side fixes) whose streams have ONE distinct symbol — the LZ stream of
+    255s of every photograph without matches, the residual planes of a flat image — carry the over-wide
+    frequency field of SURVEY D6; HOH_FIX_CARRY recognises the pattern and undoes it."""
+    g = gpu_lib.gpu()
+    w = h = 256
+    flat = np.full((h, w, 3), (10, 200, 77), np.uint8)
+    flat[100:130, 50:90] = (255, 0, 255)          # 2 colours: palette territory, sub-green bytes are still produced
+    photo = ol.synth_rgb(w, h, 3).reshape(h, w, 3)
+    rgb = np.concatenate([flat.ravel(), photo.ravel()])
+    tiles, rec = g.encode_images(rgb, 2, w, h, 0, 0)
+    assert list(rec["flags"]) == [2, 0]
+    back, st = g.decode_images(tiles, 2, w, h)
+    assert (st == 0).all(), st
+    assert np.array_equal(back, rgb)

@@ -56,7 +56,7 @@ def main():
     d_st = g.alloc(n * 4)
     for distance in [int(x) for x in a.distances.split(",")]:
         def run():
-            g._ck(g.lib.hoh_find_lz_rgb_batch(g.ctx, d_rgb.ptr, n, w, h, distance, None, d_nuke.ptr, d_lz.ptr, stride,
+            g._ck(g.lib.hoh_find_lz_rgb_batch(g.ctx, d_rgb.ptr, n, w, h, distance, 0, None, d_nuke.ptr, d_lz.ptr, stride,
                                               d_size.ptr, d_st.ptr), "hoh_find_lz_rgb_batch")
         run()
         g.sync()

@@ -61,7 +61,7 @@ def main():
     d_tiles = g.alloc(n_tiles * mod.TILE_DT.itemsize)
     for mode in [int(x) for x in a.modes.split(",")]:
         def run():
-            g._ck(g.lib.hoh_encode_images(g.ctx, d_rgb.ptr, n, w, h, mode, d_packed.ptr, packed_cap, d_off.ptr,
+            g._ck(g.lib.hoh_encode_images(g.ctx, d_rgb.ptr, n, w, h, mode, 0, d_packed.ptr, packed_cap, d_off.ptr,
                                           d_tiles.ptr), "hoh_encode_images")
         run()
         g.sync()
