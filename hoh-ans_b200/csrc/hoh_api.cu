@@ -23,7 +23,7 @@ enum Slot {
     S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
     S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
     S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_D_TILES, S_D_PLANES, S_D_LZSYM, S_D_IDXSYM, S_D_RESID, S_D_OUT, S_D_BACKREF, S_D_MAPS,
-    S_D_STREAMS, S_D_RES_A, S_D_RES_B, S_D_TOP, S_D_BP, S_D_PSTATUS, S_COUNT
+    S_D_STREAMS, S_D_RES_A, S_D_RES_B, S_D_TOP, S_D_BP, S_D_PSTATUS, S_PA_BEST, S_COUNT
 };
 
 struct Buf {
@@ -52,6 +52,11 @@ struct hoh_ctx {
     uint64_t* h_off[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_off_cap[4] = {0, 0, 0, 0};
     hoh_ctx* child[4] = {nullptr, nullptr, nullptr, nullptr};  // one per chunk in flight (own stream + scratch)
+    // side streams for launches that are independent of each other and each bound by the serial chain of a
+    // stream (the table-size classes of one entropy batch): they overlap instead of queueing
+    bool aux_ready = false;
+    cudaStream_t aux[8] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
     // per-kernel profiling (hoh_profile_*)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;       // event 0 = begin, event i = after launch i
@@ -159,6 +164,31 @@ int ensure_smem_opt_in(hoh_ctx* ctx) {
     return HOH_OK;
 }
 
+int aux_init(hoh_ctx* ctx) {
+    if (ctx->aux_ready) return HOH_OK;
+    for (int k = 0; k < 8; k++) {
+        CK(cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    ctx->aux_ready = true;
+    return HOH_OK;
+}
+// everything queued on the context's stream so far happens before what is queued on aux[0..count) from now on
+int aux_fork(hoh_ctx* ctx, int count) {
+    TRY(aux_init(ctx));
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int k = 0; k < count; k++) CK(cudaStreamWaitEvent(ctx->aux[k], ctx->ev_fork, 0));
+    return HOH_OK;
+}
+int aux_join(hoh_ctx* ctx, int count) {
+    for (int k = 0; k < count; k++) {
+        CK(cudaEventRecord(ctx->ev_join[k], ctx->aux[k]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
+    }
+    return HOH_OK;
+}
+
 // Shared tail of the encode pipeline once the raw histograms are in `freqs`.
 // min_prob_bits: a lower bound the CALLER guarantees for every stream's prob_bits (0 = unknown).
 int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, const uint16_t* d_symbols,
@@ -174,18 +204,23 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
     k_build_tables<<<blocks_for(n, kTableWarps), kTableWarps * 32, 0, ctx->stream>>>(d_streams, (uint32_t)n, freqs,
                                                                                     cum, heads, meta);
     LAUNCHED("k_build_tables");
-    // one launch per (table width, window-size class); every warp takes part in exactly one of them
+    // one launch per (table width, window-size class); every warp takes part in exactly one of them.  The
+    // launches are independent and each lasts as long as its longest stream, so they go to side streams and
+    // overlap (not while profiling: the per-kernel event times would no longer add up).
     const uint32_t classes[5] = {0, 64, 128, 256, HOH_MAX_RANGE + 1};
+    const bool overlap = !ctx->profiling;
+    if (overlap) TRY(aux_fork(ctx, 8));
     for (int c = 0; c < 4; c++) {
         if (classes[c] >= max_range + 1) break;
         const uint32_t rows = classes[c + 1];
         const size_t stage = 2 * 32 * kSymStride * sizeof(uint16_t);
         const size_t smem16 = (size_t)rows * 32 * sizeof(uint16_t) + stage, smem32 = (size_t)rows * 32 * sizeof(uint32_t) + stage;
+        cudaStream_t s16 = overlap ? ctx->aux[2 * c] : ctx->stream, s32 = overlap ? ctx->aux[2 * c + 1] : ctx->stream;
         if (min_prob_bits >= 14) {
-            k_rans_encode<uint16_t, false><<<blocks_for(n, 32), 32, smem16, ctx->stream>>>(
+            k_rans_encode<uint16_t, false><<<blocks_for(n, 32), 32, smem16, s16>>>(
                 d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
         } else {
-            k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, ctx->stream>>>(
+            k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, s16>>>(
                 d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
         }
         static const char* const names16[4] = {"k_rans_encode<u16>[rows<=64]", "k_rans_encode<u16>[rows<=128]",
@@ -194,11 +229,12 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
                                                "k_rans_encode<u32>[rows<=256]", "k_rans_encode<u32>[rows<=513]"};
         LAUNCHED(names16[c]);
         if (max_prob_bits > 15) {  // 32-bit table lanes; prob_bits >= 16 there, so never LOW_BITS
-            k_rans_encode<uint32_t, false><<<blocks_for(n, 32), 32, smem32, ctx->stream>>>(
+            k_rans_encode<uint32_t, false><<<blocks_for(n, 32), 32, smem32, s32>>>(
                 d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);
             LAUNCHED(names32[c]);
         }
     }
+    if (overlap) TRY(aux_join(ctx, 8));
     k_finish_streams<<<blocks_for(n, 4), 128, 0, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, heads, meta, d_out,
                                                                 d_results);
     LAUNCHED("k_finish_streams");
@@ -219,21 +255,25 @@ int decode_common(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n, const
     LAUNCHED("k_unpack_stored");
     // one launch per table-size class; every warp takes part in exactly one of them
     const uint32_t classes[5] = {0, 64, 128, 256, HOH_MAX_RANGE + 3};
+    const bool overlap = !ctx->profiling;  // as in encode_from_freqs
+    if (overlap) TRY(aux_fork(ctx, 4));
     for (int c = 0; c < 4; c++) {
         const uint32_t rows = classes[c + 1];
         const size_t fixed = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kRingWords * sizeof(uint32_t) +
                              32 * kDecStride * sizeof(uint16_t);
+        cudaStream_t sc = overlap ? ctx->aux[c] : ctx->stream;
         if (rows <= 256) {
-            k_rans_decode<uint8_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 1, ctx->stream>>>(
+            k_rans_decode<uint8_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 1, sc>>>(
                 d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, classes[c], rows);
         } else {
-            k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 2, ctx->stream>>>(
+            k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 2, sc>>>(
                 d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, classes[c], rows);
         }
         static const char* const names[4] = {"k_rans_decode[rows<=64]", "k_rans_decode[rows<=128]",
                                              "k_rans_decode[rows<=256]", "k_rans_decode[rows<=515]"};
         LAUNCHED(names[c]);
     }
+    if (overlap) TRY(aux_join(ctx, 4));
     return HOH_OK;
 }
 
@@ -294,6 +334,21 @@ __global__ void k_normalize_only(uint32_t* __restrict__ freqs, uint32_t* __restr
 }  // namespace
 
 namespace {
+// channelpredict_all (prediction.hpp:153) for many planes, every pixel in parallel (encode side)
+int predict_all_parallel(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth, int x_tiles,
+                         int y_tiles, const uint16_t* d_tile_maps, uint16_t* d_resid, uint64_t resid_stride) {
+    uint8_t* best;
+    const uint64_t total = (uint64_t)n_planes * w * h;
+    TRY(scratch_t(ctx, S_PA_BEST, total, &best));
+    k_predict_all_best<<<blocks_for(total, 256), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, x_tiles, y_tiles,
+                                                                      d_tile_maps, best);
+    LAUNCHED("k_predict_all_best");
+    k_predict_all_resid<<<blocks_for(total, 256), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, best, d_resid,
+                                                                       resid_stride);
+    LAUNCHED("k_predict_all_resid");
+    return HOH_OK;
+}
+
 template <typename T>
 int stage_in(hoh_ctx* ctx, Slot slot, const T* host, size_t count, T** dev) {
     TRY(scratch_t(ctx, slot, count ? count : 1, dev));
@@ -360,6 +415,11 @@ void hoh_ctx_destroy(hoh_ctx* ctx) {
         if (ctx->h_off[k]) cudaFreeHost(ctx->h_off[k]);
     }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    for (int k = 0; k < 8; k++) {
+        if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
+        if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -680,7 +740,7 @@ int pipe_init(hoh_ctx* ctx) {
         CK(cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_off[k], cudaEventDisableTiming));
-        if (hoh_ctx_create(ctx->device, nullptr, &ctx->child[k]) != HOH_OK) return HOH_E_CUDA;
+        if (!ctx->child[k] && hoh_ctx_create(ctx->device, nullptr, &ctx->child[k]) != HOH_OK) return HOH_E_CUDA;
     }
     CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     ctx->pipe_ready = true;
@@ -926,14 +986,8 @@ int hoh_predict_all_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes,
         y_tiles <= 0)
         return HOH_E_ARG;
     if (!n_planes) return HOH_OK;
-    uint16_t* top;
-    uint8_t* bp;
-    TRY(scratch_t(ctx, S_TOP, n_planes * (size_t)w, &top));
-    TRY(scratch_t(ctx, S_BP, n_planes * (size_t)w, &bp));
-    k_raster_walk<false><<<blocks_for(n_planes, 64), 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, x_tiles,
-                                                                          y_tiles, d_tile_maps, nullptr, d_resid, top, bp, (uint64_t)w * h);
-    LAUNCHED("k_raster_walk<predict>");
-    return HOH_OK;
+    return predict_all_parallel(ctx, d_planes, n_planes, w, h, depth, x_tiles, y_tiles, d_tile_maps, d_resid,
+                                (uint64_t)w * h);
 }
 
 int hoh_unpredict_all_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_planes, int w, int h, int depth,
@@ -1016,16 +1070,21 @@ int predictor_search_impl(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plane
         k_cost_from_hist<<<blocks_for(n_planes * (uint64_t)c, 256), 256, 0, ctx->stream>>>(hist, n_planes * (uint64_t)c,
                                                                                           e_tab, e_len, cost);
         LAUNCHED("k_cost_from_hist");
-        k_section<true><<<blocks_for(jobs, 64), 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks,
-                                                                     n_masks, nullptr, 0, nullptr, cost, sums, nullptr,
-                                                                     nullptr);
-        LAUNCHED("k_section<cost>");
+        {  // all masks of a cell in one walk: one thread per (plane, cell)
+            const uint64_t cell_jobs = (uint64_t)n_planes * cells;
+            const unsigned blocks = blocks_for(cell_jobs, 64);
+            if (n_masks == 5)
+                k_section_costs<5><<<blocks, 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks, cost, sums);
+            else if (n_masks == 10)
+                k_section_costs<10><<<blocks, 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks, cost, sums);
+            else
+                k_section_costs<14><<<blocks, 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks, cost, sums);
+            LAUNCHED("k_section_costs");
+        }
         k_pick_masks<<<blocks_for(n_planes * (uint64_t)cells, 256), 256, 0, ctx->stream>>>(
             sums, n_planes * (uint64_t)cells, n_masks, masks, d_tile_maps, d_index_lists);
         LAUNCHED("k_pick_masks");
-        k_raster_walk<false><<<blocks_for(n_planes, 64), 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt,
-                                                                              d_tile_maps, nullptr, d_resid, top, bp, resid_stride);
-        LAUNCHED("k_raster_walk<predict>");
+        TRY(predict_all_parallel(ctx, d_planes, n_planes, w, h, depth, xt, yt, d_tile_maps, d_resid, resid_stride));
     }
     return HOH_OK;
 }
@@ -1053,7 +1112,7 @@ static LayerGeom layer_geom(int w, int h, int depth, int mode) {
     lg.mode = mode;
     lg.enc_flags = 0;
     // candidate slabs sized by what each is coded with: A 15 bits, B the index map at 8, C 16, D 15, E-G up to 19
-    const uint32_t bits_of[kLayerSlots] = {15, 8, 16, 15, 19, 19, 19};
+    const uint32_t bits_of[kLayerSlots] = {15, 8, 16, 15, 17, 18, 19, 14, 13, 12};
     uint32_t at = 0, widest = 0;
     for (int k = 0; k < kLayerSlots; k++) {
         const bool used = k == 0 || (mode >= 1 && (k != 1 || lg.cells));
@@ -1104,22 +1163,22 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     with_idx = best + n;
     if (d_nuke) kept_px = with_idx + n;
     TRY(scratch_t(ctx, S_L_STATUS, n, &status));
-    TRY(scratch_t(ctx, S_STREAMS, 3 * n, &streams));
-    TRY(scratch_t(ctx, S_L_RR, 3 * n, &rr));
+    TRY(scratch_t(ctx, S_STREAMS, 9 * n, &streams));
+    TRY(scratch_t(ctx, S_L_RR, 9 * n, &rr));
     TRY(scratch_t(ctx, S_L_RES, (size_t)kLayerSlots * n, &res));
     CK(cudaMemsetAsync(res, 0, (size_t)kLayerSlots * n * sizeof(hoh_stream_result), ctx->stream));
     uint16_t* resid0 = syms;
     uint16_t* resid1 = syms + n * lg.per_pad;
     const uint32_t range = 1u << depth;
     auto run_round = [&](int round, size_t count, uint32_t max_range, uint32_t max_pb) -> int {
-        k_layer_streams<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, n_used, kept_px, res, streams);
+        k_layer_streams<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, n_used, kept_px, streams);
         LAUNCHED("k_layer_streams");
         TRY(hoh_encode_entropy_batch(ctx, streams, count, syms, d_out, rr, max_range, max_pb, lg.per));
-        k_layer_scatter<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(n, round, rr, res);
+        k_layer_scatter<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, rr, res);
         LAUNCHED("k_layer_scatter");
         return HOH_OK;
     };
-    // layer_encode.hpp:63-120: fastpath residuals, prob_bits 15
+    // layer_encode.hpp:63-120: fastpath residuals
     k_predict_fastpath<<<grid_cap(n * (uint64_t)lg.per, 256), 256, 0, ctx->stream>>>(d_planes, n, w, h, depth, resid0,
                                                                                   lg.per_pad);
     LAUNCHED("k_predict_fastpath");
@@ -1131,21 +1190,15 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
         return HOH_OK;
     };
     TRY(compact(resid0));
-    TRY(run_round(0, n, range, 15));
-    if (mode >= 1) {
-        if (lg.cells) {  // :126-272
-            TRY(predictor_search_impl(ctx, d_planes, n, w, h, depth, mode, maps, idx, resid1, lg.per_pad));
-            TRY(compact(resid1));
-        }
-        k_layer_headers<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(lg, n, idx, syms, n_used, hdr, hdr_len);
-        LAUNCHED("k_layer_headers");
-        if (lg.cells) TRY(run_round(1, n, 14, 8));  // :308-317
-        TRY(run_round(2, 2 * n, range, 16));         // :334-353
-        TRY(run_round(3, 3 * n, range, 19));         // :355-392
-    } else {
-        k_layer_headers<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(lg, n, idx, syms, n_used, hdr, hdr_len);
-        LAUNCHED("k_layer_headers");
+    if (mode >= 1 && lg.cells) {  // :126-272
+        TRY(predictor_search_impl(ctx, d_planes, n, w, h, depth, mode, maps, idx, resid1, lg.per_pad));
+        TRY(compact(resid1));
     }
+    k_layer_headers<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(lg, n, idx, syms, n_used, hdr, hdr_len);
+    LAUNCHED("k_layer_headers");
+    // every candidate of every plane in one round (:106, 334-392), then the predictor-index maps (:308-317)
+    TRY(run_round(0, mode >= 1 ? 9 * n : n, range, mode >= 1 ? 19 : 15));
+    if (mode >= 1 && lg.cells) TRY(run_round(1, n, 14, 8));
     k_layer_decide<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(lg, n, res, (flags & HOH_FIX_STALE) ? 1u : 0u, hdr, hdr_len,
                                                                 kept, best, with_idx, status);
     LAUNCHED("k_layer_decide");
@@ -1322,10 +1375,30 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
                          info));
         k_tile_planes<<<(unsigned)nt, 256, 0, ctx->stream>>>(rgb, g, 0, per8, p8, p9);
         LAUNCHED("k_tile_planes");
-        TRY(hoh_layer_encode_batch(ctx, p8, nt * per8, tw, th, 8, mode, flags, nuke, g.plane_stride, per8, out8, nt * out8_tile, r8,
+        // the 8-bit planes and the 9-bit planes are two independent batches, each bound by stream length rather
+        // than stream count: they run side by side in two child contexts (own stream, own scratch)
+        hoh_ctx* c8 = ctx;
+        hoh_ctx* c9 = ctx;
+        if (!ctx->profiling) {
+            for (int k = 0; k < 2; k++)
+                if (!ctx->child[k] && hoh_ctx_create(ctx->device, nullptr, &ctx->child[k]) != HOH_OK) return HOH_E_CUDA;
+            c8 = ctx->child[0];
+            c9 = ctx->child[1];
+            TRY(aux_init(ctx));
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CK(cudaStreamWaitEvent(c8->stream, ctx->ev_fork, 0));
+            CK(cudaStreamWaitEvent(c9->stream, ctx->ev_fork, 0));
+        }
+        TRY(hoh_layer_encode_batch(c8, p8, nt * per8, tw, th, 8, mode, flags, nuke, g.plane_stride, per8, out8, nt * out8_tile, r8,
                                    nullptr, 0, nullptr));
-        TRY(hoh_layer_encode_batch(ctx, p9, nt * 2, tw, th, 9, mode, flags, nuke, g.plane_stride, 2, out9, nt * out9_tile, r9,
+        TRY(hoh_layer_encode_batch(c9, p9, nt * 2, tw, th, 9, mode, flags, nuke, g.plane_stride, 2, out9, nt * out9_tile, r9,
                                    nullptr, 0, nullptr));
+        if (c8 != ctx) {
+            CK(cudaEventRecord(ctx->ev_join[0], c8->stream));
+            CK(cudaEventRecord(ctx->ev_join[1], c9->stream));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
+        }
         k_tile_decide<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, first, per8, r8, r9, lz_size, lz_status, info, d_tiles);
         LAUNCHED("k_tile_decide");
         k_tile_scan<<<1, 1024, 0, ctx->stream>>>(d_tiles, first, (uint32_t)nt, d_tile_off);

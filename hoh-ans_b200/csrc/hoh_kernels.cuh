@@ -1686,6 +1686,71 @@ __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// channelpredict_all on the ENCODE side, every pixel in parallel.  The walk above is serial only through its
+// state arrays; when all pixel values are known (encoding) that state is a function of the pixels:
+//   bp[x] while (x, y) is predicted = the best predictor of the pixel ABOVE, (x, y-1)  [4 on the first row]
+//   bp_left                         = the best predictor of the pixel to the LEFT, (x-1, y); for x == 0 it is
+//                                     bp[w-1], which still holds row y-1's last pixel             [4 at (0, 0)]
+//   best predictor of pixel q       = 0 on the last row, else the argmin over the mask of the cell that holds
+//                                     the pixel BELOW q (prediction.hpp:213-225)
+// Pass 1 computes the best predictor of every pixel, pass 2 the residuals.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pa_candidates(const uint16_t* __restrict__ src, int w, int x, int y, int half, Cand& k) {
+    const uint16_t* row = src + (size_t)y * w;
+    const uint16_t* up = row - w;
+    const int L = x > 0 ? row[x - 1] : half;
+    const int T = y > 0 ? up[x] : half;
+    const int TL = (x > 0 && y > 0) ? up[x - 1] : half;
+    int TR;
+    if (x + 1 < w) TR = y > 0 ? up[x + 1] : half;
+    else TR = w > 1 ? row[0] : (y > 0 ? up[0] : half);  // last column: top[0] already holds this row's first pixel
+    candidates(L, T, TL, TR, false, k);
+}
+
+__global__ void __launch_bounds__(256) k_predict_all_best(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
+                                                          int h, int depth, int x_tiles, int y_tiles,
+                                                          const uint16_t* __restrict__ tile_maps,
+                                                          uint8_t* __restrict__ best) {
+    const uint64_t per = (uint64_t)w * h;
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= per * n_planes) return;
+    const uint64_t p = i / per;
+    const uint32_t at = (uint32_t)(i % per);
+    const int x = (int)(at % (uint32_t)w), y = (int)(at / (uint32_t)w);
+    if (y + 1 >= h) {
+        best[i] = 0;
+        return;
+    }
+    const int c = 1 << depth, half = c >> 1;
+    const int tw = (w + x_tiles - 1) / x_tiles, th = (h + y_tiles - 1) / y_tiles;
+    const uint16_t* src = planes + p * per;
+    Cand k;
+    pa_candidates(src, w, x, y, half, k);
+    const uint32_t mask = tile_maps[p * (uint64_t)x_tiles * y_tiles + (size_t)((y + 1) / th) * x_tiles + x / tw];
+    best[i] = (uint8_t)pick_best(src[at], k, mask, c);
+}
+
+__global__ void __launch_bounds__(256) k_predict_all_resid(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
+                                                           int h, int depth, const uint8_t* __restrict__ best,
+                                                           uint16_t* __restrict__ out, uint64_t out_stride) {
+    const uint64_t per = (uint64_t)w * h;
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= per * n_planes) return;
+    const uint64_t p = i / per;
+    const uint32_t at = (uint32_t)(i % per);
+    const int x = (int)(at % (uint32_t)w), y = (int)(at / (uint32_t)w);
+    const int c = 1 << depth, half = c >> 1;
+    const uint16_t* src = planes + p * per;
+    const uint8_t* b = best + p * per;
+    Cand k;
+    pa_candidates(src, w, x, y, half, k);
+    const int bp_top = y > 0 ? b[at - w] : 4;
+    const int bp_left = x > 0 ? b[at - 1] : (y > 0 ? b[at - 1] : 4);  // x == 0: (w-1, y-1) is the element before (0, y)
+    const int pred = p_mid(cand_at(k, bp_top), cand_at(k, bp_left));
+    out[p * out_stride + at] = (uint16_t)(((int)src[at] - pred + half + c) % c);  // prediction.hpp:208
+}
+
 // =================================================================================================
 // channelpredict_section — prediction.hpp:46-151.  One thread per (plane, cell, mask).
 // Writes the cell's residuals in cell-raster order.  COST mode instead accumulates
@@ -1759,6 +1824,92 @@ __global__ void __launch_bounds__(64) k_section(const uint16_t* __restrict__ pla
         }
     }
     if (COST) sums[job] = sum; else counts[job] = k;
+}
+
+// The search's cost sums (layer_encode.hpp:176-203, 233-272) for ALL masks of a cell in one walk.  k_section<true>
+// spends its time recomputing what does not depend on the mask: the 16 candidates of a pixel and its 16
+// prediction errors.  Here a thread owns one (plane, cell), computes those once per pixel, parks the
+// candidates in shared memory ([candidate][thread], one 32-bit word each: bank = lane) and then runs the
+// NM masks over them: the per-mask best predictors of a column live in one 64-bit word (4 bits per mask), the
+// argmin is a min over keys (error << 4 | index: lowest index wins ties, prediction.hpp:138-146), and each
+// mask's cost is accumulated in raster order in its own double exactly as the one-mask walk does.
+template <int NM>
+__global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
+                                                      int h, int depth, int x_tiles, int y_tiles,
+                                                      const uint16_t* __restrict__ masks,
+                                                      const double* __restrict__ cost, double* __restrict__ sums) {
+    __shared__ uint32_t s_cand[16][64];
+    const int cells = x_tiles * y_tiles;
+    const uint64_t job = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (job >= n_planes * (uint64_t)cells) return;
+    const int cell = (int)(job % cells);
+    const uint64_t p = job / (uint64_t)cells;
+    const int c = 1 << depth, half = c >> 1;
+    const int tw = (w + x_tiles - 1) / x_tiles, th = (h + y_tiles - 1) / y_tiles;
+    const int cx = cell % x_tiles, cy = cell / x_tiles;
+    const int x0 = cx * tw, y0 = cy * th;
+    const uint64_t per = (uint64_t)w * h;
+    const uint16_t* data = planes + p * per;
+    const double* ctab = cost + p * (uint64_t)c;
+    uint32_t mask[NM];
+#pragma unroll
+    for (int m = 0; m < NM; m++) mask[m] = masks[m];
+    uint16_t top[kMaxCellW];
+    uint64_t bpcol[kMaxCellW];
+    for (int i = 0; i < tw; i++) {  // prediction.hpp:76-94, as in k_section
+        bpcol[i] = 0x4444444444444444ull;
+        if (cy) {
+            const int64_t idx = (int64_t)y0 * w + x0 + i - w;
+            top[i] = (idx >= 0 && (uint64_t)idx < per) ? data[idx] : (uint16_t)0;
+        } else {
+            top[i] = (uint16_t)half;
+        }
+    }
+    double sum[NM];
+#pragma unroll
+    for (int m = 0; m < NM; m++) sum[m] = 0.0;
+    const uint32_t tid = threadIdx.x;
+    for (int ym = 0; ym < th && y0 + ym < h; ym++) {
+        int left, left_top;
+        if (cx) {  // prediction.hpp:97-105
+            left = data[(uint64_t)(y0 + ym) * w + x0 - 1];
+            left_top = (ym || cy) ? data[(uint64_t)(y0 + ym - 1) * w + x0 - 1] : half;
+        } else {
+            left = left_top = half;
+        }
+        for (int xm = 0; xm < tw && x0 + xm < w; xm++) {
+            const int v = data[(uint64_t)(y0 + ym) * w + x0 + xm];
+            Cand kk;
+            candidates(left, top[xm], left_top, top[(xm + 1) % tw], true, kk);  // :115 TR wraps inside the cell
+            int key[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                s_cand[j][tid] = (uint32_t)kk.v[j];
+                const int err = abs(v - kk.v[j]);
+                key[j] = err < 2 * c ? (err << 4) | j : 0x7fffffff;
+            }
+            const uint64_t above = bpcol[xm];
+            const uint64_t before = bpcol[(xm + tw - 1) % tw];  // :134 (this row's left pixel once xm > 0)
+            uint64_t now = 0;
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const uint32_t bt = (uint32_t)(above >> (4 * m)) & 15u, bl = (uint32_t)(before >> (4 * m)) & 15u;
+                const int pred = p_mid((int)s_cand[bt][tid], (int)s_cand[bl][tid]);
+                const int r = (v - pred + half + c) % c;
+                sum[m] += ctab[r];
+                int best = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < 16; j++) best = min(best, ((mask[m] >> j) & 1u) ? key[j] : 0x7fffffff);
+                now |= (uint64_t)(best == 0x7fffffff ? 0 : (best & 15)) << (4 * m);
+            }
+            bpcol[xm] = now;
+            left_top = top[xm];
+            top[xm] = (uint16_t)v;
+            left = v;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NM; m++) sums[job * NM + m] = sum[m];
 }
 
 // layer_encode.hpp:133-144 / :217-225: +1-smoothed histogram of a residual plane.  One CTA per plane.
@@ -2227,7 +2378,8 @@ __global__ void __launch_bounds__(kUnpWarps * 32, 3) k_tile_unpredict_s0(const u
 // round of entropy coding, the predictor-map header, the "which buffer wins" logic (including the
 // stale-buffer behaviour D7) and the final assembly of every channel payload.
 // =================================================================================================
-constexpr int kLayerSlots = 7;   // per plane: A (fastpath, 15 bits), B (predictor-index map), C (16), D (15), E, F, G
+constexpr int kLayerSlots = 10;  // per plane: A (fastpath, 15 bits), B (predictor-index map), C (16), D (15),
+                                 // E, F, G going up (17, 18, 19 bits) and going down (14, 13, 12 bits)
 constexpr int kLayerHdrCap = 48;  // 0x10 + x_tiles-1 + y_tiles-1 + count + 14 masks * 2
 
 struct LayerGeom {
@@ -2237,58 +2389,52 @@ struct LayerGeom {
     uint32_t cells_pad;
     uint32_t xt, yt;
     uint32_t depth, mode;
-    uint32_t slot_off[7]; // byte offset of each candidate's slab inside a plane's block (kLayerSlots entries)
-    uint32_t slot_cap[7]; // ... and its capacity (sized for the candidate's prob_bits; 0 = not used at this mode)
+    uint32_t slot_off[kLayerSlots]; // byte offset of each candidate's slab inside a plane's block
+    uint32_t slot_cap[kLayerSlots]; // ... and its capacity (sized for the candidate's prob_bits; 0 = not used at this mode)
     uint32_t plane_bytes; // candidate bytes per plane
     uint32_t enc_flags;   // HOH_FIX_LONE or 0, handed to every entropy stream
     uint32_t out_cap;     // bytes of one assembled channel payload
 };
 
-// Round descriptors.  round 0: A = fastpath residuals at 15 bits.  round 1: B = predictor-index map at 8
-// bits (range = number of masks used).  round 2: C, D = final residuals at 16 and 15 bits.  round 3: E, F, G
-// = 17, 18, 19 bits if C beat D (layer_encode.hpp:359-374) else 14, 13, 12 (:376-392).
+// Stream descriptors.  The reference codes its candidates one after the other and only tries 17-19 bits if 16
+// beat 15, else 14-12 (layer_encode.hpp:357-392).  A kernel launch here lasts as long as its longest stream
+// whatever the number of streams, so BOTH directions are coded speculatively together with A, C and D in ONE
+// round (round 0: 9 streams per plane at mode >= 1, just A at mode 0) and k_layer_decide looks only at the
+// direction the reference would have taken.  Round 1: B = the predictor-index map at 8 bits (range = number of
+// masks used), one stream per plane.
+__device__ __forceinline__ uint32_t layer_slot_bits(uint32_t slot) {
+    return slot == 0u ? 15u : slot == 2u ? 16u : slot == 3u ? 15u : slot <= 6u ? 13u + slot : 21u - slot;
+}
+
 __global__ void k_layer_streams(LayerGeom lg, uint64_t n_planes, int round, const uint32_t* __restrict__ n_used,
-                                const uint32_t* __restrict__ kept_px,
-                                const hoh_stream_result* __restrict__ results, hoh_enc_stream* __restrict__ streams) {
+                                const uint32_t* __restrict__ kept_px, hoh_enc_stream* __restrict__ streams) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const uint32_t per_round = round == 0 ? 1u : (round == 1 ? 1u : (round == 2 ? 2u : 3u));
+    const uint32_t per_round = (round == 0 && lg.mode) ? 9u : 1u;
     if (i >= n_planes * per_round) return;
     const uint64_t p = i / per_round;
     const uint32_t k = (uint32_t)(i % per_round);
     const uint64_t resid0 = p * lg.per_pad, resid1 = (n_planes + p) * (uint64_t)lg.per_pad;
-    const uint64_t idx_sym = 2u * n_planes * (uint64_t)lg.per_pad + p * lg.cells_pad;
-    const bool searched = lg.cells != 0u;
     hoh_enc_stream st;
     st.prefix_len = 0;
     for (int b = 0; b < 8; b++) st.prefix[b] = 0;
     st.reserved = lg.enc_flags;
-    st.range = 1u << lg.depth;
-    st.n = kept_px ? kept_px[p] : lg.per;  // residuals left after NUKE compaction (layer_encode.hpp:93-99, 328-333)
     uint32_t slot;
     if (round == 0) {
-        slot = 0;
-        st.sym_off = resid0;
-        st.prob_bits = 15;
-    } else if (round == 1) {
+        slot = k == 0u ? 0u : k + 1u;  // A, then C, D, E..G up, E..G down
+        st.range = 1u << lg.depth;
+        st.n = kept_px ? kept_px[p] : lg.per;  // residuals left after NUKE compaction (layer_encode.hpp:93-99, 328-333)
+        st.sym_off = (slot != 0u && lg.cells != 0u) ? resid1 : resid0;
+        st.prob_bits = layer_slot_bits(slot);
+    } else {
         slot = 1;
-        st.sym_off = idx_sym;
+        st.sym_off = 2u * n_planes * (uint64_t)lg.per_pad + p * lg.cells_pad;
         st.n = lg.cells;
         st.range = n_used[p];
         st.prob_bits = 8;
-    } else if (round == 2) {
-        slot = 2 + k;
-        st.sym_off = searched ? resid1 : resid0;
-        st.prob_bits = k == 0 ? 16u : 15u;
-    } else {
-        slot = 4 + k;
-        st.sym_off = searched ? resid1 : resid0;
-        const hoh_stream_result c = results[p * kLayerSlots + 2], d = results[p * kLayerSlots + 3];
-        const bool up = c.size < d.size;  // layer_encode.hpp:357
-        st.prob_bits = up ? 17u + k : 14u - k;
     }
     st.out_off = p * (uint64_t)lg.plane_bytes + lg.slot_off[slot];
     st.out_cap = lg.slot_cap[slot];
-    streams[round == 2 ? p * 2 + k : (round == 3 ? p * 3 + k : p)] = st;
+    streams[i] = st;
 }
 
 // After the predictor search: channel header bytes + the predictor-index symbols (layer_encode.hpp:276-306).
@@ -2350,16 +2496,23 @@ __global__ void k_layer_decide(LayerGeom lg, uint64_t n_planes, const hoh_stream
     uint32_t kept = 0xffffffffu;  // nothing kept: the reference would emit an uninitialised buffer
     uint32_t idx = lg.cells ? 1u : 0u;
     int32_t st = r[0].status;
+    const bool up = lg.mode && r[2].size < r[3].size;  // layer_encode.hpp:357: 16 bits beat 15 -> try 17, 18, 19
+    const uint32_t third = up ? 4u : 7u;               // first slot of the direction the reference takes
     if (lg.mode) {
         if (lg.cells) st = st ? st : r[1].status;
-        for (int k = 2; k < kLayerSlots; k++) st = st ? st : r[k].status;
+        st = st ? st : (r[2].status ? r[2].status : r[3].status);
+        for (uint32_t k = 0; k < 3u; k++) st = st ? st : r[third + k].status;
     }
     if (fix) {
         best = r[0].size;
         kept = 0;
         if (lg.mode) {
             uint32_t sb = r[2].size, sk = 2;
-            for (uint32_t k = 3; k < (uint32_t)kLayerSlots; k++)
+            if (r[3].size < sb) {
+                sb = r[3].size;
+                sk = 3;
+            }
+            for (uint32_t k = third; k < third + 3u; k++)
                 if (r[k].size < sb) {
                     sb = r[k].size;
                     sk = k;
@@ -2385,13 +2538,12 @@ __global__ void k_layer_decide(LayerGeom lg, uint64_t n_planes, const hoh_stream
             kept = 0;
         }
         if (lg.mode) {
-            const bool up = r[2].size < r[3].size;
             const uint32_t first = up ? r[2].size : r[3].size;
             if (first < best) best = first;  // size updated, buffers NOT swapped (D7): kept stays
-            for (int k = 0; k < 3; k++)
-                if (r[4 + k].size < best) {
-                    best = r[4 + k].size;
-                    kept = 4 + k;
+            for (uint32_t k = 0; k < 3u; k++)
+                if (r[third + k].size < best) {
+                    best = r[third + k].size;
+                    kept = third + k;
                 }
         }
     }
@@ -2438,14 +2590,14 @@ __global__ void __launch_bounds__(256) k_layer_assemble(LayerGeom lg, const uint
 }
 
 // round-local result order -> results[plane * kLayerSlots + slot]
-__global__ void k_layer_scatter(uint64_t n_planes, int round, const hoh_stream_result* __restrict__ rr,
+__global__ void k_layer_scatter(LayerGeom lg, uint64_t n_planes, int round, const hoh_stream_result* __restrict__ rr,
                                 hoh_stream_result* __restrict__ results) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const uint32_t per_round = round == 2 ? 2u : (round == 3 ? 3u : 1u);
+    const uint32_t per_round = (round == 0 && lg.mode) ? 9u : 1u;
     if (i >= n_planes * per_round) return;
     const uint64_t p = i / per_round;
     const uint32_t k = (uint32_t)(i % per_round);
-    const uint32_t slot = round == 0 ? 0u : (round == 1 ? 1u : (round == 2 ? 2u + k : 4u + k));
+    const uint32_t slot = round == 1 ? 1u : (k == 0u ? 0u : k + 1u);
     results[p * kLayerSlots + slot] = rr[i];
 }
 
