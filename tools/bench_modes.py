@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--modes", default="0,2")
     ap.add_argument("--cpu-tiles", type=int, default=16)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--flags", type=int, default=24, help="encoder flags: 24 = HOH_FIX_ENCODER (decodable), 0 = stock bytes")
     a = ap.parse_args()
     mod = bench._load("hohgpu", os.path.join(ROOT, "hoh-ans_b200", "host", "hohgpu.py"))
     g = mod.HohGpu(0)
@@ -61,7 +62,7 @@ def main():
     d_tiles = g.alloc(n_tiles * mod.TILE_DT.itemsize)
     for mode in [int(x) for x in a.modes.split(",")]:
         def run():
-            g._ck(g.lib.hoh_encode_images(g.ctx, d_rgb.ptr, n, w, h, mode, 0, d_packed.ptr, packed_cap, d_off.ptr,
+            g._ck(g.lib.hoh_encode_images(g.ctx, d_rgb.ptr, n, w, h, mode, a.flags, d_packed.ptr, packed_cap, d_off.ptr,
                                           d_tiles.ptr), "hoh_encode_images")
         run()
         g.sync()
@@ -76,6 +77,27 @@ def main():
         rec = d_tiles.download(mod.TILE_DT, n_tiles)
         total = int(d_off.download(np.uint64, n_tiles + 1)[-1])
         assert (rec["status"] == 0).all()
+        # decode what was just written (hoh_decode_images) and check the round trip when the output is decodable
+        d_back = g.alloc(raw)
+        d_st = g.alloc(n_tiles * 4)
+
+        def run_dec():
+            g._ck(g.lib.hoh_decode_images(g.ctx, d_packed.ptr, packed_cap, d_off.ptr, n, w, h, d_back.ptr, d_st.ptr),
+                  "hoh_decode_images")
+        run_dec()
+        g.sync()
+        g.timer_start(1)
+        for _ in range(a.steps):
+            run_dec()
+        g.timer_stop(1)
+        dec_ms = g.timer_ms(1) / a.steps
+        g.profile_begin()
+        run_dec()
+        dprof = g.profile_end()
+        dec_ok = bool((d_st.download(np.int32, n_tiles) == 0).all())
+        same = bool(np.array_equal(d_back.download(np.uint8, raw), rgb)) if dec_ok else False
+        d_back.free()
+        d_st.free()
         with ProcessPoolExecutor(os.cpu_count()) as ex:
             list(ex.map(_cpu, [(1, 32, 32, 0)] * (os.cpu_count() or 1)))  # start the workers, load the libraries
             t0 = time.perf_counter()
@@ -89,6 +111,9 @@ def main():
             "colour_modes": {int(k): int(v) for k, v in zip(*np.unique(rec["colour_mode"], return_counts=True))},
             "kernels_ms": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:10]},
             "launches": int(sum(v[1] for v in prof.values())),
+            "decode_ms": dec_ms, "decode_raw_mbs": raw / (dec_ms / 1e3) / 1e6, "decode_status_ok": dec_ok,
+            "roundtrip_exact": same, "encoder_flags": a.flags,
+            "decode_kernels_ms": {k: round(v[0], 3) for k, v in sorted(dprof.items(), key=lambda kv: -kv[1][0])[:6]},
             "cpu_ref_ms_per_tile_one_core": 1e3 * float(np.mean(per)),
             "cpu_raw_mbs_all_cores": a.cpu_tiles * tile_raw / wall / 1e6, "cpu_cores": os.cpu_count()}))
 
