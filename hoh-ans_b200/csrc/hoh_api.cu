@@ -1173,7 +1173,15 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     auto run_round = [&](int round, size_t count, uint32_t max_range, uint32_t max_pb) -> int {
         k_layer_streams<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, n_used, kept_px, streams);
         LAUNCHED("k_layer_streams");
-        TRY(hoh_encode_entropy_batch(ctx, streams, count, syms, d_out, rr, max_range, max_pb, lg.per));
+        if (round == 0) {  // two histograms per plane instead of one per stream
+            uint32_t* freqs;
+            TRY(scratch_t(ctx, S_FREQS, count * kFreqRow, &freqs));
+            k_layer_histograms<<<(unsigned)(2 * n), 256, 0, ctx->stream>>>(lg, n, streams, syms, freqs);
+            LAUNCHED("k_layer_histograms");
+            TRY(encode_from_freqs(ctx, streams, count, syms, d_out, rr, freqs, max_range, max_pb, 0));
+        } else {
+            TRY(hoh_encode_entropy_batch(ctx, streams, count, syms, d_out, rr, max_range, max_pb, lg.per));
+        }
         k_layer_scatter<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, rr, res);
         LAUNCHED("k_layer_scatter");
         return HOH_OK;

@@ -144,6 +144,56 @@ __device__ int warp_normalize(uint32_t* f, uint32_t* sc, uint32_t* cum, uint32_t
     // stattools.hpp:28-57: every used symbol that rounded to zero takes one count from the
     // lowest-index symbol of smallest frequency > 1, in ascending thief order.
     int status = HOH_S_OK;
+    uint32_t thieves = 0, capacity = 0;
+    for (uint32_t i = lane; i < range; i += 32) {
+        thieves += (f[i] != 0 && sc[i] == 0) ? 1u : 0u;
+        capacity += sc[i] > 1u ? sc[i] - 1u : 0u;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        thieves += __shfl_xor_sync(0xffffffffu, thieves, d);
+        capacity += __shfl_xor_sync(0xffffffffu, capacity, d);
+    }
+    if (thieves > 16u) {
+        // Many thieves (small prob_bits against a wide alphabet).  The order of the donors never changes: a steal
+        // makes the current donor even smaller, so it stays the minimum until it is down to 1, and nobody else
+        // moves.  Donors are therefore drained in ascending (frequency, index) order, each giving frequency - 1
+        // counts, the last one partially — found by a binary search on that key instead of one search per thief.
+        if (capacity < thieves) return HOH_S_NO_DONOR;  // stattools.hpp:42 fires at the first thief left without donor
+        uint32_t lo = 0, hi = 1u << 30;  // largest key K with cap(K) = sum over donors with key < K of (freq - 1) <= thieves
+        while (hi - lo > 1u) {
+            const uint32_t mid = lo + (hi - lo) / 2u;
+            uint32_t cap = 0;
+            for (uint32_t j = lane; j < range; j += 32) {
+                const uint32_t v = sc[j];
+                cap += (v > 1u && ((v << 10) | j) < mid) ? v - 1u : 0u;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) cap += __shfl_xor_sync(0xffffffffu, cap, d);
+            if (cap <= thieves) lo = mid;
+            else hi = mid;
+        }
+        uint32_t cap = 0;
+        for (uint32_t j = lane; j < range; j += 32) {
+            const uint32_t v = sc[j];
+            cap += (v > 1u && ((v << 10) | j) < lo) ? v - 1u : 0u;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cap += __shfl_xor_sync(0xffffffffu, cap, d);
+        const uint32_t rest = thieves - cap;  // taken from the donor whose key is exactly lo
+        __syncwarp();
+        for (uint32_t j = lane; j < range; j += 32) {
+            const uint32_t v = sc[j];
+            if (v > 1u) {
+                const uint32_t key = (v << 10) | j;
+                if (key < lo) sc[j] = 1;
+                else if (key == lo) sc[j] = v - rest;
+            } else if (f[j] != 0 && v == 0) {
+                sc[j] = 1;
+            }
+        }
+        __syncwarp();
+    } else
     for (uint32_t base = 0; base < range; base += 32) {
         uint32_t i = base + lane;
         bool thief = i < range && f[i] != 0 && sc[i] == 0;
@@ -2476,6 +2526,40 @@ __global__ void k_layer_headers(LayerGeom lg, uint64_t n_planes, const uint8_t* 
     for (uint32_t c = 0; c < lg.cells; c++) sym[c] = remap[idx[c]];
     n_used[p] = count;
     hdr_len[p] = at;
+}
+
+// Histograms for round 0 of hoh_layer_encode_batch.  The nine candidates of a plane code the same residuals
+// (A the fastpath ones, the other eight the searched ones) and differ only in prob_bits, so a plane needs two
+// histograms, not nine: CTA (plane, which) counts once — one sub-histogram per warp, the residuals of a
+// smooth image pile up on a few values and would serialise on one shared copy — and writes the result to the
+// frequency row of every stream that uses it.
+__global__ void __launch_bounds__(256) k_layer_histograms(LayerGeom lg, uint64_t n_planes,
+                                                          const hoh_enc_stream* __restrict__ streams,
+                                                          const uint16_t* __restrict__ symbols,
+                                                          uint32_t* __restrict__ freqs) {
+    __shared__ uint32_t s_h[8][kFreqRow];
+    const uint64_t p = blockIdx.x >> 1;
+    const uint32_t which = blockIdx.x & 1u;  // 0: stream A, 1: streams C .. G
+    const uint32_t per_plane = lg.mode ? 9u : 1u;
+    if (which == 1u && per_plane == 1u) return;
+    const uint64_t first = p * per_plane + which;
+    const hoh_enc_stream st = streams[first];
+    for (uint32_t i = threadIdx.x; i < 8u * kFreqRow; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const uint16_t* src = symbols + st.sym_off;
+    uint32_t* mine = s_h[threadIdx.x >> 5];
+    for (uint32_t i = threadIdx.x; i < st.n; i += blockDim.x) {
+        const uint32_t v = src[i];
+        if (v < st.range) atomicAdd(&mine[v], 1u);
+    }
+    __syncthreads();
+    const uint32_t copies = which ? 8u : 1u;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kFreqRow; i += blockDim.x) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += s_h[w][i];
+        for (uint32_t k = 0; k < copies; k++) freqs[(first + k) * kFreqRow + i] = t;
+    }
 }
 
 // layer_encode.hpp:108-120, 326-398: which candidate's bytes are emitted and how many of them.

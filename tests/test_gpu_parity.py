@@ -190,6 +190,35 @@ def test_normalize_freqs_vs_oracle():
             assert np.array_equal(gf, of) and np.array_equal(gc, oc), (it, size, pb)
 
 
+def test_normalize_freqs_many_thieves():
+    """Small prob_bits against a wide, almost fully used alphabet: dozens to hundreds of symbols round to zero
+    and steal (the binary-search form of the steal loop).  (Running out of donors cannot happen once
+    target >= size: the scaled counts sum to the target, so the spare counts always cover the thieves.)"""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(44)
+    seen_many = 0
+    for it in range(150):
+        size = int(rng.choice([256, 512]))
+        pb = int(rng.integers(8, 15))
+        if (1 << pb) < size:
+            pb = 9 if size == 512 else 8
+        k = int(rng.integers(size // 2, size + 1))
+        f = np.zeros(size, np.uint32)
+        idx = rng.choice(size, k, replace=False)
+        shape = [rng.geometric(0.02, k), (rng.pareto(1.2, k) * 5 + 1), rng.integers(1, 4, k),
+                 np.where(rng.random(k) < 0.1, 5000, 1)][it % 4]
+        f[idx] = np.maximum(1, np.asarray(shape)).astype(np.uint32)
+        of, oc = f.copy(), np.zeros(size + 1, np.uint32)
+        ost = ol.oracle().orc_normalize_freqs(of, oc, size, 1 << pb)
+        gf, gc, gst = g.normalize_freqs(f, 1 << pb)
+        assert gst == ost, (it, size, pb, gst, ost)
+        if ost == 0:
+            assert np.array_equal(gf, of) and np.array_equal(gc, oc), (it, size, pb)
+            scaled = np.diff((np.concatenate([[0], np.cumsum(f, dtype=np.uint64)]) * (1 << pb)) // int(f.sum()))
+            seen_many += int(np.count_nonzero((f > 0) & (scaled == 0)) > 16)
+    assert seen_many > 20
+
+
 def test_rans_static_table_sweep_sample():
     """Config 4 shape: 8-bit alphabet, one static prob_bits-12 table, 65 536-symbol streams."""
     mod = gpu_lib.hohgpu()
