@@ -160,6 +160,8 @@ int ensure_smem_opt_in(hoh_ctx* ctx) {
     CK(cudaFuncSetAttribute(k_tile_unpredict_s0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_tile_unpredict_s0<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_unpredict_fastpath_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_decode_static_direct<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_decode_static_direct<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     ctx->smem_opt_in = true;
     return HOH_OK;
 }
@@ -609,6 +611,21 @@ int hoh_rans_decode_static(hoh_ctx* ctx, const uint8_t* d_in, uint32_t slab_byte
     if (stream_len == 0 || stream_len % 8 || slab_bytes % 16) return HOH_E_ARG;
     if (n == 0) return HOH_OK;
     const uint64_t streams = (n + stream_len - 1) / stream_len;
+    if (prob_bits <= 15) {  // the slot -> symbol table fits shared memory: direct lookups
+        const size_t sym_bytes = range <= 256 ? 1 : 2;
+        const size_t smem = (size_t)kStaticDirectWarps * 32 * kRingWords * 4 + (size_t)kStaticDirectWarps * 32 * kDecStride * 2 +
+                            (size_t)HOH_MAX_RANGE * 4 + ((size_t)sym_bytes << prob_bits);
+        TRY(ensure_smem_opt_in(ctx));
+        const unsigned blocks = blocks_for(streams, kStaticDirectWarps * 32);
+        if (range <= 256)
+            k_rans_decode_static_direct<uint8_t><<<blocks, kStaticDirectWarps * 32, smem, ctx->stream>>>(
+                d_in, slab_bytes, d_payload_bytes, n, stream_len, d_cum, range, prob_bits, d_symbols);
+        else
+            k_rans_decode_static_direct<uint16_t><<<blocks, kStaticDirectWarps * 32, smem, ctx->stream>>>(
+                d_in, slab_bytes, d_payload_bytes, n, stream_len, d_cum, range, prob_bits, d_symbols);
+        LAUNCHED("k_rans_decode_static_direct");
+        return HOH_OK;
+    }
     k_rans_decode_static<<<blocks_for(streams, kStaticDecWarps * 32), kStaticDecWarps * 32, 0, ctx->stream>>>(
         d_in, slab_bytes, d_payload_bytes, n, stream_len, d_cum, range, prob_bits, d_symbols);
     LAUNCHED("k_rans_decode_static");

@@ -1412,6 +1412,87 @@ __global__ void __launch_bounds__(kStaticDecWarps * 32) k_rans_decode_static(
     }
 }
 
+// Static decode with the reference's own lookup structure.  With ONE table for all streams the 2^prob_bits-entry
+// slot -> symbol table of entropy_decoding.hpp:262-267 fits shared memory (prob_bits <= 15: at most 32 KB of
+// bytes for an 8-bit alphabet) when a whole CTA of 8 warps shares it, and a symbol costs two dependent
+// shared-memory reads (symbol, then its packed start | freq << 16) with no search at all — the midpoint table
+// of the per-stream decoder degenerates here, because at 12 bits many symbols share a bucket.
+constexpr int kStaticDirectWarps = 8;
+
+template <typename SymT>
+__global__ void __launch_bounds__(kStaticDirectWarps * 32) k_rans_decode_static_direct(
+    const uint8_t* __restrict__ in, uint32_t slab_bytes, const uint32_t* __restrict__ payload_bytes,
+    uint64_t n_total, uint32_t stream_len, const uint32_t* __restrict__ cum_g, uint32_t range,
+    uint32_t bits, uint16_t* __restrict__ symbols) {
+    extern __shared__ __align__(16) uint8_t sd_smem[];
+    uint32_t* s_rings = reinterpret_cast<uint32_t*>(sd_smem);                              // [warp][32 * kRingWords]
+    uint16_t* s_stage = reinterpret_cast<uint16_t*>(s_rings + kStaticDirectWarps * 32 * kRingWords);  // [warp][32 * kDecStride]
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(s_stage + kStaticDirectWarps * 32 * kDecStride);   // [range]
+    SymT* s_c2s = reinterpret_cast<SymT*>(s_info + HOH_MAX_RANGE);                           // [1 << bits]
+    __shared__ uint64_t s_off[kStaticDirectWarps][32];
+    __shared__ uint32_t s_n[kStaticDirectWarps][32];
+    const uint32_t total = 1u << bits;
+    for (uint32_t i = threadIdx.x; i < range; i += blockDim.x) s_info[i] = cum_g[i] | ((cum_g[i + 1] - cum_g[i]) << 16);
+    for (uint32_t slot = threadIdx.x; slot < total; slot += blockDim.x) {  // largest symbol with cum <= slot
+        uint32_t lo = 0, hi = range;  // cum_g[lo] <= slot < cum_g[hi] (cum_g[range] = total for a valid table)
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (cum_g[mid] <= slot) lo = mid;
+            else hi = mid;
+        }
+        s_c2s[slot] = (SymT)lo;
+    }
+    const uint32_t w = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t n_streams = (n_total + stream_len - 1) / stream_len;
+    const uint64_t s = ((uint64_t)blockIdx.x * kStaticDirectWarps + w) * 32u + lane;
+    const bool exists = s < n_streams;
+    const uint64_t first = s * stream_len;
+    const uint32_t pb = exists ? payload_bytes[s] : 0u;
+    const bool live = exists && pb >= 8u && pb <= slab_bytes;
+    const uint32_t my_n = live ? (uint32_t)min((uint64_t)stream_len, n_total - first) : 0u;
+    s_off[w][lane] = live ? first : 0ull;
+    s_n[w][lane] = my_n;
+    __syncthreads();
+    if (__ballot_sync(0xffffffffu, live) == 0u) return;
+    const uint32_t mask = total - 1u;
+    uint32_t n_max = my_n;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
+    WordRing rd;
+    const uint64_t total_bytes = n_streams * (uint64_t)slab_bytes;
+    rd.open(in, total_bytes, live ? (s + 1) * (uint64_t)slab_bytes - pb : 0ull, s_rings + (w * 32u + lane) * kRingWords);
+    uint64_t x;
+    {
+        const uint32_t lo = rd.next;
+        rd.take_if(true);
+        const uint32_t hi = rd.next;
+        rd.take_if(true);
+        x = live ? ((uint64_t)lo | ((uint64_t)hi << 32)) : kRansL;
+    }
+    uint16_t* stage = s_stage + w * 32u * kDecStride;
+    uint16_t* my_row = stage + lane * kDecStride;
+    const uint32_t chunks = (n_max + kDecChunk - 1) / kDecChunk;
+    for (uint32_t chunk = 0; chunk < chunks; chunk++) {
+        __syncwarp();
+        for (uint32_t k0 = 0; k0 < (uint32_t)kDecChunk; k0 += kTopUp) {
+            rd.top_up();
+#pragma unroll
+            for (uint32_t k = k0; k < k0 + kTopUp; k++) {
+                const uint32_t slot = (uint32_t)x & mask;  // rans64.hpp:118-121
+                const uint32_t sym = s_c2s[slot];
+                const uint32_t info = s_info[sym];
+                x = (uint64_t)(info >> 16) * (x >> bits) + (slot - (info & 0xffffu));  // rans64.hpp:126-134
+                const bool refill = x < kRansL;                                            // :137-141
+                x = refill ? ((x << 32) | rd.next) : x;
+                rd.take_if(refill);
+                my_row[k] = (uint16_t)sym;
+            }
+        }
+        __syncwarp();
+        stage_store_chunk(stage, symbols, s_off[w], s_n[w], chunk);
+    }
+}
+
 // =================================================================================================
 // Offsets and gather — "stream-offset prefix sums with warp shuffles" + the final gather.
 // =================================================================================================
