@@ -1100,10 +1100,18 @@ struct PerLaneDense {
     const uint32_t* tab;
     uint32_t lane;
     __device__ __forceinline__ uint32_t at(uint32_t p) const { return tab[p * 32u + lane]; }
+    // A load the compiler may not predicate on the outcome of the other rows' comparisons: the four rows of a
+    // lookup must leave together (one shared-memory round trip on the dependent chain, not two).
+    __device__ __forceinline__ uint32_t at_eager(uint32_t p) const {
+        uint32_t v;
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(tab + p * 32u + lane)));
+        return v;
+    }
 };
 struct SharedDense {
     const uint32_t* tab;
     __device__ __forceinline__ uint32_t at(uint32_t p) const { return tab[p]; }
+    __device__ __forceinline__ uint32_t at_eager(uint32_t p) const { return tab[p]; }
 };
 
 template <typename Table, typename LutT>
@@ -1125,11 +1133,15 @@ __device__ __forceinline__ uint32_t rans_lookup(const Table& T, const LutT* lut,
                                                 uint32_t lut_shift, uint32_t slot, uint32_t& c0, uint32_t& c1) {
     uint32_t p = lut[(slot >> lut_shift) * lut_stride];
     const uint32_t key = (slot + 1u) << kSymBits;
-    const uint32_t em = T.at(p - 1u), e0 = T.at(p), e1 = T.at(p + 1u), e2 = T.at(p + 2u);
+    const uint32_t em = T.at(p - 1u), e0 = T.at(p), e1 = T.at(p + 1u), e2 = T.at_eager(p + 2u);
     const bool down = e0 >= key;  // the row holding the bucket's middle starts after the slot
     const bool up = e1 < key;     // ... or ends before it
     uint32_t e = down ? em : (up ? e1 : e0);
-    uint32_t hi = down ? e0 : (up ? e2 : e1);
+    // e2 enters arithmetically: written as a select the compiler predicates its load on `up`, which puts a
+    // second shared-memory round trip on the chain whenever any lane of the warp needs the upper neighbour
+    uint32_t up_ones;  // all ones when e1 < key; produced where the compiler cannot turn it back into a select
+    asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(up_ones) : "r"(e1), "r"(key));
+    uint32_t hi = down ? e0 : e1 + ((e2 - e1) & up_ones);
     // more than one row away (several symbols inside 1/128th of the range): rare; the vote makes the
     // branch uniform so that the common path carries no divergence bookkeeping
     if (__any_sync(0xffffffffu, e >= key || hi < key)) {
