@@ -1126,56 +1126,66 @@ __device__ __forceinline__ void lut_build(const Table& T, LutT* lut, uint32_t lu
     }
 }
 
-// Returns the symbol; c0 / c1 = cumulative count of the symbol / of the next used symbol.
-// With key = (slot + 1) << 9, "cum(row) <= slot" is simply "row < key" on the packed words.
+// The lookup proper: (e, hi) = the packed rows around the slot, assuming the wanted row is the midpoint row or a
+// direct neighbour.  With key = (slot + 1) << 9, "cum(row) <= slot" is simply "row < key" on the packed words.
+// Returns false when that assumption does not hold for this lane (several symbols inside 1/128th of the range).
 template <typename Table, typename LutT>
-__device__ __forceinline__ uint32_t rans_lookup(const Table& T, const LutT* lut, uint32_t lut_stride,
-                                                uint32_t lut_shift, uint32_t slot, uint32_t& c0, uint32_t& c1) {
-    uint32_t p = lut[(slot >> lut_shift) * lut_stride];
-    const uint32_t key = (slot + 1u) << kSymBits;
+__device__ __forceinline__ bool rans_lookup_near(const Table& T, const LutT* lut, uint32_t lut_stride,
+                                                 uint32_t lut_shift, uint32_t slot, uint32_t key, uint32_t& p,
+                                                 uint32_t& e, uint32_t& hi) {
+    p = lut[(slot >> lut_shift) * lut_stride];
     const uint32_t em = T.at(p - 1u), e0 = T.at(p), e1 = T.at(p + 1u), e2 = T.at_eager(p + 2u);
     const bool down = e0 >= key;  // the row holding the bucket's middle starts after the slot
     const bool up = e1 < key;     // ... or ends before it
-    uint32_t e = down ? em : (up ? e1 : e0);
+    e = down ? em : (up ? e1 : e0);
     // e2 enters arithmetically: written as a select the compiler predicates its load on `up`, which puts a
     // second shared-memory round trip on the chain whenever any lane of the warp needs the upper neighbour
     uint32_t up_ones;  // all ones when e1 < key; produced where the compiler cannot turn it back into a select
     asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(up_ones) : "r"(e1), "r"(key));
-    uint32_t hi = down ? e0 : e1 + ((e2 - e1) & up_ones);
-    // more than one row away (several symbols inside 1/128th of the range): rare; the vote makes the
-    // branch uniform so that the common path carries no divergence bookkeeping
-    if (__any_sync(0xffffffffu, e >= key || hi < key)) {
-        p = down ? p - 1u : (up ? p + 1u : p);
-        while (e >= key) {
-            p--;
-            hi = e;
-            e = T.at(p);
-        }
-        while (hi < key) {
-            p++;
-            e = hi;
-            hi = T.at(p + 1u);
-        }
+    hi = down ? e0 : e1 + ((e2 - e1) & up_ones);
+    p = down ? p - 1u : (up ? p + 1u : p);
+    return e < key && hi >= key;
+}
+
+// Walks from row p to the row that holds the slot (rare: only lanes for which rans_lookup_near said no move).
+template <typename Table>
+__device__ __forceinline__ void rans_lookup_far(const Table& T, uint32_t key, uint32_t p, uint32_t& e, uint32_t& hi) {
+    while (e >= key) {
+        p--;
+        hi = e;
+        e = T.at(p);
     }
-    c0 = e >> kSymBits;
-    c1 = hi >> kSymBits;
-    return e & kSymMask;
+    while (hi < key) {
+        p++;
+        e = hi;
+        hi = T.at(p + 1u);
+    }
 }
 
 // One decode step (rans64.hpp:118-142).  There is no "past the end of this stream" case: a lane whose
 // stream is shorter than its neighbours' keeps decoding (its table lookups and word reads stay in
 // bounds whatever the state is) and the surplus symbols are simply not stored.
+// The state update is computed from the near lookup straight away; whether some lane needs the far walk is
+// voted on meanwhile, and only then (rare, warp-uniform) is the update redone — the vote's latency overlaps
+// the multiply instead of preceding it.
 template <typename Table, typename LutT>
 __device__ __forceinline__ uint32_t rans_get(uint64_t& x, WordRing& rd, const Table& T, const LutT* lut,
                                              uint32_t lut_stride, uint32_t lut_shift, uint32_t bits, uint32_t mask) {
     const uint32_t slot = (uint32_t)x & mask;  // rans64.hpp:118-121
-    uint32_t c0, c1;
-    const uint32_t sym = rans_lookup(T, lut, lut_stride, lut_shift, slot, c0, c1);
-    x = (uint64_t)(c1 - c0) * (x >> bits) + (slot - c0);  // rans64.hpp:126-134
-    const bool refill = x < kRansL;                       // rans64.hpp:137-141
+    const uint32_t key = (slot + 1u) << kSymBits;
+    uint32_t p, e, hi;
+    const bool near = rans_lookup_near(T, lut, lut_stride, lut_shift, slot, key, p, e, hi);
+    const uint64_t top = x >> bits;
+    uint64_t next = (uint64_t)((hi >> kSymBits) - (e >> kSymBits)) * top + (slot - (e >> kSymBits));  // rans64.hpp:126-134
+    if (__any_sync(0xffffffffu, !near)) {
+        rans_lookup_far(T, key, p, e, hi);
+        next = (uint64_t)((hi >> kSymBits) - (e >> kSymBits)) * top + (slot - (e >> kSymBits));
+    }
+    x = next;
+    const bool refill = x < kRansL;  // rans64.hpp:137-141
     x = refill ? ((x << 32) | rd.next) : x;
     rd.take_if(refill);
-    return sym;
+    return e & kSymMask;
 }
 
 // One warp per CTA, one stream per lane.  `rows_lo < need <= rows` selects the warps of this launch's
