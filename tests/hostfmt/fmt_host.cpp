@@ -18,4 +18,12 @@ uint64_t fmt_parse(const uint8_t* in, uint64_t at, unsigned flags, uint32_t* fie
     return hohfmt::parse_table(in, h, freqs);
 }
 uint32_t fmt_put_varint(uint8_t* dst, uint32_t at, uint32_t v) { return hohfmt::put_varint(dst, at, v); }
+// table mode plan_head picks, with and without the "representable tables only" rule (HOH_FIX_LONE)
+uint32_t fmt_table_mode(const uint32_t* freqs, uint32_t range, uint32_t n, uint32_t prob_bits, uint32_t representable) {
+    uint8_t head[16];
+    uint32_t stored, mode;
+    hohfmt::ClampSet cs;
+    hohfmt::plan_head(freqs, range, n, prob_bits, head, &stored, &cs, &mode, representable);
+    return mode;
+}
 }

@@ -22,6 +22,8 @@ def _lib():
     L.fmt_build_head.argtypes = [ol.u32p, C.c_uint32, C.c_uint32, C.c_uint32, ol.u8p, C.POINTER(C.c_uint32)]
     L.fmt_parse.restype = C.c_uint64
     L.fmt_parse.argtypes = [ol.u8p, C.c_uint64, C.c_uint, ol.u32p, ol.u32p]
+    L.fmt_table_mode.restype = C.c_uint32
+    L.fmt_table_mode.argtypes = [ol.u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.fmt_put_varint.restype = C.c_uint32
     L.fmt_put_varint.argtypes = [ol.u8p, C.c_uint32, C.c_uint32]
     return L
@@ -97,3 +99,28 @@ def test_head_and_parse_match_oracle_streams():
         else:
             assert stored.value == len(want)
     assert checked > 200
+
+
+def test_representable_rule_only_changes_lossy_mode1_tables():
+    """HOH_FIX_LONE's table rule (plan_head's `representable`): table mode 1 writes every frequency on
+    bit_length(range-1) bits (SURVEY D6), so it is replaced by mode 2 exactly when some frequency does not fit;
+    every other decision is the reference's."""
+    L = _lib()
+    rng = np.random.default_rng(12)
+    changed = kept1 = 0
+    for it in range(3000):
+        rangev = int(rng.choice([2, 3, 5, 9, 14, 16, 40, 256]))
+        pb = int(rng.integers(max(4, int(np.ceil(np.log2(rangev)))), 13))
+        n = int(rng.integers(rangev, 400))
+        sym = np.minimum(rng.geometric(float(rng.uniform(0.05, 0.9)), n) - 1, rangev - 1).astype(np.uint16)
+        f, cum, st = _norm(sym, rangev, pb)
+        if st:
+            continue
+        m0 = L.fmt_table_mode(f, rangev, n, pb, 0)
+        m1 = L.fmt_table_mode(f, rangev, n, pb, 1)
+        maxbits = int(rangev - 1).bit_length()
+        lossy = m0 == 1 and bool((f >> maxbits).any())
+        assert m1 == (2 if lossy else m0), (it, rangev, pb, m0, m1)
+        changed += lossy
+        kept1 += (m0 == 1 and not lossy)
+    assert changed > 20 and kept1 > 20
