@@ -1182,7 +1182,9 @@ __device__ __forceinline__ uint32_t rans_get(uint64_t& x, WordRing& rd, const Ta
         next = (uint64_t)((hi >> kSymBits) - (e >> kSymBits)) * top + (slot - (e >> kSymBits));
     }
     x = next;
-    const bool refill = x < kRansL;  // rans64.hpp:137-141
+    // rans64.hpp:137-141: x < 2^31, written on the two halves so that ONE predicate serves the state update and
+    // the word ring (the 64-bit comparison was being evaluated twice, as >= and as >)
+    const bool refill = ((uint32_t)(x >> 32) | ((uint32_t)x >> 31)) == 0u;
     x = refill ? ((x << 32) | rd.next) : x;
     rd.take_if(refill);
     return e & kSymMask;
@@ -1504,7 +1506,7 @@ __global__ void __launch_bounds__(kStaticDirectWarps * 32) k_rans_decode_static_
                 const uint32_t sym = s_c2s[slot];
                 const uint32_t info = s_info[sym];
                 x = (uint64_t)(info >> 16) * (x >> bits) + (slot - (info & 0xffffu));  // rans64.hpp:126-134
-                const bool refill = x < kRansL;                                            // :137-141
+                const bool refill = ((uint32_t)(x >> 32) | ((uint32_t)x >> 31)) == 0u;       // :137-141, x < 2^31
                 x = refill ? ((x << 32) | rd.next) : x;
                 rd.take_if(refill);
                 my_row[k] = (uint16_t)sym;
