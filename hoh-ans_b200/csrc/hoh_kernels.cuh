@@ -1143,13 +1143,14 @@ __device__ __forceinline__ bool rans_lookup_near(const Table& T, const LutT* lut
     uint32_t up_ones;  // all ones when e1 < key; produced where the compiler cannot turn it back into a select
     asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(up_ones) : "r"(e1), "r"(key));
     hi = down ? e0 : e1 + ((e2 - e1) & up_ones);
-    p = down ? p - 1u : (up ? p + 1u : p);
     return e < key && hi >= key;
 }
 
-// Walks from row p to the row that holds the slot (rare: only lanes for which rans_lookup_near said no move).
+// Walks to the row that holds the slot from where the near lookup ended (p = the midpoint row it started from;
+// rare: only lanes for which rans_lookup_near said no move).
 template <typename Table>
 __device__ __forceinline__ void rans_lookup_far(const Table& T, uint32_t key, uint32_t p, uint32_t& e, uint32_t& hi) {
+    p = T.at(p) >= key ? p - 1u : (T.at(p + 1u) < key ? p + 1u : p);  // the row `e` came from
     while (e >= key) {
         p--;
         hi = e;
