@@ -22,7 +22,7 @@ namespace {
 enum Slot {
     S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
     S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
-    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_D_TILES, S_D_PLANES, S_D_LZSYM, S_D_IDXSYM, S_D_RESID, S_D_OUT, S_D_BACKREF, S_D_MAPS,
+    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_T_MORE_SHAPES, S_T_LAST = S_T_NUKE + 4 * 9 - 1, S_D_TILES, S_D_PLANES, S_D_LZSYM, S_D_IDXSYM, S_D_RESID, S_D_OUT, S_D_BACKREF, S_D_MAPS,
     S_D_STREAMS, S_D_RES_A, S_D_RES_B, S_D_TOP, S_D_BP, S_D_PSTATUS, S_PA_BEST, S_COUNT
 };
 
@@ -1241,6 +1241,59 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     return HOH_OK;
 }
 
+} // extern "C" (reopened below)
+namespace {
+// The tile shapes of an image (choh.cpp:459-474): the last column and the last row take what is left of the
+// image, so there are up to four shapes, each a rectangular sub-grid of the tile grid.
+struct TileClass {
+    TileSel sel;
+    int tw, th;
+};
+int tile_classes(const TileGeom& g, TileClass out[4]) {
+    const uint32_t rw = g.width - (g.x_tiles - 1) * g.tile_w, bh = g.height - (g.y_tiles - 1) * g.tile_h;
+    uint32_t xs[2][3], ys[2][3];  // {first, count, size}
+    int nx = 0, ny = 0;
+    if (rw == g.tile_w) {
+        xs[nx][0] = 0, xs[nx][1] = g.x_tiles, xs[nx][2] = g.tile_w, nx++;
+    } else {
+        if (g.x_tiles > 1) xs[nx][0] = 0, xs[nx][1] = g.x_tiles - 1, xs[nx][2] = g.tile_w, nx++;
+        xs[nx][0] = g.x_tiles - 1, xs[nx][1] = 1, xs[nx][2] = rw, nx++;
+    }
+    if (bh == g.tile_h) {
+        ys[ny][0] = 0, ys[ny][1] = g.y_tiles, ys[ny][2] = g.tile_h, ny++;
+    } else {
+        if (g.y_tiles > 1) ys[ny][0] = 0, ys[ny][1] = g.y_tiles - 1, ys[ny][2] = g.tile_h, ny++;
+        ys[ny][0] = g.y_tiles - 1, ys[ny][1] = 1, ys[ny][2] = bh, ny++;
+    }
+    int n = 0;
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            TileClass& c = out[n++];
+            c.sel.g = g;
+            c.sel.x_first = xs[i][0];
+            c.sel.x_count = xs[i][1];
+            c.sel.y_first = ys[j][0];
+            c.sel.y_count = ys[j][1];
+            c.sel.per_image = xs[i][1] * ys[j][1];
+            c.tw = (int)xs[i][2];
+            c.th = (int)ys[j][2];
+        }
+    return n;
+}
+TileSel whole_grid(const TileGeom& g) {
+    TileSel s;
+    s.g = g;
+    s.x_first = s.y_first = 0;
+    s.x_count = g.x_tiles;
+    s.y_count = g.y_tiles;
+    s.per_image = g.tiles_per_image;
+    return s;
+}
+constexpr int kTSlots = 9;  // scratch buffers of one tile shape in hoh_encode_images (S_T_NUKE .. S_T_R9)
+inline Slot tslot(int cls, Slot base) { return (Slot)(S_T_NUKE + cls * kTSlots + (base - S_T_NUKE)); }
+}  // namespace
+extern "C" {
+
 // -------------------------------------------------------------------------------------------------
 // lz.hpp:6 for many tiles
 // -------------------------------------------------------------------------------------------------
@@ -1333,10 +1386,10 @@ int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint
     LzShape sh;
     memset(&sh, 0, sizeof(sh));
     sh.tiled = 1;
-    sh.g = to_geom(hg);
-    sh.stride = sh.g.plane_stride;
-    return find_lz_impl(ctx, d_rgb, sh, n_images * sh.g.tiles_per_image, (size_t)hg.tile_w * hg.tile_h, distance, flags, d_bonus,
-                        d_nuke, sh.g.plane_stride, d_lz, lz_stride, d_lz_size, d_status);
+    sh.sel = whole_grid(to_geom(hg));
+    sh.stride = sh.sel.g.plane_stride;
+    return find_lz_impl(ctx, d_rgb, sh, n_images * sh.sel.g.tiles_per_image, (size_t)hg.tile_w * hg.tile_h, distance, flags, d_bonus,
+                        d_nuke, sh.sel.g.plane_stride, d_lz, lz_stride, d_lz_size, d_status);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1348,89 +1401,106 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
     if (!ctx || !d_rgb || !d_packed || !d_tile_off || !d_tiles || mode < 0 || mode > 4) return HOH_E_ARG;
     hoh_tile_geometry hg;
     TRY(hoh_tile_geometry_for(width, height, &hg));
-    if (width % hg.x_tiles || height % hg.y_tiles) return HOH_E_UNSUPPORTED;  // unequal tiles: not in this round
     CK(cudaMemsetAsync(d_tile_off, 0, sizeof(uint64_t), ctx->stream));
     if (n_images == 0) return HOH_OK;
     const TileGeom g = to_geom(hg);
-    const int tw = (int)hg.tile_w, th = (int)hg.tile_h;
-    const size_t npx = (size_t)tw * th;
+    TileClass cls[4];
+    const int n_cls = tile_classes(g, cls);
     static const int dist_of_mode[5] = {6, 10, 11, 12, 14};  // choh.cpp:123-136
     const int distance = dist_of_mode[mode];
     const uint32_t per8 = mode > 2 ? 3u : 1u;
-    const size_t lz_stride = hoh_find_lz_stride(tw, th);
-    const size_t out8_tile = hoh_layer_encode_out_bytes(per8, tw, th, 8, mode);
-    const size_t out9_tile = hoh_layer_encode_out_bytes(2, tw, th, 9, mode);
-    // scratch per tile: this function's buffers + what the LZ finder and layer_encode_batch allocate themselves
-    const size_t lz_words = (1u << distance) + (npx + kLzSeg) + 32 * kLzAhead;
-    const size_t per_tile = (per8 + 2) * npx * 2 + out8_tile + out9_tile + lz_stride + g.plane_stride +
-                            lz_words * 4 + npx * 4 + 4 * (size_t)lz_side_stride(npx) * 2 +
-                            4 * hoh_enc_slab_bytes(lz_side_stride(npx), 10) + 3 * (2 * npx * 2 + 8192) + 4096;
+    // scratch per IMAGE: this function's buffers + what the LZ finder and layer_encode_batch allocate themselves.
+    // The candidates of every shape stay alive until the image chunk's tiles have been emitted in tile order.
+    size_t lz_stride[4], out8_tile[4], out9_tile[4], per_image = 0;
+    for (int c = 0; c < n_cls; c++) {
+        const size_t npx = (size_t)cls[c].tw * cls[c].th;
+        lz_stride[c] = hoh_find_lz_stride(cls[c].tw, cls[c].th);
+        out8_tile[c] = hoh_layer_encode_out_bytes(per8, cls[c].tw, cls[c].th, 8, mode);
+        out9_tile[c] = hoh_layer_encode_out_bytes(2, cls[c].tw, cls[c].th, 9, mode);
+        const size_t lz_words = (1u << distance) + (npx + kLzSeg) + 32 * kLzAhead;
+        per_image += cls[c].sel.per_image *
+                     ((per8 + 2) * npx * 2 + out8_tile[c] + out9_tile[c] + lz_stride[c] + g.plane_stride + lz_words * 4 +
+                      npx * 4 + 4 * (size_t)lz_side_stride(npx) * 2 + 4 * hoh_enc_slab_bytes(lz_side_stride(npx), 10) +
+                      3 * (2 * npx * 2 + 8192) + 4096);
+    }
     size_t budget = (size_t)32 << 30;
     if (const char* e = getenv("HOH_SCRATCH_GB")) budget = (size_t)atof(e) * ((size_t)1 << 30);
-    size_t images_per_chunk = budget / (per_tile * g.tiles_per_image);
+    size_t images_per_chunk = budget / per_image;
     if (images_per_chunk == 0) images_per_chunk = 1;
     if (images_per_chunk > n_images) images_per_chunk = n_images;
-    const size_t chunk_tiles = images_per_chunk * g.tiles_per_image;
-    uint8_t *nuke, *lz, *out8, *out9;
-    uint32_t* u32;
-    uint16_t *p8, *p9;
-    hoh_stream_result *r8, *r9;
-    TRY(scratch_t(ctx, S_T_NUKE, chunk_tiles * g.plane_stride, &nuke));
-    TRY(scratch_t(ctx, S_T_LZ, chunk_tiles * lz_stride, &lz));
-    TRY(scratch_t(ctx, S_T_U32, chunk_tiles * 3, &u32));
-    TRY(scratch_t(ctx, S_T_P8, chunk_tiles * per8 * npx, &p8));
-    TRY(scratch_t(ctx, S_T_P9, chunk_tiles * 2 * npx, &p9));
-    TRY(scratch_t(ctx, S_T_O8, chunk_tiles * out8_tile, &out8));
-    TRY(scratch_t(ctx, S_T_O9, chunk_tiles * out9_tile, &out9));
-    TRY(scratch_t(ctx, S_T_R8, chunk_tiles * per8, &r8));
-    TRY(scratch_t(ctx, S_T_R9, chunk_tiles * 2, &r9));
-    uint32_t* lz_size = u32;
-    int32_t* lz_status = reinterpret_cast<int32_t*>(u32 + chunk_tiles);
-    uint32_t* info = u32 + 2 * chunk_tiles;
+    uint8_t *nuke[4], *lz[4], *out8[4], *out9[4];
+    uint32_t* u32[4];
+    uint16_t *p8[4], *p9[4];
+    hoh_stream_result *r8[4], *r9[4];
+    for (int c = 0; c < n_cls; c++) {
+        const size_t ct = images_per_chunk * cls[c].sel.per_image, npx = (size_t)cls[c].tw * cls[c].th;
+        TRY(scratch_t(ctx, tslot(c, S_T_NUKE), ct * g.plane_stride, &nuke[c]));
+        TRY(scratch_t(ctx, tslot(c, S_T_LZ), ct * lz_stride[c], &lz[c]));
+        TRY(scratch_t(ctx, tslot(c, S_T_U32), ct * 3, &u32[c]));
+        TRY(scratch_t(ctx, tslot(c, S_T_P8), ct * per8 * npx, &p8[c]));
+        TRY(scratch_t(ctx, tslot(c, S_T_P9), ct * 2 * npx, &p9[c]));
+        TRY(scratch_t(ctx, tslot(c, S_T_O8), ct * out8_tile[c], &out8[c]));
+        TRY(scratch_t(ctx, tslot(c, S_T_O9), ct * out9_tile[c], &out9[c]));
+        TRY(scratch_t(ctx, tslot(c, S_T_R8), ct * per8, &r8[c]));
+        TRY(scratch_t(ctx, tslot(c, S_T_R9), ct * 2, &r9[c]));
+    }
     for (size_t img0 = 0; img0 < n_images; img0 += images_per_chunk) {
         const size_t ni = std::min(images_per_chunk, n_images - img0);
-        const size_t nt = ni * g.tiles_per_image, first = img0 * g.tiles_per_image;
         const uint8_t* rgb = d_rgb + img0 * (size_t)width * height * 3;
-        LzShape sh;
-        memset(&sh, 0, sizeof(sh));
-        sh.tiled = 1;
-        sh.g = g;
-        sh.stride = g.plane_stride;
-        TRY(find_lz_impl(ctx, rgb, sh, nt, npx, distance, flags, nullptr, nuke, g.plane_stride, lz, lz_stride, lz_size, lz_status,
-                         info));
-        k_tile_planes<<<(unsigned)nt, 256, 0, ctx->stream>>>(rgb, g, 0, per8, p8, p9);
-        LAUNCHED("k_tile_planes");
-        // the 8-bit planes and the 9-bit planes are two independent batches, each bound by stream length rather
-        // than stream count: they run side by side in two child contexts (own stream, own scratch)
-        hoh_ctx* c8 = ctx;
-        hoh_ctx* c9 = ctx;
-        if (!ctx->profiling) {
-            for (int k = 0; k < 2; k++)
-                if (!ctx->child[k] && hoh_ctx_create(ctx->device, nullptr, &ctx->child[k]) != HOH_OK) return HOH_E_CUDA;
-            c8 = ctx->child[0];
-            c9 = ctx->child[1];
-            TRY(aux_init(ctx));
-            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-            CK(cudaStreamWaitEvent(c8->stream, ctx->ev_fork, 0));
-            CK(cudaStreamWaitEvent(c9->stream, ctx->ev_fork, 0));
+        for (int c = 0; c < n_cls; c++) {
+            const TileSel& sel = cls[c].sel;
+            const int tw = cls[c].tw, th = cls[c].th;
+            const size_t nt = ni * sel.per_image, npx = (size_t)tw * th;
+            uint32_t* lz_size = u32[c];
+            int32_t* lz_status = reinterpret_cast<int32_t*>(u32[c] + nt);
+            uint32_t* info = u32[c] + 2 * nt;
+            LzShape sh;
+            memset(&sh, 0, sizeof(sh));
+            sh.tiled = 1;
+            sh.sel = sel;
+            sh.stride = g.plane_stride;
+            TRY(find_lz_impl(ctx, rgb, sh, nt, npx, distance, flags, nullptr, nuke[c], g.plane_stride, lz[c], lz_stride[c],
+                             lz_size, lz_status, info));
+            k_tile_planes<<<(unsigned)nt, 256, 0, ctx->stream>>>(rgb, sel, per8, p8[c], p9[c]);
+            LAUNCHED("k_tile_planes");
+            // the 8-bit planes and the 9-bit planes are two independent batches, each bound by stream length rather
+            // than stream count: they run side by side in two child contexts (own stream, own scratch)
+            hoh_ctx* c8 = ctx;
+            hoh_ctx* c9 = ctx;
+            if (!ctx->profiling) {
+                for (int k = 0; k < 2; k++)
+                    if (!ctx->child[k] && hoh_ctx_create(ctx->device, nullptr, &ctx->child[k]) != HOH_OK) return HOH_E_CUDA;
+                c8 = ctx->child[0];
+                c9 = ctx->child[1];
+                TRY(aux_init(ctx));
+                CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                CK(cudaStreamWaitEvent(c8->stream, ctx->ev_fork, 0));
+                CK(cudaStreamWaitEvent(c9->stream, ctx->ev_fork, 0));
+            }
+            TRY(hoh_layer_encode_batch(c8, p8[c], nt * per8, tw, th, 8, mode, flags, nuke[c], g.plane_stride, per8, out8[c],
+                                       nt * out8_tile[c], r8[c], nullptr, 0, nullptr));
+            TRY(hoh_layer_encode_batch(c9, p9[c], nt * 2, tw, th, 9, mode, flags, nuke[c], g.plane_stride, 2, out9[c],
+                                       nt * out9_tile[c], r9[c], nullptr, 0, nullptr));
+            if (c8 != ctx) {
+                CK(cudaEventRecord(ctx->ev_join[0], c8->stream));
+                CK(cudaEventRecord(ctx->ev_join[1], c9->stream));
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
+            }
+            k_tile_decide<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, sel, img0, per8, r8[c], r9[c], lz_size, lz_status,
+                                                                        info, d_tiles);
+            LAUNCHED("k_tile_decide");
         }
-        TRY(hoh_layer_encode_batch(c8, p8, nt * per8, tw, th, 8, mode, flags, nuke, g.plane_stride, per8, out8, nt * out8_tile, r8,
-                                   nullptr, 0, nullptr));
-        TRY(hoh_layer_encode_batch(c9, p9, nt * 2, tw, th, 9, mode, flags, nuke, g.plane_stride, 2, out9, nt * out9_tile, r9,
-                                   nullptr, 0, nullptr));
-        if (c8 != ctx) {
-            CK(cudaEventRecord(ctx->ev_join[0], c8->stream));
-            CK(cudaEventRecord(ctx->ev_join[1], c9->stream));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
-        }
-        k_tile_decide<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, first, per8, r8, r9, lz_size, lz_status, info, d_tiles);
-        LAUNCHED("k_tile_decide");
-        k_tile_scan<<<1, 1024, 0, ctx->stream>>>(d_tiles, first, (uint32_t)nt, d_tile_off);
+        // offsets in tile order over the chunk's images, then every shape emits its tiles
+        k_tile_scan<<<1, 1024, 0, ctx->stream>>>(d_tiles, img0 * g.tiles_per_image, (uint32_t)(ni * g.tiles_per_image),
+                                                 d_tile_off);
         LAUNCHED("k_tile_scan");
-        k_tile_emit<<<(unsigned)nt, 256, 0, ctx->stream>>>(first, per8, r8, r9, out8, out9, lz, (uint32_t)lz_stride, d_tiles,
-                                                          d_packed, packed_cap);
-        LAUNCHED("k_tile_emit");
+        for (int c = 0; c < n_cls; c++) {
+            const size_t nt = ni * cls[c].sel.per_image;
+            k_tile_emit<<<(unsigned)nt, 256, 0, ctx->stream>>>(cls[c].sel, img0, per8, r8[c], r9[c], out8[c], out9[c], lz[c],
+                                                              (uint32_t)lz_stride[c], d_tiles, d_packed, packed_cap);
+            LAUNCHED("k_tile_emit");
+        }
     }
     return HOH_OK;
 }
@@ -1444,21 +1514,21 @@ int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes
     if (n_images == 0) return HOH_OK;
     hoh_tile_geometry hg;
     TRY(hoh_tile_geometry_for(width, height, &hg));
-    if (width % hg.x_tiles || height % hg.y_tiles) return HOH_E_UNSUPPORTED;
     const TileGeom g = to_geom(hg);
-    const int tw = (int)hg.tile_w, th = (int)hg.tile_h;
-    const uint32_t npx = (uint32_t)tw * th;
-    const uint32_t xt = (tw + 39) / 40, yt = (th + 39) / 40, cells = xt * yt, cells_pad = (cells + 7u) & ~7u;
-    if (xt > 256 || yt > 256) return HOH_E_UNSUPPORTED;
-    const uint32_t side = lz_side_stride(npx);
-    const size_t per_tile = 4 * (size_t)side * 2 + 3 * (size_t)g.plane_stride * 2 * 2 + (size_t)g.plane_stride * 2 +
-                            3 * (size_t)(kCumRow * 4 + kFreqRow * 4) + 3 * (size_t)tw * 3 + 4096;
+    TileClass cls[4];
+    const int n_cls = tile_classes(g, cls);
+    const uint32_t max_cells = (((uint32_t)hg.tile_w + 39) / 40) * (((uint32_t)hg.tile_h + 39) / 40);
+    if ((hg.tile_w + 39) / 40 > 256 || (hg.tile_h + 39) / 40 > 256) return HOH_E_UNSUPPORTED;
+    const uint32_t max_cells_pad = (max_cells + 7u) & ~7u;
+    const uint32_t max_side = lz_side_stride((size_t)hg.tile_w * hg.tile_h);
+    const size_t per_tile = 4 * (size_t)max_side * 2 + 3 * (size_t)g.plane_stride * 2 * 2 + (size_t)g.plane_stride * 2 +
+                            3 * (size_t)(kCumRow * 4 + kFreqRow * 4) + 3 * (size_t)hg.tile_w * 3 + 4096;
     size_t budget = (size_t)32 << 30;
     if (const char* e = getenv("HOH_SCRATCH_GB")) budget = (size_t)atof(e) * ((size_t)1 << 30);
     size_t images_per_chunk = budget / (per_tile * g.tiles_per_image);
     if (images_per_chunk == 0) images_per_chunk = 1;
     if (images_per_chunk > n_images) images_per_chunk = n_images;
-    const size_t ct = images_per_chunk * g.tiles_per_image;
+    const size_t ct = images_per_chunk * g.tiles_per_image;  // upper bound for any one shape's tiles in a chunk
     DTile* tiles;
     DPlane* planes;
     uint16_t *lz_sym, *idx_sym, *resid, *out, *backref, *maps, *top;
@@ -1468,46 +1538,53 @@ int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes
     hoh_dec_result *res_a, *res_b;
     TRY(scratch_t(ctx, S_D_TILES, ct, &tiles));
     TRY(scratch_t(ctx, S_D_PLANES, ct * 3, &planes));
-    TRY(scratch_t(ctx, S_D_LZSYM, ct * 4 * side, &lz_sym));
-    TRY(scratch_t(ctx, S_D_IDXSYM, ct * 3 * cells_pad, &idx_sym));
+    TRY(scratch_t(ctx, S_D_LZSYM, ct * 4 * max_side, &lz_sym));
+    TRY(scratch_t(ctx, S_D_IDXSYM, ct * 3 * max_cells_pad, &idx_sym));
     TRY(scratch_t(ctx, S_D_RESID, ct * 3 * g.plane_stride, &resid));
     TRY(scratch_t(ctx, S_D_OUT, ct * 3 * g.plane_stride, &out));
     TRY(scratch_t(ctx, S_D_BACKREF, ct * g.plane_stride, &backref));
-    TRY(scratch_t(ctx, S_D_MAPS, ct * 3 * cells, &maps));
+    TRY(scratch_t(ctx, S_D_MAPS, ct * 3 * max_cells, &maps));
     TRY(scratch_t(ctx, S_D_STREAMS, ct * 3, &streams));
     TRY(scratch_t(ctx, S_D_RES_A, ct * 3, &res_a));
     TRY(scratch_t(ctx, S_D_RES_B, ct * 3, &res_b));
-    TRY(scratch_t(ctx, S_D_TOP, ct * 3 * (size_t)tw, &top));
-    TRY(scratch_t(ctx, S_D_BP, ct * 3 * (size_t)tw, &bp));
+    TRY(scratch_t(ctx, S_D_TOP, ct * 3 * (size_t)hg.tile_w, &top));
+    TRY(scratch_t(ctx, S_D_BP, ct * 3 * (size_t)hg.tile_w, &bp));
     TRY(scratch_t(ctx, S_D_PSTATUS, ct * 3, &pstatus));
     for (size_t img0 = 0; img0 < n_images; img0 += images_per_chunk) {
         const size_t ni = std::min(images_per_chunk, n_images - img0);
-        const size_t nt = ni * g.tiles_per_image, first = img0 * g.tiles_per_image;
-        k_dt_begin<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, d_packed, packed_bytes, d_tile_off + first, side, tiles,
-                                                                 streams);
-        LAUNCHED("k_dt_begin");
-        for (uint32_t k = 0; k < 4; k++) {  // un_lz.hpp:100-145: the side streams follow one another
-            TRY(decode_common(ctx, streams, nt, d_packed, packed_bytes, lz_sym, res_a));
-            k_dt_lz_next<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, k, d_packed, packed_bytes, res_a, side, tiles,
-                                                                       streams);
-            LAUNCHED("k_dt_lz_next");
+        for (int c = 0; c < n_cls; c++) {  // one pass per tile shape (choh.cpp:459-474)
+            const TileSel& sel = cls[c].sel;
+            const int tw = cls[c].tw, th = cls[c].th;
+            const uint32_t npx = (uint32_t)tw * th;
+            const uint32_t xt = (tw + 39) / 40, yt = (th + 39) / 40, cells = xt * yt, cells_pad = (cells + 7u) & ~7u;
+            const uint32_t side = lz_side_stride(npx);
+            const size_t nt = ni * sel.per_image;
+            k_dt_begin<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, sel, img0, d_packed, packed_bytes, d_tile_off, side,
+                                                                     tiles, streams);
+            LAUNCHED("k_dt_begin");
+            for (uint32_t k = 0; k < 4; k++) {  // un_lz.hpp:100-145: the side streams follow one another
+                TRY(decode_common(ctx, streams, nt, d_packed, packed_bytes, lz_sym, res_a));
+                k_dt_lz_next<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, k, d_packed, packed_bytes, res_a, side, tiles,
+                                                                           streams);
+                LAUNCHED("k_dt_lz_next");
+            }
+            k_dt_channels<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, d_packed, packed_bytes, xt, yt, cells_pad, tiles,
+                                                                        planes, streams);
+            LAUNCHED("k_dt_channels");
+            TRY(decode_common(ctx, streams, nt * 3, d_packed, packed_bytes, idx_sym, res_a));
+            k_dt_main<<<blocks_for(nt * 3, 128), 128, 0, ctx->stream>>>(nt * 3, cells, cells_pad, g.plane_stride, npx, res_a,
+                                                                        idx_sym, planes, maps, streams);
+            LAUNCHED("k_dt_main");
+            TRY(decode_common(ctx, streams, nt * 3, d_packed, packed_bytes, resid, res_b));
+            k_dt_unlz<<<blocks_for(nt * 32, 128), 128, 0, ctx->stream>>>(nt, npx, g.plane_stride, lz_sym, side, tiles, backref);
+            LAUNCHED("k_dt_unlz");
+            k_dt_unpredict<<<blocks_for(nt * 3, 64), 64, 0, ctx->stream>>>(nt * 3, tw, th, (int)xt, (int)yt, g.plane_stride,
+                                                                           planes, tiles, res_b, resid, maps, backref, out,
+                                                                           top, bp, pstatus);
+            LAUNCHED("k_dt_unpredict");
+            k_dt_store<<<(unsigned)nt, 256, 0, ctx->stream>>>(sel, img0, g.plane_stride, tiles, pstatus, out, d_rgb, d_status);
+            LAUNCHED("k_dt_store");
         }
-        k_dt_channels<<<blocks_for(nt, 128), 128, 0, ctx->stream>>>(nt, d_packed, packed_bytes, xt, yt, cells_pad, tiles,
-                                                                    planes, streams);
-        LAUNCHED("k_dt_channels");
-        TRY(decode_common(ctx, streams, nt * 3, d_packed, packed_bytes, idx_sym, res_a));
-        k_dt_main<<<blocks_for(nt * 3, 128), 128, 0, ctx->stream>>>(nt * 3, cells, cells_pad, g.plane_stride, npx, res_a,
-                                                                    idx_sym, planes, maps, streams);
-        LAUNCHED("k_dt_main");
-        TRY(decode_common(ctx, streams, nt * 3, d_packed, packed_bytes, resid, res_b));
-        k_dt_unlz<<<blocks_for(nt * 32, 128), 128, 0, ctx->stream>>>(nt, npx, g.plane_stride, lz_sym, side, tiles, backref);
-        LAUNCHED("k_dt_unlz");
-        k_dt_unpredict<<<blocks_for(nt * 3, 64), 64, 0, ctx->stream>>>(nt * 3, tw, th, (int)xt, (int)yt, g.plane_stride,
-                                                                       planes, tiles, res_b, resid, maps, backref, out, top,
-                                                                       bp, pstatus);
-        LAUNCHED("k_dt_unpredict");
-        k_dt_store<<<(unsigned)nt, 256, 0, ctx->stream>>>(g, first, g.plane_stride, tiles, pstatus, out, d_rgb, d_status);
-        LAUNCHED("k_dt_store");
     }
     return HOH_OK;
 }

@@ -2134,6 +2134,24 @@ __device__ __forceinline__ void tile_rect(const TileGeom& g, uint32_t tile, uint
     th = min(g.tile_h, g.height - y0);
 }
 
+// A rectangular sub-grid of an image's tile grid: the tiles of one SHAPE.  choh.cpp:459-474 gives every tile the
+// nominal size except those of the last column / last row, which take what is left, so an image has up to four
+// shapes (interior, right edge, bottom edge, corner); kernels that need equal tiles run once per shape.
+// Local tile lt of a selection over a batch: image lt / per_image, then row-major inside the sub-grid.
+struct TileSel {
+    TileGeom g;
+    uint32_t x_first, x_count, y_first, y_count, per_image;
+};
+
+__device__ __forceinline__ void sel_tile(const TileSel& s, uint64_t lt, uint64_t& image, uint32_t& tile_in_image,
+                                         uint32_t& x0, uint32_t& y0, uint32_t& tw, uint32_t& th) {
+    image = lt / s.per_image;
+    const uint32_t k = (uint32_t)(lt % s.per_image);
+    const uint32_t tx = s.x_first + k % s.x_count, ty = s.y_first + k / s.x_count;
+    tile_in_image = ty * s.g.x_tiles + tx;
+    tile_rect(s.g, tile_in_image, x0, y0, tw, th);
+}
+
 __global__ void __launch_bounds__(256) k_tile_residuals_s0_generic(const uint8_t* __restrict__ rgb, TileGeom g,
                                                            uint16_t* __restrict__ resid,
                                                            uint32_t* __restrict__ freqs) {
@@ -2819,7 +2837,7 @@ struct LzShape {
     uint32_t tiled, npx, width, stride;
     uint32_t pad;        // never-matching words in front of every tile's packed pixels (>= 2^distance)
     uint32_t px_stride;  // words per tile in the packed-pixel array: pad + segments * kLzSeg + 32 * kLzAhead
-    TileGeom g;
+    TileSel sel;         // tiled == 1: which tiles (the whole grid, or the tiles of one shape)
 };
 
 __device__ __forceinline__ void lz_dims(const LzShape& sh, uint64_t tile, uint32_t& npx, uint32_t& width) {
@@ -2828,8 +2846,9 @@ __device__ __forceinline__ void lz_dims(const LzShape& sh, uint64_t tile, uint32
         width = sh.width;
         return;
     }
-    uint32_t x0, y0, tw, th;
-    tile_rect(sh.g, (uint32_t)(tile % sh.g.tiles_per_image), x0, y0, tw, th);
+    uint64_t image;
+    uint32_t in_image, x0, y0, tw, th;
+    sel_tile(sh.sel, tile, image, in_image, x0, y0, tw, th);
     npx = tw * th;
     width = tw;
 }
@@ -2854,12 +2873,13 @@ __global__ void __launch_bounds__(256) k_lz_pack(const uint8_t* __restrict__ rgb
         }
         return;
     }
-    uint32_t x0, y0, tw, th;
-    tile_rect(sh.g, (uint32_t)(tile % sh.g.tiles_per_image), x0, y0, tw, th);
-    const uint8_t* img = rgb + (tile / sh.g.tiles_per_image) * (uint64_t)sh.g.width * sh.g.height * 3u;
+    uint64_t image;
+    uint32_t in_image, x0, y0, tw, th;
+    sel_tile(sh.sel, tile, image, in_image, x0, y0, tw, th);
+    const uint8_t* img = rgb + image * (uint64_t)sh.sel.g.width * sh.sel.g.height * 3u;
     for (uint32_t i = threadIdx.x; i < tw * th; i += blockDim.x) {
         const uint32_t x = i % tw, y = i / tw;
-        const uint8_t* p = img + ((uint64_t)(y0 + y) * sh.g.width + x0 + x) * 3u;
+        const uint8_t* p = img + ((uint64_t)(y0 + y) * sh.sel.g.width + x0 + x) * 3u;
         dst[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
     }
 }
@@ -3233,14 +3253,16 @@ __global__ void k_channel_picker(const uint8_t* __restrict__ src, uint64_t n_px,
 // =================================================================================================
 // planes8[(t * per8 + k) * npx]: k = 0 green, and (per8 == 3, cruncher mode > 2: choh.cpp:263-290) 1 red, 2 blue;
 // planes9[(t * 2 + k) * npx]: R - G + 256, B - G + 256 (channel.hpp:73-79).  One CTA per tile, uniform tiles.
-__global__ void __launch_bounds__(256) k_tile_planes(const uint8_t* __restrict__ rgb, TileGeom g, uint64_t first_tile,
-                                                     uint32_t per8, uint16_t* __restrict__ planes8,
+__global__ void __launch_bounds__(256) k_tile_planes(const uint8_t* __restrict__ rgb, TileSel sel, uint32_t per8,
+                                                     uint16_t* __restrict__ planes8,
                                                      uint16_t* __restrict__ planes9) {
-    const uint64_t lt = blockIdx.x, t = first_tile + lt;
-    uint32_t x0, y0, tw, th;
-    tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
+    const uint64_t lt = blockIdx.x;
+    uint64_t image;
+    uint32_t in_image, x0, y0, tw, th;
+    sel_tile(sel, lt, image, in_image, x0, y0, tw, th);
+    const TileGeom& g = sel.g;
     const uint32_t npx = tw * th;
-    const uint8_t* img = rgb + (t / g.tiles_per_image) * (uint64_t)g.width * g.height * 3u;
+    const uint8_t* img = rgb + image * (uint64_t)g.width * g.height * 3u;
     uint16_t* p8 = planes8 + lt * per8 * (uint64_t)npx;
     uint16_t* p9 = planes9 + lt * 2u * (uint64_t)npx;
     for (uint32_t i = threadIdx.x; i < npx; i += blockDim.x) {
@@ -3260,7 +3282,7 @@ __global__ void __launch_bounds__(256) k_tile_planes(const uint8_t* __restrict__
 constexpr uint32_t kTileGrey = 1u, kTilePalette = 2u;  // = HOH_TILE_GREY, HOH_TILE_PALETTE
 
 // choh.cpp:295-327 (without the palette competitor) + sizes of what :328-363 emits.  One thread per tile.
-__global__ void k_tile_decide(uint64_t n_tiles, uint64_t first_tile, uint32_t per8,
+__global__ void k_tile_decide(uint64_t n_tiles, TileSel sel, uint64_t first_image, uint32_t per8,
                               const hoh_stream_result* __restrict__ res8, const hoh_stream_result* __restrict__ res9,
                               const uint32_t* __restrict__ lz_size, const int32_t* __restrict__ lz_status,
                               const uint32_t* __restrict__ info, hoh_tile_result* __restrict__ tiles) {
@@ -3289,7 +3311,10 @@ __global__ void k_tile_decide(uint64_t n_tiles, uint64_t first_tile, uint32_t pe
     tr.size = 3u + tr.lz_size + 1u + hohfmt::varint_len(tr.chan_size[0]) + hohfmt::varint_len(tr.chan_size[1]) + tr.chan_size[0] +
               tr.chan_size[1] + tr.chan_size[2];
     tr.start = 0;
-    tiles[first_tile + lt] = tr;
+    uint64_t image;
+    uint32_t in_image, x0, y0, tw, th;
+    sel_tile(sel, lt, image, in_image, x0, y0, tw, th);
+    tiles[(first_image + image) * sel.g.tiles_per_image + in_image] = tr;
 }
 
 // off[first + i + 1] = off[first] + sizes of tiles first .. first + i.  One CTA of 1024 threads.
@@ -3338,7 +3363,7 @@ __device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint3
 }
 
 // choh.cpp:112-116, 328-363: 00 00 | colour mode | LZ record | 0x24 | varint(size 1) varint(size 2) | channels.
-__global__ void __launch_bounds__(256) k_tile_emit(uint64_t first_tile, uint32_t per8,
+__global__ void __launch_bounds__(256) k_tile_emit(TileSel sel, uint64_t first_image, uint32_t per8,
                                                    const hoh_stream_result* __restrict__ res8,
                                                    const hoh_stream_result* __restrict__ res9,
                                                    const uint8_t* __restrict__ out8, const uint8_t* __restrict__ out9,
@@ -3346,7 +3371,10 @@ __global__ void __launch_bounds__(256) k_tile_emit(uint64_t first_tile, uint32_t
                                                    hoh_tile_result* __restrict__ tiles, uint8_t* __restrict__ packed,
                                                    uint64_t packed_cap) {
     const uint64_t lt = blockIdx.x;
-    hoh_tile_result& tr = tiles[first_tile + lt];
+    uint64_t image;
+    uint32_t in_image, x0, y0, tw, th;
+    sel_tile(sel, lt, image, in_image, x0, y0, tw, th);
+    hoh_tile_result& tr = tiles[(first_image + image) * sel.g.tiles_per_image + in_image];
     if (tr.start + tr.size > packed_cap) {
         if (threadIdx.x == 0 && !tr.status) tr.status = HOH_S_OVERFLOW;
         return;
@@ -3401,15 +3429,19 @@ struct DPlane {
 };
 
 // tile header: 00 00 | colour mode | LZ tag
-__global__ void k_dt_begin(uint64_t n_tiles, const uint8_t* __restrict__ packed, uint64_t packed_bytes,
-                           const uint64_t* __restrict__ tile_off, uint32_t side_stride, DTile* __restrict__ tiles,
-                           hoh_dec_stream* __restrict__ streams) {
+__global__ void k_dt_begin(uint64_t n_tiles, TileSel sel, uint64_t first_image, const uint8_t* __restrict__ packed,
+                           uint64_t packed_bytes, const uint64_t* __restrict__ tile_off, uint32_t side_stride,
+                           DTile* __restrict__ tiles, hoh_dec_stream* __restrict__ streams) {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     const ByteView b{packed, packed_bytes};
-    const uint64_t off = tile_off[t];
+    uint64_t image;
+    uint32_t in_image, x0, y0, tw, th;
+    sel_tile(sel, t, image, in_image, x0, y0, tw, th);
+    const uint64_t gt = (first_image + image) * sel.g.tiles_per_image + in_image;  // the tile's index in the batch
+    const uint64_t off = tile_off[gt];
     DTile d;
-    d.end = tile_off[t + 1];
+    d.end = tile_off[gt + 1];
     d.status = HOH_S_OK;
     d.colour_mode = b[off + 2];
     // 1x1 sub-tiles (choh.cpp:112-116), a colour mode this library emits, the LZ tag find_lz_rgb writes (lz.hpp:100)
@@ -3695,19 +3727,21 @@ __global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, i
 }
 
 // planes -> interleaved RGB in the image (inverse of channel.hpp:73-79 for colour mode 128, D4), tile status
-__global__ void __launch_bounds__(256) k_dt_store(TileGeom g, uint64_t first_tile, uint32_t plane_stride,
+__global__ void __launch_bounds__(256) k_dt_store(TileSel sel, uint64_t first_image, uint32_t plane_stride,
                                                   const DTile* __restrict__ tiles,
                                                   const int32_t* __restrict__ plane_status,
                                                   const uint16_t* __restrict__ planes, uint8_t* __restrict__ rgb,
                                                   int32_t* __restrict__ status) {
-    const uint64_t lt = blockIdx.x, t = first_tile + lt;
+    const uint64_t lt = blockIdx.x;
+    uint64_t image;
+    uint32_t in_image, x0, y0, tw, th;
+    sel_tile(sel, lt, image, in_image, x0, y0, tw, th);
+    const TileGeom& g = sel.g;
     int32_t st = tiles[lt].status;
     for (int c = 0; c < 3; c++) st = st ? st : plane_status[lt * 3u + c];
-    if (threadIdx.x == 0) status[t] = st;
+    if (threadIdx.x == 0) status[(first_image + image) * g.tiles_per_image + in_image] = st;
     if (st) return;
-    uint32_t x0, y0, tw, th;
-    tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
-    uint8_t* img = rgb + (t / g.tiles_per_image) * (uint64_t)g.width * g.height * 3u;
+    uint8_t* img = rgb + (first_image + image) * (uint64_t)g.width * g.height * 3u;
     const uint16_t* a = planes + (lt * 3u) * (uint64_t)plane_stride;
     const uint16_t* b = a + plane_stride;
     const uint16_t* c = b + plane_stride;

@@ -301,9 +301,10 @@ typedef struct hoh_tile_result {
  * and the emission of the tile's bytes (header 00 00, colour mode, LZ record, channel-order byte, size varints,
  * channels).  Tile t = image * tiles_per_image + tile occupies d_packed[d_tile_off[t], d_tile_off[t+1]).
  * The host keeps only the file header and the tile offset table (choh.cpp:436-506).  Tiles the reference would
- * code in greyscale / indexed mode are flagged (they still get their sub-green bytes).  Tilings with unequal
- * tiles (width or height not a multiple of the tile count) return HOH_E_UNSUPPORTED.  Large batches are
- * processed in chunks of whole images sized by an internal scratch budget. */
+ * code in greyscale / indexed mode are flagged (they still get their sub-green bytes).  Image sizes whose last
+ * tile column / row is narrower than the others (choh.cpp:459-474) are handled one tile shape at a time.  Large
+ * batches are processed in chunks of whole images sized by an internal scratch budget (32 GB, or the
+ * HOH_SCRATCH_GB environment variable). */
 int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
                       int mode, unsigned flags /* 0 or HOH_FIX_ENCODER */, uint8_t* d_packed, size_t packed_cap, uint64_t* d_tile_off,
                       hoh_tile_result* d_tiles);

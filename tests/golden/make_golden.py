@@ -165,9 +165,27 @@ def lz_cases():
     print("lz.npz", k, "cases")
 
 
+def unequal_tile_files():
+    """Whole `choh` files for image sizes whose tile grid has unequal tiles (choh.cpp:459-474): size + md5."""
+    keys, sizes, md5s = [], [], []
+    with tempfile.TemporaryDirectory() as td:
+        for (w, h, mode) in [(601, 523, 0), (601, 523, 2), (1000, 700, 0), (530, 300, 1)]:
+            rgb = ol.synth_rgb(w, h, 1)
+            ip, op = os.path.join(td, "i.rgb"), os.path.join(td, "o.hoh")
+            rgb.tofile(ip)
+            ol.ref().ref_choh_main(ip.encode(), op.encode(), w, h, mode)
+            data = open(op, "rb").read()
+            keys.append(f"{w}x{h}_s{mode}")
+            sizes.append(len(data))
+            md5s.append(hashlib.md5(data).hexdigest())
+    np.savez_compressed(os.path.join(HERE, "files_unequal_tiles.npz"), files_keys=np.array(keys),
+                        files_size=np.array(sizes, np.int64), files_md5=np.array(md5s))
+
+
 if __name__ == "__main__":
     assert ol.have_ref(), "needs /root/reference (development container)"
     entropy_cases()
     predict_cases()
     layer_and_tile_cases()
     lz_cases()
+    unequal_tile_files()

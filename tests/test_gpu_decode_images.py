@@ -115,3 +115,16 @@ def test_reference_bytes_of_flat_and_matchless_images_decode():
     back, st = g.decode_images(tiles, 2, w, h)
     assert (st == 0).all(), st
     assert np.array_equal(back, rgb)
+
+
+@pytest.mark.parametrize("w,h,mode,n", [(601, 523, 0, 3), (601, 523, 2, 2), (1000, 700, 1, 2), (530, 300, 4, 2)])
+def test_roundtrip_unequal_tiles(w, h, mode, n):
+    """Tile grids with up to four tile shapes, batches of several images."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(w + mode)
+    rgb = _images(rng, w, h, n, 1200 + mode, mode)
+    tiles, rec = g.encode_images(rgb, n, w, h, mode, FIX_STALE)
+    assert (rec["status"] == 0).all()
+    back, st = g.decode_images(tiles, n, w, h)
+    assert (st == 0).all(), st
+    assert np.array_equal(back, rgb)

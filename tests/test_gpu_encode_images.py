@@ -91,3 +91,20 @@ def test_flags_for_grey_and_palette_tiles():
     pal = rng.integers(0, 256, (10, 3)).astype(np.uint8)[rng.integers(0, 10, (h, w))]
     tiles, rec = g.encode_images(np.concatenate([photo.ravel(), grey.ravel(), pal.ravel()]), 3, w, h, 0)
     assert list(rec["flags"]) == [0, 3, 2]  # a grey 8-bit tile also has at most 256 colours
+
+
+@pytest.mark.parametrize("key", ["601x523_s0", "601x523_s2", "1000x700_s0", "530x300_s1"])
+def test_whole_choh_file_md5_unequal_tiles(key):
+    """Image sizes whose tile grid has unequal tiles (the last column / row takes what is left, choh.cpp:459-474:
+    601x523 has four tile shapes): stock `choh` files by size and md5."""
+    g = gpu_lib.gpu()
+    z = np.load(os.path.join(G, "files_unequal_tiles.npz"))
+    i = list(z["files_keys"]).index(key)
+    dims, mode = key.split("_s")
+    w, h = (int(v) for v in dims.split("x"))
+    tiles, rec = g.encode_images(ol.synth_rgb(w, h, 1), 1, w, h, int(mode))
+    assert (rec["status"] == 0).all()
+    geo = g.tile_geometry(w, h)
+    data, printed = _container().assemble_file(w, h, geo.x_tiles, geo.y_tiles, tiles)
+    assert len(data) == int(z["files_size"][i])
+    assert hashlib.md5(data).hexdigest() == str(z["files_md5"][i])
