@@ -3421,6 +3421,7 @@ struct DTile {
 
 struct DPlane {
     uint64_t main_off;    // where the residual stream's header starts (set after the index stream is decoded)
+    uint64_t chan_end;    // one past the channel's last byte: the residual stream must end exactly there
     uint32_t kind;        // 0: single predictor 0x0010 = pure MED (fastpath inverse); 1: predictor grid
     uint32_t depth;       // 8 or 9
     uint32_t n_masks;
@@ -3530,6 +3531,7 @@ __global__ void k_dt_channels(uint64_t n_tiles, const uint8_t* __restrict__ pack
         pl.depth = (c == 0u || d.colour_mode == 2u) ? 8u : 9u;  // sub-green differences are 9-bit (choh.cpp:240, 251; D4)
         pl.n_masks = 1;
         pl.main_off = 0;
+        pl.chan_end = d.status == HOH_S_OK ? chan[c + 1] : 0;
         for (int m = 0; m < 16; m++) pl.masks[m] = 0x0010;
         hoh_dec_stream st;
         st.in_off = d.cursor;
@@ -3663,7 +3665,9 @@ __global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, i
     const DTile& dt = tiles[p / 3u];
     int32_t st = pl.status ? pl.status : dt.status;
     if (!st) st = main_res[p].status;
-    if (!st && (main_res[p].n != dt.uncovered || main_res[p].range != (1u << pl.depth))) st = HOH_S_BAD_LAYER;
+    if (!st && (main_res[p].n != dt.uncovered || main_res[p].range != (1u << pl.depth) ||
+                main_res[p].end_off != pl.chan_end))  // channels follow one another without gaps (choh.cpp:355-363)
+        st = HOH_S_BAD_LAYER;
     plane_status[p] = st;
     if (st) return;
     const int c = 1 << pl.depth, half = c >> 1;
