@@ -317,8 +317,10 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
  * stream, LZ expansion into back-references, un-prediction (pure-MED inverse for the single-predictor header,
  * unpredict_all otherwise) with the copies of unprediction.hpp:63-65, colour inverse, tile scatter.
  * Tile t's bytes are d_packed[d_tile_off[t], d_tile_off[t+1]).  d_status[t] != 0: the tile could not be decoded
- * (its pixels are left untouched).  Channels the reference emitted under defect D7 (see HOH_FIX_STALE) decode
- * to wrong pixels without any error, exactly as they would with any conforming decoder. */
+ * (its pixels are left untouched).  Every stream has to end where the container says it ends, so truncated tiles
+ * and the channels the reference emits under defect D7 (a stale buffer cut to another candidate's length, see
+ * HOH_FIX_STALE) are reported rather than decoded to wrong pixels; flipped payload bytes are not detectable
+ * (rANS carries no checksum). */
 int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes, const uint64_t* d_tile_off,
                       size_t n_images, uint32_t width, uint32_t height, uint8_t* d_rgb, int32_t* d_status);
 
