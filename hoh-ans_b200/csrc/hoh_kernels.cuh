@@ -243,6 +243,129 @@ __device__ __forceinline__ void bits_or(uint32_t* words, uint32_t bit, uint32_t 
     if ((uint32_t)win) atomicOr(&words[k + 1u], (uint32_t)win);
 }
 
+// hohfmt::plan_head with the two clamp walks (entropy_encoding.hpp:53-122) done by the whole warp.  A walk visits
+// the symbols from one end, its field width is the running maximum of the width each frequency needs on the ladder
+// 0, 1, 4, 8, 12, ..., it stops at the first symbol whose running width reaches prob_bits, records where each rung
+// was first needed and adds up the running widths: a prefix maximum.  Every lane owns a contiguous run of symbols:
+// run maxima are combined by shuffles, each lane then walks its own run from the width it inherits.
+// Results in scratch as warp_build_head expects: [0] = bytes of varints + metadata, [1] = table mode,
+// [2] = stored-mode size, [3] = clamp count, [4 + j] = lo | hi << 16, [20 + k] = the head bytes.
+__device__ __forceinline__ uint32_t ladder_need(uint32_t v) {  // smallest ladder width w with v < 2^w
+    return v == 0u ? 0u : (v < 2u ? 1u : ((32u - (uint32_t)__clz((int)v) + 3u) & ~3u));
+}
+__device__ __forceinline__ uint32_t ladder_rung(uint32_t w) { return w == 0u ? 0u : (w == 1u ? 1u : w / 4u + 1u); }
+
+__device__ void warp_plan_head(const uint32_t* f, uint32_t range, uint32_t n, uint32_t prob_bits, uint32_t* scratch,
+                               uint32_t representable) {
+    const uint32_t lane = lane_id();
+    const uint32_t maxbits = hohfmt::bit_length(range - 1);
+    const uint32_t count = (prob_bits - 1u) / 4u + 2u;  // :51
+    const uint32_t per = (range + 31u) / 32u;
+    const uint32_t lo = min(lane * per, range), hi = min(lo + per, range);
+    uint32_t run_max = 0;
+    bool wide = false;  // a frequency that does not fit a maxbits-wide field (table mode 1, D6)
+    for (uint32_t i = lo; i < hi; i++) {
+        run_max = max(run_max, ladder_need(f[i]));
+        wide = wide || (f[i] >> maxbits) != 0u;
+    }
+    const bool any_wide = __any_sync(0xffffffffu, wide);
+    // inclusive maxima over the lanes up to / from this one, then the widths a lane inherits
+    uint32_t upto = run_max, from = run_max;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t b = __shfl_up_sync(0xffffffffu, upto, d), a = __shfl_down_sync(0xffffffffu, from, d);
+        if ((int)lane >= d) upto = max(upto, b);
+        if ((int)lane + d < 32) from = max(from, a);
+    }
+    uint32_t w_in_up = __shfl_up_sync(0xffffffffu, upto, 1), w_in_down = __shfl_down_sync(0xffffffffu, from, 1);
+    if (lane == 0) w_in_up = 0;
+    if (lane == 31) w_in_down = 0;
+    const uint32_t w_all = __shfl_sync(0xffffffffu, from, 0);  // the running width after a walk over every symbol
+    // pass 1: where does each walk stop, and the sum of the running widths before that
+    uint64_t bits_up = 0, bits_down = 0;
+    uint32_t stop_up = 0xffffffffu, stop_down = 0xffffffffu;
+    {
+        uint32_t w = w_in_up;
+        for (uint32_t i = lo; i < hi; i++) {
+            w = max(w, ladder_need(f[i]));
+            if (w >= prob_bits) {
+                stop_up = i;
+                break;
+            }
+            bits_up += w;
+        }
+        w = w_in_down;
+        for (uint32_t i = hi; i-- > lo;) {
+            w = max(w, ladder_need(f[i]));
+            if (w >= prob_bits) {
+                stop_down = i;
+                break;
+            }
+            bits_down += w;
+        }
+    }
+    const uint32_t found_up = __ballot_sync(0xffffffffu, stop_up != 0xffffffffu);
+    const uint32_t found_down = __ballot_sync(0xffffffffu, stop_down != 0xffffffffu);
+    const int lane_up = found_up ? __ffs((int)found_up) - 1 : 32;          // the ascending walk visits lanes <= lane_up
+    const int lane_down = found_down ? 31 - __clz((int)found_down) : -1;  // the descending walk visits lanes >= lane_down
+    const bool seen_up = (int)lane <= lane_up, seen_down = (int)lane >= lane_down;
+    uint64_t total = (seen_up ? bits_up : 0ull) + (seen_down ? bits_down : 0ull);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+    const uint32_t s_up = found_up ? __shfl_sync(0xffffffffu, stop_up, lane_up & 31) : range;       // :53-88 ends past the last symbol
+    const uint32_t s_down = found_down ? __shfl_sync(0xffffffffu, stop_down, lane_down & 31) : 0u;  // :90-120 ends on symbol 0
+    // pass 2: the marks — where each rung of the ladder was first needed — by the lanes the walks visited
+    if (lane < 16) scratch[4 + lane] = (range - 1u) | (0u << 16);  // unused: lo = range - 1, hi = 0
+    __syncwarp();
+    if (seen_up) {
+        uint32_t w = w_in_up;
+        for (uint32_t i = lo; i < hi; i++) {
+            const uint32_t need = ladder_need(f[i]);
+            if (need > w) {
+                for (uint32_t r = ladder_rung(w); r < ladder_rung(need) && r < count; r++)
+                    atomicAnd(&scratch[4 + r], 0xffff0000u), atomicOr(&scratch[4 + r], i);
+                w = need;
+            }
+            if (w >= prob_bits) break;
+        }
+    }
+    if (seen_down) {
+        uint32_t w = w_in_down;
+        for (uint32_t i = hi; i-- > lo;) {
+            const uint32_t need = ladder_need(f[i]);
+            if (need > w) {
+                for (uint32_t r = ladder_rung(w); r < ladder_rung(need) && r < count; r++)
+                    atomicOr(&scratch[4 + r], i << 16);
+                w = need;
+            }
+            if (w >= prob_bits) break;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint8_t tmp[8];
+        uint32_t at = 0;
+        at = hohfmt::put_varint(tmp, at, range - 1);
+        at = hohfmt::put_varint(tmp, at, n);
+        const uint32_t stored = at + 1 + (uint32_t)(((uint64_t)maxbits * n + 7) / 8);
+        const uint64_t raw_table_bytes = ((uint64_t)prob_bits * range + 7) / 8;  // :47
+        uint64_t clamped_bits = (uint64_t)((uint32_t)(2 * ((int)maxbits - 1)) * count) + 2ull * prob_bits;  // :48-49
+        clamped_bits += total + (found_up ? prob_bits : 0u) + (found_down ? prob_bits : 0u);
+        const uint32_t last_down = found_down ? prob_bits : w_all;
+        clamped_bits += (uint64_t)last_down * ((uint64_t)s_down - (uint64_t)s_up - 1ull);  // :121, size_t arithmetic: wraps
+        const uint64_t clamped_bytes = (clamped_bits + 7) / 8;
+        uint32_t mode = raw_table_bytes < clamped_bytes ? 1u : 2u;  // :135 / :148
+        if (representable && mode == 1u && any_wide) mode = 2u;
+        tmp[at++] = (uint8_t)((1u << 7) + (prob_bits << 2) + mode);
+        scratch[0] = at;
+        scratch[1] = mode;
+        scratch[2] = stored;
+        scratch[3] = count;
+        for (uint32_t k = 0; k < 8; k++) scratch[20 + k] = tmp[k];
+    }
+    __syncwarp();
+}
+
 __device__ uint32_t warp_build_head(const uint32_t* f, uint32_t range, uint32_t n, uint32_t prob_bits,
                                     uint8_t* buf, uint32_t* scratch /* >= 40 words */, uint32_t* stored_size,
                                     uint32_t representable = 0) {
@@ -250,18 +373,7 @@ __device__ uint32_t warp_build_head(const uint32_t* f, uint32_t range, uint32_t 
     uint32_t* words = reinterpret_cast<uint32_t*>(buf);
     const uint32_t maxbits = hohfmt::bit_length(range - 1);
     // scratch: [0] = bytes of varints+metadata, [1] = mode, [2] = stored size, [3] = clamp count, [4..] = lo/hi
-    if (lane == 0) {
-        hohfmt::ClampSet cs;
-        uint32_t mode, st;
-        uint8_t tmp[8];
-        const uint32_t at = hohfmt::plan_head(f, range, n, prob_bits, tmp, &st, &cs, &mode, representable);
-        scratch[0] = at;
-        scratch[1] = mode;
-        scratch[2] = st;
-        scratch[3] = cs.count;
-        for (uint32_t j = 0; j < 16; j++) scratch[4 + j] = (uint32_t)cs.lo[j] | ((uint32_t)cs.hi[j] << 16);
-        for (uint32_t k = 0; k < 8; k++) scratch[20 + k] = tmp[k];
-    }
+    warp_plan_head(f, range, n, prob_bits, scratch, representable);
     for (uint32_t k = lane; k < HOH_HEAD_CAP / 4; k += 32) words[k] = 0u;
     __syncwarp();
     const uint32_t at = scratch[0], mode = scratch[1], count = scratch[3];
