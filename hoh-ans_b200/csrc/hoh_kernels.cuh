@@ -1693,10 +1693,28 @@ __global__ void __launch_bounds__(256) k_gather_streams(const hoh_stream_result*
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~3ull);
     const uint32_t sh = (uint32_t)(sa & 3ull) * 8u;
     uint32_t* dw = reinterpret_cast<uint32_t*>(d + lead);
+    // four independent words per thread and trip: the copy is bound by bytes in flight, not by instructions
+    uint32_t i = threadIdx.x;
     if (sh == 0) {
-        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dw[i] = sw[i];
+        for (; i + 3u * blockDim.x < words; i += 4u * blockDim.x) {
+            const uint32_t a = sw[i], b = sw[i + blockDim.x], c = sw[i + 2u * blockDim.x], e = sw[i + 3u * blockDim.x];
+            dw[i] = a;
+            dw[i + blockDim.x] = b;
+            dw[i + 2u * blockDim.x] = c;
+            dw[i + 3u * blockDim.x] = e;
+        }
+        for (; i < words; i += blockDim.x) dw[i] = sw[i];
     } else {
-        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dw[i] = __funnelshift_r(sw[i], sw[i + 1], sh);
+        for (; i + 3u * blockDim.x < words; i += 4u * blockDim.x) {
+            const uint32_t a0 = sw[i], a1 = sw[i + 1u], b0 = sw[i + blockDim.x], b1 = sw[i + blockDim.x + 1u];
+            const uint32_t c0 = sw[i + 2u * blockDim.x], c1 = sw[i + 2u * blockDim.x + 1u];
+            const uint32_t e0 = sw[i + 3u * blockDim.x], e1 = sw[i + 3u * blockDim.x + 1u];
+            dw[i] = __funnelshift_r(a0, a1, sh);
+            dw[i + blockDim.x] = __funnelshift_r(b0, b1, sh);
+            dw[i + 2u * blockDim.x] = __funnelshift_r(c0, c1, sh);
+            dw[i + 3u * blockDim.x] = __funnelshift_r(e0, e1, sh);
+        }
+        for (; i < words; i += blockDim.x) dw[i] = __funnelshift_r(sw[i], sw[i + 1], sh);
     }
     const uint32_t done = lead + words * 4u;
     if (threadIdx.x < r.size - done) d[done + threadIdx.x] = s[done + threadIdx.x];
