@@ -3788,7 +3788,7 @@ __global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, i
                                                      const uint16_t* __restrict__ maps,
                                                      const uint16_t* __restrict__ backref, uint16_t* __restrict__ out,
                                                      uint16_t* __restrict__ top_s, uint8_t* __restrict__ bp_s,
-                                                     int32_t* __restrict__ plane_status) {
+                                                     int32_t* __restrict__ plane_status, uint32_t only_kind0) {
     const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (p >= n_planes) return;
     const DPlane pl = planes[p];
@@ -3798,6 +3798,7 @@ __global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, i
     if (!st && (main_res[p].n != dt.uncovered || main_res[p].range != (1u << pl.depth) ||
                 main_res[p].end_off != pl.chan_end))  // channels follow one another without gaps (choh.cpp:355-363)
         st = HOH_S_BAD_LAYER;
+    if (only_kind0 && pl.kind != 0u) return;  // predictor-grid planes are walked by k_dt_unpredict16
     plane_status[p] = st;
     if (st) return;
     const int c = 1 << pl.depth, half = c >> 1;
@@ -3857,6 +3858,134 @@ __global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, i
             bp[x] = (uint8_t)nb;
             bp_left = nb;
         }
+    }
+}
+
+// The same un-prediction with the 16 candidate predictors of a pixel spread over 16 lanes: a half-warp per plane.
+// The walk stays serial per plane (H4), but what one thread did in ~200 dependent instructions per pixel — 16
+// candidates, 16 errors, a 16-way masked argmin, two 16-way selects — becomes one candidate and one error per
+// lane, two shuffles for the prediction and a 4-step shuffle minimum for the best predictor.  The row above
+// and its best predictors live in shared memory (w * 3 bytes per plane); lane 0 of the half-warp owns all
+// stores.  Planes under the single-predictor header (kind 0) are walked by lane 0 alone.
+constexpr int kUp16Planes = 8;  // planes (half-warps) per CTA
+
+__global__ void __launch_bounds__(kUp16Planes * 16) k_dt_unpredict16(
+    uint64_t n_planes, int w, int h, int x_tiles, int y_tiles, uint32_t plane_stride, const DPlane* __restrict__ planes,
+    const DTile* __restrict__ tiles, const hoh_dec_result* __restrict__ main_res, const uint16_t* __restrict__ resid,
+    const uint16_t* __restrict__ maps, const uint16_t* __restrict__ backref, uint16_t* __restrict__ out,
+    int32_t* __restrict__ plane_status) {
+    extern __shared__ __align__(16) uint8_t up_smem[];
+    const uint32_t hw = threadIdx.x >> 4, j = threadIdx.x & 15u;
+    const int w_pad = (w + 1) & ~1;
+    uint16_t* top = reinterpret_cast<uint16_t*>(up_smem + (size_t)hw * w_pad * 3);
+    uint8_t* bp = up_smem + (size_t)hw * w_pad * 3 + (size_t)w_pad * 2;
+    const uint64_t p = (uint64_t)blockIdx.x * kUp16Planes + hw;
+    // The two half-warps of a warp walk their planes in lockstep (same w, h: same trip counts) so that every
+    // shuffle is one full-warp instruction; a half without a plane to decode runs along and stores nothing.
+    bool alive = p < n_planes;
+    DPlane pl;
+    pl.kind = 0;
+    pl.depth = 8;
+    if (alive) {
+        pl = planes[p];
+        const DTile& dt = tiles[p / 3u];
+        int32_t st = pl.status ? pl.status : dt.status;
+        if (!st) st = main_res[p].status;
+        if (!st && (main_res[p].n != dt.uncovered || main_res[p].range != (1u << pl.depth) ||
+                    main_res[p].end_off != pl.chan_end))  // channels follow one another without gaps (choh.cpp:355-363)
+            st = HOH_S_BAD_LAYER;
+        if (pl.kind == 1u && j == 0) plane_status[p] = st;  // kind 0 planes belong to k_dt_unpredict
+        alive = st == 0 && pl.kind == 1u;
+    }
+    if (__ballot_sync(0xffffffffu, alive) == 0u) return;
+    const uint64_t q = alive ? p : 0;  // a plane index that is safe to read from
+    const int c = 1 << pl.depth, half = c >> 1;
+    const uint16_t* src = resid + q * (uint64_t)plane_stride;
+    const uint16_t* br = backref + (q / 3u) * (uint64_t)plane_stride;
+    uint16_t* dst = out + q * (uint64_t)plane_stride;
+    // my candidate (prediction.hpp:190-207) = type(A, B, C) with the operands picked from (L, T, TL, TR) = 0..3:
+    //   j        0  1  2  3 | 4            | 5       6        7        8        | 9               | 10 .. 15
+    //   type     the operand | med-grad     | midpoint                            | paeth           | average of three
+    //   A B C    L  T TL TR  | T L TL       | L,T     L,TL     TL,T     T,TR     | L TL T          | L L TL / L TL TL / TL TL T / TL T T / T T TR / T TR TR
+    // The four neighbours are 16-bit values packed in two registers (L | T << 16, TL | TR << 16); an operand is one
+    // byte-permute with a per-lane selector (0x4410 + 0x22 * code puts halfword `code` in the low half) and a mask.
+    const uint32_t type = j < 4u ? 0u : (j == 4u ? 3u : (j < 9u ? 1u : (j == 9u ? 4u : 2u)));
+    const uint32_t sel_a = 0x4410u + 0x22u * ((0x5a0181e4u >> (2u * j)) & 3u);
+    const uint32_t sel_b = 0x4410u + 0x22u * ((0xd68b6400u >> (2u * j)) & 3u);
+    const uint32_t sel_c = 0x4410u + 0x22u * ((0xf5a40200u >> (2u * j)) & 3u);
+    const bool is_id = type == 0u, is_mid = type == 1u, is_med = type == 3u, is_paeth = type == 4u;
+    const int tw = (w + x_tiles - 1) / x_tiles, th = (h + y_tiles - 1) / y_tiles;
+    const uint16_t* tmap = maps + q * (uint64_t)x_tiles * y_tiles;
+    for (int i = (int)j; i < w; i += 16) {
+        top[i] = (uint16_t)half;
+        bp[i] = 4;
+    }
+    __syncwarp();
+    const bool writer = alive && j == 0u;
+    const int bias = -c - half;
+    const uint32_t cmask = (uint32_t)(c - 1);
+    const int err_cap = 2 * c;
+    const uint16_t* br_p = br;
+    uint16_t* dst_p = dst;
+    const uint16_t* src_p = src;
+    const uint16_t* src_end = src + (size_t)w * h;
+    for (int y = 0; y < h; y++) {  // the walk of k_raster_walk<true>
+        int left = half, left_top = half;
+        int bp_left = bp[w - 1];
+        const bool last_row = y + 1 >= h;
+        const uint16_t* mrow = tmap + (size_t)((y + 1) / th) * x_tiles;
+        int first_of_row = 0;
+        int t = top[0];
+        int in_cell = tw;
+        uint32_t mask = 0, my_bit = 0;
+        for (int x = 0; x < w; x++) {
+            if (in_cell == tw) {  // next grid cell of the row below: its mask picks this pixel's best predictor
+                in_cell = 0;
+                mask = (last_row || !alive) ? 0u : *mrow++;
+                my_bit = (mask >> j) & 1u;
+            }
+            in_cell++;
+            const bool last_col = x + 1 >= w;
+            const int t_next = last_col ? 0 : top[x + 1];
+            const int tr = last_col ? (w > 1 ? first_of_row : t) : t_next;
+            const int bp_top = bp[x];
+            const uint32_t brv = alive ? *br_p : 0u;
+            br_p++;
+            const int rv = (alive && src_p < src_end) ? (int)*src_p : 0;
+            src_p += brv ? 0 : 1;
+            const uint32_t lo = (uint32_t)left | ((uint32_t)t << 16), hi2 = (uint32_t)left_top | ((uint32_t)tr << 16);
+            const int A = (int)(__byte_perm(lo, hi2, sel_a) & 0xffffu), B = (int)(__byte_perm(lo, hi2, sel_b) & 0xffffu),
+                      C = (int)(__byte_perm(lo, hi2, sel_c) & 0xffffu);
+            const int mid = p_mid(A, B), avg = p_avg3(A, B, C), med = p_med_grad(A, B, C), pae = p_paeth(A, B, C);
+            int cand = is_id ? A : (is_mid ? mid : avg);
+            cand = is_med ? med : cand;
+            cand = is_paeth ? pae : cand;
+            const int pa = __shfl_sync(0xffffffffu, cand, bp_top, 16), pb = __shfl_sync(0xffffffffu, cand, bp_left, 16);
+            // unprediction.hpp:63-65: an LZ-covered pixel is a copy; lane 0 wrote every earlier pixel of this plane
+            int copy = 0;
+            if (writer && brv) copy = (int)*(dst_p - brv);
+            copy = __shfl_sync(0xffffffffu, copy, 0, 16);
+            const uint32_t tval = (uint32_t)(rv + bias + p_mid(pa, pb)) & 0xffffu;  // :67
+            const int v = brv ? copy : (int)(tval & cmask);
+            // best predictor for the pixels below / to the right: lowest index among the smallest errors < 2c
+            const int err = abs(v - cand);
+            uint32_t key = (err < err_cap && my_bit) ? ((uint32_t)err << 4) | j : 0x7fffffffu;
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, d, 16));
+            const int nb = key == 0x7fffffffu ? 0 : (int)(key & 15u);  // (mask is 0 on the last row: nb = 0)
+            if (writer) *dst_p = (uint16_t)v;
+            dst_p++;
+            if (j == 0u) {
+                top[x] = (uint16_t)v;
+                bp[x] = (uint8_t)nb;
+            }
+            first_of_row = x == 0 ? v : first_of_row;
+            left_top = t;
+            left = v;
+            bp_left = nb;
+            t = t_next;
+        }
+        __syncwarp();  // lane 0's row of top / bp becomes visible to its half-warp
     }
 }
 
