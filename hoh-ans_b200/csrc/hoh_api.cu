@@ -1578,15 +1578,21 @@ int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes
             TRY(decode_common(ctx, streams, nt * 3, d_packed, packed_bytes, resid, res_b));
             k_dt_unlz<<<blocks_for(nt * 32, 128), 128, 0, ctx->stream>>>(nt, npx, g.plane_stride, lz_sym, side, tiles, backref);
             LAUNCHED("k_dt_unlz");
-            // single-predictor planes: one thread each (pure-MED inverse); predictor-grid planes: a half-warp each
+            // Predictor-grid planes: a half-warp each while the launch is bound by the length of one plane's walk
+            // (37 vs 55 ms for 5 760 planes), one thread each once there are enough planes to be bound by
+            // instruction throughput instead, where one lane per plane wastes nothing (162 vs 240 ms for 87 840);
+            // the measured crossover is near 20 000 planes.  Single-predictor planes always take one thread.
+            const bool wide_walk = nt * 3 <= 16384;
             k_dt_unpredict<<<blocks_for(nt * 3, 64), 64, 0, ctx->stream>>>(nt * 3, tw, th, (int)xt, (int)yt, g.plane_stride,
                                                                            planes, tiles, res_b, resid, maps, backref, out,
-                                                                           top, bp, pstatus, 1u);
+                                                                           top, bp, pstatus, wide_walk ? 1u : 0u);
             LAUNCHED("k_dt_unpredict");
-            k_dt_unpredict16<<<blocks_for(nt * 3, kUp16Planes), kUp16Planes * 16, (size_t)kUp16Planes * ((tw + 1) & ~1) * 3,
-                               ctx->stream>>>(nt * 3, tw, th, (int)xt, (int)yt, g.plane_stride, planes, tiles, res_b, resid, maps,
-                                              backref, out, pstatus);
-            LAUNCHED("k_dt_unpredict16");
+            if (wide_walk) {
+                k_dt_unpredict16<<<blocks_for(nt * 3, kUp16Planes), kUp16Planes * 16,
+                                   (size_t)kUp16Planes * ((tw + 1) & ~1) * 3, ctx->stream>>>(
+                    nt * 3, tw, th, (int)xt, (int)yt, g.plane_stride, planes, tiles, res_b, resid, maps, backref, out, pstatus);
+                LAUNCHED("k_dt_unpredict16");
+            }
             k_dt_store<<<(unsigned)nt, 256, 0, ctx->stream>>>(sel, img0, g.plane_stride, tiles, pstatus, out, d_rgb, d_status);
             LAUNCHED("k_dt_store");
         }

@@ -164,3 +164,17 @@ def test_decoder_survives_random_damage():
         # truncations are always noticed (a stream or channel no longer ends where the tile says); flipped payload
         # bytes are not: rANS carries no checksum
         assert all(st[i] != 0 for i in bad if i % 4 == 2)
+
+
+def test_roundtrip_many_small_tiles():
+    """6 000 tiles = 18 000 planes in one call: above the plane count at which the decoder switches from the
+    half-warp un-prediction walk to one thread per plane."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(8)
+    w, h, n = 64, 48, 6000
+    base = [ol.photo_with_repeats(rng, w, h, 3000 + i) for i in range(40)]
+    rgb = np.concatenate([base[i % 40].ravel() for i in range(n)])
+    tiles, rec = g.encode_images(rgb, n, w, h, 2, FIX_STALE)
+    assert (rec["status"] == 0).all()
+    back, st = g.decode_images(tiles, n, w, h)
+    assert (st == 0).all() and np.array_equal(back, rgb)
