@@ -1784,15 +1784,19 @@ __global__ void k_add_green(const uint16_t* __restrict__ g, const uint16_t* __re
 __global__ void k_predict_fastpath(const uint16_t* __restrict__ planes, uint64_t n_planes, int w, int h,
                                    int depth, uint16_t* __restrict__ resid, uint64_t out_stride) {
     const int c = 1 << depth, half = c >> 1;
-    const uint64_t per = (uint64_t)w * h, total = per * n_planes;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t at = i % per;
-        const int x = (int)(at % w), y = (int)(at / w);
-        const uint16_t* p = planes + i;
-        const int L = x ? p[-1] : half;
-        const int T = y ? p[-w] : half;
-        const int TL = (x && y) ? p[-w - 1] : half;
-        resid[(i / per) * out_stride + at] = (uint16_t)(((int)p[0] - p_med_grad(T, L, TL) + half + c) % c);
+    // grid-stride over (plane, row): a CTA takes whole rows, so the only divisions are per row
+    const uint64_t rows = n_planes * (uint64_t)h;
+    for (uint64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const uint64_t pl = row / (uint32_t)h;
+        const int y = (int)(row % (uint32_t)h);
+        const uint16_t* p = planes + pl * (uint64_t)w * h + (uint64_t)y * w;
+        uint16_t* o = resid + pl * out_stride + (uint64_t)y * w;
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            const int L = x ? p[x - 1] : half;
+            const int T = y ? p[x - w] : half;
+            const int TL = (x && y) ? p[x - w - 1] : half;
+            o[x] = (uint16_t)(((int)p[x] - p_med_grad(T, L, TL) + half + c) & (c - 1));  // numerator >= 0: % c == & (c - 1)
+        }
     }
 }
 
@@ -1910,6 +1914,24 @@ __device__ __forceinline__ int pick_best(int v, const Cand& k, uint32_t mask, in
     return best;
 }
 
+// pick_best for a walk that keeps the same mask for a whole grid cell: the mask is folded once per cell into 16
+// additive biases (j for an allowed candidate, j + 2^30 for a forbidden one), after which a candidate costs a
+// subtract, an absolute value, a multiply-add and a minimum.  Same answer as pick_best: smallest error, lowest
+// index among equals, 0 when no allowed candidate has an error below 2c.
+struct MaskBias {
+    int jb[16];
+};
+__device__ __forceinline__ void mask_bias(uint32_t mask, MaskBias& m) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) m.jb[j] = ((mask >> j) & 1u) ? j : (0x40000000 | j);
+}
+__device__ __forceinline__ int pick_best_biased(int v, const Cand& k, const MaskBias& m, int c) {
+    int key = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 16; j++) key = min(key, abs(v - k.v[j]) * 16 + m.jb[j]);
+    return (key >> 4) < 2 * c ? (key & 15) : 0;
+}
+
 // state per plane in global scratch: top[w] u16 followed by bp[w] u8
 template <bool INVERSE>
 __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__ in, uint64_t n_planes, int w,
@@ -1940,7 +1962,14 @@ __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__
         const bool last_row = y + 1 >= h;
         const uint16_t* mrow = tmap + (size_t)((y + 1) / th) * x_tiles;
         int first_of_row = 0;
+        MaskBias mb;
+        int in_cell = tw;
         for (int x = 0; x < w; x++) {
+            if (in_cell == tw) {  // a new grid cell of the row below: fold its mask once
+                in_cell = 0;
+                mask_bias(last_row ? 0u : *mrow++, mb);
+            }
+            in_cell++;
             const uint64_t at = (uint64_t)y * w + x;
             // TR of the last column = top[0], which already holds this row's first pixel
             const int tr = (x + 1 < w) ? top[x + 1] : (w > 1 ? first_of_row : top[0]);
@@ -1958,14 +1987,14 @@ __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__
                 dst[at] = (uint16_t)v;
             } else {
                 const uint32_t tval = (uint32_t)((int)src[next_resid++] - c - half + pred) & 0xffffu;  // :67
-                v = (int)(tval % (uint32_t)c);
+                v = (int)(tval & (uint32_t)(c - 1));  // % c, c a power of two
                 dst[at] = (uint16_t)v;
             }
             if (x == 0) first_of_row = v;
             left_top = t;
             top[x] = (uint16_t)v;
             left = v;
-            const int nb = last_row ? 0 : pick_best(v, k, mrow[x / tw], c);  // prediction.hpp:213-225
+            const int nb = last_row ? 0 : pick_best_biased(v, k, mb, c);  // prediction.hpp:213-225
             bp[x] = (uint8_t)nb;
             bp_left = nb;
         }
@@ -1998,11 +2027,12 @@ __global__ void __launch_bounds__(256) k_predict_all_best(const uint16_t* __rest
                                                           int h, int depth, int x_tiles, int y_tiles,
                                                           const uint16_t* __restrict__ tile_maps,
                                                           uint8_t* __restrict__ best) {
-    const uint64_t per = (uint64_t)w * h;
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= per * n_planes) return;
-    const uint64_t p = i / per;
-    const uint32_t at = (uint32_t)(i % per);
+    // blocks_per_plane consecutive CTAs share a plane: 32-bit index arithmetic only
+    const uint32_t per = (uint32_t)w * (uint32_t)h, bpp = (per + blockDim.x - 1u) / blockDim.x;
+    const uint64_t p = blockIdx.x / bpp;
+    const uint32_t at = (blockIdx.x % bpp) * blockDim.x + threadIdx.x;
+    if (p >= n_planes || at >= per) return;
+    const uint64_t i = p * per + at;
     const int x = (int)(at % (uint32_t)w), y = (int)(at / (uint32_t)w);
     if (y + 1 >= h) {
         best[i] = 0;
@@ -2020,11 +2050,10 @@ __global__ void __launch_bounds__(256) k_predict_all_best(const uint16_t* __rest
 __global__ void __launch_bounds__(256) k_predict_all_resid(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
                                                            int h, int depth, const uint8_t* __restrict__ best,
                                                            uint16_t* __restrict__ out, uint64_t out_stride) {
-    const uint64_t per = (uint64_t)w * h;
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= per * n_planes) return;
-    const uint64_t p = i / per;
-    const uint32_t at = (uint32_t)(i % per);
+    const uint32_t per = (uint32_t)w * (uint32_t)h, bpp = (per + blockDim.x - 1u) / blockDim.x;
+    const uint64_t p = blockIdx.x / bpp;
+    const uint32_t at = (blockIdx.x % bpp) * blockDim.x + threadIdx.x;
+    if (p >= n_planes || at >= per) return;
     const int x = (int)(at % (uint32_t)w), y = (int)(at / (uint32_t)w);
     const int c = 1 << depth, half = c >> 1;
     const uint16_t* src = planes + p * per;
@@ -3835,7 +3864,14 @@ __global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, i
         const bool last_row = y + 1 >= h;
         const uint16_t* mrow = tmap + (size_t)((y + 1) / th) * x_tiles;
         int first_of_row = 0;
+        MaskBias mb;
+        int in_cell = tw;
         for (int x = 0; x < w; x++) {
+            if (in_cell == tw) {
+                in_cell = 0;
+                mask_bias(last_row ? 0u : *mrow++, mb);
+            }
+            in_cell++;
             const uint64_t at = (uint64_t)y * w + x;
             const int tr = (x + 1 < w) ? top[x + 1] : (w > 1 ? first_of_row : top[0]);
             const int t = top[x];
@@ -3847,14 +3883,14 @@ __global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, i
                 v = dst[at - br[at]];  // unprediction.hpp:63-65
             } else {
                 const uint32_t tval = (uint32_t)((int)src[next_resid++] - c - half + pred) & 0xffffu;  // :67
-                v = (int)(tval % (uint32_t)c);
+                v = (int)(tval & (uint32_t)(c - 1));  // % c, c a power of two
             }
             dst[at] = (uint16_t)v;
             if (x == 0) first_of_row = v;
             left_top = t;
             top[x] = (uint16_t)v;
             left = v;
-            const int nb = last_row ? 0 : pick_best(v, k, mrow[x / tw], c);
+            const int nb = last_row ? 0 : pick_best_biased(v, k, mb, c);
             bp[x] = (uint8_t)nb;
             bp_left = nb;
         }

@@ -170,9 +170,31 @@ def ref_encode_entropy(symbols, range_, prob_bits):
     return out[:n].copy()
 
 
+def _padded_for_decode(stream, pos):
+    """The reference's decoder (and the oracle, which mirrors it) trusts the stream: with a table the format could
+    not represent the state collapses and it reads one 32-bit word per remaining symbol past the
+    payload.  Give it zeros to read instead of whatever follows the array in memory: 4 bytes per declared
+    symbol beyond the stream's own bytes."""
+    n = 0
+    try:
+        at = pos
+        for _ in range(2):  # varint(range - 1), varint(n): varint.hpp:6-27
+            b0 = int(stream[at]); at += 1
+            v = b0
+            if b0 & 0x80:
+                b1 = int(stream[at]); at += 1
+                v = ((b0 & 0x7f) << 7) + b1
+                if b1 & 0x80:
+                    v = ((b0 & 0x7f) << 14) + ((b1 & 0x7f) << 7) + int(stream[at]); at += 1
+            n = v
+    except IndexError:
+        n = 0
+    return np.concatenate([stream, np.zeros(4 * n + 4096, np.uint8)])
+
+
 def orc_decode_entropy(stream, pos=0, flags=7, cap=1 << 22):
     stream = np.ascontiguousarray(stream, dtype=np.uint8)
-    padded = np.concatenate([stream, np.zeros(16, np.uint8)])
+    padded = _padded_for_decode(stream, pos)
     out = np.zeros(cap, np.uint16)
     bp = sz(pos)
     st = C.c_int(0)
@@ -182,7 +204,7 @@ def orc_decode_entropy(stream, pos=0, flags=7, cap=1 << 22):
 
 def ref_decode_entropy(stream, pos=0, cap=1 << 22):
     stream = np.ascontiguousarray(stream, dtype=np.uint8)
-    padded = np.concatenate([stream, np.zeros(16, np.uint8)])
+    padded = _padded_for_decode(stream, pos)
     out = np.zeros(cap, np.uint16)
     bp = sz(pos)
     n = ref().ref_decode_entropy(padded, len(stream), C.byref(bp), out, cap)
