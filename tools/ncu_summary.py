@@ -84,7 +84,10 @@ def full(path, traffic_path=None, images=4096):
             elif metric == "gpu__time_duration.sum":
                 cells.append(f"{dur_ms(r):.2f}")
             else:
-                cells.append(f"{float(r[i].replace(',', '')) * scale:.2f}" if r[i] else "-")
+                try:
+                    cells.append(f"{float(r[i].replace(',', '')) * scale:.2f}")
+                except ValueError:  # empty, or "no data"
+                    cells.append("-")
         print(f"| `{n}` | " + " | ".join(cells) + " |")
         rd = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
         wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
