@@ -22,7 +22,7 @@ namespace {
 enum Slot {
     S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
     S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
-    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_T_MORE_SHAPES, S_T_LAST = S_T_NUKE + 4 * 9 - 1, S_D_TILES, S_D_PLANES, S_D_LZSYM, S_D_IDXSYM, S_D_RESID, S_D_OUT, S_D_BACKREF, S_D_MAPS,
+    S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_LZ_KEYS, S_LZ_VALS, S_LZ_FLAG, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_T_MORE_SHAPES, S_T_LAST = S_T_NUKE + 4 * 9 - 1, S_D_TILES, S_D_PLANES, S_D_LZSYM, S_D_IDXSYM, S_D_RESID, S_D_OUT, S_D_BACKREF, S_D_MAPS,
     S_D_STREAMS, S_D_RES_A, S_D_RES_B, S_D_TOP, S_D_BP, S_D_PSTATUS, S_PA_BEST, S_COUNT
 };
 
@@ -1343,7 +1343,24 @@ int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles,
         if (!d_bonus) d_bonus = bonus;
     }
     const uint64_t segs = (sh.stride + kLzSeg - 1) / kLzSeg;
-    k_lz_match<<<blocks_for(n_tiles * segs * 32, 128), 128, 0, ctx->stream>>>(px, sh, n_tiles, 1u << distance, wide, state);
+    uint32_t* flag = nullptr;
+    if (distance >= 10 && !getenv("HOH_LZ_DENSE")) {
+        // wide windows: candidates from chains of 4-pixel hashes; the dense scan only redoes flagged tiles
+        uint32_t *heads, *next;
+        TRY(scratch_t(ctx, S_LZ_KEYS, (size_t)n_tiles * kLzHeads, &heads));
+        TRY(scratch_t(ctx, S_LZ_VALS, (size_t)n_tiles * sh.stride, &next));
+        TRY(scratch_t(ctx, S_LZ_FLAG, n_tiles, &flag));
+        CK(cudaMemsetAsync(flag, 0, n_tiles * sizeof(uint32_t), ctx->stream));
+        CK(cudaMemsetAsync(heads, 0xff, (size_t)n_tiles * kLzHeads * sizeof(uint32_t), ctx->stream));
+        const uint64_t bpt = (sh.stride + 255) / 256;
+        k_lz_chains<<<(unsigned)(n_tiles * bpt), 256, 0, ctx->stream>>>(px, sh, n_tiles, heads, next);
+        LAUNCHED("k_lz_chains");
+        k_lz_match_sparse<<<(unsigned)(n_tiles * bpt), 256, 0, ctx->stream>>>(px, sh, n_tiles, 1u << distance, heads, next, state,
+                                                                             flag);
+        LAUNCHED("k_lz_match_sparse");
+    }
+    k_lz_match<<<blocks_for(n_tiles * segs * 32, 128), 128, 0, ctx->stream>>>(px, sh, n_tiles, 1u << distance, wide, state,
+                                                                             flag);
     LAUNCHED("k_lz_match");
     k_lz_walk<<<blocks_for(n_tiles * 32, 128), 128, 0, ctx->stream>>>(state, sh, n_tiles, d_bonus, 0, wide, d_nuke,
                                                                      nuke_stride, side, stride, counts);
@@ -1422,7 +1439,8 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
         const size_t lz_words = (1u << distance) + (npx + kLzSeg) + 32 * kLzAhead;
         per_image += cls[c].sel.per_image *
                      ((per8 + 2) * npx * 2 + out8_tile[c] + out9_tile[c] + lz_stride[c] + g.plane_stride + lz_words * 4 +
-                      npx * 4 + 4 * (size_t)lz_side_stride(npx) * 2 + 4 * hoh_enc_slab_bytes(lz_side_stride(npx), 10) +
+                      npx * 4 + (distance >= 10 ? 4 * npx + 4 * (size_t)kLzHeads : 0) + 4 * (size_t)lz_side_stride(npx) * 2 +
+                      4 * hoh_enc_slab_bytes(lz_side_stride(npx), 10) +
                       3 * (2 * npx * 2 + 8192) + 4096);
     }
     size_t budget = (size_t)32 << 30;

@@ -3132,7 +3132,8 @@ __device__ __forceinline__ void lz_distance_group(const uint32_t* __restrict__ P
 // state[tile * stride + i] = longest << 17 | distance  (longest 0 when nothing matches)
 __global__ void __launch_bounds__(128) k_lz_match(const uint32_t* __restrict__ px, LzShape sh, uint64_t n_tiles,
                                                   uint32_t near_limit, uint32_t wide,
-                                                  uint32_t* __restrict__ state) {
+                                                  uint32_t* __restrict__ state,
+                                                  const uint32_t* __restrict__ only_flagged) {
     const uint32_t lane = lane_id();
     const uint32_t segs = (sh.stride + kLzSeg - 1) / kLzSeg;
     const uint64_t wid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -3142,6 +3143,7 @@ __global__ void __launch_bounds__(128) k_lz_match(const uint32_t* __restrict__ p
     uint32_t npx, width;
     lz_dims(sh, tile, npx, width);
     if (s0 >= npx) return;
+    if (only_flagged && only_flagged[tile] == 0u) return;  // the sparse pass has answered this tile
     const uint32_t* P = px + tile * sh.px_stride + sh.pad;
     uint32_t mine[32], best[32];
 #pragma unroll
@@ -3189,6 +3191,72 @@ __global__ void __launch_bounds__(128) k_lz_match(const uint32_t* __restrict__ p
         const uint32_t i = s0 + 32u * k + lane;
         if (i < npx) S[i] = (best[k] & ~0x1ffffu) | (0x1ffffu - (best[k] & 0x1ffffu));
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Sparse candidates for wide seek windows.  Only runs of at least 4 pixels can become matches (lz.hpp:75:
+// longest >= 4 + bonus), and such a run starts with four equal pixels on both sides.  So instead of testing every
+// distance, the positions of a tile are chained by a 16-bit hash of their next four pixels (one atomic exchange
+// per position into a table of chain heads) and a pixel only looks at the earlier positions of its own chain: on
+// photographic content a chain has a couple of entries.  The order of a chain does not matter — the best
+// candidate is a maximum (lz_key).  A tile with a chain longer than kLzChainLimit (flat or periodic content)
+// raises a flag and is redone by the dense kernel; the others are skipped there.  The answers for pixels whose
+// longest run is shorter than 4 differ from the dense kernel's (0 instead of 1..3) — the walk never looks at those.
+// -------------------------------------------------------------------------------------------------
+constexpr uint32_t kLzChainLimit = 64;
+constexpr uint32_t kLzHeads = 1u << 16;  // chain heads per tile
+
+__device__ __forceinline__ uint32_t lz_hash4(const uint32_t* __restrict__ P, uint32_t i) {  // 16 bits
+    uint32_t h = P[i] * 0x9E3779B1u;
+    h = (h ^ (h >> 15)) + P[i + 1u] * 0x85EBCA77u;
+    h = (h ^ (h >> 13)) + P[i + 2u] * 0xC2B2AE3Du;
+    h = (h ^ (h >> 16)) + P[i + 3u] * 0x27D4EB2Fu;
+    h ^= h >> 15;
+    return (h * 0x2C1B3C6Du) >> 16;
+}
+
+// heads: kLzHeads words per tile, all ones (empty) on entry; next: `stride` words per tile.
+__global__ void __launch_bounds__(256) k_lz_chains(const uint32_t* __restrict__ px, LzShape sh, uint64_t n_tiles,
+                                                   uint32_t* __restrict__ heads, uint32_t* __restrict__ next) {
+    const uint32_t bpt = (sh.stride + 255u) / 256u;  // CTAs per tile
+    const uint64_t tile = blockIdx.x / bpt;
+    const uint32_t i = (blockIdx.x % bpt) * 256u + threadIdx.x;
+    if (tile >= n_tiles) return;
+    uint32_t npx, width_unused;
+    lz_dims(sh, tile, npx, width_unused);
+    if (i >= npx) return;
+    const uint32_t* P = px + tile * sh.px_stride + sh.pad;  // the framing words make P[i + 3] readable
+    next[tile * sh.stride + i] = atomicExch(&heads[tile * kLzHeads + lz_hash4(P, i)], i);
+}
+
+// One thread per position: the earlier positions of its chain are its only candidates.
+__global__ void __launch_bounds__(256) k_lz_match_sparse(const uint32_t* __restrict__ px, LzShape sh, uint64_t n_tiles,
+                                                         uint32_t near_limit, const uint32_t* __restrict__ heads,
+                                                         const uint32_t* __restrict__ next,
+                                                         uint32_t* __restrict__ state, uint32_t* __restrict__ dense_flag) {
+    const uint32_t bpt = (sh.stride + 255u) / 256u;
+    const uint64_t tile = blockIdx.x / bpt;
+    const uint32_t i = (blockIdx.x % bpt) * 256u + threadIdx.x;
+    if (tile >= n_tiles) return;
+    uint32_t npx, width;
+    lz_dims(sh, tile, npx, width);
+    if (i >= npx) return;
+    const uint32_t* P = px + tile * sh.px_stride + sh.pad;
+    const uint32_t* N = next + tile * sh.stride;
+    uint32_t best = 0, seen = 0;
+    for (uint32_t j = heads[tile * kLzHeads + lz_hash4(P, i)]; j != 0xffffffffu; j = N[j]) {
+        if (++seen > kLzChainLimit) {
+            atomicOr(&dense_flag[tile], 1u);
+            break;
+        }
+        if (j >= i) continue;  // itself, or a later position
+        const uint32_t b = i - j;
+        if (!(b <= near_limit || (b <= 65536u && b % width == 0u))) continue;  // lz.hpp:34, :54
+        uint32_t run = 0;
+        while (run < (uint32_t)kLzMaxRun && i + run < npx && P[i + run] == P[j + run]) run++;
+        if (run >= 4u) best = max(best, lz_key(run, b));
+    }
+    state[tile * sh.stride + i] = best ? ((best & ~0x1ffffu) | (0x1ffffu - (best & 0x1ffffu))) : 0x1ffffu;
 }
 
 // choh.cpp:17-50 + :134-154: distinct colours of a tile (more than 256 = "many") -> break-even bonus.
