@@ -976,7 +976,7 @@ int hoh_predict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pl
                              uint16_t* d_resid) {
     if (!ctx || !d_planes || !d_resid || w <= 0 || h <= 0 || depth < 1 || depth > 9) return HOH_E_ARG;
     if (!n_planes) return HOH_OK;
-    k_predict_fastpath<<<grid_cap((uint64_t)n_planes * h * 256, 256, 148u * 64u), w >= 192 ? 256 : 64, 0, ctx->stream>>>(d_planes, n_planes, w, h,
+    k_predict_fastpath<<<grid_cap((uint64_t)n_planes * ((h + kFastpathBand - 1) / kFastpathBand) * 256, 256, 148u * 64u), w >= 192 ? 256 : 64, 0, ctx->stream>>>(d_planes, n_planes, w, h,
                                                                                           depth, d_resid, (uint64_t)w * h);
     LAUNCHED("k_predict_fastpath");
     return HOH_OK;
@@ -1079,7 +1079,7 @@ int predictor_search_impl(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plane
     TRY(scratch_t(ctx, S_BP, n_planes * (size_t)w, &bp));
     TRY(cost_table_for(ctx, per, &e_tab, &e_len));
     CK(cudaMemcpyAsync(masks, kStockMasks, sizeof kStockMasks, cudaMemcpyHostToDevice, ctx->stream));
-    k_predict_fastpath<<<grid_cap((uint64_t)n_planes * h * 256, 256, 148u * 64u), w >= 192 ? 256 : 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, d_resid,
+    k_predict_fastpath<<<grid_cap((uint64_t)n_planes * ((h + kFastpathBand - 1) / kFastpathBand) * 256, 256, 148u * 64u), w >= 192 ? 256 : 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, d_resid,
                                                                                 resid_stride);
     LAUNCHED("k_predict_fastpath");
     const int passes = mode > 2 ? 2 : 1;  // layer_encode.hpp:215
@@ -1206,7 +1206,7 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
         return HOH_OK;
     };
     // layer_encode.hpp:63-120: fastpath residuals
-    k_predict_fastpath<<<grid_cap((uint64_t)n * h * 256, 256, 148u * 64u), w >= 192 ? 256 : 64, 0, ctx->stream>>>(d_planes, n, w, h, depth, resid0,
+    k_predict_fastpath<<<grid_cap((uint64_t)n * ((h + kFastpathBand - 1) / kFastpathBand) * 256, 256, 148u * 64u), w >= 192 ? 256 : 64, 0, ctx->stream>>>(d_planes, n, w, h, depth, resid0,
                                                                                   lg.per_pad);
     LAUNCHED("k_predict_fastpath");
     auto compact = [&](uint16_t* resid) -> int {  // :93-99, :328-333

@@ -1781,21 +1781,31 @@ __global__ void k_add_green(const uint16_t* __restrict__ g, const uint16_t* __re
 // channelpredict_fastpath — prediction.hpp:6-44.  Per-pixel data parallel on planes.
 // =================================================================================================
 // out_stride: u16 elements between consecutive residual planes (>= w*h)
+constexpr int kFastpathBand = 16;  // rows per CTA trip: the row above travels down in registers
+
 __global__ void k_predict_fastpath(const uint16_t* __restrict__ planes, uint64_t n_planes, int w, int h,
                                    int depth, uint16_t* __restrict__ resid, uint64_t out_stride) {
     const int c = 1 << depth, half = c >> 1;
-    // grid-stride over (plane, row): a CTA takes whole rows, so the only divisions are per row
-    const uint64_t rows = n_planes * (uint64_t)h;
-    for (uint64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-        const uint64_t pl = row / (uint32_t)h;
-        const int y = (int)(row % (uint32_t)h);
-        const uint16_t* p = planes + pl * (uint64_t)w * h + (uint64_t)y * w;
-        uint16_t* o = resid + pl * out_stride + (uint64_t)y * w;
+    // grid-stride over (plane, band of rows); a thread owns a column of the band: one new pixel and its left
+    // neighbour per row, T and TL come from the previous row's registers
+    const uint32_t bands = ((uint32_t)h + kFastpathBand - 1u) / kFastpathBand;
+    const uint64_t jobs = n_planes * bands;
+    for (uint64_t job = blockIdx.x; job < jobs; job += gridDim.x) {
+        const uint64_t pl = job / bands;
+        const int y0 = (int)(job % bands) * kFastpathBand, y1 = min(y0 + kFastpathBand, h);
+        const uint16_t* base = planes + pl * (uint64_t)w * h;
+        uint16_t* obase = resid + pl * out_stride;
         for (int x = threadIdx.x; x < w; x += blockDim.x) {
-            const int L = x ? p[x - 1] : half;
-            const int T = y ? p[x - w] : half;
-            const int TL = (x && y) ? p[x - w - 1] : half;
-            o[x] = (uint16_t)(((int)p[x] - p_med_grad(T, L, TL) + half + c) & (c - 1));  // numerator >= 0: % c == & (c - 1)
+            int T = y0 ? base[(size_t)(y0 - 1) * w + x] : half;
+            int TL = (x && y0) ? base[(size_t)(y0 - 1) * w + x - 1] : half;
+            for (int y = y0; y < y1; y++) {
+                const uint16_t* p = base + (size_t)y * w + x;
+                const int v = p[0];
+                const int L = x ? p[-1] : half;
+                obase[(size_t)y * w + x] = (uint16_t)((v - p_med_grad(T, L, TL) + half + c) & (c - 1));  // numerator > 0
+                T = v;
+                TL = x ? L : half;
+            }
         }
     }
 }
