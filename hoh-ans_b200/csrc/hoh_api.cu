@@ -1189,13 +1189,17 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     uint16_t* resid0 = syms;
     uint16_t* resid1 = syms + n * lg.per_pad;
     const uint32_t range = 1u << depth;
-    auto run_round = [&](int round, size_t count, uint32_t max_range, uint32_t max_pb) -> int {
-        k_layer_streams<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, n_used, kept_px, streams);
+    auto run_round = [&](int round, uint32_t max_range, uint32_t max_pb) -> int {
+        const uint32_t per_plane = round == 0 ? (mode >= 1 ? 9u : 1u) : (round == 1 ? 1u : 3u);
+        const size_t count = n * per_plane;
+        k_layer_streams<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, round, n_used, kept_px, res, streams);
         LAUNCHED("k_layer_streams");
-        if (round == 0) {  // two histograms per plane instead of one per stream
+        if (round != 1) {  // one histogram per residual array instead of one per stream
             uint32_t* freqs;
             TRY(scratch_t(ctx, S_FREQS, count * kFreqRow, &freqs));
-            k_layer_histograms<<<(unsigned)(2 * n), 256, 0, ctx->stream>>>(lg, n, streams, syms, freqs);
+            const uint32_t a = round == 3 ? 0u : 1u, b_first = round == 3 ? 0u : 1u;
+            const uint32_t b = round == 0 ? (mode >= 1 ? 8u : 0u) : (round == 2 ? 2u : 3u);
+            k_layer_histograms<<<(unsigned)(2 * n), 256, 0, ctx->stream>>>(n, per_plane, a, b_first, b, streams, syms, freqs);
             LAUNCHED("k_layer_histograms");
             TRY(encode_from_freqs(ctx, streams, count, syms, d_out, rr, freqs, max_range, max_pb, 0));
         } else {
@@ -1223,9 +1227,16 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     }
     k_layer_headers<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(lg, n, idx, syms, n_used, hdr, hdr_len);
     LAUNCHED("k_layer_headers");
-    // every candidate of every plane in one round (:106, 334-392), then the predictor-index maps (:308-317)
-    TRY(run_round(0, mode >= 1 ? 9 * n : n, range, mode >= 1 ? 19 : 15));
-    if (mode >= 1 && lg.cells) TRY(run_round(1, n, 14, 8));
+    // The candidates (:106, 334-392).  Few planes: all nine at once, both prob_bits directions speculatively — a
+    // launch lasts as long as its longest stream however many streams there are.  Many planes: the launches are
+    // bound by throughput, so A, C, D first and then only the direction C and D decide (a third less work).
+    if (mode == 0 || 9 * n <= 49152) {
+        TRY(run_round(0, range, mode >= 1 ? 19 : 15));
+    } else {
+        TRY(run_round(2, range, 16));
+        TRY(run_round(3, range, 19));
+    }
+    if (mode >= 1 && lg.cells) TRY(run_round(1, 14, 8));  // the predictor-index maps (:308-317)
     k_layer_decide<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(lg, n, res, (flags & HOH_FIX_STALE) ? 1u : 0u, hdr, hdr_len,
                                                                 kept, best, with_idx, status);
     LAUNCHED("k_layer_decide");

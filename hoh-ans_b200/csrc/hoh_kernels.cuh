@@ -2749,10 +2749,24 @@ __device__ __forceinline__ uint32_t layer_slot_bits(uint32_t slot) {
     return slot == 0u ? 15u : slot == 2u ? 16u : slot == 3u ? 15u : slot <= 6u ? 13u + slot : 21u - slot;
 }
 
+// round 0: every candidate at once (speculative, small batches: a launch lasts as long as its longest stream);
+// round 1: B; rounds 2 and 3 (large batches, bound by throughput: no wasted work): A, C, D, then the three
+// candidates of the direction C and D decide, exactly the reference's order.
+__device__ __forceinline__ uint32_t layer_round_streams(const LayerGeom& lg, int round) {
+    return round == 0 ? (lg.mode ? 9u : 1u) : (round == 1 ? 1u : 3u);
+}
+__device__ __forceinline__ uint32_t layer_round_slot(int round, uint32_t k, bool up) {
+    if (round == 0) return k == 0u ? 0u : k + 1u;  // A, then C, D, E..G up, E..G down
+    if (round == 1) return 1u;
+    if (round == 2) return k == 0u ? 0u : k + 1u;  // A, C, D
+    return (up ? 4u : 7u) + k;
+}
+
 __global__ void k_layer_streams(LayerGeom lg, uint64_t n_planes, int round, const uint32_t* __restrict__ n_used,
-                                const uint32_t* __restrict__ kept_px, hoh_enc_stream* __restrict__ streams) {
+                                const uint32_t* __restrict__ kept_px, const hoh_stream_result* __restrict__ results,
+                                hoh_enc_stream* __restrict__ streams) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const uint32_t per_round = (round == 0 && lg.mode) ? 9u : 1u;
+    const uint32_t per_round = layer_round_streams(lg, round);
     if (i >= n_planes * per_round) return;
     const uint64_t p = i / per_round;
     const uint32_t k = (uint32_t)(i % per_round);
@@ -2761,15 +2775,14 @@ __global__ void k_layer_streams(LayerGeom lg, uint64_t n_planes, int round, cons
     st.prefix_len = 0;
     for (int b = 0; b < 8; b++) st.prefix[b] = 0;
     st.reserved = lg.enc_flags;
-    uint32_t slot;
-    if (round == 0) {
-        slot = k == 0u ? 0u : k + 1u;  // A, then C, D, E..G up, E..G down
+    const bool up = round == 3 && results[p * kLayerSlots + 2].size < results[p * kLayerSlots + 3].size;  // :357
+    const uint32_t slot = layer_round_slot(round, k, up);
+    if (round != 1) {
         st.range = 1u << lg.depth;
         st.n = kept_px ? kept_px[p] : lg.per;  // residuals left after NUKE compaction (layer_encode.hpp:93-99, 328-333)
         st.sym_off = (slot != 0u && lg.cells != 0u) ? resid1 : resid0;
         st.prob_bits = layer_slot_bits(slot);
     } else {
-        slot = 1;
         st.sym_off = 2u * n_planes * (uint64_t)lg.per_pad + p * lg.cells_pad;
         st.n = lg.cells;
         st.range = n_used[p];
@@ -2826,16 +2839,19 @@ __global__ void k_layer_headers(LayerGeom lg, uint64_t n_planes, const uint8_t* 
 // histograms, not nine: CTA (plane, which) counts once — one sub-histogram per warp, the residuals of a
 // smooth image pile up on a few values and would serialise on one shared copy — and writes the result to the
 // frequency row of every stream that uses it.
-__global__ void __launch_bounds__(256) k_layer_histograms(LayerGeom lg, uint64_t n_planes,
+__global__ void __launch_bounds__(256) k_layer_histograms(uint64_t n_planes, uint32_t per_plane, uint32_t a_copies,
+                                                          uint32_t b_first, uint32_t b_copies,
                                                           const hoh_enc_stream* __restrict__ streams,
                                                           const uint16_t* __restrict__ symbols,
                                                           uint32_t* __restrict__ freqs) {
+    // streams of plane p: [p * per_plane, ...); the first a_copies of them code one residual array (A), the
+    // b_copies from b_first on another (or the same): one count per array, written to each stream's row
     __shared__ uint32_t s_h[8][kFreqRow];
     const uint64_t p = blockIdx.x >> 1;
-    const uint32_t which = blockIdx.x & 1u;  // 0: stream A, 1: streams C .. G
-    const uint32_t per_plane = lg.mode ? 9u : 1u;
-    if (which == 1u && per_plane == 1u) return;
-    const uint64_t first = p * per_plane + which;
+    const uint32_t which = blockIdx.x & 1u;
+    const uint32_t copies = which ? b_copies : a_copies;
+    if (copies == 0u) return;
+    const uint64_t first = p * per_plane + (which ? b_first : 0u);
     const hoh_enc_stream st = streams[first];
     for (uint32_t i = threadIdx.x; i < 8u * kFreqRow; i += blockDim.x) (&s_h[0][0])[i] = 0;
     __syncthreads();
@@ -2846,7 +2862,6 @@ __global__ void __launch_bounds__(256) k_layer_histograms(LayerGeom lg, uint64_t
         if (v < st.range) atomicAdd(&mine[v], 1u);
     }
     __syncthreads();
-    const uint32_t copies = which ? 8u : 1u;
     for (uint32_t i = threadIdx.x; i < (uint32_t)kFreqRow; i += blockDim.x) {
         uint32_t t = 0;
 #pragma unroll
@@ -2970,12 +2985,12 @@ __global__ void __launch_bounds__(256) k_layer_assemble(LayerGeom lg, const uint
 __global__ void k_layer_scatter(LayerGeom lg, uint64_t n_planes, int round, const hoh_stream_result* __restrict__ rr,
                                 hoh_stream_result* __restrict__ results) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const uint32_t per_round = (round == 0 && lg.mode) ? 9u : 1u;
+    const uint32_t per_round = layer_round_streams(lg, round);
     if (i >= n_planes * per_round) return;
     const uint64_t p = i / per_round;
     const uint32_t k = (uint32_t)(i % per_round);
-    const uint32_t slot = round == 1 ? 1u : (k == 0u ? 0u : k + 1u);
-    results[p * kLayerSlots + slot] = rr[i];
+    const bool up = round == 3 && results[p * kLayerSlots + 2].size < results[p * kLayerSlots + 3].size;
+    results[p * kLayerSlots + layer_round_slot(round, k, up)] = rr[i];
 }
 
 // =================================================================================================

@@ -178,3 +178,9 @@ def test_roundtrip_many_small_tiles():
     assert (rec["status"] == 0).all()
     back, st = g.decode_images(tiles, n, w, h)
     assert (st == 0).all() and np.array_equal(back, rgb)
+    # the same batch in the reference's format (this many planes take the two-round candidate schedule of
+    # hoh_layer_encode_batch): sampled tiles against the oracle's encode_tile
+    ref_tiles, rec = g.encode_images(rgb, n, w, h, 2, 0)
+    for i in (0, 7, 1234, 5999):
+        want, _ = ol.orc_encode_tile_subgreen(base[i % 40], 2)
+        assert ref_tiles[i] == want, i
