@@ -279,6 +279,26 @@ METRIC = "raw RGB MB/s, encode+decode (BASELINE.json: raw RGB MB/s encode & deco
 
 
 # ------------------------------------------------------------------------------------------------
+def host_memory_allows(need_bytes, reserve=8 << 30):
+    """True when `need_bytes` more (summed over the ranks of this box) fit under /proc/meminfo's MemAvailable and
+    the cgroup's limit with `reserve` to spare."""
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except OSError:
+        return True
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        cur = int(open("/sys/fs/cgroup/memory.current").read().strip())
+        if lim != "max":
+            avail = min(avail, int(lim) - cur) if avail is not None else int(lim) - cur
+    except (OSError, ValueError):
+        pass
+    return avail is None or need_bytes + reserve <= avail
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -441,6 +461,12 @@ def main():
 
     # e2e: host buffers through the C-ABI, copies inside the timed region
     e2e = None
+    barrier()
+    short = 0.0 if host_memory_allows(world * (packed_cap + raw + (n_streams + 1) * 8)) else 1.0
+    if not args.no_e2e and shard.reduce_max(short, world, device="cuda") > 0:  # one decision for all ranks
+        # every rank pins ~7.4 GB more for this leg: a host that cannot hold that loses the leg, not the box
+        sys.stderr.write("bench: e2e leg skipped, not enough free host memory for the pinned buffers\n")
+        args.no_e2e = True
     if not args.no_e2e:
         packed_host = g.host_alloc(packed_cap)
         off_host = g.host_alloc((n_streams + 1) * 8, np.uint64)

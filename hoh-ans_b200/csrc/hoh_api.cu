@@ -723,7 +723,7 @@ int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_by
     TRY(scratch_t(ctx, S_RESID, n_streams * g.plane_stride, &resid));
     TRY(scratch_t(ctx, S_DSTREAMS, n_streams, &streams));
     TRY(scratch_t(ctx, S_DRESULTS, n_streams, &results));
-    const size_t unp_smem = (size_t)kUnpWarps * (2 * 32 * kRingStride + g.tile_w + (g.tile_w + 1) / 2) * sizeof(uint32_t);
+    const size_t unp_smem = (size_t)kUnpWarps * (32 * kRingStride + g.tile_w + (g.tile_w + 1) / 2) * sizeof(uint32_t);
     if (unp_smem > 200 * 1024) return HOH_E_UNSUPPORTED;
     k_make_tile_dec_streams<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(g, n_tiles, d_packed, packed_bytes,
                                                                                  d_packed_off, streams, d_status);
@@ -1609,11 +1609,12 @@ int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes
             TRY(decode_common(ctx, streams, nt * 3, d_packed, packed_bytes, resid, res_b));
             k_dt_unlz<<<blocks_for(nt * 32, 128), 128, 0, ctx->stream>>>(nt, npx, g.plane_stride, lz_sym, side, tiles, backref);
             LAUNCHED("k_dt_unlz");
-            // Predictor-grid planes: a half-warp each while the launch is bound by the length of one plane's walk
-            // (37 vs 55 ms for 5 760 planes), one thread each once there are enough planes to be bound by
-            // instruction throughput instead, where one lane per plane wastes nothing (162 vs 240 ms for 87 840);
-            // the measured crossover is near 20 000 planes.  Single-predictor planes always take one thread.
-            const bool wide_walk = nt * 3 <= 16384;
+            // One thread per plane with its inputs prefetched in 8-pixel groups (tile widths that are multiples of
+            // 8: 17 ms for 5 760 planes of 256x270, 37 ms for 46 080).  Other widths take the scalar walk, whose
+            // loads sit on the pixel chain: there a half-warp per predictor-grid plane is faster while the launch is
+            // bound by the length of one plane's walk (37 vs 55 ms for 5 760 planes; crossover near 20 000).
+            const bool grouped = tw % 8 == 0 && tw >= 16 && g.plane_stride % 8 == 0;  // k_dt_unpredict's prefetched walk
+            const bool wide_walk = !grouped && nt * 3 <= 16384;
             k_dt_unpredict<<<blocks_for(nt * 3, 64), 64, 0, ctx->stream>>>(nt * 3, tw, th, (int)xt, (int)yt, g.plane_stride,
                                                                            planes, tiles, res_b, resid, maps, backref, out,
                                                                            top, bp, pstatus, wide_walk ? 1u : 0u);

@@ -1942,6 +1942,29 @@ __device__ __forceinline__ int pick_best_biased(int v, const Cand& k, const Mask
     return (key >> 4) < 2 * c ? (key & 15) : 0;
 }
 
+// cand_at / pick_best_biased with the selects and minima arranged as trees (depth 4 instead of 15): the walks are
+// bound by the dependent chain of a pixel, and both sit on it (the index comes from the previous pixel's argmin).
+__device__ __forceinline__ int cand_at_tree(const Cand& k, int j) {
+    const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8;
+    int a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = b0 ? k.v[2 * i + 1] : k.v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = b1 ? a[2 * i + 1] : a[2 * i];
+    const int c0 = b2 ? b[1] : b[0], c1 = b2 ? b[3] : b[2];
+    return b3 ? c1 : c0;
+}
+__device__ __forceinline__ int pick_best_biased_tree(int v, const Cand& k, const MaskBias& m, int c) {
+    int key[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) key[j] = abs(v - k.v[j]) * 16 + m.jb[j];
+#pragma unroll
+    for (int d = 8; d > 0; d >>= 1)
+#pragma unroll
+        for (int j = 0; j < d; j++) key[j] = min(key[j], key[j + d]);
+    return (key[0] >> 4) < 2 * c ? (key[0] & 15) : 0;
+}
+
 // state per plane in global scratch: top[w] u16 followed by bp[w] u8
 template <bool INVERSE>
 __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__ in, uint64_t n_planes, int w,
@@ -2619,23 +2642,26 @@ __device__ __forceinline__ void unp_store_block(const uint32_t* ring, uint8_t* _
 // inverse colour transform and the scatter into the interleaved image (dhoh.cpp:72-84, 268-276).
 // One warp per tile; lane = row inside a 32-row band; lane r works on column t - r at step t and gets
 // its top neighbour from lane r-1 by shuffle (anti-diagonal wavefront).  Residuals and pixels move
-// through two shared-memory rings (32 rows x 64 columns = 4 blocks of 16, row stride 66 words so that
+// through a shared-memory ring (32 rows x 64 columns = 4 blocks of 16, row stride 66 words so that
 // both the row-wise transfers and the diagonal accesses are bank-conflict free).  Every 16 steps: the
 // block completed three boundaries ago is written back with coalesced stores, the residual block
 // fetched (into registers) one boundary ago is committed to the ring, and the fetch of the next one is
 // issued, so global-memory latency overlaps a whole block of computation.
 template <bool ALIGNED>
-__global__ void __launch_bounds__(kUnpWarps * 32, 3) k_tile_unpredict_s0(const uint16_t* __restrict__ resid, TileGeom g,
+__global__ void __launch_bounds__(kUnpWarps * 32, 5) k_tile_unpredict_s0(const uint16_t* __restrict__ resid, TileGeom g,
                                                                       uint64_t n_tiles, uint8_t* __restrict__ rgb) {
-    extern __shared__ uint32_t s_unp[];  // per warp: in ring, out ring, carry row (tile_w words)
+    extern __shared__ uint32_t s_unp[];  // per warp: the ring, carry row (tile_w words)
     const uint32_t wid = threadIdx.x >> 5, lane = lane_id();
     const uint64_t t = (uint64_t)blockIdx.x * kUnpWarps + wid;
     if (t >= n_tiles) return;
     const uint32_t carry_words = g.tile_w + (g.tile_w + 1u) / 2u;  // (rg | bg << 16) as u32 + g as u16
-    const uint32_t per_warp = 2u * 32u * kRingStride + carry_words;
+    const uint32_t per_warp = 32u * kRingStride + carry_words;
+    // ONE ring: a slot holds the pixel's residuals until its step and the pixel from then on.  At boundary b the
+    // block written back is b-3 (its last column was finished by lane 31 at step 16b-1) and the residual block
+    // committed is b, which takes the slot of b-4, written back one boundary earlier.
     uint32_t* ring_in = s_unp + (size_t)wid * per_warp;
-    uint32_t* ring_out = ring_in + 32 * kRingStride;
-    uint32_t* carry_rb = ring_out + 32 * kRingStride;  // last row of the previous band
+    uint32_t* ring_out = ring_in;
+    uint32_t* carry_rb = ring_in + 32 * kRingStride;  // last row of the previous band
     uint16_t* carry_g = reinterpret_cast<uint16_t*>(carry_rb + g.tile_w);
     const uint64_t image = t / g.tiles_per_image;
     uint32_t x0, y0, tw, th;
@@ -3928,6 +3954,65 @@ __global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, i
     const uint16_t* br = backref + (p / 3u) * (uint64_t)plane_stride;
     uint16_t* dst = out + p * (uint64_t)plane_stride;
     uint64_t next_resid = 0;
+    const bool grouped = (w & 7) == 0 && w >= 16 && (plane_stride & 7u) == 0u;  // the 8-pixel group walks below
+    if (pl.kind == 0u && grouped) {
+        // pure MED inverse, inputs fetched one 8-pixel group ahead (see the predictor-grid walk below)
+        const uint32_t hh = (uint32_t)half * 0x00010001u;
+        uint4 c_br, c_top, c_src, n_br, n_top, n_src;
+        auto fetch0 = [&](uint4& Gbr, uint4& Gtop, uint4& Gsrc, int y, int x0, uint64_t nr) {
+            const uint64_t at = (uint64_t)y * w + x0;
+            Gbr = __ldg(reinterpret_cast<const uint4*>(br + at));
+            Gtop = y ? *reinterpret_cast<const uint4*>(dst + at - w) : make_uint4(hh, hh, hh, hh);
+            if ((nr & 7u) == 0u && nr + 8u <= plane_stride) {
+                Gsrc = __ldg(reinterpret_cast<const uint4*>(src + nr));
+            } else {
+                uint32_t r[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) r[k] = nr + k < plane_stride ? (uint32_t)__ldg(src + nr + k) : 0u;
+                Gsrc = make_uint4(r[0] | (r[1] << 16), r[2] | (r[3] << 16), r[4] | (r[5] << 16), r[6] | (r[7] << 16));
+            }
+        };
+        auto uncovered0 = [](const uint4& b) {
+            auto z = [](uint32_t wd) { return (uint32_t)((wd & 0xffffu) == 0u) + (uint32_t)((wd >> 16) == 0u); };
+            return z(b.x) + z(b.y) + z(b.z) + z(b.w);
+        };
+        fetch0(c_br, c_top, c_src, 0, 0, 0);
+        n_br = c_br, n_top = c_top, n_src = c_src;
+        for (int y = 0; y < h; y++) {
+            int L = half, TL = half;
+            for (int x0 = 0; x0 < w; x0 += 8) {
+                const bool row_goes_on = x0 + 8 < w;
+                if (row_goes_on || y + 1 < h)
+                    fetch0(n_br, n_top, n_src, row_goes_on ? y : y + 1, row_goes_on ? x0 + 8 : 0,
+                           next_resid + uncovered0(c_br));
+                const uint32_t brw[4] = {c_br.x, c_br.y, c_br.z, c_br.w};
+                const uint32_t tpw[4] = {c_top.x, c_top.y, c_top.z, c_top.w};
+                uint32_t q0 = c_src.x, q1 = c_src.y, q2 = c_src.z, q3 = c_src.w;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint64_t at = (uint64_t)y * w + x0 + k;
+                    const uint32_t back = (k & 1) ? (brw[k >> 1] >> 16) : (brw[k >> 1] & 0xffffu);
+                    const int T = (int)((k & 1) ? (tpw[k >> 1] >> 16) : (tpw[k >> 1] & 0xffffu));
+                    int v;
+                    if (back) {
+                        v = dst[at - back];
+                    } else {
+                        v = ((int)(q0 & 0xffffu) + p_med_grad(T, L, TL) - half) & (c - 1);
+                        q0 = __funnelshift_r(q0, q1, 16);
+                        q1 = __funnelshift_r(q1, q2, 16);
+                        q2 = __funnelshift_r(q2, q3, 16);
+                        q3 >>= 16;
+                        next_resid++;
+                    }
+                    dst[at] = (uint16_t)v;
+                    L = v;
+                    TL = T;
+                }
+                c_br = n_br, c_top = n_top, c_src = n_src;
+            }
+        }
+        return;
+    }
     if (pl.kind == 0u) {
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++) {
@@ -3947,6 +4032,113 @@ __global__ void __launch_bounds__(64) k_dt_unpredict(uint64_t n_planes, int w, i
     const uint16_t* tmap = maps + p * (uint64_t)x_tiles * y_tiles;
     uint16_t* top = top_s + p * (uint64_t)w;
     uint8_t* bp = bp_s + p * (uint64_t)w;
+    if (grouped) {
+        // The same walk with every global-memory access taken off the pixel chain (the scalar walk below spends
+        // 80 % of its time waiting on loads: ncu, long scoreboard).  Pixels go in groups of 8 whose inputs — the
+        // back-reference map, the row above (which is simply the previous row of `dst`: no `top` array), the best
+        // predictors of the row above and the next 8 residuals — are fetched as 16-byte words ONE GROUP AHEAD into
+        // registers; where the residuals of the next group start only depends on this group's back-references.
+        // The residuals sit in a 128-bit shift register, the new best predictors are stored as one 8-byte word.
+        struct Grp {
+            uint4 br, top, src;
+            uint2 bp;
+        };
+        const uint32_t hh = (uint32_t)half * 0x00010001u;
+        auto fetch = [&](Grp& G, int y, int x0, uint64_t nr) {
+            const uint64_t at = (uint64_t)y * w + x0;
+            G.br = __ldg(reinterpret_cast<const uint4*>(br + at));
+            if (y) {
+                G.top = *reinterpret_cast<const uint4*>(dst + at - w);
+                G.bp = *reinterpret_cast<const uint2*>(bp + x0);
+            } else {
+                G.top = make_uint4(hh, hh, hh, hh);
+                G.bp = make_uint2(0x04040404u, 0x04040404u);
+            }
+            if ((nr & 7u) == 0u && nr + 8u <= plane_stride) {
+                G.src = __ldg(reinterpret_cast<const uint4*>(src + nr));
+            } else {  // planes with LZ matches: the residuals of a group start anywhere
+                uint32_t r[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) r[k] = nr + k < plane_stride ? (uint32_t)__ldg(src + nr + k) : 0u;
+                G.src = make_uint4(r[0] | (r[1] << 16), r[2] | (r[3] << 16), r[4] | (r[5] << 16), r[6] | (r[7] << 16));
+            }
+        };
+        auto uncovered = [](const uint4& b) {  // how many of the 8 pixels take a residual
+            auto z = [](uint32_t wd) { return (uint32_t)((wd & 0xffffu) == 0u) + (uint32_t)((wd >> 16) == 0u); };
+            return z(b.x) + z(b.y) + z(b.z) + z(b.w);
+        };
+        Grp cur, nxt;
+        fetch(cur, 0, 0, 0);
+        nxt = cur;
+        int bp_row_end = 4;  // best predictor of the previous row's last pixel (bp[w - 1])
+        for (int y = 0; y < h; y++) {
+            int left = half, left_top = half;
+            int bp_left = bp_row_end;
+            const bool last_row = y + 1 >= h;
+            const uint16_t* mrow = tmap + (size_t)((y + 1) / th) * x_tiles;
+            uint32_t next_mask = last_row ? 0u : mrow[0];
+            int cell_i = 0;
+            int first_of_row = 0;
+            MaskBias mb;
+            int in_cell = tw;
+            for (int x0 = 0; x0 < w; x0 += 8) {
+                const bool row_goes_on = x0 + 8 < w;
+                if (row_goes_on || !last_row)
+                    fetch(nxt, row_goes_on ? y : y + 1, row_goes_on ? x0 + 8 : 0, next_resid + uncovered(cur.br));
+                const uint32_t brw[4] = {cur.br.x, cur.br.y, cur.br.z, cur.br.w};
+                const uint32_t tpw[4] = {cur.top.x, cur.top.y, cur.top.z, cur.top.w};
+                const uint32_t bpw[2] = {cur.bp.x, cur.bp.y};
+                uint32_t q0 = cur.src.x, q1 = cur.src.y, q2 = cur.src.z, q3 = cur.src.w;  // residual queue, next one lowest
+                uint32_t nbw[2] = {0u, 0u};
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int x = x0 + k;
+                    if (in_cell == tw) {
+                        in_cell = 0;
+                        mask_bias(next_mask, mb);
+                        cell_i++;
+                        next_mask = (last_row || cell_i >= x_tiles) ? 0u : mrow[cell_i];
+                    }
+                    in_cell++;
+                    const uint64_t at = (uint64_t)y * w + x;
+                    const uint32_t back = (k & 1) ? (brw[k >> 1] >> 16) : (brw[k >> 1] & 0xffffu);
+                    const int t = (int)((k & 1) ? (tpw[k >> 1] >> 16) : (tpw[k >> 1] & 0xffffu));
+                    int tr;
+                    if (k < 7)
+                        tr = (int)(((k + 1) & 1) ? (tpw[(k + 1) >> 1] >> 16) : (tpw[(k + 1) >> 1] & 0xffffu));
+                    else
+                        tr = row_goes_on ? (int)(nxt.top.x & 0xffffu) : first_of_row;
+                    const int bpx = (int)((bpw[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                    Cand kk;
+                    candidates(left, t, left_top, tr, false, kk);
+                    const int pred = p_mid(cand_at_tree(kk, bpx), cand_at_tree(kk, bp_left));
+                    int v;
+                    if (back) {
+                        v = dst[at - back];  // unprediction.hpp:63-65
+                    } else {
+                        const uint32_t tval = (uint32_t)((int)(q0 & 0xffffu) - c - half + pred) & 0xffffu;  // :67
+                        v = (int)(tval & (uint32_t)(c - 1));
+                        q0 = __funnelshift_r(q0, q1, 16);
+                        q1 = __funnelshift_r(q1, q2, 16);
+                        q2 = __funnelshift_r(q2, q3, 16);
+                        q3 >>= 16;
+                        next_resid++;
+                    }
+                    dst[at] = (uint16_t)v;
+                    if (x == 0) first_of_row = v;
+                    left_top = t;
+                    left = v;
+                    const int nb = last_row ? 0 : pick_best_biased_tree(v, kk, mb, c);
+                    nbw[k >> 2] |= (uint32_t)nb << (8 * (k & 3));
+                    bp_left = nb;
+                }
+                *reinterpret_cast<uint2*>(bp + x0) = make_uint2(nbw[0], nbw[1]);
+                cur = nxt;
+            }
+            bp_row_end = bp_left;
+        }
+        return;
+    }
     for (int i = 0; i < w; i++) {
         top[i] = (uint16_t)half;
         bp[i] = 4;
