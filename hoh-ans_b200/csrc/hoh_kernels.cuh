@@ -539,8 +539,8 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
 // state in shared memory is the cumulative count.  A stream is one serial chain of steps, so what
 // bounds the kernel is the LENGTH OF THE DEPENDENT CHAIN per symbol, not the instruction count:
 // the reciprocal 1/f is computed in fp64 off the chain (it does not depend on x: MUFU.RCP64H + two
-// Newton steps, biased low), and the chain itself is  u64 -> f64, one DMUL, f64 -> u64, one IMAD for the
-// remainder, one correction.  The estimate never exceeds the true quotient (operand truncated, the
+// Newton steps, biased low), and the chain itself is  u64 -> f64, one DFMA.RZ whose mantissa is the quotient
+// (prob_bits >= 14; DMUL + f64 -> u64 below that), one IMAD for the remainder, one correction.  The estimate never exceeds the true quotient (operand truncated, the
 // reciprocal biased by 2^-50, checked on the CPU over 2*10^8 cases) and is at most 1 short for
 // prob_bits >= 14 (3 for 12..13), so the corrections below make the result exact for every input.
 
@@ -572,7 +572,16 @@ __device__ __forceinline__ uint64_t rans_put(uint64_t x, uint32_t start, uint32_
     const bool emit = ((uint32_t)(x >> 32) >> (31u - bits)) >= freq;
     if (emit) words[--widx] = (uint32_t)x;
     x = emit ? (x >> 32) : x;
-    uint64_t q = __double2ull_rz(__ull2double_rz(x) * inv);  // q <= floor(x / freq), short by <= 1 (bits >= 14)
+    uint64_t q;  // q <= floor(x / freq), short by <= 1 (bits >= 14)
+    if (LOW_BITS) {
+        q = __double2ull_rz(__ull2double_rz(x) * inv);
+    } else {
+        // x / freq < 2^(63 - bits) <= 2^49: the product is added to 2^52 in the SAME fused operation, rounding
+        // towards zero, so the mantissa of the sum IS floor(x_d * inv) — one DFMA instead of DMUL + F2I.U64.F64
+        // (8 instead of 34 cycles on the chain).  Same bound as before (the product is not even rounded before
+        // the floor); modelled on the CPU in tests/hostfmt (fmt_div_model) over the boundaries of every quotient.
+        q = (uint64_t)__double_as_longlong(__fma_rz(__ull2double_rz(x), inv, 4503599627370496.0)) & 0x000fffffffffffffull;
+    }
     uint32_t r = (uint32_t)x - (uint32_t)q * freq;           // true remainder < 2^32: exact mod 2^32
     if (r >= freq) {
         r -= freq;

@@ -16,7 +16,7 @@ HDR = os.path.join(os.path.dirname(HERE), "hoh-ans_b200", "csrc", "hoh_format.cu
 
 def _lib():
     if (not os.path.exists(SO)) or max(os.path.getmtime(SRC), os.path.getmtime(HDR)) > os.path.getmtime(SO):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", SO, SRC])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-frounding-math", "-fPIC", "-shared", "-x", "c++", "-o", SO, SRC])
     L = C.CDLL(SO)
     L.fmt_build_head.restype = C.c_uint32
     L.fmt_build_head.argtypes = [ol.u32p, C.c_uint32, C.c_uint32, C.c_uint32, ol.u8p, C.POINTER(C.c_uint32)]
@@ -24,6 +24,8 @@ def _lib():
     L.fmt_parse.argtypes = [ol.u8p, C.c_uint64, C.c_uint, ol.u32p, ol.u32p]
     L.fmt_table_mode.restype = C.c_uint32
     L.fmt_table_mode.argtypes = [ol.u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.fmt_div_model.restype = C.c_uint64
+    L.fmt_div_model.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_int]
     L.fmt_put_varint.restype = C.c_uint32
     L.fmt_put_varint.argtypes = [ol.u8p, C.c_uint32, C.c_uint32]
     return L
@@ -124,3 +126,14 @@ def test_representable_rule_only_changes_lossy_mode1_tables():
         changed += lossy
         kept1 += (m0 == 1 and not lossy)
     assert changed > 20 and kept1 > 20
+
+
+def test_encoder_division_step_model_is_exact():
+    """The rANS encoder's x / freq for prob_bits >= 14 is one fused multiply-add rounded towards zero whose
+    mantissa is the quotient (hoh_kernels.cuh, rans_put<false>): its CPU model against the integer division, over
+    random states, the top of the state range and both ends of quotient intervals, for reciprocals up to two
+    ulps either side of the nominal one."""
+    L = _lib()
+    for bits in range(14, 20):
+        for ulps in (-2, 0, 2):
+            assert L.fmt_div_model(bits, 400000, 1234567 + bits, ulps) == 0, (bits, ulps)
