@@ -142,6 +142,25 @@ int scratch_t(hoh_ctx* ctx, Slot slot, size_t count, T** out) {
     return HOH_OK;
 }
 
+// Bytes of scratch one chunk of a chunked walk (hoh_encode_images / hoh_decode_images) may plan for.  The entropy
+// kernels last as long as one stream's chain however few streams a launch has, so fewer, larger chunks are faster:
+// half of the device's memory (90 GB on a B200), but no more than 55 % of what is free now plus what this context
+// and its children already hold as scratch (that memory is reused by the walk).  HOH_SCRATCH_GB overrides.
+size_t scratch_budget(hoh_ctx* ctx) {
+    if (const char* e = getenv("HOH_SCRATCH_GB")) return (size_t)(atof(e) * (double)((size_t)1 << 30));
+    size_t held = 0;
+    for (int i = 0; i < S_COUNT; i++) held += ctx->scratch[i].cap;
+    for (hoh_ctx* ch : ctx->child)
+        if (ch)
+            for (int i = 0; i < S_COUNT; i++) held += ch->scratch[i].cap;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (size_t)8 << 30;
+    size_t budget = (size_t)((double)(free_b + held) * 0.55);
+    if (budget > total_b / 2) budget = total_b / 2;
+    if (budget < ((size_t)1 << 30)) budget = (size_t)1 << 30;
+    return budget;
+}
+
 inline unsigned blocks_for(uint64_t items, unsigned per_block) { return (unsigned)((items + per_block - 1) / per_block); }
 inline unsigned grid_cap(uint64_t items, unsigned per_block, unsigned cap = 148u * 32u) {
     uint64_t b = (items + per_block - 1) / per_block;
@@ -1454,8 +1473,7 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
                       4 * hoh_enc_slab_bytes(lz_side_stride(npx), 10) +
                       3 * (2 * npx * 2 + 8192) + 4096);
     }
-    size_t budget = (size_t)32 << 30;
-    if (const char* e = getenv("HOH_SCRATCH_GB")) budget = (size_t)atof(e) * ((size_t)1 << 30);
+    const size_t budget = scratch_budget(ctx);
     size_t images_per_chunk = budget / per_image;
     if (images_per_chunk == 0) images_per_chunk = 1;
     if (images_per_chunk > n_images) images_per_chunk = n_images;
@@ -1554,8 +1572,7 @@ int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes
     const uint32_t max_side = lz_side_stride((size_t)hg.tile_w * hg.tile_h);
     const size_t per_tile = 4 * (size_t)max_side * 2 + 3 * (size_t)g.plane_stride * 2 * 2 + (size_t)g.plane_stride * 2 +
                             3 * (size_t)(kCumRow * 4 + kFreqRow * 4) + 3 * (size_t)hg.tile_w * 3 + 4096;
-    size_t budget = (size_t)32 << 30;
-    if (const char* e = getenv("HOH_SCRATCH_GB")) budget = (size_t)atof(e) * ((size_t)1 << 30);
+    const size_t budget = scratch_budget(ctx);
     size_t images_per_chunk = budget / (per_tile * g.tiles_per_image);
     if (images_per_chunk == 0) images_per_chunk = 1;
     if (images_per_chunk > n_images) images_per_chunk = n_images;

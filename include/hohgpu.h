@@ -303,8 +303,8 @@ typedef struct hoh_tile_result {
  * The host keeps only the file header and the tile offset table (choh.cpp:436-506).  Tiles the reference would
  * code in greyscale / indexed mode are flagged (they still get their sub-green bytes).  Image sizes whose last
  * tile column / row is narrower than the others (choh.cpp:459-474) are handled one tile shape at a time.  Large
- * batches are processed in chunks of whole images sized by an internal scratch budget (32 GB, or the
- * HOH_SCRATCH_GB environment variable). */
+ * batches are processed in chunks of whole images sized by an internal scratch budget (half of the device's
+ * memory, at most 55 % of what is free, or the HOH_SCRATCH_GB environment variable). */
 int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
                       int mode, unsigned flags /* 0 or HOH_FIX_ENCODER */, uint8_t* d_packed, size_t packed_cap, uint64_t* d_tile_off,
                       hoh_tile_result* d_tiles);
