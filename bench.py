@@ -279,6 +279,38 @@ METRIC = "raw RGB MB/s, encode+decode (BASELINE.json: raw RGB MB/s encode & deco
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(gpu_index):
+    """Pins this process to the CPUs next to its GPU (the PCI device's local_cpulist) BEFORE the pinned staging
+    buffers are allocated, so that first touch puts them on the GPU's own NUMA node: with one rank per GPU and the
+    buffers on whichever node the ranks happened to start on, the host copies of an 8-GPU box cross the socket
+    link.  Returns what was done, for the JSON line; does nothing on a single-node host."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = gpu_index
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            phys = int(vis.split(",")[gpu_index])
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return {"node": node, "nodes": len(nodes), "bound": False}
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": node, "nodes": len(nodes), "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "nodes": len(nodes), "bound": True, "cpus": len(cpus)}
+    except Exception as e:  # no NVML, no sysfs: run unbound
+        return {"bound": False, "why": type(e).__name__}
+
+
 def host_memory_allows(need_bytes, reserve=8 << 30):
     """True when `need_bytes` more (summed over the ranks of this box) fit under /proc/meminfo's MemAvailable and
     the cgroup's limit with `reserve` to spare."""
@@ -351,6 +383,8 @@ def main():
         return 0
 
     # ---------------------------------------------------------------- B200 arm
+    # one rank alone keeps every core (the cpu_baseline leg forks its workers from this process)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else {"bound": False, "why": "single rank"}
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -571,7 +605,7 @@ def main():
             line["e2e"] = {"value": 2 * job_raw / (e2e["ms"] / 1e3) / 1e6, "unit": "MB/s",
                            "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                            "ms_per_step": e2e["ms"], "encode_ms": e2e["enc_ms"], "decode_ms": e2e["dec_ms"],
-                           "verified": e2e_all_ok}
+                           "verified": e2e_all_ok, "numa_rank0": numa}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = args.cpu_sample or max(cores * 4, 32)

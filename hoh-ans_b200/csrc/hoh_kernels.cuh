@@ -2208,9 +2208,27 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
     const uint64_t per = (uint64_t)w * h;
     const uint16_t* data = planes + p * per;
     const double* ctab = cost + p * (uint64_t)c;
-    uint32_t mask[NM];
+    // The reference's masks are single predictors, pairs, "all" and "all but one" (layer_encode.hpp:160-174), and for
+    // those the masked argmin needs no walk over the 16 keys: a singleton or pair is one or two keys, and the minimum
+    // over all-but-j is the second smallest key when the smallest is j's, else the smallest (keys are distinct: the
+    // index is part of the key).  The two smallest keys are found once per pixel.  info = kind | a << 2 | b << 7;
+    // kind 0: all / all but a (a = 16: none missing), 1: {a}, 2: {a, b}, 3: anything else (the generic walk).
+    uint32_t info[NM];
 #pragma unroll
-    for (int m = 0; m < NM; m++) mask[m] = masks[m];
+    for (int m = 0; m < NM; m++) {
+        const uint32_t mk = masks[m] & 0xffffu;
+        const int pc = __popc(mk);
+        uint32_t kind = 3u, a = 0u, b = 0u;
+        if (pc >= 15) {
+            kind = 0u;
+            a = pc == 16 ? 16u : (uint32_t)__ffs((int)(~mk & 0xffffu)) - 1u;
+        } else if (pc == 1 || pc == 2) {
+            kind = (uint32_t)pc;
+            a = (uint32_t)__ffs((int)mk) - 1u;
+            b = 31u - (uint32_t)__clz((int)mk);
+        }
+        info[m] = kind | (a << 2) | (b << 7);
+    }
     uint16_t top[kMaxCellW];
     uint64_t bpcol[kMaxCellW];
     for (int i = 0; i < tw; i++) {  // prediction.hpp:76-94, as in k_section
@@ -2242,9 +2260,15 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 s_cand[j][tid] = (uint32_t)kk.v[j];
-                const int err = abs(v - kk.v[j]);
-                key[j] = err < 2 * c ? (err << 4) | j : 0x7fffffff;
+                key[j] = abs(v - kk.v[j]) * 16 + j;  // "error below 2c" (prediction.hpp:138) is tested on the winner only
             }
+            int b1 = 0x7fffffff, b2 = 0x7fffffff;  // the two smallest keys
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                b2 = min(b2, max(b1, key[j]));
+                b1 = min(b1, key[j]);
+            }
+            auto key_of = [&](uint32_t j) { return abs(v - (int)s_cand[j][tid]) * 16 + (int)j; };
             const uint64_t above = bpcol[xm];
             const uint64_t before = bpcol[(xm + tw - 1) % tw];  // :134 (this row's left pixel once xm > 0)
             uint64_t now = 0;
@@ -2254,10 +2278,20 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
                 const int pred = p_mid((int)s_cand[bt][tid], (int)s_cand[bl][tid]);
                 const int r = (v - pred + half + c) % c;
                 sum[m] += ctab[r];
-                int best = 0x7fffffff;
+                const uint32_t kind = info[m] & 3u, ia = (info[m] >> 2) & 31u, ib = info[m] >> 7;
+                int best;
+                if (kind == 0u) {
+                    best = (uint32_t)(b1 & 15) == ia ? b2 : b1;
+                } else if (kind == 3u) {
+                    const uint32_t mk = masks[m];
+                    best = 0x7fffffff;
 #pragma unroll
-                for (int j = 0; j < 16; j++) best = min(best, ((mask[m] >> j) & 1u) ? key[j] : 0x7fffffff);
-                now |= (uint64_t)(best == 0x7fffffff ? 0 : (best & 15)) << (4 * m);
+                    for (int j = 0; j < 16; j++) best = min(best, ((mk >> j) & 1u) ? key[j] : 0x7fffffff);
+                } else {
+                    best = key_of(ia);
+                    if (kind == 2u) best = min(best, key_of(ib));
+                }
+                now |= (uint64_t)((best >> 4) < 2 * c ? (best & 15) : 0) << (4 * m);  // 0x7fffffff: empty mask
             }
             bpcol[xm] = now;
             left_top = top[xm];
