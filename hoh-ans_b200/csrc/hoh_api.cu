@@ -742,7 +742,7 @@ int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_by
     TRY(scratch_t(ctx, S_RESID, n_streams * g.plane_stride, &resid));
     TRY(scratch_t(ctx, S_DSTREAMS, n_streams, &streams));
     TRY(scratch_t(ctx, S_DRESULTS, n_streams, &results));
-    const size_t unp_smem = (size_t)kUnpWarps * (32 * kRingStride + g.tile_w + (g.tile_w + 1) / 2) * sizeof(uint32_t);
+    const size_t unp_smem = (size_t)kUnpWarps * ((32 * kRingStride + g.tile_w + (g.tile_w + 1) / 2 + 3) & ~(size_t)3) * sizeof(uint32_t);
     if (unp_smem > 200 * 1024) return HOH_E_UNSUPPORTED;
     k_make_tile_dec_streams<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(g, n_tiles, d_packed, packed_bytes,
                                                                                  d_packed_off, streams, d_status);

@@ -2693,12 +2693,12 @@ __device__ __forceinline__ void unp_store_block(const uint32_t* ring, uint8_t* _
 template <bool ALIGNED>
 __global__ void __launch_bounds__(kUnpWarps * 32, 5) k_tile_unpredict_s0(const uint16_t* __restrict__ resid, TileGeom g,
                                                                       uint64_t n_tiles, uint8_t* __restrict__ rgb) {
-    extern __shared__ uint32_t s_unp[];  // per warp: the ring, carry row (tile_w words)
+    extern __shared__ __align__(16) uint32_t s_unp[];  // per warp: the ring, carry row (tile_w words)
     const uint32_t wid = threadIdx.x >> 5, lane = lane_id();
     const uint64_t t = (uint64_t)blockIdx.x * kUnpWarps + wid;
     if (t >= n_tiles) return;
     const uint32_t carry_words = g.tile_w + (g.tile_w + 1u) / 2u;  // (rg | bg << 16) as u32 + g as u16
-    const uint32_t per_warp = 32u * kRingStride + carry_words;
+    const uint32_t per_warp = (32u * kRingStride + carry_words + 3u) & ~3u;  // 16-byte multiples: vector carry accesses
     // ONE ring: a slot holds the pixel's residuals until its step and the pixel from then on.  At boundary b the
     // block written back is b-3 (its last column was finished by lane 31 at step 16b-1) and the residual block
     // committed is b, which takes the slot of b-4, written back one boundary earlier.
@@ -2763,6 +2763,51 @@ __global__ void __launch_bounds__(kUnpWarps * 32, 5) k_tile_unpredict_s0(const u
                 }
             }
         };
+        // Four steady-state steps (ALIGNED tiles).  The carry row is what lane 0 reads (the row above the band) and
+        // lane 31 writes (the band's last row): as scalar accesses those were a third of the kernel's shared-memory
+        // wavefronts, which is what bounds it.  Lane 0 is at column s..s+3 — an aligned group, fetched as one 8-byte
+        // and one 16-byte load — and lane 31 at s-31..s-28, so with the value it produced one step earlier (prev)
+        // it completes the aligned group s-32..s-29 and stores it the same way.
+        uint32_t prev_g = 128u, prev_rb = kHalfRB;
+        auto group_fn = [&](uint32_t s) {
+            uint2 cg = make_uint2(0u, 0u);
+            uint4 crb = make_uint4(0u, 0u, 0u, 0u);
+            if (lane == 0u) {
+                cg = *reinterpret_cast<const uint2*>(carry_g + s);
+                crb = *reinterpret_cast<const uint4*>(carry_rb + s);
+            }
+            const uint32_t cgv[4] = {cg.x & 0xffffu, cg.x >> 16, cg.y & 0xffffu, cg.y >> 16};
+            const uint32_t crbv[4] = {crb.x, crb.y, crb.z, crb.w};
+            uint32_t og[4], orb[4];
+#pragma unroll
+            for (uint32_t i = 0; i < 4u; i++) {
+                const uint32_t xc = s + i - lane;
+                const uint32_t tg_up = __shfl_up_sync(0xffffffffu, mine_g, 1);
+                const uint32_t trb_up = __shfl_up_sync(0xffffffffu, mine_rb, 1);
+                const uint32_t Tg = lane == 0u ? cgv[i] : tg_up;
+                const uint32_t Trb = lane == 0u ? crbv[i] : trb_up;
+                const uint32_t v = my_in[xc & 63];
+                const uint32_t rg2 = ((v >> 8) & 511u) | ((v >> 17) << 16);
+                const uint32_t vg = ((v & 255u) + p_med_grad2(Tg, Lg, TLg) - 128u) & 255u;
+                const uint32_t vrb = __vsub2(__vadd2(rg2, p_med_grad2(Trb, Lrb, TLrb)), kHalfRB) & kMaskRB;
+                const uint32_t rb8 = __vsub2(__vadd2(vrb, vg * 0x00010001u), kHalfRB) & 0x00ff00ffu;
+                my_out[xc & 63] = rb8 | (vg << 8);
+                mine_g = vg;
+                mine_rb = vrb;
+                Lg = vg;
+                Lrb = vrb;
+                TLg = Tg;
+                TLrb = Trb;
+                og[i] = vg;
+                orb[i] = vrb;
+            }
+            if (lane == 31u) {
+                *reinterpret_cast<uint2*>(carry_g + (s - 32u)) = make_uint2(prev_g | (og[0] << 16), og[1] | (og[2] << 16));
+                *reinterpret_cast<uint4*>(carry_rb + (s - 32u)) = make_uint4(prev_rb, orb[0], orb[1], orb[2]);
+            }
+            prev_g = og[3];
+            prev_rb = orb[3];
+        };
         UnpPrefetch pf;
         unp_fetch_block<ALIGNED>(pf, in_g, in_rg, in_bg, y_base, th, tw, 0u);
         for (uint32_t blk = 0; blk < n_blocks + 3u; blk++) {
@@ -2773,11 +2818,21 @@ __global__ void __launch_bounds__(kUnpWarps * 32, 5) k_tile_unpredict_s0(const u
             __syncwarp();
             const uint32_t s0 = blk * kUnpBlock;
             if (s0 >= 31u && s0 + kUnpBlock <= tw) {
+                if (ALIGNED) {
+                    for (uint32_t k = 0; k < (uint32_t)kUnpBlock; k += 4u) group_fn(s0 + k);
+                    if (lane == 31u) {  // the value of the block's last step waits for its group: a later block that
+                        carry_g[s0 - 16u] = (uint16_t)prev_g;  // is not steady-state would never store it
+                        carry_rb[s0 - 16u] = prev_rb;
+                    }
+                } else {
 #pragma unroll 4
-                for (uint32_t k = 0; k < (uint32_t)kUnpBlock; k++) step_fn(s0 + k, std::true_type{});
+                    for (uint32_t k = 0; k < (uint32_t)kUnpBlock; k++) step_fn(s0 + k, std::true_type{});
+                }
             } else {
 #pragma unroll 4
                 for (uint32_t k = 0; k < (uint32_t)kUnpBlock; k++) step_fn(s0 + k, std::false_type{});
+                prev_g = mine_g;
+                prev_rb = mine_rb;
             }
         }
         __syncwarp();
