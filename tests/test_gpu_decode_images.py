@@ -184,3 +184,23 @@ def test_roundtrip_many_small_tiles():
     for i in (0, 7, 1234, 5999):
         want, _ = ol.orc_encode_tile_subgreen(base[i % 40], 2)
         assert ref_tiles[i] == want, i
+
+
+def test_chunked_walks_equal_one_pass(monkeypatch):
+    """hoh_encode_images / hoh_decode_images cut a batch into chunks of whole images under a scratch budget
+    (normally a fraction of the device's memory; HOH_SCRATCH_GB overrides).  With a budget of a few megabytes six
+    small images take several chunks: same tile bytes as the one-pass call, same decoded pixels."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(99)
+    w, h, n = 256, 192, 6
+    rgb = _images(rng, w, h, n, 4100, 2)
+    tiles_one, rec_one = g.encode_images(rgb, n, w, h, 2, FIX_STALE)
+    back_one, st_one = g.decode_images(tiles_one, n, w, h)
+    assert (st_one == 0).all() and np.array_equal(back_one, rgb)
+    for budget in ("0.004", "0.02"):
+        monkeypatch.setenv("HOH_SCRATCH_GB", budget)
+        tiles, rec = g.encode_images(rgb, n, w, h, 2, FIX_STALE)
+        assert (rec["status"] == 0).all()
+        assert tiles == tiles_one, budget
+        back, st = g.decode_images(tiles, n, w, h)
+        assert (st == 0).all() and np.array_equal(back, rgb), budget
