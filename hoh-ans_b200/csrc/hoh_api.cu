@@ -285,10 +285,10 @@ int decode_common(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n, const
         cudaStream_t sc = overlap ? ctx->aux[c] : ctx->stream;
         if (rows <= 256) {
             k_rans_decode<uint8_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 1, sc>>>(
-                d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, classes[c], rows);
+                d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, d_results, classes[c], rows);
         } else {
             k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 2, sc>>>(
-                d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, classes[c], rows);
+                d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, d_results, classes[c], rows);
         }
         static const char* const names[4] = {"k_rans_decode[rows<=64]", "k_rans_decode[rows<=128]",
                                              "k_rans_decode[rows<=256]", "k_rans_decode[rows<=515]"};
@@ -1718,9 +1718,9 @@ int hoh_decode_entropy(hoh_ctx* ctx, const uint8_t* in, size_t in_size, size_t* 
     *symbol_size = res.n;
     *byte_pointer = res.end_off;
     size_t take = res.n < symbols_cap ? res.n : symbols_cap;
-    if (res.status != HOH_S_OK && res.status != HOH_S_OVERFLOW) return HOH_E_STREAM;
-    TRY(stage_out(ctx, symbols, d_sym, take));
-    return res.status == HOH_S_OK ? HOH_OK : HOH_E_CAPACITY;
+    if (res.status != HOH_S_OK && res.status != HOH_S_OVERFLOW && res.status != HOH_S_BAD_STATE) return HOH_E_STREAM;
+    TRY(stage_out(ctx, symbols, d_sym, take));  // a stream that fails the final-state check still hands its symbols out
+    return res.status == HOH_S_OK ? HOH_OK : res.status == HOH_S_OVERFLOW ? HOH_E_CAPACITY : HOH_E_STREAM;
 }
 
 int hoh_normalize_freqs(hoh_ctx* ctx, uint32_t* freqs, uint32_t* cum_freqs, size_t size, uint32_t target_total,

@@ -1322,7 +1322,8 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
                                                     uint32_t n_streams, const uint8_t* __restrict__ in,
                                                     uint64_t in_bytes, const uint32_t* __restrict__ cumtab,
                                                     const DecMeta* __restrict__ meta,
-                                                    uint16_t* __restrict__ symbols, uint32_t rows_lo,
+                                                    uint16_t* __restrict__ symbols,
+                                                    hoh_dec_result* __restrict__ results, uint32_t rows_lo,
                                                     uint32_t rows) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);
@@ -1400,17 +1401,34 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
     }
     uint16_t* my_row = stage + lane * kDecStride;
     const uint32_t chunks = (n_max + kDecChunk - 1) / kDecChunk;
+    // The encoder starts from 2^31 (rans64.hpp:65) and decoding undoes its steps one by one, so after the last
+    // symbol of a sound stream the state is 2^31 again: the only integrity check the format offers (it carries no
+    // checksum).  The state is sampled in the chunk where the lane's stream ends (a warp-uniform choice of loop).
+    uint64_t x_end = kRansL;
     for (uint32_t chunk = 0; chunk < chunks; chunk++) {
         __syncwarp();
-        for (uint32_t k0 = 0; k0 < (uint32_t)kDecChunk; k0 += kTopUp) {
-            rd.top_up();
+        const uint32_t left = my_n - min(my_n, chunk * (uint32_t)kDecChunk);  // symbols of mine from this chunk on
+        if (__any_sync(0xffffffffu, left >= 1u && left <= (uint32_t)kDecChunk)) {
+            for (uint32_t k0 = 0; k0 < (uint32_t)kDecChunk; k0 += kTopUp) {
+                rd.top_up();
 #pragma unroll
-            for (uint32_t k = k0; k < k0 + kTopUp; k++)
-                my_row[k] = (uint16_t)rans_get(x, rd, T, lut + lane, 32u, lut_shift, bits, mask);
+                for (uint32_t k = k0; k < k0 + kTopUp; k++) {
+                    my_row[k] = (uint16_t)rans_get(x, rd, T, lut + lane, 32u, lut_shift, bits, mask);
+                    x_end = left == k + 1u ? x : x_end;
+                }
+            }
+        } else {
+            for (uint32_t k0 = 0; k0 < (uint32_t)kDecChunk; k0 += kTopUp) {
+                rd.top_up();
+#pragma unroll
+                for (uint32_t k = k0; k < k0 + kTopUp; k++)
+                    my_row[k] = (uint16_t)rans_get(x, rd, T, lut + lane, 32u, lut_shift, bits, mask);
+            }
         }
         __syncwarp();
         stage_store_chunk(stage, symbols, s_off, s_n, chunk);
     }
+    if (live && my_n == m.n && x_end != kRansL && results[s].status == HOH_S_OK) results[s].status = HOH_S_BAD_STATE;
 }
 
 // -------------------------------------------------------------------------------------------------

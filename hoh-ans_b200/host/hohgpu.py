@@ -442,6 +442,7 @@ class HohGpu:
             self._ck(self.lib.hoh_decode_entropy_batch(self.ctx, d_desc.ptr, k, d_in.ptr, padded.nbytes, d_sym.ptr,
                                                        d_res.ptr, int(max(caps))), "hoh_decode_entropy_batch")
             res = d_res.download(DEC_RESULT_DT, k)
+            self.last_dec_results = res  # the full records (stored, prob_bits, table_mode ...) of the last call
             syms = d_sym.download(np.uint16, max(sym_off, 8))
         finally:
             for b in (d_in, d_desc, d_sym, d_res):

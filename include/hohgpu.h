@@ -47,6 +47,9 @@ extern "C" {
 #define HOH_S_BAD_TABLE 3      /* decode: table storage mode 3                                     */
 #define HOH_S_OVERFLOW 4       /* output slab / symbol capacity too small                          */
 #define HOH_S_BAD_LAYER 5      /* tile decode: channel header is not the mode-0 form 10 00 00 00 10 */
+#define HOH_S_BAD_STATE 6      /* decode: the rANS state after the last symbol is not 2^31, the value the
+                                * encoder starts from (rans64.hpp:65): the table or the payload is damaged.
+                                * The symbols are still delivered (the reference would not notice).      */
 
 /* decode flags: 0 reproduces entropy_decoding.hpp byte for byte including its defects; the FIX
  * bits turn individual defects off. */
@@ -319,8 +322,9 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
  * Tile t's bytes are d_packed[d_tile_off[t], d_tile_off[t+1]).  d_status[t] != 0: the tile could not be decoded
  * (its pixels are left untouched).  Every stream has to end where the container says it ends, so truncated tiles
  * and the channels the reference emits under defect D7 (a stale buffer cut to another candidate's length, see
- * HOH_FIX_STALE) are reported rather than decoded to wrong pixels; flipped payload bytes are not detectable
- * (rANS carries no checksum). */
+ * HOH_FIX_STALE) are reported rather than decoded to wrong pixels; a changed payload byte is caught by the final
+ * rANS state (HOH_S_BAD_STATE: a sound stream ends in the encoder's initial state 2^31) — the format carries no
+ * checksum, so that is a 2^-32-ish guarantee per stream, not a proof. */
 int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes, const uint64_t* d_tile_off,
                       size_t n_images, uint32_t width, uint32_t height, uint8_t* d_rgb, int32_t* d_status);
 

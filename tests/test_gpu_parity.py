@@ -138,7 +138,7 @@ def test_decode_entropy_vs_oracle_and_roundtrip():
     got = g.decode_entropy_batch(blob, offs, caps, flags=7)
     for i, ((sym, end, st), (s, e)) in enumerate(zip(got, exp)):
         if s is None:  # garbage table (lossy mode 1): decoded without faulting, or refused as a bad table
-            assert st in (0, 3), i
+            assert st in (0, 3, 6), i  # 6 = HOH_S_BAD_STATE: the final rANS state gives the garbage away
             continue
         assert st == 0 and end == e and np.array_equal(sym, s), i
     # single-call shim, reference semantics: byte_pointer stops at the payload (D8), 4-bit prob_bits (D9)
@@ -157,6 +157,45 @@ def test_decode_entropy_vs_oracle_and_roundtrip():
         assert sta == stb == 0 and bpa == bpb and np.array_equal(a, b)
         checked_ref += 1
     assert checked_ref > 15
+
+
+def test_final_state_check_flags_damaged_payloads():
+    """The decoder's only integrity check (the format has no checksum): a sound stream ends in the state the encoder
+    started from, 2^31.  Streams with one payload byte changed report HOH_S_BAD_STATE (6) and still hand out their
+    symbols; their intact neighbours decode exactly with status 0."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(61)
+    encs, syms = [], []
+    for it in range(96):
+        n = int(rng.choice([700, 5000, 65536]))
+        s = _symbols(rng, 1 + it % 3, n, 256)
+        s[0] = (int(s[0]) + 1) % 256
+        enc, st = ol.orc_encode_entropy(s, 256, 15)
+        assert st == 0
+        encs.append(np.array(enc, np.uint8))
+        syms.append(s)
+    offs, pos = [], 0
+    for e in encs:
+        offs.append(pos)
+        pos += len(e)
+    caps = [len(s) for s in syms]
+    clean = g.decode_entropy_batch(np.concatenate(encs), offs, caps, flags=7)
+    decodable = [st == 0 and np.array_equal(sym, s) for (sym, _, st), s in zip(clean, syms)]
+    assert sum(decodable) > 80  # the rest: lossy mode-1 tables (SURVEY D6)
+    coded = [int(r["stored"]) == 0 for r in g.last_dec_results]  # stored-mode streams have no state to check
+    damaged = [e.copy() for e in encs]
+    # (a near-constant stream is a table and a bare final state: only streams with a real payload are damaged)
+    hit = [i for i in range(len(encs)) if i % 2 and decodable[i] and coded[i] and len(encs[i]) > 400]
+    assert len(hit) > 20
+    for i in hit:
+        at = int(rng.integers(len(encs[i]) * 2 // 3, len(encs[i]) - 8))  # well inside the payload
+        damaged[i][at] ^= int(rng.integers(1, 256))
+    got = g.decode_entropy_batch(np.concatenate(damaged), offs, caps, flags=7)
+    for i, ((sym, _, st), s) in enumerate(zip(got, syms)):
+        if i in hit:
+            assert st == 6 and len(sym) == len(s), (i, st)
+        elif decodable[i]:
+            assert st == 0 and np.array_equal(sym, s), i
 
 
 def test_decode_entropy_golden_and_empty():
