@@ -1111,12 +1111,13 @@ int predictor_search_impl(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plane
         {  // all masks of a cell in one walk: one thread per (plane, cell)
             const uint64_t cell_jobs = (uint64_t)n_planes * cells;
             const unsigned blocks = blocks_for(cell_jobs, 64);
+            // `masks` holds the reference's own list (kStockMasks): the STOCK instantiations have it compiled in
             if (n_masks == 5)
-                k_section_costs<5><<<blocks, 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks, cost, sums);
+                k_section_costs<5, true><<<blocks, 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks, cost, sums);
             else if (n_masks == 10)
-                k_section_costs<10><<<blocks, 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks, cost, sums);
+                k_section_costs<10, true><<<blocks, 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks, cost, sums);
             else
-                k_section_costs<14><<<blocks, 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks, cost, sums);
+                k_section_costs<14, true><<<blocks, 64, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, xt, yt, masks, cost, sums);
             LAUNCHED("k_section_costs");
         }
         k_pick_masks<<<blocks_for(n_planes * (uint64_t)cells, 256), 256, 0, ctx->stream>>>(

@@ -2208,7 +2208,24 @@ __global__ void __launch_bounds__(64) k_section(const uint16_t* __restrict__ pla
 // NM masks over them: the per-mask best predictors of a column live in one 64-bit word (4 bits per mask), the
 // argmin is a min over keys (error << 4 | index: lowest index wins ties, prediction.hpp:138-146), and each
 // mask's cost is accumulated in raster order in its own double exactly as the one-mask walk does.
-template <int NM>
+// STOCK: the masks are the first NM of the reference's own list (layer_encode.hpp:159-175, the only list the
+// encoder uses): they are compile-time constants then, so after unrolling every mask's kind and indices fold
+// away — a singleton's key is a register, no branches, no per-mask descriptors in registers.
+__device__ __forceinline__ void mask_kind(uint32_t mk, uint32_t& kind, uint32_t& a, uint32_t& b) {
+    mk &= 0xffffu;
+    const int pc = __popc(mk);
+    kind = 3u;
+    a = b = 0u;
+    if (pc >= 15) {
+        kind = 0u;
+        a = pc == 16 ? 16u : (uint32_t)__ffs((int)(~mk & 0xffffu)) - 1u;
+    } else if (pc == 1 || pc == 2) {
+        kind = (uint32_t)pc;
+        a = (uint32_t)__ffs((int)mk) - 1u;
+        b = 31u - (uint32_t)__clz((int)mk);
+    }
+}
+template <int NM, bool STOCK>
 __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
                                                       int h, int depth, int x_tiles, int y_tiles,
                                                       const uint16_t* __restrict__ masks,
@@ -2231,21 +2248,16 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
     // over all-but-j is the second smallest key when the smallest is j's, else the smallest (keys are distinct: the
     // index is part of the key).  The two smallest keys are found once per pixel.  info = kind | a << 2 | b << 7;
     // kind 0: all / all but a (a = 16: none missing), 1: {a}, 2: {a, b}, 3: anything else (the generic walk).
-    uint32_t info[NM];
+    constexpr uint32_t kStock[14] = {0x0001, 0x0002, 0x0020, 0x0010, 0xffbf, 0x0003, 0xfffd,
+                                     0xfffb, 0xfff7, 0xffef, 0xffdf, 0xff7f, 0xfdff, 0xffff};
+    uint32_t info[STOCK ? 1 : NM];
+    if (!STOCK) {
 #pragma unroll
-    for (int m = 0; m < NM; m++) {
-        const uint32_t mk = masks[m] & 0xffffu;
-        const int pc = __popc(mk);
-        uint32_t kind = 3u, a = 0u, b = 0u;
-        if (pc >= 15) {
-            kind = 0u;
-            a = pc == 16 ? 16u : (uint32_t)__ffs((int)(~mk & 0xffffu)) - 1u;
-        } else if (pc == 1 || pc == 2) {
-            kind = (uint32_t)pc;
-            a = (uint32_t)__ffs((int)mk) - 1u;
-            b = 31u - (uint32_t)__clz((int)mk);
+        for (int m = 0; m < NM; m++) {
+            uint32_t kind, a, b;
+            mask_kind(masks[m], kind, a, b);
+            info[m] = kind | (a << 2) | (b << 7);
         }
-        info[m] = kind | (a << 2) | (b << 7);
     }
     uint16_t top[kMaxCellW];
     uint64_t bpcol[kMaxCellW];
@@ -2296,15 +2308,30 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
                 const int pred = p_mid((int)s_cand[bt][tid], (int)s_cand[bl][tid]);
                 const int r = (v - pred + half + c) % c;
                 sum[m] += ctab[r];
-                const uint32_t kind = info[m] & 3u, ia = (info[m] >> 2) & 31u, ib = info[m] >> 7;
+                uint32_t kind, ia, ib;
+                if (STOCK) {
+                    mask_kind(kStock[m], kind, ia, ib);  // constants after unrolling
+                } else {
+                    kind = info[m] & 3u, ia = (info[m] >> 2) & 31u, ib = info[m] >> 7;
+                }
                 int best;
                 if (kind == 0u) {
                     best = (uint32_t)(b1 & 15) == ia ? b2 : b1;
                 } else if (kind == 3u) {
-                    const uint32_t mk = masks[m];
+                    const uint32_t mk = STOCK ? kStock[m] : (uint32_t)masks[m];
                     best = 0x7fffffff;
 #pragma unroll
                     for (int j = 0; j < 16; j++) best = min(best, ((mk >> j) & 1u) ? key[j] : 0x7fffffff);
+                } else if (STOCK) {
+                    // the indices are constants here: the selects fold to one register (written as selects, not as
+                    // key[ia], so that the array never looks dynamically indexed and stays in registers)
+                    int ka = key[0], kb = key[0];
+#pragma unroll
+                    for (int j = 1; j < 16; j++) {
+                        ka = ia == (uint32_t)j ? key[j] : ka;
+                        kb = ib == (uint32_t)j ? key[j] : kb;
+                    }
+                    best = kind == 2u ? min(ka, kb) : ka;
                 } else {
                     best = key_of(ia);
                     if (kind == 2u) best = min(best, key_of(ib));
