@@ -69,8 +69,25 @@ struct hoh_ctx {
 
 namespace {
 
+// Every entry point runs on the context's device whatever the caller's current device is, and puts the
+// caller's device back on return (a process may hold contexts on several GPUs, or share the thread with torch).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const hoh_ctx* ctx);
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 const uint16_t kStockMasks[14] = {  // layer_encode.hpp:159-175
     0x0001, 0x0002, 0x0020, 0x0010, 0xffbf, 0x0003, 0xfffd, 0xfffb, 0xfff7, 0xffef, 0xffdf, 0xff7f, 0xfdff, 0xffff};
+
+DeviceGuard::DeviceGuard(const hoh_ctx* ctx) {
+    if (!ctx) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    if (prev != ctx->device && cudaSetDevice(ctx->device) == cudaSuccess) switched = true;
+}
 
 int fail_cuda(hoh_ctx* c, cudaError_t e, const char* what) {
     if (c) snprintf(c->err, sizeof c->err, "%s: %s", what, cudaGetErrorString(e));
@@ -335,9 +352,19 @@ int cost_table_for(hoh_ctx* ctx, uint64_t size, double** out, uint32_t* len) {
 }  // namespace
 
 namespace {
-__global__ void k_merge_status(const hoh_dec_result* __restrict__ res, uint64_t n, int32_t* __restrict__ status) {
+// full != 0: every stream must hold one symbol per pixel of its tile (no LZ map given): a dense stream coded with
+// a NUKE map would otherwise decode into a tile of wrong pixels without anyone noticing
+__global__ void k_merge_status(const hoh_dec_result* __restrict__ res, uint64_t n, TileGeom g, uint32_t full,
+                               int32_t* __restrict__ status) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n && status[i] == HOH_S_OK) status[i] = res[i].status;
+    if (i >= n || status[i] != HOH_S_OK) return;
+    int32_t st = res[i].status;
+    if (st == HOH_S_OK && full) {
+        uint32_t x0, y0, tw, th;
+        tile_rect(g, (uint32_t)((i / 3u) % g.tiles_per_image), x0, y0, tw, th);
+        if (res[i].n != tw * th) st = HOH_S_BAD_LAYER;
+    }
+    status[i] = st;
 }
 __global__ void k_normalize_only(uint32_t* __restrict__ freqs, uint32_t* __restrict__ cum, uint32_t range,
                                  uint32_t target, int32_t* __restrict__ status) {
@@ -448,6 +475,7 @@ void hoh_ctx_destroy(hoh_ctx* ctx) {
 }
 
 int hoh_sync(hoh_ctx* ctx) {
+    DeviceGuard guard_(ctx);
     if (!ctx) return HOH_E_ARG;
     CK(cudaStreamSynchronize(ctx->stream));
     return HOH_OK;
@@ -469,43 +497,51 @@ const char* hoh_last_cuda_error(hoh_ctx* ctx) { return ctx ? ctx->err : "no cont
 uint64_t hoh_launch_count(hoh_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int hoh_dev_alloc(hoh_ctx* ctx, size_t bytes, void** dptr) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !dptr) return HOH_E_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMalloc(dptr, bytes ? bytes : 16));
     return HOH_OK;
 }
 int hoh_dev_free(hoh_ctx* ctx, void* dptr) {
+    DeviceGuard guard_(ctx);
     if (!ctx) return HOH_E_ARG;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaFree(dptr));
     return HOH_OK;
 }
 int hoh_dev_memset(hoh_ctx* ctx, void* dptr, int value, size_t bytes) {
+    DeviceGuard guard_(ctx);
     if (!ctx) return HOH_E_ARG;
     CK(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
     return HOH_OK;
 }
 int hoh_host_alloc(hoh_ctx* ctx, size_t bytes, void** hptr) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !hptr) return HOH_E_ARG;
     CK(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
     return HOH_OK;
 }
 int hoh_host_free(hoh_ctx* ctx, void* hptr) {
+    DeviceGuard guard_(ctx);
     if (!ctx) return HOH_E_ARG;
     CK(cudaFreeHost(hptr));
     return HOH_OK;
 }
 int hoh_h2d(hoh_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    DeviceGuard guard_(ctx);
     if (!ctx) return HOH_E_ARG;
     CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return HOH_OK;
 }
 int hoh_d2h(hoh_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    DeviceGuard guard_(ctx);
     if (!ctx) return HOH_E_ARG;
     CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return HOH_OK;
 }
 int hoh_timer_start(hoh_ctx* ctx, int slot) {
+    DeviceGuard guard_(ctx);
     if (!ctx || slot < 0 || slot >= 16) return HOH_E_ARG;
     for (int k = 0; k < 2; k++)
         if (!ctx->ev[slot][k]) CK(cudaEventCreate(&ctx->ev[slot][k]));
@@ -513,17 +549,20 @@ int hoh_timer_start(hoh_ctx* ctx, int slot) {
     return HOH_OK;
 }
 int hoh_timer_stop(hoh_ctx* ctx, int slot) {
+    DeviceGuard guard_(ctx);
     if (!ctx || slot < 0 || slot >= 16 || !ctx->ev[slot][1]) return HOH_E_ARG;
     CK(cudaEventRecord(ctx->ev[slot][1], ctx->stream));
     return HOH_OK;
 }
 int hoh_timer_elapsed_ms(hoh_ctx* ctx, int slot, float* ms) {
+    DeviceGuard guard_(ctx);
     if (!ctx || slot < 0 || slot >= 16 || !ms || !ctx->ev[slot][1]) return HOH_E_ARG;
     CK(cudaEventSynchronize(ctx->ev[slot][1]));
     CK(cudaEventElapsedTime(ms, ctx->ev[slot][0], ctx->ev[slot][1]));
     return HOH_OK;
 }
 int hoh_profile_begin(hoh_ctx* ctx) {
+    DeviceGuard guard_(ctx);
     if (!ctx) return HOH_E_ARG;
     for (auto ev : ctx->prof_events) ctx->prof_pool.push_back(ev);
     ctx->prof_events.clear();
@@ -536,6 +575,7 @@ int hoh_profile_begin(hoh_ctx* ctx) {
     return HOH_OK;
 }
 int hoh_profile_end(hoh_ctx* ctx) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !ctx->profiling) return HOH_E_ARG;
     ctx->profiling = false;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -557,6 +597,7 @@ int hoh_profile_end(hoh_ctx* ctx) {
 }
 int hoh_profile_count(hoh_ctx* ctx) { return ctx ? (int)ctx->prof_keys.size() : 0; }
 int hoh_profile_entry(hoh_ctx* ctx, int index, const char** name, double* total_ms, uint64_t* launches) {
+    DeviceGuard guard_(ctx);
     if (!ctx || index < 0 || index >= (int)ctx->prof_keys.size()) return HOH_E_ARG;
     if (name) *name = ctx->prof_keys[index].c_str();
     if (total_ms) *total_ms = ctx->prof_ms[index];
@@ -564,6 +605,7 @@ int hoh_profile_entry(hoh_ctx* ctx, int index, const char** name, double* total_
     return HOH_OK;
 }
 int hoh_flush_l2(hoh_ctx* ctx) {
+    DeviceGuard guard_(ctx);
     if (!ctx) return HOH_E_ARG;
     if (!ctx->flush) {
         ctx->flush_bytes = 256ull << 20;  // > 126 MB L2
@@ -589,6 +631,7 @@ size_t hoh_enc_slab_bytes(size_t n, uint32_t prob_bits) {
 int hoh_encode_entropy_batch(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n_streams,
                              const uint16_t* d_symbols, uint8_t* d_out, hoh_stream_result* d_results,
                              uint32_t max_range, uint32_t max_prob_bits, uint32_t max_n) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_streams || !d_out || !d_results) return HOH_E_ARG;
     if (n_streams == 0) return HOH_OK;
     if (max_range == 0 || max_range > HOH_MAX_RANGE || max_prob_bits == 0 || max_prob_bits > HOH_MAX_PROB_BITS)
@@ -604,8 +647,10 @@ int hoh_encode_entropy_batch(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size
 int hoh_decode_entropy_batch(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n_streams,
                              const uint8_t* d_in, size_t in_bytes, uint16_t* d_symbols,
                              hoh_dec_result* d_results, uint32_t max_n) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_streams || !d_in || !d_symbols || !d_results) return HOH_E_ARG;
     if (n_streams == 0) return HOH_OK;
+    if (in_bytes < 32) return HOH_E_ARG;  // hohgpu.h, input contract: 32 zero bytes of padding are part of in_bytes
     (void)max_n;
     return decode_common(ctx, d_streams, n_streams, d_in, in_bytes, d_symbols, d_results);
 }
@@ -613,6 +658,7 @@ int hoh_decode_entropy_batch(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size
 int hoh_rans_encode_static(hoh_ctx* ctx, const uint16_t* d_symbols, size_t n, uint32_t stream_len,
                            const uint32_t* d_cum, uint32_t range, uint32_t prob_bits, uint8_t* d_out,
                            uint32_t slab_bytes, uint32_t* d_payload_bytes) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_symbols || !d_cum || !d_out || !d_payload_bytes) return HOH_E_ARG;
     if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > HOH_MAX_PROB_BITS) return HOH_E_UNSUPPORTED;
     if (stream_len == 0 || stream_len % 8 || slab_bytes % 16) return HOH_E_ARG;
@@ -627,6 +673,7 @@ int hoh_rans_encode_static(hoh_ctx* ctx, const uint16_t* d_symbols, size_t n, ui
 int hoh_rans_decode_static(hoh_ctx* ctx, const uint8_t* d_in, uint32_t slab_bytes,
                            const uint32_t* d_payload_bytes, size_t n, uint32_t stream_len,
                            const uint32_t* d_cum, uint32_t range, uint32_t prob_bits, uint16_t* d_symbols) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_symbols || !d_cum || !d_in || !d_payload_bytes) return HOH_E_ARG;
     if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > HOH_MAX_PROB_BITS) return HOH_E_UNSUPPORTED;
     if (stream_len == 0 || stream_len % 8 || slab_bytes % 16) return HOH_E_ARG;
@@ -683,6 +730,7 @@ size_t hoh_encode_images_out_bytes(const hoh_tile_geometry* g, size_t n_images) 
 int hoh_encode_images_s0(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
                          const uint8_t* d_nuke, uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
                          uint8_t* d_packed, size_t packed_cap, uint64_t* d_packed_off) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_rgb || !d_out || !d_results) return HOH_E_ARG;
     if (n_images == 0) return HOH_OK;
     hoh_tile_geometry hg;
@@ -729,9 +777,10 @@ int hoh_encode_images_s0(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, ui
 int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes, const uint64_t* d_packed_off,
                          size_t n_images, uint32_t width, uint32_t height, const uint16_t* d_backref,
                          uint8_t* d_rgb, int32_t* d_status) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_packed || !d_packed_off || !d_rgb || !d_status) return HOH_E_ARG;
-    if (d_backref) return HOH_E_UNSUPPORTED;  // LZ back-reference copies: not in this round
     if (n_images == 0) return HOH_OK;
+    if (packed_bytes < 32) return HOH_E_ARG;  // input contract (hohgpu.h)
     hoh_tile_geometry hg;
     TRY(hoh_tile_geometry_for(width, height, &hg));
     const TileGeom g = to_geom(hg);
@@ -748,8 +797,18 @@ int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_by
                                                                                  d_packed_off, streams, d_status);
     LAUNCHED("k_make_tile_dec_streams");
     TRY(decode_common(ctx, streams, n_streams, d_packed, packed_bytes, resid, results));
-    k_merge_status<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(results, n_streams, d_status);
+    k_merge_status<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(results, n_streams, g, d_backref ? 0u : 1u, d_status);
     LAUNCHED("k_merge_status");
+    if (d_backref) {  // unprediction.hpp:63-65: copies make a pixel depend on any earlier one -> raster walk per plane
+        uint16_t* planes;
+        TRY(scratch_t(ctx, S_D_OUT, n_streams * g.plane_stride, &planes));
+        k_tile_unpredict_s0_backref<<<blocks_for(n_streams, 64), 64, 0, ctx->stream>>>(resid, g, n_tiles, results, d_backref,
+                                                                                      planes, d_status);
+        LAUNCHED("k_tile_unpredict_s0_backref");
+        k_tile_store_s0<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(planes, g, d_rgb);
+        LAUNCHED("k_tile_store_s0");
+        return HOH_OK;
+    }
     if (g.width % 4 == 0 && g.tile_w % 4 == 0) {
         k_tile_unpredict_s0<true><<<blocks_for(n_tiles, kUnpWarps), kUnpWarps * 32, unp_smem, ctx->stream>>>(resid, g, n_tiles, d_rgb);
     } else {
@@ -768,6 +827,19 @@ int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_by
 // are on the small per-chunk offset table (its total decides how many bytes to fetch).
 namespace {
 constexpr int kPipeDepth = 4;
+
+// Whatever way a pipelined host call ends, nothing may still be reading or writing the caller's host buffers.
+struct PipeDrain {
+    hoh_ctx* ctx;
+    explicit PipeDrain(hoh_ctx* c) : ctx(c) {}
+    ~PipeDrain() {
+        if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
+        if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
+        cudaStreamSynchronize(ctx->stream);
+        for (hoh_ctx* ch : ctx->child)
+            if (ch) cudaStreamSynchronize(ch->stream);
+    }
+};
 
 int pipe_init(hoh_ctx* ctx) {
     if (ctx->pipe_ready) return HOH_OK;
@@ -824,6 +896,7 @@ int pipe_leave(hoh_ctx* ctx, uint64_t* launches_before) {
 int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_images, uint32_t width,
                               uint32_t height, uint8_t* packed_host, size_t packed_cap, uint64_t* off_host,
                               hoh_stream_result* results_host) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !rgb_host || !packed_host || !off_host) return HOH_E_ARG;
     if (n_images == 0) return HOH_OK;
     hoh_tile_geometry hg;
@@ -852,6 +925,7 @@ int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_im
         TRY(pinned_off(ctx, k, chunk_streams + 1, &h_off[k]));
     }
     TRY(pipe_enter(ctx));
+    PipeDrain drain(ctx);
     uint64_t base = 0;
     off_host[0] = 0;
     // chunk c: (1) H2D + kernels are queued `depth - 1` chunks ahead of (2) the fetch of its payloads
@@ -902,6 +976,7 @@ int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_im
 int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t packed_bytes,
                               const uint64_t* off_host, size_t n_images, uint32_t width, uint32_t height,
                               uint8_t* rgb_host, int32_t* status_host) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !rgb_host || !packed_host || !off_host) return HOH_E_ARG;
     if (n_images == 0) return HOH_OK;
     hoh_tile_geometry hg;
@@ -934,6 +1009,7 @@ int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t p
         TRY(pinned_off(ctx, k, chunk_streams + 1, &h_off[k]));
     }
     TRY(pipe_enter(ctx));
+    PipeDrain drain(ctx);
     for (size_t c = 0; c < n_chunks; c++) {
         const int b = (int)(c % depth);
         hoh_ctx* ch = ctx->child[b];
@@ -941,7 +1017,7 @@ int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t p
         const size_t n_c = first + per <= n_images ? per : n_images - first;
         const size_t s0 = first * spi, ns = n_c * spi;
         const uint64_t lo = off_host[s0], bytes = off_host[s0 + ns] - lo;
-        const size_t padded = (bytes + 31) & ~(size_t)15;
+        const size_t padded = (bytes + 47) & ~(size_t)15;
         if (c >= (size_t)depth) CK(cudaEventSynchronize(ctx->ev_h2d[b]));  // h_off[b] was read by chunk c-depth's copy
         for (size_t i = 0; i <= ns; i++) h_off[b][i] = off_host[s0 + i] - lo;
         if (c >= (size_t)depth) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[b], 0));  // d_packed[b] / d_off[b] free
@@ -967,6 +1043,7 @@ int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t p
 // =================================================================================================
 int hoh_subtract_green_dev(hoh_ctx* ctx, const uint8_t* d_rgb, size_t pixels, uint16_t* d_g, uint16_t* d_rg,
                            uint16_t* d_bg) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_rgb || !d_g || !d_rg || !d_bg) return HOH_E_ARG;
     if (!pixels) return HOH_OK;
     k_subtract_green<<<grid_cap(pixels, 256), 256, 0, ctx->stream>>>(d_rgb, pixels, d_g, d_rg, d_bg);
@@ -976,6 +1053,7 @@ int hoh_subtract_green_dev(hoh_ctx* ctx, const uint8_t* d_rgb, size_t pixels, ui
 
 int hoh_add_green_dev(hoh_ctx* ctx, const uint16_t* d_g, const uint16_t* d_rg, const uint16_t* d_bg, size_t pixels,
                       uint8_t* d_rgb) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_rgb || !d_g || !d_rg || !d_bg) return HOH_E_ARG;
     if (!pixels) return HOH_OK;
     k_add_green<<<grid_cap(pixels, 256), 256, 0, ctx->stream>>>(d_g, d_rg, d_bg, pixels, d_rgb);
@@ -984,6 +1062,7 @@ int hoh_add_green_dev(hoh_ctx* ctx, const uint16_t* d_g, const uint16_t* d_rg, c
 }
 
 int hoh_channel_picker_dev(hoh_ctx* ctx, const uint8_t* d_src, size_t n_px, int total, int target, uint16_t* d_out) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_src || !d_out || total <= 0 || target < 0 || target >= total) return HOH_E_ARG;
     if (n_px == 0) return HOH_OK;
     k_channel_picker<<<grid_cap(n_px, 256), 256, 0, ctx->stream>>>(d_src, n_px, (uint32_t)total, (uint32_t)target, d_out);
@@ -993,6 +1072,7 @@ int hoh_channel_picker_dev(hoh_ctx* ctx, const uint8_t* d_src, size_t n_px, int 
 
 int hoh_predict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
                              uint16_t* d_resid) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_planes || !d_resid || w <= 0 || h <= 0 || depth < 1 || depth > 9) return HOH_E_ARG;
     if (!n_planes) return HOH_OK;
     k_predict_fastpath<<<grid_cap((uint64_t)n_planes * ((h + kFastpathBand - 1) / kFastpathBand) * 256, 256, 148u * 64u), w >= 192 ? 256 : 64, 0, ctx->stream>>>(d_planes, n_planes, w, h,
@@ -1003,6 +1083,7 @@ int hoh_predict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pl
 
 int hoh_unpredict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_planes, int w, int h, int depth,
                                const uint16_t* d_backref, uint16_t* d_planes) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_planes || !d_resid || w <= 0 || h <= 0 || depth < 1 || depth > 9) return HOH_E_ARG;
     if (!n_planes) return HOH_OK;
     TRY(ensure_smem_opt_in(ctx));
@@ -1020,6 +1101,7 @@ int hoh_unpredict_fastpath_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_p
 
 int hoh_predict_all_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
                         int x_tiles, int y_tiles, const uint16_t* d_tile_maps, uint16_t* d_resid) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_planes || !d_resid || !d_tile_maps || w <= 0 || h <= 0 || depth < 1 || depth > 9 || x_tiles <= 0 ||
         y_tiles <= 0)
         return HOH_E_ARG;
@@ -1031,6 +1113,7 @@ int hoh_predict_all_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes,
 int hoh_unpredict_all_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_planes, int w, int h, int depth,
                           int x_tiles, int y_tiles, const uint16_t* d_tile_maps, const uint16_t* d_backref,
                           uint16_t* d_planes) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_planes || !d_resid || !d_tile_maps || w <= 0 || h <= 0 || depth < 1 || depth > 9 || x_tiles <= 0 ||
         y_tiles <= 0)
         return HOH_E_ARG;
@@ -1048,6 +1131,7 @@ int hoh_unpredict_all_dev(hoh_ctx* ctx, const uint16_t* d_resid, size_t n_planes
 int hoh_predict_section_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
                             int x_tiles, int y_tiles, const uint16_t* d_masks, int n_masks, uint16_t* d_resid,
                             uint32_t cell_cap, uint32_t* d_counts) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_planes || !d_resid || !d_masks || !d_counts || w <= 0 || h <= 0 || depth < 1 || depth > 9 ||
         x_tiles <= 0 || y_tiles <= 0 || n_masks <= 0)
         return HOH_E_ARG;
@@ -1132,6 +1216,7 @@ extern "C" {
 
 int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth,
                              int mode, uint16_t* d_tile_maps, uint8_t* d_index_lists, uint16_t* d_resid) {
+    DeviceGuard guard_(ctx);
     return predictor_search_impl(ctx, d_planes, n_planes, w, h, depth, mode, d_tile_maps, d_index_lists, d_resid,
                                  (uint64_t)w * h);
 }
@@ -1174,6 +1259,7 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
                            int mode, unsigned flags, const uint8_t* d_nuke, size_t nuke_stride, uint32_t planes_per_map,
                            uint8_t* d_out, size_t out_bytes, hoh_stream_result* d_results,
                            uint8_t* d_packed, size_t packed_cap, uint64_t* d_packed_off) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_planes || !d_out || !d_results || w <= 0 || h <= 0 || depth < 1 || depth > 9 || mode < 0 || mode > 4)
         return HOH_E_ARG;
     if (d_nuke && (planes_per_map == 0 || nuke_stride < (size_t)w * h)) return HOH_E_ARG;
@@ -1411,6 +1497,7 @@ extern "C" {
 int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, int w, int h, int distance,
                           unsigned flags, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
                           uint32_t* d_lz_size, int32_t* d_status) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_rgb || !d_nuke || !d_lz || !d_lz_size || w <= 0 || h <= 0 || distance < 0 || distance > 16)
         return HOH_E_ARG;
     if (n_tiles == 0) return HOH_OK;
@@ -1429,6 +1516,7 @@ int hoh_find_lz_rgb_batch(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_tiles, in
 int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
                        int distance, unsigned flags, const int32_t* d_bonus, uint8_t* d_nuke, uint8_t* d_lz, size_t lz_stride,
                        uint32_t* d_lz_size, int32_t* d_status) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_rgb || !d_nuke || !d_lz || !d_lz_size || distance < 0 || distance > 16) return HOH_E_ARG;
     if (n_images == 0) return HOH_OK;
     hoh_tile_geometry hg;
@@ -1448,6 +1536,7 @@ int hoh_find_lz_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint
 int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint32_t width, uint32_t height,
                       int mode, unsigned flags, uint8_t* d_packed, size_t packed_cap, uint64_t* d_tile_off,
                       hoh_tile_result* d_tiles) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_rgb || !d_packed || !d_tile_off || !d_tiles || mode < 0 || mode > 4) return HOH_E_ARG;
     hoh_tile_geometry hg;
     TRY(hoh_tile_geometry_for(width, height, &hg));
@@ -1560,8 +1649,10 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
 // -------------------------------------------------------------------------------------------------
 int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes, const uint64_t* d_tile_off,
                       size_t n_images, uint32_t width, uint32_t height, uint8_t* d_rgb, int32_t* d_status) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !d_packed || !d_tile_off || !d_rgb || !d_status) return HOH_E_ARG;
     if (n_images == 0) return HOH_OK;
+    if (packed_bytes < 32) return HOH_E_ARG;  // input contract (hohgpu.h)
     hoh_tile_geometry hg;
     TRY(hoh_tile_geometry_for(width, height, &hg));
     const TileGeom g = to_geom(hg);
@@ -1650,12 +1741,191 @@ int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes
     return HOH_OK;
 }
 
+// -------------------------------------------------------------------------------------------------
+// host-buffer forms of the two whole-tile calls (what tools/choh_batch.cpp / dhoh_batch.cpp call)
+// -------------------------------------------------------------------------------------------------
+} // extern "C" (reopened below)
+namespace {
+// Images per chunk of a whole-tile host call: at most four chunks (a launch of the entropy kernels lasts as long as
+// one stream's chain, so few large chunks beat many small ones; two are in flight), at least ~64 MB of pixels, and
+// the double-buffered staging (raw + packed, twice) must leave most of the device to the codec's own scratch.
+size_t tile_chunk_images(size_t n_images, size_t raw_per_image) {
+    size_t per = (n_images + 3) / 4;
+    const size_t min_per = (64u << 20) / (raw_per_image ? raw_per_image : 1) + 1;
+    if (per < min_per) per = min_per;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const size_t cap = free_b / 8 / (raw_per_image * 5 + 1);  // 2 x (raw + 1.5 raw packed) within an eighth of what is free
+        if (cap >= 1 && per > cap) per = cap;
+    }
+    if (per > n_images) per = n_images;
+    return per ? per : 1;
+}
+}  // namespace
+extern "C" {
+
+int hoh_encode_images_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_images, uint32_t width, uint32_t height,
+                           int mode, unsigned flags, uint8_t* packed_host, size_t packed_cap, uint64_t* tile_off_host,
+                           hoh_tile_result* tiles_host) {
+    DeviceGuard guard_(ctx);
+    if (!ctx || !rgb_host || !packed_host || !tile_off_host || !tiles_host || mode < 0 || mode > 4) return HOH_E_ARG;
+    tile_off_host[0] = 0;
+    if (n_images == 0) return HOH_OK;
+    hoh_tile_geometry hg;
+    TRY(hoh_tile_geometry_for(width, height, &hg));
+    TRY(pipe_init(ctx));
+    const size_t raw1 = (size_t)width * height * 3, tpi = hg.tiles_per_image;
+    const size_t per = tile_chunk_images(n_images, raw1);
+    const size_t n_chunks = (n_images + per - 1) / per;
+    const size_t chunk_tiles = per * tpi;
+    const size_t dev_cap = per * raw1 + per * raw1 / 2 + 8192 * chunk_tiles;
+    constexpr int kBuf = 2;
+    uint8_t *d_rgb[kBuf], *d_packed[kBuf];
+    uint64_t *d_off[kBuf], *h_off[kBuf];
+    hoh_tile_result* d_tiles[kBuf];
+    const int nbuf = n_chunks < (size_t)kBuf ? (int)n_chunks : kBuf;
+    hoh_ctx* stage = ctx->child[2];  // staging lives in a child that the codec itself never uses (it forks into child 0/1)
+    {
+        uint8_t *rgb2, *packed2;
+        uint64_t* off2;
+        hoh_tile_result* tiles2;
+        TRY(scratch_t(stage, S_IO_A, nbuf * per * raw1, &rgb2));
+        TRY(scratch_t(stage, S_IO_B, nbuf * dev_cap, &packed2));
+        TRY(scratch_t(stage, S_IO_C, nbuf * (chunk_tiles + 1), &off2));
+        TRY(scratch_t(stage, S_IO_D, nbuf * chunk_tiles, &tiles2));
+        for (int k = 0; k < nbuf; k++) {
+            d_rgb[k] = rgb2 + (size_t)k * per * raw1;
+            d_packed[k] = packed2 + (size_t)k * dev_cap;
+            d_off[k] = off2 + (size_t)k * (chunk_tiles + 1);
+            d_tiles[k] = tiles2 + (size_t)k * chunk_tiles;
+            TRY(pinned_off(ctx, k, chunk_tiles + 1, &h_off[k]));
+        }
+    }
+    PipeDrain drain(ctx);
+    CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_start, 0));
+    std::vector<uint64_t> chunk_base(n_chunks, 0);
+    uint64_t base = 0;
+    for (size_t c = 0; c <= n_chunks; c++) {
+        if (c < n_chunks) {  // copy in and code chunk c
+            const int b = (int)(c % nbuf);
+            const size_t first = c * per, n_c = std::min(per, n_images - first);
+            if (c >= (size_t)nbuf) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[b], 0));  // d_rgb[b] consumed
+            CK(cudaMemcpyAsync(d_rgb[b], rgb_host + first * raw1, n_c * raw1, cudaMemcpyHostToDevice, ctx->s_h2d));
+            CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+            if (c >= (size_t)nbuf) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));  // d_packed[b] fetched
+            TRY(hoh_encode_images(ctx, d_rgb[b], n_c, width, height, mode, flags, d_packed[b], dev_cap, d_off[b], d_tiles[b]));
+            CK(cudaEventRecord(ctx->ev_comp[b], ctx->stream));
+            CK(cudaMemcpyAsync(h_off[b], d_off[b], (n_c * tpi + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaEventRecord(ctx->ev_off[b], ctx->stream));
+        }
+        if (c >= 1) {  // fetch chunk c-1 while chunk c is being coded
+            const size_t pc = c - 1;
+            const int p = (int)(pc % nbuf);
+            const size_t pfirst = pc * per, n_p = std::min(per, n_images - pfirst);
+            CK(cudaEventSynchronize(ctx->ev_off[p]));
+            const uint64_t total = h_off[p][n_p * tpi];
+            if (total > dev_cap || base + total > packed_cap) return HOH_E_CAPACITY;
+            CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[p], 0));
+            CK(cudaMemcpyAsync(packed_host + base, d_packed[p], total, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(cudaMemcpyAsync(tiles_host + pfirst * tpi, d_tiles[p], n_p * tpi * sizeof(hoh_tile_result),
+                               cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(cudaEventRecord(ctx->ev_d2h[p], ctx->s_d2h));
+            for (size_t i = 1; i <= n_p * tpi; i++) tile_off_host[pfirst * tpi + i] = base + h_off[p][i];
+            chunk_base[pc] = base;
+            base += total;
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    for (size_t c = 0; c < n_chunks; c++) {  // tile records carry chunk-relative offsets: rebase
+        const size_t first = c * per * tpi, cnt = std::min(per, n_images - c * per) * tpi;
+        for (size_t i = 0; i < cnt; i++) tiles_host[first + i].start += chunk_base[c];
+    }
+    return HOH_OK;
+}
+
+int hoh_decode_images_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t packed_bytes, const uint64_t* tile_off_host,
+                           size_t n_images, uint32_t width, uint32_t height, uint8_t* rgb_host, int32_t* status_host) {
+    DeviceGuard guard_(ctx);
+    if (!ctx || !packed_host || !tile_off_host || !rgb_host || !status_host) return HOH_E_ARG;
+    if (n_images == 0) return HOH_OK;
+    hoh_tile_geometry hg;
+    TRY(hoh_tile_geometry_for(width, height, &hg));
+    TRY(pipe_init(ctx));
+    const size_t raw1 = (size_t)width * height * 3, tpi = hg.tiles_per_image;
+    const size_t per = tile_chunk_images(n_images, raw1);
+    const size_t n_chunks = (n_images + per - 1) / per;
+    const size_t chunk_tiles = per * tpi;
+    size_t max_packed = 0;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t t0 = c * chunk_tiles, t1 = std::min((c + 1) * per, n_images) * tpi;
+        if (tile_off_host[t1] < tile_off_host[t0] || tile_off_host[t1] > packed_bytes) return HOH_E_ARG;
+        max_packed = std::max<size_t>(max_packed, tile_off_host[t1] - tile_off_host[t0]);
+    }
+    const size_t padded_cap = (max_packed + 63) & ~(size_t)15;
+    constexpr int kBuf = 2;
+    const int nbuf = n_chunks < (size_t)kBuf ? (int)n_chunks : kBuf;
+    hoh_ctx* stage = ctx->child[2];
+    uint8_t *d_rgb[kBuf], *d_packed[kBuf];
+    uint64_t *d_off[kBuf], *h_off[kBuf];
+    int32_t* d_st[kBuf];
+    {
+        uint8_t *rgb2, *packed2;
+        uint64_t* off2;
+        int32_t* st2;
+        TRY(scratch_t(stage, S_IO_A, nbuf * per * raw1, &rgb2));
+        TRY(scratch_t(stage, S_IO_B, nbuf * padded_cap, &packed2));
+        TRY(scratch_t(stage, S_IO_C, nbuf * (chunk_tiles + 1), &off2));
+        TRY(scratch_t(stage, S_IO_D, nbuf * chunk_tiles, &st2));
+        for (int k = 0; k < nbuf; k++) {
+            d_rgb[k] = rgb2 + (size_t)k * per * raw1;
+            d_packed[k] = packed2 + (size_t)k * padded_cap;
+            d_off[k] = off2 + (size_t)k * (chunk_tiles + 1);
+            d_st[k] = st2 + (size_t)k * chunk_tiles;
+            TRY(pinned_off(ctx, k, chunk_tiles + 1, &h_off[k]));
+        }
+    }
+    PipeDrain drain(ctx);
+    CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_start, 0));
+    for (size_t c = 0; c < n_chunks; c++) {
+        const int b = (int)(c % nbuf);
+        const size_t first = c * per, n_c = std::min(per, n_images - first);
+        const size_t t0 = first * tpi, nt = n_c * tpi;
+        const uint64_t lo = tile_off_host[t0], bytes = tile_off_host[t0 + nt] - lo;
+        const size_t padded = (bytes + 47) & ~(size_t)15;  // >= 32 zero bytes behind the last tile (hohgpu.h, decode contract)
+        if (c >= (size_t)nbuf) CK(cudaEventSynchronize(ctx->ev_h2d[b]));  // h_off[b] was read by chunk c-nbuf's copy
+        for (size_t i = 0; i <= nt; i++) h_off[b][i] = tile_off_host[t0 + i] - lo;
+        if (c >= (size_t)nbuf) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[b], 0));  // d_packed[b] / d_off[b] consumed
+        CK(cudaMemsetAsync(d_packed[b] + (bytes & ~(size_t)15), 0, padded - (bytes & ~(size_t)15), ctx->s_h2d));
+        CK(cudaMemcpyAsync(d_packed[b], packed_host + lo, bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaMemcpyAsync(d_off[b], h_off[b], (nt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+        if (c >= (size_t)nbuf) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));  // d_rgb[b] fetched
+        // a tile that fails to decode leaves its pixels untouched: make "untouched" mean zero
+        CK(cudaMemsetAsync(d_rgb[b], 0, n_c * raw1, ctx->stream));
+        TRY(hoh_decode_images(ctx, d_packed[b], padded, d_off[b], n_c, width, height, d_rgb[b], d_st[b]));
+        CK(cudaEventRecord(ctx->ev_comp[b], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[b], 0));
+        CK(cudaMemcpyAsync(rgb_host + first * raw1, d_rgb[b], n_c * raw1, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaMemcpyAsync(status_host + t0, d_st[b], nt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+    }
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    return HOH_OK;
+}
+
 // =================================================================================================
 // compat shims (host pointers)
 // =================================================================================================
 
 int hoh_encode_entropy(hoh_ctx* ctx, const uint16_t* symbols, size_t n, size_t range, uint8_t* out, size_t out_cap,
                        uint32_t prob_bits, size_t* out_size, int* stream_status) {
+    DeviceGuard guard_(ctx);
     if (!ctx || (!symbols && n) || !out || !out_size) return HOH_E_ARG;
     if (range == 0 || range > HOH_MAX_RANGE || prob_bits == 0 || prob_bits > HOH_MAX_PROB_BITS || n > 0xfffffff0ull)
         return HOH_E_UNSUPPORTED;
@@ -1687,6 +1957,7 @@ int hoh_encode_entropy(hoh_ctx* ctx, const uint16_t* symbols, size_t n, size_t r
 
 int hoh_encode_entropy_8bit(hoh_ctx* ctx, const uint8_t* symbols, size_t n, size_t range, uint8_t* out,
                             size_t out_cap, uint32_t prob_bits, size_t* out_size, int* stream_status) {
+    DeviceGuard guard_(ctx);
     // entropy_encoding.hpp:283-303 widens to u16 and calls the 16-bit form
     std::vector<uint16_t> wide(n);
     for (size_t i = 0; i < n; i++) wide[i] = symbols[i];
@@ -1695,9 +1966,10 @@ int hoh_encode_entropy_8bit(hoh_ctx* ctx, const uint8_t* symbols, size_t n, size
 
 int hoh_decode_entropy(hoh_ctx* ctx, const uint8_t* in, size_t in_size, size_t* byte_pointer, uint16_t* symbols,
                        size_t symbols_cap, size_t* symbol_size, unsigned flags, int* stream_status) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !in || !byte_pointer || !symbol_size || (!symbols && symbols_cap)) return HOH_E_ARG;
     uint8_t* d_in;
-    const size_t padded = (in_size + 31) & ~(size_t)15;
+    const size_t padded = (in_size + 47) & ~(size_t)15;
     TRY(scratch_t(ctx, S_IO_A, padded, &d_in));
     CK(cudaMemsetAsync(d_in + (in_size & ~(size_t)15), 0, padded - (in_size & ~(size_t)15), ctx->stream));
     CK(cudaMemcpyAsync(d_in, in, in_size, cudaMemcpyHostToDevice, ctx->stream));
@@ -1726,6 +1998,7 @@ int hoh_decode_entropy(hoh_ctx* ctx, const uint8_t* in, size_t in_size, size_t* 
 
 int hoh_normalize_freqs(hoh_ctx* ctx, uint32_t* freqs, uint32_t* cum_freqs, size_t size, uint32_t target_total,
                         int* stream_status) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !freqs || !cum_freqs || size == 0) return HOH_E_ARG;
     if (size > HOH_MAX_RANGE) return HOH_E_UNSUPPORTED;
     uint32_t *d_f, *d_c;
@@ -1746,6 +2019,7 @@ int hoh_normalize_freqs(hoh_ctx* ctx, uint32_t* freqs, uint32_t* cum_freqs, size
 
 int hoh_subtract_green(hoh_ctx* ctx, const uint8_t* rgb, size_t size, uint16_t* green, uint16_t* red_g,
                        uint16_t* blue_g) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !rgb || !green || !red_g || !blue_g) return HOH_E_ARG;
     const size_t px = size / 3;
     uint8_t* d_rgb;
@@ -1761,6 +2035,7 @@ int hoh_subtract_green(hoh_ctx* ctx, const uint8_t* rgb, size_t size, uint16_t* 
 
 int hoh_add_green(hoh_ctx* ctx, const uint16_t* green, const uint16_t* red_g, const uint16_t* blue_g, size_t pixels,
                   uint8_t* rgb) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !rgb || !green || !red_g || !blue_g) return HOH_E_ARG;
     uint16_t* d_pl;
     uint8_t* d_rgb;
@@ -1775,6 +2050,7 @@ int hoh_add_green(hoh_ctx* ctx, const uint16_t* green, const uint16_t* red_g, co
 }
 
 int hoh_channelpredict_fastpath(hoh_ctx* ctx, const uint16_t* data, int w, int h, int depth, uint16_t* out) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !data || !out || w <= 0 || h <= 0) return HOH_E_ARG;
     const size_t px = (size_t)w * h;
     uint16_t *d_in, *d_out;
@@ -1786,6 +2062,7 @@ int hoh_channelpredict_fastpath(hoh_ctx* ctx, const uint16_t* data, int w, int h
 
 int hoh_channelpredict_section(hoh_ctx* ctx, const uint16_t* data, int w, int h, int depth, int x_tiles, int y_tiles,
                                int x, int y, uint16_t predictor, uint16_t* out, size_t out_cap, size_t* out_count) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !data || !out || !out_count || w <= 0 || h <= 0 || x_tiles <= 0 || y_tiles <= 0 || x < 0 || y < 0 ||
         x >= x_tiles || y >= y_tiles)
         return HOH_E_ARG;
@@ -1810,6 +2087,7 @@ int hoh_channelpredict_section(hoh_ctx* ctx, const uint16_t* data, int w, int h,
 
 int hoh_channelpredict_all(hoh_ctx* ctx, const uint16_t* data, int w, int h, int depth, int x_tiles, int y_tiles,
                            const uint16_t* tile_map, uint16_t* out) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !data || !out || !tile_map || w <= 0 || h <= 0 || x_tiles <= 0 || y_tiles <= 0) return HOH_E_ARG;
     const size_t px = (size_t)w * h;
     uint16_t *d_in, *d_map, *d_out;
@@ -1822,6 +2100,7 @@ int hoh_channelpredict_all(hoh_ctx* ctx, const uint16_t* data, int w, int h, int
 
 int hoh_unpredict_all(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, int w, int h, int depth, int x_tiles,
                       int y_tiles, const uint16_t* tile_map, const uint16_t* backref, uint16_t* out) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !resid || !out || !tile_map || w <= 0 || h <= 0 || x_tiles <= 0 || y_tiles <= 0) return HOH_E_ARG;
     const size_t px = (size_t)w * h;
     if (n_resid > px) n_resid = px;
@@ -1838,6 +2117,7 @@ int hoh_unpredict_all(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, int w
 
 int hoh_unpredict_fastpath(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, int w, int h, int depth,
                            const uint16_t* backref, uint16_t* out) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !resid || !out || w <= 0 || h <= 0) return HOH_E_ARG;
     const size_t px = (size_t)w * h;
     if (n_resid > px) n_resid = px;
@@ -1853,6 +2133,7 @@ int hoh_unpredict_fastpath(hoh_ctx* ctx, const uint16_t* resid, size_t n_resid, 
 
 int hoh_predictor_search(hoh_ctx* ctx, const uint16_t* plane, int w, int h, int depth, int mode, uint16_t* tile_map,
                          uint8_t* index_list, uint16_t* final_resid) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !plane || !tile_map || !index_list || w <= 0 || h <= 0) return HOH_E_ARG;
     const size_t px = (size_t)w * h;
     const size_t cells = (size_t)((w + 39) / 40) * ((h + 39) / 40);
@@ -1871,6 +2152,7 @@ int hoh_predictor_search(hoh_ctx* ctx, const uint16_t* plane, int w, int h, int 
 
 int hoh_find_lz_rgb(hoh_ctx* ctx, const uint8_t* source, size_t size, int width, int height, uint8_t* lz_symbols,
                     size_t lz_cap, uint8_t* nukemap, int distance, int break_even_bonus, size_t* lz_size) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !source || !lz_symbols || !nukemap || !lz_size || width <= 0 || height <= 0) return HOH_E_ARG;
     const size_t npx = (size_t)width * height;
     if (size != npx * 3) return HOH_E_ARG;
@@ -1897,6 +2179,7 @@ int hoh_find_lz_rgb(hoh_ctx* ctx, const uint8_t* source, size_t size, int width,
 }
 
 int hoh_channel_picker(hoh_ctx* ctx, const uint8_t* src, size_t size, int total, int target, uint16_t* out) {
+    DeviceGuard guard_(ctx);
     if (!ctx || !src || !out || total <= 0 || size % (size_t)total) return HOH_E_ARG;
     uint8_t* d_in;
     uint16_t* d_out;

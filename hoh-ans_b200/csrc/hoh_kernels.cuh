@@ -4483,4 +4483,71 @@ __global__ void __launch_bounds__(256) k_dt_store(TileSel sel, uint64_t first_im
     }
 }
 
+// Mode-0 tile back end WITH LZ back-references (hoh_decode_images_s0, d_backref != NULL): a copied pixel may
+// depend on any earlier pixel of its tile (unprediction.hpp:63-65), so the wavefront does not apply; one thread
+// walks one channel plane in raster order.  Residuals are dense (only the pixels no match covers have one,
+// layer_encode.hpp:93-99); a stream that holds fewer or more residuals than the map leaves uncovered is reported.
+__global__ void __launch_bounds__(64) k_tile_unpredict_s0_backref(const uint16_t* __restrict__ resid, TileGeom g,
+                                                                  uint64_t n_tiles, const hoh_dec_result* __restrict__ res,
+                                                                  const uint16_t* __restrict__ backref,
+                                                                  uint16_t* __restrict__ planes,
+                                                                  int32_t* __restrict__ status) {
+    const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= n_tiles * 3u) return;
+    if (status[s] != HOH_S_OK) return;
+    const uint64_t t = s / 3u;
+    const uint32_t ch = (uint32_t)(s % 3u);
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
+    const int c = ch == 0 ? 256 : 512, half = c >> 1;
+    const uint16_t* r = resid + s * (uint64_t)g.plane_stride;
+    const uint16_t* br = backref + t * (uint64_t)g.plane_stride;
+    uint16_t* o = planes + s * (uint64_t)g.plane_stride;
+    const uint32_t have = res[s].n;
+    uint32_t k = 0;
+    bool bad = false;
+    for (uint32_t y = 0; y < th; y++)
+        for (uint32_t x = 0; x < tw; x++) {
+            const uint32_t at = y * tw + x;
+            const uint32_t b = br[at];
+            if (b) {
+                if (b > at) {
+                    bad = true;
+                    o[at] = (uint16_t)half;
+                } else {
+                    o[at] = o[at - b];
+                }
+                continue;
+            }
+            const int L = x ? o[at - 1] : half;
+            const int T = y ? o[at - tw] : half;
+            const int TL = (x && y) ? o[at - tw - 1] : half;
+            const int rv = k < have ? r[k] : half;
+            k++;
+            o[at] = (uint16_t)((rv + p_med_grad(T, L, TL) - half) & (c - 1));
+        }
+    if (bad || k != have) status[s] = HOH_S_BAD_LAYER;
+}
+
+// planes (G, R-G, B-G at s*plane_stride) -> RGB8 in the image: algebraic inverse of channel.hpp:73-79 + tile scatter
+__global__ void __launch_bounds__(256) k_tile_store_s0(const uint16_t* __restrict__ planes, TileGeom g,
+                                                       uint8_t* __restrict__ rgb) {
+    const uint64_t t = blockIdx.x;
+    const uint64_t image = t / g.tiles_per_image;
+    uint32_t x0, y0, tw, th;
+    tile_rect(g, (uint32_t)(t % g.tiles_per_image), x0, y0, tw, th);
+    uint8_t* img = rgb + image * (uint64_t)g.width * g.height * 3u;
+    const uint16_t* a = planes + (t * 3u) * (uint64_t)g.plane_stride;
+    const uint16_t* b = a + g.plane_stride;
+    const uint16_t* c = b + g.plane_stride;
+    for (uint32_t i = threadIdx.x; i < tw * th; i += blockDim.x) {
+        const uint32_t x = i % tw, y = i / tw;
+        uint8_t* o = img + ((uint64_t)(y0 + y) * g.width + x0 + x) * 3u;
+        const uint32_t gr = a[i];
+        o[1] = (uint8_t)gr;
+        o[0] = (uint8_t)((b[i] + gr - 256u) & 255u);
+        o[2] = (uint8_t)((c[i] + gr - 256u) & 255u);
+    }
+}
+
 }  // namespace hohk

@@ -115,6 +115,8 @@ SIGNATURES = {
     "hoh_predictor_search_dev": (_int, [_vp, _vp, _sz, _int, _int, _int, _int, _vp, _vp, _vp]),
     "hoh_encode_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, C.c_uint, _vp, _sz, _vp, _vp]),
     "hoh_decode_images": (_int, [_vp, _vp, _sz, _vp, _sz, _u32, _u32, _vp, _vp]),
+    "hoh_encode_images_host": (_int, [_vp, _vp, _sz, _u32, _u32, _int, C.c_uint, _vp, _sz, _vp, _vp]),
+    "hoh_decode_images_host": (_int, [_vp, _vp, _sz, _vp, _sz, _u32, _u32, _vp, _vp]),
     "hoh_find_lz_stride": (_sz, [_int, _int]),
     "hoh_find_lz_rgb_batch": (_int, [_vp, _vp, _sz, _int, _int, _int, C.c_uint, _vp, _vp, _vp, _sz, _vp, _vp]),
     "hoh_find_lz_images": (_int, [_vp, _vp, _sz, _u32, _u32, _int, C.c_uint, _vp, _vp, _vp, _sz, _vp, _vp]),
@@ -433,7 +435,7 @@ class HohGpu:
         for i, (o, cpt) in enumerate(zip(offsets, caps)):
             desc[i]["in_off"], desc[i]["sym_off"], desc[i]["sym_cap"], desc[i]["flags"] = o, sym_off, cpt, flags
             sym_off += (cpt + 7) & ~7
-        padded = np.concatenate([blob, np.zeros(32 - len(blob) % 16, np.uint8)])
+        padded = np.concatenate([blob, np.zeros(48 - len(blob) % 16, np.uint8)])
         d_in = self.alloc(padded.nbytes).upload(padded)
         d_desc = self.alloc(desc.nbytes).upload(desc)
         d_sym = self.alloc(max(sym_off, 8) * 2)
@@ -601,6 +603,32 @@ class HohGpu:
                 b.free()
         return rgb, st
 
+    def encode_images_host(self, rgb, n_images, width, height, mode, flags=0):
+        """hoh_encode_images_host: pinned host buffers in and out, chunked and pipelined inside the library ->
+        (packed u8 view, tile offsets, TILE_DT records)."""
+        g = self.tile_geometry(width, height)
+        n_tiles = n_images * g.tiles_per_image
+        raw = n_images * width * height * 3
+        src = self.host_alloc(raw)
+        src[:] = np.asarray(rgb, dtype=np.uint8).ravel()
+        cap = raw + raw // 2 + 8192 * n_tiles
+        packed = self.host_alloc(cap)
+        off = np.zeros(n_tiles + 1, np.uint64)
+        rec = np.zeros(n_tiles, TILE_DT)
+        self._ck(self.lib.hoh_encode_images_host(self.ctx, _ptr(src), n_images, width, height, mode, flags, _ptr(packed),
+                                                 cap, _ptr(off), _ptr(rec)), "hoh_encode_images_host")
+        return packed[:int(off[-1])], off, rec
+
+    def decode_images_host(self, packed, off, n_images, width, height):
+        """hoh_decode_images_host: exact-size host buffers -> (rgb, per-tile status)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        rgb = self.host_alloc(n_images * width * height * 3)
+        st = np.zeros(len(off) - 1, np.int32)
+        self._ck(self.lib.hoh_decode_images_host(self.ctx, _ptr(packed), packed.size, _ptr(off), n_images, width, height,
+                                                 _ptr(rgb), _ptr(st)), "hoh_decode_images_host")
+        return rgb, st
+
     def layer_encode_batch(self, planes, n_planes, w, h, depth, mode, nuke=None, planes_per_map=1, flags=0):
         """layer_encode.hpp:11 for n_planes planes of the same shape -> list of (payload bytes, status, kept slot).
         nuke: (n_planes / planes_per_map) maps of w*h bytes, or None."""
@@ -633,24 +661,31 @@ class HohGpu:
         return [(packed[int(off[i]):int(off[i + 1])].tobytes(), int(res[i]["status"]), int(res[i]["stored"]))
                 for i in range(n_planes)]
 
-    def decode_images_s0(self, packed, offsets, n_images, width, height):
-        """Host-buffer convenience over hoh_decode_images_s0 -> (rgb, per-stream status)."""
+    def decode_images_s0(self, packed, offsets, n_images, width, height, backref=None):
+        """Host-buffer convenience over hoh_decode_images_s0 -> (rgb, per-stream status).  backref: u16 maps, tile t's
+        at t * plane_stride (tile_w*tile_h rounded up to 8), or None."""
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         g = self.tile_geometry(width, height)
         n_streams = n_images * g.streams_per_image
-        padded = np.concatenate([packed, np.zeros(32 - len(packed) % 16, np.uint8)])
+        padded = np.concatenate([packed, np.zeros(48 - len(packed) % 16, np.uint8)])
         d_packed = self.alloc(padded.nbytes).upload(padded)
         d_off = self.alloc(offsets.nbytes).upload(offsets)
         d_rgb = self.alloc(n_images * width * height * 3)
         d_rgb.zero()
         d_st = self.alloc(n_streams * 4)
+        d_br = None
+        if backref is not None:
+            backref = np.ascontiguousarray(backref, dtype=np.uint16).ravel()
+            d_br = self.alloc(backref.nbytes).upload(backref)
         try:
             self._ck(self.lib.hoh_decode_images_s0(self.ctx, d_packed.ptr, padded.nbytes, d_off.ptr, n_images, width,
-                                                   height, None, d_rgb.ptr, d_st.ptr), "hoh_decode_images_s0")
+                                                   height, d_br.ptr if d_br else None, d_rgb.ptr, d_st.ptr),
+                     "hoh_decode_images_s0")
             rgb = d_rgb.download(np.uint8, n_images * width * height * 3)
             st = d_st.download(np.int32, n_streams)
         finally:
-            for b in (d_packed, d_off, d_rgb, d_st):
-                b.free()
+            for b in (d_packed, d_off, d_rgb, d_st, d_br):
+                if b is not None:
+                    b.free()
         return rgb, st

@@ -167,7 +167,13 @@ typedef struct hoh_dec_result {
     uint32_t table_mode;
 } hoh_dec_result;
 
-/* decode_entropy for every stream.  in_bytes = size of d_in (reads are clamped to it). */
+/* decode_entropy for every stream.  in_bytes = size of d_in.
+ * INPUT CONTRACT of every device-pointer decode entry point (this one, hoh_decode_images_s0, hoh_decode_images):
+ * the payload words are fetched as aligned 16-byte vectors and never at or past the last whole 16-byte line of the
+ * buffer, so d_in must be READABLE AND ZERO for at least 32 bytes behind the last stream byte, and in_bytes must
+ * include that padding (pass in_bytes = data bytes + 32, rounded as you like).  in_bytes < 32 is HOH_E_ARG.  The
+ * host-pointer forms (hoh_decode_entropy, hoh_decode_images_s0_host, hoh_decode_images_host) take exact sizes and
+ * add the padding themselves. */
 int hoh_decode_entropy_batch(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n_streams,
                              const uint8_t* d_in, size_t in_bytes, uint16_t* d_symbols,
                              hoh_dec_result* d_results, uint32_t max_n);
@@ -220,8 +226,13 @@ int hoh_encode_images_s0(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, ui
 /* Inverse: channel payloads (as produced above: d_packed + d_packed_off, n_images*streams_per_image
  * of them, each starting with the 5-byte mode-0 channel header) -> interleaved RGB8 images.
  * The un-prediction is the exact inverse of channelpredict_fastpath (pure MED) and the
- * colour inverse is the algebraic inverse of channel.hpp:73-79; d_backref = NULL or the
- * LEMPEL_BACKREF map (u16 per pixel, tile-major) for unprediction.hpp:63-65 copies. */
+ * colour inverse is the algebraic inverse of channel.hpp:73-79.  d_backref = NULL (the fused
+ * wavefront kernel) or the LEMPEL_BACKREF maps for the copies of unprediction.hpp:63-65: one u16 per pixel, tile
+ * t's map in raster order at t * plane_stride, plane_stride = tile_w*tile_h rounded up to 8 (the layout of d_nuke
+ * on the encode side); 0 = coded pixel, b > 0 = copy of the pixel b positions earlier in the tile.  With a map the
+ * residual streams are dense (covered pixels have none) and the un-prediction is a raster walk per plane; a stream
+ * whose symbol count differs from the number of uncovered pixels gets HOH_S_BAD_LAYER.
+ * packed_bytes: see the input contract at hoh_decode_entropy_batch (32 zero bytes of padding included). */
 int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes,
                          const uint64_t* d_packed_off, size_t n_images, uint32_t width,
                          uint32_t height, const uint16_t* d_backref, uint8_t* d_rgb,
@@ -290,7 +301,10 @@ int hoh_predictor_search_dev(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_pl
 
 typedef struct hoh_tile_result {
     uint64_t start;        /* byte offset of the tile's bytes in d_packed                                  */
-    uint32_t size;         /* = encode_tile's return value                                                 */
+    uint32_t size;         /* bytes of the tile as emitted here; = encode_tile's return value when flags == 0
+                            * (a tile with HOH_TILE_GREY / HOH_TILE_PALETTE is emitted in subtract-green mode, where
+                            * the reference would have taken its greyscale / indexed branch: the bytes are a valid
+                            * tile but NOT what choh writes — the host must notice the flag)                    */
     int32_t status;        /* HOH_S_* of the first failing stage                                           */
     uint32_t colour_mode;  /* 128 subtract-green, 2 plain RGB (choh.cpp:295-327)                           */
     uint32_t lz_size;      /* bytes of the LZ record inside the tile                                       */
@@ -327,6 +341,19 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
  * checksum, so that is a 2^-32-ish guarantee per stream, not a proof. */
 int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes, const uint64_t* d_tile_off,
                       size_t n_images, uint32_t width, uint32_t height, uint8_t* d_rgb, int32_t* d_status);
+
+/* Host-buffer forms of the two calls above — what a batched container writer / reader calls (tools/choh_batch.cpp,
+ * tools/dhoh_batch.cpp): the batch is cut into chunks of whole images, chunk c+1 is copied in while chunk c is coded
+ * and chunk c-1 is copied out (own copy streams; pass pinned buffers from hoh_host_alloc for full PCIe bandwidth).
+ * encode: packed_host[0, tile_off_host[n_tiles]) receives the tiles back to back, tile_off_host has n_tiles+1
+ * entries, tiles_host n_tiles records (start rebased to packed_host).  decode: exact sizes, no padding needed;
+ * status_host has n_tiles entries; pixels of tiles that fail to decode are zero.  On any failure every copy has
+ * been drained before the call returns. */
+int hoh_encode_images_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_images, uint32_t width, uint32_t height,
+                           int mode, unsigned flags, uint8_t* packed_host, size_t packed_cap, uint64_t* tile_off_host,
+                           hoh_tile_result* tiles_host);
+int hoh_decode_images_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t packed_bytes, const uint64_t* tile_off_host,
+                           size_t n_images, uint32_t width, uint32_t height, uint8_t* rgb_host, int32_t* status_host);
 
 /* ------------------------------------------------------------------------------------------ */
 /* (v) LZ match finder — find_lz_rgb lz.hpp:6-145 over N tiles                 */

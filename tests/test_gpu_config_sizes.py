@@ -1,8 +1,10 @@
-"""BASELINE.json's configurations at (or near) their stated sizes, through properties that do not need the CPU
-oracle to process the whole batch: exact encode -> decode round trips, sums of sizes, and byte parity against the
-oracle on a SAMPLE of tiles.  Config 2 is run at full size; configs 3 and 5 on slices whose tiles have exactly
-the configurations' shapes (256x270 tiles of 4K frames at -s2; untiled 256x256 thumbnails at -s4); config 4 at
-2^26 symbols is in test_gpu_parity.py (test_rans_static_sweep_64mb_round_trip)."""
+"""BASELINE.json's configurations at (or near) their stated sizes: exact encode -> decode round trips, sums of
+sizes, and byte parity against the oracle.  Config 2 is run at full size and EVERY one of its 49 152 channel payloads
+is compared with the oracle's layer_encode bytes (the oracle runs on all host cores: ctypes releases the GIL);
+configs 3 and 5 run on slices whose tiles have exactly the configurations' shapes (256x270 tiles of 4K frames at
+-s2; untiled 256x256 thumbnails at -s4) with 64+ tiles each compared with the oracle's encode_tile bytes; config 4
+at 2^26 symbols is in test_gpu_parity.py (test_rans_static_sweep_64mb_round_trip)."""
+from concurrent.futures import ThreadPoolExecutor
 import ctypes as C
 import importlib.util
 import os
@@ -59,15 +61,25 @@ def test_config2_full_size_roundtrip_and_sampled_parity():
         assert int(off[-1]) == int(res["size"].astype(np.uint64).sum())           # a checksum of the size table
         assert 0.50 < int(off[-1]) / rgb.nbytes < 0.54                           # section 8(d): about 0.52 at -s0
         assert np.array_equal(d_back.download(np.uint8, rgb.nbytes), rgb)
-        for image in (0, 1777, n - 1):
+        packed = d_packed.download(np.uint8, int(off[-1]))
+        ol.oracle()                                                             # built / loaded before the threads start
+
+        def check_image(image):                                                 # all 12 channel payloads of one image
             img = rgb[image * w * h * 3:(image + 1) * w * h * 3].reshape(h, w, 3)
-            tile = np.ascontiguousarray(img[geo.tile_h:, geo.tile_w:])          # the last of the four tiles
-            planes = ol.orc_subtract_green(tile)
-            s = (image * geo.tiles_per_image + 3) * 3
-            for c, (p, d) in enumerate(zip(planes, (8, 9, 9))):
-                want, _ = ol.orc_layer_encode(p, geo.tile_w, geo.tile_h, d, 0)
-                lo, hi = int(off[s + c]), int(off[s + c + 1])
-                assert d_packed.download(np.uint8, hi)[lo:].tobytes() == want.tobytes(), (image, c)
+            bad = []
+            for t in range(geo.tiles_per_image):
+                x0, y0 = (t % geo.x_tiles) * geo.tile_w, (t // geo.x_tiles) * geo.tile_h
+                planes = ol.orc_subtract_green(np.ascontiguousarray(img[y0:y0 + geo.tile_h, x0:x0 + geo.tile_w]))
+                s = (image * geo.tiles_per_image + t) * 3
+                for c, (p, d) in enumerate(zip(planes, (8, 9, 9))):
+                    want, _ = ol.orc_layer_encode(p, geo.tile_w, geo.tile_h, d, 0)
+                    if packed[int(off[s + c]):int(off[s + c + 1])].tobytes() != want.tobytes():
+                        bad.append(s + c)
+            return bad
+
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+            mismatches = [s for bad in pool.map(check_image, range(n)) for s in bad]
+        assert mismatches == [], mismatches[:10]                                # 49 152 of 49 152 streams byte-exact
     finally:
         for b in bufs:
             b.free()
@@ -83,12 +95,19 @@ def test_config3_slice_4k_frames_mode2():
     assert (rec["status"] == 0).all() and len(tiles) == 960
     back, st = g.decode_images(tiles, n, w, h)
     assert (st == 0).all() and np.array_equal(back, rgb)
-    ref_tiles, rec0 = g.encode_images(rgb[: w * h * 3], 1, w, h, 2, 0)
+    ref_tiles, rec0 = g.encode_images(rgb[: w * h * 3], 1, w, h, 2, 0)        # stock bytes of frame 0: 120 tiles
     img = rgb[: w * h * 3].reshape(h, w, 3)
-    for t in (0, 119):
+    ol.oracle()
+
+    def check_tile(t):
         x0, y0 = (t % 15) * 256, (t // 15) * 270
         want, _ = ol.orc_encode_tile_subgreen(np.ascontiguousarray(img[y0:y0 + 270, x0:x0 + 256]), 2)
-        assert ref_tiles[t] == want, t
+        return ref_tiles[t] == want
+
+    picked = list(range(0, 120, 2)) + [111, 113, 115, 117, 119]                # 65 tiles incl. both edges of the grid
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+        ok = list(pool.map(check_tile, picked))
+    assert all(ok), [t for t, v in zip(picked, ok) if not v]
 
 
 def test_config5_slice_thumbnails_mode4():
@@ -101,7 +120,15 @@ def test_config5_slice_thumbnails_mode4():
     assert (rec["status"] == 0).all()
     back, st = g.decode_images(tiles, n, w, h)
     assert (st == 0).all() and np.array_equal(back, rgb)
-    k = 1234
-    ref_tile, _ = g.encode_images(rgb[k * w * h * 3:(k + 1) * w * h * 3], 1, w, h, 4, 0)
-    want, _ = ol.orc_encode_tile_subgreen(rgb[k * w * h * 3:(k + 1) * w * h * 3].reshape(h, w, 3), 4)
-    assert ref_tile[0] == want
+    picked = list(range(3, n, 32))                                             # 64 thumbnails, stock bytes (flags = 0)
+    sub = np.concatenate([rgb[k * w * h * 3:(k + 1) * w * h * 3] for k in picked])
+    ref_tiles, _ = g.encode_images(sub, len(picked), w, h, 4, 0)
+    ol.oracle()
+
+    def check_thumb(i):
+        want, _ = ol.orc_encode_tile_subgreen(sub[i * w * h * 3:(i + 1) * w * h * 3].reshape(h, w, 3), 4)
+        return ref_tiles[i] == want
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+        ok = list(pool.map(check_thumb, range(len(picked))))
+    assert all(ok), [picked[i] for i, v in enumerate(ok) if not v]

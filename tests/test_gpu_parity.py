@@ -1,6 +1,7 @@
 """GPU parity: every stage of the CUDA path, called through the C-ABI, against the CPU oracle
 (oracle/hoh_oracle.c, pinned to the real reference) and the committed golden vectors.
 Bit-exact everywhere: this is integer / byte work."""
+import ctypes as C
 import hashlib
 import os
 
@@ -585,3 +586,82 @@ def test_rans_static_sweep_64mb_round_trip():
     assert abs(lens.sum() * 8.0 / ideal_bits - 1.0) < 0.01
     for b in (d_sym, d_cum, d_out, d_len, d_dec):
         b.free()
+
+
+@pytest.mark.parametrize("total,target,n_px", [(3, 0, 1000), (3, 1, 65536), (3, 2, 70001), (4, 3, 513), (1, 0, 77), (2, 1, 4096)])
+def test_channel_picker_direct(total, target, n_px):
+    """channel.hpp:63-71 on the device, compared with the oracle and with plain slicing."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(100 * total + target)
+    src = rng.integers(0, 256, n_px * total, dtype=np.uint8)
+    got = g.channel_picker(src, total, target)
+    assert got.dtype == np.uint16 and np.array_equal(got, src[target::total].astype(np.uint16))
+    assert np.array_equal(got, ol.orc_channel_picker(src, total, target))
+
+
+def _backref_maps(rgb, n_images, w, h, geo, nukes):
+    """LEMPEL_BACKREF maps for decode: a covered pixel copies the nearest earlier pixel of its tile with the same
+    colour (any in-tile distance that reproduces the pixel is a valid back-reference for the decoder)."""
+    stride = (geo.tile_w * geo.tile_h + 7) & ~7
+    maps = np.zeros(n_images * geo.tiles_per_image * stride, np.uint16)
+    for i in range(n_images):
+        img = rgb[i * w * h * 3:(i + 1) * w * h * 3].reshape(h, w, 3)
+        for t in range(geo.tiles_per_image):
+            x0, y0 = (t % geo.x_tiles) * geo.tile_w, (t // geo.x_tiles) * geo.tile_h
+            tile = img[y0:y0 + geo.tile_h, x0:x0 + geo.tile_w].reshape(-1, 3).astype(np.uint32)
+            key = (tile[:, 0] << 16) | (tile[:, 1] << 8) | tile[:, 2]
+            k = i * geo.tiles_per_image + t
+            nuke = nukes[k * stride:k * stride + key.size]
+            last = {}
+            for p in range(key.size):
+                if nuke[p]:
+                    assert int(key[p]) in last, "a covered pixel must have an earlier equal pixel"
+                    maps[k * stride + p] = p - last[int(key[p])]
+                last[int(key[p])] = p
+    return maps
+
+
+@pytest.mark.parametrize("w,h,n", [(96, 80, 3), (512, 256, 2), (601, 523, 1)])
+def test_decode_images_s0_with_backrefs(w, h, n):
+    """hoh_decode_images_s0 with LEMPEL_BACKREF maps (unprediction.hpp:63-65): streams coded with the NUKE maps of
+    the LZ finder hold residuals only for uncovered pixels; the decoder copies the covered ones."""
+    g = gpu_lib.gpu()
+    mod = gpu_lib.hohgpu()
+    rng = np.random.default_rng(w + h)
+    rgb = np.concatenate([ol.photo_with_repeats(rng, w, h, 40 + i).ravel() for i in range(n)])
+    geo = g.tile_geometry(w, h)
+    n_tiles = n * geo.tiles_per_image
+    n_streams = n_tiles * 3
+    stride = (geo.tile_w * geo.tile_h + 7) & ~7
+    lz_stride = int(g.lib.hoh_find_lz_stride(geo.tile_w, geo.tile_h))
+    out_bytes = int(g.lib.hoh_encode_images_out_bytes(C.byref(geo), n))
+    cap = rgb.nbytes * 2 + 4096 * n_streams
+    bufs = [g.alloc(rgb.nbytes).upload(rgb), g.alloc(n_tiles * stride), g.alloc(n_tiles * lz_stride), g.alloc(n_tiles * 4),
+            g.alloc(n_tiles * 4), g.alloc(out_bytes), g.alloc(n_streams * mod.RESULT_DT.itemsize), g.alloc(cap),
+            g.alloc((n_streams + 1) * 8)]
+    d_rgb, d_nuke, d_lz, d_size, d_st, d_out, d_res, d_packed, d_off = bufs
+    try:
+        d_nuke.zero()
+        g._ck(g.lib.hoh_find_lz_images(g.ctx, d_rgb.ptr, n, w, h, 6, 0, None, d_nuke.ptr, d_lz.ptr, lz_stride, d_size.ptr,
+                                       d_st.ptr), "lz")
+        g._ck(g.lib.hoh_encode_images_s0(g.ctx, d_rgb.ptr, n, w, h, d_nuke.ptr, d_out.ptr, out_bytes, d_res.ptr,
+                                         d_packed.ptr, cap, d_off.ptr), "encode")
+        nukes = d_nuke.download(np.uint8, n_tiles * stride)
+        off = d_off.download(np.uint64, n_streams + 1)
+        packed = d_packed.download(np.uint8, int(off[-1]))
+    finally:
+        for b in bufs:
+            b.free()
+    assert nukes.sum() > 50
+    maps = _backref_maps(rgb, n, w, h, geo, nukes)
+    back, st = g.decode_images_s0(packed, off, n, w, h, backref=maps)
+    assert (st == 0).all() and np.array_equal(back, rgb)
+    # without the maps the dense streams cannot fill the tiles: every tile with a match is reported, not mis-decoded
+    back2, st2 = g.decode_images_s0(packed, off, n, w, h)
+    assert (st2 != 0).any()
+    # a map that disagrees with the stream (one more covered pixel) is caught as well
+    wrong = maps.copy()
+    first_free = int(np.flatnonzero(wrong[:geo.tile_w * geo.tile_h] == 0)[5])
+    wrong[first_free] = 1
+    back3, st3 = g.decode_images_s0(packed, off, n, w, h, backref=wrong)
+    assert st3[0] == 5 and st3[1] == 5 and st3[2] == 5
