@@ -183,6 +183,122 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own hot path (oracle/_ref, else the oracle port) on host cores
 # ------------------------------------------------------------------------------------------------
+class TileGrid:
+    """choh.cpp:454-460: the 256-pixel tiling rule (host arithmetic for the CPU arm)."""
+
+    def __init__(self, w, h):
+        if (w >= 512 or h >= 512) and w >= 256 and h >= 256:
+            self.x_tiles, self.y_tiles = w // 256, h // 256
+        else:
+            self.x_tiles = self.y_tiles = 1
+        self.tile_w = (w + self.x_tiles - 1) // self.x_tiles
+        self.tile_h = (h + self.y_tiles - 1) // self.y_tiles
+        self.tiles_per_image = self.x_tiles * self.y_tiles
+
+
+def tile_grid(w, h):
+    return TileGrid(w, h)
+
+
+def load_reference_in_parent():
+    """dlopen oracle/_ref/libhohref.so (or the oracle port) in THIS process before the workers are forked, so that
+    a driver looking at the process's mapped libraries sees what the CPU arm really runs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    ol.oracle()
+    if ol.have_ref():
+        ol.ref()
+        return "reference"
+    return "port"
+
+
+def _whole_tool_worker(args):
+    """Stock `choh` (choh.cpp:394 main, through oracle/_ref's ref_choh_main): file in, file out, LZ included."""
+    first_seed, count, w, h, mode, tmpdir = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    if not ol.have_ref():
+        return None
+    R = ol.ref()
+    rgb = np.zeros(w * h * 3, np.uint8)
+    busy = 0.0
+    out_bytes = 0
+    for i in range(count):
+        synth_lib().synth_rgb_batch(rgb.ctypes.data, w, h, first_seed + i, 1)
+        src = os.path.join(tmpdir, f"in_{os.getpid()}_{i}.rgb")
+        dst = os.path.join(tmpdir, f"out_{os.getpid()}_{i}.hoh")
+        rgb.tofile(src)
+        t0 = time.perf_counter()
+        devnull = os.open(os.devnull, os.O_WRONLY)  # choh prints the size
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            rc = R.ref_choh_main(src.encode(), dst.encode(), w, h, mode)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+        busy += time.perf_counter() - t0
+        assert rc == 0
+        out_bytes += os.path.getsize(dst)
+        os.remove(src)
+        os.remove(dst)
+    return busy, count * w * h * 3, out_bytes
+
+
+def cpu_whole_tool(images, w, h, mode, cores, seed0=1):
+    """stock choh, one process per core, over `images` images.  MB/s of raw RGB over the
+    busy time of the slowest worker.  Encode only: the reference's dhoh cannot decode choh's output."""
+    import multiprocessing as mp
+    import tempfile
+    per = [images // cores + (1 if i < images % cores else 0) for i in range(cores)]
+    with tempfile.TemporaryDirectory() as tmp:
+        jobs, seed = [], seed0
+        for n in per:
+            if n:
+                jobs.append((seed, n, w, h, mode, tmp))
+                seed += n
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            res = pool.map(_whole_tool_worker, jobs)
+    if any(r is None for r in res):
+        return None
+    raw = sum(r[1] for r in res)
+    slowest = max(r[0] for r in res)
+    return {"encode_mbs": raw / slowest / 1e6, "cores": len(jobs), "images": images, "mode": mode,
+            "compressed_ratio": sum(r[2] for r in res) / raw,
+            "what": "stock choh main() file to file (host LZ, colour-mode competition, container), one process per "
+                    "core; decode has no whole-tool figure because dhoh cannot read choh's files"}
+
+
+def _tile_worker(args):
+    """reference encode_tile (choh.cpp:104) on whole tiles of a given shape and mode: the CPU figure beside the
+    mode >= 1 configurations."""
+    first_seed, count, w, h, mode = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    busy = 0.0
+    for i in range(count):
+        rgb = ol.synth_rgb(w, h, first_seed + i)
+        t0 = time.perf_counter()
+        if ol.have_ref():
+            buf = np.zeros(rgb.size * 3 + 4096, np.uint8)
+            ol.ref().ref_encode_tile(rgb, rgb.size, buf, w, h, mode)
+        else:
+            ol.orc_encode_tile_subgreen(rgb.reshape(h, w, 3), mode)
+        busy += time.perf_counter() - t0
+    return busy
+
+
+def cpu_encode_tiles(tiles, w, h, mode, cores):
+    import multiprocessing as mp
+    per = [tiles // cores + (1 if i < tiles % cores else 0) for i in range(cores)]
+    jobs = [(1000 + 97 * i, n, w, h, mode) for i, n in enumerate(per) if n]
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        res = pool.map(_tile_worker, jobs)
+    return {"encode_mbs": tiles * w * h * 3 / max(res) / 1e6, "cores": len(jobs), "tiles": tiles,
+            "ms_per_tile_one_core": 1e3 * sum(res) / tiles}
+
+
 def _cpu_worker(args):
     first_seed, count, w, h = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -192,10 +308,7 @@ def _cpu_worker(args):
     O = ol.oracle()
     rgb = np.zeros(count * w * h * 3, np.uint8)
     synth_lib().synth_rgb_batch(rgb.ctypes.data, w, h, first_seed, count)
-    gpu_mod = _load("hohgpu", os.path.join(ROOT, "hoh-ans_b200", "host", "hohgpu.py"))
-    lib = gpu_mod.load_library()  # hoh_tile_geometry_for is pure host arithmetic (choh.cpp:454-460)
-    g = gpu_mod.TileGeometry()
-    lib.hoh_tile_geometry_for(w, h, C.byref(g))
+    g = tile_grid(w, h)  # choh.cpp:454-460 in Python: the reference arm loads nothing of this repo's product
     t_enc = t_dec = t_lz = 0.0
     nuke = np.zeros(g.tile_w * g.tile_h, np.uint8)
     lz_out = np.zeros(g.tile_w * g.tile_h * 2 + 8192, np.uint8)
