@@ -444,6 +444,235 @@ def host_memory_allows(need_bytes, reserve=8 << 30):
     return avail is None or need_bytes + reserve <= avail
 
 
+def kernel_source_sha1():
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("hoh_kernels.cuh", "hoh_api.cu", "hoh_format.cuh"):
+        h.update(open(os.path.join(ROOT, "hoh-ans_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
+def pcie_probe(g, lib, ctx, h_src, h_dst, d_a, d_b, nbytes, reps=3):
+    """H2D alone, D2H alone, both at once (pinned host memory; the context's stream and a second context's)."""
+    other = type(g)(g.device)
+
+    def run(h2d, d2h):
+        g.sync()
+        other.sync()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                g._ck(lib.hoh_h2d(ctx, d_a.ptr, h_src.ctypes.data, nbytes), "h2d")
+            if d2h:
+                g._ck(lib.hoh_d2h(other.ctx, h_dst.ctypes.data, d_b.ptr, nbytes), "d2h")
+        g.sync()
+        other.sync()
+        return reps * nbytes / (time.perf_counter() - t0) / 1e9
+
+    run(True, True)
+    out = {"h2d_alone_gbs": run(True, False), "d2h_alone_gbs": run(False, True)}
+    both = run(True, True)
+    out["h2d_both_gbs"] = both
+    out["d2h_both_gbs"] = both
+    other.close()
+    return out
+
+
+def run_config_tiles(g, mod, shard, rank, world, host_threads, hbm_peak, barrier, name, w, h, mode, total_images, strong,
+                     parity_tiles, steps, e2e_leg=True):
+    """Whole tiles at cruncher mode >= 1 (hoh_encode_images / hoh_decode_images, device resident): BASELINE configs 3
+    and 5.  strong: total_images is the whole job, split by image index; else total_images per rank."""
+    lib, ctx = g.lib, g.ctx
+    if strong:
+        lo, hi = shard.shard_range(total_images, rank, world)
+    else:
+        lo, hi = rank * total_images, (rank + 1) * total_images
+    n = hi - lo
+    geo = g.tile_geometry(w, h)
+    n_tiles = n * geo.tiles_per_image
+    raw = n * w * h * 3
+    rgb = np.zeros(max(raw, 1), np.uint8)
+    if n:
+        fill_images(rgb, 1 + lo, n, w, h, host_threads)
+    cap = raw + raw // 2 + 8192 * n_tiles + 64
+    bufs = [g.alloc(max(raw, 16)), g.alloc(cap), g.alloc((n_tiles + 1) * 8), g.alloc(max(n_tiles, 1) * mod.TILE_DT.itemsize),
+            g.alloc(max(raw, 16)), g.alloc(max(n_tiles, 1) * 4)]
+    d_rgb, d_packed, d_off, d_tiles, d_back, d_st = bufs
+    if n:
+        d_rgb.upload(rgb[:raw])
+    FIX_ENCODER = 24
+
+    def enc(flags=FIX_ENCODER):
+        if n:
+            g._ck(lib.hoh_encode_images(ctx, d_rgb.ptr, n, w, h, mode, flags, d_packed.ptr, cap, d_off.ptr, d_tiles.ptr), "hoh_encode_images")
+
+    def dec():
+        if n:
+            g._ck(lib.hoh_decode_images(ctx, d_packed.ptr, cap, d_off.ptr, n, w, h, d_back.ptr, d_st.ptr), "hoh_decode_images")
+
+    enc()
+    dec()
+    g.sync()
+    l0 = g.launch_count()
+    barrier()
+    g.timer_start(4)
+    for _ in range(steps):
+        enc()
+    g.timer_stop(4)
+    g.timer_start(5)
+    for _ in range(steps):
+        dec()
+    g.timer_stop(5)
+    enc_ms, dec_ms = g.timer_ms(4) / steps, g.timer_ms(5) / steps
+    barrier()
+    launches = g.launch_count() - l0
+    comp = int(d_off.download(np.uint64, n_tiles + 1)[-1]) if n else 0
+    ok = True
+    if n:
+        rec = d_tiles.download(mod.TILE_DT, n_tiles)
+        ok = bool((rec["status"] == 0).all() and (d_st.download(np.int32, n_tiles) == 0).all()
+                  and np.array_equal(d_back.download(np.uint8, raw), rgb[:raw]))
+    # sampled byte parity with the oracle at flags = 0 (stock choh bytes), rank 0 only: the oracle needs 0.6 s
+    # (mode 2) to 3 s (mode 4) per tile, so the sample is small here; tests/test_gpu_config_sizes.py compares 64+
+    parity = None
+    if rank == 0 and n and parity_tiles:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        from concurrent.futures import ThreadPoolExecutor
+        first = rgb[: w * h * 3]
+        tiles, _ = g.encode_images(first, 1, w, h, mode, 0)
+        img = first.reshape(h, w, 3)
+        picks = sorted({(k * (geo.tiles_per_image - 1)) // max(parity_tiles - 1, 1) for k in range(parity_tiles)})
+
+        def check(t):
+            x0, y0 = (t % geo.x_tiles) * geo.tile_w, (t // geo.x_tiles) * geo.tile_h
+            want, _ = ol.orc_encode_tile_subgreen(np.ascontiguousarray(img[y0:y0 + geo.tile_h, x0:x0 + geo.tile_w]), mode)
+            return tiles[t] == want
+        ol.oracle()
+        with ThreadPoolExecutor(len(picks)) as pool:
+            parity = {"tiles_compared": len(picks), "byte_exact": bool(all(pool.map(check, picks)))}
+    for b in bufs:
+        b.free()
+    # end to end through the host-buffer C-ABI calls the C++ tools use (hoh_encode_images_host / hoh_decode_images_host):
+    # pinned buffers, chunked H2D / kernels / D2H inside the library, copies inside the timed region
+    e2e = None
+    if n and e2e_leg:
+        src = g.host_alloc(raw)
+        src[:] = rgb[:raw]
+        packed = g.host_alloc(cap)
+        back = g.host_alloc(raw)
+        off = np.zeros(n_tiles + 1, np.uint64)
+        rec = np.zeros(n_tiles, mod.TILE_DT)
+        st = np.zeros(n_tiles, np.int32)
+
+        def e2e_once():
+            ta = time.perf_counter()
+            g._ck(lib.hoh_encode_images_host(ctx, src.ctypes.data, n, w, h, mode, FIX_ENCODER, packed.ctypes.data, cap,
+                                             off.ctypes.data, rec.ctypes.data), "hoh_encode_images_host")
+            tb = time.perf_counter()
+            g._ck(lib.hoh_decode_images_host(ctx, packed.ctypes.data, int(off[-1]), off.ctypes.data, n, w, h,
+                                             back.ctypes.data, st.ctypes.data), "hoh_decode_images_host")
+            return tb - ta, time.perf_counter() - tb
+        e2e_once()
+        barrier()
+        te, td = e2e_once()
+        e2e = {"encode_ms": 1e3 * te, "decode_ms": 1e3 * td,
+               "ok": bool((rec["status"] == 0).all() and (st == 0).all() and np.array_equal(back, src)),
+               "h2d": raw + int(off[-1]), "d2h": raw + int(off[-1])}
+        for a in (src, packed, back):
+            g.host_free(a)
+        del src, packed, back
+    elif e2e_leg:
+        barrier()
+    e2e_out = None
+    if e2e_leg:
+        e_ms = shard.reduce_max(e2e["encode_ms"] + e2e["decode_ms"] if e2e else 0.0, world, device="cuda")
+        e_ok = shard.reduce_sum(1.0 if (e2e is None or e2e["ok"]) else 0.0, world, device="cuda") == world
+        e2e_out = {"value_mbs": 2 * shard.reduce_sum(float(raw), world, device="cuda") / e_ms / 1e3, "ms_per_step": e_ms,
+                   "encode_ms_this_rank": e2e["encode_ms"] if e2e else None, "decode_ms_this_rank": e2e["decode_ms"] if e2e else None,
+                   "h2d_bytes_per_step": e2e["h2d"] if e2e else 0, "d2h_bytes_per_step": e2e["d2h"] if e2e else 0, "verified": e_ok}
+    enc_ms, dec_ms = shard.reduce_max(enc_ms, world, device="cuda"), shard.reduce_max(dec_ms, world, device="cuda")
+    job_raw = shard.reduce_sum(float(raw), world, device="cuda")
+    job_comp = shard.reduce_sum(float(comp), world, device="cuda")
+    all_ok = shard.reduce_sum(1.0 if ok else 0.0, world, device="cuda") == world
+    alg = job_raw + job_comp
+    return {"workload": name, "scaling": "strong" if strong else "weak", "images_in_job": int(job_raw // (w * h * 3)),
+            "images_this_rank": n, "mode": mode, "encode_ms": enc_ms, "decode_ms": dec_ms,
+            "encode_mbs": job_raw / enc_ms / 1e3, "decode_mbs": job_raw / dec_ms / 1e3,
+            "value_mbs": 2 * job_raw / (enc_ms + dec_ms) / 1e3, "compressed_ratio": job_comp / max(job_raw, 1),
+            "hbm_frac_encode": alg / world / enc_ms / 1e6 / hbm_peak, "hbm_frac_decode": alg / world / dec_ms / 1e6 / hbm_peak,
+            "roundtrip_exact": all_ok, "oracle_parity_sample": parity, "gpu_launches": int(launches), "e2e": e2e_out,
+            "limit": "a launch of the entropy / un-prediction kernels lasts as long as ONE stream's serial chain however few "
+                     "streams a rank holds, so strong scaling flattens once the per-rank batch no longer fills the SMs"
+                     if strong else "throughput-bound: six to nine rANS candidates per plane plus the predictor search"}
+
+
+def run_config_static(g, mod, shard, rank, world, hbm_peak, barrier, log2n, steps):
+    """BASELINE config 4: rans64 sweep point — 2^log2n symbols per GPU over an 8-bit alphabet, one static 12-bit
+    table, 65 536-symbol streams (tools/bench_static.py walks the whole 1 MB .. 4 GB range)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    lib, ctx = g.lib, g.ctx
+    STREAM, PB = 65536, 12
+    n = 1 << log2n
+    n_streams = n // STREAM
+    base = ol.synth_symbols(1 << 24, 7 + rank)
+    f = np.bincount(base, minlength=256).astype(np.uint32)
+    cum = np.zeros(257, np.uint32)
+    assert ol.oracle().orc_normalize_freqs(f, cum, 256, 1 << PB) == 0
+    d_cum = g.alloc(cum.nbytes).upload(cum)
+    slab = (STREAM * PB // 8 + 64 + 15) & ~15
+    sym = base.astype(np.uint16)
+    d_sym, d_out, d_len, d_dec = g.alloc(n * 2 + 64), g.alloc(n_streams * slab), g.alloc(n_streams * 4), g.alloc(n * 2 + 64)
+    piece = sym[:min(n, sym.size)]
+    for r in range(max(1, n // sym.size)):
+        g._ck(lib.hoh_h2d(ctx, d_sym.ptr + r * piece.nbytes, piece.ctypes.data, piece.nbytes), "h2d")
+
+    def enc():
+        g._ck(lib.hoh_rans_encode_static(ctx, d_sym.ptr, n, STREAM, d_cum.ptr, 256, PB, d_out.ptr, slab, d_len.ptr), "enc")
+
+    def dec():
+        g._ck(lib.hoh_rans_decode_static(ctx, d_out.ptr, slab, d_len.ptr, n, STREAM, d_cum.ptr, 256, PB, d_dec.ptr), "dec")
+    enc()
+    dec()
+    g.sync()
+    barrier()
+    g.timer_start(4)
+    for _ in range(steps):
+        enc()
+    g.timer_stop(4)
+    g.timer_start(5)
+    for _ in range(steps):
+        dec()
+    g.timer_stop(5)
+    e_ms, d_ms = g.timer_ms(4) / steps, g.timer_ms(5) / steps
+    barrier()
+    lens = d_len.download(np.uint32, n_streams)
+    back = d_dec.download(np.uint16, min(n, 1 << 24))
+    ok = bool(np.array_equal(back, sym[:back.size]))
+    # oracle parity on a sample of streams: payload bytes of the reference's Rans64 loop with the same table
+    buf = np.zeros(STREAM * 2 + 64, np.uint8)
+    exact = True
+    for k in (0, n_streams // 2, n_streams - 1):
+        part = np.ascontiguousarray(sym[(k * STREAM) % sym.size:(k * STREAM) % sym.size + STREAM])
+        nb = ol.oracle().orc_rans_encode_static(part, STREAM, f, cum, 256, PB, buf)
+        got = d_out.download(np.uint8, (k + 1) * slab)[k * slab:]
+        exact = exact and int(lens[k]) == nb and got[slab - nb:].tobytes() == buf[:nb].tobytes()
+    comp = int(lens.astype(np.uint64).sum())
+    for b in (d_sym, d_out, d_len, d_dec, d_cum):
+        b.free()
+    e_ms, d_ms = shard.reduce_max(e_ms, world, device="cuda"), shard.reduce_max(d_ms, world, device="cuda")
+    job_n = shard.reduce_sum(float(n), world, device="cuda")
+    job_comp = shard.reduce_sum(float(comp), world, device="cuda")
+    all_ok = shard.reduce_sum(1.0 if (ok and exact) else 0.0, world, device="cuda") == world
+    alg = job_n + job_comp  # SURVEY 8(d): 1 B per symbol + H/8 B
+    return {"workload": f"rans64 static-table stream sweep point: 2^{log2n} symbols per GPU, 8-bit alphabet, one 12-bit table, "
+                        f"65 536-symbol streams", "scaling": "weak", "symbols_in_job": int(job_n), "encode_ms": e_ms, "decode_ms": d_ms,
+            "encode_msym_s": job_n / e_ms / 1e3, "decode_msym_s": job_n / d_ms / 1e3, "bits_per_symbol": job_comp * 8 / job_n,
+            "hbm_frac_encode": alg / world / e_ms / 1e6 / hbm_peak, "hbm_frac_decode": alg / world / d_ms / 1e6 / hbm_peak,
+            "roundtrip_exact_and_oracle_parity": all_ok}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -455,7 +684,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = 4 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--configs", default="3,4,5", help="BASELINE.json configs reported beside the config-2 headline "
+                    "(comma list of 3, 4, 5; empty = headline only)")
+    ap.add_argument("--frames", type=int, default=256, help="config 3: 3840x2160 frames in the whole job (strong scaling)")
+    ap.add_argument("--thumbs", type=int, default=8192, help="config 5: 256x256 thumbnails per GPU")
+    ap.add_argument("--static-log2", type=int, default=30, help="config 4: log2 of the symbols per GPU")
     args = ap.parse_args()
+    extra = [int(x) for x in args.configs.split(",") if x.strip()]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -473,6 +708,7 @@ def main():
             return 0
         cores = os.cpu_count() or 1
         sample = args.cpu_sample or max(cores * 2, 16)
+        load_reference_in_parent()
         vals = []
         for it in range(warmup + steps):
             r = cpu_hot_path(sample, W, H, cores, seed0=1)
@@ -658,6 +894,50 @@ def main():
     def rsum(x):
         return shard.reduce_sum(x, world, device="cuda")
 
+    def rmin(x):
+        return -shard.reduce_max(-x, world, device="cuda")
+
+    # what the PCIe links of THIS box give when every rank copies at once (both directions together): the ceiling
+    # of the e2e leg, measured in the same run so that a low e2e number can be told apart from a slow box
+    pcie = None
+    if not args.no_e2e:
+        probe_bytes = min(raw, 1 << 30)
+        barrier()
+        pcie = pcie_probe(g, lib, ctx, rgb_host, back_host, d_rgb, d_back, probe_bytes)
+        barrier()
+        pcie = {k: rmin(v) for k, v in pcie.items()}
+        g.host_free(packed_host)
+        g.host_free(off_host)
+        g.host_free(back_host)
+        del packed_host, off_host, back_host
+    for b in (d_rgb, d_back, d_out, d_packed, d_res, d_off, d_st):
+        b.free()
+    g.host_free(rgb_host)
+    del rgb_host
+
+    configs_out = {}
+    hbm_peak_all = 6650.0
+    try:
+        hbm_peak_all = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:
+        pass
+    for c in extra:
+        barrier()
+        g.release_scratch()
+        if c == 3:
+            configs_out["config3"] = run_config_tiles(g, mod, shard, rank, world, host_threads, hbm_peak_all, barrier,
+                                                      name="256 x 3840x2160 -s2, frames sharded across the GPUs (strong scaling)",
+                                                      w=3840, h=2160, mode=2, total_images=args.frames, strong=True,
+                                                      parity_tiles=4, steps=2, e2e_leg=not args.no_e2e)
+        elif c == 5:
+            configs_out["config5"] = run_config_tiles(g, mod, shard, rank, world, host_threads, hbm_peak_all, barrier,
+                                                      name=f"slice of the 1M 256x256 thumbnails at -s4: {args.thumbs} per GPU "
+                                                           f"(weak scaling; the full 10^6 / 8 GPUs = {125000 // args.thumbs + 1} such chunks per GPU)",
+                                                      w=256, h=256, mode=4, total_images=args.thumbs, strong=False,
+                                                      parity_tiles=2, steps=2, e2e_leg=not args.no_e2e)
+        elif c == 4:
+            configs_out["config4"] = run_config_static(g, mod, shard, rank, world, hbm_peak_all, barrier, args.static_log2, steps=3)
+
     total_ms = rmax(total_ms)
     t_enc, t_dec = rmax(t_enc), rmax(t_dec)
     job_raw = rsum(float(raw))
@@ -684,12 +964,18 @@ def main():
         # algorithmic bytes of one launch: encode-side kernels move 3*W*H in + C out
         # per image, decode-side kernels C in + 3*W*H out; a launch covers the rank's whole batch
         alg_bytes = raw + comp_bytes
-        traffic = None
+        # DRAM bytes per launch come from an `ncu --set full` capture (profiles/ncu_traffic.json); the file is stamped
+        # with the hash of the kernel source it was captured from and is only quoted while that source is unchanged
+        traffic, traffic_note = None, "no capture"
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             ent = tj.get(top_name.split("<")[0].split("[")[0])
             if ent and ent.get("images"):
-                traffic = ent["dram_bytes_per_launch"] * n_img / ent["images"]
+                if tj.get("_kernel_source_sha1") == kernel_source_sha1():
+                    traffic = ent["dram_bytes_per_launch"] * n_img / ent["images"]
+                    traffic_note = f"ncu --set full capture at kernel source {tj['_kernel_source_sha1'][:12]}"
+                else:
+                    traffic_note = "capture is older than the kernel source: not quoted"
         except Exception:
             pass
         achieved = alg_bytes / (per_launch_ms / 1e3) / 1e9
@@ -704,7 +990,7 @@ def main():
             "hbm_frac_whole_step": ((job_raw + job_comp) * 2 * steps / world / (total_ms / 1e3) / 1e9) / hbm_peak,
             "gpu_launches": launches, "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
                          "share_of_step": top_ms / step_ms_prof},
             "kernels_ms": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
@@ -719,9 +1005,28 @@ def main():
                            "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                            "ms_per_step": e2e["ms"], "encode_ms": e2e["enc_ms"], "decode_ms": e2e["dec_ms"],
                            "verified": e2e_all_ok, "numa_rank0": numa}
+        if e2e and pcie:
+            h2d_gbs, d2h_gbs = pcie["h2d_both_gbs"], pcie["d2h_both_gbs"]
+            # encode moves raw in / C out, decode C in / raw out, overlapped: the longer direction of each phase bounds it
+            bound_s = (raw / 1e9) / h2d_gbs + (raw / 1e9) / d2h_gbs
+            line["e2e"]["pcie_bound_gbs"] = {"h2d_alone": pcie["h2d_alone_gbs"], "d2h_alone": pcie["d2h_alone_gbs"],
+                                             "h2d_with_d2h": h2d_gbs, "d2h_with_h2d": d2h_gbs,
+                                             "what": f"per rank, min over the {world} ranks copying at the same time, pinned memory"}
+            line["e2e"]["pcie_bound_value"] = 2 * raw * world / bound_s / 1e6
+            line["e2e"]["frac_of_pcie_bound"] = line["e2e"]["value"] / line["e2e"]["pcie_bound_value"]
+        if configs_out:
+            line["configs"] = configs_out
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = args.cpu_sample or max(cores * 4, 32)
+            load_reference_in_parent()
+            whole = cpu_whole_tool(max(cores * 4, 32), W, H, MODE, cores)
+            if whole:
+                line["cpu_whole_tool"] = whole
+            if "config3" in configs_out:
+                configs_out["config3"]["cpu_reference"] = cpu_encode_tiles(cores, 256, 270, 2, cores)
+            if "config5" in configs_out:
+                configs_out["config5"]["cpu_reference"] = cpu_encode_tiles(cores, 256, 256, 4, cores)
             cb = cpu_hot_path(sample, W, H, cores, seed0=1)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "MB/s", "cores": cb["cores"], "kind": cb["kind"],
                                     "encode_mbs": cb["encode_mbs"], "decode_mbs": cb["decode_mbs"],

@@ -38,6 +38,7 @@ struct hoh_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
+    uint64_t enc_key = 0, dec_key = 0;  // image shape / mode the cached scratch of the chunked walks was sized for
     char err[512] = {0};
     Buf scratch[S_COUNT];
     cudaEvent_t ev[16][2] = {};
@@ -177,6 +178,8 @@ size_t scratch_budget(hoh_ctx* ctx) {
     if (budget < ((size_t)1 << 30)) budget = (size_t)1 << 30;
     return budget;
 }
+
+int new_shape(hoh_ctx* ctx, uint64_t key, bool decode);
 
 inline unsigned blocks_for(uint64_t items, unsigned per_block) { return (unsigned)((items + per_block - 1) / per_block); }
 inline unsigned grid_cap(uint64_t items, unsigned per_block, unsigned cap = 148u * 32u) {
@@ -413,6 +416,33 @@ int stage_out(hoh_ctx* ctx, T* host, const T* dev, size_t count) {
 }
 }  // namespace
 
+namespace {
+// The chunked walks size their scratch from what the device has free plus what the context already holds, which
+// is only true while the held buffers have the proportions the walk wants: when the image shape or mode changes
+// between calls, the cached scratch of the previous shape is released first.
+int new_shape(hoh_ctx* ctx, uint64_t key, bool decode) {
+    uint64_t& slot = decode ? ctx->dec_key : ctx->enc_key;
+    if (slot == key) return HOH_OK;
+    if (slot != 0) {
+        // this context's own codec scratch and the two children the encoder forks into; NOT children 2 and 3,
+        // which hold the staging buffers of a host-buffer call that may be the caller of this very function
+        CK(cudaStreamSynchronize(ctx->stream));
+        hoh_ctx* who[3] = {ctx, ctx->child[0], ctx->child[1]};
+        for (hoh_ctx* c : who) {
+            if (!c) continue;
+            CK(cudaStreamSynchronize(c->stream));
+            for (auto& b : c->scratch) {
+                if (b.p) CK(cudaFree(b.p));
+                b.p = nullptr;
+                b.cap = 0;
+            }
+        }
+    }
+    slot = key;
+    return HOH_OK;
+}
+}  // namespace
+
 // =================================================================================================
 // context
 // =================================================================================================
@@ -472,6 +502,20 @@ void hoh_ctx_destroy(hoh_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int hoh_release_scratch(hoh_ctx* ctx) {
+    DeviceGuard guard_(ctx);
+    if (!ctx) return HOH_E_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& b : ctx->scratch) {
+        if (b.p) CK(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    for (hoh_ctx* ch : ctx->child)
+        if (ch) TRY(hoh_release_scratch(ch));
+    return HOH_OK;
 }
 
 int hoh_sync(hoh_ctx* ctx) {
@@ -1563,6 +1607,7 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
                       4 * hoh_enc_slab_bytes(lz_side_stride(npx), 10) +
                       3 * (2 * npx * 2 + 8192) + 4096);
     }
+    TRY(new_shape(ctx, ((uint64_t)width << 40) ^ ((uint64_t)height << 16) ^ ((uint64_t)mode << 8) ^ 1u, false));
     const size_t budget = scratch_budget(ctx);
     size_t images_per_chunk = budget / per_image;
     if (images_per_chunk == 0) images_per_chunk = 1;
@@ -1664,6 +1709,7 @@ int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes
     const uint32_t max_side = lz_side_stride((size_t)hg.tile_w * hg.tile_h);
     const size_t per_tile = 4 * (size_t)max_side * 2 + 3 * (size_t)g.plane_stride * 2 * 2 + (size_t)g.plane_stride * 2 +
                             3 * (size_t)(kCumRow * 4 + kFreqRow * 4) + 3 * (size_t)hg.tile_w * 3 + 4096;
+    TRY(new_shape(ctx, ((uint64_t)width << 40) ^ ((uint64_t)height << 16) ^ 2u, true));
     const size_t budget = scratch_budget(ctx);
     size_t images_per_chunk = budget / (per_tile * g.tiles_per_image);
     if (images_per_chunk == 0) images_per_chunk = 1;

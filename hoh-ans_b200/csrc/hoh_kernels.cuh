@@ -1284,6 +1284,16 @@ __device__ __forceinline__ void rans_lookup_far(const Table& T, uint32_t key, ui
     }
 }
 
+template <typename Table>
+__device__ __noinline__ ulonglong2 rans_far_step(const Table T, uint32_t key, uint32_t p, uint32_t e, uint32_t hi,
+                                                 uint64_t top, uint32_t slot) {
+    rans_lookup_far(T, key, p, e, hi);
+    ulonglong2 r;
+    r.x = (uint64_t)((hi >> kSymBits) - (e >> kSymBits)) * top + (slot - (e >> kSymBits));
+    r.y = e;
+    return r;
+}
+
 // One decode step (rans64.hpp:118-142).  There is no "past the end of this stream" case: a lane whose
 // stream is shorter than its neighbours' keeps decoding (its table lookups and word reads stay in
 // bounds whatever the state is) and the surplus symbols are simply not stored.
@@ -1299,9 +1309,12 @@ __device__ __forceinline__ uint32_t rans_get(uint64_t& x, WordRing& rd, const Ta
     const bool near = rans_lookup_near(T, lut, lut_stride, lut_shift, slot, key, p, e, hi);
     const uint64_t top = x >> bits;
     uint64_t next = (uint64_t)((hi >> kSymBits) - (e >> kSymBits)) * top + (slot - (e >> kSymBits));  // rans64.hpp:126-134
-    if (__any_sync(0xffffffffu, !near)) {
-        rans_lookup_far(T, key, p, e, hi);
-        next = (uint64_t)((hi >> kSymBits) - (e >> kSymBits)) * top + (slot - (e >> kSymBits));
+    if (__builtin_expect(__any_sync(0xffffffffu, !near), 0)) {
+        // out of line: inlined, the walk sat in the middle of the step and the common case jumped over it — a taken
+        // branch and an instruction-fetch bubble (~20 cycles of a ~315-cycle step, ncu source view) on every symbol
+        const ulonglong2 fixed = rans_far_step(T, key, p, e, hi, top, slot);
+        next = fixed.x;
+        e = (uint32_t)fixed.y;
     }
     x = next;
     // rans64.hpp:137-141: x < 2^31, written on the two halves so that ONE predicate serves the state update and

@@ -76,6 +76,7 @@ SIGNATURES = {
     "hoh_ctx_create": (_int, [_int, _vp, C.POINTER(_vp)]),
     "hoh_ctx_destroy": (None, [_vp]),
     "hoh_sync": (_int, [_vp]),
+    "hoh_release_scratch": (_int, [_vp]),
     "hoh_strerror": (C.c_char_p, [_int]),
     "hoh_last_cuda_error": (C.c_char_p, [_vp]),
     "hoh_launch_count": (C.c_uint64, [_vp]),
@@ -206,6 +207,7 @@ class HohGpu:
         if st != HOH_OK:
             raise HohError(st, "hoh_ctx_create", "(no CUDA device? this library has no CPU fallback)")
         self.ctx = ctx
+        self.device = device
 
     def close(self):
         if self.ctx:
@@ -221,6 +223,9 @@ class HohGpu:
 
     def sync(self):
         self._ck(self.lib.hoh_sync(self.ctx), "hoh_sync")
+
+    def release_scratch(self):
+        self._ck(self.lib.hoh_release_scratch(self.ctx), "hoh_release_scratch")
 
     def launch_count(self):
         return int(self.lib.hoh_launch_count(self.ctx))
@@ -263,6 +268,10 @@ class HohGpu:
         buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=np.uint8).view(dtype)
         return arr
+
+    def host_free(self, arr):
+        """Release an array from host_alloc (the caller drops every view of it)."""
+        self._ck(self.lib.hoh_host_free(self.ctx, C.c_void_p(arr.ctypes.data)), "hoh_host_free")
 
     # ---- compat shims: reference names, reference value semantics -------------------------------
     def encode_entropy(self, symbols, range_, prob_bits):

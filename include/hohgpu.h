@@ -88,6 +88,9 @@ typedef struct hoh_ctx hoh_ctx;
 int hoh_ctx_create(int device, void* cuda_stream, hoh_ctx** out);
 void hoh_ctx_destroy(hoh_ctx* ctx);
 int hoh_sync(hoh_ctx* ctx);
+/* Frees the scratch device memory the context (and its internal child contexts) caches between calls.  The
+ * chunked entry points do this themselves when the image shape or mode changes. */
+int hoh_release_scratch(hoh_ctx* ctx);
 const char* hoh_strerror(int status);
 const char* hoh_last_cuda_error(hoh_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches claim). */

@@ -108,3 +108,21 @@ def test_whole_choh_file_md5_unequal_tiles(key):
     data, printed = _container().assemble_file(w, h, geo.x_tiles, geo.y_tiles, tiles)
     assert len(data) == int(z["files_size"][i])
     assert hashlib.md5(data).hexdigest() == str(z["files_md5"][i])
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_host_forms_round_trip_and_match_device_forms(mode):
+    """hoh_encode_images_host / hoh_decode_images_host (what tools/choh_batch.cpp and dhoh_batch.cpp call): same
+    tile bytes as the device-pointer form, exact round trip, two image shapes one after the other in one context
+    (the cached scratch of the first shape is released, the staging of the running call is not)."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(5 + mode)
+    for (w, h, n) in [(601, 523, 3), (256, 256, 5), (601, 523, 2)]:
+        imgs = np.concatenate([ol.photo_with_repeats(rng, w, h, 70 + i).ravel() for i in range(n)])
+        packed, off, rec = g.encode_images_host(imgs, n, w, h, mode, 24)
+        assert (rec["status"] == 0).all()
+        tiles, rec2 = g.encode_images(imgs, n, w, h, mode, 24)
+        assert [packed[int(off[t]):int(off[t + 1])].tobytes() for t in range(len(tiles))] == tiles
+        assert np.array_equal(rec["start"], off[:-1]) and np.array_equal(rec["size"], rec2["size"])
+        back, st = g.decode_images_host(packed, off, n, w, h)
+        assert (st == 0).all() and np.array_equal(back, imgs)
