@@ -196,6 +196,8 @@ int ensure_smem_opt_in(hoh_ctx* ctx) {
     CK(cudaFuncSetAttribute(k_rans_encode<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_decode<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_decode<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_decode_tiles_s0<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_decode_tiles_s0<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_tile_unpredict_s0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_tile_unpredict_s0<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_unpredict_fastpath_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -832,9 +834,48 @@ int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_by
     uint16_t* resid;
     hoh_dec_stream* streams;
     hoh_dec_result* results;
-    TRY(scratch_t(ctx, S_RESID, n_streams * g.plane_stride, &resid));
     TRY(scratch_t(ctx, S_DSTREAMS, n_streams, &streams));
     TRY(scratch_t(ctx, S_DRESULTS, n_streams, &results));
+    // Fused path: entropy decode, un-prediction, colour inverse and scatter in one kernel (k_rans_decode_tiles_s0);
+    // needs equal tiles whose rows are whole groups of 8 pixels and 8-byte aligned image rows.
+    const bool fused = !d_backref && g.tile_w * g.x_tiles == g.width && g.tile_h * g.y_tiles == g.height && g.tile_w % 8 == 0 &&
+                       g.tile_w >= 16 && g.width % 8 == 0 && (reinterpret_cast<uintptr_t>(d_rgb) & 7u) == 0 &&
+                       !getenv("HOH_NO_FUSED_DECODE");
+    if (fused) {
+        uint32_t* cum;
+        DecMeta* meta;
+        TRY(scratch_t(ctx, S_CUM, n_streams * kCumRow, &cum));
+        TRY(scratch_t(ctx, S_DECMETA, n_streams, &meta));
+        TRY(ensure_smem_opt_in(ctx));
+        k_make_tile_dec_streams<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(g, n_tiles, d_packed, packed_bytes,
+                                                                                     d_packed_off, streams, d_status);
+        LAUNCHED("k_make_tile_dec_streams");
+        k_parse_streams<<<blocks_for(n_streams, kTableWarps), kTableWarps * 32, 0, ctx->stream>>>(
+            streams, (uint32_t)n_streams, d_packed, packed_bytes, cum, meta, results);
+        LAUNCHED("k_parse_streams");
+        const uint32_t classes[5] = {0, 64, 128, 256, HOH_MAX_RANGE + 3};
+        const bool overlap = !ctx->profiling;
+        if (overlap) TRY(aux_fork(ctx, 4));
+        const unsigned grid = blocks_for(n_tiles, kFusedTiles);
+        for (int c = 0; c < 4; c++) {
+            const uint32_t rows = classes[c + 1];
+            const size_t fixed = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kRingWords * sizeof(uint32_t) + kFusedStage;
+            cudaStream_t sc = overlap ? ctx->aux[c] : ctx->stream;
+            if (rows <= 256) {
+                k_rans_decode_tiles_s0<uint8_t><<<grid, 32, fixed + kLutSize * 32 * 1, sc>>>(
+                    streams, (uint32_t)n_streams, d_packed, packed_bytes, cum, meta, results, g, d_rgb, d_status, classes[c], rows);
+            } else {
+                k_rans_decode_tiles_s0<uint16_t><<<grid, 32, fixed + kLutSize * 32 * 2, sc>>>(
+                    streams, (uint32_t)n_streams, d_packed, packed_bytes, cum, meta, results, g, d_rgb, d_status, classes[c], rows);
+            }
+            static const char* const names[4] = {"k_rans_decode_tiles_s0[rows<=64]", "k_rans_decode_tiles_s0[rows<=128]",
+                                                 "k_rans_decode_tiles_s0[rows<=256]", "k_rans_decode_tiles_s0[rows<=515]"};
+            LAUNCHED(names[c]);
+        }
+        if (overlap) TRY(aux_join(ctx, 4));
+        return HOH_OK;
+    }
+    TRY(scratch_t(ctx, S_RESID, n_streams * g.plane_stride, &resid));
     const size_t unp_smem = (size_t)kUnpWarps * ((32 * kRingStride + g.tile_w + (g.tile_w + 1) / 2 + 3) & ~(size_t)3) * sizeof(uint32_t);
     if (unp_smem > 200 * 1024) return HOH_E_UNSUPPORTED;
     k_make_tile_dec_streams<<<blocks_for(n_streams, 256), 256, 0, ctx->stream>>>(g, n_tiles, d_packed, packed_bytes,

@@ -4496,6 +4496,289 @@ __global__ void __launch_bounds__(256) k_dt_store(TileSel sel, uint64_t first_im
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Fused mode-0 tile decoder: rANS decode + MED un-prediction + colour inverse + tile scatter in ONE kernel.
+// -------------------------------------------------------------------------------------------------
+// The rANS step of a stream is one long dependent chain that leaves half of the issue slots of an SM idle
+// (k_rans_decode: 2.5 warps per scheduler, ~60 instructions per ~315-cycle step), and the un-prediction of a pixel
+// is a second, independent chain: v = (r + med(T, L, T + L - TL) - c/2) mod c depends on the pixel to the left, not
+// on the coder's state.  Run in the same lane they interleave, the residual planes never exist in memory (the
+// unfused pair writes and re-reads 2 x 6.4 GB of u16 symbols at BASELINE config 2) and k_tile_unpredict_s0's launch
+// (4.3 ms) disappears.
+//
+// One warp per CTA, 30 lanes = the G, R-G, B-G streams of 10 whole tiles (lanes 30, 31 idle), all tiles of the launch
+// of one shape with tile_w % 8 == 0.  At step k a lane holds residual k of its plane, i.e. pixel (k / tile_w,
+// k % tile_w): its left neighbour is the value it produced one step ago (a register), and the row above comes from
+// the OUTPUT IMAGE itself — the RGB bytes this warp stored tile_w steps earlier, re-read through L2 (__ldcg, after
+// the __syncwarp that orders the stores) 24 bytes = 8 pixels at a time, one group ahead of their use, and turned back
+// into the lane's plane (G, or R - G + 256 / B - G + 256: channel.hpp:75-77).  The finished value reaches the other
+// two channels of its tile by one shuffle (G), every lane puts ITS byte of the pixel into a 24-byte row of shared
+// memory, and after 8 steps each lane stores 8 of its tile's 24 bytes with one aligned 8-byte store.
+// Streams in stored mode (entropy_encoding.hpp:244-267) are read by the same lanes from the same word ring
+// (maxbits per symbol, MSB first); a tile with a damaged stream is reported and left untouched.
+constexpr int kFusedTiles = 10;                  // tiles per warp
+constexpr int kFusedLanes = 3 * kFusedTiles;     // working lanes
+constexpr int kFusedStage = 272;                 // bytes of output staging per warp
+
+struct StoredYes { static constexpr bool value = true; };
+struct StoredNo { static constexpr bool value = false; };
+
+template <typename LutT>
+__global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_stream* __restrict__ streams,
+                                                             uint32_t n_streams, const uint8_t* __restrict__ in,
+                                                             uint64_t in_bytes, const uint32_t* __restrict__ cumtab,
+                                                             const DecMeta* __restrict__ meta,
+                                                             const hoh_dec_result* __restrict__ results, TileGeom g,
+                                                             uint8_t* __restrict__ rgb, int32_t* __restrict__ status,
+                                                             uint32_t rows_lo, uint32_t rows) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* rings = tab + (size_t)rows * 32u;
+    uint8_t* stage = reinterpret_cast<uint8_t*>(rings + 32 * kRingWords);  // 11 rows of 24 bytes: 10 tiles + one for the idle lanes
+    LutT* lut = reinterpret_cast<LutT*>(stage + kFusedStage);
+
+    const uint32_t lane = lane_id();
+    const uint32_t ch = lane % 3u, tl = lane / 3u;  // channel (0 G, 1 R-G, 2 B-G) and tile inside the warp
+    const uint32_t s = blockIdx.x * (uint32_t)kFusedLanes + lane;
+    const bool exists = lane < (uint32_t)kFusedLanes && s < n_streams;
+    hoh_dec_stream st;
+    DecMeta m;
+    st.sym_cap = 0;
+    m.kind = 0;
+    m.n = 0;
+    m.range = 1;
+    m.prob_bits = 1;
+    m.maxbits = 1;
+    m.payload_off = 0;
+    m.status = HOH_S_OK;
+    m.used = 0;
+    int32_t my_status = HOH_S_OK;
+    if (exists) {
+        st = streams[s];
+        m = meta[s];
+        my_status = status[s];
+        if (my_status == HOH_S_OK) my_status = results[s].status;
+    }
+    const uint32_t tw = g.tile_w, th = g.tile_h, npx = tw * th;
+    // a stream that can fill its plane: sound header, one symbol per pixel (no LZ map here), rANS or stored
+    const bool sound = exists && my_status == HOH_S_OK && (m.kind == 2u || m.kind == 1u) && m.n == npx && st.sym_cap >= npx;
+    if (exists && my_status == HOH_S_OK && !sound) my_status = HOH_S_BAD_LAYER;
+    const bool coded = sound && m.kind == 2u;   // takes part in the rANS chain
+    const bool stored = sound && m.kind == 1u;  // reads maxbits-wide symbols
+    uint32_t need = coded ? m.used + 3u : 1u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) need = max(need, __shfl_xor_sync(0xffffffffu, need, d));
+    if (need <= rows_lo || need > rows) return;  // another class's launch
+    // the whole tile is decoded or none of it
+    const uint32_t base_lane = lane - ch;
+    // (three unconditional shuffles: with && a lane whose first answer is 0 would skip the others and fall out of step)
+    const int ok0 = __shfl_sync(0xffffffffu, (int)sound, min(base_lane, 31u));
+    const int ok1 = __shfl_sync(0xffffffffu, (int)sound, min(base_lane + 1u, 31u));
+    const int ok2 = __shfl_sync(0xffffffffu, (int)sound, min(base_lane + 2u, 31u));
+    const bool tile_ok = (ok0 & ok1 & ok2) != 0 && lane < (uint32_t)kFusedLanes;
+
+    for (uint32_t j = 0; j < (uint32_t)kFusedLanes; j++) {
+        const uint32_t sj = blockIdx.x * (uint32_t)kFusedLanes + j;
+        const bool lj = __shfl_sync(0xffffffffu, (int)coded, j) != 0;
+        const uint32_t uj = __shfl_sync(0xffffffffu, m.used, j);
+#ifdef HOH_DEBUG_FUSED
+        if (blockIdx.x == 0 && j < 3 && (lane == 0 || lane == 5)) printf("fill j %u lane %u lj %d uj %u my used %u\n", j, lane, (int)lj, uj, m.used);
+#endif
+        if (!lj) continue;
+        const uint32_t* src = cumtab + (size_t)sj * kCumRow;
+        for (uint32_t i = lane; i < uj + 3u; i += 32) tab[i * 32u + j] = src[i];
+    }
+    __syncwarp();
+#ifdef HOH_DEBUG_FUSED
+    if (blockIdx.x == 0 && lane == 0) printf("A after fill: tab[128]=%08x tab[160]=%08x rows=%u need=%u\n", tab[128], tab[160], rows, need);
+#endif
+
+    const PerLaneDense T{tab, lane};
+    const uint32_t bits = coded ? m.prob_bits : 1u;
+    const uint32_t mask = (1u << bits) - 1u;
+    const uint32_t lut_shift = bits > 7u ? bits - 7u : 0u;
+    if (coded) {
+        lut_build(T, lut + lane, 32u, lut_shift, m.used);
+    } else {  // stored / idle / damaged lane: a one-symbol table that owns the whole range, so that its state never moves
+        tab[lane] = 0u;
+        tab[32u + lane] = 0u;
+        tab[64u + lane] = (1u << bits) << kSymBits;
+        tab[96u + lane] = 0xffffffffu;
+        for (uint32_t j = 0; j < (uint32_t)kLutSize; j++) lut[j * 32u + lane] = (LutT)1;
+    }
+    __syncwarp();
+#ifdef HOH_DEBUG_FUSED
+    if (blockIdx.x == 0 && lane == 0) printf("B after lut: tab[128]=%08x tab[160]=%08x\n", tab[128], tab[160]);
+#endif
+
+    WordRing rd;
+    rd.open(in, in_bytes, sound ? m.payload_off : 0ull, rings + lane * kRingWords);
+#ifdef HOH_DEBUG_FUSED
+    if (blockIdx.x == 0 && lane == 0) printf("C after open: tab[128]=%08x tab[160]=%08x\n", tab[128], tab[160]);
+#endif
+    uint64_t x = kRansL;
+    if (coded) {  // rans64.hpp:107-116
+        const uint32_t lo = rd.next;
+        rd.take_if(true);
+        const uint32_t hi = rd.next;
+        rd.take_if(true);
+        x = (uint64_t)lo | ((uint64_t)hi << 32);
+    }
+#ifdef HOH_DEBUG_FUSED
+    if (blockIdx.x == 0 && lane < 3) {
+        printf("lane %u cumtab: %08x %08x %08x %08x %08x %08x %08x\n", lane, cumtab[(size_t)s * kCumRow], cumtab[(size_t)s * kCumRow + 1], cumtab[(size_t)s * kCumRow + 2], cumtab[(size_t)s * kCumRow + 3], cumtab[(size_t)s * kCumRow + 4], cumtab[(size_t)s * kCumRow + 5], cumtab[(size_t)s * kCumRow + 6]);
+        printf("lane %u tab:    %08x %08x %08x %08x %08x %08x %08x\n", lane, T.at(0), T.at(1), T.at(2), T.at(3), T.at(4), T.at(5), T.at(6));
+        printf("lane %u s %u payload_off %llu x0 %llx rows: %08x %08x %08x %08x %08x lut0 %u lut64 %u lut127 %u pos %u shift %u\n", lane, s,
+               (unsigned long long)m.payload_off, (unsigned long long)x, T.at(0), T.at(1), T.at(2), T.at(3), T.at(4), (unsigned)lut[lane],
+               (unsigned)lut[64 * 32 + lane], (unsigned)lut[127 * 32 + lane], rd.pos, rd.shift);
+    }
+#endif
+    const bool any_stored = __any_sync(0xffffffffu, stored);
+    uint64_t acc = 0;  // stored lanes: bits not yet consumed, left-aligned
+    uint32_t have = 0;
+    const uint32_t sbits = m.maxbits;
+
+    // geometry of the lane's tile (all tiles of the launch have the shape tw x th)
+    const uint64_t t_glob = (uint64_t)blockIdx.x * kFusedTiles + min(tl, (uint32_t)kFusedTiles - 1u);
+    const uint64_t image = t_glob / g.tiles_per_image;
+    const uint32_t tile = (uint32_t)(t_glob % g.tiles_per_image);
+    const uint32_t x0 = (tile % g.x_tiles) * g.tile_w, y0 = (tile / g.x_tiles) * g.tile_h;
+    uint8_t* img = rgb + image * (uint64_t)g.width * g.height * 3u;
+    const uint64_t row_bytes = (uint64_t)g.width * 3u;
+    uint8_t* tile0 = img + ((uint64_t)y0 * g.width + x0) * 3u;  // pixel (0, 0) of the tile
+    // per-lane constants of the colour transform: byte of the pixel this lane owns (R, G, B = 0, 1, 2)
+    const uint32_t half = ch == 0u ? 128u : 256u, cmask = ch == 0u ? 255u : 511u;
+    const uint32_t own_shift = ch == 0u ? 8u : (ch == 1u ? 0u : 16u);
+    const uint32_t gsub = ch == 0u ? 0u : 1u;          // planes 1, 2 are differences to G
+    const uint32_t off256 = ch == 0u ? 0u : 256u;
+    uint8_t* my_stage = stage + tl * 24u + (own_shift >> 3);
+    const uint2* my_out_src = reinterpret_cast<const uint2*>(stage + tl * 24u + 8u * ch);
+
+    // The two chains are software-pipelined by one pixel: step (grp, i) decodes symbol 8 grp + i and, in the shadow of
+    // its two shared-memory round trips, un-predicts the pixel whose residual the PREVIOUS step delivered.  (The
+    // far-walk vote of every step is a branch the compiler does not schedule across, so work that depended on this
+    // step's symbol would sit at the end of the step, on the chain.)
+    uint32_t L = half, TLv = half;
+    uint32_t r_prev = 0, t_prev = half;               // residual of the pixel in flight and the T value that goes with it
+    uint2 ta = make_uint2(0x80808080u, 0x80808080u), tb = ta, tc = ta;  // the 24 bytes above the current group (row 0: c/2)
+    const uint32_t groups = npx / 8u;                 // tw % 8 == 0
+    uint32_t gx = 0, gy = 0;                          // position of the current group in the tile (warp-uniform)
+    uint32_t px_x = 0, px_gy = 0;                     // the same for the group the pixel in flight belongs to
+    // un-predict the pixel in flight (column `col` of its row), hand its byte to the stage slot `slot`
+    auto finish_pixel = [&](uint32_t slot, bool row_start) {
+        if (row_start) {  // prediction.hpp:25-26
+            L = half;
+            TLv = half;
+        }
+        // median(T, L, (u16)(T + L - TL)) on 10-bit values: a negative gradient wraps to a huge unsigned value in 32 bits
+        // exactly as it does in the reference's 16 (predictor_operations.hpp:37-60), so no 16-bit mask is needed
+        const uint32_t grad = t_prev + L - TLv;
+        const uint32_t med = max(min(t_prev, L), min(max(t_prev, L), grad));
+        const uint32_t v = (r_prev + med - half) & cmask;  // inverse of prediction.hpp:34
+        TLv = t_prev;
+        L = v;
+        const uint32_t gv = __shfl_sync(0xffffffffu, v, base_lane);
+        my_stage[3u * slot] = (uint8_t)(v + gsub * gv - off256);  // inverse of channel.hpp:75-77 (mod 256)
+    };
+    // T of the 8 pixels of a group from the 24 RGB bytes above them, byte-wise: own byte minus G (mod 256) in t_lo, and for
+    // the difference planes the ninth bit (R - G + 256 has bit 8 set iff R >= G) in t_hi; row 0 is fed bytes 0x80, which
+    // give c/2 for every plane (prediction.hpp:20-22)
+    uint32_t t_lo0 = 0, t_lo1 = 0, t_hi0 = 0, t_hi1 = 0;
+    // __byte_perm selectors that pick this lane's own byte of pixels 0-3 / 4-7 out of three words (R, G or B)
+    const uint32_t own_sel1 = ch == 0u ? 0x0741u : (ch == 1u ? 0x0630u : 0x0052u);
+    const uint32_t own_sel2 = ch == 0u ? 0x6210u : (ch == 1u ? 0x5210u : 0x7410u);
+    const uint32_t g_keep = ch == 0u ? 0u : 0xffffffffu, hi_keep = ch == 0u ? 0u : 0x01010101u;
+    auto t_prepare = [&](uint2 a, uint2 b, uint2 c) {
+        // bytes: a.x = R0 G0 B0 R1 | a.y = G1 B1 R2 G2 | b.x = B2 R3 G3 B3 | b.y = R4 G4 B4 R5 | c.x = G5 B5 R6 G6 | c.y = B6 R7 G7 B7
+        const uint32_t g03 = __byte_perm(__byte_perm(a.x, a.y, 0x0741), b.x, 0x6210);  // G0 G1 G2 G3
+        const uint32_t g47 = __byte_perm(__byte_perm(b.y, c.x, 0x0741), c.y, 0x6210);  // G4 G5 G6 G7
+        const uint32_t o03 = __byte_perm(__byte_perm(a.x, a.y, own_sel1), b.x, own_sel2);
+        const uint32_t o47 = __byte_perm(__byte_perm(b.y, c.x, own_sel1), c.y, own_sel2);
+        t_lo0 = __vsub4(o03, g03 & g_keep);
+        t_lo1 = __vsub4(o47, g47 & g_keep);
+        t_hi0 = __vcmpgeu4(o03, g03) & hi_keep;
+        t_hi1 = __vcmpgeu4(o47, g47) & hi_keep;
+    };
+    auto t_of = [&](uint32_t i) -> uint32_t {
+        const uint32_t lo = i < 4u ? t_lo0 : t_lo1, hi = i < 4u ? t_hi0 : t_hi1;
+        return ((lo >> (8u * (i & 3u))) & 255u) | (((hi >> (8u * (i & 3u))) & 1u) << 8);
+    };
+    auto next_symbol = [&](auto has_stored) -> uint32_t {
+        uint32_t r = rans_get(x, rd, T, lut + lane, 32u, lut_shift, bits, mask);
+        if (decltype(has_stored)::value) {
+            const bool refill = stored && have < sbits;
+            if (refill) {
+                acc |= (uint64_t)__byte_perm(rd.next, 0u, 0x0123) << (32u - have);
+                have += 32u;
+            }
+            rd.take_if(refill);
+            if (stored) {
+                r = (uint32_t)(acc >> (64u - sbits));
+                acc <<= sbits;
+                have -= sbits;
+            }
+        }
+        return r;
+    };
+    auto flush_group = [&](uint32_t fx, uint32_t fy) {  // the 24 staged bytes of every tile -> the image
+        __syncwarp();
+        if (tile_ok) *reinterpret_cast<uint2*>(tile0 + (uint64_t)fy * row_bytes + (uint64_t)fx * 3u + 8u * ch) = *my_out_src;
+        __syncwarp();  // the stage may be rewritten, and the stores are ordered before the loads of later groups
+    };
+    // the loop exists twice: warps without a stored-mode stream (nearly all) run a copy without the bit reader
+    auto run = [&](auto has_stored) {
+    for (uint32_t grp = 0; grp < groups; grp++) {
+        rd.top_up();
+        uint32_t nx = gx + 8u, ny = gy;
+        if (nx == tw) {
+            nx = 0u;
+            ny++;
+        }
+        t_prepare(ta, tb, tc);
+        // step 0: symbol 0 of this group; pixel 7 of the previous one, which completes that group
+        {
+            if (grp > 0u) finish_pixel(7u, false);
+            const uint32_t r = next_symbol(has_stored);
+            r_prev = r;
+            t_prev = t_of(0u);
+            if (grp > 0u) flush_group(px_x, px_gy);
+        }
+        // the bytes above the NEXT group: stored at least one whole group ago (tile_w >= 16), and after the flush above
+        uint2 na = make_uint2(0x80808080u, 0x80808080u), nb = na, nc = na;
+        if (ny > 0u && ny < th && tile_ok) {
+            const uint2* src = reinterpret_cast<const uint2*>(tile0 + (uint64_t)(ny - 1u) * row_bytes + (uint64_t)nx * 3u);
+            na = __ldcg(src);
+            nb = __ldcg(src + 1);
+            nc = __ldcg(src + 2);
+        }
+#pragma unroll
+        for (uint32_t i = 1; i < 8u; i++) {
+            finish_pixel(i - 1u, i == 1u && gx == 0u);
+            const uint32_t r = next_symbol(has_stored);
+            r_prev = r;
+            t_prev = t_of(i);
+        }
+        px_x = gx;
+        px_gy = gy;
+        ta = na;
+        tb = nb;
+        tc = nc;
+        gx = nx;
+        gy = ny;
+    }
+    };
+    if (any_stored) {
+        run(StoredYes{});
+    } else {
+        run(StoredNo{});
+    }
+    finish_pixel(7u, false);
+    flush_group(px_x, px_gy);
+    // rans64.hpp:65: decoding undoes the encoder's steps, so a sound stream ends in the encoder's initial state
+    if (coded && x != kRansL) my_status = HOH_S_BAD_STATE;
+    if (exists) status[s] = my_status;
+}
+
 // Mode-0 tile back end WITH LZ back-references (hoh_decode_images_s0, d_backref != NULL): a copied pixel may
 // depend on any earlier pixel of its tile (unprediction.hpp:63-65), so the wavefront does not apply; one thread
 // walks one channel plane in raster order.  Residuals are dense (only the pixels no match covers have one,

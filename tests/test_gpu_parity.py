@@ -665,3 +665,32 @@ def test_decode_images_s0_with_backrefs(w, h, n):
     wrong[first_free] = 1
     back3, st3 = g.decode_images_s0(packed, off, n, w, h, backref=wrong)
     assert st3[0] == 5 and st3[1] == 5 and st3[2] == 5
+
+
+def test_fused_tile_decoder_reports_damage_and_leaves_the_tile_alone():
+    """k_rans_decode_tiles_s0 (entropy decode + un-prediction + colour inverse + scatter in one kernel): a changed
+    payload byte shows up as HOH_S_BAD_STATE on its stream, a broken channel header as HOH_S_BAD_LAYER and its tile is
+    not written; every other tile of the batch still decodes exactly."""
+    g = gpu_lib.gpu()
+    W, H, n = 512, 512, 3
+    rgb = np.concatenate([ol.synth_rgb(W, H, 20 + i) for i in range(n)])
+    packed, off, res = g.encode_images_s0(rgb, n, W, H)
+    geom = g.tile_geometry(W, H)
+    bad = packed.copy()
+    s_state, s_layer = 7, 22                       # stream 7 = tile 2 of image 0, stream 22 = tile 3 of image 1
+    bad[int(off[s_state]) + 900] ^= 0x10           # inside the rANS payload
+    bad[int(off[s_layer])] = 0x11                  # channel header byte (layer_encode.hpp:57)
+    back, st = g.decode_images_s0(bad, off, n, W, H)
+    assert st[s_state] == 6 and st[s_layer] == 5
+    assert np.count_nonzero(st) == 2
+    img = back.reshape(n, H, W, 3)
+    want = rgb.reshape(n, H, W, 3)
+    for i in range(n):
+        for t in range(geom.tiles_per_image):
+            x0, y0 = (t % geom.x_tiles) * geom.tile_w, (t // geom.x_tiles) * geom.tile_h
+            got_t = img[i, y0:y0 + geom.tile_h, x0:x0 + geom.tile_w]
+            k = i * geom.tiles_per_image + t
+            if k == s_layer // 3:
+                assert not got_t.any()             # the wrapper zeroes the output: the tile was never written
+            elif k != s_state // 3:                # (a BAD_STATE tile is written: its symbols are still delivered)
+                assert np.array_equal(got_t, want[i, y0:y0 + geom.tile_h, x0:x0 + geom.tile_w]), (i, t)
