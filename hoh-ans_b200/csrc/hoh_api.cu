@@ -256,7 +256,7 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
     for (int c = 0; c < 4; c++) {
         if (classes[c] >= max_range + 1) break;
         const uint32_t rows = classes[c + 1];
-        const size_t stage = 2 * 32 * kSymStride * sizeof(uint16_t);
+        const size_t stage = 2 * 32 * kBulkStride * sizeof(uint16_t);
         const size_t smem16 = (size_t)rows * 32 * sizeof(uint16_t) + stage, smem32 = (size_t)rows * 32 * sizeof(uint32_t) + stage;
         cudaStream_t s16 = overlap ? ctx->aux[2 * c] : ctx->stream, s32 = overlap ? ctx->aux[2 * c + 1] : ctx->stream;
         if (min_prob_bits >= 14) {
@@ -859,7 +859,12 @@ int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_by
         const unsigned grid = blocks_for(n_tiles, kFusedTiles);
         for (int c = 0; c < 4; c++) {
             const uint32_t rows = classes[c + 1];
-            const size_t fixed = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kRingWords * sizeof(uint32_t) + kFusedStage;
+            size_t fixed = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kRingWords * sizeof(uint32_t) + kFusedStage;
+            // The kernel is bound by instruction-pipe throughput, so an SM's time grows with the number of warps it
+            // holds: 13 CTAs of the smallest class would fit one SM, and with the other classes' launches running
+            // beside it the block scheduler does fill some SMs that far while others hold 10.  Asking for 17 KB
+            // caps every SM at 12 (BASELINE config 2: 1 639 warps = 11.07 per SM).
+            if (fixed + kLutSize * 32 < 17408) fixed = 17408 - kLutSize * 32;
             cudaStream_t sc = overlap ? ctx->aux[c] : ctx->stream;
             if (rows <= 256) {
                 k_rans_decode_tiles_s0<uint8_t><<<grid, 32, fixed + kLutSize * 32 * 1, sc>>>(

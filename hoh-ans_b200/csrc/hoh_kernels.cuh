@@ -627,6 +627,7 @@ __device__ __forceinline__ void stage_wait() {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
 }
+template <int STRIDE = kSymStride>
 __device__ __forceinline__ void stage_load_chunk(uint16_t* stage, const uint16_t* __restrict__ symbols,
                                                  const uint64_t* s_off, const uint32_t* s_n, uint32_t chunk) {
     const uint32_t lane = lane_id(), half = lane >> 4, q = lane & 15u;
@@ -639,11 +640,47 @@ __device__ __forceinline__ void stage_load_chunk(uint16_t* stage, const uint16_t
         const uint32_t left = n > first ? min(n - first, 4u) : 0u;  // symbols of this quad that exist
         // never form an address past the stream: clamp the source to its start when nothing is read
         const uint16_t* src = symbols + s_off[r] + (left ? first : 0u);
-        const uint32_t dst = stage_addr + (r * (kSymStride / 2) + 2u * q) * 4u;
+        const uint32_t dst = stage_addr + (r * (STRIDE / 2) + 2u * q) * 4u;
         cp_async4(dst, src, min(left, 2u) * 2u);
         cp_async4(dst + 4u, src + (left > 2u ? 2 : 0), left > 2u ? (left - 2u) * 2u : 0u);
     }
 }
+
+// The same chunk moved by the copy engine: when every stream of the warp has the whole chunk (all but the ragged last
+// chunk of a stream), each lane issues ONE 128-byte cp.async.bulk for its own row (UBLKCP: source and destination
+// 16-byte aligned, completion counted in bytes on an mbarrier) instead of the warp walking 16 x 2 four-byte LDGSTS with
+// their address arithmetic (about 8.5 warp instructions per symbol of a ~67-instruction step).  Rows are 144 bytes
+// apart (kBulkStride): 16-byte aligned for the copy engine, and a lane's 8 symbols of a group come out with one
+// conflict-free LDS.128 (36 r mod 32 = 4 r: eight lanes x four words cover the 32 banks).
+constexpr int kBulkStride = 72;  // u16 per staged row
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Decode side: rows of `stage` (32 symbols per stream, row stride kDecStride) -> global symbol arrays.
 // Eight lanes cover one row with 8-byte stores, four rows per instruction.
@@ -684,6 +721,7 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
     uint16_t* stage0 = reinterpret_cast<uint16_t*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));
     __shared__ uint64_t s_off[32];
     __shared__ uint32_t s_n[32];
+    __shared__ __align__(8) uint64_t s_bar[2];  // one per staging buffer: bytes of its bulk copies still in flight
 
     const uint32_t lane = lane_id();
     const uint32_t s = blockIdx.x * 32u + lane;
@@ -719,6 +757,11 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
     }
     s_off[lane] = st.sym_off;
     s_n[lane] = live ? st.n : 0u;
+    if (lane == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
     __syncwarp();
 
     // tables: row i of stream j's window -> tab[i*32 + j]
@@ -754,15 +797,46 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
     // group g covers symbols [kGroup*g, kGroup*g + kGroup).
     const int n_chunks = (int)((n_max + kChunk - 1) / kChunk);
     constexpr int kGroupsPerChunk = kChunk / kGroup;
+    const uint16_t* my_sym = symbols + st.sym_off;
+    uint32_t bar_parity = 0;   // bit b: parity of the next completion of s_bar[b]
+    uint32_t bulk_loaded = 0;  // bit b: the chunk in buffer b came through the copy engine (else cp.async)
+    // chunk -> buffer (chunk & 1).  Warp-uniform choice of mechanism: the copy engine when no stream has a ragged chunk.
+    auto load_chunk = [&](int chunk) {
+        const uint32_t b = (uint32_t)chunk & 1u, first = (uint32_t)chunk * kChunk;
+        const uint32_t left = my_n > first ? my_n - first : 0u;
+        uint16_t* buf = stage0 + b * 32 * kBulkStride;
+        if (__any_sync(0xffffffffu, left > 0u && left < (uint32_t)kChunk)) {
+            stage_load_chunk<kBulkStride>(buf, symbols, s_off, s_n, (uint32_t)chunk);
+            bulk_loaded &= ~(1u << b);
+        } else {
+            const uint32_t rows_in = __popc(__ballot_sync(0xffffffffu, left != 0u));
+            fence_proxy_async();  // the buffer's previous contents were read through the generic proxy
+            if (left) bulk_g2s(buf + lane * kBulkStride, my_sym + first, kChunk * 2u, &s_bar[b]);
+            if (lane == 0) mbar_expect_tx(&s_bar[b], rows_in * kChunk * 2u);
+            bulk_loaded |= 1u << b;
+        }
+    };
+    auto wait_chunk = [&](int chunk) {
+        const uint32_t b = (uint32_t)chunk & 1u;
+        if (bulk_loaded & (1u << b)) {
+            mbar_wait(&s_bar[b], (bar_parity >> b) & 1u);
+            bar_parity ^= 1u << b;
+            __syncwarp();
+        } else {
+            stage_wait();
+        }
+    };
     auto prepare = [&](int g, uint32_t(&g_start)[kGroup], uint32_t(&g_freq)[kGroup], double(&g_inv)[kGroup]) {
         const int chunk = g / kGroupsPerChunk, k0 = (g % kGroupsPerChunk) * kGroup;
-        const uint16_t* row = stage0 + (chunk & 1) * 32 * kSymStride + lane * kSymStride + k0;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage0 + (chunk & 1) * 32 * kBulkStride + lane * kBulkStride + k0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         const uint32_t base = (uint32_t)g * kGroup;
 #pragma unroll
         for (int j = 0; j < kGroup; j++) {
             const bool on = base + (uint32_t)j < my_n;
+            const uint32_t raw = (j & 1) ? (w[j / 2] >> 16) : (w[j / 2] & 0xffffu);
             // window-relative index; out-of-alphabet input must not index past the lane's table
-            const uint32_t sym = on ? min((uint32_t)row[j] - win_lo, sym_max) : 0u;
+            const uint32_t sym = on ? min(raw - win_lo, sym_max) : 0u;
             const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
             g_start[j] = on ? c0 : 0u;  // padding step: freq = 2^bits, start = 0 leaves x untouched
             g_freq[j] = on ? c1 - c0 : full;
@@ -777,10 +851,9 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
     if (n_chunks > 0) {
         uint32_t a_start[kGroup], a_freq[kGroup], b_start[kGroup], b_freq[kGroup];
         double a_inv[kGroup], b_inv[kGroup];
-        stage_load_chunk(stage0 + ((n_chunks - 1) & 1) * 32 * kSymStride, symbols, s_off, s_n, (uint32_t)(n_chunks - 1));
-        stage_wait();
-        if (n_chunks > 1)
-            stage_load_chunk(stage0 + ((n_chunks - 2) & 1) * 32 * kSymStride, symbols, s_off, s_n, (uint32_t)(n_chunks - 2));
+        load_chunk(n_chunks - 1);
+        wait_chunk(n_chunks - 1);
+        if (n_chunks > 1) load_chunk(n_chunks - 2);
         const int n_groups = n_chunks * kGroupsPerChunk;  // even
         prepare(n_groups - 1, a_start, a_freq, a_inv);
         for (int g = n_groups - 1; g >= 1; g -= 2) {
@@ -789,9 +862,8 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
             if (g - 1 >= 1) {
                 if (((g - 1) % kGroupsPerChunk) == 0) {  // group g-2 is the last of the previous chunk
                     const int chunk = (g - 1) / kGroupsPerChunk;
-                    stage_wait();  // chunk-1 has landed; this chunk's buffer is free (its last group is in b_*)
-                    if (chunk >= 2)
-                        stage_load_chunk(stage0 + (chunk & 1) * 32 * kSymStride, symbols, s_off, s_n, (uint32_t)(chunk - 2));
+                    wait_chunk(chunk - 1);  // chunk-1 has landed; this chunk's buffer is free (its last group is in b_*)
+                    if (chunk >= 2) load_chunk(chunk - 2);
                 }
                 prepare(g - 2, a_start, a_freq, a_inv);
             }
