@@ -4721,8 +4721,6 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
     // per-lane constants of the colour transform: byte of the pixel this lane owns (R, G, B = 0, 1, 2)
     const uint32_t half = ch == 0u ? 128u : 256u, cmask = ch == 0u ? 255u : 511u;
     const uint32_t own_shift = ch == 0u ? 8u : (ch == 1u ? 0u : 16u);
-    const uint32_t gsub = ch == 0u ? 0u : 1u;          // planes 1, 2 are differences to G
-    const uint32_t off256 = ch == 0u ? 0u : 256u;
     uint8_t* my_stage = stage + tl * 24u + (own_shift >> 3);
     const uint2* my_out_src = reinterpret_cast<const uint2*>(stage + tl * 24u + 8u * ch);
 
@@ -4750,12 +4748,12 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
         TLv = t_prev;
         L = v;
         const uint32_t gv = __shfl_sync(0xffffffffu, v, base_lane);
-        my_stage[3u * slot] = (uint8_t)(v + gsub * gv - off256);  // inverse of channel.hpp:75-77 (mod 256)
+        my_stage[3u * slot] = (uint8_t)(v + (gv & g_keep));  // inverse of channel.hpp:75-77 (mod 256: the +256 drops out)
     };
     // T of the 8 pixels of a group from the 24 RGB bytes above them, byte-wise: own byte minus G (mod 256) in t_lo, and for
     // the difference planes the ninth bit (R - G + 256 has bit 8 set iff R >= G) in t_hi; row 0 is fed bytes 0x80, which
     // give c/2 for every plane (prediction.hpp:20-22)
-    uint32_t t_lo0 = 0, t_lo1 = 0, t_hi0 = 0, t_hi1 = 0;
+    uint32_t t01 = 0, t23 = 0, t45 = 0, t67 = 0;  // T of pixels (0,1), (2,3), (4,5), (6,7) of the group, two u16 each
     // __byte_perm selectors that pick this lane's own byte of pixels 0-3 / 4-7 out of three words (R, G or B)
     const uint32_t own_sel1 = ch == 0u ? 0x0741u : (ch == 1u ? 0x0630u : 0x0052u);
     const uint32_t own_sel2 = ch == 0u ? 0x6210u : (ch == 1u ? 0x5210u : 0x7410u);
@@ -4766,14 +4764,16 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
         const uint32_t g47 = __byte_perm(__byte_perm(b.y, c.x, 0x0741), c.y, 0x6210);  // G4 G5 G6 G7
         const uint32_t o03 = __byte_perm(__byte_perm(a.x, a.y, own_sel1), b.x, own_sel2);
         const uint32_t o47 = __byte_perm(__byte_perm(b.y, c.x, own_sel1), c.y, own_sel2);
-        t_lo0 = __vsub4(o03, g03 & g_keep);
-        t_lo1 = __vsub4(o47, g47 & g_keep);
-        t_hi0 = __vcmpgeu4(o03, g03) & hi_keep;
-        t_hi1 = __vcmpgeu4(o47, g47) & hi_keep;
+        const uint32_t lo03 = __vsub4(o03, g03 & g_keep), lo47 = __vsub4(o47, g47 & g_keep);
+        const uint32_t hi03 = __vcmpgeu4(o03, g03) & hi_keep, hi47 = __vcmpgeu4(o47, g47) & hi_keep;
+        t01 = __byte_perm(lo03, hi03, 0x5140);  // lo0 hi0 lo1 hi1
+        t23 = __byte_perm(lo03, hi03, 0x7362);
+        t45 = __byte_perm(lo47, hi47, 0x5140);
+        t67 = __byte_perm(lo47, hi47, 0x7362);
     };
     auto t_of = [&](uint32_t i) -> uint32_t {
-        const uint32_t lo = i < 4u ? t_lo0 : t_lo1, hi = i < 4u ? t_hi0 : t_hi1;
-        return ((lo >> (8u * (i & 3u))) & 255u) | (((hi >> (8u * (i & 3u))) & 1u) << 8);
+        const uint32_t pair = i < 2u ? t01 : (i < 4u ? t23 : (i < 6u ? t45 : t67));
+        return (i & 1u) ? (pair >> 16) : (pair & 0xffffu);
     };
     auto next_symbol = [&](auto has_stored) -> uint32_t {
         uint32_t r = rans_get(x, rd, T, lut + lane, 32u, lut_shift, bits, mask);
