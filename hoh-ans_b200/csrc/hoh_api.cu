@@ -1526,6 +1526,7 @@ int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles,
     const uint32_t slab = (uint32_t)hoh_enc_slab_bytes(stride, 10);
     if (lz_stride < (1 + 4 * (size_t)slab + 15) / 16 * 16 || lz_stride > 0xffffffffull) return HOH_E_CAPACITY;
     const uint32_t wide = distance > 8;
+    const uint32_t row_limit = (flags & HOH_FIX_LONE) ? 65535u : 65536u;  // lz.hpp:54 / :88-89, see k_lz_match
     sh.pad = 1u << distance;
     sh.px_stride = sh.pad + (sh.stride + kLzSeg - 1) / kLzSeg * kLzSeg + 32 * kLzAhead;
     uint32_t *px, *state, *counts;
@@ -1562,11 +1563,11 @@ int find_lz_impl(hoh_ctx* ctx, const uint8_t* d_rgb, LzShape sh, size_t n_tiles,
         const uint64_t bpt = (sh.stride + 255) / 256;
         k_lz_chains<<<(unsigned)(n_tiles * bpt), 256, 0, ctx->stream>>>(px, sh, n_tiles, heads, next);
         LAUNCHED("k_lz_chains");
-        k_lz_match_sparse<<<(unsigned)(n_tiles * bpt), 256, 0, ctx->stream>>>(px, sh, n_tiles, 1u << distance, heads, next, state,
+        k_lz_match_sparse<<<(unsigned)(n_tiles * bpt), 256, 0, ctx->stream>>>(px, sh, n_tiles, 1u << distance, row_limit, heads, next, state,
                                                                              flag);
         LAUNCHED("k_lz_match_sparse");
     }
-    k_lz_match<<<blocks_for(n_tiles * segs * 32, 128), 128, 0, ctx->stream>>>(px, sh, n_tiles, 1u << distance, wide, state,
+    k_lz_match<<<blocks_for(n_tiles * segs * 32, 128), 128, 0, ctx->stream>>>(px, sh, n_tiles, 1u << distance, wide ? row_limit : 0u, state,
                                                                              flag);
     LAUNCHED("k_lz_match");
     k_lz_walk<<<blocks_for(n_tiles * 32, 128), 128, 0, ctx->stream>>>(state, sh, n_tiles, d_bonus, 0, wide, d_nuke,
@@ -1838,16 +1839,19 @@ int hoh_decode_images(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_bytes
 // -------------------------------------------------------------------------------------------------
 } // extern "C" (reopened below)
 namespace {
-// Images per chunk of a whole-tile host call: at most four chunks (a launch of the entropy kernels lasts as long as
-// one stream's chain, so few large chunks beat many small ones; two are in flight), at least ~64 MB of pixels, and
-// the double-buffered staging (raw + packed, twice) must leave most of the device to the codec's own scratch.
+// Images per chunk of a whole-tile host call.  The mode >= 1 kernels (rANS candidates, the plane walks of the decoder) last
+// as long as ONE stream's serial chain however few streams a launch holds, so cutting a batch into k chunks multiplies
+// their time by almost k (BASELINE config 3, decode: 112 ms for 256 frames at once, 4 x ~100 ms in four chunks) while
+// the copies it would hide are short (6.4 GB at 55 GB/s = 116 ms).  Two chunks: the second one's H2D and the first
+// one's D2H overlap the kernels, and the chain is paid twice, not four times; one chunk when the batch is small.  The
+// double-buffered staging (raw + packed, twice) must leave most of the device to the codec's own scratch.
 size_t tile_chunk_images(size_t n_images, size_t raw_per_image) {
-    size_t per = (n_images + 3) / 4;
-    const size_t min_per = (64u << 20) / (raw_per_image ? raw_per_image : 1) + 1;
+    size_t per = (n_images + 1) / 2;
+    const size_t min_per = (256u << 20) / (raw_per_image ? raw_per_image : 1) + 1;
     if (per < min_per) per = min_per;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-        const size_t cap = free_b / 8 / (raw_per_image * 5 + 1);  // 2 x (raw + 1.5 raw packed) within an eighth of what is free
+        const size_t cap = free_b / 4 / (raw_per_image * 5 + 1);  // 2 x (raw + 1.5 raw packed) within a quarter of what is free
         if (cap >= 1 && per > cap) per = cap;
     }
     if (per > n_images) per = n_images;

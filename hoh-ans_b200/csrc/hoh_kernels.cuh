@@ -3413,6 +3413,10 @@ __global__ void __launch_bounds__(128) k_lz_match(const uint32_t* __restrict__ p
                                                   uint32_t near_limit, uint32_t wide,
                                                   uint32_t* __restrict__ state,
                                                   const uint32_t* __restrict__ only_flagged) {
+    // wide: 0 = near window only (lz.hpp:53: distance <= 8), else the largest whole-row distance tried.  The reference
+    // goes up to 65536 inclusive (lz.hpp:54) and then stores the distance in two bytes, so 65536 is written as 0
+    // (lz.hpp:88-89): byte-exact, but no decoder can tell it from "no distance".  With HOH_FIX_LONE the encoder stops
+    // at 65535, which costs one candidate distance and keeps every tile decodable.
     const uint32_t lane = lane_id();
     const uint32_t segs = (sh.stride + kLzSeg - 1) / kLzSeg;
     const uint64_t wid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -3450,7 +3454,7 @@ __global__ void __launch_bounds__(128) k_lz_match(const uint32_t* __restrict__ p
     // lz.hpp:53-74: whole rows up, multiples of the width up to 65536
     if (wide) {
         const uint32_t last = min(s0 + kLzSeg, npx) - 1u;  // highest pixel of the segment: larger distances reach nothing
-        for (uint32_t b = width; b <= 65536u && b <= last; b += width) {
+        for (uint32_t b = width; b <= wide && b <= last; b += width) {  // wide = the largest row distance: 65536, see below
             const bool framed = b <= s0 + sh.pad;
             if (framed) {  // quick test first: one load and one compare per 32 pixels
                 const uint32_t* q = P + s0 + lane - b;
@@ -3510,7 +3514,7 @@ __global__ void __launch_bounds__(256) k_lz_chains(const uint32_t* __restrict__ 
 
 // One thread per position: the earlier positions of its chain are its only candidates.
 __global__ void __launch_bounds__(256) k_lz_match_sparse(const uint32_t* __restrict__ px, LzShape sh, uint64_t n_tiles,
-                                                         uint32_t near_limit, const uint32_t* __restrict__ heads,
+                                                         uint32_t near_limit, uint32_t row_limit, const uint32_t* __restrict__ heads,
                                                          const uint32_t* __restrict__ next,
                                                          uint32_t* __restrict__ state, uint32_t* __restrict__ dense_flag) {
     const uint32_t bpt = (sh.stride + 255u) / 256u;
@@ -3530,7 +3534,7 @@ __global__ void __launch_bounds__(256) k_lz_match_sparse(const uint32_t* __restr
         }
         if (j >= i) continue;  // itself, or a later position
         const uint32_t b = i - j;
-        if (!(b <= near_limit || (b <= 65536u && b % width == 0u))) continue;  // lz.hpp:34, :54
+        if (!(b <= near_limit || (b <= row_limit && b % width == 0u))) continue;  // lz.hpp:34, :54
         uint32_t run = 0;
         while (run < (uint32_t)kLzMaxRun && i + run < npx && P[i + run] == P[j + run]) run++;
         if (run >= 4u) best = max(best, lz_key(run, b));
@@ -4721,6 +4725,7 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
     // per-lane constants of the colour transform: byte of the pixel this lane owns (R, G, B = 0, 1, 2)
     const uint32_t half = ch == 0u ? 128u : 256u, cmask = ch == 0u ? 255u : 511u;
     const uint32_t own_shift = ch == 0u ? 8u : (ch == 1u ? 0u : 16u);
+    const uint32_t g_keep = ch == 0u ? 0u : 0xffffffffu, hi_keep = ch == 0u ? 0u : 0x01010101u;  // planes 1, 2 are differences to G
     uint8_t* my_stage = stage + tl * 24u + (own_shift >> 3);
     const uint2* my_out_src = reinterpret_cast<const uint2*>(stage + tl * 24u + 8u * ch);
 
@@ -4757,7 +4762,6 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
     // __byte_perm selectors that pick this lane's own byte of pixels 0-3 / 4-7 out of three words (R, G or B)
     const uint32_t own_sel1 = ch == 0u ? 0x0741u : (ch == 1u ? 0x0630u : 0x0052u);
     const uint32_t own_sel2 = ch == 0u ? 0x6210u : (ch == 1u ? 0x5210u : 0x7410u);
-    const uint32_t g_keep = ch == 0u ? 0u : 0xffffffffu, hi_keep = ch == 0u ? 0u : 0x01010101u;
     auto t_prepare = [&](uint2 a, uint2 b, uint2 c) {
         // bytes: a.x = R0 G0 B0 R1 | a.y = G1 B1 R2 G2 | b.x = B2 R3 G3 B3 | b.y = R4 G4 B4 R5 | c.x = G5 B5 R6 G6 | c.y = B6 R7 G7 B7
         const uint32_t g03 = __byte_perm(__byte_perm(a.x, a.y, 0x0741), b.x, 0x6210);  // G0 G1 G2 G3

@@ -204,3 +204,22 @@ def test_chunked_walks_equal_one_pass(monkeypatch):
         assert tiles == tiles_one, budget
         back, st = g.decode_images(tiles, n, w, h)
         assert (st == 0).all() and np.array_equal(back, rgb), budget
+
+
+def test_row_distance_65536_stays_decodable_with_the_encoder_fix():
+    """lz.hpp:54 accepts whole-row distances up to 65536 inclusive and lz.hpp:88-89 stores a distance in two bytes, so
+    65536 is written as 0 — byte-exact with the reference, but undecodable.  A 256-wide tile whose rows repeat 256
+    rows further up hits exactly that distance.  flags = 0 must still reproduce the reference's bytes; with
+    HOH_FIX_ENCODER the finder stops at 65535 and the tile round-trips."""
+    g = gpu_lib.gpu()
+    w, h = 256, 300
+    img = ol.synth_rgb(w, h, 77).reshape(h, w, 3).copy()
+    img[256:] = img[:44]                                    # rows 256.. repeat rows 0..: distance 256 * 256
+    flat = img.ravel()
+    tiles0, rec0 = g.encode_images(flat, 1, w, h, 2, 0)
+    want, nuke = ol.orc_encode_tile_subgreen(img, 2)
+    assert tiles0[0] == want and nuke[256 * w:].sum() > 1000   # the reference does take the 65536-distance matches
+    tiles, rec = g.encode_images(flat, 1, w, h, 2, 24)
+    assert rec["status"][0] == 0
+    back, st = g.decode_images(tiles, 1, w, h)
+    assert st[0] == 0 and np.array_equal(back, flat)

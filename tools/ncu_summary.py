@@ -96,6 +96,14 @@ def full(path, traffic_path=None, images=4096):
             traffic[b] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                           "ms_under_ncu": dur_ms(r), "kernel": n, "images": images}
     if traffic_path:
+        # stamp with the kernel source the capture was taken from: bench.py quotes the figures only while it is unchanged
+        import hashlib
+        import os
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        h = hashlib.sha1()
+        for f in ("hoh_kernels.cuh", "hoh_api.cu", "hoh_format.cuh"):
+            h.update(open(os.path.join(root, "hoh-ans_b200", "csrc", f), "rb").read())
+        traffic["_kernel_source_sha1"] = h.hexdigest()
         json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 
 
