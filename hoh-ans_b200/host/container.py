@@ -20,9 +20,14 @@ def file_header(width, height):
     return bytes([153, 72, 79, 72, 2, 8]) + write_varint(width - 1) + write_varint(height - 1)
 
 
-def assemble_file(width, height, x_tiles, y_tiles, tiles):
+def assemble_file(width, height, x_tiles, y_tiles, tiles, flags=None):
     """choh.cpp:454-506.  tiles: the encode_tile bytes of every tile in raster order.  Returns the file bytes
-    and the size `choh` prints."""
+    and the size `choh` prints.  flags: the `flags` column of hoh_encode_images' tile records; a tile flagged
+    HOH_TILE_GREY / HOH_TILE_PALETTE was emitted in subtract-green mode where the reference would have taken its
+    greyscale / indexed branch, so the file would be valid but NOT what choh writes: refused unless flags is None."""
+    if flags is not None and any(int(f) for f in flags):
+        raise ValueError("tiles flagged HOH_TILE_GREY / HOH_TILE_PALETTE: the reference codes them in a colour mode "
+                         "that stays on the host (choh.cpp:180-213, 298-307)")
     out = bytearray(file_header(width, height))
     if (width >= 512 or height >= 512) and width >= 256 and height >= 256:
         assert len(tiles) == x_tiles * y_tiles

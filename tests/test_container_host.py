@@ -50,3 +50,14 @@ def test_untiled_image_writes_only_the_header():
     out, printed = c.assemble_file(2, 2, 1, 1, [bytes(26)])
     assert out == bytes([0x99, 0x48, 0x4f, 0x48, 0x02, 0x08, 0x01, 0x01])   # example.rgb at -s0
     assert printed == 34
+
+
+def test_flagged_tiles_are_refused():
+    """A tile the device emitted in subtract-green mode where the reference would have gone greyscale / indexed must not
+    end up in a file silently (hoh_tile_result.flags)."""
+    import pytest
+    c = _container()
+    tiles = [bytes(30)] * 4
+    c.assemble_file(512, 512, 2, 2, tiles, [0, 0, 0, 0])
+    with pytest.raises(ValueError):
+        c.assemble_file(512, 512, 2, 2, tiles, [0, 2, 0, 0])

@@ -46,7 +46,7 @@ def test_whole_choh_file_md5(key):
     tiles, rec = g.encode_images(ol.synth_rgb(w, h, 1), 1, w, h, int(mode))
     assert (rec["status"] == 0).all()
     geo = g.tile_geometry(w, h)
-    data, printed = _container().assemble_file(w, h, geo.x_tiles, geo.y_tiles, tiles)
+    data, printed = _container().assemble_file(w, h, geo.x_tiles, geo.y_tiles, tiles, rec["flags"])
     assert len(data) == int(z["files_size"][i])
     assert hashlib.md5(data).hexdigest() == str(z["files_md5"][i])
     if key == "512x512_s0":
@@ -105,7 +105,7 @@ def test_whole_choh_file_md5_unequal_tiles(key):
     tiles, rec = g.encode_images(ol.synth_rgb(w, h, 1), 1, w, h, int(mode))
     assert (rec["status"] == 0).all()
     geo = g.tile_geometry(w, h)
-    data, printed = _container().assemble_file(w, h, geo.x_tiles, geo.y_tiles, tiles)
+    data, printed = _container().assemble_file(w, h, geo.x_tiles, geo.y_tiles, tiles, rec["flags"])
     assert len(data) == int(z["files_size"][i])
     assert hashlib.md5(data).hexdigest() == str(z["files_md5"][i])
 
