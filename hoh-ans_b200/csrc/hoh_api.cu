@@ -259,18 +259,22 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
         const size_t stage = 2 * 32 * kBulkStride * sizeof(uint16_t);
         const size_t smem16 = (size_t)rows * 32 * sizeof(uint16_t) + stage, smem32 = (size_t)rows * 32 * sizeof(uint32_t) + stage;
         cudaStream_t s16 = overlap ? ctx->aux[2 * c] : ctx->stream, s32 = overlap ? ctx->aux[2 * c + 1] : ctx->stream;
-        if (min_prob_bits >= 14) {
-            k_rans_encode<uint16_t, false><<<blocks_for(n, 32), 32, smem16, s16>>>(
-                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
-        } else {
-            k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, s16>>>(
-                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
-        }
+        // warps whose streams all have prob_bits >= 14 take the short division chain; the others (only when the caller
+        // cannot rule them out) the LOW_BITS instantiation: every warp runs in exactly one of the two
         static const char* const names16[4] = {"k_rans_encode<u16>[rows<=64]", "k_rans_encode<u16>[rows<=128]",
                                                "k_rans_encode<u16>[rows<=256]", "k_rans_encode<u16>[rows<=513]"};
+        static const char* const names16l[4] = {"k_rans_encode<u16,low>[rows<=64]", "k_rans_encode<u16,low>[rows<=128]",
+                                                "k_rans_encode<u16,low>[rows<=256]", "k_rans_encode<u16,low>[rows<=513]"};
         static const char* const names32[4] = {"k_rans_encode<u32>[rows<=64]", "k_rans_encode<u32>[rows<=128]",
                                                "k_rans_encode<u32>[rows<=256]", "k_rans_encode<u32>[rows<=513]"};
+        k_rans_encode<uint16_t, false><<<blocks_for(n, 32), 32, smem16, s16>>>(
+            d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
         LAUNCHED(names16[c]);
+        if (min_prob_bits < 14) {
+            k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, s16>>>(
+                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+            LAUNCHED(names16l[c]);
+        }
         if (max_prob_bits > 15) {  // 32-bit table lanes; prob_bits >= 16 there, so never LOW_BITS
             k_rans_encode<uint32_t, false><<<blocks_for(n, 32), 32, smem32, s32>>>(
                 d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);

@@ -569,18 +569,27 @@ template <bool LOW_BITS>
 __device__ __forceinline__ uint64_t rans_put(uint64_t x, uint32_t start, uint32_t freq, double inv, uint32_t bits,
                                              uint32_t* __restrict__ words, uint32_t& widx) {
     // x >= ((L >> bits) << 32) * freq  <=>  (x >> (63 - bits)) >= freq, and 63 - bits >= 32
-    const bool emit = ((uint32_t)(x >> 32) >> (31u - bits)) >= freq;
+    const uint32_t xh = (uint32_t)(x >> 32);
+    const bool emit = (xh >> (31u - bits)) >= freq;
     if (emit) words[--widx] = (uint32_t)x;
-    x = emit ? (x >> 32) : x;
+    // The state as a double (truncated), for BOTH outcomes of the renormalisation test, converted while the test is
+    // still being evaluated: the select then picks a finished double, and shift / compare / two moves leave the chain
+    // (I2F.F64.U64 is 19 cycles; it used to start only after the test and the select).  Same values as converting
+    // the selected state, so the exactness argument below is untouched.
+    double d_full, d_hi;  // (opaque to the compiler, which otherwise branches around the 64-bit conversion)
+    asm("cvt.rz.f64.u64 %0, %1;" : "=d"(d_full) : "l"(x));
+    asm("cvt.rn.f64.u32 %0, %1;" : "=d"(d_hi) : "r"(xh));
+    const double xd = emit ? d_hi : d_full;
+    x = emit ? (uint64_t)xh : x;
     uint64_t q;  // q <= floor(x / freq), short by <= 1 (bits >= 14)
     if (LOW_BITS) {
-        q = __double2ull_rz(__ull2double_rz(x) * inv);
+        q = __double2ull_rz(xd * inv);
     } else {
         // x / freq < 2^(63 - bits) <= 2^49: the product is added to 2^52 in the SAME fused operation, rounding
         // towards zero, so the mantissa of the sum IS floor(x_d * inv) — one DFMA instead of DMUL + F2I.U64.F64
         // (8 instead of 34 cycles on the chain).  Same bound as before (the product is not even rounded before
         // the floor); modelled on the CPU in tests/hostfmt (fmt_div_model) over the boundaries of every quotient.
-        q = (uint64_t)__double_as_longlong(__fma_rz(__ull2double_rz(x), inv, 4503599627370496.0)) & 0x000fffffffffffffull;
+        q = (uint64_t)__double_as_longlong(__fma_rz(xd, inv, 4503599627370496.0)) & 0x000fffffffffffffull;
     }
     uint32_t r = (uint32_t)x - (uint32_t)q * freq;           // true remainder < 2^32: exact mod 2^32
     if (r >= freq) {
@@ -750,6 +759,13 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) need = max(need, __shfl_xor_sync(0xffffffffu, need, d));
     if (need <= rows_lo || need > rows) return;  // another class's launch (or nothing to do)
+    // ... and of the two instantiations the one that fits the warp: the short division chain (LOW_BITS = false) is
+    // exact for prob_bits >= 14 only, so a warp with a narrower stream belongs to the LOW_BITS launch (the host issues
+    // that launch only when such streams may exist)
+    uint32_t low = live ? st.prob_bits : 32u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) low = min(low, __shfl_xor_sync(0xffffffffu, low, d));
+    if ((low < 14u) != LOW_BITS) return;
     if (live && (uint64_t)st.out_cap < rans_words_bound(st.n, st.prob_bits) * 4u + HOH_HEAD_CAP + 32u) {
         m.status = HOH_S_OVERFLOW;  // slab too small for the worst case: refuse rather than test per symbol
         meta[s] = m;
@@ -826,27 +842,54 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
             stage_wait();
         }
     };
-    auto prepare = [&](int g, uint32_t(&g_start)[kGroup], uint32_t(&g_freq)[kGroup], double(&g_inv)[kGroup]) {
+    const uint32_t zero = rows_lo & 0x80000000u;  // 0 at run time, unknown to the compiler: ties the two instruction streams together
+    auto group_words = [&](int g) -> uint4 {  // the 8 symbols of group g from the staging buffer (one LDS.128)
         const int chunk = g / kGroupsPerChunk, k0 = (g % kGroupsPerChunk) * kGroup;
-        const uint4 v = *reinterpret_cast<const uint4*>(stage0 + (chunk & 1) * 32 * kBulkStride + lane * kBulkStride + k0);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        const uint32_t base = (uint32_t)g * kGroup;
+        return *reinterpret_cast<const uint4*>(stage0 + (chunk & 1) * 32 * kBulkStride + lane * kBulkStride + k0);
+    };
+    // start / freq / reciprocal of symbol j of group g (independent of the coder's state)
+    auto prepare_one = [&](int g, int j, const uint4& v, uint32_t& o_start, uint32_t& o_freq, double& o_inv) {
+        const uint32_t w = j < 2 ? v.x : (j < 4 ? v.y : (j < 6 ? v.z : v.w));
+        const bool on = (uint32_t)g * kGroup + (uint32_t)j < my_n;
+        const uint32_t raw = (j & 1) ? (w >> 16) : (w & 0xffffu);
+        // window-relative index; out-of-alphabet input must not index past the lane's table
+        const uint32_t sym = on ? min(raw - win_lo, sym_max) : 0u;
+        const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+        o_start = on ? c0 : 0u;  // padding step: freq = 2^bits, start = 0 leaves x untouched
+        o_freq = on ? c1 - c0 : full;
+        o_inv = recip_low(o_freq);
+    };
+    auto prepare = [&](int g, uint32_t(&g_start)[kGroup], uint32_t(&g_freq)[kGroup], double(&g_inv)[kGroup]) {
+        const uint4 v = group_words(g);
 #pragma unroll
-        for (int j = 0; j < kGroup; j++) {
-            const bool on = base + (uint32_t)j < my_n;
-            const uint32_t raw = (j & 1) ? (w[j / 2] >> 16) : (w[j / 2] & 0xffffu);
-            // window-relative index; out-of-alphabet input must not index past the lane's table
-            const uint32_t sym = on ? min(raw - win_lo, sym_max) : 0u;
-            const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
-            g_start[j] = on ? c0 : 0u;  // padding step: freq = 2^bits, start = 0 leaves x untouched
-            g_freq[j] = on ? c1 - c0 : full;
-            g_inv[j] = recip_low(g_freq[j]);
-        }
+        for (int j = 0; j < kGroup; j++) prepare_one(g, j, v, g_start[j], g_freq[j], g_inv[j]);
     };
     auto run = [&](const uint32_t(&g_start)[kGroup], const uint32_t(&g_freq)[kGroup], const double(&g_inv)[kGroup]) {
 #pragma unroll
         for (int j = kGroup - 1; j >= 0; j--)
             x = rans_put<LOW_BITS>(x, g_start[j], g_freq[j], g_inv[j], bits, words, widx);
+    };
+    // The serial steps of one group with the preparation of the NEXT group woven in symbol by symbol: a step is a
+    // chain of ~20 dependent instructions (~80 cycles) that leaves the issue slots between them empty, and one symbol's
+    // preparation is ~35 independent ones.  Written as two separate loops the compiler kept them apart (five of the
+    // eight steps ran bare) and a warp paid for both, one after the other.
+    auto run_prepare = [&](const uint32_t(&r_start)[kGroup], const uint32_t(&r_freq)[kGroup], const double(&r_inv)[kGroup],
+                           int g_next, uint32_t(&p_start)[kGroup], uint32_t(&p_freq)[kGroup], double(&p_inv)[kGroup]) {
+        const uint4 v = group_words(g_next);
+        // ptxas undoes the weaving (it sinks all eight preparations below the eight steps) unless the two streams are
+        // tied together: the preparation of symbol j takes a (run-time zero) bit of the state before step j, and step
+        // j - 2 takes one of its reciprocal, so it can neither be hoisted above its step nor sunk past the second next.
+        uint32_t tie1 = 0, tie2 = 0;
+#pragma unroll
+        for (int j = kGroup - 1; j >= 0; j--) {
+            const uint32_t before = (uint32_t)x & zero;
+            x = rans_put<LOW_BITS>(x, r_start[j], r_freq[j] | tie2, r_inv[j], bits, words, widx);
+            uint4 vv = v;
+            vv.x |= before; vv.y |= before; vv.z |= before; vv.w |= before;
+            prepare_one(g_next, j, vv, p_start[j], p_freq[j], p_inv[j]);
+            tie2 = tie1;
+            tie1 = (uint32_t)__double_as_longlong(p_inv[j]) & zero;
+        }
     };
     if (n_chunks > 0) {
         uint32_t a_start[kGroup], a_freq[kGroup], b_start[kGroup], b_freq[kGroup];
@@ -857,17 +900,17 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
         const int n_groups = n_chunks * kGroupsPerChunk;  // even
         prepare(n_groups - 1, a_start, a_freq, a_inv);
         for (int g = n_groups - 1; g >= 1; g -= 2) {
-            prepare(g - 1, b_start, b_freq, b_inv);  // g odd: g-1 is in the same chunk
-            run(a_start, a_freq, a_inv);
+            run_prepare(a_start, a_freq, a_inv, g - 1, b_start, b_freq, b_inv);  // g odd: g-1 is in the same chunk
             if (g - 1 >= 1) {
                 if (((g - 1) % kGroupsPerChunk) == 0) {  // group g-2 is the last of the previous chunk
                     const int chunk = (g - 1) / kGroupsPerChunk;
                     wait_chunk(chunk - 1);  // chunk-1 has landed; this chunk's buffer is free (its last group is in b_*)
                     if (chunk >= 2) load_chunk(chunk - 2);
                 }
-                prepare(g - 2, a_start, a_freq, a_inv);
+                run_prepare(b_start, b_freq, b_inv, g - 2, a_start, a_freq, a_inv);
+            } else {
+                run(b_start, b_freq, b_inv);
             }
-            run(b_start, b_freq, b_inv);
         }
     }
     if (live) {
@@ -1218,6 +1261,17 @@ constexpr int kAhead = 20;      // words requested ahead of the read position (>
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
+// the same under a predicate of the instruction itself (no branch around it; the address is not touched when off)
+__device__ __forceinline__ void cp_async16_if(uint32_t smem_addr, const void* gptr, bool on) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %2, 0;\n"
+        "@p cp.async.cg.shared.global [%0], [%1], 16;\n"
+        "}\n" ::"r"(smem_addr),
+        "l"(gptr), "r"((uint32_t)on)
+        : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() {
@@ -1261,9 +1315,18 @@ struct WordRing {
         wa = ring[(pos + 1u) & (kRingWords - 1)];
         wb = ring[(pos + 2u) & (kRingWords - 1)];
     }
-    // uniform point, every kTopUp symbols: request ahead, and make everything but that request resident
+    // uniform point, every kTopUp symbols: request ahead, and make everything but that request resident.
+    // Straight-line: the previous top-up left end >= pos_then + kAhead and at most kTopUp words were consumed since, so
+    // at most two 4-word blocks are missing; each is one PREDICATED cp.async (the request() loop compiled to a chain of
+    // ~8 branches, ~330 cycles per top-up in the ncu source view of the fused decoder — a tenth of the kernel).
     __device__ __forceinline__ void top_up() {
-        request(pos + kAhead);
+        const uint32_t want = pos + kAhead;
+#pragma unroll
+        for (int k = 0; k < (kTopUp + 3) / 4; k++) {
+            const bool need = end < want;
+            cp_async16_if(ring_addr + (end & (kRingWords - 1)) * 4u, base16 + end, need && end < limit);
+            end += need ? 4u : 0u;
+        }
         cp_async_commit();
         cp_async_wait_group<1>();
     }
@@ -1305,6 +1368,28 @@ struct SharedDense {
     const uint32_t* tab;
     __device__ __forceinline__ uint32_t at(uint32_t p) const { return tab[p]; }
     __device__ __forceinline__ uint32_t at_eager(uint32_t p) const { return tab[p]; }
+};
+
+// The same table addressed by a 32-bit shared-window address computed ONCE (base = address of tab[lane]): the loads
+// are LDS [R + imm] with no uniform-register window base.  With generic pointers into the dynamic shared array the
+// compiler rebuilds that base (S2UR SR_CgaCtaId / UMOV / ULEA) in every decode step of the fused kernel, because the
+// out-of-line far walk clobbers the uniform registers, and the step waits ~10 cycles for it.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+struct PerLaneDenseS {
+    uint32_t base;  // shared address of row 0 of this lane's table
+    __device__ __forceinline__ uint32_t at(uint32_t p) const { return lds_u32(base + p * 128u); }
+    __device__ __forceinline__ uint32_t at_eager(uint32_t p) const { return lds_u32(base + p * 128u); }
+    // rows p-1 .. p+2 from one address register (four independent loads: one round trip on the chain)
+    __device__ __forceinline__ void at4(uint32_t p, uint32_t& em, uint32_t& e0, uint32_t& e1, uint32_t& e2) const {
+        const uint32_t a = base + p * 128u;
+        asm("ld.shared.u32 %0, [%4+-128];\n\tld.shared.u32 %1, [%4];\n\tld.shared.u32 %2, [%4+128];\n\tld.shared.u32 %3, [%4+256];"
+            : "=r"(em), "=r"(e0), "=r"(e1), "=r"(e2)
+            : "r"(a));
+    }
 };
 
 template <typename Table, typename LutT>
@@ -1391,6 +1476,42 @@ __device__ __forceinline__ uint32_t rans_get(uint64_t& x, WordRing& rd, const Ta
     x = next;
     // rans64.hpp:137-141: x < 2^31, written on the two halves so that ONE predicate serves the state update and
     // the word ring (the 64-bit comparison was being evaluated twice, as >= and as >)
+    const bool refill = ((uint32_t)(x >> 32) | ((uint32_t)x >> 31)) == 0u;
+    x = refill ? ((x << 32) | rd.next) : x;
+    rd.take_if(refill);
+    return e & kSymMask;
+}
+
+// rans_get for kernels that address their tables by shared-window addresses (PerLaneDenseS; lut_s = address of this
+// lane's entry 0 of the midpoint table, entries 32 * sizeof(LutT) bytes apart): same lookup, same step.
+template <typename LutT>
+__device__ __forceinline__ uint32_t rans_get_s(uint64_t& x, WordRing& rd, const PerLaneDenseS& T, uint32_t lut_s,
+                                               uint32_t lut_shift, uint32_t bits, uint32_t mask) {
+    const uint32_t slot = (uint32_t)x & mask;  // rans64.hpp:118-121
+    const uint32_t key = (slot + 1u) << kSymBits;
+    uint32_t p;
+    if (sizeof(LutT) == 1) {
+        asm("ld.shared.u8 %0, [%1];" : "=r"(p) : "r"(lut_s + (slot >> lut_shift) * 32u));
+    } else {
+        asm("ld.shared.u16 %0, [%1];" : "=r"(p) : "r"(lut_s + (slot >> lut_shift) * 64u));
+    }
+    uint32_t em, e0, e1, e2;
+    T.at4(p, em, e0, e1, e2);
+    const bool down = e0 >= key;  // see rans_lookup_near
+    const bool up = e1 < key;
+    uint32_t e = down ? em : (up ? e1 : e0);
+    uint32_t up_ones;
+    asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(up_ones) : "r"(e1), "r"(key));
+    uint32_t hi = down ? e0 : e1 + ((e2 - e1) & up_ones);
+    const bool near = e < key && hi >= key;
+    const uint64_t top = x >> bits;
+    uint64_t next = (uint64_t)((hi >> kSymBits) - (e >> kSymBits)) * top + (slot - (e >> kSymBits));  // rans64.hpp:126-134
+    if (__builtin_expect(__any_sync(0xffffffffu, !near), 0)) {
+        const ulonglong2 fixed = rans_far_step(T, key, p, e, hi, top, slot);
+        next = fixed.x;
+        e = (uint32_t)fixed.y;
+    }
+    x = next;
     const bool refill = ((uint32_t)(x >> 32) | ((uint32_t)x >> 31)) == 0u;
     x = refill ? ((x << 32) | rd.next) : x;
     rd.take_if(refill);
@@ -1485,6 +1606,8 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
         x = live ? ((uint64_t)lo | ((uint64_t)hi << 32)) : kRansL;
     }
     uint16_t* my_row = stage + lane * kDecStride;
+    const PerLaneDenseS TS{(uint32_t)__cvta_generic_to_shared(tab + lane)};  // the loop's view of the table: see PerLaneDenseS
+    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(lut + lane);
     const uint32_t chunks = (n_max + kDecChunk - 1) / kDecChunk;
     // The encoder starts from 2^31 (rans64.hpp:65) and decoding undoes its steps one by one, so after the last
     // symbol of a sound stream the state is 2^31 again: the only integrity check the format offers (it carries no
@@ -1498,7 +1621,7 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
                 rd.top_up();
 #pragma unroll
                 for (uint32_t k = k0; k < k0 + kTopUp; k++) {
-                    my_row[k] = (uint16_t)rans_get(x, rd, T, lut + lane, 32u, lut_shift, bits, mask);
+                    my_row[k] = (uint16_t)rans_get_s<LutT>(x, rd, TS, lut_s, lut_shift, bits, mask);
                     x_end = left == k + 1u ? x : x_end;
                 }
             }
@@ -1507,7 +1630,7 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
                 rd.top_up();
 #pragma unroll
                 for (uint32_t k = k0; k < k0 + kTopUp; k++)
-                    my_row[k] = (uint16_t)rans_get(x, rd, T, lut + lane, 32u, lut_shift, bits, mask);
+                    my_row[k] = (uint16_t)rans_get_s<LutT>(x, rd, TS, lut_s, lut_shift, bits, mask);
             }
         }
         __syncwarp();
@@ -1554,28 +1677,48 @@ __global__ void __launch_bounds__(kStaticWarps * 32) k_rans_encode_static(
     for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
     const uint16_t* my_row = stage + lane * kSymStride;
     const uint32_t full = 1u << bits;
+    const uint32_t zero = slab_bytes & 1u;  // slabs are whole words: 0 at run time, unknown to the compiler
     for (int chunk = (int)((n_max + kChunk - 1) / kChunk) - 1; chunk >= 0; chunk--) {
         __syncwarp();
         stage_load_chunk(stage, symbols, s_off[w], s_n[w], (uint32_t)chunk);
         stage_wait();
         const uint32_t base = (uint32_t)chunk * kChunk;
-        for (int k0 = kChunk - kGroup; k0 >= 0; k0 -= kGroup) {
-            uint32_t g_start[kGroup], g_freq[kGroup];
-            double g_inv[kGroup];
+        // groups of the chunk from the last to the first; the preparation of the next group (table rows, reciprocals:
+        // independent of the state) is woven into the serial steps of the current one, as in k_rans_encode
+        auto prepare_one = [&](int k, uint32_t dep, uint32_t& o_start, uint32_t& o_freq, double& o_inv) {
+            const bool on = base + (uint32_t)k < run_n;
+            const uint32_t sym = on ? min((uint32_t)my_row[k] | dep, range - 1u) : 0u;
+            const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+            o_start = on ? c0 : 0u;
+            o_freq = on ? c1 - c0 : full;
+            o_inv = recip_low(o_freq);
+        };
+        auto run_prepare = [&](const uint32_t(&r_start)[kGroup], const uint32_t(&r_freq)[kGroup], const double(&r_inv)[kGroup],
+                               int k0_next, uint32_t(&p_start)[kGroup], uint32_t(&p_freq)[kGroup], double(&p_inv)[kGroup]) {
+            uint32_t tie1 = 0, tie2 = 0;  // false dependencies (0 at run time) that keep the two instruction streams woven
 #pragma unroll
-            for (int j = 0; j < kGroup; j++) {
-                const int k = k0 + j;
-                const bool on = base + (uint32_t)k < run_n;
-                const uint32_t sym = on ? min((uint32_t)my_row[k], range - 1u) : 0u;
-                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
-                g_start[j] = on ? c0 : 0u;
-                g_freq[j] = on ? c1 - c0 : full;
-                g_inv[j] = recip_low(g_freq[j]);
+            for (int j = kGroup - 1; j >= 0; j--) {
+                const uint32_t before = (uint32_t)x & zero;
+                x = rans_put<true>(x, r_start[j], r_freq[j] | tie2, r_inv[j], bits, words, widx);
+                prepare_one(k0_next + j, before, p_start[j], p_freq[j], p_inv[j]);
+                tie2 = tie1;
+                tie1 = (uint32_t)__double_as_longlong(p_inv[j]) & zero;
             }
+        };
+        uint32_t a_start[kGroup], a_freq[kGroup], b_start[kGroup], b_freq[kGroup];
+        double a_inv[kGroup], b_inv[kGroup];
 #pragma unroll
-            for (int j = kGroup - 1; j >= 0; j--)
-                x = rans_put<true>(x, g_start[j], g_freq[j], g_inv[j], bits, words, widx);
+        for (int j = 0; j < kGroup; j++) prepare_one(kChunk - kGroup + j, 0u, a_start[j], a_freq[j], a_inv[j]);
+        static_assert((kChunk / kGroup) % 2 == 0 && kChunk >= 2 * kGroup, "groups of a chunk are coded in pairs");
+#pragma unroll 1
+        for (int k0 = kChunk - kGroup; k0 >= 3 * kGroup; k0 -= 2 * kGroup) {
+            run_prepare(a_start, a_freq, a_inv, k0 - kGroup, b_start, b_freq, b_inv);
+            run_prepare(b_start, b_freq, b_inv, k0 - 2 * kGroup, a_start, a_freq, a_inv);
         }
+        run_prepare(a_start, a_freq, a_inv, 0, b_start, b_freq, b_inv);  // a = group at kGroup, b = the chunk's first
+#pragma unroll
+        for (int j = kGroup - 1; j >= 0; j--)
+            x = rans_put<true>(x, b_start[j], b_freq[j], b_inv[j], bits, words, widx);
     }
     if (live) {
         if (fits) {
@@ -4670,9 +4813,12 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
 #endif
 
     const PerLaneDense T{tab, lane};
+    const PerLaneDenseS TS{(uint32_t)__cvta_generic_to_shared(tab + lane)};              // the hot loop's view of it
+    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(lut + lane);
     const uint32_t bits = coded ? m.prob_bits : 1u;
     const uint32_t mask = (1u << bits) - 1u;
     const uint32_t lut_shift = bits > 7u ? bits - 7u : 0u;
+    for (uint32_t i = lane; i < (uint32_t)kFusedStage / 4u; i += 32) reinterpret_cast<uint32_t*>(stage)[i] = 0u;
     if (coded) {
         lut_build(T, lut + lane, 32u, lut_shift, m.used);
     } else {  // stored / idle / damaged lane: a one-symbol table that owns the whole range, so that its state never moves
@@ -4726,8 +4872,15 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
     const uint32_t half = ch == 0u ? 128u : 256u, cmask = ch == 0u ? 255u : 511u;
     const uint32_t own_shift = ch == 0u ? 8u : (ch == 1u ? 0u : 16u);
     const uint32_t g_keep = ch == 0u ? 0u : 0xffffffffu, hi_keep = ch == 0u ? 0u : 0x01010101u;  // planes 1, 2 are differences to G
-    uint8_t* my_stage = stage + tl * 24u + (own_shift >> 3);
+    const uint32_t my_stage_s = (uint32_t)__cvta_generic_to_shared(stage + tl * 24u + (own_shift >> 3));
     const uint2* my_out_src = reinterpret_cast<const uint2*>(stage + tl * 24u + 8u * ch);
+    // Image addresses advance incrementally, one 64-bit add per group: p_cur = first byte of the current group of 8
+    // pixels, p_px = where this lane stores its 8 bytes of the group the pixel in flight belongs to.  (Recomputed from
+    // (x, y) per group they cost two chains of 64-bit multiply-adds and constant-bank loads, and the `if` around the
+    // store a divergent region with its reconvergence barrier: ~200 cycles per group in the ncu source view.)
+    const uint64_t row_skip = row_bytes - (uint64_t)(tw - 8u) * 3u;  // last group of a row -> first group of the next
+    uint8_t* p_cur = tile0;
+    uint8_t* p_px = tile0 + 8u * ch;
 
     // The two chains are software-pipelined by one pixel: step (grp, i) decodes symbol 8 grp + i and, in the shadow of
     // its two shared-memory round trips, un-predicts the pixel whose residual the PREVIOUS step delivered.  (The
@@ -4738,7 +4891,6 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
     uint2 ta = make_uint2(0x80808080u, 0x80808080u), tb = ta, tc = ta;  // the 24 bytes above the current group (row 0: c/2)
     const uint32_t groups = npx / 8u;                 // tw % 8 == 0
     uint32_t gx = 0, gy = 0;                          // position of the current group in the tile (warp-uniform)
-    uint32_t px_x = 0, px_gy = 0;                     // the same for the group the pixel in flight belongs to
     // un-predict the pixel in flight (column `col` of its row), hand its byte to the stage slot `slot`
     auto finish_pixel = [&](uint32_t slot, bool row_start) {
         if (row_start) {  // prediction.hpp:25-26
@@ -4753,7 +4905,8 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
         TLv = t_prev;
         L = v;
         const uint32_t gv = __shfl_sync(0xffffffffu, v, base_lane);
-        my_stage[3u * slot] = (uint8_t)(v + (gv & g_keep));  // inverse of channel.hpp:75-77 (mod 256: the +256 drops out)
+        // inverse of channel.hpp:75-77 (mod 256: the +256 drops out)
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(my_stage_s + 3u * slot), "r"(v + (gv & g_keep)) : "memory");
     };
     // T of the 8 pixels of a group from the 24 RGB bytes above them, byte-wise: own byte minus G (mod 256) in t_lo, and for
     // the difference planes the ninth bit (R - G + 256 has bit 8 set iff R >= G) in t_hi; row 0 is fed bytes 0x80, which
@@ -4780,7 +4933,7 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
         return (i & 1u) ? (pair >> 16) : (pair & 0xffffu);
     };
     auto next_symbol = [&](auto has_stored) -> uint32_t {
-        uint32_t r = rans_get(x, rd, T, lut + lane, 32u, lut_shift, bits, mask);
+        uint32_t r = rans_get_s<LutT>(x, rd, TS, lut_s, lut_shift, bits, mask);
         if (decltype(has_stored)::value) {
             const bool refill = stored && have < sbits;
             if (refill) {
@@ -4796,9 +4949,17 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
         }
         return r;
     };
-    auto flush_group = [&](uint32_t fx, uint32_t fy) {  // the 24 staged bytes of every tile -> the image
+    auto flush_group = [&]() {  // the 24 staged bytes of every tile -> the image (a predicated store, no branch)
         __syncwarp();
-        if (tile_ok) *reinterpret_cast<uint2*>(tile0 + (uint64_t)fy * row_bytes + (uint64_t)fx * 3u + 8u * ch) = *my_out_src;
+        const uint2 v = *my_out_src;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.u32 p, %3, 0;\n"
+            "@p st.global.v2.u32 [%0], {%1, %2};\n"
+            "}\n" ::"l"(p_px),
+            "r"(v.x), "r"(v.y), "r"((uint32_t)tile_ok)
+            : "memory");
         __syncwarp();  // the stage may be rewritten, and the stores are ordered before the loads of later groups
     };
     // the loop exists twice: warps without a stored-mode stream (nearly all) run a copy without the bit reader
@@ -4806,23 +4967,27 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
     for (uint32_t grp = 0; grp < groups; grp++) {
         rd.top_up();
         uint32_t nx = gx + 8u, ny = gy;
-        if (nx == tw) {
+        const bool wrap = nx == tw;
+        if (wrap) {
             nx = 0u;
             ny++;
         }
+        uint8_t* p_next = p_cur + (wrap ? row_skip : 24ull);
         t_prepare(ta, tb, tc);
-        // step 0: symbol 0 of this group; pixel 7 of the previous one, which completes that group
+        // step 0: symbol 0 of this group; pixel 7 of the previous one, which completes that group.  (In group 0 there
+        // is no such pixel: the step un-predicts a zero residual into slot 7 and the flush stores the zeroed stage to
+        // the tile's first 24 bytes, which group 0's own flush overwrites one group later - cheaper than a branch here.)
         {
-            if (grp > 0u) finish_pixel(7u, false);
+            finish_pixel(7u, false);
             const uint32_t r = next_symbol(has_stored);
             r_prev = r;
             t_prev = t_of(0u);
-            if (grp > 0u) flush_group(px_x, px_gy);
+            flush_group();
         }
         // the bytes above the NEXT group: stored at least one whole group ago (tile_w >= 16), and after the flush above
         uint2 na = make_uint2(0x80808080u, 0x80808080u), nb = na, nc = na;
         if (ny > 0u && ny < th && tile_ok) {
-            const uint2* src = reinterpret_cast<const uint2*>(tile0 + (uint64_t)(ny - 1u) * row_bytes + (uint64_t)nx * 3u);
+            const uint2* src = reinterpret_cast<const uint2*>(p_next - row_bytes);
             na = __ldcg(src);
             nb = __ldcg(src + 1);
             nc = __ldcg(src + 2);
@@ -4834,8 +4999,8 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
             r_prev = r;
             t_prev = t_of(i);
         }
-        px_x = gx;
-        px_gy = gy;
+        p_px = p_cur + 8u * ch;
+        p_cur = p_next;
         ta = na;
         tb = nb;
         tc = nc;
@@ -4849,7 +5014,7 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
         run(StoredNo{});
     }
     finish_pixel(7u, false);
-    flush_group(px_x, px_gy);
+    flush_group();
     // rans64.hpp:65: decoding undoes the encoder's steps, so a sound stream ends in the encoder's initial state
     if (coded && x != kRansL) my_status = HOH_S_BAD_STATE;
     if (exists) status[s] = my_status;
