@@ -194,6 +194,9 @@ int ensure_smem_opt_in(hoh_ctx* ctx) {
     CK(cudaFuncSetAttribute(k_rans_encode<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_encode<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_encode<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_decode<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_decode<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_decode_tiles_s0<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -234,9 +237,11 @@ int aux_join(hoh_ctx* ctx, int count) {
 
 // Shared tail of the encode pipeline once the raw histograms are in `freqs`.
 // min_prob_bits: a lower bound the CALLER guarantees for every stream's prob_bits (0 = unknown).
+// padded8: the CALLER guarantees that every stream's symbols start 16-byte aligned and are readable up to the next
+// multiple of 8 symbols (planes at a stride rounded up to 8): the warp-specialised encoder then reads them directly.
 int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, const uint16_t* d_symbols,
                       uint8_t* d_out, hoh_stream_result* d_results, const uint32_t* freqs,
-                      uint32_t max_range, uint32_t max_prob_bits, uint32_t min_prob_bits) {
+                      uint32_t max_range, uint32_t max_prob_bits, uint32_t min_prob_bits, bool padded8 = false) {
     uint32_t* cum;
     uint8_t* heads;
     EncMeta* meta;
@@ -267,17 +272,34 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
                                                 "k_rans_encode<u16,low>[rows<=256]", "k_rans_encode<u16,low>[rows<=513]"};
         static const char* const names32[4] = {"k_rans_encode<u32>[rows<=64]", "k_rans_encode<u32>[rows<=128]",
                                                "k_rans_encode<u32>[rows<=256]", "k_rans_encode<u32>[rows<=513]"};
-        k_rans_encode<uint16_t, false><<<blocks_for(n, 32), 32, smem16, s16>>>(
-            d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+        const size_t hand = 2 * kWsGroup * 32 * sizeof(uint4);
+        const size_t ws16 = (size_t)rows * 32 * sizeof(uint16_t) + hand, ws32 = (size_t)rows * 32 * sizeof(uint32_t) + hand;
+        if (padded8) {
+            k_rans_encode_ws<uint16_t, false><<<blocks_for(n, 32), 64, ws16, s16>>>(
+                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+        } else {
+            k_rans_encode<uint16_t, false><<<blocks_for(n, 32), 32, smem16, s16>>>(
+                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+        }
         LAUNCHED(names16[c]);
         if (min_prob_bits < 14) {
-            k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, s16>>>(
-                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+            if (padded8) {
+                k_rans_encode_ws<uint16_t, true><<<blocks_for(n, 32), 64, ws16, s16>>>(
+                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+            } else {
+                k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, s16>>>(
+                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+            }
             LAUNCHED(names16l[c]);
         }
         if (max_prob_bits > 15) {  // 32-bit table lanes; prob_bits >= 16 there, so never LOW_BITS
-            k_rans_encode<uint32_t, false><<<blocks_for(n, 32), 32, smem32, s32>>>(
-                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);
+            if (padded8) {
+                k_rans_encode_ws<uint32_t, false><<<blocks_for(n, 32), 64, ws32, s32>>>(
+                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);
+            } else {
+                k_rans_encode<uint32_t, false><<<blocks_for(n, 32), 32, smem32, s32>>>(
+                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);
+            }
             LAUNCHED(names32[c]);
         }
     }
@@ -811,7 +833,7 @@ int hoh_encode_images_s0(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, ui
         k_histogram<<<(unsigned)n_streams, 256, 0, ctx->stream>>>(streams, resid, freqs);
         LAUNCHED("k_histogram");
     }
-    TRY(encode_from_freqs(ctx, streams, n_streams, resid, d_out, d_results, freqs, 512, 15, 15));
+    TRY(encode_from_freqs(ctx, streams, n_streams, resid, d_out, d_results, freqs, 512, 15, 15, true));
     if (d_packed) {
         if (!d_packed_off) return HOH_E_ARG;
         k_scan_sizes<<<1, 1024, 0, ctx->stream>>>(d_results, (uint32_t)n_streams, d_packed_off);
@@ -1401,7 +1423,7 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
             const uint32_t b = round == 0 ? (mode >= 1 ? 8u : 0u) : (round == 2 ? 2u : 3u);
             k_layer_histograms<<<(unsigned)(2 * n), 256, 0, ctx->stream>>>(n, per_plane, a, b_first, b, streams, syms, freqs);
             LAUNCHED("k_layer_histograms");
-            TRY(encode_from_freqs(ctx, streams, count, syms, d_out, rr, freqs, max_range, max_pb, 0));
+            TRY(encode_from_freqs(ctx, streams, count, syms, d_out, rr, freqs, max_range, max_pb, 0, true));
         } else {
             TRY(hoh_encode_entropy_batch(ctx, streams, count, syms, d_out, rr, max_range, max_pb, lg.per));
         }

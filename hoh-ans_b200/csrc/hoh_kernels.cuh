@@ -925,6 +925,173 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
 }
 
 // -------------------------------------------------------------------------------------------------
+// The same encoder, warp-specialised: two warps per CTA share 32 streams (lane = stream in both).
+// -------------------------------------------------------------------------------------------------
+// A stream's step is a chain of ~20 dependent instructions (~80 cycles) and the preparation of a symbol (two table
+// rows, an fp64 reciprocal) is ~35 instructions of which a group of eight overlap each other.  In ONE warp the two
+// run one after the other whatever the source says — a warp issues in order and ptxas does not weave a second
+// dependent chain into the stalls of the first (ncu source view of k_rans_encode with the weaving forced by false
+// dependencies: the reciprocal's DFMA chain simply sits between two steps, 237 cycles per symbol all the same).
+// In TWO warps the hardware scheduler does the weaving: the FEEDER warp reads the symbols (16 bytes = 8 symbols per lane
+// straight from global memory, two groups ahead: no staging buffer, no copy loop), looks up start / freq, computes the
+// reciprocal and hands (start, freq, 1/freq) over through shared memory, 8 symbols per lane at a time, double
+// buffered; the CODER warp runs nothing but the serial steps and the renormalisation stores.  Hand-over by named
+// barriers (bar.sync / bar.arrive, 64 threads): buffer b is "empty" on barrier b and "full" on barrier 2 + b (four
+// barriers per CTA: an SM has 64, and they must not be what limits the CTAs it holds).
+// Requires every stream's symbols 16-byte aligned and readable up to the next multiple of 8 symbols (the tile codec's
+// and layer_encode's planes are); other callers keep k_rans_encode.
+constexpr int kWsGroup = 8;
+template <int ID>
+__device__ __forceinline__ void bar_sync_named() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_arrive_named() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
+
+template <typename CumT, bool LOW_BITS>
+__global__ void __launch_bounds__(64) k_rans_encode_ws(const hoh_enc_stream* __restrict__ streams, uint32_t n_streams,
+                                                       const uint16_t* __restrict__ symbols,
+                                                       const uint32_t* __restrict__ cumtab, uint8_t* __restrict__ out,
+                                                       EncMeta* __restrict__ meta, uint32_t rows_lo, uint32_t rows,
+                                                       uint32_t want_u16) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    CumT* tab = reinterpret_cast<CumT*>(smem_raw);
+    uint4* hand = reinterpret_cast<uint4*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));  // [2][kWsGroup][32]
+
+    const uint32_t lane = lane_id();
+    const bool feeder = threadIdx.x >= 32u;
+    const uint32_t s = blockIdx.x * 32u + lane;
+    const bool exists = s < n_streams;
+    hoh_enc_stream st;
+    EncMeta m;
+    if (exists) {
+        st = streams[s];
+        m = meta[s];
+    } else {
+        st.n = 0;
+        st.range = 1;
+        st.prob_bits = 1;
+        st.sym_off = 0;
+        st.out_off = 0;
+        st.out_cap = 0;
+        m.status = HOH_S_OK;
+        m.table_u16 = want_u16;
+        m.win_lo = 0;
+        m.win_rows = 0;
+    }
+    // (both warps evaluate the same streams, so every decision below is the same in both)
+    bool live = exists && st.n > 0 && m.status == HOH_S_OK && m.table_u16 == want_u16;
+    uint32_t need = live ? m.win_rows : 0u;
+    uint32_t low = live ? st.prob_bits : 32u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        need = max(need, __shfl_xor_sync(0xffffffffu, need, d));
+        low = min(low, __shfl_xor_sync(0xffffffffu, low, d));
+    }
+    if (need <= rows_lo || need > rows) return;  // another class's launch (or nothing to do)
+    if ((low < 14u) != LOW_BITS) return;         // the other instantiation's warps
+    if (live && (uint64_t)st.out_cap < rans_words_bound(st.n, st.prob_bits) * 4u + HOH_HEAD_CAP + 32u) {
+        m.status = HOH_S_OVERFLOW;  // slab too small for the worst case: refuse rather than test per symbol
+        if (!feeder) meta[s] = m;
+        live = false;
+    }
+    // tables: row i of stream j's window -> tab[i*32 + j], filled by all 64 threads
+    for (uint32_t j = 0; j < 32; j++) {
+        const uint32_t sj = blockIdx.x * 32u + j;
+        const bool lj = __shfl_sync(0xffffffffu, (int)live, j) != 0;
+        const uint32_t wj = __shfl_sync(0xffffffffu, m.win_rows, j);
+        const uint32_t oj = __shfl_sync(0xffffffffu, m.win_lo, j);
+        if (!lj) continue;
+        const uint32_t* src = cumtab + (size_t)sj * kCumRow + oj;
+        for (uint32_t i = threadIdx.x; i < wj; i += 64) tab[i * 32u + j] = (CumT)src[i];
+    }
+    __syncthreads();
+
+    const uint32_t bits = st.prob_bits;
+    const uint32_t my_n = live ? st.n : 0u;
+    uint32_t n_max = my_n;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
+    const int n_groups = (int)((n_max + kWsGroup - 1) / kWsGroup);
+
+    if (feeder) {
+        const PerLaneTable<CumT> T{tab, lane};
+        const uint32_t full = 1u << bits;
+        const uint32_t win_lo = m.win_lo;
+        const uint32_t sym_max = live ? m.win_rows - 2u : 0u;  // index of the last window row that is a symbol
+        const uint16_t* my_sym = symbols + st.sym_off;
+        auto load = [&](int g) -> uint4 {  // the 8 symbols of group g (never past the stream's last group)
+            if (g >= 0 && (uint32_t)g * kWsGroup < my_n) return __ldg(reinterpret_cast<const uint4*>(my_sym + (size_t)g * kWsGroup));
+            return make_uint4(0u, 0u, 0u, 0u);
+        };
+        // entropy_encoding.hpp:222-225: last symbol first.  Two groups per trip: the barrier numbers are literals, and each
+        // half owns a register set that it reloads (for the group two further on) as soon as it has unpacked it - a
+        // rotation by register moves would wait for the load it moves (ncu: 36 % of the feeder's time, long scoreboard)
+        uint4 set0 = load(n_groups - 1), set1 = load(n_groups - 2);
+        auto feed = [&](int g, auto buf, uint4& mine) {
+            constexpr int b = decltype(buf)::value;
+            const uint4 cur = mine;
+            uint32_t o_start[kWsGroup], o_freq[kWsGroup];
+            double o_inv[kWsGroup];
+#pragma unroll
+            for (int j = 0; j < kWsGroup; j++) {
+                const uint32_t w = j < 2 ? cur.x : (j < 4 ? cur.y : (j < 6 ? cur.z : cur.w));
+                const bool on = (uint32_t)g * kWsGroup + (uint32_t)j < my_n;
+                const uint32_t raw = (j & 1) ? (w >> 16) : (w & 0xffffu);
+                // window-relative index; out-of-alphabet input must not index past the lane's table
+                const uint32_t sym = on ? min(raw - win_lo, sym_max) : 0u;
+                const uint32_t c0 = T.cum(sym), c1 = T.cum(sym + 1u);
+                o_start[j] = on ? c0 : 0u;  // padding step: freq = 2^bits, start = 0 leaves x untouched
+                o_freq[j] = on ? c1 - c0 : full;
+                o_inv[j] = recip_low(o_freq[j]);
+            }
+            mine = load(g - 2);  // in flight while two groups are prepared
+            bar_sync_named<b>();  // the coder has taken the buffer's previous contents
+            uint4* dst = hand + (b * kWsGroup) * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < kWsGroup; j++)
+                dst[j * 32] = make_uint4(o_start[j], o_freq[j], (uint32_t)__double2loint(o_inv[j]), (uint32_t)__double2hiint(o_inv[j]));
+            bar_arrive_named<2 + b>();  // full
+        };
+        for (int g = n_groups - 1; g >= 0; g -= 2) {
+            feed(g, std::integral_constant<int, 0>{}, set0);
+            if (g >= 1) feed(g - 1, std::integral_constant<int, 1>{}, set1);
+        }
+        return;
+    }
+
+    uint32_t* words = reinterpret_cast<uint32_t*>(out + st.out_off);
+    const uint32_t cap_words = st.out_cap / 4u;
+    uint32_t widx = cap_words;
+    uint64_t x = kRansL;  // rans64.hpp:65
+    bar_arrive_named<0>();  // both buffers start empty
+    bar_arrive_named<1>();
+    auto code = [&](auto buf) {
+        constexpr int b = decltype(buf)::value;
+        bar_sync_named<2 + b>();
+        const uint4* src = hand + (b * kWsGroup) * 32 + lane;
+        uint4 h[kWsGroup];
+#pragma unroll
+        for (int j = 0; j < kWsGroup; j++) h[j] = src[j * 32];
+        bar_arrive_named<b>();  // everything is in registers: the feeder may refill
+#pragma unroll
+        for (int j = kWsGroup - 1; j >= 0; j--)
+            x = rans_put<LOW_BITS>(x, h[j].x, h[j].y, __hiloint2double((int)h[j].w, (int)h[j].z), bits, words, widx);
+    };
+    for (int it = 0; it < n_groups; it += 2) {
+        code(std::integral_constant<int, 0>{});
+        if (it + 1 < n_groups) code(std::integral_constant<int, 1>{});
+    }
+    if (live) {
+        // rans64.hpp:96-103 flush: low word at the lower address
+        widx -= 2;
+        words[widx] = (uint32_t)x;
+        words[widx + 1] = (uint32_t)(x >> 32);
+        m.payload_start = st.out_off + (uint64_t)widx * 4u;
+        m.payload_bytes = (cap_words - widx) * 4u;
+        meta[s] = m;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Finish — entropy_encoding.hpp:232-267: length varint in front of the payload, or the stored-mode
 // rewrite when that is smaller.  One warp per stream.  The header is written immediately in front
 // of the payload (which already sits at the END of the stream's slab), so the payload never moves.
