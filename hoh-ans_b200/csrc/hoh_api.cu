@@ -194,9 +194,10 @@ int ensure_smem_opt_in(hoh_ctx* ctx) {
     CK(cudaFuncSetAttribute(k_rans_encode<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_encode<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_encode<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint16_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint32_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(k_rans_encode_ws<uint16_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_decode<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_decode<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(k_rans_decode_tiles_s0<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -275,7 +276,7 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
         const size_t hand = 2 * kWsGroup * 32 * sizeof(uint4);
         const size_t ws16 = (size_t)rows * 32 * sizeof(uint16_t) + hand, ws32 = (size_t)rows * 32 * sizeof(uint32_t) + hand;
         if (padded8) {
-            k_rans_encode_ws<uint16_t, false><<<blocks_for(n, 32), 64, ws16, s16>>>(
+            k_rans_encode_ws<uint16_t, 0><<<blocks_for(n, 32), 64, ws16, s16>>>(
                 d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
         } else {
             k_rans_encode<uint16_t, false><<<blocks_for(n, 32), 32, smem16, s16>>>(
@@ -283,8 +284,11 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
         }
         LAUNCHED(names16[c]);
         if (min_prob_bits < 14) {
-            if (padded8) {
-                k_rans_encode_ws<uint16_t, true><<<blocks_for(n, 32), 64, ws16, s16>>>(
+            if (padded8) {  // prob_bits 12-13, and below 12: two more instantiations
+                k_rans_encode_ws<uint16_t, 2><<<blocks_for(n, 32), 64, ws16, s16>>>(
+                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+                LAUNCHED(names16l[c]);
+                k_rans_encode_ws<uint16_t, 1><<<blocks_for(n, 32), 64, ws16, s16>>>(
                     d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
             } else {
                 k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, s16>>>(
@@ -294,7 +298,7 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
         }
         if (max_prob_bits > 15) {  // 32-bit table lanes; prob_bits >= 16 there, so never LOW_BITS
             if (padded8) {
-                k_rans_encode_ws<uint32_t, false><<<blocks_for(n, 32), 64, ws32, s32>>>(
+                k_rans_encode_ws<uint32_t, 0><<<blocks_for(n, 32), 64, ws32, s32>>>(
                     d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);
             } else {
                 k_rans_encode<uint32_t, false><<<blocks_for(n, 32), 32, smem32, s32>>>(
@@ -736,8 +740,14 @@ int hoh_rans_encode_static(hoh_ctx* ctx, const uint16_t* d_symbols, size_t n, ui
     if (stream_len == 0 || stream_len % 8 || slab_bytes % 16) return HOH_E_ARG;
     if (n == 0) return HOH_OK;
     const uint64_t streams = (n + stream_len - 1) / stream_len;
-    k_rans_encode_static<<<blocks_for(streams, kStaticWarps * 32), kStaticWarps * 32, 0, ctx->stream>>>(
-        d_symbols, n, stream_len, d_cum, range, prob_bits, d_out, slab_bytes, d_payload_bytes);
+    const unsigned sgrid = blocks_for(streams, kStaticWarps * 32);
+    if (prob_bits >= 14) {
+        k_rans_encode_static<0><<<sgrid, kStaticWarps * 32, 0, ctx->stream>>>(d_symbols, n, stream_len, d_cum, range, prob_bits, d_out,
+                                                                          slab_bytes, d_payload_bytes);
+    } else {
+        k_rans_encode_static<1><<<sgrid, kStaticWarps * 32, 0, ctx->stream>>>(d_symbols, n, stream_len, d_cum, range, prob_bits, d_out,
+                                                                          slab_bytes, d_payload_bytes);
+    }
     LAUNCHED("k_rans_encode_static");
     return HOH_OK;
 }

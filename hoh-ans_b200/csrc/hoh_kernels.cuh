@@ -565,38 +565,43 @@ __device__ __forceinline__ double recip_low(uint32_t f) {
 // `inv` = recip_low(freq) is passed in: it does not depend on the state, so callers compute it for a
 // group of symbols ahead of the serial part (those computations overlap each other) and the serial
 // part is only the short dependent chain.
-template <bool LOW_BITS>
+// DIV selects how x / freq is taken:
+//   0  prob_bits >= 14: the quotient is the mantissa of ONE fused multiply-add (below), short by at most 1
+//   2  prob_bits >= 12: the same estimate, short by at most 3 (x / freq < 2^51 still fits the mantissa)
+//   1  any prob_bits:   DMUL + F2I.U64.F64 (the conversion unit again, but such streams are short and few)
+template <int DIV>
 __device__ __forceinline__ uint64_t rans_put(uint64_t x, uint32_t start, uint32_t freq, double inv, uint32_t bits,
                                              uint32_t* __restrict__ words, uint32_t& widx) {
     // x >= ((L >> bits) << 32) * freq  <=>  (x >> (63 - bits)) >= freq, and 63 - bits >= 32
-    const uint32_t xh = (uint32_t)(x >> 32);
+    const uint32_t xh = (uint32_t)(x >> 32), xl = (uint32_t)x;
     const bool emit = (xh >> (31u - bits)) >= freq;
-    if (emit) words[--widx] = (uint32_t)x;
+    if (emit) words[--widx] = xl;
     // The state as a double (truncated), for BOTH outcomes of the renormalisation test, converted while the test is
-    // still being evaluated: the select then picks a finished double, and shift / compare / two moves leave the chain
-    // (I2F.F64.U64 is 19 cycles; it used to start only after the test and the select).  Same values as converting
-    // the selected state, so the exactness argument below is untouched.
-    double d_full, d_hi;  // (opaque to the compiler, which otherwise branches around the 64-bit conversion)
+    // still being evaluated: the select then picks a finished double and the test leaves the chain.  Same values as
+    // converting the selected state, so the exactness argument below is untouched.  (Opaque to the compiler, which
+    // otherwise branches around the 64-bit conversion.  Building the double on the FP64 pipe instead - two magic-number
+    // additions, no conversion unit - was measured: 9.30 against 8.89 ms, the extra register moves cost more.)
+    double d_full, d_hi;
     asm("cvt.rz.f64.u64 %0, %1;" : "=d"(d_full) : "l"(x));
     asm("cvt.rn.f64.u32 %0, %1;" : "=d"(d_hi) : "r"(xh));
     const double xd = emit ? d_hi : d_full;
     x = emit ? (uint64_t)xh : x;
     uint64_t q;  // q <= floor(x / freq), short by <= 1 (bits >= 14)
-    if (LOW_BITS) {
+    if (DIV == 1) {
         q = __double2ull_rz(xd * inv);
     } else {
-        // x / freq < 2^(63 - bits) <= 2^49: the product is added to 2^52 in the SAME fused operation, rounding
+        // x / freq < 2^(63 - bits) <= 2^51: the product is added to 2^52 in the SAME fused operation, rounding
         // towards zero, so the mantissa of the sum IS floor(x_d * inv) — one DFMA instead of DMUL + F2I.U64.F64
         // (8 instead of 34 cycles on the chain).  Same bound as before (the product is not even rounded before
         // the floor); modelled on the CPU in tests/hostfmt (fmt_div_model) over the boundaries of every quotient.
-        q = (uint64_t)__double_as_longlong(__fma_rz(xd, inv, 4503599627370496.0)) & 0x000fffffffffffffull;
+        q = (uint64_t)__double_as_longlong(__fma_rz(xd, inv, 0x1p+52)) & 0x000fffffffffffffull;
     }
     uint32_t r = (uint32_t)x - (uint32_t)q * freq;           // true remainder < 2^32: exact mod 2^32
     if (r >= freq) {
         r -= freq;
         q++;
     }
-    if (LOW_BITS) {
+    if (DIV != 0) {
         while (r >= freq) {
             r -= freq;
             q++;
@@ -842,7 +847,6 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
             stage_wait();
         }
     };
-    const uint32_t zero = rows_lo & 0x80000000u;  // 0 at run time, unknown to the compiler: ties the two instruction streams together
     auto group_words = [&](int g) -> uint4 {  // the 8 symbols of group g from the staging buffer (one LDS.128)
         const int chunk = g / kGroupsPerChunk, k0 = (g % kGroupsPerChunk) * kGroup;
         return *reinterpret_cast<const uint4*>(stage0 + (chunk & 1) * 32 * kBulkStride + lane * kBulkStride + k0);
@@ -867,29 +871,7 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
     auto run = [&](const uint32_t(&g_start)[kGroup], const uint32_t(&g_freq)[kGroup], const double(&g_inv)[kGroup]) {
 #pragma unroll
         for (int j = kGroup - 1; j >= 0; j--)
-            x = rans_put<LOW_BITS>(x, g_start[j], g_freq[j], g_inv[j], bits, words, widx);
-    };
-    // The serial steps of one group with the preparation of the NEXT group woven in symbol by symbol: a step is a
-    // chain of ~20 dependent instructions (~80 cycles) that leaves the issue slots between them empty, and one symbol's
-    // preparation is ~35 independent ones.  Written as two separate loops the compiler kept them apart (five of the
-    // eight steps ran bare) and a warp paid for both, one after the other.
-    auto run_prepare = [&](const uint32_t(&r_start)[kGroup], const uint32_t(&r_freq)[kGroup], const double(&r_inv)[kGroup],
-                           int g_next, uint32_t(&p_start)[kGroup], uint32_t(&p_freq)[kGroup], double(&p_inv)[kGroup]) {
-        const uint4 v = group_words(g_next);
-        // ptxas undoes the weaving (it sinks all eight preparations below the eight steps) unless the two streams are
-        // tied together: the preparation of symbol j takes a (run-time zero) bit of the state before step j, and step
-        // j - 2 takes one of its reciprocal, so it can neither be hoisted above its step nor sunk past the second next.
-        uint32_t tie1 = 0, tie2 = 0;
-#pragma unroll
-        for (int j = kGroup - 1; j >= 0; j--) {
-            const uint32_t before = (uint32_t)x & zero;
-            x = rans_put<LOW_BITS>(x, r_start[j], r_freq[j] | tie2, r_inv[j], bits, words, widx);
-            uint4 vv = v;
-            vv.x |= before; vv.y |= before; vv.z |= before; vv.w |= before;
-            prepare_one(g_next, j, vv, p_start[j], p_freq[j], p_inv[j]);
-            tie2 = tie1;
-            tie1 = (uint32_t)__double_as_longlong(p_inv[j]) & zero;
-        }
+            x = rans_put<LOW_BITS ? 1 : 0>(x, g_start[j], g_freq[j], g_inv[j], bits, words, widx);
     };
     if (n_chunks > 0) {
         uint32_t a_start[kGroup], a_freq[kGroup], b_start[kGroup], b_freq[kGroup];
@@ -899,18 +881,20 @@ __global__ void __launch_bounds__(32) k_rans_encode(const hoh_enc_stream* __rest
         if (n_chunks > 1) load_chunk(n_chunks - 2);
         const int n_groups = n_chunks * kGroupsPerChunk;  // even
         prepare(n_groups - 1, a_start, a_freq, a_inv);
+        // (Weaving the preparation of group g-1 into the steps of group g by hand - symbol by symbol, held in place by
+        // false dependencies - was tried: ptxas then does interleave the two streams, and the kernel takes the same 8.9 ms.)
         for (int g = n_groups - 1; g >= 1; g -= 2) {
-            run_prepare(a_start, a_freq, a_inv, g - 1, b_start, b_freq, b_inv);  // g odd: g-1 is in the same chunk
+            prepare(g - 1, b_start, b_freq, b_inv);  // g odd: g-1 is in the same chunk
+            run(a_start, a_freq, a_inv);
             if (g - 1 >= 1) {
                 if (((g - 1) % kGroupsPerChunk) == 0) {  // group g-2 is the last of the previous chunk
                     const int chunk = (g - 1) / kGroupsPerChunk;
                     wait_chunk(chunk - 1);  // chunk-1 has landed; this chunk's buffer is free (its last group is in b_*)
                     if (chunk >= 2) load_chunk(chunk - 2);
                 }
-                run_prepare(b_start, b_freq, b_inv, g - 2, a_start, a_freq, a_inv);
-            } else {
-                run(b_start, b_freq, b_inv);
+                prepare(g - 2, a_start, a_freq, a_inv);
             }
+            run(b_start, b_freq, b_inv);
         }
     }
     if (live) {
@@ -946,7 +930,7 @@ __device__ __forceinline__ void bar_sync_named() { asm volatile("bar.sync %0, 64
 template <int ID>
 __device__ __forceinline__ void bar_arrive_named() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
 
-template <typename CumT, bool LOW_BITS>
+template <typename CumT, int DIV>
 __global__ void __launch_bounds__(64) k_rans_encode_ws(const hoh_enc_stream* __restrict__ streams, uint32_t n_streams,
                                                        const uint16_t* __restrict__ symbols,
                                                        const uint32_t* __restrict__ cumtab, uint8_t* __restrict__ out,
@@ -987,7 +971,8 @@ __global__ void __launch_bounds__(64) k_rans_encode_ws(const hoh_enc_stream* __r
         low = min(low, __shfl_xor_sync(0xffffffffu, low, d));
     }
     if (need <= rows_lo || need > rows) return;  // another class's launch (or nothing to do)
-    if ((low < 14u) != LOW_BITS) return;         // the other instantiation's warps
+    // the instantiation that fits the warp's narrowest stream (rans_put): every warp runs in exactly one of the three
+    if ((low >= 14u ? 0 : (low >= 12u ? 2 : 1)) != DIV) return;
     if (live && (uint64_t)st.out_cap < rans_words_bound(st.n, st.prob_bits) * 4u + HOH_HEAD_CAP + 32u) {
         m.status = HOH_S_OVERFLOW;  // slab too small for the worst case: refuse rather than test per symbol
         if (!feeder) meta[s] = m;
@@ -1074,7 +1059,7 @@ __global__ void __launch_bounds__(64) k_rans_encode_ws(const hoh_enc_stream* __r
         bar_arrive_named<b>();  // everything is in registers: the feeder may refill
 #pragma unroll
         for (int j = kWsGroup - 1; j >= 0; j--)
-            x = rans_put<LOW_BITS>(x, h[j].x, h[j].y, __hiloint2double((int)h[j].w, (int)h[j].z), bits, words, widx);
+            x = rans_put<DIV>(x, h[j].x, h[j].y, __hiloint2double((int)h[j].w, (int)h[j].z), bits, words, widx);
     };
     for (int it = 0; it < n_groups; it += 2) {
         code(std::integral_constant<int, 0>{});
@@ -1812,6 +1797,7 @@ __global__ void __launch_bounds__(32) k_rans_decode(const hoh_dec_stream* __rest
 // -------------------------------------------------------------------------------------------------
 constexpr int kStaticWarps = 4;
 
+template <int DIV>  // how x / freq is taken (rans_put), chosen by the host from prob_bits
 __global__ void __launch_bounds__(kStaticWarps * 32) k_rans_encode_static(
     const uint16_t* __restrict__ symbols, uint64_t n_total, uint32_t stream_len,
     const uint32_t* __restrict__ cum_g, uint32_t range, uint32_t bits, uint8_t* __restrict__ out,
@@ -1862,11 +1848,16 @@ __global__ void __launch_bounds__(kStaticWarps * 32) k_rans_encode_static(
         };
         auto run_prepare = [&](const uint32_t(&r_start)[kGroup], const uint32_t(&r_freq)[kGroup], const double(&r_inv)[kGroup],
                                int k0_next, uint32_t(&p_start)[kGroup], uint32_t(&p_freq)[kGroup], double(&p_inv)[kGroup]) {
-            uint32_t tie1 = 0, tie2 = 0;  // false dependencies (0 at run time) that keep the two instruction streams woven
+            // ptxas undoes the weaving (it sinks all eight preparations below the eight steps) unless the two streams
+            // are tied together by false dependencies (0 at run time): the preparation of symbol j takes a bit of the
+            // state before step j, and step j - 2 one of its reciprocal.  Worth 7 % here, where a warp has a scheduler
+            // almost to itself (8.68 -> 8.10 ms at 2^30 symbols); nothing in k_rans_encode, whose 2.4 warps per
+            // scheduler already fill each other's stalls.
+            uint32_t tie1 = 0, tie2 = 0;
 #pragma unroll
             for (int j = kGroup - 1; j >= 0; j--) {
                 const uint32_t before = (uint32_t)x & zero;
-                x = rans_put<true>(x, r_start[j], r_freq[j] | tie2, r_inv[j], bits, words, widx);
+                x = rans_put<DIV>(x, r_start[j], r_freq[j] | tie2, r_inv[j], bits, words, widx);
                 prepare_one(k0_next + j, before, p_start[j], p_freq[j], p_inv[j]);
                 tie2 = tie1;
                 tie1 = (uint32_t)__double_as_longlong(p_inv[j]) & zero;
@@ -1885,7 +1876,7 @@ __global__ void __launch_bounds__(kStaticWarps * 32) k_rans_encode_static(
         run_prepare(a_start, a_freq, a_inv, 0, b_start, b_freq, b_inv);  // a = group at kGroup, b = the chunk's first
 #pragma unroll
         for (int j = kGroup - 1; j >= 0; j--)
-            x = rans_put<true>(x, b_start[j], b_freq[j], b_inv[j], bits, words, widx);
+            x = rans_put<DIV>(x, b_start[j], b_freq[j], b_inv[j], bits, words, widx);
     }
     if (live) {
         if (fits) {
@@ -5049,31 +5040,33 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
     uint8_t* p_cur = tile0;
     uint8_t* p_px = tile0 + 8u * ch;
 
-    // The two chains are software-pipelined by one pixel: step (grp, i) decodes symbol 8 grp + i and, in the shadow of
-    // its two shared-memory round trips, un-predicts the pixel whose residual the PREVIOUS step delivered.  (The
-    // far-walk vote of every step is a branch the compiler does not schedule across, so work that depended on this
-    // step's symbol would sit at the end of the step, on the chain.)
+    // The two chains are woven by hand (`step` below): the far-walk vote of every step is a branch the compiler
+    // schedules nothing across, so what fills the lookup's two shared-memory round trips has to stand there in the source.
     uint32_t L = half, TLv = half;
-    uint32_t r_prev = 0, t_prev = half;               // residual of the pixel in flight and the T value that goes with it
     uint2 ta = make_uint2(0x80808080u, 0x80808080u), tb = ta, tc = ta;  // the 24 bytes above the current group (row 0: c/2)
     const uint32_t groups = npx / 8u;                 // tw % 8 == 0
     uint32_t gx = 0, gy = 0;                          // position of the current group in the tile (warp-uniform)
-    // un-predict the pixel in flight (column `col` of its row), hand its byte to the stage slot `slot`
-    auto finish_pixel = [&](uint32_t slot, bool row_start) {
+    // A pixel is finished in two parts that sit in the two shadows of the NEXT symbol's lookup (see the step below):
+    // un-prediction proper (and the shuffle that carries G to the difference planes) while the midpoint entry is on
+    // its way, the staging of the byte while the four table rows are.
+    uint32_t v_pend = 0, gv_pend = 0;  // the pixel between its two parts: value in its plane, G of its tile
+    auto pixel_part1 = [&](uint32_t r, uint32_t t, bool row_start) {
         if (row_start) {  // prediction.hpp:25-26
             L = half;
             TLv = half;
         }
         // median(T, L, (u16)(T + L - TL)) on 10-bit values: a negative gradient wraps to a huge unsigned value in 32 bits
         // exactly as it does in the reference's 16 (predictor_operations.hpp:37-60), so no 16-bit mask is needed
-        const uint32_t grad = t_prev + L - TLv;
-        const uint32_t med = max(min(t_prev, L), min(max(t_prev, L), grad));
-        const uint32_t v = (r_prev + med - half) & cmask;  // inverse of prediction.hpp:34
-        TLv = t_prev;
+        const uint32_t grad = t + L - TLv;
+        const uint32_t med = max(min(t, L), min(max(t, L), grad));
+        const uint32_t v = (r + med - half) & cmask;  // inverse of prediction.hpp:34
+        TLv = t;
         L = v;
-        const uint32_t gv = __shfl_sync(0xffffffffu, v, base_lane);
-        // inverse of channel.hpp:75-77 (mod 256: the +256 drops out)
-        asm volatile("st.shared.u8 [%0], %1;" ::"r"(my_stage_s + 3u * slot), "r"(v + (gv & g_keep)) : "memory");
+        v_pend = v;
+        gv_pend = __shfl_sync(0xffffffffu, v, base_lane);
+    };
+    auto pixel_part2 = [&](uint32_t slot) {  // inverse of channel.hpp:75-77 (mod 256: the +256 drops out)
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(my_stage_s + 3u * slot), "r"(v_pend + (gv_pend & g_keep)) : "memory");
     };
     // T of the 8 pixels of a group from the 24 RGB bytes above them, byte-wise: own byte minus G (mod 256) in t_lo, and for
     // the difference planes the ninth bit (R - G + 256 has bit 8 set iff R >= G) in t_hi; row 0 is fed bytes 0x80, which
@@ -5099,22 +5092,61 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
         const uint32_t pair = i < 2u ? t01 : (i < 4u ? t23 : (i < 6u ? t45 : t67));
         return (i & 1u) ? (pair >> 16) : (pair & 0xffffu);
     };
-    auto next_symbol = [&](auto has_stored) -> uint32_t {
-        uint32_t r = rans_get_s<LutT>(x, rd, TS, lut_s, lut_shift, bits, mask);
+    // One symbol (rans_get_s, rans64.hpp:118-142) and one pixel, ordered by hand for the in-order issue of a warp: the
+    // lookup of a symbol has two shared-memory round trips on the coder's chain (midpoint entry, then four table rows),
+    // and ptxas leaves instructions where the source has them.  So the slot and the midpoint load of the NEXT symbol are
+    // issued the moment the state is renormalised, the un-prediction of the symbol just decoded follows (it fills the
+    // first round trip), and the staging of that pixel's byte comes after the row loads of the next step (it starts
+    // filling the second).  Written as "finish the previous pixel, then decode" the two round trips were bare:
+    // 48 + 40 cycles of a 311-cycle step waiting with nothing to issue (ncu source view).
+    uint32_t slot = 0, key = 0, p_lut = 0;
+    auto lookup_begin = [&]() {
+        slot = (uint32_t)x & mask;  // rans64.hpp:118-121
+        key = (slot + 1u) << kSymBits;
+        if (sizeof(LutT) == 1) {
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p_lut) : "r"(lut_s + (slot >> lut_shift) * 32u));
+        } else {
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(p_lut) : "r"(lut_s + (slot >> lut_shift) * 64u));
+        }
+    };
+    auto step = [&](auto has_stored, uint32_t i, bool row_start) {
+        uint32_t em, e0, e1, e2;
+        TS.at4(p_lut, em, e0, e1, e2);
+        pixel_part2((i + 7u) & 7u);  // the pixel decoded one step ago (step 0: pixel 7 of the previous group)
+        const bool down = e0 >= key;  // see rans_lookup_near
+        const bool up = e1 < key;
+        uint32_t e = down ? em : (up ? e1 : e0);
+        uint32_t up_ones;
+        asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(up_ones) : "r"(e1), "r"(key));
+        uint32_t hi = down ? e0 : e1 + ((e2 - e1) & up_ones);
+        const bool near = e < key && hi >= key;
+        const uint64_t top = x >> bits;
+        uint64_t next = (uint64_t)((hi >> kSymBits) - (e >> kSymBits)) * top + (slot - (e >> kSymBits));  // rans64.hpp:126-134
+        if (__builtin_expect(__any_sync(0xffffffffu, !near), 0)) {
+            const ulonglong2 fixed = rans_far_step(TS, key, p_lut, e, hi, top, slot);
+            next = fixed.x;
+            e = (uint32_t)fixed.y;
+        }
+        x = next;
+        const bool refill = ((uint32_t)(x >> 32) | ((uint32_t)x >> 31)) == 0u;  // rans64.hpp:137-141
+        x = refill ? ((x << 32) | rd.next) : x;
+        rd.take_if(refill);
+        uint32_t r = e & kSymMask;
         if (decltype(has_stored)::value) {
-            const bool refill = stored && have < sbits;
-            if (refill) {
+            const bool fill = stored && have < sbits;
+            if (fill) {
                 acc |= (uint64_t)__byte_perm(rd.next, 0u, 0x0123) << (32u - have);
                 have += 32u;
             }
-            rd.take_if(refill);
+            rd.take_if(fill);
             if (stored) {
                 r = (uint32_t)(acc >> (64u - sbits));
                 acc <<= sbits;
                 have -= sbits;
             }
         }
-        return r;
+        lookup_begin();
+        pixel_part1(r, t_of(i), row_start);
     };
     auto flush_group = [&]() {  // the 24 staged bytes of every tile -> the image (a predicated store, no branch)
         __syncwarp();
@@ -5141,16 +5173,11 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
         }
         uint8_t* p_next = p_cur + (wrap ? row_skip : 24ull);
         t_prepare(ta, tb, tc);
-        // step 0: symbol 0 of this group; pixel 7 of the previous one, which completes that group.  (In group 0 there
-        // is no such pixel: the step un-predicts a zero residual into slot 7 and the flush stores the zeroed stage to
-        // the tile's first 24 bytes, which group 0's own flush overwrites one group later - cheaper than a branch here.)
-        {
-            finish_pixel(7u, false);
-            const uint32_t r = next_symbol(has_stored);
-            r_prev = r;
-            t_prev = t_of(0u);
-            flush_group();
-        }
+        // step 0: symbol 0 of this group, and the byte of pixel 7 of the previous one, which completes that group.  (In
+        // group 0 there is no such pixel: a zero byte goes to slot 7 and the flush stores the zeroed stage to the
+        // tile's first 24 bytes, which group 0's own flush overwrites one group later - cheaper than a branch here.)
+        step(has_stored, 0u, gx == 0u);
+        flush_group();
         // the bytes above the NEXT group: stored at least one whole group ago (tile_w >= 16), and after the flush above
         uint2 na = make_uint2(0x80808080u, 0x80808080u), nb = na, nc = na;
         if (ny > 0u && ny < th && tile_ok) {
@@ -5160,12 +5187,7 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
             nc = __ldcg(src + 2);
         }
 #pragma unroll
-        for (uint32_t i = 1; i < 8u; i++) {
-            finish_pixel(i - 1u, i == 1u && gx == 0u);
-            const uint32_t r = next_symbol(has_stored);
-            r_prev = r;
-            t_prev = t_of(i);
-        }
+        for (uint32_t i = 1; i < 8u; i++) step(has_stored, i, false);
         p_px = p_cur + 8u * ch;
         p_cur = p_next;
         ta = na;
@@ -5175,12 +5197,13 @@ __global__ void __launch_bounds__(32) k_rans_decode_tiles_s0(const hoh_dec_strea
         gy = ny;
     }
     };
+    lookup_begin();  // the first symbol's
     if (any_stored) {
         run(StoredYes{});
     } else {
         run(StoredNo{});
     }
-    finish_pixel(7u, false);
+    pixel_part2(7u);
     flush_group();
     // rans64.hpp:65: decoding undoes the encoder's steps, so a sound stream ends in the encoder's initial state
     if (coded && x != kRansL) my_status = HOH_S_BAD_STATE;

@@ -29,7 +29,7 @@ uint32_t fmt_table_mode(const uint32_t* freqs, uint32_t range, uint32_t n, uint3
     hohfmt::plan_head(freqs, range, n, prob_bits, head, &stored, &cs, &mode, representable);
     return mode;
 }
-// CPU model of the encoder's division step for prob_bits >= 14 (hoh_kernels.cuh rans_put<false>):
+// CPU model of the encoder's division step for prob_bits >= 12 (hoh_kernels.cuh rans_put<0> / rans_put<2>):
 // q = mantissa(fma_rz(double_rz(x), inv, 2^52)), r = lo(x) - lo(q) * f, one upward fix-up.  `inv` is modelled as
 // RN(1/f) * (1 - 2^-50) moved by `ulps` (the device's Newton result may differ from RN(1/f) by an ulp or two).
 // Walks states below x_max = f << (63 - bits) — random ones, the top of the range, both ends of quotient
@@ -66,6 +66,8 @@ uint64_t fmt_div_model(uint32_t bits, uint64_t cases, uint64_t seed, int ulps) {
         uint64_t q = b & 0x000fffffffffffffull;
         uint32_t r = (uint32_t)x - (uint32_t)q * f;
         if (r >= f) { r -= f; q++; }
+        if (bits < 14)  // rans_put<2>: prob_bits 12-13, the estimate may be short by a few more; the device loops
+            for (int k = 0; k < 6 && r >= f; k++) { r -= f; q++; }
         bad += !(q == x / f && r == x % f);
     }
     std::fesetround(FE_TONEAREST);

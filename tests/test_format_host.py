@@ -130,10 +130,10 @@ def test_representable_rule_only_changes_lossy_mode1_tables():
 
 def test_encoder_division_step_model_is_exact():
     """The rANS encoder's x / freq for prob_bits >= 14 is one fused multiply-add rounded towards zero whose
-    mantissa is the quotient (hoh_kernels.cuh, rans_put<false>): its CPU model against the integer division, over
+    mantissa is the quotient (hoh_kernels.cuh, rans_put<0> / <2>): its CPU model against the integer division, over
     random states, the top of the state range and both ends of quotient intervals, for reciprocals up to two
     ulps either side of the nominal one."""
     L = _lib()
-    for bits in range(14, 20):
+    for bits in range(12, 20):  # 12-13: rans_put<2>, up to three fix-ups; 14-19: rans_put<0>, one
         for ulps in (-2, 0, 2):
             assert L.fmt_div_model(bits, 400000, 1234567 + bits, ulps) == 0, (bits, ulps)
