@@ -425,11 +425,13 @@ int predict_all_parallel(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes
     TRY(scratch_t(ctx, S_PA_BEST, total, &best));
     const uint64_t bpp = ((uint64_t)w * h + 255) / 256;  // CTAs per plane
     if (n_planes * bpp > 0x7fffffffull) return HOH_E_UNSUPPORTED;
+    const FastDiv d_bpp = fastdiv_make((uint32_t)bpp), d_w = fastdiv_make((uint32_t)w);
+    const FastDiv d_tw = fastdiv_make((uint32_t)((w + x_tiles - 1) / x_tiles)), d_th = fastdiv_make((uint32_t)((h + y_tiles - 1) / y_tiles));
     k_predict_all_best<<<(unsigned)(n_planes * bpp), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, x_tiles, y_tiles,
-                                                                          d_tile_maps, best);
+                                                                          d_tile_maps, best, d_bpp, d_w, d_tw, d_th);
     LAUNCHED("k_predict_all_best");
     k_predict_all_resid<<<(unsigned)(n_planes * bpp), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, best, d_resid,
-                                                                           resid_stride);
+                                                                           resid_stride, d_bpp, d_w);
     LAUNCHED("k_predict_all_resid");
     return HOH_OK;
 }

@@ -2137,6 +2137,13 @@ __global__ void __launch_bounds__(256) k_gather_streams(const hoh_stream_result*
 // Predictor primitives — predictor_operations.hpp (u16 forms, C int promotion semantics)
 // =================================================================================================
 __device__ __forceinline__ int p_mid(int a, int b) { return a + (b - a) / 2; }  // :8-10, truncating
+// x % c for c a power of two, with C's truncation for negative x (what the reference's `% centre` does with an
+// out-of-range pixel).  c is a run-time value in these kernels, so `%` itself compiles to a software division
+// (~14 instructions; it was a quarter of k_section_costs).
+__device__ __forceinline__ int mod_pow2(int x, int c) {
+    const int r = abs(x) & (c - 1);
+    return x < 0 ? -r : r;
+}
 __device__ __forceinline__ int p_med(int a, int b, int c) {                     // :37-60
     const int lo = min(a, b), hi = max(a, b);
     return c < lo ? lo : (c > hi ? hi : c);
@@ -2427,7 +2434,7 @@ __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__
             int v;
             if (!INVERSE) {
                 v = src[at];
-                dst[at] = (uint16_t)((v - pred + half + c) % c);  // prediction.hpp:208
+                dst[at] = (uint16_t)mod_pow2(v - pred + half + c, c);  // prediction.hpp:208
             } else if (br && br[at]) {
                 v = dst[at - br[at]];  // unprediction.hpp:63-65
                 dst[at] = (uint16_t)v;
@@ -2457,6 +2464,23 @@ __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__
 //                                     the pixel BELOW q (prediction.hpp:213-225)
 // Pass 1 computes the best predictor of every pixel, pass 2 the residuals.
 // -------------------------------------------------------------------------------------------------
+// Division of a 31-bit number by a run-time constant without the software divide (~20 instructions; the per-pixel
+// kernels below spent half of theirs splitting a linear index into plane / row / column / grid cell): the host
+// prepares (multiplier, shift) once per launch, the device needs a multiply-high, an add and a shift.
+struct FastDiv {
+    uint32_t d, mul, shift;
+};
+__host__ __device__ inline FastDiv fastdiv_make(uint32_t d) {  // d >= 1; exact for every n < 2^31
+    FastDiv f;
+    f.d = d;
+    uint32_t s = 0;
+    while ((1ull << s) < d) s++;
+    f.shift = s;
+    f.mul = (uint32_t)((((1ull << s) - d) << 32) / d + 1ull);
+    return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) { return (__umulhi(n, f.mul) + n) >> f.shift; }
+
 __device__ __forceinline__ void pa_candidates(const uint16_t* __restrict__ src, int w, int x, int y, int half, Cand& k) {
     const uint16_t* row = src + (size_t)y * w;
     const uint16_t* up = row - w;
@@ -2472,35 +2496,39 @@ __device__ __forceinline__ void pa_candidates(const uint16_t* __restrict__ src, 
 __global__ void __launch_bounds__(256) k_predict_all_best(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
                                                           int h, int depth, int x_tiles, int y_tiles,
                                                           const uint16_t* __restrict__ tile_maps,
-                                                          uint8_t* __restrict__ best) {
-    // blocks_per_plane consecutive CTAs share a plane: 32-bit index arithmetic only
-    const uint32_t per = (uint32_t)w * (uint32_t)h, bpp = (per + blockDim.x - 1u) / blockDim.x;
-    const uint64_t p = blockIdx.x / bpp;
-    const uint32_t at = (blockIdx.x % bpp) * blockDim.x + threadIdx.x;
+                                                          uint8_t* __restrict__ best, FastDiv d_bpp, FastDiv d_w,
+                                                          FastDiv d_tw, FastDiv d_th) {
+    // blocks_per_plane consecutive CTAs share a plane: 32-bit index arithmetic only (d_bpp = CTAs per plane, d_w = w,
+    // d_tw / d_th = the grid cell's size)
+    const uint32_t per = (uint32_t)w * (uint32_t)h;
+    const uint32_t pl = fd_div(blockIdx.x, d_bpp);
+    const uint64_t p = pl;
+    const uint32_t at = (blockIdx.x - pl * d_bpp.d) * blockDim.x + threadIdx.x;
     if (p >= n_planes || at >= per) return;
     const uint64_t i = p * per + at;
-    const int x = (int)(at % (uint32_t)w), y = (int)(at / (uint32_t)w);
+    const int y = (int)fd_div(at, d_w), x = (int)(at - (uint32_t)y * (uint32_t)w);
     if (y + 1 >= h) {
         best[i] = 0;
         return;
     }
     const int c = 1 << depth, half = c >> 1;
-    const int tw = (w + x_tiles - 1) / x_tiles, th = (h + y_tiles - 1) / y_tiles;
     const uint16_t* src = planes + p * per;
     Cand k;
     pa_candidates(src, w, x, y, half, k);
-    const uint32_t mask = tile_maps[p * (uint64_t)x_tiles * y_tiles + (size_t)((y + 1) / th) * x_tiles + x / tw];
+    const uint32_t mask = tile_maps[p * (uint64_t)x_tiles * y_tiles + (size_t)fd_div((uint32_t)(y + 1), d_th) * x_tiles + fd_div((uint32_t)x, d_tw)];
     best[i] = (uint8_t)pick_best(src[at], k, mask, c);
 }
 
 __global__ void __launch_bounds__(256) k_predict_all_resid(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
                                                            int h, int depth, const uint8_t* __restrict__ best,
-                                                           uint16_t* __restrict__ out, uint64_t out_stride) {
-    const uint32_t per = (uint32_t)w * (uint32_t)h, bpp = (per + blockDim.x - 1u) / blockDim.x;
-    const uint64_t p = blockIdx.x / bpp;
-    const uint32_t at = (blockIdx.x % bpp) * blockDim.x + threadIdx.x;
+                                                           uint16_t* __restrict__ out, uint64_t out_stride, FastDiv d_bpp,
+                                                           FastDiv d_w) {
+    const uint32_t per = (uint32_t)w * (uint32_t)h;
+    const uint32_t pl = fd_div(blockIdx.x, d_bpp);
+    const uint64_t p = pl;
+    const uint32_t at = (blockIdx.x - pl * d_bpp.d) * blockDim.x + threadIdx.x;
     if (p >= n_planes || at >= per) return;
-    const int x = (int)(at % (uint32_t)w), y = (int)(at / (uint32_t)w);
+    const int y = (int)fd_div(at, d_w), x = (int)(at - (uint32_t)y * (uint32_t)w);
     const int c = 1 << depth, half = c >> 1;
     const uint16_t* src = planes + p * per;
     const uint8_t* b = best + p * per;
@@ -2509,7 +2537,7 @@ __global__ void __launch_bounds__(256) k_predict_all_resid(const uint16_t* __res
     const int bp_top = y > 0 ? b[at - w] : 4;
     const int bp_left = x > 0 ? b[at - 1] : (y > 0 ? b[at - 1] : 4);  // x == 0: (w-1, y-1) is the element before (0, y)
     const int pred = p_mid(cand_at(k, bp_top), cand_at(k, bp_left));
-    out[p * out_stride + at] = (uint16_t)(((int)src[at] - pred + half + c) % c);  // prediction.hpp:208
+    out[p * out_stride + at] = (uint16_t)mod_pow2((int)src[at] - pred + half + c, c);  // prediction.hpp:208
 }
 
 // =================================================================================================
@@ -2573,9 +2601,10 @@ __global__ void __launch_bounds__(64) k_section(const uint16_t* __restrict__ pla
         for (int xm = 0; xm < tw && x0 + xm < w; xm++) {
             const int v = data[(uint64_t)(y0 + ym) * w + x0 + xm];
             Cand kk;
-            candidates(left, top[xm], left_top, top[(xm + 1) % tw], true, kk);  // :115 TR wraps inside the cell
-            const int pred = p_mid(cand_at(kk, bp[xm]), cand_at(kk, bp[(xm + tw - 1) % tw]));  // :134
-            const int r = (v - pred + half + c) % c;
+            // (xm + 1) % tw and (xm + tw - 1) % tw as selects: tw is a run-time value, `%` a software division
+            candidates(left, top[xm], left_top, top[xm + 1 == tw ? 0 : xm + 1], true, kk);  // :115 TR wraps inside the cell
+            const int pred = p_mid(cand_at(kk, bp[xm]), cand_at(kk, bp[xm ? xm - 1 : tw - 1]));  // :134
+            const int r = mod_pow2(v - pred + half + c, c);
             if (COST) sum += ctab[r]; else if (k < cell_cap) dst[k] = (uint16_t)r;
             k++;
             left_top = top[xm];
@@ -2671,7 +2700,7 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
         for (int xm = 0; xm < tw && x0 + xm < w; xm++) {
             const int v = data[(uint64_t)(y0 + ym) * w + x0 + xm];
             Cand kk;
-            candidates(left, top[xm], left_top, top[(xm + 1) % tw], true, kk);  // :115 TR wraps inside the cell
+            candidates(left, top[xm], left_top, top[xm + 1 == tw ? 0 : xm + 1], true, kk);  // :115 TR wraps inside the cell
             int key[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) {
@@ -2686,13 +2715,14 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
             }
             auto key_of = [&](uint32_t j) { return abs(v - (int)s_cand[j][tid]) * 16 + (int)j; };
             const uint64_t above = bpcol[xm];
-            const uint64_t before = bpcol[(xm + tw - 1) % tw];  // :134 (this row's left pixel once xm > 0)
+            const uint64_t before = bpcol[xm ? xm - 1 : tw - 1];  // :134 (xm + tw - 1) % tw: this row's left pixel once xm > 0
             uint64_t now = 0;
 #pragma unroll
             for (int m = 0; m < NM; m++) {
                 const uint32_t bt = (uint32_t)(above >> (4 * m)) & 15u, bl = (uint32_t)(before >> (4 * m)) & 15u;
                 const int pred = p_mid((int)s_cand[bt][tid], (int)s_cand[bl][tid]);
-                const int r = (v - pred + half + c) % c;
+                // (v - pred + half + c) % c: the operand is positive for pixels below c, and the table has c entries
+                const int r = (v - pred + half + c) & (c - 1);
                 sum[m] += ctab[r];
                 uint32_t kind, ia, ib;
                 if (STOCK) {
@@ -2722,7 +2752,11 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
                     best = key_of(ia);
                     if (kind == 2u) best = min(best, key_of(ib));
                 }
-                now |= (uint64_t)((best >> 4) < 2 * c ? (best & 15) : 0) << (4 * m);  // 0x7fffffff: empty mask
+                // "stays 0 when nothing beats 2c" (prediction.hpp:138): every candidate is a median / average / copy of
+                // in-range neighbours, so an allowed candidate's error is below c; only an EMPTY mask (0x7fffffff, not in
+                // the stock list) can fail the test
+                const int won = STOCK ? (best & 15) : ((best >> 4) < 2 * c ? (best & 15) : 0);
+                now |= (uint64_t)won << (4 * m);
             }
             bpcol[xm] = now;
             left_top = top[xm];
