@@ -35,6 +35,7 @@ struct Buf {
 
 struct hoh_ctx {
     int device = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
@@ -236,6 +237,25 @@ int aux_join(hoh_ctx* ctx, int count) {
     return HOH_OK;
 }
 
+// The dynamic shared memory to ask for so that an SM holds at most `per_sm` CTAs of a kernel that needs `smem` bytes
+// (sm_100: 228 KB per SM, 1 KB of it reserved per resident CTA).  The entropy kernels are bound by instruction-pipe
+// throughput, so an SM's time grows with the number of warps it holds, and the block scheduler does not balance CTAs
+// across SMs when several launches run side by side: capping the count at the even share keeps the slowest SM short.
+size_t smem_for_cap(size_t smem, unsigned per_sm) {
+    const size_t sm_total = 228u * 1024u;
+    size_t need = sm_total / (per_sm + 1u) - 1024u + 128u;
+    need = (need + 127u) & ~(size_t)127u;
+    return smem > need ? smem : need;
+}
+
+// ... for a launch of `grid` one-warp-chain CTAs on this device: the even share per SM when the launch is a large single
+// wave (a small launch is left alone: it may be one of several pipeline chunks in flight that share the SMs).
+size_t smem_even_share(const hoh_ctx* ctx, size_t smem, unsigned grid) {
+    const unsigned share = (grid + (unsigned)ctx->sm_count - 1u) / (unsigned)ctx->sm_count;
+    if (const char* e = getenv("HOH_ENC_CAP")) return atoi(e) > 0 ? smem_for_cap(smem, (unsigned)atoi(e)) : smem;
+    return share >= 8u ? smem_for_cap(smem, share) : smem;
+}
+
 // Shared tail of the encode pipeline once the raw histograms are in `freqs`.
 // min_prob_bits: a lower bound the CALLER guarantees for every stream's prob_bits (0 = unknown).
 // padded8: the CALLER guarantees that every stream's symbols start 16-byte aligned and are readable up to the next
@@ -274,7 +294,11 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
         static const char* const names32[4] = {"k_rans_encode<u32>[rows<=64]", "k_rans_encode<u32>[rows<=128]",
                                                "k_rans_encode<u32>[rows<=256]", "k_rans_encode<u32>[rows<=513]"};
         const size_t hand = 2 * kWsGroup * 32 * sizeof(uint4);
-        const size_t ws16 = (size_t)rows * 32 * sizeof(uint16_t) + hand, ws32 = (size_t)rows * 32 * sizeof(uint32_t) + hand;
+        size_t ws16 = (size_t)rows * 32 * sizeof(uint16_t) + hand, ws32 = (size_t)rows * 32 * sizeof(uint32_t) + hand;
+        // BASELINE config 2: 1 536 CTAs = 10.4 per SM; left to itself the block scheduler puts up to 14 on some SMs while
+        // the other classes' launches come and go (encode 14.5 ms), capped at 11 everywhere 12.9 ms
+        ws16 = smem_even_share(ctx, ws16, blocks_for(n, 32));
+        ws32 = smem_even_share(ctx, ws32, blocks_for(n, 32));
         if (padded8) {
             k_rans_encode_ws<uint16_t, 0><<<blocks_for(n, 32), 64, ws16, s16>>>(
                 d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
@@ -491,6 +515,8 @@ int hoh_ctx_create(int device, void* cuda_stream, hoh_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return HOH_E_CUDA;
     hoh_ctx* ctx = new hoh_ctx();
     ctx->device = device;
+    if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->sm_count <= 0)
+        ctx->sm_count = 148;
     if (cuda_stream) {
         ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     } else {
@@ -897,18 +923,19 @@ int hoh_decode_images_s0(hoh_ctx* ctx, const uint8_t* d_packed, size_t packed_by
         const unsigned grid = blocks_for(n_tiles, kFusedTiles);
         for (int c = 0; c < 4; c++) {
             const uint32_t rows = classes[c + 1];
-            size_t fixed = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kRingWords * sizeof(uint32_t) + kFusedStage;
+            const size_t fixed = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kRingWords * sizeof(uint32_t) + kFusedStage;
             // The kernel is bound by instruction-pipe throughput, so an SM's time grows with the number of warps it
             // holds: 13 CTAs of the smallest class would fit one SM, and with the other classes' launches running
-            // beside it the block scheduler does fill some SMs that far while others hold 10.  Asking for 17 KB
-            // caps every SM at 12 (BASELINE config 2: 1 639 warps = 11.07 per SM).
-            if (fixed + kLutSize * 32 < 17408) fixed = 17408 - kLutSize * 32;
+            // beside it the block scheduler does fill some SMs that far while others hold 10.  Asking for the even
+            // share caps every SM at 12 (BASELINE config 2: 1 639 warps = 11.07 per SM).
+            const size_t lut_bytes = (size_t)kLutSize * 32 * (rows <= 256 ? 1 : 2);
+            const size_t smem = smem_even_share(ctx, fixed + lut_bytes, grid);
             cudaStream_t sc = overlap ? ctx->aux[c] : ctx->stream;
             if (rows <= 256) {
-                k_rans_decode_tiles_s0<uint8_t><<<grid, 32, fixed + kLutSize * 32 * 1, sc>>>(
+                k_rans_decode_tiles_s0<uint8_t><<<grid, 32, smem, sc>>>(
                     streams, (uint32_t)n_streams, d_packed, packed_bytes, cum, meta, results, g, d_rgb, d_status, classes[c], rows);
             } else {
-                k_rans_decode_tiles_s0<uint16_t><<<grid, 32, fixed + kLutSize * 32 * 2, sc>>>(
+                k_rans_decode_tiles_s0<uint16_t><<<grid, 32, smem, sc>>>(
                     streams, (uint32_t)n_streams, d_packed, packed_bytes, cum, meta, results, g, d_rgb, d_status, classes[c], rows);
             }
             static const char* const names[4] = {"k_rans_decode_tiles_s0[rows<=64]", "k_rans_decode_tiles_s0[rows<=128]",
@@ -994,13 +1021,45 @@ int pinned_off(hoh_ctx* ctx, int k, size_t entries, uint64_t** out) {
     *out = ctx->h_off[k];
     return HOH_OK;
 }
+// smallest steady chunk in bytes of pixels (HOH_PIPE_CHUNK_KB: for tests, so that small batches take the chunked path)
+size_t pipe_chunk_floor() {
+    if (const char* e = getenv("HOH_PIPE_CHUNK_KB")) return (size_t)atol(e) << 10;
+    return (size_t)64 << 20;
+}
 size_t chunk_images_for(size_t n_images, size_t raw_per_image) {
     // about 8 chunks, but not below ~64 MB of pixels per chunk (small batches are not worth pipelining)
     size_t per = (n_images + 7) / 8;
-    const size_t min_per = (64u << 20) / (raw_per_image ? raw_per_image : 1) + 1;
+    const size_t min_per = pipe_chunk_floor() / (raw_per_image ? raw_per_image : 1) + 1;
     if (per < min_per) per = min_per;
     if (per > n_images) per = n_images;
     return per;
+}
+// Chunk boundaries (image indices, n_chunks + 1 of them) of a pipelined host call.  What the pipeline cannot hide is its
+// head and its tail: before the first chunk's kernels have run nothing flows back, and the last chunk's kernels and
+// fetch run after the last byte has gone in.  A chunk's kernels last about as long whatever its size (one stream's
+// serial chain), so both ends are made of short chunks that double up to the steady size: per/8, per/4, per/2, per, ...,
+// per, per/2, per/4, per/8 (never below ~32 MB of pixels).
+std::vector<size_t> chunk_plan(size_t n_images, size_t raw_per_image, size_t* max_chunk) {
+    const size_t per = chunk_images_for(n_images, raw_per_image);
+    std::vector<size_t> bounds{0};
+    const size_t floor_per = pipe_chunk_floor() / 2 / (raw_per_image ? raw_per_image : 1) + 1;
+    std::vector<size_t> ramp;
+    if (!getenv("HOH_NO_RAMP"))
+        for (size_t r = std::max<size_t>(per / 8, 1); r < per; r *= 2)
+            if (r >= floor_per) ramp.push_back(r);
+    size_t ramp_sum = 0;
+    for (size_t r : ramp) ramp_sum += r;
+    if (n_images < 2 * ramp_sum + 2 * per) {
+        ramp.clear();
+        ramp_sum = 0;
+    }
+    for (size_t r : ramp) bounds.push_back(bounds.back() + r);
+    const size_t middle = n_images - 2 * ramp_sum, n_mid = (middle + per - 1) / per;
+    for (size_t k = 0; k < n_mid; k++) bounds.push_back(bounds.back() + middle / n_mid + (k < middle % n_mid ? 1 : 0));
+    for (size_t k = ramp.size(); k-- > 0;) bounds.push_back(bounds.back() + ramp[k]);
+    *max_chunk = 0;
+    for (size_t k = 0; k + 1 < bounds.size(); k++) *max_chunk = std::max(*max_chunk, bounds[k + 1] - bounds[k]);
+    return bounds;
 }
 // everything queued on the parent's stream so far happens before the pipeline, and the pipeline's
 // completion is visible on the parent's stream afterwards
@@ -1031,8 +1090,9 @@ int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_im
     TRY(hoh_tile_geometry_for(width, height, &hg));
     TRY(pipe_init(ctx));
     const size_t raw1 = (size_t)width * height * 3;
-    const size_t per = chunk_images_for(n_images, raw1);
-    const size_t n_chunks = (n_images + per - 1) / per;
+    size_t per;  // the largest chunk
+    const std::vector<size_t> bounds = chunk_plan(n_images, raw1, &per);
+    const size_t n_chunks = bounds.size() - 1;
     const size_t spi = hg.streams_per_image;
     const size_t chunk_streams = per * spi;
     const size_t out_bytes = hoh_encode_images_out_bytes(&hg, per);
@@ -1061,8 +1121,7 @@ int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_im
         if (c < n_chunks) {
             const int b = (int)(c % depth);
             hoh_ctx* ch = ctx->child[b];
-            const size_t first = c * per;
-            const size_t n_c = first + per <= n_images ? per : n_images - first;
+            const size_t first = bounds[c], n_c = bounds[c + 1] - first;
             if (c >= (size_t)depth) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[b], 0));  // d_rgb[b] free again
             CK(cudaMemcpyAsync(d_rgb[b], rgb_host + first * raw1, n_c * raw1, cudaMemcpyHostToDevice, ctx->s_h2d));
             CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
@@ -1078,8 +1137,7 @@ int hoh_encode_images_s0_host(hoh_ctx* ctx, const uint8_t* rgb_host, size_t n_im
         if (c + 1 >= (size_t)depth && c + 1 - depth < n_chunks) {  // fetch chunk p = c - (depth - 1)
             const size_t pc = c + 1 - depth;
             const int p = (int)(pc % depth);
-            const size_t pfirst = pc * per;
-            const size_t n_p = pfirst + per <= n_images ? per : n_images - pfirst;
+            const size_t pfirst = bounds[pc], n_p = bounds[pc + 1] - pfirst;
             CK(cudaEventSynchronize(ctx->ev_off[p]));
             const uint64_t total = h_off[p][n_p * spi];
             if (base + total > packed_cap || total > dev_packed_cap) {
@@ -1111,13 +1169,14 @@ int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t p
     TRY(hoh_tile_geometry_for(width, height, &hg));
     TRY(pipe_init(ctx));
     const size_t raw1 = (size_t)width * height * 3;
-    const size_t per = chunk_images_for(n_images, raw1);
-    const size_t n_chunks = (n_images + per - 1) / per;
+    size_t per;  // the largest chunk
+    const std::vector<size_t> bounds = chunk_plan(n_images, raw1, &per);
+    const size_t n_chunks = bounds.size() - 1;
     const size_t spi = hg.streams_per_image;
     const size_t chunk_streams = per * spi;
     size_t max_packed = 0;  // largest packed chunk
     for (size_t c = 0; c < n_chunks; c++) {
-        const size_t s0 = c * per * spi, s1 = (c + 1) * per < n_images ? (c + 1) * per * spi : n_images * spi;
+        const size_t s0 = bounds[c] * spi, s1 = bounds[c + 1] * spi;
         if (off_host[s1] < off_host[s0] || off_host[s1] > packed_bytes) return HOH_E_ARG;
         if (off_host[s1] - off_host[s0] > max_packed) max_packed = off_host[s1] - off_host[s0];
     }
@@ -1141,8 +1200,7 @@ int hoh_decode_images_s0_host(hoh_ctx* ctx, const uint8_t* packed_host, size_t p
     for (size_t c = 0; c < n_chunks; c++) {
         const int b = (int)(c % depth);
         hoh_ctx* ch = ctx->child[b];
-        const size_t first = c * per;
-        const size_t n_c = first + per <= n_images ? per : n_images - first;
+        const size_t first = bounds[c], n_c = bounds[c + 1] - first;
         const size_t s0 = first * spi, ns = n_c * spi;
         const uint64_t lo = off_host[s0], bytes = off_host[s0 + ns] - lo;
         const size_t padded = (bytes + 47) & ~(size_t)15;

@@ -2333,15 +2333,12 @@ __device__ __forceinline__ int cand_at(const Cand& k, int j) {
 }
 // prediction.hpp:138-146: lowest index wins ties, stays 0 when nothing beats 2*c
 __device__ __forceinline__ int pick_best(int v, const Cand& k, uint32_t mask, int c) {
-    int best = 0, best_err = c * 2;
+    // as a minimum over keys error << 4 | index (a forbidden candidate's key is INT_MAX): the smallest error wins and
+    // among equal errors the lowest index, which is what the reference's ascending walk with a strict `<` keeps
+    int key = 0x7fffffff;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const int err = abs(v - k.v[j]);
-        const bool take = err < best_err && ((mask >> j) & 1u);
-        best_err = take ? err : best_err;
-        best = take ? j : best;
-    }
-    return best;
+    for (int j = 0; j < 16; j++) key = min(key, ((mask >> j) & 1u) ? abs(v - k.v[j]) * 16 + j : 0x7fffffff);
+    return (key >> 4) < 2 * c ? (key & 15) : 0;
 }
 
 // pick_best for a walk that keeps the same mask for a whole grid cell: the mask is folded once per cell into 16
@@ -2657,7 +2654,7 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
     const int x0 = cx * tw, y0 = cy * th;
     const uint64_t per = (uint64_t)w * h;
     const uint16_t* data = planes + p * per;
-    const double* ctab = cost + p * (uint64_t)c;
+    const uint32_t ctab0 = (uint32_t)p * (uint32_t)c;  // this plane's cost table inside `cost` (32-bit index arithmetic)
     // The reference's masks are single predictors, pairs, "all" and "all but one" (layer_encode.hpp:160-174), and for
     // those the masked argmin needs no walk over the 16 keys: a singleton or pair is one or two keys, and the minimum
     // over all-but-j is the second smallest key when the smallest is j's, else the smallest (keys are distinct: the
@@ -2722,8 +2719,8 @@ __global__ void __launch_bounds__(64) k_section_costs(const uint16_t* __restrict
                 const uint32_t bt = (uint32_t)(above >> (4 * m)) & 15u, bl = (uint32_t)(before >> (4 * m)) & 15u;
                 const int pred = p_mid((int)s_cand[bt][tid], (int)s_cand[bl][tid]);
                 // (v - pred + half + c) % c: the operand is positive for pixels below c, and the table has c entries
-                const int r = (v - pred + half + c) & (c - 1);
-                sum[m] += ctab[r];
+                const uint32_t r = (uint32_t)(v - pred + half + c) & (uint32_t)(c - 1);
+                sum[m] += __ldg(cost + (ctab0 + r));
                 uint32_t kind, ia, ib;
                 if (STOCK) {
                     mask_kind(kStock[m], kind, ia, ib);  // constants after unrolling

@@ -504,6 +504,38 @@ def test_host_buffer_pipeline_matches_device_path():
     assert np.array_equal(back, rgb)
 
 
+def test_host_buffer_pipeline_ramped_chunks(monkeypatch):
+    """The pipelined host calls cut a large batch into short chunks at both ends and steady ones between them
+    (chunk_plan in hoh_api.cu).  HOH_PIPE_CHUNK_KB lowers the chunk floor so that a small batch takes that path: 64 images
+    of 128x128 become chunks of 4, 8 x 7, 4 images over 4 buffers, and must give the one-shot device path's bytes."""
+    monkeypatch.setenv("HOH_PIPE_CHUNK_KB", "200")
+    g = gpu_lib.gpu()
+    mod = gpu_lib.hohgpu()
+    W = H = 128
+    n = 64
+    rgb = g.host_alloc(n * W * H * 3)
+    for i in range(n):
+        rgb[i * W * H * 3:(i + 1) * W * H * 3] = ol.synth_rgb(W, H, 11 + i)
+    geom = g.tile_geometry(W, H)
+    ns = n * geom.streams_per_image
+    cap = rgb.size * 2 + 4096 * ns
+    packed = g.host_alloc(cap)
+    off = g.host_alloc((ns + 1) * 8, np.uint64)
+    res = np.zeros(ns, mod.RESULT_DT)
+    g._ck(g.lib.hoh_encode_images_s0_host(g.ctx, rgb.ctypes.data, n, W, H, packed.ctypes.data, cap, off.ctypes.data,
+                                          res.ctypes.data), "encode_host")
+    assert (res["status"] == 0).all()
+    ref_packed, ref_off, _ = g.encode_images_s0(np.asarray(rgb), n, W, H)
+    assert np.array_equal(off, ref_off)
+    assert packed[:int(ref_off[-1])].tobytes() == ref_packed.tobytes()
+    back = g.host_alloc(rgb.size)
+    st = np.zeros(ns, np.int32)
+    g._ck(g.lib.hoh_decode_images_s0_host(g.ctx, packed.ctypes.data, int(off[ns]), off.ctypes.data, n, W, H,
+                                          back.ctypes.data, st.ctypes.data), "decode_host")
+    assert (st == 0).all()
+    assert np.array_equal(back, rgb)
+
+
 def test_predictor_search_batched_planes_vs_oracle():
     """hoh_predictor_search_dev over several planes at once (the BASELINE config 3 / 5 shape: every
     channel of every tile is one plane) equals the per-plane oracle."""

@@ -28,6 +28,12 @@ __global__ void probe(uint32_t seed, uint32_t mul, uint32_t* out, long long* cyc
             if (MIX == 5) a[k] = __byte_perm(a[k], a[(k + 1) & 7], 0x3215);                    // PRMT
             if (MIX == 6) a[k] = __funnelshift_r(a[k], a[(k + 1) & 7], 7);                     // SHF
             if (MIX == 7) a[k] = a[k] > seed ? a[(k + 1) & 7] : a[k] + 3u;                     // ISETP + SEL (+IADD)
+            if (MIX == 9) a[k] = (uint32_t)__double2hiint(__ull2double_rz(((uint64_t)a[k] << 20) | a[(k + 1) & 7])) + seed;  // I2F.F64.U64 (+IADD)
+            if (MIX == 10) a[k] = (uint32_t)__double2hiint((double)a[k]) ^ a[(k + 1) & 7];       // I2F.F64.U32 (+LOP3)
+            if (MIX == 11) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(__hiloint2double((int)(a[k] | 0x40000000u), 0))); a[k] = (uint32_t)__double2hiint(r) + seed; }  // MUFU.RCP64H (+IADD)
+            if (MIX == 12) { double r = fma(__hiloint2double((int)(a[k] & 0x400fffffu) | 0x3ff00000, (int)seed), 1.0000001, 0.5); a[k] = (uint32_t)__double2loint(r) ^ (uint32_t)__double2hiint(r); }  // DFMA (+2 LOP3)
+            if (MIX == 13) { const uint64_t w = (uint64_t)a[k] * mul + a[(k + 1) & 7]; a[k] = (uint32_t)w ^ (uint32_t)(w >> 32); }  // IMAD.WIDE (+LOP3)
+            if (MIX == 14) { const uint64_t w = __umul64hi(((uint64_t)a[k] << 32) | seed, ((uint64_t)mul << 32) | a[(k + 1) & 7]); a[k] = (uint32_t)w ^ (uint32_t)(w >> 32); }  // mul.hi.u64 (+LOP3)
             if (MIX == 8) { a[k] = (a[k] ^ seed) & (a[(k + 1) & 7] | 0x55u); a[k] = sm[(a[k] & 0xfe0u) | lane]; a[k] = a[k] * mul + seed; }  // LOP3,LOP3,LDS,IMAD
         }
     }
@@ -40,13 +46,13 @@ __global__ void probe(uint32_t seed, uint32_t mul, uint32_t* out, long long* cyc
 }
 int main() {
     uint32_t* out; long long* cyc;
-    cudaMalloc(&out, 148 * 1024 * 4); cudaMallocManaged(&cyc, 16 * sizeof(long long));
-    const char* names[] = {"LOP3", "IMAD", "LOP3+IMAD", "LOP3+LDS", "VIMNMX+IADD", "PRMT", "SHF", "ISETP+SEL(+IADD)", "LOP3,LOP3,LDS,IMAD"};
+    cudaMalloc(&out, 148 * 1024 * 4); cudaMallocManaged(&cyc, 32 * sizeof(long long));
+    const char* names[] = {"LOP3", "IMAD", "LOP3+IMAD", "LOP3+LDS", "VIMNMX+IADD", "PRMT", "SHF", "ISETP+SEL(+IADD)", "LOP3,LOP3,LDS,IMAD", "I2F.F64.U64+IADD", "I2F.F64.U32+LOP3", "MUFU.RCP64H+IADD", "DFMA+2LOP3", "IMAD.WIDE+LOP3", "mul.hi.u64+LOP3"};
     for (int warps = 4; warps <= 32; warps *= 2) {  // warps per SM (one CTA per SM)
 #define RUN(K) probe<K><<<148, warps * 32>>>(12345u, 3u, out, cyc);
-        RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8)
+        RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) RUN(11) RUN(12) RUN(13) RUN(14)
         cudaDeviceSynchronize();
-        for (int k = 0; k < 9; k++)
+        for (int k = 0; k < 15; k++)
             printf("warps/SM %2d  %-22s %9.2f cycles per loop trip\n", warps, names[k], (double)cyc[k] / ITERS);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
