@@ -513,6 +513,7 @@ def run_config_tiles(g, mod, shard, rank, world, host_threads, hbm_peak, barrier
     enc()
     dec()
     g.sync()
+    g.layer_stats()  # reset: what follows counts the timed calls only
     l0 = g.launch_count()
     barrier()
     cfg_clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))  # the clocks of THIS timed region
@@ -535,6 +536,7 @@ def run_config_tiles(g, mod, shard, rank, world, host_threads, hbm_peak, barrier
     cfg_clk = cfg_clocks.stop()
     barrier()
     launches = g.launch_count() - l0
+    coded, unsettled, planes = g.layer_stats()
     comp = int(d_off.download(np.uint64, n_tiles + 1)[-1]) if n else 0
     ok = True
     if n:
@@ -613,6 +615,10 @@ def run_config_tiles(g, mod, shard, rank, world, host_threads, hbm_peak, barrier
             "value_mbs": 2 * job_raw / (enc_ms + dec_ms) / 1e3, "compressed_ratio": job_comp / max(job_raw, 1),
             "hbm_frac_encode": alg / world / enc_ms / 1e6 / hbm_peak, "hbm_frac_decode": alg / world / dec_ms / 1e6 / hbm_peak,
             "roundtrip_exact": all_ok, "oracle_parity_sample": parity, "gpu_launches": int(launches), "clocks": cfg_clk,
+            "entropy_candidates": {"planes": planes, "coded_per_plane": coded / max(planes, 1),
+                                   "planes_coded_in_full_frac": unsettled / max(planes, 1),
+                                   "what": "layer_encode tries six rANS candidates per plane; their sizes follow from histogram "
+                                           "and table up to one word, so only the kept one is coded unless a comparison is open"},
             "e2e": e2e_out,
             "limit": "a launch of the entropy / un-prediction kernels lasts as long as ONE stream's serial chain however few "
                      "streams a rank holds, so strong scaling flattens once the per-rank batch no longer fills the SMs"

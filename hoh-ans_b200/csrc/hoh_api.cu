@@ -23,7 +23,7 @@ enum Slot {
     S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
     S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
     S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_LZ_KEYS, S_LZ_VALS, S_LZ_FLAG, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_T_MORE_SHAPES, S_T_LAST = S_T_NUKE + 4 * 9 - 1, S_D_TILES, S_D_PLANES, S_D_LZSYM, S_D_IDXSYM, S_D_RESID, S_D_OUT, S_D_BACKREF, S_D_MAPS,
-    S_D_STREAMS, S_D_RES_A, S_D_RES_B, S_D_TOP, S_D_BP, S_D_PSTATUS, S_PA_BEST, S_COUNT
+    S_D_STREAMS, S_D_RES_A, S_D_RES_B, S_D_TOP, S_D_BP, S_D_PSTATUS, S_PA_BEST, S_L_NEED, S_L_ORDER, S_COUNT
 };
 
 struct Buf {
@@ -36,6 +36,9 @@ struct Buf {
 struct hoh_ctx {
     int device = 0;
     int sm_count = 148;
+    // hoh_layer_encode_batch since the last hoh_debug_layer_stats: {candidates coded, planes the size intervals did not
+    // settle, planes} (device counters, summed over the child contexts when read)
+    uint32_t* d_layer_stats = nullptr;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
@@ -256,23 +259,24 @@ size_t smem_even_share(const hoh_ctx* ctx, size_t smem, unsigned grid) {
     return share >= 8u ? smem_for_cap(smem, share) : smem;
 }
 
-// Shared tail of the encode pipeline once the raw histograms are in `freqs`.
-// min_prob_bits: a lower bound the CALLER guarantees for every stream's prob_bits (0 = unknown).
-// padded8: the CALLER guarantees that every stream's symbols start 16-byte aligned and are readable up to the next
-// multiple of 8 symbols (planes at a stride rounded up to 8): the warp-specialised encoder then reads them directly.
-int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, const uint16_t* d_symbols,
-                      uint8_t* d_out, hoh_stream_result* d_results, const uint32_t* freqs,
-                      uint32_t max_range, uint32_t max_prob_bits, uint32_t min_prob_bits, bool padded8 = false) {
-    uint32_t* cum;
-    uint8_t* heads;
-    EncMeta* meta;
-    TRY(scratch_t(ctx, S_CUM, n * kCumRow, &cum));
-    TRY(scratch_t(ctx, S_HEADS, n * HOH_HEAD_CAP, &heads));
-    TRY(scratch_t(ctx, S_ENCMETA, n, &meta));
+// First half: normalised tables, stream heads and the size estimates (EncMeta::est) of n streams.
+int build_tables(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, const uint32_t* freqs, uint32_t** cum_out,
+                 uint8_t** heads_out, EncMeta** meta_out) {
+    TRY(scratch_t(ctx, S_CUM, n * kCumRow, cum_out));
+    TRY(scratch_t(ctx, S_HEADS, n * HOH_HEAD_CAP, heads_out));
+    TRY(scratch_t(ctx, S_ENCMETA, n, meta_out));
     TRY(ensure_smem_opt_in(ctx));
     k_build_tables<<<blocks_for(n, kTableWarps), kTableWarps * 32, 0, ctx->stream>>>(d_streams, (uint32_t)n, freqs,
-                                                                                    cum, heads, meta);
+                                                                                    *cum_out, *heads_out, *meta_out);
     LAUNCHED("k_build_tables");
+    return HOH_OK;
+}
+// Second half: the coder and the finish.  order / n_active (device, optional): code only the streams listed (padded8 only).
+int encode_with_tables(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, const uint16_t* d_symbols, uint8_t* d_out,
+                       hoh_stream_result* d_results, uint32_t* cum, uint8_t* heads, EncMeta* meta, uint32_t max_range,
+                       uint32_t max_prob_bits, uint32_t min_prob_bits, bool padded8, const uint32_t* order = nullptr,
+                       const uint32_t* n_active = nullptr) {
+    if (order && !padded8) return HOH_E_ARG;
     // one launch per (table width, window-size class); every warp takes part in exactly one of them.  The
     // launches are independent and each lasts as long as its longest stream, so they go to side streams and
     // overlap (not while profiling: the per-kernel event times would no longer add up).
@@ -301,7 +305,7 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
         ws32 = smem_even_share(ctx, ws32, blocks_for(n, 32));
         if (padded8) {
             k_rans_encode_ws<uint16_t, 0><<<blocks_for(n, 32), 64, ws16, s16>>>(
-                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+                d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u, order, n_active);
         } else {
             k_rans_encode<uint16_t, false><<<blocks_for(n, 32), 32, smem16, s16>>>(
                 d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
@@ -310,10 +314,10 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
         if (min_prob_bits < 14) {
             if (padded8) {  // prob_bits 12-13, and below 12: two more instantiations
                 k_rans_encode_ws<uint16_t, 2><<<blocks_for(n, 32), 64, ws16, s16>>>(
-                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u, order, n_active);
                 LAUNCHED(names16l[c]);
                 k_rans_encode_ws<uint16_t, 1><<<blocks_for(n, 32), 64, ws16, s16>>>(
-                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
+                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u, order, n_active);
             } else {
                 k_rans_encode<uint16_t, true><<<blocks_for(n, 32), 32, smem16, s16>>>(
                     d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 1u);
@@ -323,7 +327,7 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
         if (max_prob_bits > 15) {  // 32-bit table lanes; prob_bits >= 16 there, so never LOW_BITS
             if (padded8) {
                 k_rans_encode_ws<uint32_t, 0><<<blocks_for(n, 32), 64, ws32, s32>>>(
-                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);
+                    d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u, order, n_active);
             } else {
                 k_rans_encode<uint32_t, false><<<blocks_for(n, 32), 32, smem32, s32>>>(
                     d_streams, (uint32_t)n, d_symbols, cum, d_out, meta, classes[c], rows, 0u);
@@ -333,9 +337,24 @@ int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, c
     }
     if (overlap) TRY(aux_join(ctx, 8));
     k_finish_streams<<<blocks_for(n, 4), 128, 0, ctx->stream>>>(d_streams, (uint32_t)n, d_symbols, heads, meta, d_out,
-                                                                d_results);
+                                                                d_results, order, n_active);
     LAUNCHED("k_finish_streams");
     return HOH_OK;
+}
+
+// Shared tail of the encode pipeline once the raw histograms are in `freqs`.
+// min_prob_bits: a lower bound the CALLER guarantees for every stream's prob_bits (0 = unknown).
+// padded8: the CALLER guarantees that every stream's symbols start 16-byte aligned and are readable up to the next
+// multiple of 8 symbols (planes at a stride rounded up to 8): the warp-specialised encoder then reads them directly.
+int encode_from_freqs(hoh_ctx* ctx, const hoh_enc_stream* d_streams, size_t n, const uint16_t* d_symbols,
+                      uint8_t* d_out, hoh_stream_result* d_results, const uint32_t* freqs,
+                      uint32_t max_range, uint32_t max_prob_bits, uint32_t min_prob_bits, bool padded8 = false) {
+    uint32_t* cum;
+    uint8_t* heads;
+    EncMeta* meta;
+    TRY(build_tables(ctx, d_streams, n, freqs, &cum, &heads, &meta));
+    return encode_with_tables(ctx, d_streams, n, d_symbols, d_out, d_results, cum, heads, meta, max_range, max_prob_bits,
+                              min_prob_bits, padded8);
 }
 
 int decode_common(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n, const uint8_t* d_in, size_t in_bytes,
@@ -538,6 +557,7 @@ void hoh_ctx_destroy(hoh_ctx* ctx) {
         if (b.p) cudaFree(b.p);
     for (auto& kv : ctx->e_tabs) cudaFree(kv.second);
     if (ctx->flush) cudaFree(ctx->flush);
+    if (ctx->d_layer_stats) cudaFree(ctx->d_layer_stats);
     for (auto& pair : ctx->ev)
         for (auto& ev : pair)
             if (ev) cudaEventDestroy(ev);
@@ -599,6 +619,22 @@ const char* hoh_strerror(int status) {
 
 const char* hoh_last_cuda_error(hoh_ctx* ctx) { return ctx ? ctx->err : "no context"; }
 uint64_t hoh_launch_count(hoh_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hoh_debug_layer_stats(hoh_ctx* ctx, uint64_t out[3]) {
+    if (!ctx || !out) return HOH_E_ARG;
+    DeviceGuard guard_(ctx);
+    out[0] = out[1] = out[2] = 0;
+    hoh_ctx* all[5] = {ctx, ctx->child[0], ctx->child[1], ctx->child[2], ctx->child[3]};
+    for (hoh_ctx* c : all) {
+        if (!c || !c->d_layer_stats) continue;
+        uint32_t v[4];
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(v, c->d_layer_stats, sizeof v, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(c->d_layer_stats, 0, sizeof v));
+        for (int k = 0; k < 3; k++) out[k] += v[k];
+    }
+    return HOH_OK;
+}
 
 int hoh_dev_alloc(hoh_ctx* ctx, size_t bytes, void** dptr) {
     DeviceGuard guard_(ctx);
@@ -1519,16 +1555,48 @@ int hoh_layer_encode_batch(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_plan
     }
     k_layer_headers<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(lg, n, idx, syms, n_used, hdr, hdr_len);
     LAUNCHED("k_layer_headers");
-    // The candidates (:106, 334-392).  Few planes: all nine at once, both prob_bits directions speculatively — a
-    // launch lasts as long as its longest stream however many streams there are.  Many planes: the launches are
-    // bound by throughput, so A, C, D first and then only the direction C and D decide (a third less work).
-    if (mode == 0 || 9 * n <= 49152) {
-        TRY(run_round(0, range, mode >= 1 ? 19 : 15));
-    } else {
-        TRY(run_round(2, range, 16));
-        TRY(run_round(3, range, 19));
-    }
     if (mode >= 1 && lg.cells) TRY(run_round(1, 14, 8));  // the predictor-index maps (:308-317)
+    // The candidates (:106, 334-392).  The reference codes six of them per plane and keeps one.  Here the tables of all
+    // nine (both prob_bits directions) are built, which gives every candidate's size up to one word without coding it
+    // (warp_estimate_words); k_layer_plan replays the decisions over those intervals and only the candidates whose bytes
+    // or exact size the outcome needs go through the coder, as one dense list (typically one per plane).
+    // HOH_LAYER_CODE_ALL=1 codes every candidate on the path (the previous behaviour, for tests and comparisons).
+    if (mode == 0) {
+        TRY(run_round(0, range, 15));
+    } else {
+        const size_t count = 9 * n;
+        uint8_t* need;
+        uint32_t* order;
+        TRY(scratch_t(ctx, S_L_NEED, count, &need));
+        TRY(scratch_t(ctx, S_L_ORDER, count + 1, &order));
+        uint32_t* n_active = order + count;
+        if (!ctx->d_layer_stats) {
+            CK(cudaMalloc(&ctx->d_layer_stats, 4 * sizeof(uint32_t)));
+            CK(cudaMemsetAsync(ctx->d_layer_stats, 0, 4 * sizeof(uint32_t), ctx->stream));
+        }
+        k_layer_streams<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, 0, n_used, kept_px, res, streams);
+        LAUNCHED("k_layer_streams");
+        uint32_t* freqs;
+        TRY(scratch_t(ctx, S_FREQS, count * kFreqRow, &freqs));
+        k_layer_histograms<<<(unsigned)(2 * n), 256, 0, ctx->stream>>>(n, 9u, 1u, 1u, 8u, streams, syms, freqs);
+        LAUNCHED("k_layer_histograms");
+        uint32_t* cum;
+        uint8_t* heads;
+        EncMeta* meta;
+        TRY(build_tables(ctx, streams, count, freqs, &cum, &heads, &meta));
+        const bool code_all = getenv("HOH_LAYER_CODE_ALL") != nullptr;
+        k_layer_plan<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(lg, n, streams, meta, res, hdr_len,
+                                                                  (flags & HOH_FIX_STALE) ? 1u : 0u, code_all ? 1u : 0u, need,
+                                                                  ctx->d_layer_stats);
+        LAUNCHED("k_layer_plan");
+        k_layer_order<<<1, 1024, 0, ctx->stream>>>(need, streams, (uint32_t)count, order, n_active);
+        LAUNCHED("k_layer_order");
+        k_layer_est_results<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(count, streams, meta, rr);
+        LAUNCHED("k_layer_est_results");
+        TRY(encode_with_tables(ctx, streams, count, syms, d_out, rr, cum, heads, meta, range, 19, 0, true, order, n_active));
+        k_layer_scatter<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(lg, n, 0, rr, res);
+        LAUNCHED("k_layer_scatter");
+    }
     k_layer_decide<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(lg, n, res, (flags & HOH_FIX_STALE) ? 1u : 0u, hdr, hdr_len,
                                                                 kept, best, with_idx, status);
     LAUNCHED("k_layer_decide");

@@ -43,7 +43,7 @@ struct EncMeta {
     uint32_t table_u16;  // 1 if prob_bits <= 15 (every cumulative count fits a 16-bit lane)
     uint32_t win_lo;     // lowest symbol with a non-zero frequency
     uint32_t win_rows;   // (highest - lowest + 1) + 1: rows of cum[] the encoder needs for this stream
-    uint32_t pad;
+    uint32_t est;        // payload words known without coding: low 24 bits = lower bound, top 8 = upper - lower (255: unknown)
 };
 
 // Per-stream scratch of the decode pipeline.
@@ -443,6 +443,62 @@ __device__ uint32_t warp_build_head(const uint32_t* f, uint32_t range, uint32_t 
 
 constexpr int kTableWarps = 4;
 
+// -------------------------------------------------------------------------------------------------
+// How many 32-bit words the Rans64 coder will emit for a stream, from its histogram and its table alone.
+// -------------------------------------------------------------------------------------------------
+// The state starts at 2^31 (rans64.hpp:65) and ends in [2^31, 2^63); every step multiplies it by M / f (M = 2^prob_bits)
+// up to a small relative error, every renormalisation (rans64.hpp:82-86) divides it by 2^32 up to a truncation.  With
+// W emitted words:   log2(x_end) + 32 W = 31 + S + E,   S = sum over the symbols of (prob_bits - log2 f),
+// hence W = floor((S + E) / 32) exactly.  E is bounded from the same data:
+//   a step turns x = q f + r into q M + r + start = x M / f + d with |d| <= M - f, a relative error below f / x:
+//     x >= 2^31 when the step did not renormalise      -> |e| <= 1.45 f / 2^31
+//     x >= 2^(31 - prob_bits) f when it did (<= W steps) -> |e| <= 1.45 * 2^(prob_bits - 31)
+//   a renormalisation drops the low word of an x >= 2^(63 - prob_bits) f: -1.45 * 2^(prob_bits - 31) <= e <= 0.
+// So E lies in [-(B + 2 W k), B + W k] with B = 1.45 / 2^31 * sum(count f), k = 1.45 * 2^(prob_bits - 31): a fraction of a
+// bit for 15-bit tables, a few bits at 19, and floor((S + E) / 32) is the same number at both ends of the interval
+// for most streams.  layer_encode's candidates (layer_encode.hpp:334-392: the same residuals under six tables) are
+// compared through these intervals, and only a candidate whose bytes or exact size the outcome needs is coded.
+// k_finish_streams checks every coded stream against its interval (HOH_S_BAD_ESTIMATE).
+// Returns EncMeta::est.  Warp-cooperative; `counts` = the raw histogram, `f` = the normalised frequencies.
+__device__ __forceinline__ uint32_t warp_estimate_words(const uint32_t* __restrict__ counts, const uint32_t* f,
+                                                        uint32_t range, uint32_t n, uint32_t bits) {
+    const uint32_t lane = lane_id();
+    double S = 0.0, B = 0.0;
+    uint32_t seen = 0;
+    for (uint32_t i = lane; i < range; i += 32) {
+        const uint32_t c = counts[i];
+        if (c != 0u) {
+            const double fi = (double)f[i];
+            S += (double)c * ((double)bits - log2(fi));
+            B += (double)c * fi;
+            seen += c;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, d);
+        B += __shfl_xor_sync(0xffffffffu, B, d);
+        seen += __shfl_xor_sync(0xffffffffu, seen, d);
+    }
+    if (seen != n) return 0xff000000u;  // symbols outside the alphabet: the coder clamps them, the histogram skipped them
+    B *= 1.45 / 2147483648.0;
+    const double k = 1.45 * exp2((double)bits - 31.0);
+    const double w_cap = floor((S + B + 1.0) / 32.0) + 1.0;
+    const double slack = 1e-4 + 1e-12 * S;  // evaluation error of S (log2: 1 ulp, <= 512 terms)
+    const double e_hi = B + w_cap * k + slack, e_lo = -(B + 2.0 * w_cap * k + slack);
+    const double lo = fmax(0.0, floor((S + e_lo) / 32.0)), hi = floor((S + e_hi) / 32.0);
+    if (hi - lo > 254.0 || hi >= 16777216.0) return 0xff000000u;
+    return (uint32_t)lo | ((uint32_t)(hi - lo) << 24);
+}
+// What k_finish_streams will report as the stream's size if the coder emits `words` words (entropy_encoding.hpp:232-267).
+__device__ __forceinline__ uint32_t stream_size_for(const hoh_enc_stream& st, const EncMeta& m, uint32_t words) {
+    if (m.status != HOH_S_OK) return 0u;
+    if (st.n == 0u) return st.prefix_len + m.head_len;
+    const uint32_t payload = 4u * words + 8u;  // rans64.hpp:96-103: the flush writes the 64-bit state
+    const uint32_t coded = m.head_len + hohfmt::varint_len(payload) + payload;
+    return st.prefix_len + (m.stored_size < coded ? m.stored_size : coded);
+}
+
 __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
     const hoh_enc_stream* __restrict__ streams, uint32_t n_streams, const uint32_t* __restrict__ freqs,
     uint32_t* __restrict__ cumtab, uint8_t* __restrict__ heads, EncMeta* __restrict__ meta) {
@@ -463,7 +519,7 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
     m.table_u16 = st.prob_bits <= 15 ? 1u : 0u;
     m.win_lo = 0;
     m.win_rows = 0;
-    m.pad = 0;
+    m.est = 0xff000000u;
     uint8_t* head = heads + (size_t)s * HOH_HEAD_CAP;
     if (st.n == 0) {  // entropy_encoding.hpp:19-23: two varints and nothing else (D2)
         if (lane == 0) {
@@ -523,6 +579,7 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_build_tables(
     }
     m.head_len = warp_build_head(f, st.range, st.n, st.prob_bits, s_head[w], sc, &m.stored_size, st.reserved & HOH_FIX_LONE);
     __syncwarp();
+    m.est = warp_estimate_words(src, f, st.range, st.n, st.prob_bits);
     const uint32_t words = (m.head_len + 3u) / 4u;
     for (uint32_t k = lane; k < words; k += 32)
         reinterpret_cast<uint32_t*>(head)[k] = reinterpret_cast<const uint32_t*>(s_head[w])[k];
@@ -935,15 +992,21 @@ __global__ void __launch_bounds__(64) k_rans_encode_ws(const hoh_enc_stream* __r
                                                        const uint16_t* __restrict__ symbols,
                                                        const uint32_t* __restrict__ cumtab, uint8_t* __restrict__ out,
                                                        EncMeta* __restrict__ meta, uint32_t rows_lo, uint32_t rows,
-                                                       uint32_t want_u16) {
+                                                       uint32_t want_u16, const uint32_t* __restrict__ order,
+                                                       const uint32_t* __restrict__ n_active) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CumT* tab = reinterpret_cast<CumT*>(smem_raw);
     uint4* hand = reinterpret_cast<uint4*>(smem_raw + (size_t)rows * 32u * sizeof(CumT));  // [2][kWsGroup][32]
 
     const uint32_t lane = lane_id();
     const bool feeder = threadIdx.x >= 32u;
-    const uint32_t s = blockIdx.x * 32u + lane;
-    const bool exists = s < n_streams;
+    // `order` (optional): the streams to code, as a dense list of *n_active indices into `streams` - a caller that
+    // wants a subset coded keeps the warps full this way (hoh_layer_encode_batch codes one candidate in six)
+    const uint32_t slot = blockIdx.x * 32u + lane;
+    const uint32_t n_slots = order ? *n_active : n_streams;
+    if (blockIdx.x * 32u >= n_slots) return;
+    const bool exists = slot < n_slots;
+    const uint32_t s = exists ? (order ? order[slot] : slot) : 0u;
     hoh_enc_stream st;
     EncMeta m;
     if (exists) {
@@ -980,7 +1043,7 @@ __global__ void __launch_bounds__(64) k_rans_encode_ws(const hoh_enc_stream* __r
     }
     // tables: row i of stream j's window -> tab[i*32 + j], filled by all 64 threads
     for (uint32_t j = 0; j < 32; j++) {
-        const uint32_t sj = blockIdx.x * 32u + j;
+        const uint32_t sj = __shfl_sync(0xffffffffu, s, j);
         const bool lj = __shfl_sync(0xffffffffu, (int)live, j) != 0;
         const uint32_t wj = __shfl_sync(0xffffffffu, m.win_rows, j);
         const uint32_t oj = __shfl_sync(0xffffffffu, m.win_lo, j);
@@ -1085,9 +1148,12 @@ __global__ void __launch_bounds__(128) k_finish_streams(const hoh_enc_stream* __
                                                         uint32_t n_streams, const uint16_t* __restrict__ symbols,
                                                         const uint8_t* __restrict__ heads,
                                                         const EncMeta* __restrict__ meta, uint8_t* __restrict__ out,
-                                                        hoh_stream_result* __restrict__ results) {
-    const uint32_t s = blockIdx.x * 4u + (threadIdx.x >> 5), lane = lane_id();
-    if (s >= n_streams) return;
+                                                        hoh_stream_result* __restrict__ results,
+                                                        const uint32_t* __restrict__ order,
+                                                        const uint32_t* __restrict__ n_active) {
+    const uint32_t slot = blockIdx.x * 4u + (threadIdx.x >> 5), lane = lane_id();
+    if (slot >= (order ? *n_active : n_streams)) return;
+    const uint32_t s = order ? order[slot] : slot;  // as in k_rans_encode_ws
     const hoh_enc_stream st = streams[s];
     const EncMeta m = meta[s];
     const uint8_t* head = heads + (size_t)s * HOH_HEAD_CAP;
@@ -1110,6 +1176,10 @@ __global__ void __launch_bounds__(128) k_finish_streams(const hoh_enc_stream* __
             results[s] = res;
         }
         return;
+    }
+    {  // the coded length against what k_build_tables derived from the histogram (warp_estimate_words)
+        const uint32_t w = (m.payload_bytes - 8u) / 4u, lo = m.est & 0xffffffu, span = m.est >> 24;
+        if (span != 255u && (w < lo || w > lo + span)) res.status = HOH_S_BAD_ESTIMATE;
     }
     const uint32_t vlen = hohfmt::varint_len(m.payload_bytes);
     const uint32_t coded = m.head_len + vlen + m.payload_bytes;  // what encode_entropy returns
@@ -3577,6 +3647,177 @@ __global__ void k_layer_scatter(LayerGeom lg, uint64_t n_planes, int round, cons
     const uint32_t k = (uint32_t)(i % per_round);
     const bool up = round == 3 && results[p * kLayerSlots + 2].size < results[p * kLayerSlots + 3].size;
     results[p * kLayerSlots + layer_round_slot(round, k, up)] = rr[i];
+}
+
+// -------------------------------------------------------------------------------------------------
+// Which candidates of a plane have to be CODED.  The reference codes all six on its path (A; C, D; three more in the
+// direction C and D decide) and keeps one; a candidate's size, though, follows from its histogram and table up to one
+// word (warp_estimate_words), so the decision sequence of k_layer_decide is replayed here over size INTERVALS.
+// While every comparison comes out the same at both ends of the intervals involved, only two things are needed
+// from the coder: the bytes of the candidate that ends up kept, and the exact size that ends up emitted when its
+// interval is not a single number.  A plane with a comparison the intervals cannot settle has its whole path coded,
+// as before.  need[9 * plane + k] = 1: round-0 stream k of the plane goes to the coder.
+// -------------------------------------------------------------------------------------------------
+struct SizeIv {
+    uint32_t lo, hi;
+};
+__device__ __forceinline__ int iv_less(const SizeIv& a, const SizeIv& b) {  // a < b: 1 yes, 0 no, -1 depends
+    return a.hi < b.lo ? 1 : (a.lo >= b.hi ? 0 : -1);
+}
+__global__ void k_layer_plan(LayerGeom lg, uint64_t n_planes, const hoh_enc_stream* __restrict__ streams,
+                             const EncMeta* __restrict__ meta, const hoh_stream_result* __restrict__ results,
+                             const uint32_t* __restrict__ hdr_len, uint32_t fix, uint32_t code_all,
+                             uint8_t* __restrict__ need, uint32_t* __restrict__ counters) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_planes) return;
+    const uint32_t per = lg.mode ? 9u : 1u;
+    SizeIv iv[kLayerSlots];
+    bool exact[kLayerSlots];
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t slot = layer_round_slot(0, k, false);
+        const hoh_enc_stream st = streams[p * per + k];
+        const EncMeta m = meta[p * per + k];
+        const uint32_t lo = m.est & 0xffffffu, span = m.est >> 24;
+        if (m.status != HOH_S_OK || st.n == 0u) {
+            iv[slot].lo = iv[slot].hi = stream_size_for(st, m, 0u);
+        } else if (span == 255u) {
+            iv[slot].lo = 0u;
+            iv[slot].hi = 0xffffffffu;
+        } else {
+            iv[slot].lo = stream_size_for(st, m, lo);
+            iv[slot].hi = stream_size_for(st, m, lo + span);
+        }
+        exact[slot] = iv[slot].lo == iv[slot].hi;
+    }
+    uint32_t want = 0;  // bit per slot
+    bool settled = !code_all;
+    const uint64_t bits = (uint64_t)lg.depth * lg.per;
+    const uint32_t bound = (uint32_t)((bits + bits % 8 + 1024) / 8);  // layer_encode.hpp:22
+    int up = 0;
+    if (settled && lg.mode) {
+        up = iv_less(iv[2], iv[3]);  // layer_encode.hpp:357
+        if (up < 0) settled = false;
+    }
+    const uint32_t third = up > 0 ? 4u : 7u;
+    if (settled && !fix) {  // k_layer_decide, fix == 0
+        SizeIv best{bound, bound};
+        uint32_t best_slot = 0xffffffffu, kept = 0xffffffffu;
+        int c = iv_less(iv[0], best);
+        if (c < 0) settled = false;
+        if (c > 0) {
+            best = iv[0];
+            best_slot = kept = 0u;
+        }
+        if (settled && lg.mode) {
+            const uint32_t first = up > 0 ? 2u : 3u;
+            c = iv_less(iv[first], best);
+            if (c < 0) settled = false;
+            if (c > 0) {
+                best = iv[first];
+                best_slot = first;
+            }
+            for (uint32_t k = 0; settled && k < 3u; k++) {
+                c = iv_less(iv[third + k], best);
+                if (c < 0) settled = false;
+                if (c > 0) {
+                    best = iv[third + k];
+                    best_slot = kept = third + k;
+                }
+            }
+        }
+        if (settled) {
+            if (kept != 0xffffffffu) want |= 1u << kept;
+            if (best_slot != 0xffffffffu && !exact[best_slot]) want |= 1u << best_slot;
+        }
+    } else if (settled) {  // k_layer_decide, fix != 0: the smallest searched candidate against A
+        uint32_t kept = 0u;
+        if (lg.mode) {
+            uint32_t sk = 2u;
+            int c = iv_less(iv[3], iv[2]);
+            if (c < 0) settled = false;
+            if (c > 0) sk = 3u;
+            for (uint32_t k = third; settled && k < third + 3u; k++) {
+                c = iv_less(iv[k], iv[sk]);
+                if (c < 0) settled = false;
+                if (c > 0) sk = k;
+            }
+            if (settled) {
+                const uint32_t extra = lg.cells ? hdr_len[p] + results[p * kLayerSlots + 1].size : 5u;
+                const SizeIv searched{iv[sk].lo + extra, iv[sk].hi + extra}, plain{iv[0].lo + 5u, iv[0].hi + 5u};
+                c = iv_less(searched, plain);
+                if (c < 0) settled = false;
+                if (c > 0) kept = sk;
+            }
+        }
+        if (settled) want |= 1u << kept;
+    }
+    if (!settled) {  // the reference's whole path (both directions when even that comparison is open)
+        want = 1u;
+        if (lg.mode) want |= (1u << 2) | (1u << 3) | (code_all || up < 0 ? 0x3f0u : (7u << third));
+    }
+    uint32_t n_want = 0;
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t on = (want >> layer_round_slot(0, k, false)) & 1u;
+        need[p * per + k] = (uint8_t)on;
+        n_want += on;
+    }
+    if (counters) {
+        atomicAdd(&counters[0], n_want);
+        if (!settled) atomicAdd(&counters[1], 1u);
+        atomicAdd(&counters[2], 1u);
+    }
+}
+
+// need[] -> the dense list of stream indices the coder walks, and their number.  The streams with 16-bit table lanes
+// (prob_bits <= 15) come first, then those with 32-bit lanes, each group ascending: a warp of the coder serves one
+// table width per launch, and a warp with both would run twice with half of its lanes idle.  One CTA.
+__global__ void __launch_bounds__(1024) k_layer_order(const uint8_t* __restrict__ need,
+                                                      const hoh_enc_stream* __restrict__ streams, uint32_t count,
+                                                      uint32_t* __restrict__ order, uint32_t* __restrict__ n_active) {
+    __shared__ uint32_t s_a[1024], s_b[1024];
+    const uint32_t per = (count + 1023u) / 1024u;
+    const uint32_t lo = min(count, threadIdx.x * per), hi = min(count, lo + per);
+    uint32_t mine_a = 0, mine_b = 0;
+    for (uint32_t i = lo; i < hi; i++)
+        if (need[i]) {
+            if (streams[i].prob_bits <= 15u) mine_a++;
+            else mine_b++;
+        }
+    s_a[threadIdx.x] = mine_a;
+    s_b[threadIdx.x] = mine_b;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024u; d <<= 1) {
+        const uint32_t va = threadIdx.x >= d ? s_a[threadIdx.x - d] : 0u, vb = threadIdx.x >= d ? s_b[threadIdx.x - d] : 0u;
+        __syncthreads();
+        s_a[threadIdx.x] += va;
+        s_b[threadIdx.x] += vb;
+        __syncthreads();
+    }
+    uint32_t at_a = s_a[threadIdx.x] - mine_a, at_b = s_a[1023] + s_b[threadIdx.x] - mine_b;
+    for (uint32_t i = lo; i < hi; i++)
+        if (need[i]) {
+            if (streams[i].prob_bits <= 15u) order[at_a++] = i;
+            else order[at_b++] = i;
+        }
+    if (threadIdx.x == 1023u) *n_active = s_a[1023] + s_b[1023];
+}
+
+// The round's result records for candidates that are NOT coded: status and the lower end of the size interval (the
+// plan made sure that no decision depends on where in the interval the size lies); k_finish_streams then overwrites
+// the records of the coded ones.
+__global__ void k_layer_est_results(uint64_t count, const hoh_enc_stream* __restrict__ streams,
+                                    const EncMeta* __restrict__ meta, hoh_stream_result* __restrict__ rr) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const hoh_enc_stream st = streams[i];
+    const EncMeta m = meta[i];
+    hoh_stream_result r;
+    r.status = m.status;
+    r.start = st.out_off;
+    r.size = stream_size_for(st, m, m.est & 0xffffffu);
+    r.payload_bytes = 0;
+    r.stored = 0;
+    rr[i] = r;
 }
 
 // =================================================================================================

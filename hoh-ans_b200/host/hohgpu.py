@@ -77,6 +77,7 @@ SIGNATURES = {
     "hoh_ctx_destroy": (None, [_vp]),
     "hoh_sync": (_int, [_vp]),
     "hoh_release_scratch": (_int, [_vp]),
+    "hoh_debug_layer_stats": (_int, [_vp, C.POINTER(C.c_uint64)]),
     "hoh_strerror": (C.c_char_p, [_int]),
     "hoh_last_cuda_error": (C.c_char_p, [_vp]),
     "hoh_launch_count": (C.c_uint64, [_vp]),
@@ -226,6 +227,12 @@ class HohGpu:
 
     def release_scratch(self):
         self._ck(self.lib.hoh_release_scratch(self.ctx), "hoh_release_scratch")
+
+    def layer_stats(self):
+        """(candidates coded, planes coded in full, planes) of the mode >= 1 encoder since the last call."""
+        out = (C.c_uint64 * 3)()
+        self._ck(self.lib.hoh_debug_layer_stats(self.ctx, out), "hoh_debug_layer_stats")
+        return int(out[0]), int(out[1]), int(out[2])
 
     def launch_count(self):
         return int(self.lib.hoh_launch_count(self.ctx))

@@ -50,6 +50,9 @@ extern "C" {
 #define HOH_S_BAD_STATE 6      /* decode: the rANS state after the last symbol is not 2^31, the value the
                                 * encoder starts from (rans64.hpp:65): the table or the payload is damaged.
                                 * The symbols are still delivered (the reference would not notice).      */
+#define HOH_S_BAD_ESTIMATE 7   /* encode: the payload length computed from the histogram alone (used to pick a
+                                * channel's candidate without coding the others) does not contain the coded
+                                * length: an internal error, never expected                               */
 
 /* decode flags: 0 reproduces entropy_decoding.hpp byte for byte including its defects; the FIX
  * bits turn individual defects off. */
@@ -88,6 +91,11 @@ typedef struct hoh_ctx hoh_ctx;
 int hoh_ctx_create(int device, void* cuda_stream, hoh_ctx** out);
 void hoh_ctx_destroy(hoh_ctx* ctx);
 int hoh_sync(hoh_ctx* ctx);
+/* Development aid: what hoh_layer_encode_batch / hoh_encode_images (cruncher mode >= 1) did since the last call of this
+ * function, summed over the context and its child contexts: out[0] = candidates that went through the rANS coder,
+ * out[1] = planes whose candidate sizes the histogram-derived intervals could not settle (their whole path was coded, as
+ * the reference does for every plane), out[2] = planes.  Synchronises the context. */
+int hoh_debug_layer_stats(hoh_ctx* ctx, uint64_t out[3]);
 /* Frees the scratch device memory the context (and its internal child contexts) caches between calls.  The
  * chunked entry points do this themselves when the image shape or mode changes. */
 int hoh_release_scratch(hoh_ctx* ctx);

@@ -126,3 +126,28 @@ def test_host_forms_round_trip_and_match_device_forms(mode):
         assert np.array_equal(rec["start"], off[:-1]) and np.array_equal(rec["size"], rec2["size"])
         back, st = g.decode_images_host(packed, off, n, w, h)
         assert (st == 0).all() and np.array_equal(back, imgs)
+
+
+@pytest.mark.parametrize("w,h,mode,flags", [(256, 192, 2, 0), (256, 192, 2, 24), (128, 128, 4, 0), (128, 128, 4, 24),
+                                            (96, 40, 1, 0)])
+def test_candidates_picked_from_size_intervals(monkeypatch, w, h, mode, flags):
+    """layer_encode's candidates (layer_encode.hpp:334-392) are compared through size intervals derived from their
+    histograms and tables, and only the ones the outcome needs are coded (k_layer_plan).  The result must be the bytes
+    of coding every candidate on the path, which HOH_LAYER_CODE_ALL=1 still does, with far fewer candidates coded."""
+    g = gpu_lib.gpu()
+    rng = np.random.default_rng(17)
+    n = 6
+    flat = np.concatenate([ol.photo_with_repeats(rng, w, h, 70 + i).ravel() for i in range(n - 1)] +
+                          [ol.synth_rgb(w, h, 9)])
+    g.layer_stats()
+    tiles_a, rec_a = g.encode_images(flat, n, w, h, mode, flags)
+    coded, unsettled, planes = g.layer_stats()
+    monkeypatch.setenv("HOH_LAYER_CODE_ALL", "1")
+    tiles_b, rec_b = g.encode_images(flat, n, w, h, mode, flags)
+    coded_all, unsettled_all, planes_all = g.layer_stats()
+    assert (rec_a["status"] == 0).all() and (rec_b["status"] == 0).all()
+    assert tiles_a == tiles_b
+    assert planes == planes_all > 0
+    assert coded_all == 9 * planes_all and unsettled_all == planes_all
+    assert coded <= 6 * unsettled + 2 * (planes - unsettled)
+    assert unsettled * 2 <= planes  # the intervals settle most planes
