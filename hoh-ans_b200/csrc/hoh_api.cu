@@ -253,10 +253,10 @@ size_t smem_for_cap(size_t smem, unsigned per_sm) {
 
 // ... for a launch of `grid` one-warp-chain CTAs on this device: the even share per SM when the launch is a large single
 // wave (a small launch is left alone: it may be one of several pipeline chunks in flight that share the SMs).
-size_t smem_even_share(const hoh_ctx* ctx, size_t smem, unsigned grid) {
+size_t smem_even_share(const hoh_ctx* ctx, size_t smem, unsigned grid, unsigned min_share = 8u) {
     const unsigned share = (grid + (unsigned)ctx->sm_count - 1u) / (unsigned)ctx->sm_count;
     if (const char* e = getenv("HOH_ENC_CAP")) return atoi(e) > 0 ? smem_for_cap(smem, (unsigned)atoi(e)) : smem;
-    return share >= 8u ? smem_for_cap(smem, share) : smem;
+    return share >= min_share ? smem_for_cap(smem, share) : smem;
 }
 
 // First half: normalised tables, stream heads and the size estimates (EncMeta::est) of n streams.
@@ -378,11 +378,16 @@ int decode_common(hoh_ctx* ctx, const hoh_dec_stream* d_streams, size_t n, const
         const size_t fixed = (size_t)rows * 32 * sizeof(uint32_t) + 32 * kRingWords * sizeof(uint32_t) +
                              32 * kDecStride * sizeof(uint16_t);
         cudaStream_t sc = overlap ? ctx->aux[c] : ctx->stream;
+        // (the even share of CTAs per SM, as for the fused decoder and the encoder: an SM that the block scheduler
+        // loads with twice its share makes the whole launch last twice as long)
+        const unsigned dec_share = getenv("HOH_DEC_CAP") ? (unsigned)atoi(getenv("HOH_DEC_CAP")) : 4u;
+        const size_t lut_bytes = (size_t)kLutSize * 32 * (rows <= 256 ? 1 : 2);
+        const size_t smem = dec_share ? smem_even_share(ctx, fixed + lut_bytes, blocks_for(n, 32), dec_share) : fixed + lut_bytes;
         if (rows <= 256) {
-            k_rans_decode<uint8_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 1, sc>>>(
+            k_rans_decode<uint8_t><<<blocks_for(n, 32), 32, smem, sc>>>(
                 d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, d_results, classes[c], rows);
         } else {
-            k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, fixed + kLutSize * 32 * 2, sc>>>(
+            k_rans_decode<uint16_t><<<blocks_for(n, 32), 32, smem, sc>>>(
                 d_streams, (uint32_t)n, d_in, in_bytes, cum, meta, d_symbols, d_results, classes[c], rows);
         }
         static const char* const names[4] = {"k_rans_decode[rows<=64]", "k_rans_decode[rows<=128]",

@@ -1,2 +1,5 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/t11.log 2>&1; tail -5 gpurun_out/t11.log
-python bench.py --no-cpu-baseline > gpurun_out/b11.json 2> gpurun_out/b11.err; tail -c 300 gpurun_out/b11.err
+for cap in 0 4; do
+echo "HOH_DEC_CAP=$cap"
+HOH_DEC_CAP=$cap python tools/jitter_probe.py 8192 256 256 4 12
+HOH_DEC_CAP=$cap python tools/jitter_probe.py 64 3840 2160 2 8
+done

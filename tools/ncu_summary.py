@@ -49,7 +49,12 @@ COLS = [("ms", "gpu__time_duration.sum", 1e-6), ("DRAM rd GB", "dram__bytes_read
         ("short_sb", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", 1),
         ("long_sb", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", 1),
         ("branch", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", 1),
-        ("smem conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", 1)]
+        ("smem conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", 1),
+        ("alu %", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", 1),
+        ("fma %", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", 1),
+        ("xu %", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", 1),
+        ("fp64 %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", 1),
+        ("lsu wavefronts %", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", 1)]
 
 
 def to_bytes(val, unit):
