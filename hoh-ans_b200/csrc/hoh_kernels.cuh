@@ -2982,6 +2982,9 @@ __global__ void __launch_bounds__(256) k_tile_residuals_s0_generic(const uint8_t
 // left neighbour), so global traffic is 32-bit loads and 8-byte stores and the row/column bookkeeping
 // is incremental (no per-pixel division).  The two 9-bit planes (R-G, B-G) travel as two 16-bit lanes
 // of one register through the packed median.
+// A thread owns a column of four pixels over a band of rows and walks DOWN it: the row above is what it converted
+// one iteration earlier (registers), so every RGB word is loaded and split into planes once instead of twice, and the
+// next row's words are requested before the current row is worked on.
 __global__ void __launch_bounds__(256) k_tile_residuals_s0(const uint8_t* __restrict__ rgb, TileGeom g,
                                                            uint16_t* __restrict__ resid,
                                                            uint32_t* __restrict__ freqs) {
@@ -2998,64 +3001,77 @@ __global__ void __launch_bounds__(256) k_tile_residuals_s0(const uint8_t* __rest
     uint16_t* out_rg = resid + (t * 3u + 1u) * g.plane_stride;
     uint16_t* out_bg = resid + (t * 3u + 2u) * g.plane_stride;
     const uint32_t quads = tw / 4u;  // tw % 4 == 0 on this path
-    const uint32_t dy = 256u / quads, dq = 256u % quads;
-    uint32_t y = threadIdx.x / quads, q = threadIdx.x % quads;
+    const uint32_t qpt = min(quads, 256u);  // quad columns walked at the same time
+    const uint32_t n_bands = 256u / qpt, band_rows = (th + n_bands - 1u) / n_bands;
+    const uint32_t band = threadIdx.x / qpt;
     const uint32_t row_words = g.width * 3u / 4u;
-    for (; y < th; y += dy, q += dq) {
-        if (q >= quads) {
-            q -= quads;
-            y++;
-            if (y >= th) break;
-        }
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(img + ((uint64_t)(y0 + y) * g.width + x0 + 4u * q) * 3u);
-        const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
-        // five pixels of this row (left neighbour + the quad) and of the row above, as g and (rg | bg << 16)
-        uint32_t cg[5], cr[5], tg[5], tr[5];
-        planes2_of(w0 & 0xffffffu, cg[1], cr[1]);
-        planes2_of((w0 >> 24) | ((w1 & 0xffffu) << 8), cg[2], cr[2]);
-        planes2_of((w1 >> 16) | ((w2 & 0xffu) << 16), cg[3], cr[3]);
-        planes2_of(w2 >> 8, cg[4], cr[4]);
-        if (q) {
-            planes2_of(row[-1] >> 8, cg[0], cr[0]);
-        } else {  // column 0: L = c/2
-            cg[0] = 128u;
-            cr[0] = kHalfRB;
-        }
-        if (y) {
-            const uint32_t* up = row - row_words;
-            const uint32_t u0 = up[0], u1 = up[1], u2 = up[2];
-            planes2_of(u0 & 0xffffffu, tg[1], tr[1]);
-            planes2_of((u0 >> 24) | ((u1 & 0xffffu) << 8), tg[2], tr[2]);
-            planes2_of((u1 >> 16) | ((u2 & 0xffu) << 16), tg[3], tr[3]);
-            planes2_of(u2 >> 8, tg[4], tr[4]);
-            if (q) {
-                planes2_of(up[-1] >> 8, tg[0], tr[0]);
-            } else {  // column 0: TL = c/2
+    if (band < n_bands) {
+        const uint32_t ya = band * band_rows, yb = min(th, ya + band_rows);
+        for (uint32_t q = threadIdx.x % qpt; q < quads && ya < yb; q += qpt) {
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(img + ((uint64_t)(y0 + ya) * g.width + x0 + 4u * q) * 3u);
+            uint32_t tg[5], tr[5];  // the row above: left neighbour + the quad, as g and (rg | bg << 16)
+            if (ya) {
+                const uint32_t* up = row - row_words;
+                const uint32_t u0 = up[0], u1 = up[1], u2 = up[2];
+                planes2_of(u0 & 0xffffffu, tg[1], tr[1]);
+                planes2_of((u0 >> 24) | ((u1 & 0xffffu) << 8), tg[2], tr[2]);
+                planes2_of((u1 >> 16) | ((u2 & 0xffu) << 16), tg[3], tr[3]);
+                planes2_of(u2 >> 8, tg[4], tr[4]);
+                if (q) planes2_of(up[-1] >> 8, tg[0], tr[0]);
+            } else {
+#pragma unroll
+                for (int i = 1; i < 5; i++) {  // row 0: T = TL = c/2
+                    tg[i] = 128u;
+                    tr[i] = kHalfRB;
+                }
+            }
+            if (!q || !ya) {  // column 0 / row 0: TL = c/2
                 tg[0] = 128u;
                 tr[0] = kHalfRB;
             }
-        } else {
+            uint32_t n0 = row[0], n1 = row[1], n2 = row[2], nl = q ? row[-1] : 0u;
+            uint32_t at = ya * tw + 4u * q;
+            for (uint32_t y = ya; y < yb; y++, at += tw) {
+                const uint32_t w0 = n0, w1 = n1, w2 = n2, wl = nl;
+                if (y + 1u < yb) {  // the next row's words, in flight while this row is worked on
+                    row += row_words;
+                    n0 = row[0];
+                    n1 = row[1];
+                    n2 = row[2];
+                    if (q) nl = row[-1];
+                }
+                uint32_t cg[5], cr[5];
+                planes2_of(w0 & 0xffffffu, cg[1], cr[1]);
+                planes2_of((w0 >> 24) | ((w1 & 0xffffu) << 8), cg[2], cr[2]);
+                planes2_of((w1 >> 16) | ((w2 & 0xffu) << 16), cg[3], cr[3]);
+                planes2_of(w2 >> 8, cg[4], cr[4]);
+                if (q) {
+                    planes2_of(wl >> 8, cg[0], cr[0]);
+                } else {  // column 0: L = c/2
+                    cg[0] = 128u;
+                    cr[0] = kHalfRB;
+                }
+                uint32_t rg_[4], rr_[4];
 #pragma unroll
-            for (int i = 0; i < 5; i++) {  // row 0: T = TL = c/2
-                tg[i] = 128u;
-                tr[i] = kHalfRB;
+                for (int i = 0; i < 4; i++) {  // prediction.hpp:35-41: (v - median + c/2 + c) % c
+                    rg_[i] = (cg[i + 1] - p_med_grad2(tg[i + 1], cg[i], tg[i]) + 128u + 256u) & 255u;
+                    rr_[i] = __vadd2(__vsub2(cr[i + 1], p_med_grad2(tr[i + 1], cr[i], tr[i])), kHalfRB) & kMaskRB;
+                    atomicAdd(&s_h[0][rg_[i]], 1u);
+                    atomicAdd(&s_h[1][rr_[i] & 0xffffu], 1u);
+                    atomicAdd(&s_h[2][rr_[i] >> 16], 1u);
+                }
+                *reinterpret_cast<uint2*>(out_g + at) = make_uint2(rg_[0] | (rg_[1] << 16), rg_[2] | (rg_[3] << 16));
+                *reinterpret_cast<uint2*>(out_rg + at) =
+                    make_uint2(__byte_perm(rr_[0], rr_[1], 0x5410), __byte_perm(rr_[2], rr_[3], 0x5410));
+                *reinterpret_cast<uint2*>(out_bg + at) =
+                    make_uint2(__byte_perm(rr_[0], rr_[1], 0x7632), __byte_perm(rr_[2], rr_[3], 0x7632));
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    tg[i] = cg[i];
+                    tr[i] = cr[i];
+                }
             }
         }
-        uint32_t rg_[4], rr_[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {  // prediction.hpp:35-41: (v - median + c/2 + c) % c
-            rg_[i] = (cg[i + 1] - p_med_grad2(tg[i + 1], cg[i], tg[i]) + 128u + 256u) & 255u;
-            rr_[i] = __vadd2(__vsub2(cr[i + 1], p_med_grad2(tr[i + 1], cr[i], tr[i])), kHalfRB) & kMaskRB;
-            atomicAdd(&s_h[0][rg_[i]], 1u);
-            atomicAdd(&s_h[1][rr_[i] & 0xffffu], 1u);
-            atomicAdd(&s_h[2][rr_[i] >> 16], 1u);
-        }
-        const uint32_t at = y * tw + 4u * q;
-        *reinterpret_cast<uint2*>(out_g + at) = make_uint2(rg_[0] | (rg_[1] << 16), rg_[2] | (rg_[3] << 16));
-        *reinterpret_cast<uint2*>(out_rg + at) =
-            make_uint2(__byte_perm(rr_[0], rr_[1], 0x5410), __byte_perm(rr_[2], rr_[3], 0x5410));
-        *reinterpret_cast<uint2*>(out_bg + at) =
-            make_uint2(__byte_perm(rr_[0], rr_[1], 0x7632), __byte_perm(rr_[2], rr_[3], 0x7632));
     }
     __syncthreads();
     for (int ch = 0; ch < 3; ch++) {

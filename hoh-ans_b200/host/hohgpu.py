@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libhohgpu.so")
+# (HOH_GPU_LIB: another build of the same library, for A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("HOH_GPU_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libhohgpu.so")
 
 HOH_OK = 0
 HOH_E_CUDA, HOH_E_ARG, HOH_E_UNSUPPORTED, HOH_E_CAPACITY, HOH_E_STREAM = 1, 2, 3, 4, 5
