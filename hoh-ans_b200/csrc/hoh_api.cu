@@ -29,6 +29,7 @@ enum Slot {
 struct Buf {
     void* p = nullptr;
     size_t cap = 0;
+    uint64_t epoch = 0;  // the top-level call (root context's `epoch`) that last asked for this buffer
 };
 
 }  // namespace
@@ -57,6 +58,12 @@ struct hoh_ctx {
     uint64_t* h_off[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_off_cap[4] = {0, 0, 0, 0};
     hoh_ctx* child[4] = {nullptr, nullptr, nullptr, nullptr};  // one per chunk in flight (own stream + scratch)
+    // Scratch of EARLIER top-level calls stays cached (the next call of the same kind reuses it) but is given back when an
+    // allocation fails: the root context counts top-level calls (`epoch`, bumped by the outermost entry point: `depth`),
+    // every buffer remembers the call that last asked for it, and scratch() frees the others before it gives up.
+    hoh_ctx* parent = nullptr;
+    uint64_t epoch = 1;
+    int depth = 0;
     // side streams for launches that are independent of each other and each bound by the serial chain of a
     // stream (the table-size classes of one entropy batch): they overlap instead of queueing
     bool aux_ready = false;
@@ -76,11 +83,17 @@ namespace {
 
 // Every entry point runs on the context's device whatever the caller's current device is, and puts the
 // caller's device back on return (a process may hold contexts on several GPUs, or share the thread with torch).
+inline hoh_ctx* root_of(hoh_ctx* c) {
+    while (c->parent) c = c->parent;
+    return c;
+}
 struct DeviceGuard {
     int prev = -1;
     bool switched = false;
+    hoh_ctx* root = nullptr;
     explicit DeviceGuard(const hoh_ctx* ctx);
     ~DeviceGuard() {
+        if (root) root->depth--;
         if (switched) cudaSetDevice(prev);
     }
 };
@@ -90,6 +103,8 @@ const uint16_t kStockMasks[14] = {  // layer_encode.hpp:159-175
 
 DeviceGuard::DeviceGuard(const hoh_ctx* ctx) {
     if (!ctx) return;
+    root = root_of(const_cast<hoh_ctx*>(ctx));
+    if (root->depth++ == 0) root->epoch++;  // a new top-level call: what the previous ones left cached is now stale
     if (cudaGetDevice(&prev) != cudaSuccess) return;
     if (prev != ctx->device && cudaSetDevice(ctx->device) == cudaSuccess) switched = true;
 }
@@ -138,8 +153,21 @@ int prof_mark(hoh_ctx* ctx, const char* name) {
     return HOH_OK;
 }
 
+// Frees every cached scratch buffer of the context tree that the CURRENT top-level call has not asked for.
+void free_stale_scratch(hoh_ctx* c, uint64_t epoch) {
+    for (auto& b : c->scratch)
+        if (b.p && b.epoch != epoch) {
+            cudaFree(b.p);
+            b.p = nullptr;
+            b.cap = 0;
+        }
+    for (hoh_ctx* ch : c->child)
+        if (ch) free_stale_scratch(ch, epoch);
+}
+
 int scratch(hoh_ctx* ctx, Slot slot, size_t bytes, void** out) {
     Buf& b = ctx->scratch[slot];
+    hoh_ctx* root = root_of(ctx);
     if (bytes == 0) bytes = 16;
     if (b.cap < bytes) {
         if (b.p) {
@@ -149,9 +177,28 @@ int scratch(hoh_ctx* ctx, Slot slot, size_t bytes, void** out) {
             b.cap = 0;
         }
         size_t want = bytes + bytes / 8 + 256;
-        CK(cudaMalloc(&b.p, want));
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e == cudaErrorMemoryAllocation) {
+            // e.g. a decode of a large batch right after its encode: the encoder's scratch is still cached and
+            // scratch_budget() counted it as reusable.  Nothing of an earlier call is in use once the device is idle.
+            cudaGetLastError();
+            CK(cudaDeviceSynchronize());
+            free_stale_scratch(root, root->epoch);
+            b.p = nullptr;
+            e = cudaMalloc(&b.p, want);
+            if (e == cudaErrorMemoryAllocation) {  // without the 12 % of slack
+                cudaGetLastError();
+                want = bytes;
+                e = cudaMalloc(&b.p, want);
+            }
+        }
+        if (e != cudaSuccess) {
+            b.p = nullptr;
+            return fail_cuda(ctx, e, "cudaMalloc(scratch)");
+        }
         b.cap = want;
     }
+    b.epoch = root->epoch;
     *out = b.p;
     return HOH_OK;
 }
@@ -1047,6 +1094,7 @@ int pipe_init(hoh_ctx* ctx) {
         CK(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_off[k], cudaEventDisableTiming));
         if (!ctx->child[k] && hoh_ctx_create(ctx->device, nullptr, &ctx->child[k]) != HOH_OK) return HOH_E_CUDA;
+        ctx->child[k]->parent = ctx;
     }
     CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     ctx->pipe_ready = true;
@@ -1868,8 +1916,10 @@ int hoh_encode_images(hoh_ctx* ctx, const uint8_t* d_rgb, size_t n_images, uint3
             hoh_ctx* c8 = ctx;
             hoh_ctx* c9 = ctx;
             if (!ctx->profiling) {
-                for (int k = 0; k < 2; k++)
+                for (int k = 0; k < 2; k++) {
                     if (!ctx->child[k] && hoh_ctx_create(ctx->device, nullptr, &ctx->child[k]) != HOH_OK) return HOH_E_CUDA;
+                    ctx->child[k]->parent = ctx;
+                }
                 c8 = ctx->child[0];
                 c9 = ctx->child[1];
                 TRY(aux_init(ctx));
