@@ -223,3 +223,37 @@ def test_row_distance_65536_stays_decodable_with_the_encoder_fix():
     assert rec["status"][0] == 0
     back, st = g.decode_images(tiles, 1, w, h)
     assert st[0] == 0 and np.array_equal(back, flat)
+
+
+def test_decode_after_encode_when_device_memory_is_short():
+    """The codec's scratch stays cached between calls.  A decode right after an encode must not fail because the
+    encoder's cached scratch holds the memory it needs: stale scratch (last used by an earlier top-level call) is freed
+    when an allocation fails (hoh_api.cu scratch()).  A ballast leaves less free memory than the decode's scratch."""
+    torch = pytest.importorskip("torch")
+    mod = gpu_lib.hohgpu()
+    g = mod.HohGpu(0)  # its own context: nothing cached from other tests
+    try:
+        w = h = 256
+        n = 768
+        rgb = np.concatenate([ol.synth_rgb(w, h, 3000 + i % 7) for i in range(n)])
+        geo = g.tile_geometry(w, h)
+        n_tiles = n * geo.tiles_per_image
+        raw = rgb.size
+        cap = raw + raw // 2 + 8192 * n_tiles + 64
+        bufs = [g.alloc(raw), g.alloc(cap), g.alloc((n_tiles + 1) * 8), g.alloc(n_tiles * mod.TILE_DT.itemsize),
+                g.alloc(raw), g.alloc(n_tiles * 4)]
+        d_rgb, d_packed, d_off, d_tiles, d_back, d_st = bufs
+        d_rgb.upload(rgb)
+        g._ck(g.lib.hoh_encode_images(g.ctx, d_rgb.ptr, n, w, h, 2, FIX_STALE, d_packed.ptr, cap, d_off.ptr, d_tiles.ptr),
+              "hoh_encode_images")
+        g.sync()
+        free_b, _total = torch.cuda.mem_get_info(0)
+        ballast = g.alloc(max(free_b - (384 << 20), 1 << 20))  # what is left is far less than the decoder plans for
+        bufs.append(ballast)
+        g._ck(g.lib.hoh_decode_images(g.ctx, d_packed.ptr, cap, d_off.ptr, n, w, h, d_back.ptr, d_st.ptr), "hoh_decode_images")
+        assert (d_st.download(np.int32, n_tiles) == 0).all()
+        assert np.array_equal(d_back.download(np.uint8, raw), rgb)
+    finally:
+        for b in bufs:
+            b.free()
+        g.close()
