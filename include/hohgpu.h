@@ -97,7 +97,9 @@ int hoh_sync(hoh_ctx* ctx);
  * the reference does for every plane), out[2] = planes.  Synchronises the context. */
 int hoh_debug_layer_stats(hoh_ctx* ctx, uint64_t out[3]);
 /* Frees the scratch device memory the context (and its internal child contexts) caches between calls.  The
- * chunked entry points do this themselves when the image shape or mode changes. */
+ * chunked entry points do this themselves when the image shape or mode changes, and an allocation that fails
+ * first frees whatever scratch the CURRENT top-level call has not asked for (e.g. the encoder's, during a decode)
+ * and tries again, so a caller never has to call this for correctness — only to hand the memory back early. */
 int hoh_release_scratch(hoh_ctx* ctx);
 const char* hoh_strerror(int status);
 const char* hoh_last_cuda_error(hoh_ctx* ctx);
