@@ -23,7 +23,7 @@ enum Slot {
     S_FREQS = 0, S_CUM, S_HEADS, S_ENCMETA, S_DECMETA, S_RESID, S_STREAMS, S_DSTREAMS, S_DRESULTS,
     S_IO_A, S_IO_B, S_IO_C, S_IO_D, S_IO_E, S_RESULTS, S_TOP, S_BP, S_HIST, S_COST, S_SUMS, S_MASKS,
     S_WIDE_TOP, S_WIDE_BP, S_MISC, S_L_MAPS, S_L_IDX, S_L_HDR, S_L_U32, S_L_STATUS, S_L_RR, S_L_RES, S_LZ_PX, S_LZ_STATE, S_LZ_SIDE, S_LZ_COUNTS, S_LZ_SLABS, S_LZ_RES, S_LZ_BONUS, S_LZ_KEYS, S_LZ_VALS, S_LZ_FLAG, S_T_NUKE, S_T_LZ, S_T_U32, S_T_P8, S_T_P9, S_T_O8, S_T_O9, S_T_R8, S_T_R9, S_T_MORE_SHAPES, S_T_LAST = S_T_NUKE + 4 * 9 - 1, S_D_TILES, S_D_PLANES, S_D_LZSYM, S_D_IDXSYM, S_D_RESID, S_D_OUT, S_D_BACKREF, S_D_MAPS,
-    S_D_STREAMS, S_D_RES_A, S_D_RES_B, S_D_TOP, S_D_BP, S_D_PSTATUS, S_PA_BEST, S_L_NEED, S_L_ORDER, S_COUNT
+    S_D_STREAMS, S_D_RES_A, S_D_RES_B, S_D_TOP, S_D_BP, S_D_PSTATUS, S_L_NEED, S_L_ORDER, S_COUNT
 };
 
 struct Buf {
@@ -515,19 +515,14 @@ namespace {
 // channelpredict_all (prediction.hpp:153) for many planes, every pixel in parallel (encode side)
 int predict_all_parallel(hoh_ctx* ctx, const uint16_t* d_planes, size_t n_planes, int w, int h, int depth, int x_tiles,
                          int y_tiles, const uint16_t* d_tile_maps, uint16_t* d_resid, uint64_t resid_stride) {
-    uint8_t* best;
-    const uint64_t total = (uint64_t)n_planes * w * h;
-    TRY(scratch_t(ctx, S_PA_BEST, total, &best));
-    const uint64_t bpp = ((uint64_t)w * h + 255) / 256;  // CTAs per plane
-    if (n_planes * bpp > 0x7fffffffull) return HOH_E_UNSUPPORTED;
-    const FastDiv d_bpp = fastdiv_make((uint32_t)bpp), d_w = fastdiv_make((uint32_t)w);
-    const FastDiv d_tw = fastdiv_make((uint32_t)((w + x_tiles - 1) / x_tiles)), d_th = fastdiv_make((uint32_t)((h + y_tiles - 1) / y_tiles));
-    k_predict_all_best<<<(unsigned)(n_planes * bpp), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, x_tiles, y_tiles,
-                                                                          d_tile_maps, best, d_bpp, d_w, d_tw, d_th);
-    LAUNCHED("k_predict_all_best");
-    k_predict_all_resid<<<(unsigned)(n_planes * bpp), 256, 0, ctx->stream>>>(d_planes, n_planes, w, h, depth, best, d_resid,
-                                                                           resid_stride, d_bpp, d_w);
-    LAUNCHED("k_predict_all_resid");
+    // one kernel, 32 x 16 pixel tiles
+    const uint64_t tpr = ((uint64_t)w + kPaTx - 1) / kPaTx, tpp = tpr * (((uint64_t)h + kPaTy - 1) / kPaTy);
+    if (n_planes * tpp > 0x7fffffffull) return HOH_E_UNSUPPORTED;
+    k_predict_all_fused<<<(unsigned)(n_planes * tpp), 256, 0, ctx->stream>>>(
+        d_planes, n_planes, w, h, depth, x_tiles, y_tiles, d_tile_maps, d_resid, resid_stride, fastdiv_make((uint32_t)tpp),
+        fastdiv_make((uint32_t)tpr), fastdiv_make((uint32_t)((w + x_tiles - 1) / x_tiles)),
+        fastdiv_make((uint32_t)((h + y_tiles - 1) / y_tiles)));
+    LAUNCHED("k_predict_all_fused");
     return HOH_OK;
 }
 

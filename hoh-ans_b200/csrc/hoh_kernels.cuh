@@ -2529,7 +2529,7 @@ __global__ void __launch_bounds__(64) k_raster_walk(const uint16_t* __restrict__
 //                                     bp[w-1], which still holds row y-1's last pixel             [4 at (0, 0)]
 //   best predictor of pixel q       = 0 on the last row, else the argmin over the mask of the cell that holds
 //                                     the pixel BELOW q (prediction.hpp:213-225)
-// Pass 1 computes the best predictor of every pixel, pass 2 the residuals.
+// Phase 1 computes the best predictor of every pixel, phase 2 the residuals (k_predict_all_fused).
 // -------------------------------------------------------------------------------------------------
 // Division of a 31-bit number by a run-time constant without the software divide (~20 instructions; the per-pixel
 // kernels below spent half of theirs splitting a linear index into plane / row / column / grid cell): the host
@@ -2560,51 +2560,79 @@ __device__ __forceinline__ void pa_candidates(const uint16_t* __restrict__ src, 
     candidates(L, T, TL, TR, false, k);
 }
 
-__global__ void __launch_bounds__(256) k_predict_all_best(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
-                                                          int h, int depth, int x_tiles, int y_tiles,
-                                                          const uint16_t* __restrict__ tile_maps,
-                                                          uint8_t* __restrict__ best, FastDiv d_bpp, FastDiv d_w,
-                                                          FastDiv d_tw, FastDiv d_th) {
-    // blocks_per_plane consecutive CTAs share a plane: 32-bit index arithmetic only (d_bpp = CTAs per plane, d_w = w,
-    // d_tw / d_th = the grid cell's size)
+// Both phases in ONE kernel for a 32 x 16 pixel tile of a plane: the best predictors of the tile (and of the row above
+// it and the column to its left, which are recomputed: +9 % of phase 1) go through shared memory, and the 16 candidates
+// of a pixel, its neighbour loads and its position arithmetic are made once.  (Round 2 started with two kernels and a u8
+// plane of best predictors in global memory: 275 + 216 executed instructions per pixel, ncu on a config-3 slice;
+// fused: config 3 encode 427 -> 411 ms, config 5 280 -> 262 ms.)  A thread owns the pixels (tx, ty) and (tx, ty + 8) of
+// the tile and keeps their candidates in registers between the phases.
+constexpr int kPaTx = 32, kPaTy = 16;
+__global__ void __launch_bounds__(256) k_predict_all_fused(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
+                                                           int h, int depth, int x_tiles, int y_tiles,
+                                                           const uint16_t* __restrict__ tile_maps,
+                                                           uint16_t* __restrict__ out, uint64_t out_stride, FastDiv d_tpp,
+                                                           FastDiv d_tpr, FastDiv d_tw, FastDiv d_th) {
+    // best predictor of pixel (x0 - 1 + i, y0 - 1 + j) at s_best[j][i]; row 0 / column 0 are the halo
+    __shared__ uint8_t s_best[kPaTy + 1][kPaTx + 4];
+    const uint32_t pl = fd_div(blockIdx.x, d_tpp);  // d_tpp = tiles per plane, d_tpr = tiles per tile row
+    if (pl >= n_planes) return;
+    const uint32_t t_in = blockIdx.x - pl * d_tpp.d;
+    const uint32_t t_y = fd_div(t_in, d_tpr), t_x = t_in - t_y * d_tpr.d;
+    const int x0 = (int)t_x * kPaTx, y0 = (int)t_y * kPaTy;
+    const int c = 1 << depth, half = c >> 1;
     const uint32_t per = (uint32_t)w * (uint32_t)h;
-    const uint32_t pl = fd_div(blockIdx.x, d_bpp);
-    const uint64_t p = pl;
-    const uint32_t at = (blockIdx.x - pl * d_bpp.d) * blockDim.x + threadIdx.x;
-    if (p >= n_planes || at >= per) return;
-    const uint64_t i = p * per + at;
-    const int y = (int)fd_div(at, d_w), x = (int)(at - (uint32_t)y * (uint32_t)w);
-    if (y + 1 >= h) {
-        best[i] = 0;
-        return;
+    const uint16_t* src = planes + (uint64_t)pl * per;
+    const uint16_t* maps = tile_maps + (uint64_t)pl * (uint64_t)x_tiles * y_tiles;
+    // prediction.hpp:213-225: 0 on the last row, else the argmin under the mask of the cell holding the pixel below
+    auto best_of = [&](int x, int y, const Cand& k) -> int {
+        if (y + 1 >= h) return 0;
+        const uint32_t mask = maps[(size_t)fd_div((uint32_t)(y + 1), d_th) * x_tiles + fd_div((uint32_t)x, d_tw)];
+        return pick_best(src[(size_t)y * w + x], k, mask, c);
+    };
+    const int tx = (int)(threadIdx.x & 31u), ty = (int)(threadIdx.x >> 5);
+    const int x = x0 + tx, ya = y0 + ty, yb = y0 + ty + 8;
+    const bool in_a = x < w && ya < h, in_b = x < w && yb < h;
+    Cand ka, kb;
+    if (in_a) {
+        pa_candidates(src, w, x, ya, half, ka);
+        s_best[ty + 1][tx + 1] = (uint8_t)best_of(x, ya, ka);
     }
-    const int c = 1 << depth, half = c >> 1;
-    const uint16_t* src = planes + p * per;
-    Cand k;
-    pa_candidates(src, w, x, y, half, k);
-    const uint32_t mask = tile_maps[p * (uint64_t)x_tiles * y_tiles + (size_t)fd_div((uint32_t)(y + 1), d_th) * x_tiles + fd_div((uint32_t)x, d_tw)];
-    best[i] = (uint8_t)pick_best(src[at], k, mask, c);
-}
-
-__global__ void __launch_bounds__(256) k_predict_all_resid(const uint16_t* __restrict__ planes, uint64_t n_planes, int w,
-                                                           int h, int depth, const uint8_t* __restrict__ best,
-                                                           uint16_t* __restrict__ out, uint64_t out_stride, FastDiv d_bpp,
-                                                           FastDiv d_w) {
-    const uint32_t per = (uint32_t)w * (uint32_t)h;
-    const uint32_t pl = fd_div(blockIdx.x, d_bpp);
-    const uint64_t p = pl;
-    const uint32_t at = (blockIdx.x - pl * d_bpp.d) * blockDim.x + threadIdx.x;
-    if (p >= n_planes || at >= per) return;
-    const int y = (int)fd_div(at, d_w), x = (int)(at - (uint32_t)y * (uint32_t)w);
-    const int c = 1 << depth, half = c >> 1;
-    const uint16_t* src = planes + p * per;
-    const uint8_t* b = best + p * per;
-    Cand k;
-    pa_candidates(src, w, x, y, half, k);
-    const int bp_top = y > 0 ? b[at - w] : 4;
-    const int bp_left = x > 0 ? b[at - 1] : (y > 0 ? b[at - 1] : 4);  // x == 0: (w-1, y-1) is the element before (0, y)
-    const int pred = p_mid(cand_at(k, bp_top), cand_at(k, bp_left));
-    out[p * out_stride + at] = (uint16_t)mod_pow2((int)src[at] - pred + half + c, c);  // prediction.hpp:208
+    if (in_b) {
+        pa_candidates(src, w, x, yb, half, kb);
+        s_best[ty + 9][tx + 1] = (uint8_t)best_of(x, yb, kb);
+    }
+    // halo: threads 0..31 the row above the tile, threads 32..47 the column to its left.  For column 0 "the pixel to the
+    // left" is the previous row's last pixel (bp[w - 1] still holds it when the walk starts a row: SURVEY H4); positions
+    // that do not exist (row -1) read 4, the initial value of the reference's arrays (prediction.hpp:170-174)
+    if (threadIdx.x < 32u + (uint32_t)kPaTy) {
+        int hx, hy, sx, sy;
+        if (threadIdx.x < 32u) {
+            hx = x0 + tx, hy = y0 - 1, sx = tx + 1, sy = 0;
+        } else {
+            const int r = (int)threadIdx.x - 32;
+            sx = 0, sy = r + 1;
+            if (x0 > 0) hx = x0 - 1, hy = y0 + r;
+            else hx = w - 1, hy = y0 + r - 1;
+        }
+        int b = 4;
+        if (hx < w && hy >= 0 && hy < h) {
+            Cand kh;
+            pa_candidates(src, w, hx, hy, half, kh);
+            b = best_of(hx, hy, kh);
+        }
+        s_best[sy][sx] = (uint8_t)b;
+    }
+    __syncthreads();
+    if (in_a) {
+        const int pred = p_mid(cand_at(ka, s_best[ty][tx + 1]), cand_at(ka, s_best[ty + 1][tx]));
+        const size_t at = (size_t)ya * w + x;
+        out[(uint64_t)pl * out_stride + at] = (uint16_t)mod_pow2((int)src[at] - pred + half + c, c);  // prediction.hpp:208
+    }
+    if (in_b) {
+        const int pred = p_mid(cand_at(kb, s_best[ty + 8][tx + 1]), cand_at(kb, s_best[ty + 9][tx]));
+        const size_t at = (size_t)yb * w + x;
+        out[(uint64_t)pl * out_stride + at] = (uint16_t)mod_pow2((int)src[at] - pred + half + c, c);
+    }
 }
 
 // =================================================================================================
