@@ -122,7 +122,8 @@ def _smooth_planes(rng, n, w, h, depth):
 
 @pytest.mark.parametrize("w,h,depth,mode,n", [(96, 64, 8, 1, 5), (100, 90, 9, 2, 4), (128, 128, 8, 3, 3),
                                               (64, 100, 9, 4, 3), (33, 27, 8, 2, 6), (81, 41, 8, 0, 4),
-                                              (41, 43, 9, 1, 3)])
+                                              (41, 43, 9, 1, 3), (2, 90, 8, 2, 3), (1, 85, 9, 1, 2), (90, 2, 8, 2, 2),
+                                              (45, 1, 8, 3, 2)])
 def test_layer_encode_batch_vs_oracle(w, h, depth, mode, n):
     """hoh_layer_encode_batch: the whole of layer_encode.hpp:11-412 on the device for n planes at once,
     byte-identical to the oracle's layer_encode plane by plane (odd plane sizes exercise the padded
