@@ -76,3 +76,33 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(mod.HohError) as e:
         mod.HohGpu(0)
     assert e.value.status == mod.HOH_E_CUDA
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C-ABI: include/hohgpu.h compiles as C99 (-pedantic, no C++), and a C program that takes the
+    address of entry points links against libhohgpu.so and runs (hoh_ctx_create fails cleanly without a device)."""
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc absent")
+    import subprocess
+    lib = _lib_path()
+    src = tmp_path / "c_user.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "hohgpu.h"\n'
+        "typedef void (*fn)(void);\n"
+        "static fn volatile table[] = {(fn)hoh_encode_images_host, (fn)hoh_decode_images_host, (fn)hoh_encode_images_s0};\n"
+        "int main(void) {\n"
+        "    hoh_ctx* ctx = NULL;\n"
+        "    int st = hoh_ctx_create(0, NULL, &ctx);\n"
+        '    printf("%d %s\\n", st, hoh_strerror(st));\n'
+        "    if (st == HOH_OK) hoh_ctx_destroy(ctx);\n"
+        "    return table[0] == 0 || table[1] == 0 || table[2] == 0;\n"
+        "}\n")
+    exe = tmp_path / "c_user"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                           "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", os.path.dirname(lib), "-lhohgpu", "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    st = int(out.stdout.split()[0])
+    assert st in (0, 1), out.stdout  # HOH_OK on a GPU box, HOH_E_CUDA here: never a crash, never a CPU fallback
